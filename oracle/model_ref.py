@@ -1,0 +1,224 @@
+"""ORACLE (test infrastructure, never shipped): fp32 CPU restatement, in plain torch
+tensor ops over a flat state_dict, of the reference's model graph on the hot path:
+
+  feats -> GlobalCMVN -> Conv2dSubsampling4 -> 18x (LSL) Conformer block -> after_norm
+        -> CTC head (Linear + log_softmax)
+  n-best -> (LSL) bi-transformer decoder, teacher forced -> log_softmax
+
+Every function cites the reference file:line it follows (paths relative to
+/root/reference/asr/wenet).  Pinned against the LIVE reference run in the authoring
+container (oracle/make_golden.py -> tests/golden/*.npz; tests/test_oracle_vs_reference.py
+re-checks whenever /root/reference is present).  The reference has no tests of its own
+for this path, so "parity unpinned" by reference-held golden vectors;
+pinned instead by outputs of the reference itself.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline / reference arm may
+import this module.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+SD = Dict[str, torch.Tensor]
+
+
+def _ln(x, sd: SD, p: str, eps: float):
+    return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], eps)
+
+
+def _lin(x, sd: SD, p: str):
+    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+
+
+def make_pad_mask(lengths: torch.Tensor, max_len: int) -> torch.Tensor:
+    """utils/mask.py:200-226 — True at padded positions."""
+    return torch.arange(max_len)[None, :] >= lengths[:, None].long()
+
+
+def sinusoid_pe(n: int, d: int) -> torch.Tensor:
+    """transformer/embedding.py:39-56."""
+    pe = torch.zeros(n, d)
+    pos = torch.arange(0, n, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d, 2, dtype=torch.float32) * -(math.log(10000.0) / d))
+    pe[:, 0::2] = torch.sin(pos * div)
+    pe[:, 1::2] = torch.cos(pos * div)
+    return pe
+
+
+def subsample4(feats: torch.Tensor, lens: torch.Tensor, sd: SD) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """GlobalCMVN (transformer/cmvn.py:36-47) + Conv2dSubsampling4.forward
+    (transformer/subsampling.py:201-226) + RelPositionalEncoding.forward
+    (transformer/embedding.py:132-146)."""
+    B, T, _ = feats.shape
+    masks = ~make_pad_mask(lens, T).unsqueeze(1)                       # encoder.py:130
+    x = (feats - sd["encoder.global_cmvn.mean"]) * sd["encoder.global_cmvn.istd"]
+    x = x.unsqueeze(1)
+    x = F.relu(F.conv2d(x, sd["encoder.embed.conv.0.weight"], sd["encoder.embed.conv.0.bias"], stride=2))
+    x = F.relu(F.conv2d(x, sd["encoder.embed.conv.2.weight"], sd["encoder.embed.conv.2.bias"], stride=2))
+    b, c, t, f = x.shape
+    x = _lin(x.transpose(1, 2).contiguous().view(b, t, c * f), sd, "encoder.embed.out.0")
+    d = x.shape[-1]
+    x = x * math.sqrt(d)
+    pos_emb = sinusoid_pe(t, d).unsqueeze(0)
+    masks = masks[:, :, 2::2][:, :, 2::2]
+    return x, pos_emb, masks
+
+
+def rel_attention(x, mask, pos_emb, sd: SD, p: str, H: int):
+    """RelPositionMultiHeadedAttention.forward (transformer/attention.py:317-399); note the
+    disabled rel_shift (:391-394): p is indexed by ABSOLUTE key position."""
+    B, T, d = x.shape
+    dk = d // H
+    q = _lin(x, sd, p + ".linear_q").view(B, T, H, dk)
+    k = _lin(x, sd, p + ".linear_k").view(B, T, H, dk).transpose(1, 2)
+    v = _lin(x, sd, p + ".linear_v").view(B, T, H, dk).transpose(1, 2)
+    pp = F.linear(pos_emb, sd[p + ".linear_pos.weight"]).view(1, -1, H, dk).transpose(1, 2)
+    qu = (q + sd[p + ".pos_bias_u"]).transpose(1, 2)
+    qv = (q + sd[p + ".pos_bias_v"]).transpose(1, 2)
+    ac = torch.matmul(qu, k.transpose(-2, -1))
+    bd = torch.matmul(qv, pp.transpose(-2, -1))
+    scores = (ac + bd) / math.sqrt(dk)
+    return _attend(v, scores, mask, sd, p)
+
+
+def _attend(v, scores, mask, sd: SD, p: str):
+    """MultiHeadedAttention.forward_attention (transformer/attention.py:81-127)."""
+    B = v.shape[0]
+    m = mask.unsqueeze(1).eq(0)
+    scores = scores.masked_fill(m, -float("inf"))
+    attn = torch.softmax(scores, dim=-1).masked_fill(m, 0.0)
+    x = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, -1, v.shape[1] * v.shape[3])
+    return _lin(x, sd, p + ".linear_out")
+
+
+def mha(q_in, kv_in, mask, sd: SD, p: str, H: int):
+    """MultiHeadedAttention.forward (transformer/attention.py:129-175)."""
+    B, Tq, d = q_in.shape
+    dk = d // H
+    q = _lin(q_in, sd, p + ".linear_q").view(B, Tq, H, dk).transpose(1, 2)
+    k = _lin(kv_in, sd, p + ".linear_k").view(B, -1, H, dk).transpose(1, 2)
+    v = _lin(kv_in, sd, p + ".linear_v").view(B, -1, H, dk).transpose(1, 2)
+    scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk)
+    return _attend(v, scores, mask, sd, p)
+
+
+def conv_module(x, mask_pad, sd: SD, p: str, K: int, causal: bool, layer_norm: bool):
+    """ConvolutionModule.forward (transformer/convolution.py:89-144)."""
+    x = x.transpose(1, 2)
+    x = x.masked_fill(~mask_pad, 0.0)
+    if causal:
+        x = F.pad(x, (K - 1, 0), "constant", 0.0)
+    x = F.conv1d(x, sd[p + ".pointwise_conv1.weight"], sd[p + ".pointwise_conv1.bias"])
+    x = F.glu(x, dim=1)
+    x = F.conv1d(x, sd[p + ".depthwise_conv.weight"], sd[p + ".depthwise_conv.bias"],
+                 padding=0 if causal else (K - 1) // 2, groups=x.shape[1])
+    if layer_norm:
+        x = F.silu(_ln(x.transpose(1, 2), sd, p + ".norm", 1e-5)).transpose(1, 2)
+    else:
+        x = F.silu(F.batch_norm(x, sd[p + ".norm.running_mean"], sd[p + ".norm.running_var"],
+                                sd[p + ".norm.weight"], sd[p + ".norm.bias"], False, 0.0, 1e-5))
+    x = F.conv1d(x, sd[p + ".pointwise_conv2.weight"], sd[p + ".pointwise_conv2.bias"])
+    x = x.masked_fill(~mask_pad, 0.0)
+    return x.transpose(1, 2)
+
+
+def ffn(x, sd: SD, p: str, act):
+    """PositionwiseFeedForward.forward (transformer/positionwise_feed_forward.py:47-55)."""
+    return _lin(act(_lin(x, sd, p + ".w_1")), sd, p + ".w_2")
+
+
+def lsl_mix(x, sd: SD, p: str, cat_embs: torch.Tensor):
+    """y = sum_i cat_embs[i] * language_layers[i](x)  (encoder_layer.py:376-390)."""
+    y = None
+    for i in range(cat_embs.shape[0]):
+        t = cat_embs[i] * _lin(x, sd, f"{p}.language_layers.{i}")
+        y = t if y is None else y + t
+    return y
+
+
+def encoder_block(x, mask, pos_emb, mask_pad, sd: SD, p: str, cfg, cat_embs, lsl: bool):
+    """ConformerEncoderLayer.forward (transformer/encoder_layer.py:164-244) and
+    LanguageSpecificConformerEncoderLayer.forward (:305-402)."""
+    ec = cfg["encoder_conf"]
+    H, K = ec["attention_heads"], ec["cnn_module_kernel"]
+    x = x + 0.5 * ffn(_ln(x, sd, p + ".norm_ff_macaron", 1e-5), sd, p + ".feed_forward_macaron", F.silu)
+    x = x + rel_attention(_ln(x, sd, p + ".norm_mha", 1e-5), mask, pos_emb, sd, p + ".self_attn", H)
+    x = x + conv_module(_ln(x, sd, p + ".norm_conv", 1e-5), mask_pad, sd, p + ".conv_module", K,
+                        ec.get("causal", False), ec.get("cnn_module_norm", "batch_norm") == "layer_norm")
+    n = _ln(x, sd, p + ".norm_ff", 1e-5)
+    if lsl:
+        y = lsl_mix(n, sd, p, cat_embs)
+        x = x + 0.5 * ffn(y, sd, p + ".feed_forward", F.silu)
+        x = _ln(x, sd, p + ".norm_final", 1e-5)
+        return x + y
+    x = x + 0.5 * ffn(n, sd, p + ".feed_forward", F.silu)
+    return _ln(x, sd, p + ".norm_final", 1e-5)
+
+
+def encoder_forward(feats, lens, sd: SD, cfg, cat_embs: Optional[torch.Tensor]):
+    """BaseEncoder.forward (transformer/encoder.py:117-149), full-context decode
+    (decoding_chunk_size=-1 => key-padding mask only, utils/mask.py:161-187).
+    Returns (encoder_out (B,T',d), encoder_lens (B,), masks (B,1,T'))."""
+    x, pos_emb, masks = subsample4(feats, lens, sd)
+    L = cfg["encoder_conf"]["num_blocks"]
+    has_lsl = bool(cfg["dataset_conf"].get("pass_cat_emb", False))
+    for i in range(L):
+        lsl = has_lsl and (i == 0 or i == L - 1)
+        x = encoder_block(x, masks, pos_emb, masks, sd, f"encoder.encoders.{i}", cfg, cat_embs, lsl)
+    x = _ln(x, sd, "encoder.after_norm", 1e-5)
+    return x, masks.squeeze(1).sum(1), masks
+
+
+def ctc_logprobs(enc_out, sd: SD, blank_penalty: float = 0.0, blank_id: int = 0):
+    """ASRModel.ctc_logprobs (transformer/asr_model.py:318-329) / CTC.log_softmax (ctc.py:106-114)."""
+    logits = _lin(enc_out, sd, "ctc.ctc_lo")
+    if blank_penalty > 0.0:
+        logits[:, :, blank_id] -= blank_penalty
+    return logits.log_softmax(dim=2)
+
+
+def decoder_forward(memory, ys_in, ys_lens, sd: SD, cfg, side: str, cat_embs):
+    """(LanguageSpecific)TransformerDecoder.forward (transformer/decoder.py:116-169, 308-383) with
+    DecoderLayer.forward (decoder_layer.py:62-133) / LanguageSpecificDecoderLayer.forward (:251-340).
+    memory (N,T,d) with an all-ones memory mask (asr_model.py:895-900). Returns logits (N,L,V)."""
+    dc = cfg["decoder_conf"]
+    H = dc["attention_heads"]
+    nb = dc["num_blocks"] if side == "left_decoder" else dc["r_num_blocks"]
+    has_lsl = bool(cfg["dataset_conf"].get("pass_cat_emb", False))
+    p = f"decoder.{side}"
+    N, L = ys_in.shape
+    d = memory.shape[-1]
+    tgt_mask = (~make_pad_mask(ys_lens, L)).unsqueeze(1) & torch.tril(torch.ones(L, L, dtype=torch.bool)).unsqueeze(0)
+    mem_mask = torch.ones(N, 1, memory.shape[1], dtype=torch.bool)
+    x = F.embedding(ys_in, sd[p + ".embed.0.weight"]) * math.sqrt(d) + sinusoid_pe(L, d).unsqueeze(0)
+    for i in range(nb):
+        q = f"{p}.decoders.{i}"
+        lsl = has_lsl and (i == 0 or i == nb - 1)
+        eps = 1e-12 if lsl else 1e-5        # decoder_layer.py:241-243 vs :53-55
+        t = _ln(x, sd, q + ".norm1", eps)
+        x = x + mha(t, t, tgt_mask, sd, q + ".self_attn", H)
+        x = x + mha(_ln(x, sd, q + ".norm2", eps), memory, mem_mask, sd, q + ".src_attn", H)
+        t = _ln(x, sd, q + ".norm3", eps)
+        if lsl:
+            t = lsl_mix(t, sd, q, cat_embs)
+        x = x + ffn(t, sd, q + ".feed_forward", F.relu)
+    x = _ln(x, sd, p + ".after_norm", 1e-5)
+    return _lin(x, sd, p + ".output_layer")
+
+
+def reverse_hyps(hyps_in: torch.Tensor, hyps_lens: torch.Tensor, eos: int) -> torch.Tensor:
+    """Right-to-left decoder input built in ASRModel.forward_attention_decoder
+    (transformer/asr_model.py:903-949): [sos, w_U..w_1, eos...]."""
+    r_lens = hyps_lens - 1
+    r = hyps_in[:, 1:]
+    max_len = int(r_lens.max())
+    idx_range = torch.arange(0, max_len)
+    seq_mask = r_lens.unsqueeze(1) > idx_range
+    index = ((r_lens.unsqueeze(1) - 1) - idx_range) * seq_mask
+    r = torch.gather(r, 1, index)
+    r = torch.where(seq_mask, r, eos)
+    return torch.cat([hyps_in[:, 0:1], r], dim=1)

@@ -1,0 +1,193 @@
+"""ORACLE (test infrastructure, never shipped): pure-Python restatement of the reference's
+CTC searches and attention rescoring (asr/wenet/transformer/search.py), operating on
+numpy/torch fp32 log-prob arrays.  Float semantics follow the reference: prefix scores are
+Python floats (C doubles) built from fp32 log-probs (`.item()`), rescoring scores are
+accumulated in fp32 (0-d torch tensors).
+
+Pinned against the LIVE reference in the authoring container (oracle/make_golden.py,
+tests/test_oracle_vs_reference.py); the reference itself holds no tests.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+NEG_INF = -float("inf")
+
+
+class DecodeResult:
+    """transformer/search.py:29-58."""
+
+    def __init__(self, tokens, score=0.0, confidence=0.0, tokens_confidence=None, times=None,
+                 nbest=None, nbest_scores=None, nbest_times=None):
+        self.tokens = tokens
+        self.score = score
+        self.confidence = confidence
+        self.tokens_confidence = tokens_confidence
+        self.times = times
+        self.nbest = nbest
+        self.nbest_scores = nbest_scores
+        self.nbest_times = nbest_times
+
+
+def log_add(args) -> float:
+    """utils/common.py:355-363."""
+    if all(a == NEG_INF for a in args):
+        return NEG_INF
+    a_max = max(args)
+    return a_max + math.log(sum(math.exp(a - a_max) for a in args))
+
+
+class PrefixScore:
+    """transformer/search.py:61-103 (context-graph fields omitted: ReverbASR always passes
+    context_graph=None, cli/reverb.py:227)."""
+    __slots__ = ("s", "ns", "v_s", "v_ns", "cur_token_prob", "times_s", "times_ns")
+
+    def __init__(self, s=NEG_INF, ns=NEG_INF, v_s=NEG_INF, v_ns=NEG_INF):
+        self.s, self.ns, self.v_s, self.v_ns = s, ns, v_s, v_ns
+        self.cur_token_prob = NEG_INF
+        self.times_s: List[int] = []
+        self.times_ns: List[int] = []
+
+    def score(self):
+        return log_add([self.s, self.ns])
+
+    def viterbi_score(self):
+        return self.v_s if self.v_s > self.v_ns else self.v_ns
+
+    def times(self):
+        return self.times_s if self.v_s > self.v_ns else self.times_ns
+
+
+def remove_duplicates_and_blank(hyp: List[int], blank_id: int = 0) -> List[int]:
+    """utils/ctc_utils.py:22-32."""
+    out, cur = [], 0
+    while cur < len(hyp):
+        if hyp[cur] != blank_id:
+            out.append(hyp[cur])
+        prev = cur
+        while cur < len(hyp) and hyp[cur] == hyp[prev]:
+            cur += 1
+    return out
+
+
+def ctc_greedy_search(ctc_probs: torch.Tensor, ctc_lens: torch.Tensor, blank_id: int = 0) -> List[DecodeResult]:
+    """transformer/search.py:106-121."""
+    B, T, _ = ctc_probs.shape
+    idx = ctc_probs.topk(1, dim=2)[1].view(B, T)
+    pad = torch.arange(T)[None, :] >= ctc_lens[:, None].long()
+    idx = idx.masked_fill(pad, blank_id)
+    return [DecodeResult(remove_duplicates_and_blank(h.tolist(), blank_id)) for h in idx]
+
+
+def ctc_prefix_beam_search(ctc_probs: torch.Tensor, ctc_lens: torch.Tensor, beam_size: int,
+                           blank_id: int = 0) -> List[DecodeResult]:
+    """transformer/search.py:124-248, literal update rules including the `vs_ns` typo at :178
+    (the repeated-token branch never updates v_ns)."""
+    results = []
+    for i in range(ctc_probs.shape[0]):
+        ctc_prob = ctc_probs[i]
+        num_t = int(ctc_lens[i])
+        cur_hyps = [(tuple(), PrefixScore(s=0.0, ns=NEG_INF, v_s=0.0, v_ns=0.0))]
+        for t in range(num_t):
+            logp = ctc_prob[t]
+            next_hyps = {}
+
+            def get(prefix):
+                ps = next_hyps.get(prefix)
+                if ps is None:
+                    ps = next_hyps[prefix] = PrefixScore()
+                return ps
+
+            _, top_k_index = logp.topk(beam_size)
+            for u in top_k_index.tolist():
+                prob = logp[u].item()
+                for prefix, ps in cur_hyps:
+                    last = prefix[-1] if len(prefix) > 0 else None
+                    if u == blank_id:
+                        n = get(prefix)
+                        n.s = log_add([n.s, ps.score() + prob])
+                        n.v_s = ps.viterbi_score() + prob
+                        n.times_s = ps.times().copy()
+                    elif u == last:
+                        n1 = get(prefix)
+                        n1.ns = log_add([n1.ns, ps.ns + prob])
+                        if n1.v_ns < ps.v_ns + prob:
+                            # reference assigns the misspelt attribute `vs_ns`: v_ns stays put
+                            if n1.cur_token_prob < prob:
+                                n1.cur_token_prob = prob
+                                n1.times_ns = ps.times_ns.copy()
+                                n1.times_ns[-1] = t
+                        n2 = get(prefix + (u,))
+                        n2.ns = log_add([n2.ns, ps.s + prob])
+                        if n2.v_ns < ps.v_s + prob:
+                            n2.v_ns = ps.v_s + prob
+                            n2.cur_token_prob = prob
+                            n2.times_ns = ps.times_s.copy()
+                            n2.times_ns.append(t)
+                    else:
+                        n = get(prefix + (u,))
+                        n.ns = log_add([n.ns, ps.score() + prob])
+                        if n.v_ns < ps.viterbi_score() + prob:
+                            n.v_ns = ps.viterbi_score() + prob
+                            n.cur_token_prob = prob
+                            n.times_ns = ps.times().copy()
+                            n.times_ns.append(t)
+            ordered = sorted(next_hyps.items(), key=lambda x: x[1].score(), reverse=True)
+            cur_hyps = ordered[:beam_size]
+        nbest = [y[0] for y in cur_hyps]
+        nbest_scores = [y[1].score() for y in cur_hyps]
+        nbest_times = [y[1].times() for y in cur_hyps]
+        results.append(DecodeResult(tokens=nbest[0], score=nbest_scores[0], times=nbest_times[0],
+                                    nbest=nbest, nbest_scores=nbest_scores, nbest_times=nbest_times))
+    return results
+
+
+def rescoring_inputs(hyps: List[tuple], sos: int, eos: int):
+    """Padded decoder inputs of attention_rescoring (transformer/search.py:384-409) /
+    add_sos_eos (utils/common.py:112-155): rows [sos, w_1..w_U, eos...], lens U+1."""
+    umax = max(len(h) for h in hyps)
+    ys = torch.full((len(hyps), umax + 1), eos, dtype=torch.long)
+    ys[:, 0] = sos
+    for i, h in enumerate(hyps):
+        if len(h):
+            ys[i, 1:1 + len(h)] = torch.tensor(h, dtype=torch.long)
+    lens = torch.tensor([len(h) + 1 for h in hyps], dtype=torch.long)
+    return ys, lens
+
+
+def rescoring_combine(hyps: List[tuple], ctc_scores: List[float], nbest_times, decoder_out: torch.Tensor,
+                      r_decoder_out: Optional[torch.Tensor], ctc_weight: float, reverse_weight: float,
+                      eos: int) -> DecodeResult:
+    """Score combination loop of attention_rescoring (transformer/search.py:413-447);
+    decoder_out / r_decoder_out are log-softmaxed (N, L, V) fp32. prefix_len == 1."""
+    best_score = -float("inf")
+    best_index = 0
+    confidences, tokens_confidences = [], []
+    for i, hyp in enumerate(hyps):
+        score = 0.0
+        tc = []
+        for j, w in enumerate(hyp):
+            s = decoder_out[i][j][w]
+            score += s
+            tc.append(math.exp(s))
+        score += decoder_out[i][len(hyp)][eos]
+        if reverse_weight > 0 and r_decoder_out is not None and r_decoder_out.dim() > 0:
+            r_score = 0.0
+            for j, w in enumerate(hyp):
+                s = r_decoder_out[i][len(hyp) - j - 1][w]
+                r_score += s
+                tc[j] = (tc[j] + math.exp(s)) / 2
+            r_score += r_decoder_out[i][len(hyp)][eos]
+            score = score * (1 - reverse_weight) + r_score * reverse_weight
+        confidences.append(math.exp(score / (len(hyp) + 1)))
+        score += ctc_scores[i] * ctc_weight
+        if score > best_score:
+            best_score = score
+            best_index = i
+        tokens_confidences.append(tc)
+    return DecodeResult(hyps[best_index], best_score, confidence=confidences[best_index],
+                        times=nbest_times[best_index], tokens_confidence=tokens_confidences[best_index])
