@@ -1,0 +1,127 @@
+/* reverb_b200 — C ABI of the B200-native hot path of revdotcom/reverb.
+ *
+ * The reference (100 % Python, asr/wenet) has no FFI of its own; this header is the boundary a maintainer binds
+ * with ctypes to replace, one for one, the operator-level calls of the reference's hot path:
+ *
+ *   rvb_fbank_*                 <- torchaudio.compliance.kaldi.fbank call   asr/wenet/cli/reverb.py:130-138
+ *   rvb_encoder_forward         <- ASRModel._forward_encoder                asr/wenet/transformer/asr_model.py:288-316
+ *                                  (BaseEncoder.forward, transformer/encoder.py:117-149)
+ *   rvb_ctc_topk                <- ASRModel.ctc_logprobs + logp.topk        asr_model.py:318-329, search.py:111,155
+ *   rvb_ctc_greedy_search       <- ctc_greedy_search                        transformer/search.py:106-121
+ *   rvb_ctc_prefix_beam_search  <- ctc_prefix_beam_search                   transformer/search.py:124-248
+ *   rvb_attention_rescoring     <- forward_attention_decoder + the gather   asr_model.py:868-978, search.py:410-436
+ *   rvb_model_*                 <- init_model / load_checkpoint             utils/init_model.py:99-277,
+ *                                                                           utils/checkpoint.py:29-80
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  `d_` pointers are device memory owned by the caller
+ * (e.g. torch tensors' data_ptr()), `h_` pointers are host memory owned by the caller.  All work is enqueued on the
+ * given CUDA stream (a `cudaStream_t` passed as void*); functions that fill `h_` outputs synchronise that stream
+ * before returning.  Return value 0 = success, < 0 = failure with a message available from rvb_last_error().
+ * There is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef RVB_B200_H_
+#define RVB_B200_H_
+
+#if defined(__GNUC__)
+#define RVB_API __attribute__((visibility("default")))
+#else
+#define RVB_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rvb_model rvb_model;
+
+typedef struct rvb_model_config {
+  int input_dim;        /* fbank bins, 80 (config.yaml: input_dim) */
+  int d_model;          /* encoder_conf.output_size */
+  int heads;            /* encoder_conf.attention_heads */
+  int ffn_dim;          /* encoder_conf.linear_units */
+  int num_blocks;       /* encoder_conf.num_blocks */
+  int cnn_kernel;       /* encoder_conf.cnn_module_kernel */
+  int causal;           /* encoder_conf.causal */
+  int cnn_layer_norm;   /* 1: cnn_module_norm == layer_norm, 0: batch_norm (eval statistics) */
+  int num_langs;        /* dataset_conf.cat_emb_conf.emb_len when pass_cat_emb, else 0 */
+  int vocab;            /* len(symbol_table) */
+  int dec_heads;        /* decoder_conf.attention_heads */
+  int dec_ffn_dim;      /* decoder_conf.linear_units */
+  int dec_blocks;       /* decoder_conf.num_blocks */
+  int r_dec_blocks;     /* decoder_conf.r_num_blocks (0: no right-to-left decoder) */
+} rvb_model_config;
+
+/* ---- diagnostics -------------------------------------------------------------------------------------------- */
+RVB_API const char* rvb_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process */
+RVB_API unsigned long long rvb_launch_count(void);
+/* 0 = tcgen05/TMA GEMM (default), 1 = plain CUDA-core bring-up GEMM (debug only) */
+RVB_API int rvb_set_gemm_impl(int impl);
+RVB_API int rvb_get_gemm_impl(void);
+
+/* ---- model lifecycle ---------------------------------------------------------------------------------------- */
+RVB_API rvb_model* rvb_model_create(const rvb_model_config* cfg);
+/* Register one tensor of the reference state_dict under its reference key name (fp32, host memory, copied). */
+RVB_API int rvb_model_set_tensor(rvb_model* m, const char* name, const float* h_data, long long numel);
+/* Pack the registered tensors into the device layout (bf16 GEMM operands, fused QKV, permuted conv weights). */
+RVB_API int rvb_model_finalize(rvb_model* m);
+RVB_API void rvb_model_destroy(rvb_model* m);
+/* T' = ((T-1)/2 - 1)/2 encoder frames for T feature frames (Conv2dSubsampling4) */
+RVB_API int rvb_encoder_out_frames(int T);
+/* encoder_lens for a feature length (subsampled padding mask, transformer/subsampling.py:226) */
+RVB_API int rvb_encoder_out_len(int feat_len, int T);
+
+/* ---- hot path ----------------------------------------------------------------------------------------------- */
+/* number of fbank frames for n_samples (snip_edges): 0 if n < 400 else 1 + (n - 400) / 160 */
+RVB_API long long rvb_fbank_num_frames(long long n_samples);
+RVB_API int rvb_fbank_f32(const float* d_wave, long long n_samples, float* d_feats, long long n_frames, void* stream);
+RVB_API int rvb_fbank_i16(const short* d_wave, long long n_samples, float* d_feats, long long n_frames, void* stream);
+
+/* feats (B, T, input_dim) fp32 -> enc_out (B, T', d_model) fp32; h_enc_lens[B] receives encoder_lens.
+ * h_cat_embs: the LSL mixing weights [verbatimicity, 1 - verbatimicity] (n_cat == num_langs), may be NULL iff
+ * num_langs == 0. */
+RVB_API int rvb_encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
+                        const float* h_cat_embs, int n_cat, float* d_enc_out, int* h_enc_lens, void* stream);
+
+/* CTC head: logits = ctc_lo(enc_out) (blank_penalty subtracted from the blank column), log_softmax, top-k.
+ * d_topk_val/d_topk_idx: (B*Tp, k) sorted descending; d_logp (B*Tp, vocab) optional (NULL to skip the write). */
+RVB_API int rvb_ctc_topk(rvb_model* m, const float* d_enc_out, int B, int Tp, int k, float blank_penalty, int blank_id,
+                 float* d_topk_val, int* d_topk_idx, float* d_logp, void* stream);
+/* top-k of an existing (rows, V) log-prob matrix (no softmax) — used to run the searches on recorded ctc_probs */
+RVB_API int rvb_logp_topk(const float* d_logp, int rows, int V, int k, float* d_topk_val, int* d_topk_idx, void* stream);
+
+/* h_tokens: (B, Tp) int32, h_lens: (B) */
+RVB_API int rvb_ctc_greedy_search(const int* d_topk_idx, int k, const int* h_enc_lens, int B, int Tp, int blank_id,
+                          int* h_tokens, int* h_lens, void* stream);
+/* n-best per utterance: h_tokens/h_times (B, beam, max_len) int32, h_lens (B, beam, 2) = {n_tokens, n_times},
+ * h_scores (B, beam) float64, h_nhyp (B).  Fails if a hypothesis is longer than max_len. */
+RVB_API int rvb_ctc_prefix_beam_search(const float* d_topk_val, const int* d_topk_idx, int k, const int* h_enc_lens, int B,
+                               int Tp, int beam, int blank_id, int max_len, int* h_tokens, int* h_times, int* h_lens,
+                               double* h_scores, int* h_nhyp, void* stream);
+
+/* Teacher-forced (bi-)decoder over the n-best.  h_hyp_tokens (B, N, max_len), h_hyp_lens (B, N) (a negative length
+ * marks an absent hypothesis).  h_l2r (B, N, max_len + 1): [j] = log p(w_j | ...) for j < U, [U] = log p(eos);
+ * h_r2l likewise for the right-to-left decoder with [j] = r_logp[U-1-j][w_j], [U] = r_logp[U][eos]
+ * (only written when reverse_weight > 0 and the model has a right decoder; may be NULL otherwise). */
+RVB_API int rvb_attention_rescoring(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp,
+                            const int* h_hyp_tokens, const int* h_hyp_lens, int N, int max_len,
+                            const float* h_cat_embs, int n_cat, float reverse_weight, float* h_l2r, float* h_r2l,
+                            void* stream);
+
+/* ---- kernel-level entry points (parity tests, profiling) ----------------------------------------------------- */
+/* C[M,N] = A[M,K] W[N,K]^T + bias; act: 0 none 1 relu 2 silu; out_mode: 0 bf16, 1 f32, 2 f32 residual += alpha*(.) */
+RVB_API int rvb_gemm_bf16(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int act, int out_mode,
+                  float alpha, void* d_out, int ldo, void* stream);
+RVB_API int rvb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, float eps, int M, int d,
+                  void* d_out_bf16, float* d_out_f32, void* stream);
+/* q/k/v/out bf16, (B, T, H, dk) with the given row strides; p (Tk, H, dk) optional rel-pos keys */
+RVB_API int rvb_attention(const void* d_q, const void* d_k, const void* d_v, const void* d_p, const float* d_bias_u,
+                  const float* d_bias_v, void* d_out, int ldq, int ldk, int ldv, int ldp, int ldo, int Bq, int Tq, int Tk,
+                  int H, int dk, int q_per_kv, const int* d_k_lens, const int* d_q_lens, int causal, float scale,
+                  void* stream);
+RVB_API int rvb_f32_to_bf16(const float* d_x, void* d_out, long long n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVB_B200_H_ */

@@ -1,0 +1,104 @@
+"""`ASRModel.decode` — the operator boundary the kernels sit behind.
+
+Same signature, argument meaning and result types as the reference's
+`ASRModel.decode` (asr/wenet/transformer/asr_model.py:331-432); the body drives the native
+plan (reverb_b200/engine.py) instead of a torch.nn graph:
+
+    encoder (csrc/engine.cu) -> CTC head + top-k (csrc/ctc.cu) -> greedy / prefix beam (GPU)
+    -> teacher-forced decoder over the n-best (GPU) -> score combination (host, search.py)
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from .engine import Engine
+from .search import DecodeResult, greedy_results, prefix_beam_results, rescoring_pick
+
+SUPPORTED_METHODS = ("ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring")
+
+
+class ASRModel:
+    def __init__(self, engine: Engine, configs: Dict, vocab_size: int):
+        self.engine = engine
+        self.configs = configs
+        self.vocab_size = vocab_size
+        st = (configs.get("tokenizer_conf") or {}).get("special_tokens")
+        # asr_model.py:79-82: eos is the same id as sos
+        self.sos = vocab_size - 1 if st is None else st.get("<sos>", vocab_size - 1)
+        self.eos = vocab_size - 1 if st is None else st.get("<eos>", vocab_size - 1)
+        self.ignore_id = -1
+        ds = configs.get("dataset_conf", {})
+        self.lsl_enc = self.lsl_dec = bool(ds.get("pass_cat_emb", False))
+        self.reverse_weight = configs.get("model_conf", {}).get("reverse_weight", 0.0)
+
+    def sos_symbol(self) -> int:
+        return self.sos
+
+    def eos_symbol(self) -> int:
+        return self.eos
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        return self
+
+    # -- pieces of decode(), exposed for tests / profiling ---------------------------------------
+    def _forward_encoder(self, speech: torch.Tensor, speech_lengths, cat_embs=None):
+        """-> (encoder_out (B, T', d) fp32 cuda, encoder_lens np.int32 (B,))."""
+        lens = speech_lengths.detach().cpu().numpy() if torch.is_tensor(speech_lengths) else np.asarray(speech_lengths)
+        return self.engine.forward_encoder(speech, lens, cat_embs)
+
+    def ctc_logprobs(self, encoder_out: torch.Tensor, blank_penalty: float = 0.0, blank_id: int = 0) -> torch.Tensor:
+        return self.engine.ctc_topk(encoder_out, 1, blank_penalty, blank_id, want_logp=True)[2]
+
+    @torch.no_grad()
+    def decode(self, methods: List[str], speech: torch.Tensor, speech_lengths: torch.Tensor, beam_size: int,
+               decoding_chunk_size: int = -1, num_decoding_left_chunks: int = -1, ctc_weight: float = 0.0,
+               simulate_streaming: bool = False, reverse_weight: float = 0.0, context_graph=None,
+               blank_id: int = 0, blank_penalty: float = 0.0, length_penalty: float = 0.0,
+               infos: Optional[Dict[str, List[str]]] = None, cat_embs: Optional[torch.Tensor] = None,
+               cv=None, cv_lengths=None) -> Dict[str, List[DecodeResult]]:
+        assert speech.shape[0] == speech_lengths.shape[0]
+        assert decoding_chunk_size != 0
+        if decoding_chunk_size > 0 or simulate_streaming:
+            raise NotImplementedError("reverb_b200: only full-context decoding (decoding_chunk_size < 0) is built")
+        if context_graph is not None:
+            raise NotImplementedError("reverb_b200: context biasing is out of scope (SURVEY.md §2)")
+        unknown = [m for m in methods if m not in SUPPORTED_METHODS]
+        if unknown:
+            raise NotImplementedError(f"reverb_b200: decoding method(s) {unknown} are not built yet (SURVEY.md §8f)")
+        if not speech.is_cuda:
+            speech = speech.to(self.engine.device, non_blocking=True)
+        speech = speech.to(torch.float32)
+        encoder_out, encoder_lens = self._forward_encoder(speech, speech_lengths, cat_embs)
+        need_beam = "ctc_prefix_beam_search" in methods or "attention_rescoring" in methods
+        k = beam_size if need_beam else 1
+        topk_val, topk_idx, _ = self.engine.ctc_topk(encoder_out, k, blank_penalty, blank_id)
+        results: Dict[str, List[DecodeResult]] = {}
+        if "ctc_greedy_search" in methods:
+            results["ctc_greedy_search"] = greedy_results(self.engine.greedy_search(topk_idx, encoder_lens, blank_id))
+        prefix = None
+        if need_beam:
+            prefix = prefix_beam_results(
+                self.engine.prefix_beam_search(topk_val, topk_idx, encoder_lens, beam_size, blank_id))
+            if "ctc_prefix_beam_search" in methods:
+                results["ctc_prefix_beam_search"] = prefix
+        if "attention_rescoring" in methods:
+            results["attention_rescoring"] = self.attention_rescoring(
+                prefix, encoder_out, encoder_lens, ctc_weight, reverse_weight, cat_embs)
+        return results
+
+    def attention_rescoring(self, prefix_results: List[DecodeResult], encoder_out: torch.Tensor, encoder_lens,
+                            ctc_weight: float = 0.0, reverse_weight: float = 0.0, cat_embs=None) -> List[DecodeResult]:
+        """asr/wenet/transformer/search.py:363-448, batched over utterances x hypotheses."""
+        nbest = [r.nbest for r in prefix_results]
+        l2r, r2l = self.engine.rescoring_scores(encoder_out, encoder_lens, nbest, cat_embs, reverse_weight)
+        out = []
+        for b, r in enumerate(prefix_results):
+            out.append(rescoring_pick(r.nbest, r.nbest_scores, r.nbest_times, l2r[b],
+                                      None if r2l is None else r2l[b], ctc_weight, reverse_weight))
+        return out

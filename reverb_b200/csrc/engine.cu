@@ -1,0 +1,995 @@
+// reverb_b200 — the model plan: packed weights + workspace + the launch sequences of the encoder, CTC head and
+// rescoring decoder, and the C ABI on top (include/rvb_b200.h).
+//
+// Reference call chain replaced here (all paths relative to asr/wenet/):
+//   ASRModel._forward_encoder (transformer/asr_model.py:288) -> BaseEncoder.forward (transformer/encoder.py:117-149)
+//     -> GlobalCMVN, Conv2dSubsampling4, RelPositionalEncoding, 18 x (LanguageSpecific)ConformerEncoderLayer, after_norm
+//   ASRModel.ctc_logprobs (asr_model.py:318)                    -> rvb_ctc_topk
+//   ASRModel.forward_attention_decoder (asr_model.py:868-978)   -> rvb_attention_rescoring
+// Data layout in HBM: residual stream fp32 (B*T', d); every GEMM operand bf16, K-major; conv activations
+// channels-last; weights packed once at rvb_model_finalize (fused QKV, permuted conv2 / embed weights, sqrt(d) folded
+// into the embed linear, language-specific linears folded per call with the caller's cat_embs).
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rvb_b200.h"
+#include "kernels.h"
+
+namespace rvb {
+
+// ---------------------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+unsigned long long g_launch_count = 0;
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + (bytes >> 3) + 256;
+    RVB_CHECK_CUDA(cudaMalloc(&p, want));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostPinned {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    RVB_CHECK_CUDA(cudaMallocHost(&p, bytes + 256));
+    cap = bytes + 256;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+static inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);                                            // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+
+struct Linear {  // bf16 weight (N, K) + fp32 bias (N) on device
+  bf16* w = nullptr;
+  float* b = nullptr;
+  int N = 0, K = 0;
+};
+struct Norm {
+  float* g = nullptr;
+  float* b = nullptr;
+};
+
+struct EncLayer {
+  Norm norm_ffm, norm_mha, norm_conv, norm_ff, norm_final;
+  Linear ffm1, ffm2, ff1, ff2, qkv, out, pw1, pw2;
+  float* pos_u = nullptr;
+  float* pos_v = nullptr;
+  float* dw_w = nullptr;  // (d, K)
+  float* dw_b = nullptr;
+  Norm cnorm;             // conv-module norm (LayerNorm or BatchNorm affine)
+  float* bn_mean = nullptr;
+  float* bn_var = nullptr;
+  bool lsl = false;
+  std::vector<float*> lang_w, lang_b;  // fp32 device copies of language_layers.{i}
+  Linear lang;                         // folded with the current cat_embs
+};
+
+struct DecLayer {
+  Norm n1, n2, n3;
+  float eps = 1e-5f;
+  Linear qkv, so, cq, ckv, co, ff1, ff2;
+  bool lsl = false;
+  std::vector<float*> lang_w, lang_b;
+  Linear lang;
+};
+
+struct Decoder {
+  float* emb = nullptr;  // (V, d) fp32
+  std::vector<DecLayer> layers;
+  Norm after;
+  Linear outl;
+  bool present = false;
+};
+
+}  // namespace rvb
+
+using namespace rvb;
+
+struct rvb_model {
+  rvb_model_config cfg;
+  std::map<std::string, std::vector<float>> host;  // raw reference tensors until finalize
+  bool finalized = false;
+  std::vector<void*> owned;  // device allocations owned by the plan
+
+  // encoder
+  float* cmvn_mean = nullptr;
+  float* cmvn_istd = nullptr;
+  float* conv1_w = nullptr;  // (d, 9)
+  float* conv1_b = nullptr;
+  Linear conv2;    // (d, 9*d) ordered (kh, kw, c)
+  Linear embed;    // (d, F2*d) ordered (f, c), scaled by sqrt(d)
+  Linear pos_all;  // (L*d, d) stacked linear_pos weights, no bias
+  std::vector<EncLayer> enc;
+  Norm after_norm;
+  Linear ctc;
+  Decoder dec_l, dec_r;
+  std::vector<float> cur_cat;  // cat_embs the LSL folds were computed for
+
+  // workspace (grow-only)
+  DevBuf ws_c1, ws_c2, ws_x, ws_n, ws_h, ws_qkv, ws_att, ws_pw, ws_cm, ws_y, ws_ybf, ws_pe, ws_pall, ws_lens;
+  DevBuf ws_encbf, ws_logits, ws_dec[12], ws_search, ws_misc;
+  HostPinned pin_a, pin_b, pin_c, pin_d, pin_e;
+  int pe_T = 0;
+  int lens_slot = 0;
+  int lens_B = 0;
+
+  int F1() const { return (cfg.input_dim - 1) / 2; }
+  int F2() const { return (F1() - 1) / 2; }
+};
+
+namespace rvb {
+
+static const std::vector<float>* find_host(rvb_model* m, const std::string& name) {
+  auto it = m->host.find(name);
+  return it == m->host.end() ? nullptr : &it->second;
+}
+
+static int need(rvb_model* m, const std::string& name, size_t numel, const std::vector<float>** out) {
+  const std::vector<float>* v = find_host(m, name);
+  RVB_REQUIRE(v != nullptr, "model: tensor '%s' was not provided", name.c_str());
+  RVB_REQUIRE(v->size() == numel, "model: tensor '%s' has %zu elements, expected %zu", name.c_str(), v->size(), numel);
+  *out = v;
+  return 0;
+}
+
+static int upload_f32(rvb_model* m, const float* src, size_t n, float** dst) {
+  void* p = nullptr;
+  RVB_CHECK_CUDA(cudaMalloc(&p, n * sizeof(float) + 16));
+  RVB_CHECK_CUDA(cudaMemcpy(p, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  m->owned.push_back(p);
+  *dst = reinterpret_cast<float*>(p);
+  return 0;
+}
+
+static int upload_bf16(rvb_model* m, const float* src, size_t n, bf16** dst) {
+  std::vector<uint16_t> tmp(n);
+  for (size_t i = 0; i < n; ++i) tmp[i] = f2bf(src[i]);
+  void* p = nullptr;
+  RVB_CHECK_CUDA(cudaMalloc(&p, n * sizeof(uint16_t) + 16));
+  RVB_CHECK_CUDA(cudaMemcpy(p, tmp.data(), n * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  m->owned.push_back(p);
+  *dst = reinterpret_cast<bf16*>(p);
+  return 0;
+}
+
+static int alloc_dev(rvb_model* m, size_t bytes, void** dst) {
+  void* p = nullptr;
+  RVB_CHECK_CUDA(cudaMalloc(&p, bytes + 16));
+  RVB_CHECK_CUDA(cudaMemset(p, 0, bytes + 16));
+  m->owned.push_back(p);
+  *dst = p;
+  return 0;
+}
+
+// nn.Linear `prefix`.{weight,bias}; bias optional (zeros when absent and `bias_optional`)
+static int load_linear(rvb_model* m, const std::string& prefix, int N, int K, Linear* out, bool has_bias = true,
+                       bool bias_optional = false) {
+  const std::vector<float>* w;
+  if (need(m, prefix + ".weight", (size_t)N * K, &w)) return -1;
+  if (upload_bf16(m, w->data(), w->size(), &out->w)) return -1;
+  out->N = N;
+  out->K = K;
+  if (has_bias) {
+    const std::vector<float>* b = find_host(m, prefix + ".bias");
+    if (b == nullptr && bias_optional) {
+      std::vector<float> z(N, 0.f);
+      if (upload_f32(m, z.data(), N, &out->b)) return -1;
+    } else {
+      if (need(m, prefix + ".bias", N, &b)) return -1;
+      if (upload_f32(m, b->data(), N, &out->b)) return -1;
+    }
+  }
+  return 0;
+}
+
+static int load_norm(rvb_model* m, const std::string& prefix, int d, Norm* out) {
+  const std::vector<float>*g, *b;
+  if (need(m, prefix + ".weight", d, &g) || need(m, prefix + ".bias", d, &b)) return -1;
+  if (upload_f32(m, g->data(), d, &out->g) || upload_f32(m, b->data(), d, &out->b)) return -1;
+  return 0;
+}
+
+// fused [q; k; v] (or [k; v]) projection
+static int load_fused(rvb_model* m, const std::string& prefix, const std::vector<std::string>& parts, int d,
+                      Linear* out) {
+  std::vector<float> w, b;
+  for (const auto& part : parts) {
+    const std::vector<float>* pw;
+    if (need(m, prefix + "." + part + ".weight", (size_t)d * d, &pw)) return -1;
+    w.insert(w.end(), pw->begin(), pw->end());
+    const std::vector<float>* pb = find_host(m, prefix + "." + part + ".bias");
+    if (pb) {
+      RVB_REQUIRE(pb->size() == (size_t)d, "model: bad bias size for %s.%s", prefix.c_str(), part.c_str());
+      b.insert(b.end(), pb->begin(), pb->end());
+    } else {
+      b.insert(b.end(), d, 0.f);  // key_bias = False
+    }
+  }
+  if (upload_bf16(m, w.data(), w.size(), &out->w) || upload_f32(m, b.data(), b.size(), &out->b)) return -1;
+  out->N = d * (int)parts.size();
+  out->K = d;
+  return 0;
+}
+
+static int load_lang(rvb_model* m, const std::string& prefix, int d, int n_lang, std::vector<float*>* lw,
+                     std::vector<float*>* lb, Linear* folded) {
+  for (int i = 0; i < n_lang; ++i) {
+    const std::vector<float>*w, *b;
+    std::string p = prefix + ".language_layers." + std::to_string(i);
+    if (need(m, p + ".weight", (size_t)d * d, &w) || need(m, p + ".bias", d, &b)) return -1;
+    float *dw, *db;
+    if (upload_f32(m, w->data(), w->size(), &dw) || upload_f32(m, b->data(), d, &db)) return -1;
+    lw->push_back(dw);
+    lb->push_back(db);
+  }
+  void* p;
+  if (alloc_dev(m, (size_t)d * d * sizeof(bf16), &p)) return -1;
+  folded->w = reinterpret_cast<bf16*>(p);
+  if (alloc_dev(m, (size_t)d * sizeof(float), &p)) return -1;
+  folded->b = reinterpret_cast<float*>(p);
+  folded->N = d;
+  folded->K = d;
+  return 0;
+}
+
+static int load_decoder(rvb_model* m, const std::string& side, int nblocks, Decoder* dec) {
+  const rvb_model_config& c = m->cfg;
+  const int d = c.d_model, V = c.vocab;
+  const std::string p = "decoder." + side;
+  const std::vector<float>* e;
+  if (need(m, p + ".embed.0.weight", (size_t)V * d, &e)) return -1;
+  if (upload_f32(m, e->data(), e->size(), &dec->emb)) return -1;
+  if (load_norm(m, p + ".after_norm", d, &dec->after)) return -1;
+  if (load_linear(m, p + ".output_layer", V, d, &dec->outl)) return -1;
+  dec->layers.resize(nblocks);
+  for (int i = 0; i < nblocks; ++i) {
+    DecLayer& L = dec->layers[i];
+    const std::string q = p + ".decoders." + std::to_string(i);
+    L.lsl = c.num_langs > 0 && (i == 0 || i == nblocks - 1);
+    L.eps = L.lsl ? 1e-12f : 1e-5f;  // decoder_layer.py:241-243 vs :53-55
+    if (load_norm(m, q + ".norm1", d, &L.n1) || load_norm(m, q + ".norm2", d, &L.n2) ||
+        load_norm(m, q + ".norm3", d, &L.n3))
+      return -1;
+    if (load_fused(m, q + ".self_attn", {"linear_q", "linear_k", "linear_v"}, d, &L.qkv)) return -1;
+    if (load_linear(m, q + ".self_attn.linear_out", d, d, &L.so)) return -1;
+    if (load_linear(m, q + ".src_attn.linear_q", d, d, &L.cq)) return -1;
+    if (load_fused(m, q + ".src_attn", {"linear_k", "linear_v"}, d, &L.ckv)) return -1;
+    if (load_linear(m, q + ".src_attn.linear_out", d, d, &L.co)) return -1;
+    if (load_linear(m, q + ".feed_forward.w_1", c.dec_ffn_dim, d, &L.ff1)) return -1;
+    if (load_linear(m, q + ".feed_forward.w_2", d, c.dec_ffn_dim, &L.ff2)) return -1;
+    if (L.lsl && load_lang(m, q, d, c.num_langs, &L.lang_w, &L.lang_b, &L.lang)) return -1;
+  }
+  dec->present = true;
+  return 0;
+}
+
+static int finalize_model(rvb_model* m) {
+  const rvb_model_config& c = m->cfg;
+  const int d = c.d_model, F = c.input_dim, L = c.num_blocks, K = c.cnn_kernel;
+  const int F2 = m->F2();
+  RVB_REQUIRE(d % 64 == 0, "model: d_model=%d must be a multiple of 64", d);
+  RVB_REQUIRE(d % c.heads == 0 && d % c.dec_heads == 0, "model: heads must divide d_model");
+  const std::vector<float>* t;
+  if (need(m, "encoder.global_cmvn.mean", F, &t) || upload_f32(m, t->data(), F, &m->cmvn_mean)) return -1;
+  if (need(m, "encoder.global_cmvn.istd", F, &t) || upload_f32(m, t->data(), F, &m->cmvn_istd)) return -1;
+  if (need(m, "encoder.embed.conv.0.weight", (size_t)d * 9, &t) || upload_f32(m, t->data(), t->size(), &m->conv1_w))
+    return -1;
+  if (need(m, "encoder.embed.conv.0.bias", d, &t) || upload_f32(m, t->data(), d, &m->conv1_b)) return -1;
+  {  // conv2 weight (o, c, kh, kw) -> (o, kh, kw, c)
+    if (need(m, "encoder.embed.conv.2.weight", (size_t)d * d * 9, &t)) return -1;
+    std::vector<float> w((size_t)d * d * 9);
+    for (int o = 0; o < d; ++o)
+      for (int ci = 0; ci < d; ++ci)
+        for (int k = 0; k < 9; ++k) w[((size_t)o * 9 + k) * d + ci] = (*t)[((size_t)o * d + ci) * 9 + k];
+    if (upload_bf16(m, w.data(), w.size(), &m->conv2.w)) return -1;
+    if (need(m, "encoder.embed.conv.2.bias", d, &t) || upload_f32(m, t->data(), d, &m->conv2.b)) return -1;
+    m->conv2.N = d;
+    m->conv2.K = 9 * d;
+  }
+  {  // embed linear (o, c*F2 + f) -> (o, f*d + c), times sqrt(d) (RelPositionalEncoding xscale, embedding.py:144)
+    if (need(m, "encoder.embed.out.0.weight", (size_t)d * d * F2, &t)) return -1;
+    const float xs = sqrtf((float)d);
+    std::vector<float> w((size_t)d * d * F2);
+    for (int o = 0; o < d; ++o)
+      for (int ci = 0; ci < d; ++ci)
+        for (int f = 0; f < F2; ++f)
+          w[(size_t)o * d * F2 + (size_t)f * d + ci] = (*t)[(size_t)o * d * F2 + (size_t)ci * F2 + f] * xs;
+    if (upload_bf16(m, w.data(), w.size(), &m->embed.w)) return -1;
+    if (need(m, "encoder.embed.out.0.bias", d, &t)) return -1;
+    std::vector<float> b(*t);
+    for (auto& v : b) v *= xs;
+    if (upload_f32(m, b.data(), d, &m->embed.b)) return -1;
+    m->embed.N = d;
+    m->embed.K = d * F2;
+  }
+  if (load_norm(m, "encoder.after_norm", d, &m->after_norm)) return -1;
+  m->enc.resize(L);
+  std::vector<float> posw;
+  for (int i = 0; i < L; ++i) {
+    EncLayer& E = m->enc[i];
+    const std::string p = "encoder.encoders." + std::to_string(i);
+    E.lsl = c.num_langs > 0 && (i == 0 || i == L - 1);
+    if (load_norm(m, p + ".norm_ff_macaron", d, &E.norm_ffm) || load_norm(m, p + ".norm_mha", d, &E.norm_mha) ||
+        load_norm(m, p + ".norm_conv", d, &E.norm_conv) || load_norm(m, p + ".norm_ff", d, &E.norm_ff) ||
+        load_norm(m, p + ".norm_final", d, &E.norm_final))
+      return -1;
+    if (load_linear(m, p + ".feed_forward_macaron.w_1", c.ffn_dim, d, &E.ffm1) ||
+        load_linear(m, p + ".feed_forward_macaron.w_2", d, c.ffn_dim, &E.ffm2) ||
+        load_linear(m, p + ".feed_forward.w_1", c.ffn_dim, d, &E.ff1) ||
+        load_linear(m, p + ".feed_forward.w_2", d, c.ffn_dim, &E.ff2))
+      return -1;
+    if (load_fused(m, p + ".self_attn", {"linear_q", "linear_k", "linear_v"}, d, &E.qkv)) return -1;
+    if (load_linear(m, p + ".self_attn.linear_out", d, d, &E.out)) return -1;
+    if (need(m, p + ".self_attn.linear_pos.weight", (size_t)d * d, &t)) return -1;
+    posw.insert(posw.end(), t->begin(), t->end());
+    if (need(m, p + ".self_attn.pos_bias_u", d, &t) || upload_f32(m, t->data(), d, &E.pos_u)) return -1;
+    if (need(m, p + ".self_attn.pos_bias_v", d, &t) || upload_f32(m, t->data(), d, &E.pos_v)) return -1;
+    if (load_linear(m, p + ".conv_module.pointwise_conv1", 2 * d, d, &E.pw1) ||
+        load_linear(m, p + ".conv_module.pointwise_conv2", d, d, &E.pw2))
+      return -1;
+    if (need(m, p + ".conv_module.depthwise_conv.weight", (size_t)d * K, &t) ||
+        upload_f32(m, t->data(), t->size(), &E.dw_w))
+      return -1;
+    if (need(m, p + ".conv_module.depthwise_conv.bias", d, &t) || upload_f32(m, t->data(), d, &E.dw_b)) return -1;
+    if (load_norm(m, p + ".conv_module.norm", d, &E.cnorm)) return -1;
+    if (!c.cnn_layer_norm) {
+      if (need(m, p + ".conv_module.norm.running_mean", d, &t) || upload_f32(m, t->data(), d, &E.bn_mean)) return -1;
+      if (need(m, p + ".conv_module.norm.running_var", d, &t) || upload_f32(m, t->data(), d, &E.bn_var)) return -1;
+    }
+    if (E.lsl && load_lang(m, p, d, c.num_langs, &E.lang_w, &E.lang_b, &E.lang)) return -1;
+  }
+  if (upload_bf16(m, posw.data(), posw.size(), &m->pos_all.w)) return -1;
+  m->pos_all.N = L * d;
+  m->pos_all.K = d;
+  if (load_linear(m, "ctc.ctc_lo", c.vocab, d, &m->ctc)) return -1;
+  if (c.dec_blocks > 0 && find_host(m, "decoder.left_decoder.embed.0.weight")) {
+    if (load_decoder(m, "left_decoder", c.dec_blocks, &m->dec_l)) return -1;
+  }
+  if (c.r_dec_blocks > 0 && find_host(m, "decoder.right_decoder.embed.0.weight")) {
+    if (load_decoder(m, "right_decoder", c.r_dec_blocks, &m->dec_r)) return -1;
+  }
+  m->host.clear();
+  m->finalized = true;
+  return 0;
+}
+
+// fold sum_i c_i * language_layers[i] for every LSL layer (encoder_layer.py:376-390, decoder_layer.py:318-331)
+static int fold_lang(rvb_model* m, const float* cat, int n_cat, cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  if (c.num_langs == 0) return 0;
+  RVB_REQUIRE(cat != nullptr && n_cat == c.num_langs, "cat_embs of length %d required (got %d)", c.num_langs, n_cat);
+  if ((int)m->cur_cat.size() == n_cat && memcmp(m->cur_cat.data(), cat, sizeof(float) * n_cat) == 0) return 0;
+  const int d = c.d_model;
+  auto fold = [&](std::vector<float*>& lw, std::vector<float*>& lb, Linear& out) -> int {
+    if (launch_weighted_sum_bf16(lw.data(), cat, n_cat, (long long)d * d, out.w, nullptr, stream)) return -1;
+    if (launch_weighted_sum_bf16(lb.data(), cat, n_cat, d, nullptr, out.b, stream)) return -1;
+    return 0;
+  };
+  for (auto& E : m->enc)
+    if (E.lsl && fold(E.lang_w, E.lang_b, E.lang)) return -1;
+  for (Decoder* D : {&m->dec_l, &m->dec_r})
+    if (D->present)
+      for (auto& Ld : D->layers)
+        if (Ld.lsl && fold(Ld.lang_w, Ld.lang_b, Ld.lang)) return -1;
+  m->cur_cat.assign(cat, cat + n_cat);
+  return 0;
+}
+
+static int gemm(const bf16* A, const Linear& W, int M, int act, int out_mode, void* out, float alpha,
+                cudaStream_t stream, const int* row_lens = nullptr, int rows_per_batch = 0, int ldo = 0,
+                bool use_bias = true) {
+  GemmArgs g;
+  g.A = A;
+  g.W = W.w;
+  g.M = M;
+  g.N = W.N;
+  g.K = W.K;
+  g.bias = use_bias ? W.b : nullptr;
+  g.act = act;
+  g.out_mode = out_mode;
+  g.out = out;
+  g.alpha = alpha;
+  g.row_lens = row_lens;
+  g.rows_per_batch = rows_per_batch;
+  g.ldo = ldo;
+  return launch_gemm(g, stream);
+}
+
+static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
+                           const float* h_cat, int n_cat, float* d_enc_out, int* h_enc_lens, cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  RVB_REQUIRE(m->finalized, "encoder_forward: model not finalized");
+  const int d = c.d_model, F = c.input_dim, H = c.heads, dk = d / H, L = c.num_blocks;
+  const int T1 = (T - 1) / 2, F1 = m->F1(), Tp = (T1 - 1) / 2, F2 = m->F2();
+  RVB_REQUIRE(T >= 7 && Tp >= 1, "encoder_forward: chunk of %d frames is too short for Conv2dSubsampling4", T);
+  RVB_REQUIRE(Tp <= 5000, "encoder_forward: %d encoder frames exceed the positional table (5000)", Tp);
+  const int T1h = (T1 + 1) / 2;
+  const long long M = (long long)B * Tp;
+  RVB_REQUIRE(M * (long long)F2 < (1ll << 31), "encoder_forward: batch too large (B*T'*F2 overflows int)");
+  if (fold_lang(m, h_cat, n_cat, stream)) return -1;
+
+  // lengths
+  // pinned staging ring: a back-to-back call must not overwrite lengths an earlier async copy still reads
+  constexpr int kRing = 16;
+  if (m->pin_a.ensure(sizeof(int) * B * kRing) || m->ws_lens.ensure(sizeof(int) * B * kRing)) return -1;
+  if (m->lens_B != B) {
+    RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
+    m->lens_B = B;
+  }
+  const int slot = (m->lens_slot++) % kRing;
+  int* h_lens = m->pin_a.as<int>() + (size_t)slot * B;
+  for (int b = 0; b < B; ++b) {
+    int e = rvb_encoder_out_len(h_feat_lens[b], T);
+    h_lens[b] = e;
+    if (h_enc_lens) h_enc_lens[b] = e;
+  }
+  int* d_lens = m->ws_lens.as<int>() + (size_t)slot * B;
+  RVB_CHECK_CUDA(cudaMemcpyAsync(d_lens, h_lens, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+
+  // workspace
+  if (m->ws_c1.ensure((size_t)B * 2 * T1h * F1 * d * 2) || m->ws_c2.ensure((size_t)M * F2 * d * 2) ||
+      m->ws_x.ensure((size_t)M * d * 4) || m->ws_n.ensure((size_t)M * d * 2) ||
+      m->ws_h.ensure((size_t)M * c.ffn_dim * 2) || m->ws_qkv.ensure((size_t)M * 3 * d * 2) ||
+      m->ws_att.ensure((size_t)M * d * 2) || m->ws_pw.ensure((size_t)M * 2 * d * 2) ||
+      m->ws_cm.ensure((size_t)M * d * 2) || m->ws_y.ensure((size_t)M * d * 4) || m->ws_ybf.ensure((size_t)M * d * 2) ||
+      m->ws_pall.ensure((size_t)Tp * L * d * 2))
+    return -1;
+  bf16* c1 = m->ws_c1.as<bf16>();
+  bf16* c2 = m->ws_c2.as<bf16>();
+  float* x = m->ws_x.as<float>();
+  bf16* n = m->ws_n.as<bf16>();
+  bf16* h = m->ws_h.as<bf16>();
+  bf16* qkv = m->ws_qkv.as<bf16>();
+  bf16* att = m->ws_att.as<bf16>();
+  bf16* pw = m->ws_pw.as<bf16>();
+  bf16* cm = m->ws_cm.as<bf16>();
+  float* y = m->ws_y.as<float>();
+  bf16* ybf = m->ws_ybf.as<bf16>();
+  bf16* pall = m->ws_pall.as<bf16>();
+
+  // positional table + all layers' linear_pos(pos_emb) in one GEMM (attention.py:374; batch-shared)
+  if (m->pe_T < Tp) {
+    if (m->ws_pe.ensure((size_t)Tp * d * 2)) return -1;
+    if (launch_sinusoid(Tp, d, nullptr, m->ws_pe.as<bf16>(), stream)) return -1;
+    m->pe_T = Tp;
+  }
+  if (gemm(m->ws_pe.as<bf16>(), m->pos_all, Tp, ACT_NONE, OUT_BF16, pall, 1.f, stream, nullptr, 0, 0, false))
+    return -1;
+
+  // subsampling: CMVN + conv1 + ReLU ; conv2 + ReLU as implicit GEMM ; Linear(19 d -> d) * sqrt(d)
+  if (launch_conv1(d_feats, m->cmvn_mean, m->cmvn_istd, m->conv1_w, m->conv1_b, c1, B, T, F, d, T1, T1h, F1, stream))
+    return -1;
+  {
+    GemmArgs g;
+    g.A = c1;
+    g.W = m->conv2.w;
+    g.M = (int)(M * F2);
+    g.N = d;
+    g.K = 9 * d;
+    g.bias = m->conv2.b;
+    g.act = ACT_RELU;
+    g.out_mode = OUT_BF16;
+    g.out = c2;
+    g.ldo = d;
+    g.conv_mode = 1;
+    g.conv_B = B;
+    g.conv_T1h = T1h;
+    g.conv_F1 = F1;
+    g.conv_C = d;
+    g.conv_T2 = Tp;
+    g.conv_F2 = F2;
+    if (launch_gemm(g, stream)) return -1;
+  }
+  if (gemm(c2, m->embed, (int)M, ACT_NONE, OUT_F32, x, 1.f, stream)) return -1;
+
+  const float att_scale = 1.0f / sqrtf((float)dk);
+  // first pre-norm of block 0
+  if (launch_layernorm(x, m->enc[0].norm_ffm.g, m->enc[0].norm_ffm.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0,
+                       stream))
+    return -1;
+  for (int l = 0; l < L; ++l) {
+    EncLayer& E = m->enc[l];
+    // macaron FFN: x += 0.5 * W2 SiLU(W1 n)                                   (encoder_layer.py:200-207)
+    if (gemm(n, E.ffm1, (int)M, ACT_SILU, OUT_BF16, h, 1.f, stream)) return -1;
+    if (gemm(h, E.ffm2, (int)M, ACT_NONE, OUT_RESID_F32, x, 0.5f, stream)) return -1;
+    // rel-pos MHSA                                                            (encoder_layer.py:209-217)
+    if (launch_layernorm(x, E.norm_mha.g, E.norm_mha.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+    if (gemm(n, E.qkv, (int)M, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    {
+      AttnArgs a;
+      a.q = qkv;
+      a.k = qkv + d;
+      a.v = qkv + 2 * d;
+      a.p = pall + (size_t)l * d;
+      a.bias_u = E.pos_u;
+      a.bias_v = E.pos_v;
+      a.out = att;
+      a.ldq = a.ldk = a.ldv = 3 * d;
+      a.ldp = L * d;
+      a.ldo = d;
+      a.Bq = B;
+      a.Tq = Tp;
+      a.Tk = Tp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_lens;
+      a.scale = att_scale;
+      if (launch_attention(a, stream)) return -1;
+    }
+    if (gemm(att, E.out, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    // convolution module                                                       (encoder_layer.py:222-231)
+    if (launch_layernorm(x, E.norm_conv.g, E.norm_conv.b, 1e-5f, (int)M, d, n, nullptr, d_lens, Tp, 1, stream))
+      return -1;
+    if (gemm(n, E.pw1, (int)M, ACT_NONE, OUT_BF16, pw, 1.f, stream)) return -1;
+    if (launch_conv_mid(pw, E.dw_w, E.dw_b, E.cnorm.g, E.cnorm.b, E.bn_mean, E.bn_var, c.cnn_layer_norm, 1e-5f, cm, B,
+                        Tp, d, c.cnn_kernel, c.causal, stream))
+      return -1;
+    if (gemm(cm, E.pw2, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream, d_lens, Tp)) return -1;
+    // FFN (+ language-specific mix on the first / last block)                   (encoder_layer.py:233-242, 372-400)
+    if (launch_layernorm(x, E.norm_ff.g, E.norm_ff.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+    const bf16* ffn_in = n;
+    if (E.lsl) {
+      if (gemm(n, E.lang, (int)M, ACT_NONE, OUT_F32, y, 1.f, stream)) return -1;
+      if (launch_f32_to_bf16(y, ybf, M * d, stream)) return -1;
+      ffn_in = ybf;
+    }
+    if (gemm(ffn_in, E.ff1, (int)M, ACT_SILU, OUT_BF16, h, 1.f, stream)) return -1;
+    if (gemm(h, E.ff2, (int)M, ACT_NONE, OUT_RESID_F32, x, 0.5f, stream)) return -1;
+    // x = norm_final(x) (+ y) ; then the next block's first pre-norm, or after_norm for the last block
+    const bool last = (l == L - 1);
+    const Norm& nx = last ? m->after_norm : m->enc[l + 1].norm_ffm;
+    if (launch_double_layernorm(x, E.norm_final.g, E.norm_final.b, E.lsl ? y : nullptr, x, nx.g, nx.b, 1e-5f, (int)M,
+                                d, last ? nullptr : n, last ? d_enc_out : nullptr, stream))
+      return -1;
+  }
+  return 0;
+}
+
+__global__ void sub_column_kernel(float* x, long long ld, int rows, int col, float v) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) x[(long long)r * ld + col] -= v;
+}
+
+static int ctc_topk(rvb_model* m, const float* d_enc_out, int B, int Tp, int k, float blank_penalty, int blank_id,
+                    float* d_topk_val, int* d_topk_idx, float* d_logp, cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  const long long M = (long long)B * Tp;
+  const int d = c.d_model, V = c.vocab;
+  const int ldv = (V + 3) & ~3;
+  if (m->ws_encbf.ensure((size_t)M * d * 2) || m->ws_logits.ensure((size_t)M * ldv * 4)) return -1;
+  bf16* encbf = m->ws_encbf.as<bf16>();
+  float* logits = m->ws_logits.as<float>();
+  if (launch_f32_to_bf16(d_enc_out, encbf, M * d, stream)) return -1;
+  if (gemm(encbf, m->ctc, (int)M, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
+  if (blank_penalty > 0.f) {
+    sub_column_kernel<<<(int)((M + 255) / 256), 256, 0, stream>>>(logits, ldv, (int)M, blank_id, blank_penalty);
+    RVB_COUNT_LAUNCH();
+    RVB_CHECK_LAUNCH();
+  }
+  return launch_logsoftmax_topk(logits, ldv, (int)M, V, k, d_topk_val, d_topk_idx, d_logp, 1, stream);
+}
+
+// One pass of a (LanguageSpecific)TransformerDecoder over R = S * Lp rows (S sequences of Lp positions).
+static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int* d_enc_lens, int B, int Tp, int N,
+                        int Lp, const int* d_tokens, const int* d_seq_lens, const int* d_gather, float* d_scores,
+                        cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  const int d = c.d_model, H = c.dec_heads, dk = d / H, V = c.vocab;
+  const int S = B * N;
+  const long long R = (long long)S * Lp;
+  const long long Mem = (long long)B * Tp;
+  const int ldv = (V + 3) & ~3;
+  RVB_REQUIRE(R < (1ll << 31) && R * ldv < (1ll << 40), "rescoring: too many hypothesis rows");
+  DevBuf* w = m->ws_dec;
+  if (w[0].ensure((size_t)R * d * 4) || w[1].ensure((size_t)R * d * 2) || w[2].ensure((size_t)R * 3 * d * 2) ||
+      w[3].ensure((size_t)R * d * 2) || w[4].ensure((size_t)Mem * 2 * d * 2) ||
+      w[5].ensure((size_t)R * c.dec_ffn_dim * 2) || w[6].ensure((size_t)R * d * 2) ||
+      m->ws_logits.ensure((size_t)R * ldv * 4))
+    return -1;
+  float* x = w[0].as<float>();
+  bf16* n = w[1].as<bf16>();
+  bf16* qkv = w[2].as<bf16>();
+  bf16* att = w[3].as<bf16>();
+  bf16* kv = w[4].as<bf16>();
+  bf16* h = w[5].as<bf16>();
+  bf16* ybf = w[6].as<bf16>();
+  float* logits = m->ws_logits.as<float>();
+  const float scale = 1.0f / sqrtf((float)dk);
+  if (launch_embed_posenc(d_tokens, D.emb, S, Lp, d, x, stream)) return -1;
+  for (size_t l = 0; l < D.layers.size(); ++l) {
+    DecLayer& Ld = D.layers[l];
+    // masked self-attention (decoder_layer.py:95-110 / 286-301)
+    if (launch_layernorm(x, Ld.n1.g, Ld.n1.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+    if (gemm(n, Ld.qkv, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    {
+      AttnArgs a;
+      a.q = qkv;
+      a.k = qkv + d;
+      a.v = qkv + 2 * d;
+      a.out = att;
+      a.ldq = a.ldk = a.ldv = 3 * d;
+      a.ldo = d;
+      a.Bq = S;
+      a.Tq = Lp;
+      a.Tk = Lp;
+      a.H = H;
+      a.dk = dk;
+      a.q_lens = d_seq_lens;
+      a.causal = 1;
+      a.scale = scale;
+      if (launch_attention(a, stream)) return -1;
+    }
+    if (gemm(att, Ld.so, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    // source attention over the utterance's encoder output, K/V projected ONCE per utterance
+    if (launch_layernorm(x, Ld.n2.g, Ld.n2.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+    if (gemm(n, Ld.cq, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;  // q -> first d cols, ld = d
+    if (gemm(enc_bf, Ld.ckv, (int)Mem, ACT_NONE, OUT_BF16, kv, 1.f, stream)) return -1;
+    {
+      AttnArgs a;
+      a.q = qkv;
+      a.k = kv;
+      a.v = kv + d;
+      a.out = att;
+      a.ldq = d;
+      a.ldk = a.ldv = 2 * d;
+      a.ldo = d;
+      a.Bq = S;
+      a.Tq = Lp;
+      a.Tk = Tp;
+      a.H = H;
+      a.dk = dk;
+      a.q_per_kv = N;
+      a.k_lens = d_enc_lens;
+      a.scale = scale;
+      if (launch_attention(a, stream)) return -1;
+    }
+    if (gemm(att, Ld.co, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    // feed forward (ReLU), language-specific mix first on LSL layers
+    if (launch_layernorm(x, Ld.n3.g, Ld.n3.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+    const bf16* ffn_in = n;
+    if (Ld.lsl) {
+      if (gemm(n, Ld.lang, (int)R, ACT_NONE, OUT_BF16, ybf, 1.f, stream)) return -1;
+      ffn_in = ybf;
+    }
+    if (gemm(ffn_in, Ld.ff1, (int)R, ACT_RELU, OUT_BF16, h, 1.f, stream)) return -1;
+    if (gemm(h, Ld.ff2, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+  }
+  if (launch_layernorm(x, D.after.g, D.after.b, 1e-5f, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+  if (gemm(n, D.outl, (int)R, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
+  return launch_logsoftmax_gather(logits, ldv, (int)R, V, d_gather, 1, d_scores, stream);
+}
+
+static int attention_rescoring(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp,
+                               const int* h_tok, const int* h_len, int N, int max_len, const float* h_cat, int n_cat,
+                               float reverse_weight, float* h_l2r, float* h_r2l, cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  RVB_REQUIRE(m->finalized && m->dec_l.present, "attention_rescoring: model has no decoder");
+  const int d = c.d_model, eos = c.vocab - 1, sos = c.vocab - 1;  // asr_model.py:79-82
+  const int Lp = max_len + 1, S = B * N;
+  const long long R = (long long)S * Lp, Mem = (long long)B * Tp;
+  const bool use_r = reverse_weight > 0.f && m->dec_r.present && h_r2l != nullptr;
+  if (fold_lang(m, h_cat, n_cat, stream)) return -1;
+  // host-side staging: decoder inputs [sos, w_1..w_U, eos..] and per-position gather targets
+  const size_t ints = (size_t)R * 4 + S + B;
+  if (m->pin_b.ensure(ints * sizeof(int)) || m->ws_misc.ensure(ints * sizeof(int) + (size_t)R * 2 * sizeof(float)))
+    return -1;
+  int* hp = m->pin_b.as<int>();
+  int* tok_l = hp;
+  int* tok_r = hp + R;
+  int* gat_l = hp + 2 * R;
+  int* gat_r = hp + 3 * R;
+  int* slen = hp + 4 * R;
+  int* elen = slen + S;
+  for (int b = 0; b < B; ++b) elen[b] = h_enc_lens[b];
+  for (int s = 0; s < S; ++s) {
+    const int U = h_len[s] < 0 ? 0 : h_len[s];
+    RVB_REQUIRE(U <= max_len, "attention_rescoring: hypothesis longer than max_len");
+    const int* wv = h_tok + (size_t)s * max_len;
+    slen[s] = U + 1;
+    for (int j = 0; j < Lp; ++j) {
+      const size_t r = (size_t)s * Lp + j;
+      tok_l[r] = (j == 0) ? sos : (j <= U ? wv[j - 1] : eos);
+      tok_r[r] = (j == 0) ? sos : (j <= U ? wv[U - j] : eos);          // asr_model.py:921-949
+      gat_l[r] = (j < U) ? wv[j] : (j == U ? eos : -1);                // search.py:417-421
+      gat_r[r] = (j < U) ? wv[U - 1 - j] : (j == U ? eos : -1);        // search.py:424-430
+    }
+  }
+  int* dp = m->ws_misc.as<int>();
+  RVB_CHECK_CUDA(cudaMemcpyAsync(dp, hp, ints * sizeof(int), cudaMemcpyHostToDevice, stream));
+  float* d_sc_l = reinterpret_cast<float*>(dp + ints);
+  float* d_sc_r = d_sc_l + R;
+  if (m->ws_encbf.ensure((size_t)Mem * d * 2)) return -1;
+  bf16* encbf = m->ws_encbf.as<bf16>();
+  if (launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream)) return -1;
+  if (decoder_pass(m, m->dec_l, encbf, dp + 4 * R + S, B, Tp, N, Lp, dp, dp + 4 * R, dp + 2 * R, d_sc_l, stream))
+    return -1;
+  if (use_r &&
+      decoder_pass(m, m->dec_r, encbf, dp + 4 * R + S, B, Tp, N, Lp, dp + R, dp + 4 * R, dp + 3 * R, d_sc_r, stream))
+    return -1;
+  if (m->pin_c.ensure((size_t)R * 2 * sizeof(float))) return -1;
+  float* hs = m->pin_c.as<float>();
+  RVB_CHECK_CUDA(cudaMemcpyAsync(hs, d_sc_l, (size_t)R * (use_r ? 2 : 1) * sizeof(float), cudaMemcpyDeviceToHost,
+                                 stream));
+  RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
+  memcpy(h_l2r, hs, (size_t)R * sizeof(float));
+  if (use_r) {
+    // position pos of the reversed pass scores token w_{U-1-pos}: store it at index j = U-1-pos
+    for (int s = 0; s < S; ++s) {
+      const int U = h_len[s] < 0 ? 0 : h_len[s];
+      const float* src = hs + R + (size_t)s * Lp;
+      float* dst = h_r2l + (size_t)s * Lp;
+      for (int j = 0; j < Lp; ++j) dst[j] = 0.f;
+      for (int j = 0; j < U; ++j) dst[j] = src[U - 1 - j];
+      dst[U] = src[U];
+    }
+  }
+  return 0;
+}
+
+}  // namespace rvb
+
+// ================================================================================================================
+// C ABI
+extern "C" {
+
+RVB_API const char* rvb_last_error(void) { return rvb::last_error(); }
+RVB_API unsigned long long rvb_launch_count(void) { return rvb::g_launch_count; }
+RVB_API int rvb_set_gemm_impl(int impl) {
+  rvb::set_gemm_impl(impl);
+  return 0;
+}
+RVB_API int rvb_get_gemm_impl(void) { return rvb::get_gemm_impl(); }
+
+RVB_API rvb_model* rvb_model_create(const rvb_model_config* cfg) {
+  if (cfg == nullptr) {
+    rvb::set_error("rvb_model_create: null config");
+    return nullptr;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    rvb::set_error("rvb_model_create: no CUDA device (this library has no CPU path)");
+    return nullptr;
+  }
+  rvb_model* m = new rvb_model();
+  m->cfg = *cfg;
+  return m;
+}
+
+RVB_API int rvb_model_set_tensor(rvb_model* m, const char* name, const float* h_data, long long numel) {
+  RVB_REQUIRE(m && name && h_data && numel >= 0, "rvb_model_set_tensor: bad arguments");
+  RVB_REQUIRE(!m->finalized, "rvb_model_set_tensor: model already finalized");
+  m->host[name].assign(h_data, h_data + numel);
+  return 0;
+}
+
+RVB_API int rvb_model_finalize(rvb_model* m) {
+  RVB_REQUIRE(m != nullptr, "rvb_model_finalize: null model");
+  if (m->finalized) return 0;
+  return rvb::finalize_model(m);
+}
+
+RVB_API void rvb_model_destroy(rvb_model* m) {
+  if (!m) return;
+  for (void* p : m->owned) cudaFree(p);
+  DevBuf* bufs[] = {&m->ws_c1, &m->ws_c2, &m->ws_x, &m->ws_n, &m->ws_h, &m->ws_qkv, &m->ws_att, &m->ws_pw, &m->ws_cm,
+                    &m->ws_y, &m->ws_ybf, &m->ws_pe, &m->ws_pall, &m->ws_lens, &m->ws_encbf, &m->ws_logits,
+                    &m->ws_search, &m->ws_misc};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& b : m->ws_dec) b.release();
+  m->pin_a.release();
+  m->pin_b.release();
+  m->pin_c.release();
+  m->pin_d.release();
+  m->pin_e.release();
+  delete m;
+}
+
+RVB_API int rvb_encoder_out_frames(int T) {
+  if (T < 3) return 0;
+  int t1 = (T - 1) / 2;
+  return t1 < 1 ? 0 : (t1 - 1) / 2;
+}
+
+RVB_API int rvb_encoder_out_len(int feat_len, int T) {
+  // x_mask[:, :, 2::2][:, :, 2::2] (transformer/subsampling.py:226): output frame j is valid iff 4j + 6 < feat_len
+  int Tp = rvb_encoder_out_frames(T);
+  if (feat_len > T) feat_len = T;
+  int e = feat_len >= 7 ? (feat_len - 3) / 4 : 0;
+  return e < Tp ? e : Tp;
+}
+
+RVB_API long long rvb_fbank_num_frames(long long n_samples) { return n_samples < 400 ? 0 : 1 + (n_samples - 400) / 160; }
+
+RVB_API int rvb_fbank_f32(const float* d_wave, long long n_samples, float* d_feats, long long n_frames, void* stream) {
+  return rvb::launch_fbank(d_wave, n_samples, d_feats, n_frames, (cudaStream_t)stream);
+}
+RVB_API int rvb_fbank_i16(const short* d_wave, long long n_samples, float* d_feats, long long n_frames, void* stream) {
+  return rvb::launch_fbank_i16(d_wave, n_samples, d_feats, n_frames, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
+                        const float* h_cat_embs, int n_cat, float* d_enc_out, int* h_enc_lens, void* stream) {
+  RVB_REQUIRE(m && d_feats && h_feat_lens && d_enc_out && B > 0, "rvb_encoder_forward: bad arguments");
+  return rvb::encoder_forward(m, d_feats, h_feat_lens, B, T, h_cat_embs, n_cat, d_enc_out, h_enc_lens,
+                              (cudaStream_t)stream);
+}
+
+RVB_API int rvb_ctc_topk(rvb_model* m, const float* d_enc_out, int B, int Tp, int k, float blank_penalty, int blank_id,
+                 float* d_topk_val, int* d_topk_idx, float* d_logp, void* stream) {
+  RVB_REQUIRE(m && m->finalized && d_enc_out && d_topk_val && d_topk_idx && B > 0 && Tp > 0, "rvb_ctc_topk: bad arguments");
+  return rvb::ctc_topk(m, d_enc_out, B, Tp, k, blank_penalty, blank_id, d_topk_val, d_topk_idx, d_logp,
+                       (cudaStream_t)stream);
+}
+
+RVB_API int rvb_logp_topk(const float* d_logp, int rows, int V, int k, float* d_topk_val, int* d_topk_idx, void* stream) {
+  return rvb::launch_logsoftmax_topk(d_logp, V, rows, V, k, d_topk_val, d_topk_idx, nullptr, 0, (cudaStream_t)stream);
+}
+
+static rvb::DevBuf g_search_ws, g_search_out;
+static rvb::HostPinned g_search_pin;
+
+RVB_API int rvb_ctc_greedy_search(const int* d_topk_idx, int k, const int* h_enc_lens, int B, int Tp, int blank_id,
+                          int* h_tokens, int* h_lens, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RVB_REQUIRE(d_topk_idx && h_enc_lens && h_tokens && h_lens && B > 0 && Tp > 0, "rvb_ctc_greedy_search: bad arguments");
+  const size_t n_out = (size_t)B * Tp + B;
+  if (g_search_out.ensure((n_out + B) * sizeof(int)) || g_search_pin.ensure((n_out + B) * sizeof(int))) return -1;
+  int* d_lens = g_search_out.as<int>();
+  int* d_tok = d_lens + B;
+  int* d_olen = d_tok + (size_t)B * Tp;
+  int* hp = g_search_pin.as<int>();
+  memcpy(hp, h_enc_lens, sizeof(int) * B);
+  RVB_CHECK_CUDA(cudaMemcpyAsync(d_lens, hp, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+  if (rvb::launch_ctc_greedy(d_topk_idx, k, d_lens, B, Tp, blank_id, d_tok, d_olen, stream)) return -1;
+  RVB_CHECK_CUDA(cudaMemcpyAsync(hp + B, d_tok, n_out * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
+  memcpy(h_tokens, hp + B, (size_t)B * Tp * sizeof(int));
+  memcpy(h_lens, hp + B + (size_t)B * Tp, sizeof(int) * B);
+  return 0;
+}
+
+RVB_API int rvb_ctc_prefix_beam_search(const float* d_topk_val, const int* d_topk_idx, int k, const int* h_enc_lens, int B,
+                               int Tp, int beam, int blank_id, int max_len, int* h_tokens, int* h_times, int* h_lens,
+                               double* h_scores, int* h_nhyp, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  RVB_REQUIRE(d_topk_val && d_topk_idx && h_enc_lens && h_tokens && h_times && h_lens && h_scores && h_nhyp && B > 0 &&
+                  Tp > 0 && max_len > 0,
+              "rvb_ctc_prefix_beam_search: bad arguments");
+  const size_t ws_bytes = rvb::prefix_beam_workspace_bytes(B, Tp, beam);
+  const size_t n_tok = (size_t)B * beam * max_len;
+  // device outputs: lens(B) | tokens | times | out_lens (B*beam*2) | nhyp (B) | scores (B*beam doubles, 8-aligned)
+  const size_t ints = B + 2 * n_tok + (size_t)B * beam * 2 + B;
+  const size_t ints_al = (ints + 1) & ~(size_t)1;
+  const size_t out_bytes = ints_al * sizeof(int) + (size_t)B * beam * sizeof(double);
+  if (g_search_ws.ensure(ws_bytes) || g_search_out.ensure(out_bytes) || g_search_pin.ensure(out_bytes)) return -1;
+  int* d_lens = g_search_out.as<int>();
+  int* d_tok = d_lens + B;
+  int* d_tim = d_tok + n_tok;
+  int* d_olen = d_tim + n_tok;
+  int* d_nhyp = d_olen + (size_t)B * beam * 2;
+  double* d_sc = reinterpret_cast<double*>(g_search_out.as<int>() + ints_al);
+  int* hp = g_search_pin.as<int>();
+  memcpy(hp, h_enc_lens, sizeof(int) * B);
+  RVB_CHECK_CUDA(cudaMemcpyAsync(d_lens, hp, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+  RVB_CHECK_CUDA(cudaMemsetAsync(d_tok, 0, (ints - B) * sizeof(int), stream));
+  if (rvb::launch_ctc_prefix_beam(d_topk_val, d_topk_idx, k, d_lens, B, Tp, beam, blank_id, g_search_ws.p, g_search_ws.cap,
+                                  max_len, d_tok, d_tim, d_olen, d_sc, d_nhyp, stream))
+    return -1;
+  RVB_CHECK_CUDA(cudaMemcpyAsync(hp, g_search_out.p, out_bytes, cudaMemcpyDeviceToHost, stream));
+  RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
+  memcpy(h_tokens, hp + B, n_tok * sizeof(int));
+  memcpy(h_times, hp + B + n_tok, n_tok * sizeof(int));
+  memcpy(h_lens, hp + B + 2 * n_tok, (size_t)B * beam * 2 * sizeof(int));
+  memcpy(h_nhyp, hp + B + 2 * n_tok + (size_t)B * beam * 2, sizeof(int) * B);
+  memcpy(h_scores, hp + ints_al, (size_t)B * beam * sizeof(double));
+  for (size_t i = 0; i < (size_t)B * beam; ++i) {
+    RVB_REQUIRE(h_lens[2 * i] <= max_len && h_lens[2 * i + 1] <= max_len,
+                "rvb_ctc_prefix_beam_search: hypothesis of %d tokens exceeds max_len=%d", h_lens[2 * i], max_len);
+  }
+  return 0;
+}
+
+RVB_API int rvb_attention_rescoring(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp,
+                            const int* h_hyp_tokens, const int* h_hyp_lens, int N, int max_len,
+                            const float* h_cat_embs, int n_cat, float reverse_weight, float* h_l2r, float* h_r2l,
+                            void* stream) {
+  RVB_REQUIRE(m && d_enc_out && h_enc_lens && h_hyp_tokens && h_hyp_lens && h_l2r && B > 0 && N > 0 && max_len >= 0,
+              "rvb_attention_rescoring: bad arguments");
+  return rvb::attention_rescoring(m, d_enc_out, h_enc_lens, B, Tp, h_hyp_tokens, h_hyp_lens, N, max_len, h_cat_embs,
+                                  n_cat, reverse_weight, h_l2r, h_r2l, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_gemm_bf16(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int act, int out_mode,
+                  float alpha, void* d_out, int ldo, void* stream) {
+  rvb::GemmArgs g;
+  g.A = reinterpret_cast<const rvb::bf16*>(d_A);
+  g.W = reinterpret_cast<const rvb::bf16*>(d_W);
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.bias = d_bias;
+  g.act = act;
+  g.out_mode = out_mode;
+  g.alpha = alpha;
+  g.out = d_out;
+  g.ldo = ldo;
+  return rvb::launch_gemm(g, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, float eps, int M, int d,
+                  void* d_out_bf16, float* d_out_f32, void* stream) {
+  return rvb::launch_layernorm(d_x, d_gamma, d_beta, eps, M, d, reinterpret_cast<rvb::bf16*>(d_out_bf16), d_out_f32,
+                               nullptr, 0, 0, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_attention(const void* d_q, const void* d_k, const void* d_v, const void* d_p, const float* d_bias_u,
+                  const float* d_bias_v, void* d_out, int ldq, int ldk, int ldv, int ldp, int ldo, int Bq, int Tq, int Tk,
+                  int H, int dk, int q_per_kv, const int* d_k_lens, const int* d_q_lens, int causal, float scale,
+                  void* stream) {
+  rvb::AttnArgs a;
+  a.q = reinterpret_cast<const rvb::bf16*>(d_q);
+  a.k = reinterpret_cast<const rvb::bf16*>(d_k);
+  a.v = reinterpret_cast<const rvb::bf16*>(d_v);
+  a.p = reinterpret_cast<const rvb::bf16*>(d_p);
+  a.bias_u = d_bias_u;
+  a.bias_v = d_bias_v;
+  a.out = reinterpret_cast<rvb::bf16*>(d_out);
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldp = ldp; a.ldo = ldo;
+  a.Bq = Bq; a.Tq = Tq; a.Tk = Tk; a.H = H; a.dk = dk;
+  a.q_per_kv = q_per_kv;
+  a.k_lens = d_k_lens; a.q_lens = d_q_lens;
+  a.causal = causal;
+  a.scale = scale;
+  return rvb::launch_attention(a, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_f32_to_bf16(const float* d_x, void* d_out, long long n, void* stream) {
+  return rvb::launch_f32_to_bf16(d_x, reinterpret_cast<rvb::bf16*>(d_out), n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

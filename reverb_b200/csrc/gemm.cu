@@ -1,0 +1,505 @@
+// reverb_b200 — persistent, warp-specialised tcgen05 + TMA GEMM for sm_100a.
+//
+//   C[M,N] = A[M,K] . W[N,K]^T  (+bias, activation, residual)      A, W: bf16, K-major; fp32 accumulate in TMEM
+//
+// One kernel serves every dense layer on the hot path: the Conformer FFN / attention projections / pointwise convs
+// (reference: asr/wenet/transformer/positionwise_feed_forward.py:47-55, attention.py:52-79, convolution.py:129,139),
+// the CTC / decoder output layers (ctc.py:106-114, decoder.py:164-166) and — with `conv_mode` — the second
+// Conv2d(d,d,3,stride 2) of Conv2dSubsampling4 (subsampling.py:186-189) as an implicit GEMM whose A tiles are fetched
+// straight out of the channels-last conv1 activation by 4-D TMA boxes (no im2col buffer).
+//
+// Structure per CTA (192 threads, 1 CTA / SM, grid = #SMs, static round-robin tile scheduler):
+//   warp 0 / lane 0 : TMA producer   — fills a STAGES-deep ring of {A 128x64, W BNx64} bf16 tiles (SWIZZLE_128B)
+//   warp 1 / lane 0 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x 4 per stage;
+//                                       tcgen05.commit frees smem stages and publishes finished accumulators
+//   warps 2..5      : epilogue       — tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x BN columns),
+//                                       bias / ReLU / SiLU / residual(+row mask) fused, vectorised global stores
+// so tile i's epilogue overlaps tile i+1's main loop.
+#include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "kernels.h"
+
+namespace rvb {
+
+static int g_gemm_impl = -1;
+void set_gemm_impl(int impl) { g_gemm_impl = impl; }
+int get_gemm_impl() {
+  if (g_gemm_impl < 0) {
+    const char* e = getenv("RVB_GEMM");
+    g_gemm_impl = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+  }
+  return g_gemm_impl;
+}
+
+struct GemmKParams {
+  int M, N, K, num_k_blocks;
+  int tiles_n, num_tiles;
+  const float* bias;
+  int act, out_mode;
+  void* out;
+  long long ldo;
+  float alpha;
+  const int* row_lens;
+  int rows_per_batch;
+  int conv_mode, conv_T2, conv_F2, conv_tt, conv_cblocks;
+  // simt fallback only
+  const bf16* A;
+  const bf16* W;
+  long long lda, ldw;
+  int conv_T1h, conv_F1, conv_C;
+};
+
+struct TileCoord {
+  int n0;        // first output column
+  int row0;      // plain: first row; conv: t0
+  int b, f;      // conv only
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const GemmKParams& p, int tile, int BN) {
+  TileCoord t;
+  int nb = tile % p.tiles_n;
+  int mt = tile / p.tiles_n;
+  t.n0 = nb * BN;
+  if (p.conv_mode) {
+    t.f = mt % p.conv_F2;
+    int r = mt / p.conv_F2;
+    t.row0 = (r % p.conv_tt) * 128;
+    t.b = r / p.conv_tt;
+  } else {
+    t.row0 = mt * 128;
+    t.b = 0;
+    t.f = 0;
+  }
+  return t;
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.0f);
+  if (act == ACT_SILU) return silu_f(v);
+  return v;
+}
+
+// One thread stores 32 consecutive output columns [n0, n0+32) of one output row.
+__device__ __forceinline__ void store_chunk(const GemmKParams& p, long long out_row, int n0, const uint32_t* acc) {
+  float v[32];
+  const bool full = (n0 + 32 <= p.N);
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float x = __uint_as_float(acc[j]);
+    int n = n0 + j;
+    if (p.bias != nullptr && (full || n < p.N)) x += __ldg(p.bias + n);
+    v[j] = apply_act(x, p.act);
+  }
+  if (p.out_mode == OUT_BF16) {
+    bf16* o = reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + n0;
+    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 u;
+        u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        reinterpret_cast<uint4*>(o)[j] = u;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) o[j] = __float2bfloat16(v[j]);
+    }
+  } else if (p.out_mode == OUT_F32) {
+    float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
+    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) o[j] = v[j];
+    }
+  } else {  // OUT_RESID_F32
+    float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
+    if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 r = reinterpret_cast<float4*>(o)[j];
+        r.x += p.alpha * v[4 * j];
+        r.y += p.alpha * v[4 * j + 1];
+        r.z += p.alpha * v[4 * j + 2];
+        r.w += p.alpha * v[4 * j + 3];
+        reinterpret_cast<float4*>(o)[j] = r;
+      }
+    } else {
+      for (int j = 0; j < 32; ++j)
+        if (n0 + j < p.N) o[j] += p.alpha * v[j];
+    }
+  }
+}
+
+// Maps (tile, row-in-tile) to the output row; returns -1 when the row must not be written.
+__device__ __forceinline__ long long output_row(const GemmKParams& p, const TileCoord& t, int r) {
+  if (p.conv_mode) {
+    int tp = t.row0 + r;
+    if (tp >= p.conv_T2) return -1;
+    return ((long long)t.b * p.conv_T2 + tp) * p.conv_F2 + t.f;
+  }
+  int m = t.row0 + r;
+  if (m >= p.M) return -1;
+  if (p.row_lens != nullptr) {
+    int b = m / p.rows_per_batch;
+    int pos = m - b * p.rows_per_batch;
+    if (pos >= __ldg(p.row_lens + b)) return -1;
+  }
+  return m;
+}
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int BK = 64;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr uint32_t B_BYTES = BN * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const GemmKParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int nkb = p.num_k_blocks;
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer
+    uint32_t stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      TileCoord t = decode_tile(p, tile, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+        if (p.conv_mode) {
+          int tap = kb / p.conv_cblocks;
+          int cb = kb - tap * p.conv_cblocks;
+          int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, 2 * t.f + kw, t.row0 + (kh >> 1),
+                      t.b * 2 + (kh & 1));
+        } else {
+          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64, t.row0, 0, 0);
+        }
+        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, t.n0);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (single thread)
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sA + stage * Cfg::A_BYTES));
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // advance 16 bf16 = 32 B along K inside the 128 B swizzle span: +2 in the (addr >> 4) field
+          umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit(&tfull[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------ epilogue warps
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    uint32_t as = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      TileCoord t = decode_tile(p, tile, BN);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int r = q * 32 + lane;
+      const long long orow = output_row(p, t, r);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (t.n0 + c >= p.N) break;
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, acc);
+        tmem_ld_wait();
+        if (orow >= 0) store_chunk(p, orow, t.n0 + c, acc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Debug / bring-up kernel: same contract on plain CUDA cores (RVB_GEMM=simt).  Never used by the benchmarks.
+__device__ __forceinline__ float load_a_elem(const GemmKParams& p, const TileCoord& t, int r, int k) {
+  if (k >= p.K) return 0.0f;
+  if (p.conv_mode) {
+    int tp = t.row0 + r;
+    if (tp >= p.conv_T2) return 0.0f;
+    int tap = k / p.conv_C;
+    int c = k - tap * p.conv_C;
+    int kh = tap / 3, kw = tap - kh * 3;
+    long long idx = (((long long)(t.b * 2 + (kh & 1)) * p.conv_T1h + (tp + (kh >> 1))) * p.conv_F1 + (2 * t.f + kw)) *
+                        p.conv_C + c;
+    return __bfloat162float(p.A[idx]);
+  }
+  int m = t.row0 + r;
+  if (m >= p.M) return 0.0f;
+  return __bfloat162float(p.A[(long long)m * p.lda + k]);
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmKParams p) {
+  // tile: 128 rows x 32 cols; thread (ty 0..31 , tx 0..7) -> 4 rows x 4 cols ... kept simple: 128x32 outputs,
+  // 256 threads, each thread: 16 outputs (4 rows x 4 cols)
+  __shared__ float sA[128][17];
+  __shared__ float sW[32][17];
+  for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    // here tiles_n counts 32-wide column tiles
+    TileCoord t = decode_tile(p, tile, 32);
+    const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+      for (int e = threadIdx.x; e < 128 * 16; e += 256) {
+        int r = e >> 4, kk = e & 15;
+        sA[r][kk] = load_a_elem(p, t, r, k0 + kk);
+      }
+      for (int e = threadIdx.x; e < 32 * 16; e += 256) {
+        int n = e >> 4, kk = e & 15;
+        int gn = t.n0 + n, gk = k0 + kk;
+        sW[n][kk] = (gn < p.N && gk < p.K) ? __bfloat162float(p.W[(long long)gn * p.ldw + gk]) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        float a[4], w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = sA[ty * 4 + i][kk];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = sW[tx * 4 + j][kk];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+    for (int i = 0; i < 4; ++i) {
+      long long orow = output_row(p, t, ty * 4 + i);
+      if (orow < 0) continue;
+      for (int j = 0; j < 4; ++j) {
+        int n = t.n0 + tx * 4 + j;
+        if (n >= p.N) continue;
+        float x = acc[i][j];
+        if (p.bias) x += p.bias[n];
+        x = apply_act(x, p.act);
+        if (p.out_mode == OUT_BF16)
+          reinterpret_cast<bf16*>(p.out)[orow * p.ldo + n] = __float2bfloat16(x);
+        else if (p.out_mode == OUT_F32)
+          reinterpret_cast<float*>(p.out)[orow * p.ldo + n] = x;
+        else
+          reinterpret_cast<float*>(p.out)[orow * p.ldo + n] += p.alpha * x;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+
+static int get_encode_fn() {
+  if (g_encode) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  RVB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  RVB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  return 0;
+}
+
+static int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                     const cuuint32_t* box) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), dims, strides_bytes, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RVB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with %d (rank %d dims %llu %llu)", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1]);
+  return 0;
+}
+
+static int g_num_sms = 0;
+
+template <int BN>
+static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tmA, tmB;
+  const long long lda = a.lda ? a.lda : a.K, ldw = a.ldw ? a.ldw : a.K;
+  if (a.conv_mode) {
+    cuuint64_t dims[4] = {(cuuint64_t)a.conv_C, (cuuint64_t)a.conv_F1, (cuuint64_t)a.conv_T1h,
+                          (cuuint64_t)(2 * a.conv_B)};
+    cuuint64_t str[3] = {(cuuint64_t)a.conv_C * 2, (cuuint64_t)a.conv_F1 * a.conv_C * 2,
+                         (cuuint64_t)a.conv_T1h * a.conv_F1 * a.conv_C * 2};
+    cuuint32_t box[4] = {64, 1, 128, 1};
+    if (make_tmap(&tmA, a.A, 4, dims, str, box)) return -1;
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)a.K, (cuuint64_t)a.M, 1, 1};
+    cuuint64_t str[3] = {(cuuint64_t)lda * 2, (cuuint64_t)lda * 2 * a.M, (cuuint64_t)lda * 2 * a.M};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    if (make_tmap(&tmA, a.A, 4, dims, str, box)) return -1;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.N};
+    cuuint64_t str[1] = {(cuuint64_t)ldw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)BN};
+    if (make_tmap(&tmB, a.W, 2, dims, str, box)) return -1;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    RVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)Cfg::SMEM_BYTES));
+    attr_set = true;
+  }
+  p.tiles_n = (a.N + BN - 1) / BN;
+  int tiles_m = a.conv_mode ? a.conv_B * a.conv_F2 * p.conv_tt : (a.M + 127) / 128;
+  p.num_tiles = tiles_m * p.tiles_n;
+  int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+  RVB_REQUIRE(a.A && a.W && a.out, "gemm: null pointer");
+  RVB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
+  if (g_num_sms == 0) {
+    int dev = 0;
+    RVB_CHECK_CUDA(cudaGetDevice(&dev));
+    RVB_CHECK_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GemmKParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = a.M;
+  p.N = a.N;
+  p.K = a.K;
+  p.num_k_blocks = (a.K + 63) / 64;
+  p.bias = a.bias;
+  p.act = a.act;
+  p.out_mode = a.out_mode;
+  p.out = a.out;
+  p.ldo = a.ldo ? a.ldo : a.N;
+  p.alpha = a.alpha;
+  p.row_lens = a.row_lens;
+  p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
+  p.conv_mode = a.conv_mode;
+  p.A = a.A;
+  p.W = a.W;
+  p.lda = a.lda ? a.lda : a.K;
+  p.ldw = a.ldw ? a.ldw : a.K;
+  if (a.conv_mode) {
+    RVB_REQUIRE(a.conv_C % 64 == 0, "conv implicit GEMM needs C %% 64 == 0 (C=%d)", a.conv_C);
+    RVB_REQUIRE(a.K == 9 * a.conv_C && a.M == a.conv_B * a.conv_F2 * a.conv_T2, "conv implicit GEMM: bad M/K");
+    p.conv_T2 = a.conv_T2;
+    p.conv_F2 = a.conv_F2;
+    p.conv_tt = (a.conv_T2 + 127) / 128;
+    p.conv_cblocks = a.conv_C / 64;
+    p.conv_T1h = a.conv_T1h;
+    p.conv_F1 = a.conv_F1;
+    p.conv_C = a.conv_C;
+  }
+  if (get_gemm_impl() == 1) {
+    p.tiles_n = (a.N + 31) / 32;
+    int tiles_m = a.conv_mode ? a.conv_B * a.conv_F2 * p.conv_tt : (a.M + 127) / 128;
+    p.num_tiles = tiles_m * p.tiles_n;
+    int grid = p.num_tiles < 148 * 8 ? p.num_tiles : 148 * 8;
+    gemm_simt_kernel<<<grid, 256, 0, stream>>>(p);
+    RVB_COUNT_LAUNCH();
+    RVB_CHECK_LAUNCH();
+    return 0;
+  }
+  RVB_REQUIRE((reinterpret_cast<uintptr_t>(a.A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.W) & 15) == 0,
+              "gemm: operands must be 16-byte aligned");
+  RVB_REQUIRE((p.lda * 2) % 16 == 0 && (p.ldw * 2) % 16 == 0, "gemm: leading dimensions must be multiples of 8");
+  if (get_encode_fn()) return -1;
+  if (a.N > 128) return launch_tc<256>(a, p, stream);
+  return launch_tc<128>(a, p, stream);
+}
+
+}  // namespace rvb

@@ -1,0 +1,118 @@
+// reverb_b200 — host-side launchers of the sm_100a kernels (internal; the public boundary is
+// include/rvb_b200.h).  Every launcher enqueues on the given stream and returns 0 / <0.
+#pragma once
+#include "common.cuh"
+
+namespace rvb {
+
+// ------------------------------------------------------------------ GEMM (gemm.cu)
+enum GemmAct { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
+enum GemmOut {
+  OUT_BF16 = 0,      // out_bf16[m, n] = act(acc + bias)
+  OUT_F32 = 1,       // out_f32[m, n]  = act(acc + bias)
+  OUT_RESID_F32 = 2  // out_f32[m, n] += alpha * act(acc + bias)   (rows masked by row_lens are left untouched)
+};
+
+struct GemmArgs {
+  // C[M,N] = A[M,K] * W[N,K]^T ; A, W bf16 row-major (K contiguous)
+  const bf16* A = nullptr;
+  const bf16* W = nullptr;
+  int M = 0, N = 0, K = 0;
+  int lda = 0;  // elements; 0 -> K
+  int ldw = 0;  // elements; 0 -> K
+  const float* bias = nullptr;
+  int act = ACT_NONE;
+  int out_mode = OUT_BF16;
+  void* out = nullptr;
+  int ldo = 0;  // elements; 0 -> N
+  float alpha = 1.0f;
+  // optional second output for OUT_RESID_F32: nothing (kept simple)
+  // row masking: row m belongs to batch m / rows_per_batch, position m % rows_per_batch;
+  // valid iff position < row_lens[batch].  nullptr -> all rows valid.
+  const int* row_lens = nullptr;
+  int rows_per_batch = 0;
+  // conv2d-subsampling second conv as implicit GEMM (A is the conv1 activation, see subsample.cu):
+  //   A logical layout (B, 2, T1h, F1, C) bf16 (time split by parity), M = B*F2*T2 rows ordered (b, f, t'),
+  //   K = 9*C ordered (kh, kw, c); output row (b, t', f) -> out[((b*T2 + t')*F2 + f) * ldo + n]
+  int conv_mode = 0;
+  int conv_B = 0, conv_T1h = 0, conv_F1 = 0, conv_C = 0, conv_T2 = 0, conv_F2 = 0;
+};
+
+int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+// 0 = tcgen05/TMA kernel (default), 1 = plain CUDA-core debug kernel (env RVB_GEMM=simt)
+void set_gemm_impl(int impl);
+int get_gemm_impl();
+
+// ------------------------------------------------------------------ fbank (fbank.cu)
+int launch_fbank(const float* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream);
+// int16 PCM input variant (the host API's H2D format)
+int launch_fbank_i16(const short* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream);
+
+// ------------------------------------------------------------------ norms / conv pieces (elementwise.cu)
+// y = LN(x) * gamma + beta ; rows with position >= row_lens[batch] are written as 0 when mask_rows != 0.
+// out_bf16 and/or out_f32 may be null.
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M, int d, bf16* out_bf16,
+                     float* out_f32, const int* row_lens, int rows_per_batch, int mask_rows, cudaStream_t stream);
+// x2 = LN_a(x) (fp32, in place allowed) ; n = LN_b(x2) -> bf16.  (norm_final of block i fused with the first
+// pre-norm of block i+1.)  y_add (optional, fp32) is added to x2 after LN_a (LSL "x = x + y").
+int launch_double_layernorm(const float* x, const float* ga, const float* ba, const float* y_add, float* x2,
+                            const float* gb, const float* bb, float eps, int M, int d, bf16* n_out,
+                            float* n_out_f32, cudaStream_t stream);
+// CMVN + Conv2d(1->C, 3x3, stride 2) + ReLU, output bf16 (B, 2, T1h, F1, C) (time split by parity)
+int launch_conv1(const float* feats, const float* mean, const float* istd, const float* w /*[C][9]*/,
+                 const float* bias, bf16* out, int B, int T, int F, int C, int T1, int T1h, int F1,
+                 cudaStream_t stream);
+// GLU + depthwise conv (K taps) + LayerNorm|BatchNorm(eval) + SiLU on (B, T, 2C) bf16 -> (B, T, C) bf16
+int launch_conv_mid(const bf16* x, const float* dw_w /*[C][K]*/, const float* dw_b, const float* norm_w,
+                    const float* norm_b, const float* bn_mean, const float* bn_var, int use_layer_norm, float eps,
+                    bf16* out, int B, int T, int C, int K, int causal, cudaStream_t stream);
+// x[m, :] = x[m, :] * scale   (fp32 -> fp32 in place) and optional bf16 copy
+int launch_scale_cast(const float* x, float scale, float* out_f32, bf16* out_bf16, long long n, cudaStream_t stream);
+int launch_f32_to_bf16(const float* x, bf16* out, long long n, cudaStream_t stream);
+// out = sum_i c[i] * in_i   (fold of the language-specific linears; n elements, up to 8 inputs)
+int launch_weighted_sum_bf16(const float* const* ins, const float* coef, int n_in, long long n, bf16* out_bf16,
+                             float* out_f32, cudaStream_t stream);
+// decoder input: x[r, :] = emb[tok[r], :] * sqrt(d) + pe[pos(r), :]   (fp32), r over (N, L)
+int launch_embed_posenc(const int* tokens, const float* emb, int N, int L, int d, float* out, cudaStream_t stream);
+// sinusoidal table pe[pos, :] for pos < T (fp32 (T, d) and bf16 copy)
+int launch_sinusoid(int T, int d, float* out_f32, bf16* out_bf16, cudaStream_t stream);
+
+// ------------------------------------------------------------------ attention (attention.cu)
+struct AttnArgs {
+  const bf16* q = nullptr;  // (Bq, Tq, H, dk) with row stride ldq elements
+  const bf16* k = nullptr;  // (Bk, Tk, H, dk) row stride ldk
+  const bf16* v = nullptr;  // (Bk, Tk, H, dk) row stride ldv
+  const bf16* p = nullptr;  // optional rel-pos keys (Tk, H, dk), row stride ldp (shared by the batch)
+  const float* bias_u = nullptr;  // (H, dk) added to q for the content term (with p)
+  const float* bias_v = nullptr;  // (H, dk) added to q for the position term (with p)
+  bf16* out = nullptr;            // (Bq, Tq, H*dk) row stride ldo
+  int ldq = 0, ldk = 0, ldv = 0, ldp = 0, ldo = 0;
+  int Bq = 0, Tq = 0, Tk = 0, H = 0, dk = 0;
+  int q_per_kv = 1;               // kv batch = q batch / q_per_kv
+  const int* k_lens = nullptr;    // per kv batch valid key count (nullptr -> Tk)
+  const int* q_lens = nullptr;    // per q batch: causal-with-length mask (key j valid iff j <= i and j < q_lens[b])
+  int causal = 0;
+  float scale = 1.0f;
+};
+int launch_attention(const AttnArgs& a, cudaStream_t stream);
+
+// ------------------------------------------------------------------ CTC head / searches (ctc.cu)
+// per row: logp = log_softmax(logits) ; top-k (k <= 16) of logp with indices ; optional full logp output.
+int launch_logsoftmax_topk(const float* logits, int ld, int M, int V, int k, float* topk_val, int* topk_idx,
+                           float* logp_out /*nullable, ld = V*/, int apply_softmax, cudaStream_t stream);
+// greedy: per utterance, arg-max ids (top-1) with padded frames -> blank, collapsed (repeats merged, blanks dropped)
+int launch_ctc_greedy(const int* top1_idx, int idx_stride, const int* lens, int B, int T, int blank, int* out_tokens,
+                      int* out_lens, cudaStream_t stream);
+struct PrefixBeamWorkspace;
+size_t prefix_beam_workspace_bytes(int B, int T, int beam);
+// CTC prefix beam search, one CTA per utterance, fp64 scores (reference: transformer/search.py:124-248)
+int launch_ctc_prefix_beam(const float* topk_val, const int* topk_idx, int k, const int* lens, int B, int T, int beam,
+                           int blank, void* workspace, size_t workspace_bytes, int max_len, int* out_tokens,
+                           int* out_times, int* out_lens, double* out_scores, int* out_nhyp, cudaStream_t stream);
+
+// ------------------------------------------------------------------ rescoring (ctc.cu)
+// per row r: lse = logsumexp(logits[r, :V]); out[r, j] = logits[r, gather_idx[r*G + j]] - lse  (idx < 0 -> 0)
+int launch_logsoftmax_gather(const float* logits, int ld, int M, int V, const int* gather_idx, int G, float* out,
+                             cudaStream_t stream);
+
+}  // namespace rvb

@@ -1,0 +1,229 @@
+"""Host-side handle of the native model plan (librvb_b200.so): PyTorch tensors in, PyTorch
+tensors / Python lists out.  PyTorch is used for device memory and streams only; every
+FLOP of the hot path runs in the hand-written sm_100a kernels behind the C ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import ModelConfig, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _np_ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def model_config_from_yaml(configs: Dict, vocab: int) -> ModelConfig:
+    """config.yaml -> rvb_model_config.  Only the architecture the hot path supports
+    (conformer encoder with conv2d input / rel_pos attention, (bi)transformer decoder) is accepted."""
+    ec, dc = configs["encoder_conf"], configs.get("decoder_conf", {})
+    if configs.get("encoder", "conformer") != "conformer":
+        raise ValueError(f"unsupported encoder type {configs.get('encoder')!r} (only 'conformer')")
+    if ec.get("input_layer", "conv2d") != "conv2d":
+        raise ValueError("only input_layer: conv2d (Conv2dSubsampling4) is supported")
+    if ec.get("pos_enc_layer_type", "rel_pos") != "rel_pos" or \
+            ec.get("selfattention_layer_type", "rel_selfattn") != "rel_selfattn":
+        raise ValueError("only rel_pos / rel_selfattn encoders are supported")
+    if ec.get("activation_type", "swish") != "swish":
+        raise ValueError("only activation_type: swish is supported")
+    if not ec.get("macaron_style", True) or not ec.get("use_cnn_module", True) or not ec.get("normalize_before", True):
+        raise ValueError("only macaron-style pre-norm Conformer blocks with the CNN module are supported")
+    ds = configs.get("dataset_conf", {})
+    num_langs = ds.get("cat_emb_conf", {}).get("emb_len", 0) if ds.get("pass_cat_emb", False) else 0
+    r_blocks = dc.get("r_num_blocks", 0)
+    cfg = ModelConfig()
+    cfg.input_dim = configs.get("input_dim", 80)
+    cfg.d_model = ec.get("output_size", 256)
+    cfg.heads = ec.get("attention_heads", 4)
+    cfg.ffn_dim = ec.get("linear_units", 2048)
+    cfg.num_blocks = ec.get("num_blocks", 6)
+    cfg.cnn_kernel = ec.get("cnn_module_kernel", 15)
+    cfg.causal = int(bool(ec.get("causal", False)))
+    cfg.cnn_layer_norm = int(ec.get("cnn_module_norm", "batch_norm") == "layer_norm")
+    cfg.num_langs = num_langs
+    cfg.vocab = vocab
+    cfg.dec_heads = dc.get("attention_heads", 4)
+    cfg.dec_ffn_dim = dc.get("linear_units", 2048)
+    cfg.dec_blocks = dc.get("num_blocks", 6)
+    cfg.r_dec_blocks = r_blocks
+    return cfg
+
+
+class Engine:
+    """Owns one `rvb_model` (packed weights + workspace) on one CUDA device."""
+
+    def __init__(self, configs: Dict, state_dict: Dict[str, torch.Tensor], vocab: int, device: torch.device):
+        if device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("reverb_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.lib = _lib.load()
+        self.device = device
+        self.cfg = model_config_from_yaml(configs, vocab)
+        self.d_model = self.cfg.d_model
+        self.vocab = vocab
+        self.num_langs = self.cfg.num_langs
+        self._h = None
+        with torch.cuda.device(device):
+            h = self.lib.rvb_model_create(C.byref(self.cfg))
+            if not h:
+                raise RuntimeError("rvb_model_create failed: " + _lib.last_error())
+            self._h = C.c_void_p(h)
+            for name, t in state_dict.items():
+                if not torch.is_tensor(t) or not t.is_floating_point():
+                    continue
+                a = t.detach().to("cpu", torch.float32).contiguous()
+                check(self.lib.rvb_model_set_tensor(self._h, name.encode("utf8"), C.c_void_p(a.data_ptr()), a.numel()),
+                      f"rvb_model_set_tensor({name})")
+            check(self.lib.rvb_model_finalize(self._h), "rvb_model_finalize")
+        self.has_right_decoder = any(k.startswith("decoder.right_decoder.") for k in state_dict)
+
+    def __del__(self):
+        try:
+            if self._h is not None and self.lib is not None:
+                self.lib.rvb_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _cat(self, cat_embs) -> Tuple[Optional[np.ndarray], int]:
+        if self.num_langs == 0:
+            return None, 0
+        if cat_embs is None:
+            raise ValueError("cat_embs is required by a model with language-specific layers")
+        a = np.ascontiguousarray(torch.as_tensor(cat_embs).detach().cpu().numpy().astype(np.float32).reshape(-1))
+        return a, int(a.shape[0])
+
+    def encoder_out_frames(self, T: int) -> int:
+        return int(self.lib.rvb_encoder_out_frames(int(T)))
+
+    # ------------------------------------------------------------------ hot path
+    def fbank(self, wave: torch.Tensor) -> torch.Tensor:
+        """(N,) float32 or int16 samples on the device (int16-VALUED) -> (m, 80) float32."""
+        assert wave.is_cuda and wave.dim() == 1 and wave.is_contiguous()
+        n = wave.numel()
+        m = int(self.lib.rvb_fbank_num_frames(n))
+        feats = torch.empty((m, 80), dtype=torch.float32, device=wave.device)
+        with torch.cuda.device(self.device):
+            if wave.dtype == torch.int16:
+                check(self.lib.rvb_fbank_i16(_ptr(wave), n, _ptr(feats), m, self._stream()), "rvb_fbank_i16")
+            elif wave.dtype == torch.float32:
+                check(self.lib.rvb_fbank_f32(_ptr(wave), n, _ptr(feats), m, self._stream()), "rvb_fbank_f32")
+            else:
+                raise TypeError(f"fbank: unsupported dtype {wave.dtype}")
+        return feats
+
+    def forward_encoder(self, feats: torch.Tensor, feat_lens: Sequence[int], cat_embs=None):
+        """(B, T, 80) fp32 cuda -> (encoder_out (B, T', d) fp32 cuda, encoder_lens np.int32 (B,))."""
+        assert feats.is_cuda and feats.dtype == torch.float32 and feats.dim() == 3
+        feats = feats.contiguous()
+        B, T, _ = feats.shape
+        Tp = self.encoder_out_frames(T)
+        lens = np.ascontiguousarray(np.asarray(feat_lens, dtype=np.int32).reshape(-1))
+        assert lens.shape[0] == B
+        enc_lens = np.zeros(B, dtype=np.int32)
+        out = torch.empty((B, Tp, self.d_model), dtype=torch.float32, device=feats.device)
+        cat, ncat = self._cat(cat_embs)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_encoder_forward(self._h, _ptr(feats), _np_ptr(lens), B, T, _np_ptr(cat), ncat,
+                                               _ptr(out), _np_ptr(enc_lens), self._stream()), "rvb_encoder_forward")
+        return out, enc_lens
+
+    def ctc_topk(self, enc_out: torch.Tensor, k: int, blank_penalty: float = 0.0, blank_id: int = 0,
+                 want_logp: bool = False):
+        B, Tp, _ = enc_out.shape
+        val = torch.empty((B, Tp, k), dtype=torch.float32, device=enc_out.device)
+        idx = torch.empty((B, Tp, k), dtype=torch.int32, device=enc_out.device)
+        logp = torch.empty((B, Tp, self.vocab), dtype=torch.float32, device=enc_out.device) if want_logp else None
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_ctc_topk(self._h, _ptr(enc_out.contiguous()), B, Tp, k, float(blank_penalty),
+                                        int(blank_id), _ptr(val), _ptr(idx), _ptr(logp), self._stream()),
+                  "rvb_ctc_topk")
+        return val, idx, logp
+
+    def logp_topk(self, logp: torch.Tensor, k: int):
+        """top-k of recorded log-probs (B, T, V) (no softmax)."""
+        logp = logp.contiguous()
+        B, T, V = logp.shape
+        val = torch.empty((B, T, k), dtype=torch.float32, device=logp.device)
+        idx = torch.empty((B, T, k), dtype=torch.int32, device=logp.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_logp_topk(_ptr(logp), B * T, V, k, _ptr(val), _ptr(idx), self._stream()),
+                  "rvb_logp_topk")
+        return val, idx
+
+    def greedy_search(self, topk_idx: torch.Tensor, enc_lens, blank_id: int = 0) -> List[List[int]]:
+        B, Tp, k = topk_idx.shape
+        lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
+        toks = np.zeros((B, Tp), dtype=np.int32)
+        olen = np.zeros(B, dtype=np.int32)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_ctc_greedy_search(_ptr(topk_idx), k, _np_ptr(lens), B, Tp, int(blank_id),
+                                                 _np_ptr(toks), _np_ptr(olen), self._stream()),
+                  "rvb_ctc_greedy_search")
+        return [toks[b, :olen[b]].tolist() for b in range(B)]
+
+    def prefix_beam_search(self, topk_val: torch.Tensor, topk_idx: torch.Tensor, enc_lens, beam: int,
+                           blank_id: int = 0):
+        """-> per utterance (nbest tokens [tuple], nbest scores [float], nbest times [list])."""
+        B, Tp, k = topk_idx.shape
+        lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
+        max_len = max(int(lens.max()) if B else 1, 1)
+        toks = np.zeros((B, beam, max_len), dtype=np.int32)
+        tims = np.zeros((B, beam, max_len), dtype=np.int32)
+        olen = np.zeros((B, beam, 2), dtype=np.int32)
+        scores = np.zeros((B, beam), dtype=np.float64)
+        nhyp = np.zeros(B, dtype=np.int32)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_ctc_prefix_beam_search(_ptr(topk_val), _ptr(topk_idx), k, _np_ptr(lens), B, Tp, beam,
+                                                      int(blank_id), max_len, _np_ptr(toks), _np_ptr(tims),
+                                                      _np_ptr(olen), _np_ptr(scores), _np_ptr(nhyp), self._stream()),
+                  "rvb_ctc_prefix_beam_search")
+        out = []
+        for b in range(B):
+            n = int(nhyp[b])
+            nbest = [tuple(toks[b, r, :olen[b, r, 0]].tolist()) for r in range(n)]
+            times = [tims[b, r, :olen[b, r, 1]].tolist() for r in range(n)]
+            out.append((nbest, [float(s) for s in scores[b, :n]], times))
+        return out
+
+    def rescoring_scores(self, enc_out: torch.Tensor, enc_lens, nbest: List[List[tuple]], cat_embs=None,
+                         reverse_weight: float = 0.0):
+        """Teacher-forced decoder log-probs of every hypothesis token.
+        -> (l2r, r2l): float32 arrays (B, N, Lmax+1), see rvb_attention_rescoring; r2l is None when unused."""
+        B, Tp, _ = enc_out.shape
+        N = max(len(h) for h in nbest)
+        max_len = max([len(h) for hs in nbest for h in hs] + [1])
+        toks = np.zeros((B, N, max_len), dtype=np.int32)
+        hlen = np.full((B, N), -1, dtype=np.int32)
+        for b, hs in enumerate(nbest):
+            for i, h in enumerate(hs):
+                hlen[b, i] = len(h)
+                if len(h):
+                    toks[b, i, :len(h)] = np.asarray(h, dtype=np.int32)
+        lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
+        l2r = np.zeros((B, N, max_len + 1), dtype=np.float32)
+        use_r = reverse_weight > 0.0 and self.has_right_decoder
+        r2l = np.zeros((B, N, max_len + 1), dtype=np.float32) if use_r else None
+        cat, ncat = self._cat(cat_embs)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_attention_rescoring(self._h, _ptr(enc_out.contiguous()), _np_ptr(lens), B, Tp,
+                                                   _np_ptr(toks), _np_ptr(hlen), N, max_len, _np_ptr(cat), ncat,
+                                                   float(reverse_weight), _np_ptr(l2r), _np_ptr(r2l), self._stream()),
+                  "rvb_attention_rescoring")
+        return l2r, r2l
+
+
+def launch_count() -> int:
+    return int(_lib.load().rvb_launch_count())

@@ -1,0 +1,55 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/rvb_b200.h declares."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    with open(os.path.join(ROOT, "include", "rvb_b200.h")) as f:
+        text = f.read()
+    return sorted(set(re.findall(r"RVB_API[^;(]*?\b(rvb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound():
+    from reverb_b200 import _lib
+    names = _declared_symbols()
+    assert len(names) >= 20
+    lib = _lib.load()
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported by librvb_b200.so"
+    assert sorted(_lib.SIGNATURES) == names, "reverb_b200/_lib.py must bind exactly the header's symbols"
+
+
+def test_pure_host_entry_points():
+    from reverb_b200 import _lib
+    lib = _lib.load()
+    assert lib.rvb_fbank_num_frames(399) == 0
+    assert lib.rvb_fbank_num_frames(400) == 1
+    assert lib.rvb_fbank_num_frames(480000) == 2998
+    assert lib.rvb_encoder_out_frames(2998) == 748 and lib.rvb_encoder_out_frames(2051) == 512
+    assert lib.rvb_launch_count() == 0 or lib.rvb_launch_count() > 0
+
+
+def test_no_cuda_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        return
+    from reverb_b200 import _lib
+    from reverb_b200._lib import ModelConfig
+    lib = _lib.load()
+    cfg = ModelConfig()
+    h = lib.rvb_model_create(ctypes.byref(cfg))
+    assert not h
+    assert "no CUDA device" in _lib.last_error()
+
+
+def test_product_never_imports_the_oracle():
+    """only tests/, smoke() and bench.py's CPU legs may touch oracle/ — the package itself must not."""
+    pkg = os.path.join(ROOT, "reverb_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn

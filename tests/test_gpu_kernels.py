@@ -1,0 +1,170 @@
+"""Kernel-level parity (GPU): each hand-written sm_100a kernel vs a plain fp32 torch / numpy
+restatement of the same op, called through the C ABI (reverb_b200/_lib.py)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from reverb_b200 import _lib
+    return _lib.load()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _check(lib, rc):
+    from reverb_b200 import _lib
+    assert rc == 0, _lib.last_error()
+
+
+def test_fbank_matches_oracle_and_torchaudio_golden(lib):
+    from oracle import fbank_np
+    from reverb_b200 import synth
+    gold = dict(np.load("tests/golden/fbank.npz"))
+    for key, ref in gold.items():
+        n = int(key.split("_")[0][1:])
+        seed = int(key.split("seed")[1])
+        pcm = synth.synth_audio(n / 16000.0 + 1e-9, seed=seed)[:n]
+        for dtype in (torch.float32, torch.int16):
+            w = torch.from_numpy(pcm.astype(np.float32 if dtype == torch.float32 else np.int16)).cuda()
+            m = lib.rvb_fbank_num_frames(n)
+            assert m == ref.shape[0]
+            out = torch.empty(m, 80, device="cuda")
+            fn = lib.rvb_fbank_f32 if dtype == torch.float32 else lib.rvb_fbank_i16
+            _check(lib, fn(_p(w), n, _p(out), m, _stream()))
+            got = out.cpu().numpy()
+            # tolerance: fp32 FFT/mel vs torchaudio's fp32 pocketfft; log-mel values are O(10)
+            np.testing.assert_allclose(got, ref, rtol=0, atol=2e-3)
+            np.testing.assert_allclose(got, fbank_np.fbank(pcm.astype(np.float32)), rtol=0, atol=2e-3)
+
+
+@pytest.mark.parametrize("d", [128, 256, 1024, 640])
+def test_layernorm(lib, d):
+    torch.manual_seed(d)
+    M = 777
+    x = torch.randn(M, d, device="cuda") * 3 + 1
+    g = torch.randn(d, device="cuda")
+    b = torch.randn(d, device="cuda")
+    out_f = torch.empty(M, d, device="cuda")
+    out_b = torch.empty(M, d, device="cuda", dtype=torch.bfloat16)
+    _check(lib, lib.rvb_layernorm(_p(x), _p(g), _p(b), 1e-5, M, d, _p(out_b), _p(out_f), _stream()))
+    ref = torch.nn.functional.layer_norm(x, (d,), g, b, 1e-5)
+    torch.testing.assert_close(out_f, ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(out_b.float(), ref.bfloat16().float(), rtol=2e-2, atol=2e-2)
+
+
+GEMM_SHAPES = [(128, 128, 64), (300, 256, 128), (257, 101, 128), (1000, 1024, 4096), (64, 384, 2432), (4096, 4096, 1024)]
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_bias_act_modes(lib, impl, M, N, K):
+    torch.manual_seed(M + N + K)
+    lib.rvb_set_gemm_impl(impl)
+    try:
+        A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+        W = (torch.randn(N, K, device="cuda") / math.sqrt(K)).bfloat16()
+        bias = torch.randn(N, device="cuda")
+        ref = A.float() @ W.float().t() + bias
+        ldo = (N + 3) & ~3
+        # fp32 out
+        out = torch.zeros(M, ldo, device="cuda")
+        _check(lib, lib.rvb_gemm_bf16(_p(A), _p(W), _p(bias), M, N, K, 0, 1, 1.0, _p(out), ldo, _stream()))
+        torch.testing.assert_close(out[:, :N], ref, rtol=1e-3, atol=1e-3)
+        # bf16 out + SiLU
+        out_b = torch.zeros(M, ldo, device="cuda", dtype=torch.bfloat16)
+        _check(lib, lib.rvb_gemm_bf16(_p(A), _p(W), _p(bias), M, N, K, 2, 0, 1.0, _p(out_b), ldo, _stream()))
+        torch.testing.assert_close(out_b[:, :N].float(), torch.nn.functional.silu(ref), rtol=2e-2, atol=2e-2)
+        # residual accumulate with alpha, ReLU
+        res = torch.randn(M, ldo, device="cuda")
+        res0 = res.clone()
+        _check(lib, lib.rvb_gemm_bf16(_p(A), _p(W), _p(bias), M, N, K, 1, 2, 0.5, _p(res), ldo, _stream()))
+        torch.testing.assert_close(res[:, :N], res0[:, :N] + 0.5 * torch.relu(ref), rtol=1e-3, atol=1e-3)
+        torch.cuda.synchronize()
+    finally:
+        lib.rvb_set_gemm_impl(0)
+
+
+@pytest.mark.parametrize("dk,H", [(64, 2), (32, 4), (128, 1)])
+@pytest.mark.parametrize("pos", [True, False])
+def test_attention(lib, dk, H, pos):
+    torch.manual_seed(dk + H)
+    B, T = 3, 150
+    d = H * dk
+    qkv = (torch.randn(B, T, 3 * d, device="cuda") * 0.7).bfloat16()
+    p = (torch.randn(T, d, device="cuda") * 0.7).bfloat16()
+    u = torch.randn(H, dk, device="cuda") * 0.3
+    v = torch.randn(H, dk, device="cuda") * 0.3
+    klens = torch.tensor([150, 97, 1], dtype=torch.int32, device="cuda")
+    out = torch.zeros(B, T, d, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dk)
+    _check(lib, lib.rvb_attention(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d),
+                                  _p(p) if pos else None, _p(u) if pos else None, _p(v) if pos else None, _p(out),
+                                  3 * d, 3 * d, 3 * d, d, d, B, T, T, H, dk, 1, _p(klens), None, 0, scale, _stream()))
+    q = qkv[..., :d].float().view(B, T, H, dk)
+    k = qkv[..., d:2 * d].float().view(B, T, H, dk).transpose(1, 2)
+    vv = qkv[..., 2 * d:].float().view(B, T, H, dk).transpose(1, 2)
+    if pos:
+        pp = p.float().view(1, T, H, dk).transpose(1, 2)
+        qu = (q + u).bfloat16().float().transpose(1, 2)
+        qv = (q + v).bfloat16().float().transpose(1, 2)
+        s = (qu @ k.transpose(-1, -2) + qv @ pp.transpose(-1, -2)) * scale
+    else:
+        s = (q.transpose(1, 2) @ k.transpose(-1, -2)) * scale
+    mask = torch.arange(T, device="cuda")[None, :] >= klens[:, None]
+    s = s.masked_fill(mask[:, None, None, :], -float("inf"))
+    a = torch.softmax(s, -1).masked_fill(mask[:, None, None, :], 0.0)
+    ref = (a @ vv).transpose(1, 2).reshape(B, T, d)
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+def test_attention_causal_cross(lib):
+    """decoder forms: causal self-attention with per-sequence lengths, and cross attention with q_per_kv."""
+    torch.manual_seed(5)
+    H, dk = 2, 64
+    d = H * dk
+    S, L, N, Tk = 6, 23, 3, 90
+    qkv = (torch.randn(S, L, 3 * d, device="cuda") * 0.7).bfloat16()
+    qlens = torch.tensor([23, 5, 1, 17, 23, 9], dtype=torch.int32, device="cuda")
+    out = torch.zeros(S, L, d, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dk)
+    _check(lib, lib.rvb_attention(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d),
+                                  None, None, None, _p(out), 3 * d, 3 * d, 3 * d, 0, d, S, L, L, H, dk, 1, None,
+                                  _p(qlens), 1, scale, _stream()))
+    q = qkv[..., :d].float().view(S, L, H, dk).transpose(1, 2)
+    k = qkv[..., d:2 * d].float().view(S, L, H, dk).transpose(1, 2)
+    v = qkv[..., 2 * d:].float().view(S, L, H, dk).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) * scale
+    j = torch.arange(L, device="cuda")
+    ok = (j[None, None, :] <= j[None, :, None]) & (j[None, None, :] < qlens[:, None, None])
+    s = s.masked_fill(~ok[:, None], -float("inf"))
+    a = torch.softmax(s, -1).masked_fill(~ok[:, None], 0.0).nan_to_num(0.0)
+    ref = (a @ v).transpose(1, 2).reshape(S, L, d)
+    valid = (j[None, :] < qlens[:, None])
+    torch.testing.assert_close(out.float()[valid], ref[valid], rtol=3e-2, atol=3e-2)
+    # cross attention: S sequences share Tk memory rows of utterance s // N
+    qx = (torch.randn(S, L, d, device="cuda") * 0.7).bfloat16()
+    kv = (torch.randn(S // N, Tk, 2 * d, device="cuda") * 0.7).bfloat16()
+    klens = torch.tensor([90, 41], dtype=torch.int32, device="cuda")
+    _check(lib, lib.rvb_attention(_p(qx), _p(kv), C.c_void_p(kv.data_ptr() + 2 * d), None, None, None, _p(out),
+                                  d, 2 * d, 2 * d, 0, d, S, L, Tk, H, dk, N, _p(klens), None, 0, scale, _stream()))
+    q = qx.float().view(S, L, H, dk).transpose(1, 2)
+    k = kv[..., :d].float().view(S // N, Tk, H, dk).transpose(1, 2).repeat_interleave(N, 0)
+    v = kv[..., d:].float().view(S // N, Tk, H, dk).transpose(1, 2).repeat_interleave(N, 0)
+    s = (q @ k.transpose(-1, -2)) * scale
+    mask = (torch.arange(Tk, device="cuda")[None, :] >= klens.repeat_interleave(N)[:, None])
+    s = s.masked_fill(mask[:, None, None, :], -float("inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(S, L, d)
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)

@@ -1,0 +1,145 @@
+"""Hot-path parity on the GPU: CUDA path (through the C ABI) vs the committed reference fixtures
+(tests/golden, produced by the live reference) and vs the CPU oracle on the same seeded inputs.
+
+Tolerances (stated): the searches consume identical fp32 log-probs and must
+be bit-exact in tokens / times (scores: 1e-9 relative, CUDA fp64 exp/log vs glibc).  The encoder runs
+its GEMMs with bf16 operands and fp32 accumulation, so encoder_out / log-probs are compared with an
+RMS-relative tolerance instead.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def asr(model_dirs):
+    import reverb_b200
+    return {n: reverb_b200.load_model(d) for n, (d, _) in model_dirs.items()}
+
+
+def _rel_rms(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean()) / (np.sqrt((b ** 2).mean()) + 1e-12))
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_searches_bit_exact_on_recorded_ctc_probs(asr, golden_cases, case):
+    """greedy + prefix beam on the reference's own ctc_probs: tokens, n-best, times identical."""
+    meta, arr = golden_cases[case]
+    eng = asr[case].engine
+    for bi, batch in enumerate(meta["batches"]):
+        logp = torch.from_numpy(arr[f"ctc_probs_{bi}"]).cuda()
+        lens = arr[f"enc_lens_{bi}"]
+        val, idx = eng.logp_topk(logp, 10)
+        # top-k itself: same values / indices as torch.topk on the recorded tensor
+        tv, ti = logp.topk(10, dim=2)
+        assert torch.equal(val, tv)
+        assert torch.equal(idx.long(), ti)
+        greedy = eng.greedy_search(idx, lens, 0)
+        for b, g in enumerate(batch["ctc_greedy_search"]):
+            assert greedy[b] == g["tokens"]
+        pb = eng.prefix_beam_search(val, idx, lens, 10, 0)
+        for b, g in enumerate(batch["ctc_prefix_beam_search"]):
+            nbest, scores, times = pb[b]
+            assert [list(h) for h in nbest] == g["nbest"]
+            assert times == g["nbest_times"]
+            np.testing.assert_allclose(scores, g["nbest_scores"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_fbank_and_encoder_vs_reference_fixture(asr, golden_cases, model_dirs, case):
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    feats = m.compute_feats(model_dirs[case][1], num_mel_bins=80, frame_length=25, frame_shift=10)
+    np.testing.assert_allclose(feats[0].cpu().numpy(), arr["feats"], rtol=0, atol=2e-3)
+    # encoder on the REFERENCE's features (identical fbank input), bf16-GEMM tolerance
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    for bi, (fb, fl) in enumerate(m.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])):
+        enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
+        assert enc_lens.tolist() == arr[f"enc_lens_{bi}"].tolist()
+        ref = arr[f"enc_out_{bi}"]
+        got = enc.cpu().numpy()
+        for b in range(ref.shape[0]):
+            n = int(enc_lens[b])
+            assert _rel_rms(got[b, :n], ref[b, :n]) < 3e-2
+        logp = m.model.ctc_logprobs(enc).cpu().numpy()
+        refp = arr[f"ctc_probs_{bi}"]
+        for b in range(ref.shape[0]):
+            n = int(enc_lens[b])
+            # log-probs: absolute tolerance on the entries that matter (p > e^-12)
+            sel = refp[b, :n] > -12
+            assert np.abs(logp[b, :n][sel] - refp[b, :n][sel]).max() < 0.25
+            assert (logp[b, :n].argmax(-1) == refp[b, :n].argmax(-1)).mean() > 0.9
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_rescoring_decoder_vs_oracle(asr, golden_cases, model_dirs, case):
+    """teacher-forced decoder log-probs on the reference's encoder_out / n-best: vs the CPU oracle."""
+    from oracle import model_ref, pipeline_ref, search_ref
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    orc = pipeline_ref.OracleASR(model_dirs[case][0])
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    rw = 0.3
+    for bi, batch in enumerate(meta["batches"]):
+        enc = torch.from_numpy(arr[f"enc_out_{bi}"])
+        lens = arr[f"enc_lens_{bi}"]
+        nbest = [[tuple(h) for h in g["nbest"]] for g in batch["ctc_prefix_beam_search"]]
+        l2r, r2l = m.engine.rescoring_scores(enc.cuda(), lens, nbest, cat, rw)
+        for b, hyps in enumerate(nbest):
+            ys, ylens = search_ref.rescoring_inputs(hyps, orc.sos, orc.eos)
+            mem = enc[b, :int(lens[b])].unsqueeze(0).repeat(len(hyps), 1, 1)
+            dec = torch.log_softmax(model_ref.decoder_forward(mem, ys, ylens, orc.sd, orc.cfg, "left_decoder", cat), -1)
+            rys = model_ref.reverse_hyps(ys, ylens, orc.eos)
+            rdec = torch.log_softmax(model_ref.decoder_forward(mem, rys, ylens, orc.sd, orc.cfg, "right_decoder", cat), -1)
+            for i, h in enumerate(hyps):
+                U = len(h)
+                want = [float(dec[i, j, h[j]]) for j in range(U)] + [float(dec[i, U, orc.eos])]
+                rwant = [float(rdec[i, U - 1 - j, h[j]]) for j in range(U)] + [float(rdec[i, U, orc.eos])]
+                np.testing.assert_allclose(l2r[b, i, :U + 1], want, rtol=0, atol=0.15)
+                np.testing.assert_allclose(r2l[b, i, :U + 1], rwant, rtol=0, atol=0.15)
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_decode_end_to_end_vs_oracle(asr, golden_cases, model_dirs, case):
+    """Full decode(): greedy tokens mostly identical, hypotheses well-formed, CTM renders.  (Exact n-best
+    equality is NOT expected with bf16 GEMMs on near-uniform synthetic posteriors — SURVEY.md App. B.6.)"""
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    wav = model_dirs[case][1]
+    out = m.transcribe_modes(wav, ["ctc_prefix_beam_search", "attention_rescoring"], format="ctm",
+                             verbatimicity=meta["verbatimicity"], chunk_size=meta["chunk_size"],
+                             batch_size=meta["batch_size"], reverse_weight=meta["reverse_weight"])
+    for text in out:
+        lines = text.split("\n")
+        assert len(lines) > 3
+        for ln in lines:
+            f = ln.split(" ")
+            assert len(f) == 6 and f[0] == "golden.wav" and float(f[2]) >= 0 and float(f[3]) >= 0
+    ref_lines = meta["transcribe"]["attention_rescoring.ctm"].split("\n")
+    # word sequences agree to a large extent with the reference's (token-level edit distance small)
+    got_words = [ln.split(" ")[4] for ln in out[1].split("\n")]
+    ref_words = [ln.split(" ")[4] for ln in ref_lines]
+    import difflib
+    ratio = difflib.SequenceMatcher(None, got_words, ref_words).ratio()
+    assert ratio > 0.7, ratio
+    txt = m.transcribe(wav, mode="attention_rescoring", format="txt", chunk_size=meta["chunk_size"],
+                       batch_size=meta["batch_size"], verbatimicity=meta["verbatimicity"],
+                       reverse_weight=meta["reverse_weight"])
+    assert txt.split(" ") == got_words
+    with pytest.raises(ValueError):
+        m.transcribe(wav, format="json")
+    with pytest.raises((AssertionError, TypeError)):
+        m.transcribe(wav, mode="ctc_greedy_search")          # reference quirk 1: greedy has no times
+
+
+def test_launch_counter_and_no_cpu_path():
+    from reverb_b200.engine import launch_count
+    assert launch_count() > 0

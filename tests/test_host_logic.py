@@ -1,0 +1,157 @@
+"""Host-side logic of the product (no GPU): chunking, word/CTM assembly, score combination, loaders."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+
+class _Cfg:
+    pass
+
+
+def _fake_asr():
+    """ReverbASR without the engine: only the pure-host methods are exercised."""
+    from reverb_b200.reverb import ReverbASR
+    obj = ReverbASR.__new__(ReverbASR)
+    obj.test_conf = {"fbank_conf": {"num_mel_bins": 80, "frame_length": 25, "frame_shift": 10}}
+    return obj
+
+
+@pytest.mark.parametrize("m,chunk,batch", [(1128, 400, 2), (898, 330, 3), (2051, 2051, 1), (5, 400, 2), (800, 400, 2)])
+def test_feats_batcher_matches_oracle_restatement(m, chunk, batch):
+    from oracle.pipeline_ref import OracleASR
+    asr = _fake_asr()
+    feats = torch.randn(1, m, 80)
+    mine = list(asr.feats_batcher(feats, chunk, batch))
+    ref = list(OracleASR.feats_batcher(feats, chunk, batch))
+    assert len(mine) == len(ref)
+    for (a, al), (b, bl) in zip(mine, ref):
+        assert torch.equal(a, b) and al.tolist() == bl.tolist() and al.dtype == torch.int32
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_ctm_and_txt_rendering_equal_reference_strings(golden_cases, model_dirs, case):
+    """get_output on the reference's hypotheses reproduces the reference's transcribe() strings exactly."""
+    from reverb_b200.reverb import get_output
+    from reverb_b200.search import DecodeResult
+    from reverb_b200.text import PieceTokenizer
+    meta, _ = golden_cases[case]
+    tok = PieceTokenizer(os.path.join(model_dirs[case][0], "tk.units.txt"))
+    for mode in ("ctc_prefix_beam_search", "attention_rescoring"):
+        hyps = []
+        for batch in meta["batches"]:
+            for r in batch[mode]:
+                hyps.append(DecodeResult(r["tokens"], r["score"], r["confidence"], r["tokens_confidence"], r["times"]))
+        for fmt in ("ctm", "txt"):
+            got = get_output(fmt, tok, "golden.wav", hyps, 230, meta["chunk_size"], 10, 40)
+            assert got == meta["transcribe"][f"{mode}.{fmt}"]
+    with pytest.raises(ValueError):
+        get_output("json", tok, "x", [], 230, 400, 10, 40)
+
+
+def test_ctc_align_requires_times_like_the_reference(model_dirs):
+    from reverb_b200.ctc_align import adjust_model_time_offset, ctc_align
+    from reverb_b200.text import PieceTokenizer
+    tok = PieceTokenizer(os.path.join(model_dirs["causal_ln"][0], "tk.units.txt"))
+    with pytest.raises((TypeError, AssertionError)):
+        ctc_align([3, 4], None, None, tok, 40, 0)
+    assert ctc_align([], [], None, tok, 40, 0) == []
+    assert adjust_model_time_offset([], 0) is None          # reference quirk 4
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_rescoring_pick_float_semantics(golden_cases, model_dirs, case):
+    """rescoring_pick on oracle decoder log-probs reproduces the reference's score / confidence bit for bit."""
+    from oracle import model_ref, pipeline_ref, search_ref
+    from reverb_b200.search import rescoring_pick
+    meta, arr = golden_cases[case]
+    orc = pipeline_ref.OracleASR(model_dirs[case][0])
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    rw, cw = meta["reverse_weight"], meta["ctc_weight"]
+    for bi, batch in enumerate(meta["batches"]):
+        enc = torch.from_numpy(arr[f"enc_out_{bi}"])
+        lens = arr[f"enc_lens_{bi}"]
+        for b, g in enumerate(batch["ctc_prefix_beam_search"]):
+            hyps = [tuple(h) for h in g["nbest"]]
+            ys, ylens = search_ref.rescoring_inputs(hyps, orc.sos, orc.eos)
+            mem = enc[b, :int(lens[b])].unsqueeze(0).repeat(len(hyps), 1, 1)
+            with torch.no_grad():
+                dec = torch.log_softmax(model_ref.decoder_forward(mem, ys, ylens, orc.sd, orc.cfg, "left_decoder", cat), -1)
+                rdec = None
+                if rw > 0:
+                    rys = model_ref.reverse_hyps(ys, ylens, orc.eos)
+                    rdec = torch.log_softmax(model_ref.decoder_forward(mem, rys, ylens, orc.sd, orc.cfg, "right_decoder", cat), -1)
+            L = ys.shape[1]
+            l2r = np.zeros((len(hyps), L), np.float32)
+            r2l = np.zeros((len(hyps), L), np.float32) if rdec is not None else None
+            for i, h in enumerate(hyps):
+                U = len(h)
+                for j in range(U):
+                    l2r[i, j] = dec[i, j, h[j]]
+                    if r2l is not None:
+                        r2l[i, j] = rdec[i, U - 1 - j, h[j]]
+                l2r[i, U] = dec[i, U, orc.eos]
+                if r2l is not None:
+                    r2l[i, U] = rdec[i, U, orc.eos]
+            got = rescoring_pick(hyps, g["nbest_scores"], g["nbest_times"], l2r, r2l, cw, rw)
+            want = batch["attention_rescoring"][b]
+            assert list(got.tokens) == want["tokens"] and got.times == want["times"]
+            assert got.score == want["score"] and got.confidence == want["confidence"]
+            assert got.tokens_confidence == want["tokens_confidence"]
+
+
+def test_cmvn_loaders(tmp_path):
+    from reverb_b200.cmvn import load_cmvn
+    mean = np.array([1.0, -2.0, 0.5])
+    var = np.array([4.0, 0.25, 1e-30])
+    n = 50.0
+    js = tmp_path / "cmvn.json"
+    js.write_text(json.dumps({"mean_stat": (mean * n).tolist(), "var_stat": ((var + mean ** 2) * n).tolist(), "frame_num": n}))
+    m, istd = load_cmvn(str(js), True)
+    np.testing.assert_allclose(m, mean)
+    np.testing.assert_allclose(istd[:2], 1 / np.sqrt(var[:2]))
+    assert istd[2] == pytest.approx(1e10)                                  # variance floor 1e-20
+    kd = tmp_path / "cmvn.kaldi"
+    kd.write_text("[\n " + " ".join(str(x) for x in mean * n) + f" {n}\n " + " ".join(str(x) for x in (var + mean ** 2) * n) + " 0 ]\n")
+    m2, istd2 = load_cmvn(str(kd), False)
+    np.testing.assert_allclose(m2, m)
+    np.testing.assert_allclose(istd2, istd)
+
+
+def test_load_model_error_behaviour(tmp_path):
+    import reverb_b200
+    assert reverb_b200.get_available_models() == ["reverb_asr_v1"]
+    with pytest.raises(ValueError):
+        reverb_b200.load_model("no_such_model_name")
+    import wenet
+    assert wenet.load_model is reverb_b200.load_model
+    if not torch.cuda.is_available():
+        from reverb_b200 import synth
+        d = synth.write_model_dir(str(tmp_path / "m"))
+        with pytest.raises(RuntimeError, match="CUDA"):                      # no CPU fallback
+            reverb_b200.load_model(d)
+
+
+def test_cli_argument_surface():
+    from reverb_b200.recognize_wav import get_args, main
+    a = get_args(["--audio_file", "a.wav", "--result_dir", "out", "--model", "m"])
+    assert a.modes == ["attention_rescoring"] and a.beam_size == 10 and a.chunk_size == 2051 and a.batch_size == 1
+    assert a.ctc_weight == 0.1 and a.reverse_weight == 0.0 and a.verbatimicity == 1.0 and a.timings_adjustment == 230
+    with pytest.raises(RuntimeError):
+        main(["--audio_file", "a.wav", "--result_dir", "out"])              # neither --model nor config+checkpoint
+
+
+def test_encoder_length_formula_matches_mask_slicing():
+    from reverb_b200 import _lib
+    lib = _lib.load()
+    for T in (7, 8, 9, 10, 11, 330, 400, 2051, 2998):
+        Tp = ((T - 1) // 2 - 1) // 2
+        assert lib.rvb_encoder_out_frames(T) == Tp
+        for ln in (0, 1, 6, 7, 8, 10, 11, 12, T - 1, T):
+            if ln > T:
+                continue
+            mask = (torch.arange(T) < ln)[None, None, :]
+            want = int(mask[:, :, 2::2][:, :, 2::2].sum())
+            assert lib.rvb_encoder_out_len(ln, T) == want, (T, ln)

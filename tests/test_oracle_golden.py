@@ -1,0 +1,74 @@
+"""The CPU oracle (oracle/) vs the committed outputs of the live reference (tests/golden): the oracle
+must reproduce the reference bit for bit on the model graph / searches (same ATen CPU ops, same float
+semantics) and to fp32 round-off on fbank (numpy vs torchaudio FFT)."""
+import numpy as np
+import pytest
+import torch
+
+
+def test_fbank_oracle_vs_torchaudio_golden():
+    from oracle import fbank_np
+    from reverb_b200 import synth
+    gold = dict(np.load("tests/golden/fbank.npz"))
+    assert len(gold) >= 5
+    for key, ref in gold.items():
+        n = int(key.split("_")[0][1:])
+        seed = int(key.split("seed")[1])
+        pcm = synth.synth_audio(n / 16000.0 + 1e-9, seed=seed)[:n]
+        got = fbank_np.fbank(pcm.astype(np.float32))
+        assert got.shape == ref.shape == (1 + (n - 400) // 160, 80)
+        np.testing.assert_allclose(got, ref, rtol=0, atol=5e-4)
+    assert fbank_np.fbank(np.zeros(399, np.float32)).shape == (0, 80)     # shorter than one window
+    silent = fbank_np.fbank(np.zeros(800, np.float32))                    # log floor: log(eps)
+    np.testing.assert_allclose(silent, np.log(np.float32(1.1920929e-07)), rtol=1e-6)
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_oracle_pipeline_vs_reference_golden(golden_cases, model_dirs, case):
+    from oracle import pipeline_ref
+    meta, arr = golden_cases[case]
+    d, wav = model_dirs[case]
+    orc = pipeline_ref.OracleASR(d)
+    feats = orc.compute_feats(wav)
+    np.testing.assert_allclose(feats[0].numpy(), arr["feats"], rtol=0, atol=5e-4)
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0)
+    modes = ["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"]
+    for bi, (fb, fl) in enumerate(orc.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])):
+        assert fl.tolist() == arr[f"feats_lens_{bi}"].tolist()
+        out = orc.decode(modes, fb, fl, 10, ctc_weight=meta["ctc_weight"], reverse_weight=meta["reverse_weight"],
+                         cat_embs=cat, return_intermediates=True)
+        assert out["_encoder_lens"].tolist() == arr[f"enc_lens_{bi}"].tolist()
+        np.testing.assert_array_equal(out["_encoder_out"].numpy(), arr[f"enc_out_{bi}"])
+        np.testing.assert_array_equal(out["_ctc_probs"].numpy(), arr[f"ctc_probs_{bi}"])
+        g = meta["batches"][bi]
+        for b in range(fb.shape[0]):
+            assert out["ctc_greedy_search"][b].tokens == g["ctc_greedy_search"][b]["tokens"]
+            p, gp = out["ctc_prefix_beam_search"][b], g["ctc_prefix_beam_search"][b]
+            assert [list(h) for h in p.nbest] == gp["nbest"]
+            assert p.nbest_scores == gp["nbest_scores"]
+            assert p.nbest_times == gp["nbest_times"]
+            r, gr = out["attention_rescoring"][b], g["attention_rescoring"][b]
+            assert list(r.tokens) == gr["tokens"] and r.times == gr["times"]
+            assert float(r.score) == gr["score"] and r.confidence == gr["confidence"]
+            assert r.tokens_confidence == gr["tokens_confidence"]
+
+
+def test_log_add_and_collapse_known_answers():
+    from oracle import search_ref
+    inf = float("inf")
+    assert search_ref.log_add([-inf, -inf]) == -inf
+    assert search_ref.log_add([-inf, -1.5]) == -1.5
+    assert abs(search_ref.log_add([0.0, 0.0]) - 0.6931471805599453) < 1e-15
+    assert search_ref.remove_duplicates_and_blank([0, 1, 1, 0, 1, 2, 2, 0, 0, 3]) == [1, 1, 2, 3]
+    assert search_ref.remove_duplicates_and_blank([]) == []
+
+
+def test_reverse_hyps_docstring_example():
+    """known-answer from the reference docstring (asr/wenet/transformer/asr_model.py:908-953)."""
+    from oracle import model_ref
+    sos = eos = 99
+    hyps = torch.tensor([[sos, 1, 2, 3], [sos, 9, 8, 4], [sos, 2, eos, eos]])
+    lens = torch.tensor([4, 4, 2])
+    r = model_ref.reverse_hyps(hyps, lens, eos)
+    assert r.tolist() == [[sos, 3, 2, 1], [sos, 4, 8, 9], [sos, 2, eos, eos]]
