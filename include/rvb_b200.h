@@ -58,6 +58,10 @@ RVB_API unsigned long long rvb_launch_count(void);
 /* 0 = tcgen05/TMA GEMM (default), 1 = plain CUDA-core bring-up GEMM (debug only) */
 RVB_API int rvb_set_gemm_impl(int impl);
 RVB_API int rvb_get_gemm_impl(void);
+/* Per-launch CUDA-event timing of the tcgen05 GEMM kernel between begin/end (the roofline numbers of bench.py):
+ * total device time (ms), algorithmic FLOPs (2*M*N*K summed) and launch count.  end() synchronises. */
+RVB_API int rvb_gemm_profile_begin(void);
+RVB_API int rvb_gemm_profile_end(double* total_ms, double* total_flops, long long* launches);
 
 /* ---- model lifecycle ---------------------------------------------------------------------------------------- */
 RVB_API rvb_model* rvb_model_create(const rvb_model_config* cfg);
@@ -76,6 +80,9 @@ RVB_API int rvb_encoder_out_len(int feat_len, int T);
 RVB_API long long rvb_fbank_num_frames(long long n_samples);
 RVB_API int rvb_fbank_f32(const float* d_wave, long long n_samples, float* d_feats, long long n_frames, void* stream);
 RVB_API int rvb_fbank_i16(const short* d_wave, long long n_samples, float* d_feats, long long n_frames, void* stream);
+/* `batch` equal-length recordings (fixed-length chunks), `wave_stride` samples apart -> d_feats (batch, n_frames, 80) */
+RVB_API int rvb_fbank_batch(const void* d_wave, int is_i16, int batch, long long wave_stride, long long n_samples,
+                            float* d_feats, long long n_frames, void* stream);
 
 /* feats (B, T, input_dim) fp32 -> enc_out (B, T', d_model) fp32; h_enc_lens[B] receives encoder_lens.
  * h_cat_embs: the LSL mixing weights [verbatimicity, 1 - verbatimicity] (n_cat == num_langs), may be NULL iff

@@ -28,6 +28,8 @@ SIGNATURES = {
     "rvb_launch_count": (C.c_ulonglong, []),
     "rvb_set_gemm_impl": (_i, [_i]),
     "rvb_get_gemm_impl": (_i, []),
+    "rvb_gemm_profile_begin": (_i, []),
+    "rvb_gemm_profile_end": (_i, [_vp, _vp, _vp]),
     "rvb_model_create": (_vp, [C.POINTER(ModelConfig)]),
     "rvb_model_set_tensor": (_i, [_vp, C.c_char_p, _vp, _ll]),
     "rvb_model_finalize": (_i, [_vp]),
@@ -37,6 +39,7 @@ SIGNATURES = {
     "rvb_fbank_num_frames": (_ll, [_ll]),
     "rvb_fbank_f32": (_i, [_vp, _ll, _vp, _ll, _vp]),
     "rvb_fbank_i16": (_i, [_vp, _ll, _vp, _ll, _vp]),
+    "rvb_fbank_batch": (_i, [_vp, _i, _i, _ll, _ll, _vp, _ll, _vp]),
     "rvb_encoder_forward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "rvb_ctc_topk": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
     "rvb_logp_topk": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -784,6 +784,13 @@ RVB_API int rvb_set_gemm_impl(int impl) {
   return 0;
 }
 RVB_API int rvb_get_gemm_impl(void) { return rvb::get_gemm_impl(); }
+RVB_API int rvb_gemm_profile_begin(void) {
+  rvb::gemm_profile_begin();
+  return 0;
+}
+RVB_API int rvb_gemm_profile_end(double* total_ms, double* total_flops, long long* launches) {
+  return rvb::gemm_profile_end(total_ms, total_flops, launches);
+}
 
 RVB_API rvb_model* rvb_model_create(const rvb_model_config* cfg) {
   if (cfg == nullptr) {
@@ -850,6 +857,12 @@ RVB_API int rvb_fbank_f32(const float* d_wave, long long n_samples, float* d_fea
 }
 RVB_API int rvb_fbank_i16(const short* d_wave, long long n_samples, float* d_feats, long long n_frames, void* stream) {
   return rvb::launch_fbank_i16(d_wave, n_samples, d_feats, n_frames, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_fbank_batch(const void* d_wave, int is_i16, int batch, long long wave_stride, long long n_samples,
+                            float* d_feats, long long n_frames, void* stream) {
+  return rvb::launch_fbank_batch(d_wave, is_i16, batch, wave_stride, n_samples, d_feats, n_frames,
+                                 (cudaStream_t)stream);
 }
 
 RVB_API int rvb_encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,

@@ -89,7 +89,7 @@ __device__ __forceinline__ float ld_sample(const short* p, long long i) { return
 
 template <typename TIn>
 __global__ void __launch_bounds__(FB_WARPS * 32)
-fbank_kernel(const TIn* __restrict__ wave, long long n_frames, float* __restrict__ feats,
+fbank_kernel(const TIn* __restrict__ wave_all, long long wave_stride, long long n_frames, float* __restrict__ feats_all,
              const float* __restrict__ window, const float2* __restrict__ twiddle, const float* __restrict__ mel_w,
              const int* __restrict__ mel_start, const int* __restrict__ mel_len) {
   __shared__ float s_re[FB_WARPS][FB_NFFT];
@@ -100,6 +100,8 @@ fbank_kernel(const TIn* __restrict__ wave, long long n_frames, float* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long frame = (long long)blockIdx.x * FB_WARPS + warp;
   if (frame >= n_frames) return;
+  const TIn* wave = wave_all + (long long)blockIdx.y * wave_stride;      // blockIdx.y = recording in the batch
+  float* feats = feats_all + (long long)blockIdx.y * n_frames * FB_NBIN;
   float* re = s_re[warp];
   float* im = s_im[warp];
   const TIn* src = wave + frame * FB_SHIFT;
@@ -177,15 +179,17 @@ fbank_kernel(const TIn* __restrict__ wave, long long n_frames, float* __restrict
 }
 
 template <typename TIn>
-static int launch_fbank_t(const TIn* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream) {
+static int launch_fbank_t(const TIn* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream,
+                          int batch = 1, long long wave_stride = 0) {
   if (init_fbank_tables()) return -1;
   long long expect = n_samples < FB_WIN ? 0 : 1 + (n_samples - FB_WIN) / FB_SHIFT;
   RVB_REQUIRE(n_frames <= expect, "fbank: %lld frames requested but only %lld fit %lld samples", n_frames, expect,
               n_samples);
   if (n_frames <= 0) return 0;
   const long long blocks = (n_frames + FB_WARPS - 1) / FB_WARPS;
-  fbank_kernel<TIn><<<(unsigned)blocks, FB_WARPS * 32, 0, stream>>>(wave, n_frames, feats, g_fb.window, g_fb.twiddle,
-                                                                   g_fb.mel_w, g_fb.mel_start, g_fb.mel_len);
+  dim3 grid((unsigned)blocks, (unsigned)batch);
+  fbank_kernel<TIn><<<grid, FB_WARPS * 32, 0, stream>>>(wave, wave_stride, n_frames, feats, g_fb.window, g_fb.twiddle,
+                                                       g_fb.mel_w, g_fb.mel_start, g_fb.mel_len);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;
@@ -196,6 +200,15 @@ int launch_fbank(const float* wave, long long n_samples, float* feats, long long
 }
 int launch_fbank_i16(const short* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream) {
   return launch_fbank_t<short>(wave, n_samples, feats, n_frames, stream);
+}
+int launch_fbank_batch(const void* wave, int is_i16, int batch, long long wave_stride, long long n_samples,
+                       float* feats, long long n_frames, cudaStream_t stream) {
+  RVB_REQUIRE(batch >= 1 && batch <= 65535 && wave_stride >= n_samples, "fbank_batch: bad batch/stride");
+  if (is_i16)
+    return launch_fbank_t<short>(reinterpret_cast<const short*>(wave), n_samples, feats, n_frames, stream, batch,
+                                 wave_stride);
+  return launch_fbank_t<float>(reinterpret_cast<const float*>(wave), n_samples, feats, n_frames, stream, batch,
+                               wave_stride);
 }
 
 }  // namespace rvb

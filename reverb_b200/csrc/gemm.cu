@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "kernels.h"
 
 namespace rvb {
@@ -406,6 +408,41 @@ static int make_tmap(CUtensorMap* m, const void* base, int rank, const cuuint64_
 
 static int g_num_sms = 0;
 
+// ---- optional per-launch timing (bench.py's live roofline): CUDA events on the launching stream
+struct GemmProfRec {
+  cudaEvent_t a, b;
+  double flops;
+};
+static bool g_prof_on = false;
+static std::vector<GemmProfRec> g_prof;
+
+void gemm_profile_begin() {
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+}
+int gemm_profile_end(double* total_ms, double* total_flops, long long* launches) {
+  g_prof_on = false;
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    RVB_CHECK_CUDA(cudaEventSynchronize(r.b));
+    RVB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t;
+    fl += r.flops;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  if (launches) *launches = (long long)g_prof.size();
+  g_prof.clear();
+  return 0;
+}
+
 template <int BN>
 static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
@@ -440,9 +477,20 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   int tiles_m = a.conv_mode ? a.conv_B * a.conv_F2 * p.conv_tt : (a.M + 127) / 128;
   p.num_tiles = tiles_m * p.tiles_n;
   int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  GemmProfRec rec;
+  if (g_prof_on) {
+    RVB_CHECK_CUDA(cudaEventCreate(&rec.a));
+    RVB_CHECK_CUDA(cudaEventCreate(&rec.b));
+    rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
+    RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
+  }
   gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
+  if (g_prof_on) {
+    RVB_CHECK_CUDA(cudaEventRecord(rec.b, stream));
+    g_prof.push_back(rec);
+  }
   return 0;
 }
 

@@ -42,11 +42,17 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // 0 = tcgen05/TMA kernel (default), 1 = plain CUDA-core debug kernel (env RVB_GEMM=simt)
 void set_gemm_impl(int impl);
 int get_gemm_impl();
+// per-launch CUDA-event timing of the tcgen05 GEMM (algorithmic FLOPs = 2*M*N*K per launch)
+void gemm_profile_begin();
+int gemm_profile_end(double* total_ms, double* total_flops, long long* launches);
 
 // ------------------------------------------------------------------ fbank (fbank.cu)
 int launch_fbank(const float* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream);
 // int16 PCM input variant (the host API's H2D format)
 int launch_fbank_i16(const short* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream);
+// `batch` equal-length recordings `wave_stride` samples apart -> feats (batch, n_frames, 80)
+int launch_fbank_batch(const void* wave, int is_i16, int batch, long long wave_stride, long long n_samples,
+                       float* feats, long long n_frames, cudaStream_t stream);
 
 // ------------------------------------------------------------------ norms / conv pieces (elementwise.cu)
 // y = LN(x) * gamma + beta ; rows with position >= row_lens[batch] are written as 0 when mask_rows != 0.

