@@ -25,13 +25,23 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
+# Optional emulation of the CUDA path's storage precision (tests only): when EMULATE_BF16 is True every tensor the
+# GPU engine stores as bf16 (GEMM operands, attention probabilities, conv activations) is rounded to bf16 at the same
+# point of the graph, everything else stays fp32.  With it the oracle and the engine differ only by accumulation
+# order, which lets the GPU parity tests use a ~10x tighter tolerance than against the pure-fp32 reference.
+EMULATE_BF16 = False
+
+
+def _q(x):
+    return x.bfloat16().float() if EMULATE_BF16 else x
+
 
 def _ln(x, sd: SD, p: str, eps: float):
     return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], eps)
 
 
 def _lin(x, sd: SD, p: str):
-    return F.linear(x, sd[p + ".weight"], sd.get(p + ".bias"))
+    return F.linear(_q(x), _q(sd[p + ".weight"]), sd.get(p + ".bias"))
 
 
 def make_pad_mask(lengths: torch.Tensor, max_len: int) -> torch.Tensor:
@@ -57,12 +67,16 @@ def subsample4(feats: torch.Tensor, lens: torch.Tensor, sd: SD) -> Tuple[torch.T
     masks = ~make_pad_mask(lens, T).unsqueeze(1)                       # encoder.py:130
     x = (feats - sd["encoder.global_cmvn.mean"]) * sd["encoder.global_cmvn.istd"]
     x = x.unsqueeze(1)
-    x = F.relu(F.conv2d(x, sd["encoder.embed.conv.0.weight"], sd["encoder.embed.conv.0.bias"], stride=2))
-    x = F.relu(F.conv2d(x, sd["encoder.embed.conv.2.weight"], sd["encoder.embed.conv.2.bias"], stride=2))
+    x = _q(F.relu(F.conv2d(x, sd["encoder.embed.conv.0.weight"], sd["encoder.embed.conv.0.bias"], stride=2)))
+    x = _q(F.relu(F.conv2d(x, _q(sd["encoder.embed.conv.2.weight"]), sd["encoder.embed.conv.2.bias"], stride=2)))
     b, c, t, f = x.shape
-    x = _lin(x.transpose(1, 2).contiguous().view(b, t, c * f), sd, "encoder.embed.out.0")
-    d = x.shape[-1]
-    x = x * math.sqrt(d)
+    x = x.transpose(1, 2).contiguous().view(b, t, c * f)
+    d = sd["encoder.embed.out.0.bias"].shape[0]
+    if EMULATE_BF16:   # the engine folds xscale = sqrt(d) into the packed bf16 weight
+        xs = math.sqrt(d)
+        x = F.linear(x, _q(sd["encoder.embed.out.0.weight"] * xs), sd["encoder.embed.out.0.bias"] * xs)
+    else:
+        x = _lin(x, sd, "encoder.embed.out.0") * math.sqrt(d)
     pos_emb = sinusoid_pe(t, d).unsqueeze(0)
     masks = masks[:, :, 2::2][:, :, 2::2]
     return x, pos_emb, masks
@@ -73,12 +87,12 @@ def rel_attention(x, mask, pos_emb, sd: SD, p: str, H: int):
     disabled rel_shift (:391-394): p is indexed by ABSOLUTE key position."""
     B, T, d = x.shape
     dk = d // H
-    q = _lin(x, sd, p + ".linear_q").view(B, T, H, dk)
-    k = _lin(x, sd, p + ".linear_k").view(B, T, H, dk).transpose(1, 2)
-    v = _lin(x, sd, p + ".linear_v").view(B, T, H, dk).transpose(1, 2)
-    pp = F.linear(pos_emb, sd[p + ".linear_pos.weight"]).view(1, -1, H, dk).transpose(1, 2)
-    qu = (q + sd[p + ".pos_bias_u"]).transpose(1, 2)
-    qv = (q + sd[p + ".pos_bias_v"]).transpose(1, 2)
+    q = _q(_lin(x, sd, p + ".linear_q")).view(B, T, H, dk)
+    k = _q(_lin(x, sd, p + ".linear_k")).view(B, T, H, dk).transpose(1, 2)
+    v = _q(_lin(x, sd, p + ".linear_v")).view(B, T, H, dk).transpose(1, 2)
+    pp = _q(F.linear(_q(pos_emb), _q(sd[p + ".linear_pos.weight"]))).view(1, -1, H, dk).transpose(1, 2)
+    qu = _q(q + sd[p + ".pos_bias_u"]).transpose(1, 2)
+    qv = _q(q + sd[p + ".pos_bias_v"]).transpose(1, 2)
     ac = torch.matmul(qu, k.transpose(-2, -1))
     bd = torch.matmul(qv, pp.transpose(-2, -1))
     scores = (ac + bd) / math.sqrt(dk)
@@ -90,8 +104,17 @@ def _attend(v, scores, mask, sd: SD, p: str):
     B = v.shape[0]
     m = mask.unsqueeze(1).eq(0)
     scores = scores.masked_fill(m, -float("inf"))
-    attn = torch.softmax(scores, dim=-1).masked_fill(m, 0.0)
-    x = torch.matmul(attn, v).transpose(1, 2).contiguous().view(B, -1, v.shape[1] * v.shape[3])
+    if EMULATE_BF16:   # probabilities are rounded to bf16 for P.V, the normaliser is the fp32 sum
+        mx = scores.amax(dim=-1, keepdim=True)
+        mx = torch.where(torch.isinf(mx), torch.zeros_like(mx), mx)
+        e = torch.exp(scores - mx).masked_fill(m, 0.0)
+        den = e.sum(dim=-1, keepdim=True)
+        x = torch.matmul(_q(e), v) / torch.where(den > 0, den, torch.ones_like(den))
+        x = _q(x)
+    else:
+        attn = torch.softmax(scores, dim=-1).masked_fill(m, 0.0)
+        x = torch.matmul(attn, v)
+    x = x.transpose(1, 2).contiguous().view(B, -1, v.shape[1] * v.shape[3])
     return _lin(x, sd, p + ".linear_out")
 
 
@@ -99,9 +122,9 @@ def mha(q_in, kv_in, mask, sd: SD, p: str, H: int):
     """MultiHeadedAttention.forward (transformer/attention.py:129-175)."""
     B, Tq, d = q_in.shape
     dk = d // H
-    q = _lin(q_in, sd, p + ".linear_q").view(B, Tq, H, dk).transpose(1, 2)
-    k = _lin(kv_in, sd, p + ".linear_k").view(B, -1, H, dk).transpose(1, 2)
-    v = _lin(kv_in, sd, p + ".linear_v").view(B, -1, H, dk).transpose(1, 2)
+    q = _q(_lin(q_in, sd, p + ".linear_q")).view(B, Tq, H, dk).transpose(1, 2)
+    k = _q(_lin(kv_in, sd, p + ".linear_k")).view(B, -1, H, dk).transpose(1, 2)
+    v = _q(_lin(kv_in, sd, p + ".linear_v")).view(B, -1, H, dk).transpose(1, 2)
     scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk)
     return _attend(v, scores, mask, sd, p)
 
@@ -112,8 +135,8 @@ def conv_module(x, mask_pad, sd: SD, p: str, K: int, causal: bool, layer_norm: b
     x = x.masked_fill(~mask_pad, 0.0)
     if causal:
         x = F.pad(x, (K - 1, 0), "constant", 0.0)
-    x = F.conv1d(x, sd[p + ".pointwise_conv1.weight"], sd[p + ".pointwise_conv1.bias"])
-    x = F.glu(x, dim=1)
+    x = _q(F.conv1d(_q(x), _q(sd[p + ".pointwise_conv1.weight"]), sd[p + ".pointwise_conv1.bias"]))
+    x = _q(F.glu(x, dim=1))
     x = F.conv1d(x, sd[p + ".depthwise_conv.weight"], sd[p + ".depthwise_conv.bias"],
                  padding=0 if causal else (K - 1) // 2, groups=x.shape[1])
     if layer_norm:
@@ -121,18 +144,22 @@ def conv_module(x, mask_pad, sd: SD, p: str, K: int, causal: bool, layer_norm: b
     else:
         x = F.silu(F.batch_norm(x, sd[p + ".norm.running_mean"], sd[p + ".norm.running_var"],
                                 sd[p + ".norm.weight"], sd[p + ".norm.bias"], False, 0.0, 1e-5))
-    x = F.conv1d(x, sd[p + ".pointwise_conv2.weight"], sd[p + ".pointwise_conv2.bias"])
+    x = F.conv1d(_q(x), _q(sd[p + ".pointwise_conv2.weight"]), sd[p + ".pointwise_conv2.bias"])
     x = x.masked_fill(~mask_pad, 0.0)
     return x.transpose(1, 2)
 
 
 def ffn(x, sd: SD, p: str, act):
     """PositionwiseFeedForward.forward (transformer/positionwise_feed_forward.py:47-55)."""
-    return _lin(act(_lin(x, sd, p + ".w_1")), sd, p + ".w_2")
+    return _lin(_q(act(_lin(x, sd, p + ".w_1"))), sd, p + ".w_2")
 
 
 def lsl_mix(x, sd: SD, p: str, cat_embs: torch.Tensor):
     """y = sum_i cat_embs[i] * language_layers[i](x)  (encoder_layer.py:376-390)."""
+    if EMULATE_BF16:   # the engine folds W = sum_i c_i W_i (fp32) and stores it as bf16
+        w = sum(cat_embs[i] * sd[f"{p}.language_layers.{i}.weight"] for i in range(cat_embs.shape[0]))
+        b = sum(cat_embs[i] * sd[f"{p}.language_layers.{i}.bias"] for i in range(cat_embs.shape[0]))
+        return F.linear(_q(x), _q(w), b)
     y = None
     for i in range(cat_embs.shape[0]):
         t = cat_embs[i] * _lin(x, sd, f"{p}.language_layers.{i}")

@@ -50,35 +50,31 @@ def rescoring_pick(hyps: Sequence[tuple], ctc_scores: Sequence[float], nbest_tim
                    r2l: Optional[np.ndarray], ctc_weight: float, reverse_weight: float) -> DecodeResult:
     """Combine decoder and CTC scores and keep the first strict maximum (search.py:413-447).
 
-    l2r[i, j] = log p(w_j | w_<j) for j < U_i and l2r[i, U_i] = log p(eos); r2l likewise for the
-    right-to-left decoder (already re-indexed to hypothesis order).  Like the reference, the decoder
-    scores are accumulated in float32 (they are 0-d float32 tensors there); confidences and the CTC
-    term use double precision Python floats.
+    l2r[i, j] = log p(w_j | w_<j) for j < U_i, l2r[i, U_i] = log p(eos), zeros behind; r2l likewise for the
+    right-to-left decoder (already re-indexed to hypothesis order).  Float semantics follow the reference: the
+    decoder scores are summed sequentially in float32 (0-d float32 tensors there) — `np.add.accumulate` is the same
+    left-to-right float32 recurrence, and the trailing zeros are exact no-ops — while confidences and the CTC term
+    go through double precision Python floats.
     """
-    best_score, best_index = -float("inf"), 0
-    confidences, tok_conf = [], []
-    rw32 = np.float32(reverse_weight)
-    for i, hyp in enumerate(hyps):
-        U = len(hyp)
-        score = np.float32(0.0)
-        tc = []
-        for j in range(U):
-            s = np.float32(l2r[i, j])
-            score = np.float32(score + s)
-            tc.append(math.exp(float(s)))
-        score = np.float32(score + np.float32(l2r[i, U]))
-        if reverse_weight > 0 and r2l is not None:
-            r_score = np.float32(0.0)
-            for j in range(U):
-                s = np.float32(r2l[i, j])
-                r_score = np.float32(r_score + s)
-                tc[j] = (tc[j] + math.exp(float(s))) / 2
-            r_score = np.float32(r_score + np.float32(r2l[i, U]))
-            score = np.float32(np.float32(score * np.float32(1 - reverse_weight)) + np.float32(r_score * rw32))
-        confidences.append(math.exp(float(np.float32(score / np.float32(U + 1)))))
-        score = np.float32(score + np.float32(ctc_scores[i] * ctc_weight))
-        if float(score) > best_score:
-            best_score, best_index = float(score), i
-        tok_conf.append(tc)
-    return DecodeResult(hyps[best_index], best_score, confidence=confidences[best_index],
-                        times=nbest_times[best_index], tokens_confidence=tok_conf[best_index])
+    n = len(hyps)
+    lens = np.fromiter((len(h) for h in hyps), dtype=np.int64, count=n)
+    score = np.add.accumulate(np.ascontiguousarray(l2r[:n], dtype=np.float32), axis=1, dtype=np.float32)[:, -1]
+    use_r = reverse_weight > 0 and r2l is not None
+    if use_r:
+        r_score = np.add.accumulate(np.ascontiguousarray(r2l[:n], dtype=np.float32), axis=1, dtype=np.float32)[:, -1]
+        score = (score * np.float32(1 - reverse_weight) + r_score * np.float32(reverse_weight)).astype(np.float32)
+    norm = (score / (lens + 1).astype(np.float32)).astype(np.float32)
+    ctc_term = np.asarray([c * ctc_weight for c in ctc_scores[:n]], dtype=np.float64).astype(np.float32)
+    total = (score + ctc_term).astype(np.float32)
+    best = int(np.argmax(total)) if n and not np.isnan(total).any() else 0     # first maximum == strict `>` scan
+    if n and np.isnan(total).any():                                            # keep the reference's scan semantics
+        best, best_score = 0, -float("inf")
+        for i in range(n):
+            if float(total[i]) > best_score:
+                best, best_score = i, float(total[i])
+    U = int(lens[best])
+    tc = [math.exp(float(l2r[best, j])) for j in range(U)]
+    if use_r:
+        tc = [(tc[j] + math.exp(float(r2l[best, j]))) / 2 for j in range(U)]
+    return DecodeResult(hyps[best], float(total[best]), confidence=math.exp(float(norm[best])),
+                        times=nbest_times[best], tokens_confidence=tc)

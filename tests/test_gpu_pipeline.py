@@ -84,6 +84,54 @@ def test_fbank_and_encoder_vs_reference_fixture(asr, golden_cases, model_dirs, c
 
 
 @pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_encoder_and_decoder_vs_bf16_emulating_oracle(asr, golden_cases, model_dirs, case):
+    """Tight check of the kernels' logic: against the oracle with EMULATE_BF16 (it rounds to bf16 exactly where the
+    engine stores bf16, everything else fp32) the only difference left is accumulation order, so the tolerance is
+    ~10x tighter than against the pure-fp32 reference: encoder rel-RMS < 4e-3, log-probs 0.1 abs, decoder 0.03."""
+    from oracle import model_ref, pipeline_ref, search_ref
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    orc = pipeline_ref.OracleASR(model_dirs[case][0])
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0)
+    model_ref.EMULATE_BF16 = True
+    try:
+        for bi, (fb, fl) in enumerate(orc.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])):
+            with torch.no_grad():
+                want, want_lens, _ = orc.forward_encoder(fb, fl, cat)
+                want_logp = model_ref.ctc_logprobs(want, orc.sd)
+            enc, enc_lens = m.model._forward_encoder(fb.cuda(), fl, cat)
+            logp = m.model.ctc_logprobs(enc).cpu().numpy()
+            got = enc.cpu().numpy()
+            worst = 0.0
+            for b in range(fb.shape[0]):
+                n = int(enc_lens[b])
+                worst = max(worst, _rel_rms(got[b, :n], want[b, :n].numpy()))
+                sel = want_logp[b, :n].numpy() > -12
+                assert np.abs(logp[b, :n][sel] - want_logp[b, :n].numpy()[sel]).max() < 0.1
+            print(f"[{case}] encoder rel-rms vs bf16-emulating oracle: {worst:.2e}; "
+                  f"vs fp32 reference: {_rel_rms(got[0, :int(enc_lens[0])], arr[f'enc_out_{bi}'][0, :int(enc_lens[0])]):.2e}")
+            assert worst < 4e-3
+            # decoder on the fp32 reference encoder_out / n-best
+            g = meta["batches"][bi]["ctc_prefix_beam_search"]
+            nbest = [[tuple(h) for h in r["nbest"]] for r in g]
+            encr = torch.from_numpy(arr[f"enc_out_{bi}"])
+            lens = arr[f"enc_lens_{bi}"]
+            l2r, _ = m.engine.rescoring_scores(encr.cuda(), lens, nbest, cat, 0.0)
+            for b, hyps in enumerate(nbest):
+                ys, ylens = search_ref.rescoring_inputs(hyps, orc.sos, orc.eos)
+                mem = encr[b, :int(lens[b])].unsqueeze(0).repeat(len(hyps), 1, 1)
+                with torch.no_grad():
+                    dec = torch.log_softmax(model_ref.decoder_forward(mem, ys, ylens, orc.sd, orc.cfg, "left_decoder", cat), -1)
+                for i, h in enumerate(hyps):
+                    U = len(h)
+                    want_s = [float(dec[i, j, h[j]]) for j in range(U)] + [float(dec[i, U, orc.eos])]
+                    np.testing.assert_allclose(l2r[b, i, :U + 1], want_s, rtol=0, atol=0.03)
+    finally:
+        model_ref.EMULATE_BF16 = False
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
 def test_rescoring_decoder_vs_oracle(asr, golden_cases, model_dirs, case):
     """teacher-forced decoder log-probs on the reference's encoder_out / n-best: vs the CPU oracle."""
     from oracle import model_ref, pipeline_ref, search_ref
