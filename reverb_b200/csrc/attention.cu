@@ -15,7 +15,8 @@
 
 namespace rvb {
 
-constexpr int ATT_BM = 64;   // queries per CTA (16 per warp)
+constexpr int ATT_BM = 128;  // queries per CTA (16 per warp, 8 warps): halves the K/V/P re-reads vs 64
+constexpr int ATT_THREADS = ATT_BM * 2;
 constexpr int ATT_BN = 64;   // keys per tile
 constexpr int ATT_PAD = 8;   // bf16 padding per smem row (keeps ldmatrix conflict-free)
 
@@ -64,7 +65,7 @@ struct AttnKParams {
 };
 
 template <int DK, bool HAS_POS>
-__global__ void __launch_bounds__(128) attention_kernel(const AttnKParams prm) {
+__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnKParams prm) {
   constexpr int LDS = DK + ATT_PAD;          // smem row stride (elements)
   constexpr int TILE = ATT_BN * LDS;         // elements per staged matrix
   constexpr int NMAT = HAS_POS ? 3 : 2;      // K, V, (P)
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(128) attention_kernel(const AttnKParams prm) {
   auto load_tile = [&](int tile, int buf) {
     bf16* dst = sbuf + (size_t)buf * NMAT * TILE;
     constexpr int CH = DK / 8;  // 16-byte chunks per row
-    for (int i = threadIdx.x; i < ATT_BN * CH; i += 128) {
+    for (int i = threadIdx.x; i < ATT_BN * CH; i += ATT_THREADS) {
       int r = i / CH, c = i - r * CH;
       int key = tile * ATT_BN + r;
       bool ok = key < prm.Tk;
@@ -271,7 +272,7 @@ static int launch_attn_t(const AttnKParams& p, int Bq, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((p.Tq + ATT_BM - 1) / ATT_BM, p.H, Bq);
-  attention_kernel<DK, HAS_POS><<<grid, 128, smem, stream>>>(p);
+  attention_kernel<DK, HAS_POS><<<grid, ATT_THREADS, smem, stream>>>(p);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;

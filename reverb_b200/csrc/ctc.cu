@@ -190,98 +190,186 @@ size_t prefix_beam_workspace_bytes(int B, int T, int beam) {
 struct PBSlot {
   double s, ns, vs, vns, ctp;
   int times_s;           // times list node (-1 = empty list)
-  int tns_src, tns_op;   // times_ns recipe: op 0 = keep src as is / none, 1 = append t, 2 = replace last by t
-  int key;               // first-touch order key (lower = inserted earlier)
+  int tns_src, tns_op;   // times_ns recipe: op 0 = none, 1 = append t to list tns_src, 2 = replace last of tns_src by t
   int src, tok;          // extension slots: source beam entry and token; stay slots: src = own index, tok = -1
 };
 
-__global__ void __launch_bounds__(32)
+constexpr int PB_THREADS = 128;
+constexpr int PB_KEY_NONE = 0x7fffffff;
+
+// One CTA (4 warps) per utterance.  Per frame:
+//   P0  stage the frame's top-k, derive score()/viterbi_score()/times() of every beam prefix
+//   P1  "stay" slots (prefix unchanged): at most three updates land on prefix j — blank, repeat of its last token,
+//       and the one extension parent(j)+last(j) that equals j — replayed in the reference's iteration order;
+//       extension slots: one thread per (token, prefix) pair, final at once unless it collides with a stay slot
+//   P2  score() of every touched slot          P3  rank (score desc, dict insertion order asc), keep top `beam`,
+//       materialise survivors: canonical trie node (find-or-create in a shared-memory hash), times list nodes
+// Prefix identity = canonical trie node id, so dict-merge semantics of the reference hold exactly.
+__global__ void __launch_bounds__(PB_THREADS)
 ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict__ topk_idx, int k,
                        const int* __restrict__ lens, int T, int beam, int blank, int* __restrict__ workspace,
-                       int max_len, int* __restrict__ out_tokens, int* __restrict__ out_times,
+                       int trie_in_smem, int max_len, int* __restrict__ out_tokens, int* __restrict__ out_times,
                        int* __restrict__ out_lens, double* __restrict__ out_scores, int* __restrict__ out_nhyp) {
-  const int b = blockIdx.x, lane = threadIdx.x;
+  extern __shared__ int pb_dyn[];
+  const int b = blockIdx.x, tid = threadIdx.x;
   const PBLayout L = pb_layout(T, beam);
   int* ws = workspace + (size_t)b * L.per_utt_ints;
-  int* trie_parent = ws;
-  int* trie_tok = ws + L.pool_cap;
-  int* hash = ws + 2 * L.pool_cap;  // pre-set to -1 by the host (cudaMemsetAsync 0xFF)
-  int* times_parent = hash + L.hash_cap;
+  int* trie_parent = trie_in_smem ? pb_dyn : ws;
+  int* trie_tok = trie_parent + L.pool_cap;
+  int* hash = trie_parent + 2 * L.pool_cap;  // -1 = empty
+  int* times_parent = ws + 2 * L.pool_cap + L.hash_cap;
   int* times_t = times_parent + L.times_cap;
 
   __shared__ PBSlot slots[PB_MAXSLOTS];
+  __shared__ double slot_score[PB_MAXSLOTS];
+  __shared__ int slot_key[PB_MAXSLOTS];
   __shared__ double c_s[PB_MAXBEAM], c_ns[PB_MAXBEAM], c_vs[PB_MAXBEAM], c_vns[PB_MAXBEAM];
   __shared__ double c_score[PB_MAXBEAM], c_vit[PB_MAXBEAM];
-  __shared__ int c_node[PB_MAXBEAM], c_ts[PB_MAXBEAM], c_tns[PB_MAXBEAM], c_times[PB_MAXBEAM];
+  __shared__ int c_node[PB_MAXBEAM], c_ts[PB_MAXBEAM], c_tns[PB_MAXBEAM], c_tnsp[PB_MAXBEAM], c_times[PB_MAXBEAM];
   __shared__ int c_last[PB_MAXBEAM], c_par[PB_MAXBEAM];
   __shared__ double n_s[PB_MAXBEAM], n_ns[PB_MAXBEAM], n_vs[PB_MAXBEAM], n_vns[PB_MAXBEAM];
-  __shared__ int n_node[PB_MAXBEAM], n_ts[PB_MAXBEAM], n_tns[PB_MAXBEAM];
-  __shared__ short cand_slot[PB_MAXBEAM * PB_MAXBEAM];
-  __shared__ short live[PB_MAXSLOTS];
-  __shared__ double live_score[PB_MAXSLOTS];
-  __shared__ int s_nlive, s_pool, s_times;
+  __shared__ int n_node[PB_MAXBEAM], n_ts[PB_MAXBEAM], n_tns[PB_MAXBEAM], n_tnsp[PB_MAXBEAM];
+  __shared__ double s_tv[PB_MAXBEAM];
+  __shared__ int s_ti[PB_MAXBEAM];
+  __shared__ int s_pool, s_times;
 
-  if (lane == 0) {
+  if (trie_in_smem)
+    for (int i = tid; i < L.hash_cap; i += PB_THREADS) hash[i] = -1;
+  if (tid == 0) {
     trie_parent[0] = -1;
     trie_tok[0] = -1;
     s_pool = 1;
     s_times = 0;
-    c_node[0] = 0;
-    c_s[0] = 0.0;
-    c_ns[0] = PB_NEG_INF;
-    c_vs[0] = 0.0;
-    c_vns[0] = 0.0;
-    c_ts[0] = -1;
-    c_tns[0] = -1;
+    n_node[0] = 0;
+    n_s[0] = 0.0;
+    n_ns[0] = PB_NEG_INF;
+    n_vs[0] = 0.0;
+    n_vns[0] = 0.0;
+    n_ts[0] = -1;
+    n_tns[0] = -1;
+    n_tnsp[0] = -1;
   }
   int nb = 1;
   const int len = min(lens[b], T);
-  __syncwarp();
+  const int kk = min(k, beam);
+  __syncthreads();
 
   for (int t = 0; t < len; ++t) {
-    const float* tv = topk_val + ((long long)b * T + t) * k;
-    const int* ti = topk_idx + ((long long)b * T + t) * k;
-    const int kk = min(k, beam);
-    // ---- 1. per-prefix derived quantities
-    if (lane < nb) {
-      c_score[lane] = log_add2(c_s[lane], c_ns[lane]);
-      const bool sb = c_vs[lane] > c_vns[lane];
-      c_vit[lane] = sb ? c_vs[lane] : c_vns[lane];
-      c_times[lane] = sb ? c_ts[lane] : c_tns[lane];
-      const int node = c_node[lane];
-      c_last[lane] = trie_tok[node];
-      c_par[lane] = trie_parent[node];
-      PBSlot& s = slots[lane];
-      s.s = s.ns = s.vs = s.vns = s.ctp = PB_NEG_INF;
-      s.times_s = -1;
-      s.tns_src = -1;
-      s.tns_op = 0;
-      s.key = 0x7fffffff;
-      s.src = lane;
-      s.tok = -1;
+    // ---- P0
+    if (tid < kk) {
+      s_tv[tid] = (double)topk_val[((long long)b * T + t) * k + tid];
+      s_ti[tid] = topk_idx[((long long)b * T + t) * k + tid];
     }
-    __syncwarp();
-    // ---- 2. resolve the target slot of every (token, prefix) extension; non-colliding ones are final at once
+    if (tid < nb) {
+      const int j = tid;
+      const double s = n_s[j], ns = n_ns[j], vs = n_vs[j], vns = n_vns[j];
+      c_s[j] = s;
+      c_ns[j] = ns;
+      c_vs[j] = vs;
+      c_vns[j] = vns;
+      c_ts[j] = n_ts[j];
+      c_tns[j] = n_tns[j];
+      c_tnsp[j] = n_tnsp[j];
+      const int node = n_node[j];
+      c_node[j] = node;
+      c_score[j] = log_add2(s, ns);
+      const bool sb = vs > vns;
+      c_vit[j] = sb ? vs : vns;
+      c_times[j] = sb ? n_ts[j] : n_tns[j];
+      c_last[j] = trie_tok[node];
+      c_par[j] = trie_parent[node];
+      PBSlot& sl = slots[j];
+      sl.s = sl.ns = sl.vs = sl.vns = sl.ctp = PB_NEG_INF;
+      sl.times_s = -1;
+      sl.tns_src = -1;
+      sl.tns_op = 0;
+      sl.src = j;
+      sl.tok = -1;
+      slot_key[j] = PB_KEY_NONE;
+    }
+    __syncthreads();
     const int ncand = kk * nb;
-    for (int c = lane; c < ncand; c += 32) {
+    const int nslots = nb + ncand;
+    // ---- P1a: stay slots
+    if (tid < nb) {
+      const int j = tid;
+      PBSlot& n = slots[j];
+      const int last_j = c_last[j];
+      const bool nonempty = c_node[j] != 0;
+      int ui_blank = -1, ui_last = -1, ip = -1;
+      for (int u = 0; u < kk; ++u) {
+        if (s_ti[u] == blank) ui_blank = u;
+        if (nonempty && s_ti[u] == last_j) ui_last = u;
+      }
+      if (nonempty && ui_last >= 0)
+        for (int i = 0; i < nb; ++i)
+          if (c_node[i] == c_par[j]) ip = i;
+      // events sorted by candidate index c = ui * nb + i
+      int ev_c[3], ev_type[3], ne = 0;  // type 0 blank, 1 repeat, 2 collision
+      if (ui_blank >= 0) { ev_c[ne] = ui_blank * nb + j; ev_type[ne++] = 0; }
+      if (ui_last >= 0) { ev_c[ne] = ui_last * nb + j; ev_type[ne++] = 1; }
+      if (ui_last >= 0 && ip >= 0) { ev_c[ne] = ui_last * nb + ip; ev_type[ne++] = 2; }
+      for (int a = 1; a < ne; ++a)
+        for (int q = a; q > 0 && ev_c[q] < ev_c[q - 1]; --q) {
+          int tc = ev_c[q]; ev_c[q] = ev_c[q - 1]; ev_c[q - 1] = tc;
+          int tt = ev_type[q]; ev_type[q] = ev_type[q - 1]; ev_type[q - 1] = tt;
+        }
+      int key = PB_KEY_NONE;
+      for (int a = 0; a < ne; ++a) {
+        const int ty = ev_type[a];
+        if (ty == 0) {
+          const double p = s_tv[ui_blank];
+          if (key == PB_KEY_NONE) key = 2 * ev_c[a];
+          n.s = log_add2(n.s, c_score[j] + p);
+          n.vs = c_vit[j] + p;
+          n.times_s = c_times[j];
+        } else if (ty == 1) {
+          const double p = s_tv[ui_last];
+          if (key == PB_KEY_NONE) key = 2 * ev_c[a];
+          n.ns = log_add2(n.ns, c_ns[j] + p);
+          if (n.vns < c_vns[j] + p) {
+            // reference typo (`vs_ns`, search.py:178): v_ns is NOT updated here
+            if (n.ctp < p) {
+              n.ctp = p;
+              n.tns_src = c_tnsp[j];  // parent of prefix j's times_ns list: "copy, then overwrite the last element"
+              n.tns_op = 2;
+            }
+          }
+        } else {
+          const double p = s_tv[ui_last];
+          if (key == PB_KEY_NONE) key = 2 * ev_c[a] + 1;
+          const bool rep = (last_j == c_last[ip]) && (c_node[ip] != 0);
+          const double add = rep ? c_s[ip] : c_score[ip];
+          const double vit = rep ? c_vs[ip] : c_vit[ip];
+          n.ns = log_add2(n.ns, add + p);
+          if (n.vns < vit + p) {
+            n.vns = vit + p;
+            n.ctp = p;
+            n.tns_src = rep ? c_ts[ip] : c_times[ip];
+            n.tns_op = 1;
+          }
+        }
+      }
+      slot_key[j] = key;
+    }
+    // ---- P1b: extension slots, one thread per (token, prefix) candidate
+    for (int c = tid; c < ncand; c += PB_THREADS) {
       const int ui = c / nb, i = c - ui * nb;
-      const int u = ti[ui];
-      const double p = (double)tv[ui];
-      int target = -1;
-      PBSlot& e = slots[nb + c];
-      e.key = 0x7fffffff;
+      const int u = s_ti[ui];
+      const double p = s_tv[ui];
+      int key = PB_KEY_NONE;
       if (u != blank) {
-        target = nb + c;
         const int node_i = c_node[i];
-        for (int j = 0; j < nb; ++j)
-          if (c_par[j] == node_i && c_last[j] == u && c_node[j] != 0) target = j;
-        if (target == nb + c) {
-          const bool rep = (u == c_last[i]) && (c_node[i] != 0);
-          // single contribution into a fresh PrefixScore (s = ns = v_s = v_ns = -inf)
+        bool collide = false;
+        for (int j = 0; j < nb; ++j) collide |= (c_par[j] == node_i && c_last[j] == u && c_node[j] != 0);
+        if (!collide) {
+          PBSlot& e = slots[nb + c];
+          const bool rep = (u == c_last[i]) && (node_i != 0);
+          // a single contribution into a fresh PrefixScore (s = ns = v_s = v_ns = -inf): log_add([-inf, x]) == x
           const double add = rep ? c_s[i] : c_score[i];
           const double vit = rep ? c_vs[i] : c_vit[i];
           e.s = PB_NEG_INF;
-          e.ns = add + p;           // log_add([-inf, x]) == x
+          e.ns = add + p;
           e.vs = PB_NEG_INF;
           e.vns = PB_NEG_INF;
           e.ctp = PB_NEG_INF;
@@ -294,165 +382,100 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
             e.tns_src = rep ? c_ts[i] : c_times[i];
             e.tns_op = 1;
           }
-          e.key = 2 * c + 1;
           e.src = i;
           e.tok = u;
+          key = 2 * c + 1;
         }
       }
-      cand_slot[c] = (short)target;
+      slot_key[nb + c] = key;
     }
-    __syncwarp();
-    // ---- 3. "stay" slots: lane j replays, in the reference's iteration order, every update that lands on prefix j
-    if (lane < nb) {
-      const int j = lane;
-      PBSlot& n = slots[j];
-      const int last_j = c_last[j];
-      const bool nonempty = c_node[j] != 0;
-      for (int c = 0; c < ncand; ++c) {
-        const int ui = c / nb, i = c - ui * nb;
-        const int u = ti[ui];
-        const double p = (double)tv[ui];
-        if (i == j) {
-          if (u == blank) {
-            if (n.key == 0x7fffffff) n.key = 2 * c;
-            n.s = log_add2(n.s, c_score[j] + p);
-            n.vs = c_vit[j] + p;
-            n.times_s = c_times[j];
-          } else if (nonempty && u == last_j) {
-            if (n.key == 0x7fffffff) n.key = 2 * c;
-            n.ns = log_add2(n.ns, c_ns[j] + p);
-            if (n.vns < c_vns[j] + p) {
-              // reference typo (`vs_ns`, search.py:178): v_ns is NOT updated here
-              if (n.ctp < p) {
-                n.ctp = p;
-                n.tns_src = c_tns[j];
-                n.tns_op = 2;
-              }
-            }
-          }
-        }
-        if (cand_slot[c] == j) {  // an extension prefix_i + u that equals prefix j
-          if (n.key == 0x7fffffff) n.key = 2 * c + 1;
-          const bool rep = (u == c_last[i]) && (c_node[i] != 0);
-          const double add = rep ? c_s[i] : c_score[i];
-          const double vit = rep ? c_vs[i] : c_vit[i];
-          n.ns = log_add2(n.ns, add + p);
-          if (n.vns < vit + p) {
-            n.vns = vit + p;
-            n.ctp = p;
-            n.tns_src = rep ? c_ts[i] : c_times[i];
-            n.tns_op = 1;
-          }
-        }
-      }
-    }
-    __syncwarp();
-    // ---- 4. second beam prune: top-`beam` by score(), stable w.r.t. dict insertion order
-    if (lane == 0) {
-      int n = 0;
-      for (int sidx = 0; sidx < nb + ncand; ++sidx)
-        if (slots[sidx].key != 0x7fffffff) live[n++] = (short)sidx;
-      s_nlive = n;
-    }
-    __syncwarp();
-    const int nlive = s_nlive;
-    for (int a = lane; a < nlive; a += 32) {
-      const PBSlot& s = slots[live[a]];
-      live_score[a] = log_add2(s.s, s.ns);
-    }
-    __syncwarp();
+    __syncthreads();
+    // ---- P2: score() of every touched slot (extension slots have s = -inf: no transcendental)
+    for (int a = tid; a < nslots; a += PB_THREADS)
+      slot_score[a] = (slot_key[a] == PB_KEY_NONE) ? PB_NEG_INF : log_add2(slots[a].s, slots[a].ns);
+    __syncthreads();
+    // ---- P3: second beam prune (stable w.r.t. dict insertion order) + materialise the survivors
+    int nlive = 0;
+    for (int o = 0; o < nslots; ++o) nlive += (slot_key[o] != PB_KEY_NONE);
     const int nnew = min(beam, nlive);
-    for (int a = lane; a < nlive; a += 32) {
-      const double sc = live_score[a];
-      const int key = slots[live[a]].key;
+    for (int a = tid; a < nslots; a += PB_THREADS) {
+      const int key = slot_key[a];
+      if (key == PB_KEY_NONE) continue;
+      const double sc = slot_score[a];
       int rank = 0;
-      for (int o = 0; o < nlive; ++o) {
-        const double so = live_score[o];
-        if (so > sc || (so == sc && slots[live[o]].key < key)) ++rank;
+      for (int o = 0; o < nslots; ++o) {
+        const int ko = slot_key[o];
+        const double so = slot_score[o];
+        rank += (ko != PB_KEY_NONE) && (so > sc || (so == sc && ko < key));
       }
-      if (rank < nnew) {
-        // ---- 5. materialise survivor `a` as new beam entry `rank`
-        const PBSlot& s = slots[live[a]];
-        int node;
-        if (s.tok < 0) {
-          node = c_node[s.src];
-        } else {
-          // find-or-create canonical trie node (parent, tok)
-          const int parent = c_node[s.src];
-          unsigned h = ((unsigned)parent * 2654435761u) ^ ((unsigned)s.tok * 40503u + 0x9e3779b9u);
-          h &= (unsigned)(L.hash_cap - 1);
-          node = -1;
-          int fresh = -1;
-          while (true) {
-            int cur = atomicAdd(&hash[h], 0);
-            if (cur == -1) {
-              if (fresh < 0) {
-                fresh = atomicAdd(&s_pool, 1);
-                trie_parent[fresh] = parent;
-                trie_tok[fresh] = s.tok;
-                __threadfence_block();
-              }
-              int old = atomicCAS(&hash[h], -1, fresh);
-              if (old == -1) {
-                node = fresh;
-                break;
-              }
-              cur = old;
+      if (rank >= nnew) continue;
+      const PBSlot& s = slots[a];
+      int node;
+      if (s.tok < 0) {
+        node = c_node[s.src];
+      } else {
+        const int parent = c_node[s.src];
+        unsigned h = ((unsigned)parent * 2654435761u) ^ ((unsigned)s.tok * 40503u + 0x9e3779b9u);
+        h &= (unsigned)(L.hash_cap - 1);
+        node = -1;
+        int fresh = -1;
+        while (true) {
+          int cur = atomicAdd(&hash[h], 0);
+          if (cur == -1) {
+            if (fresh < 0) {
+              fresh = atomicAdd(&s_pool, 1);
+              trie_parent[fresh] = parent;
+              trie_tok[fresh] = s.tok;
+              __threadfence_block();
             }
-            if (trie_parent[cur] == parent && trie_tok[cur] == s.tok) {
-              node = cur;  // (a node allocated in `fresh` but lost the race is simply left unused)
+            int old = atomicCAS(&hash[h], -1, fresh);
+            if (old == -1) {
+              node = fresh;
               break;
             }
-            h = (h + 1) & (unsigned)(L.hash_cap - 1);
+            cur = old;
           }
+          if (trie_parent[cur] == parent && trie_tok[cur] == s.tok) {
+            node = cur;
+            break;
+          }
+          h = (h + 1) & (unsigned)(L.hash_cap - 1);
         }
-        int tns = -1;
-        if (s.tns_op == 1) {
-          tns = atomicAdd(&s_times, 1);
-          times_parent[tns] = s.tns_src;
-          times_t[tns] = t;
-        } else if (s.tns_op == 2) {
-          tns = atomicAdd(&s_times, 1);
-          times_parent[tns] = (s.tns_src >= 0) ? times_parent[s.tns_src] : -1;
-          times_t[tns] = t;
-        }
-        n_node[rank] = node;
-        n_s[rank] = s.s;
-        n_ns[rank] = s.ns;
-        n_vs[rank] = s.vs;
-        n_vns[rank] = s.vns;
-        n_ts[rank] = s.times_s;
-        n_tns[rank] = tns;
       }
+      int tns = -1, tnsp = -1;
+      if (s.tns_op != 0) {
+        tns = atomicAdd(&s_times, 1);
+        tnsp = s.tns_src;      // op 1: append to list tns_src; op 2: tns_src already is the parent to hang t on
+        times_parent[tns] = tnsp;
+        times_t[tns] = t;
+      }
+      n_node[rank] = node;
+      n_s[rank] = s.s;
+      n_ns[rank] = s.ns;
+      n_vs[rank] = s.vs;
+      n_vns[rank] = s.vns;
+      n_ts[rank] = s.times_s;
+      n_tns[rank] = tns;
+      n_tnsp[rank] = tnsp;
     }
-    __syncwarp();
     nb = nnew;
-    if (lane < nb) {
-      c_node[lane] = n_node[lane];
-      c_s[lane] = n_s[lane];
-      c_ns[lane] = n_ns[lane];
-      c_vs[lane] = n_vs[lane];
-      c_vns[lane] = n_vns[lane];
-      c_ts[lane] = n_ts[lane];
-      c_tns[lane] = n_tns[lane];
-    }
-    __syncwarp();
+    __syncthreads();
   }
 
   // ---- emit the n-best: tokens, score() and times() per surviving prefix, in beam order
-  if (lane == 0) out_nhyp[b] = nb;
-  if (lane < nb) {
-    const int r = lane;
+  if (tid == 0) out_nhyp[b] = nb;
+  if (tid < nb) {
+    const int r = tid;
     int n = 0;
-    for (int node = c_node[r]; node > 0; node = trie_parent[node]) ++n;
+    for (int node = n_node[r]; node > 0; node = trie_parent[node]) ++n;
     int* tok_out = out_tokens + ((long long)b * beam + r) * max_len;
     int* tim_out = out_times + ((long long)b * beam + r) * max_len;
     int pos = n;
-    for (int node = c_node[r]; node > 0; node = trie_parent[node]) {
+    for (int node = n_node[r]; node > 0; node = trie_parent[node]) {
       --pos;
       if (pos < max_len) tok_out[pos] = trie_tok[node];
     }
-    const int tl = (c_vs[r] > c_vns[r]) ? c_ts[r] : c_tns[r];
+    const int tl = (n_vs[r] > n_vns[r]) ? n_ts[r] : n_tns[r];
     int nt = 0;
     for (int q = tl; q >= 0; q = times_parent[q]) ++nt;
     pos = nt;
@@ -462,7 +485,7 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
     }
     out_lens[(b * beam + r) * 2 + 0] = n;
     out_lens[(b * beam + r) * 2 + 1] = nt;
-    out_scores[b * beam + r] = log_add2(c_s[r], c_ns[r]);
+    out_scores[b * beam + r] = log_add2(n_s[r], n_ns[r]);
   }
 }
 
@@ -474,10 +497,19 @@ int launch_ctc_prefix_beam(const float* topk_val, const int* topk_idx, int k, co
   const size_t need = prefix_beam_workspace_bytes(B, T, beam);
   RVB_REQUIRE(workspace_bytes >= need, "prefix beam: workspace too small (%zu < %zu)", workspace_bytes, need);
   if (B <= 0) return 0;
-  RVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0xFF, need, stream));
-  ctc_prefix_beam_kernel<<<B, 32, 0, stream>>>(topk_val, topk_idx, k, lens, T, beam, blank,
-                                               reinterpret_cast<int*>(workspace), max_len, out_tokens, out_times,
-                                               out_lens, out_scores, out_nhyp);
+  const PBLayout L = pb_layout(T, beam);
+  const size_t trie_bytes = ((size_t)2 * L.pool_cap + L.hash_cap) * sizeof(int);
+  const int trie_in_smem = trie_bytes <= 150 * 1024;
+  if (!trie_in_smem) RVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0xFF, need, stream));  // hash tables = -1
+  const size_t dyn = trie_in_smem ? trie_bytes : 0;
+  static size_t configured = 0;
+  if (dyn > configured) {
+    RVB_CHECK_CUDA(cudaFuncSetAttribute(ctc_prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    configured = dyn;
+  }
+  ctc_prefix_beam_kernel<<<B, PB_THREADS, dyn, stream>>>(topk_val, topk_idx, k, lens, T, beam, blank,
+                                                        reinterpret_cast<int*>(workspace), trie_in_smem, max_len,
+                                                        out_tokens, out_times, out_lens, out_scores, out_nhyp);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;

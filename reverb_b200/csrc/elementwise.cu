@@ -290,9 +290,161 @@ int launch_conv1(const float* feats, const float* mean, const float* istd, const
 // then one warp per frame does the channel reduction.  Layout stays (B, T, C): no transposes.
 constexpr int CM_TT = 16;
 
+// Fast path: K compile-time, each thread owns NIT channel pairs and keeps its CM_TT x 2 x NIT conv outputs in
+// registers (fully unrolled sliding window), LayerNorm statistics by two block reductions; only the GLU'd halo rows
+// live in shared memory (bf16), so 3 CTAs fit per SM at C = 1024.
+template <int K, int NIT, int NT>
+__global__ void __launch_bounds__(NT)
+conv_mid_fast_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_bias, const float* __restrict__ dw_w,
+                     const float* __restrict__ dw_b,
+                     const float* __restrict__ norm_w, const float* __restrict__ norm_b,
+                     const float* __restrict__ bn_mean, const float* __restrict__ bn_var, int use_ln, float eps,
+                     bf16* __restrict__ out, int T, int C, int causal) {
+  constexpr int ROWS = CM_TT + K - 1;
+  extern __shared__ __align__(16) uint8_t smem_cm[];
+  uint32_t* s_glu = reinterpret_cast<uint32_t*>(smem_cm);  // [ROWS][C/2] packed bf16 pairs
+  __shared__ float s_part[NT / 32][CM_TT];
+  __shared__ float s_stat[2][CM_TT];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * CM_TT;
+  const int left = causal ? (K - 1) : (K - 1) / 2;
+  const int C2 = C >> 1;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < ROWS * C2; i += NT) {
+    int r = i / C2, cp = i - r * C2;
+    int t = t0 - left + r;
+    uint32_t o = 0u;
+    if (t >= 0 && t < T) {
+      const bf16* xr = x + ((long long)b * T + t) * (2 * C);
+      float2 a = unpack_bf16x2(reinterpret_cast<const uint32_t*>(xr)[cp]);
+      float2 g = unpack_bf16x2(reinterpret_cast<const uint32_t*>(xr + C)[cp]);
+      o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
+    } else if (t < 0 && causal) {
+      // the reference left-pads K-1 zero frames BEFORE pointwise_conv1 (convolution.py:113-114,129-130), so the pad
+      // frames reach the depthwise conv as GLU(bias), not as zeros
+      float2 a = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + 2 * cp), __ldg(pw1_bias + 2 * cp + 1)));
+      float2 g = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + C + 2 * cp), __ldg(pw1_bias + C + 2 * cp + 1)));
+      o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
+    }
+    s_glu[i] = o;
+  }
+  __syncthreads();
+  float acc[NIT][CM_TT][2];
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int cp = threadIdx.x + it * NT;
+    const bool ok = cp < C2;
+    float w0[K], w1[K];
+    float b0 = 0.f, b1 = 0.f;
+    if (ok) {
+      b0 = __ldg(dw_b + 2 * cp);
+      b1 = __ldg(dw_b + 2 * cp + 1);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        w0[k] = __ldg(dw_w + (2 * cp) * K + k);
+        w1[k] = __ldg(dw_w + (2 * cp + 1) * K + k);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) w0[k] = w1[k] = 0.f;
+    }
+#pragma unroll
+    for (int t = 0; t < CM_TT; ++t) {
+      acc[it][t][0] = b0;
+      acc[it][t][1] = b1;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      float2 v = ok ? unpack_bf16x2(s_glu[r * C2 + cp]) : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        constexpr int dummy = 0;
+        (void)dummy;
+        const int t = r - k;  // compile-time after unrolling
+        if (t >= 0 && t < CM_TT) {
+          acc[it][t][0] = fmaf(w0[k], v.x, acc[it][t][0]);
+          acc[it][t][1] = fmaf(w1[k], v.y, acc[it][t][1]);
+        }
+      }
+    }
+  }
+  float mean[CM_TT], rstd[CM_TT];
+  if (use_ln) {
+    // pass 1: mean over channels
+#pragma unroll
+    for (int t = 0; t < CM_TT; ++t) {
+      float s = 0.f;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
+        if (threadIdx.x + it * NT < C2) s += acc[it][t][0] + acc[it][t][1];
+      s = warp_sum(s);
+      if (lane == 0) s_part[warp][t] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < CM_TT) {
+      float s = 0.f;
+      for (int w = 0; w < NT / 32; ++w) s += s_part[w][threadIdx.x];
+      s_stat[0][threadIdx.x] = s / (float)C;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < CM_TT; ++t) mean[t] = s_stat[0][t];
+    // pass 2: variance (two-pass, like ATen)
+#pragma unroll
+    for (int t = 0; t < CM_TT; ++t) {
+      float q = 0.f;
+#pragma unroll
+      for (int it = 0; it < NIT; ++it)
+        if (threadIdx.x + it * NT < C2) {
+          float d0 = acc[it][t][0] - mean[t], d1 = acc[it][t][1] - mean[t];
+          q += d0 * d0 + d1 * d1;
+        }
+      q = warp_sum(q);
+      if (lane == 0) s_part[warp][t] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x < CM_TT) {
+      float q = 0.f;
+      for (int w = 0; w < NT / 32; ++w) q += s_part[w][threadIdx.x];
+      s_stat[1][threadIdx.x] = rsqrtf(q / (float)C + eps);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < CM_TT; ++t) rstd[t] = s_stat[1][t];
+  }
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+    const int cp = threadIdx.x + it * NT;
+    if (cp >= C2) continue;
+    const int c0 = 2 * cp, c1 = 2 * cp + 1;
+    const float g0 = __ldg(norm_w + c0), g1 = __ldg(norm_w + c1), be0 = __ldg(norm_b + c0), be1 = __ldg(norm_b + c1);
+    float m0 = 0.f, m1 = 0.f, r0 = 1.f, r1 = 1.f;
+    if (!use_ln) {
+      m0 = __ldg(bn_mean + c0);
+      m1 = __ldg(bn_mean + c1);
+      r0 = rsqrtf(__ldg(bn_var + c0) + eps);
+      r1 = rsqrtf(__ldg(bn_var + c1) + eps);
+    }
+#pragma unroll
+    for (int t = 0; t < CM_TT; ++t) {
+      if (t0 + t >= T) continue;
+      float y0, y1;
+      if (use_ln) {
+        y0 = (acc[it][t][0] - mean[t]) * rstd[t] * g0 + be0;
+        y1 = (acc[it][t][1] - mean[t]) * rstd[t] * g1 + be1;
+      } else {
+        y0 = (acc[it][t][0] - m0) * r0 * g0 + be0;
+        y1 = (acc[it][t][1] - m1) * r1 * g1 + be1;
+      }
+      reinterpret_cast<uint32_t*>(out + ((long long)b * T + t0 + t) * C)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
+    }
+  }
+}
+
+// Generic fallback (any K <= 64, any even C): conv results staged in shared memory.
 __global__ void __launch_bounds__(256)
-conv_mid_kernel(const bf16* __restrict__ x, const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                const float* __restrict__ norm_w, const float* __restrict__ norm_b, const float* __restrict__ bn_mean,
+conv_mid_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_bias, const float* __restrict__ dw_w,
+                const float* __restrict__ dw_b, const float* __restrict__ norm_w, const float* __restrict__ norm_b, const float* __restrict__ bn_mean,
                 const float* __restrict__ bn_var, int use_ln, float eps, bf16* __restrict__ out, int T, int C, int K,
                 int causal) {
   extern __shared__ __align__(16) uint8_t smem_cm[];
@@ -303,7 +455,6 @@ conv_mid_kernel(const bf16* __restrict__ x, const float* __restrict__ dw_w, cons
   const int t0 = blockIdx.x * CM_TT;
   const int left = causal ? (K - 1) : (K - 1) / 2;
   const int C2 = C >> 1;
-  // stage GLU(x) rows [t0-left, t0-left+rows)
   for (int i = threadIdx.x; i < rows * C2; i += blockDim.x) {
     int r = i / C2, cp = i - r * C2;
     int t = t0 - left + r;
@@ -313,11 +464,14 @@ conv_mid_kernel(const bf16* __restrict__ x, const float* __restrict__ dw_w, cons
       float2 a = unpack_bf16x2(reinterpret_cast<const uint32_t*>(xr)[cp]);
       float2 g = unpack_bf16x2(reinterpret_cast<const uint32_t*>(xr + C)[cp]);
       o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
+    } else if (t < 0 && causal) {
+      float2 a = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + 2 * cp), __ldg(pw1_bias + 2 * cp + 1)));
+      float2 g = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + C + 2 * cp), __ldg(pw1_bias + C + 2 * cp + 1)));
+      o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
     }
     reinterpret_cast<uint32_t*>(s_glu)[i] = o;
   }
   __syncthreads();
-  // depthwise conv: thread owns channel pairs
   for (int cp = threadIdx.x; cp < C2; cp += blockDim.x) {
     float acc0[CM_TT], acc1[CM_TT];
     const float b0 = __ldg(dw_b + 2 * cp), b1 = __ldg(dw_b + 2 * cp + 1);
@@ -328,7 +482,6 @@ conv_mid_kernel(const bf16* __restrict__ x, const float* __restrict__ dw_w, cons
     }
     for (int r = 0; r < rows; ++r) {
       float2 v = unpack_bf16x2(reinterpret_cast<const uint32_t*>(s_glu)[r * C2 + cp]);
-      // row r contributes to output t = r - k for tap k
 #pragma unroll
       for (int t = 0; t < CM_TT; ++t) {
         int k = r - t;
@@ -348,38 +501,70 @@ conv_mid_kernel(const bf16* __restrict__ x, const float* __restrict__ dw_w, cons
     if (t0 + t >= T) continue;
     const float* row = s_conv + (size_t)t * C;
     bf16* orow = out + ((long long)b * T + t0 + t) * C;
+    float mean = 0.f, rstd = 1.f;
     if (use_ln) {
       float s = 0.f;
       for (int c = lane; c < C; c += 32) s += row[c];
-      const float mean = warp_sum(s) / (float)C;
+      mean = warp_sum(s) / (float)C;
       float q = 0.f;
       for (int c = lane; c < C; c += 32) {
         float dlt = row[c] - mean;
         q += dlt * dlt;
       }
-      const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-      for (int cp = lane; cp < C2; cp += 32) {
-        float2 v = reinterpret_cast<const float2*>(row)[cp];
-        float y0 = (v.x - mean) * rstd * __ldg(norm_w + 2 * cp) + __ldg(norm_b + 2 * cp);
-        float y1 = (v.y - mean) * rstd * __ldg(norm_w + 2 * cp + 1) + __ldg(norm_b + 2 * cp + 1);
-        reinterpret_cast<uint32_t*>(orow)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
+      rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    }
+    for (int cp = lane; cp < C2; cp += 32) {
+      float2 v = reinterpret_cast<const float2*>(row)[cp];
+      const int c0 = 2 * cp, c1 = 2 * cp + 1;
+      float y0, y1;
+      if (use_ln) {
+        y0 = (v.x - mean) * rstd * __ldg(norm_w + c0) + __ldg(norm_b + c0);
+        y1 = (v.y - mean) * rstd * __ldg(norm_w + c1) + __ldg(norm_b + c1);
+      } else {
+        y0 = (v.x - __ldg(bn_mean + c0)) * rsqrtf(__ldg(bn_var + c0) + eps) * __ldg(norm_w + c0) + __ldg(norm_b + c0);
+        y1 = (v.y - __ldg(bn_mean + c1)) * rsqrtf(__ldg(bn_var + c1) + eps) * __ldg(norm_w + c1) + __ldg(norm_b + c1);
       }
-    } else {
-      for (int cp = lane; cp < C2; cp += 32) {
-        float2 v = reinterpret_cast<const float2*>(row)[cp];
-        int c0 = 2 * cp, c1 = 2 * cp + 1;
-        float y0 = (v.x - __ldg(bn_mean + c0)) * rsqrtf(__ldg(bn_var + c0) + eps) * __ldg(norm_w + c0) + __ldg(norm_b + c0);
-        float y1 = (v.y - __ldg(bn_mean + c1)) * rsqrtf(__ldg(bn_var + c1) + eps) * __ldg(norm_w + c1) + __ldg(norm_b + c1);
-        reinterpret_cast<uint32_t*>(orow)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
-      }
+      reinterpret_cast<uint32_t*>(orow)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
     }
   }
 }
 
-int launch_conv_mid(const bf16* x, const float* dw_w, const float* dw_b, const float* norm_w, const float* norm_b,
+template <int K, int NIT, int NT>
+static int launch_conv_mid_fast(const bf16* x, const float* pw1_bias, const float* dw_w, const float* dw_b, const float* norm_w,
+                                const float* norm_b, const float* bn_mean, const float* bn_var, int use_ln, float eps,
+                                bf16* out, int B, int T, int C, int causal, cudaStream_t stream) {
+  const size_t smem = (size_t)(CM_TT + K - 1) * C * sizeof(bf16);
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    RVB_CHECK_CUDA(cudaFuncSetAttribute(conv_mid_fast_kernel<K, NIT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)smem));
+    configured = smem;
+  }
+  dim3 grid((T + CM_TT - 1) / CM_TT, B);
+  conv_mid_fast_kernel<K, NIT, NT><<<grid, NT, smem, stream>>>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln,
+                                                           eps, out, T, C, causal);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+int launch_conv_mid(const bf16* x, const float* pw1_bias, const float* dw_w, const float* dw_b, const float* norm_w, const float* norm_b,
                     const float* bn_mean, const float* bn_var, int use_layer_norm, float eps, bf16* out, int B, int T,
                     int C, int K, int causal, cudaStream_t stream) {
   RVB_REQUIRE(C % 2 == 0 && K >= 1 && K <= 64, "conv_mid: unsupported C=%d K=%d", C, K);
+  RVB_REQUIRE(!causal || pw1_bias != nullptr, "conv_mid: causal mode needs the pointwise_conv1 bias");
+  // one channel pair per thread when it fits a 512-thread CTA (C <= 1024), else two per thread (C <= 2048)
+  const int C2 = C / 2;
+#define RVB_CM(KK, NN, TT)                                                                                        \
+  return launch_conv_mid_fast<KK, NN, TT>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_layer_norm, eps, out, \
+                                          B, T, C, causal, stream)
+  if (K == 15 || K == 31 || K == 7) {
+    if (C2 <= 128) { if (K == 15) RVB_CM(15, 1, 128); if (K == 31) RVB_CM(31, 1, 128); RVB_CM(7, 1, 128); }
+    if (C2 <= 256) { if (K == 15) RVB_CM(15, 1, 256); if (K == 31) RVB_CM(31, 1, 256); RVB_CM(7, 1, 256); }
+    if (C2 <= 512) { if (K == 15) RVB_CM(15, 1, 512); if (K == 31) RVB_CM(31, 1, 512); RVB_CM(7, 1, 512); }
+    if (C2 <= 1024) { if (K == 15) RVB_CM(15, 2, 512); if (K == 31) RVB_CM(31, 2, 512); RVB_CM(7, 2, 512); }
+  }
+#undef RVB_CM
   const size_t smem = (size_t)(CM_TT + K - 1) * C * sizeof(bf16) + (size_t)CM_TT * C * sizeof(float);
   RVB_REQUIRE(smem <= 200 * 1024, "conv_mid: C=%d K=%d needs %zu B of shared memory", C, K, smem);
   static size_t configured = 0;
@@ -388,7 +573,7 @@ int launch_conv_mid(const bf16* x, const float* dw_w, const float* dw_b, const f
     configured = smem;
   }
   dim3 grid((T + CM_TT - 1) / CM_TT, B);
-  conv_mid_kernel<<<grid, 256, smem, stream>>>(x, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_layer_norm, eps,
+  conv_mid_kernel<<<grid, 256, smem, stream>>>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_layer_norm, eps,
                                                out, T, C, K, causal);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();

@@ -566,7 +566,7 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
     if (launch_layernorm(x, E.norm_conv.g, E.norm_conv.b, 1e-5f, (int)M, d, n, nullptr, d_lens, Tp, 1, stream))
       return -1;
     if (gemm(n, E.pw1, (int)M, ACT_NONE, OUT_BF16, pw, 1.f, stream)) return -1;
-    if (launch_conv_mid(pw, E.dw_w, E.dw_b, E.cnorm.g, E.cnorm.b, E.bn_mean, E.bn_var, c.cnn_layer_norm, 1e-5f, cm, B,
+    if (launch_conv_mid(pw, E.pw1.b, E.dw_w, E.dw_b, E.cnorm.g, E.cnorm.b, E.bn_mean, E.bn_var, c.cnn_layer_norm, 1e-5f, cm, B,
                         Tp, d, c.cnn_kernel, c.causal, stream))
       return -1;
     if (gemm(cm, E.pw2, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream, d_lens, Tp)) return -1;

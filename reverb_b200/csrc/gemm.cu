@@ -30,7 +30,7 @@ void set_gemm_impl(int impl) { g_gemm_impl = impl; }
 int get_gemm_impl() {
   if (g_gemm_impl < 0) {
     const char* e = getenv("RVB_GEMM");
-    g_gemm_impl = (e && strcmp(e, "simt") == 0) ? 1 : 0;
+    g_gemm_impl = (e && strcmp(e, "simt") == 0) ? 1 : (e && strcmp(e, "tc2") == 0) ? 2 : 0;
   }
   return g_gemm_impl;
 }
@@ -83,18 +83,60 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-// One thread stores 32 consecutive output columns [n0, n0+32) of one output row.
+// Epilogue variants (compile-time): the hot combinations get straight-line code, everything else goes through the
+// generic runtime path.  EPI_GENERIC reads act / out_mode from the kernel parameters.
+enum Epi { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_BF16_SILU = 2, EPI_F32 = 3, EPI_RESID = 4, EPI_GENERIC = 5 };
+
+__host__ __device__ inline int select_epi(int act, int out_mode) {
+  if (out_mode == OUT_BF16) return act == ACT_NONE ? EPI_BF16 : act == ACT_RELU ? EPI_BF16_RELU : EPI_BF16_SILU;
+  if (act == ACT_NONE) return out_mode == OUT_F32 ? EPI_F32 : EPI_RESID;
+  return EPI_GENERIC;
+}
+
+__device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// One thread stores 32 consecutive output columns [n0, n0+32) of one output row (n0 % 32 == 0).
+template <int EPI>
 __device__ __forceinline__ void store_chunk(const GemmKParams& p, long long out_row, int n0, const uint32_t* acc) {
   float v[32];
   const bool full = (n0 + 32 <= p.N);
+  constexpr int OUT = (EPI <= EPI_BF16_SILU) ? OUT_BF16 : (EPI == EPI_F32) ? OUT_F32 : OUT_RESID_F32;
+  const int out_mode = (EPI == EPI_GENERIC) ? p.out_mode : OUT;
+  // bias (vectorised when the whole chunk is in range; bias + n0 is 16-byte aligned because n0 % 32 == 0)
+  if (p.bias != nullptr) {
+    if (full && ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0)) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float x = __uint_as_float(acc[j]);
-    int n = n0 + j;
-    if (p.bias != nullptr && (full || n < p.N)) x += __ldg(p.bias + n);
-    v[j] = apply_act(x, p.act);
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+        v[4 * j + 0] = __uint_as_float(acc[4 * j + 0]) + b4.x;
+        v[4 * j + 1] = __uint_as_float(acc[4 * j + 1]) + b4.y;
+        v[4 * j + 2] = __uint_as_float(acc[4 * j + 2]) + b4.z;
+        v[4 * j + 3] = __uint_as_float(acc[4 * j + 3]) + b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]) + ((n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
   }
-  if (p.out_mode == OUT_BF16) {
+  if (EPI == EPI_BF16_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  } else if (EPI == EPI_BF16_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
+  } else if (EPI == EPI_GENERIC) {
+    if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (p.act == ACT_SILU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fast_silu(v[j]);
+    }
+  }
+  if (out_mode == OUT_BF16) {
     bf16* o = reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + n0;
     if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
@@ -110,7 +152,7 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, long long out_
       for (int j = 0; j < 32; ++j)
         if (n0 + j < p.N) o[j] = __float2bfloat16(v[j]);
     }
-  } else if (p.out_mode == OUT_F32) {
+  } else if (out_mode == OUT_F32) {
     float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
     if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
 #pragma unroll
@@ -123,14 +165,16 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, long long out_
   } else {  // OUT_RESID_F32
     float* o = reinterpret_cast<float*>(p.out) + out_row * p.ldo + n0;
     if (full && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+      float4 r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = reinterpret_cast<const float4*>(o)[j];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float4 r = reinterpret_cast<float4*>(o)[j];
-        r.x += p.alpha * v[4 * j];
-        r.y += p.alpha * v[4 * j + 1];
-        r.z += p.alpha * v[4 * j + 2];
-        r.w += p.alpha * v[4 * j + 3];
-        reinterpret_cast<float4*>(o)[j] = r;
+        r[j].x += p.alpha * v[4 * j];
+        r[j].y += p.alpha * v[4 * j + 1];
+        r[j].z += p.alpha * v[4 * j + 2];
+        r[j].w += p.alpha * v[4 * j + 3];
+        reinterpret_cast<float4*>(o)[j] = r[j];
       }
     } else {
       for (int j = 0; j < 32; ++j)
@@ -168,7 +212,7 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-template <int BN>
+template <int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKParams p) {
@@ -282,7 +326,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, acc);
         tmem_ld_wait();
-        if (orow >= 0) store_chunk(p, orow, t.n0 + c, acc);
+        if (orow >= 0) store_chunk<EPI>(p, orow, t.n0 + c, acc);
       }
       tc_fence_before();
       __syncwarp();
@@ -298,6 +342,179 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a CTA pair (cluster 2x1x1, same TPC) owns a 256 x BN tile.  Each CTA stages its own
+// 128 A rows and HALF of the B rows per k-block (32 KB / stage / SM instead of 48 KB), the leader CTA issues
+// tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs' shared memory and writes both CTAs' TMEM; TMA transaction
+// bytes of both CTAs are credited to the leader's `full` barrier, tcgen05.commit multicasts the `empty` / `tmem full`
+// arrivals to both CTAs, and both CTAs' epilogue warps arrive on the leader's `tmem empty` barrier.
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int BK = 64;
+  static constexpr uint32_t A_BYTES = 128 * BK * 2;
+  static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 6 : 8;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const GemmKParams p) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 2);   // one arrival per CTA's producer (on the leader's copy)
+      mbar_init(&empty[i], 1);  // multicast tcgen05.commit
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);  // 4 epilogue warps x 2 CTAs (on the leader's copy)
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_ptr, Cfg::TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int nkb = p.num_k_blocks;
+
+  auto tile_coord = [&](int tile) {
+    // cluster tile: 256 rows; this CTA owns rows [rank*128, rank*128+128) of it
+    TileCoord t;
+    int nb = tile % p.tiles_n;
+    int mt = tile / p.tiles_n;
+    t.n0 = nb * BN;
+    if (p.conv_mode) {
+      t.f = mt % p.conv_F2;
+      int r = mt / p.conv_F2;
+      t.row0 = (r % p.conv_tt) * 256 + (int)rank * 128;
+      t.b = r / p.conv_tt;
+    } else {
+      t.row0 = mt * 256 + (int)rank * 128;
+      t.b = 0;
+      t.f = 0;
+    }
+    return t;
+  };
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    uint32_t stage = 0, phase = 0;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      TileCoord t = tile_coord(tile);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
+        else mbar_arrive_remote(&full[stage], 0);
+        if (p.conv_mode) {
+          int tap = kb / p.conv_cblocks;
+          int cb = kb - tap * p.conv_cblocks;
+          int kh = tap / 3, kw = tap - kh * 3;
+          tma_load_4d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, 2 * t.f + kw, t.row0 + (kh >> 1),
+                          t.b * 2 + (kh & 1));
+        } else {
+          tma_load_4d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64, t.row0, 0, 0);
+        }
+        tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, t.n0 + (int)rank * (BN / 2));
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((256u >> 4) << 24);
+    uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      mbar_wait(&tempty[as], aphase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sA + stage * Cfg::A_BYTES));
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sB + stage * Cfg::B_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_f16_2sm(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+        umma_commit_2sm(&empty[stage], 3);
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      umma_commit_2sm(&tfull[as], 3);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
+    const int q = warp & 3;
+    uint32_t as = 0, aphase = 0;
+    for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
+      TileCoord t = tile_coord(tile);
+      mbar_wait(&tfull[as], aphase);
+      tc_fence_after();
+      const int r = q * 32 + lane;
+      const long long orow = output_row(p, t, r);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        if (t.n0 + c >= p.N) break;
+        uint32_t acc[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, acc);
+        tmem_ld_wait();
+        if (orow >= 0) store_chunk<EPI>(p, orow, t.n0 + c, acc);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tempty[as]);
+        else mbar_arrive_remote(&tempty[as], 0);
+      }
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
@@ -467,12 +684,16 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     cuuint32_t box[2] = {64, (cuuint32_t)BN};
     if (make_tmap(&tmB, a.W, 2, dims, str, box)) return -1;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    RVB_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)Cfg::SMEM_BYTES));
-    attr_set = true;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const GemmKParams) = nullptr;
+  switch (select_epi(a.act, a.out_mode)) {
+    case EPI_BF16: kern = gemm_tc_kernel<BN, EPI_BF16>; break;
+    case EPI_BF16_RELU: kern = gemm_tc_kernel<BN, EPI_BF16_RELU>; break;
+    case EPI_BF16_SILU: kern = gemm_tc_kernel<BN, EPI_BF16_SILU>; break;
+    case EPI_F32: kern = gemm_tc_kernel<BN, EPI_F32>; break;
+    case EPI_RESID: kern = gemm_tc_kernel<BN, EPI_RESID>; break;
+    default: kern = gemm_tc_kernel<BN, EPI_GENERIC>; break;
   }
+  RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
   p.tiles_n = (a.N + BN - 1) / BN;
   int tiles_m = a.conv_mode ? a.conv_B * a.conv_F2 * p.conv_tt : (a.M + 127) / 128;
   p.num_tiles = tiles_m * p.tiles_n;
@@ -484,7 +705,64 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
     RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
-  gemm_tc_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  if (g_prof_on) {
+    RVB_CHECK_CUDA(cudaEventRecord(rec.b, stream));
+    g_prof.push_back(rec);
+  }
+  return 0;
+}
+
+template <int BN>
+static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<BN>;
+  CUtensorMap tmA, tmB;
+  const long long lda = a.lda ? a.lda : a.K, ldw = a.ldw ? a.ldw : a.K;
+  if (a.conv_mode) {
+    cuuint64_t dims[4] = {(cuuint64_t)a.conv_C, (cuuint64_t)a.conv_F1, (cuuint64_t)a.conv_T1h,
+                          (cuuint64_t)(2 * a.conv_B)};
+    cuuint64_t str[3] = {(cuuint64_t)a.conv_C * 2, (cuuint64_t)a.conv_F1 * a.conv_C * 2,
+                         (cuuint64_t)a.conv_T1h * a.conv_F1 * a.conv_C * 2};
+    cuuint32_t box[4] = {64, 1, 128, 1};
+    if (make_tmap(&tmA, a.A, 4, dims, str, box)) return -1;
+  } else {
+    cuuint64_t dims[4] = {(cuuint64_t)a.K, (cuuint64_t)a.M, 1, 1};
+    cuuint64_t str[3] = {(cuuint64_t)lda * 2, (cuuint64_t)lda * 2 * a.M, (cuuint64_t)lda * 2 * a.M};
+    cuuint32_t box[4] = {64, 128, 1, 1};
+    if (make_tmap(&tmA, a.A, 4, dims, str, box)) return -1;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.N};
+    cuuint64_t str[1] = {(cuuint64_t)ldw * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)(BN / 2)};
+    if (make_tmap(&tmB, a.W, 2, dims, str, box)) return -1;
+  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const GemmKParams) = nullptr;
+  switch (select_epi(a.act, a.out_mode)) {
+    case EPI_BF16: kern = gemm_tc2_kernel<BN, EPI_BF16>; break;
+    case EPI_BF16_RELU: kern = gemm_tc2_kernel<BN, EPI_BF16_RELU>; break;
+    case EPI_BF16_SILU: kern = gemm_tc2_kernel<BN, EPI_BF16_SILU>; break;
+    case EPI_F32: kern = gemm_tc2_kernel<BN, EPI_F32>; break;
+    case EPI_RESID: kern = gemm_tc2_kernel<BN, EPI_RESID>; break;
+    default: kern = gemm_tc2_kernel<BN, EPI_GENERIC>; break;
+  }
+  RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+  p.tiles_n = (a.N + BN - 1) / BN;
+  if (a.conv_mode) p.conv_tt = (a.conv_T2 + 255) / 256;
+  int tiles_m = a.conv_mode ? a.conv_B * a.conv_F2 * p.conv_tt : (a.M + 255) / 256;
+  p.num_tiles = tiles_m * p.tiles_n;
+  int clusters = g_num_sms / 2;
+  if (p.num_tiles < clusters) clusters = p.num_tiles;
+  GemmProfRec rec;
+  if (g_prof_on) {
+    RVB_CHECK_CUDA(cudaEventCreate(&rec.a));
+    RVB_CHECK_CUDA(cudaEventCreate(&rec.b));
+    rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
+    RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
+  }
+  kern<<<2 * clusters, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   if (g_prof_on) {
@@ -546,6 +824,10 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
               "gemm: operands must be 16-byte aligned");
   RVB_REQUIRE((p.lda * 2) % 16 == 0 && (p.ldw * 2) % 16 == 0, "gemm: leading dimensions must be multiples of 8");
   if (get_encode_fn()) return -1;
+  if (get_gemm_impl() == 2) {
+    if (a.N > 128) return launch_tc2<256>(a, p, stream);
+    return launch_tc2<128>(a, p, stream);
+  }
   if (a.N > 128) return launch_tc<256>(a, p, stream);
   return launch_tc<128>(a, p, stream);
 }

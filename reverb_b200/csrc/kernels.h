@@ -69,7 +69,8 @@ int launch_conv1(const float* feats, const float* mean, const float* istd, const
                  const float* bias, bf16* out, int B, int T, int F, int C, int T1, int T1h, int F1,
                  cudaStream_t stream);
 // GLU + depthwise conv (K taps) + LayerNorm|BatchNorm(eval) + SiLU on (B, T, 2C) bf16 -> (B, T, C) bf16
-int launch_conv_mid(const bf16* x, const float* dw_w /*[C][K]*/, const float* dw_b, const float* norm_w,
+// pw1_bias (2C, fp32): bias of pointwise_conv1 — in causal mode the K-1 left pad frames are GLU(bias), not zeros
+int launch_conv_mid(const bf16* x, const float* pw1_bias, const float* dw_w /*[C][K]*/, const float* dw_b, const float* norm_w,
                     const float* norm_b, const float* bn_mean, const float* bn_var, int use_layer_norm, float eps,
                     bf16* out, int B, int T, int C, int K, int causal, cudaStream_t stream);
 // x[m, :] = x[m, :] * scale   (fp32 -> fp32 in place) and optional bf16 copy

@@ -68,7 +68,7 @@ def test_layernorm(lib, d):
 GEMM_SHAPES = [(128, 128, 64), (300, 256, 128), (257, 101, 128), (1000, 1024, 4096), (64, 384, 2432), (4096, 4096, 1024)]
 
 
-@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["simt", "tcgen05", "tcgen05_2cta"])
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 def test_gemm_bias_act_modes(lib, impl, M, N, K):
     torch.manual_seed(M + N + K)

@@ -68,26 +68,32 @@ def test_fbank_and_encoder_vs_reference_fixture(asr, golden_cases, model_dirs, c
         got = enc.cpu().numpy()
         for b in range(ref.shape[0]):
             n = int(enc_lens[b])
-            assert _rel_rms(got[b, :n], ref[b, :n]) < 3e-2
+            rr = _rel_rms(got[b, :n], ref[b, :n])
+            print(f"[{case}] batch {bi} utt {b}: encoder_out rel-rms vs fp32 reference fixture = {rr:.2e}")
+            assert rr < 6e-3
         logp = m.model.ctc_logprobs(enc).cpu().numpy()
         refp = arr[f"ctc_probs_{bi}"]
         for b in range(ref.shape[0]):
             n = int(enc_lens[b])
             # log-probs on the entries that matter (p > e^-12).  The synthetic CTC head is scaled x6
             # (logit sigma ~3.5, reverb_b200/synth.py), which amplifies the bf16 encoder error by the same factor:
-            # stated tolerance 0.6 abs (max over ~7k entries), 0.08 RMS.
+            # stated tolerance 0.12 abs (max over ~7k entries), 0.025 RMS (measured 0.06 / 0.015).
             sel = refp[b, :n] > -12
             diff = logp[b, :n][sel] - refp[b, :n][sel]
-            assert np.abs(diff).max() < 0.6
-            assert np.sqrt((diff.astype(np.float64) ** 2).mean()) < 0.08
-            assert (logp[b, :n].argmax(-1) == refp[b, :n].argmax(-1)).mean() > 0.9
+            print(f"[{case}] batch {bi} utt {b}: log-prob max abs diff {np.abs(diff).max():.3f}, "
+                  f"rms {np.sqrt((diff.astype(np.float64) ** 2).mean()):.4f}, "
+                  f"argmax agreement {(logp[b, :n].argmax(-1) == refp[b, :n].argmax(-1)).mean():.3f}")
+            assert np.abs(diff).max() < 0.12
+            assert np.sqrt((diff.astype(np.float64) ** 2).mean()) < 0.025
+            assert (logp[b, :n].argmax(-1) == refp[b, :n].argmax(-1)).mean() > 0.98
 
 
 @pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
 def test_encoder_and_decoder_vs_bf16_emulating_oracle(asr, golden_cases, model_dirs, case):
     """Tight check of the kernels' logic: against the oracle with EMULATE_BF16 (it rounds to bf16 exactly where the
     engine stores bf16, everything else fp32) the only difference left is accumulation order, so the tolerance is
-    ~10x tighter than against the pure-fp32 reference: encoder rel-RMS < 4e-3, log-probs 0.1 abs, decoder 0.03."""
+    ~5x tighter than against the pure-fp32 reference: encoder rel-RMS < 2.5e-3, log-probs 0.1 abs, decoder 0.03.
+    (This test is what exposed the causal left-pad semantics of the conv module: pad frames are GLU(bias), not 0.)"""
     from oracle import model_ref, pipeline_ref, search_ref
     meta, arr = golden_cases[case]
     m = asr[case]
@@ -111,7 +117,7 @@ def test_encoder_and_decoder_vs_bf16_emulating_oracle(asr, golden_cases, model_d
                 assert np.abs(logp[b, :n][sel] - want_logp[b, :n].numpy()[sel]).max() < 0.1
             print(f"[{case}] encoder rel-rms vs bf16-emulating oracle: {worst:.2e}; "
                   f"vs fp32 reference: {_rel_rms(got[0, :int(enc_lens[0])], arr[f'enc_out_{bi}'][0, :int(enc_lens[0])]):.2e}")
-            assert worst < 4e-3
+            assert worst < 2.5e-3
             # decoder on the fp32 reference encoder_out / n-best
             g = meta["batches"][bi]["ctc_prefix_beam_search"]
             nbest = [[tuple(h) for h in r["nbest"]] for r in g]
