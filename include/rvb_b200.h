@@ -69,6 +69,9 @@ RVB_API rvb_model* rvb_model_create(const rvb_model_config* cfg);
 RVB_API int rvb_model_set_tensor(rvb_model* m, const char* name, const float* h_data, long long numel);
 /* Pack the registered tensors into the device layout (bf16 GEMM operands, fused QKV, permuted conv weights). */
 RVB_API int rvb_model_finalize(rvb_model* m);
+/* Second plan over the same packed weights with its own workspace: lets a second host thread / CUDA stream decode
+ * concurrently (a plan serves one stream at a time).  The parent must outlive its forks. */
+RVB_API rvb_model* rvb_model_fork(rvb_model* m);
 RVB_API void rvb_model_destroy(rvb_model* m);
 /* T' = ((T-1)/2 - 1)/2 encoder frames for T feature frames (Conv2dSubsampling4) */
 RVB_API int rvb_encoder_out_frames(int T);

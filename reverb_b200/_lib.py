@@ -33,6 +33,7 @@ SIGNATURES = {
     "rvb_model_create": (_vp, [C.POINTER(ModelConfig)]),
     "rvb_model_set_tensor": (_i, [_vp, C.c_char_p, _vp, _ll]),
     "rvb_model_finalize": (_i, [_vp]),
+    "rvb_model_fork": (_vp, [_vp]),
     "rvb_model_destroy": (None, [_vp]),
     "rvb_encoder_out_frames": (_i, [_i]),
     "rvb_encoder_out_len": (_i, [_i, _i]),

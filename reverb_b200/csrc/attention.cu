@@ -65,7 +65,7 @@ struct AttnKParams {
 };
 
 template <int DK, bool HAS_POS>
-__global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnKParams prm) {
+__global__ void __launch_bounds__(ATT_THREADS, (DK <= 64) ? 2 : 1) attention_kernel(const AttnKParams prm) {
   constexpr int LDS = DK + ATT_PAD;          // smem row stride (elements)
   constexpr int TILE = ATT_BN * LDS;         // elements per staged matrix
   constexpr int NMAT = HAS_POS ? 3 : 2;      // K, V, (P)

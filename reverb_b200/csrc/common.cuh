@@ -8,6 +8,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 namespace rvb {
 
 // ---------------------------------------------------------------- errors
@@ -35,8 +37,8 @@ const char* last_error();
 #define RVB_CHECK_LAUNCH() RVB_CHECK_CUDA(cudaGetLastError())
 
 // count of kernels this library launched (bench.py reports it as gpu_launches)
-extern unsigned long long g_launch_count;
-#define RVB_COUNT_LAUNCH() (++rvb::g_launch_count)
+extern std::atomic<unsigned long long> g_launch_count;
+#define RVB_COUNT_LAUNCH() (rvb::g_launch_count.fetch_add(1, std::memory_order_relaxed))
 
 typedef __nv_bfloat16 bf16;
 

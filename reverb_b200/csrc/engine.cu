@@ -13,6 +13,7 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <string>
 #include <vector>
@@ -24,7 +25,7 @@ namespace rvb {
 
 // ---------------------------------------------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -778,7 +779,7 @@ static int attention_rescoring(rvb_model* m, const float* d_enc_out, const int* 
 extern "C" {
 
 RVB_API const char* rvb_last_error(void) { return rvb::last_error(); }
-RVB_API unsigned long long rvb_launch_count(void) { return rvb::g_launch_count; }
+RVB_API unsigned long long rvb_launch_count(void) { return rvb::g_launch_count.load(); }
 RVB_API int rvb_set_gemm_impl(int impl) {
   rvb::set_gemm_impl(impl);
   return 0;
@@ -791,6 +792,8 @@ RVB_API int rvb_gemm_profile_begin(void) {
 RVB_API int rvb_gemm_profile_end(double* total_ms, double* total_flops, long long* launches) {
   return rvb::gemm_profile_end(total_ms, total_flops, launches);
 }
+
+RVB_API void rvb_model_destroy(rvb_model* m);
 
 RVB_API rvb_model* rvb_model_create(const rvb_model_config* cfg) {
   if (cfg == nullptr) {
@@ -818,6 +821,52 @@ RVB_API int rvb_model_finalize(rvb_model* m) {
   RVB_REQUIRE(m != nullptr, "rvb_model_finalize: null model");
   if (m->finalized) return 0;
   return rvb::finalize_model(m);
+}
+
+// A second plan over the SAME packed weights with its own workspace (and its own folded language-specific
+// weights), so two host threads / CUDA streams can decode different batches concurrently.  The parent must outlive
+// its forks.
+RVB_API rvb_model* rvb_model_fork(rvb_model* m) {
+  if (m == nullptr || !m->finalized) {
+    rvb::set_error("rvb_model_fork: model not finalized");
+    return nullptr;
+  }
+  rvb_model* f = new rvb_model();
+  f->cfg = m->cfg;
+  f->finalized = true;
+  f->cmvn_mean = m->cmvn_mean;
+  f->cmvn_istd = m->cmvn_istd;
+  f->conv1_w = m->conv1_w;
+  f->conv1_b = m->conv1_b;
+  f->conv2 = m->conv2;
+  f->embed = m->embed;
+  f->pos_all = m->pos_all;
+  f->enc = m->enc;
+  f->after_norm = m->after_norm;
+  f->ctc = m->ctc;
+  f->dec_l = m->dec_l;
+  f->dec_r = m->dec_r;
+  const int d = m->cfg.d_model;
+  auto own_fold = [&](rvb::Linear& L) -> int {
+    void* p = nullptr;
+    if (rvb::alloc_dev(f, (size_t)d * d * sizeof(rvb::bf16), &p)) return -1;
+    L.w = reinterpret_cast<rvb::bf16*>(p);
+    if (rvb::alloc_dev(f, (size_t)d * sizeof(float), &p)) return -1;
+    L.b = reinterpret_cast<float*>(p);
+    return 0;
+  };
+  bool ok = true;
+  for (auto& E : f->enc)
+    if (E.lsl && own_fold(E.lang)) ok = false;
+  for (rvb::Decoder* D : {&f->dec_l, &f->dec_r})
+    if (D->present)
+      for (auto& Ld : D->layers)
+        if (Ld.lsl && own_fold(Ld.lang)) ok = false;
+  if (!ok) {
+    rvb_model_destroy(f);
+    return nullptr;
+  }
+  return f;
 }
 
 RVB_API void rvb_model_destroy(rvb_model* m) {
@@ -883,8 +932,9 @@ RVB_API int rvb_logp_topk(const float* d_logp, int rows, int V, int k, float* d_
   return rvb::launch_logsoftmax_topk(d_logp, V, rows, V, k, d_topk_val, d_topk_idx, nullptr, 0, (cudaStream_t)stream);
 }
 
-static rvb::DevBuf g_search_ws, g_search_out;
-static rvb::HostPinned g_search_pin;
+// per host thread: two decoding lanes (threads) may run the searches concurrently
+static thread_local rvb::DevBuf g_search_ws, g_search_out;
+static thread_local rvb::HostPinned g_search_pin;
 
 RVB_API int rvb_ctc_greedy_search(const int* d_topk_idx, int k, const int* h_enc_lens, int B, int Tp, int blank_id,
                           int* h_tokens, int* h_lens, void* stream_) {

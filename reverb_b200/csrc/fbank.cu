@@ -11,6 +11,7 @@
 // entry point) + 320 B/frame out; everything else is on chip.
 #include <math.h>
 
+#include <mutex>
 #include <vector>
 
 #include "kernels.h"
@@ -30,7 +31,10 @@ struct FbankTables {
 };
 static FbankTables g_fb;
 
+static std::mutex g_fb_mutex;
+
 static int init_fbank_tables() {
+  std::lock_guard<std::mutex> lock(g_fb_mutex);
   int dev = 0;
   RVB_CHECK_CUDA(cudaGetDevice(&dev));
   if (g_fb.window != nullptr && g_fb.device == dev) return 0;

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
 #include <vector>
 
 #include "kernels.h"
@@ -632,6 +633,7 @@ struct GemmProfRec {
 };
 static bool g_prof_on = false;
 static std::vector<GemmProfRec> g_prof;
+static std::mutex g_prof_mutex;
 
 void gemm_profile_begin() {
   for (auto& r : g_prof) {
@@ -710,7 +712,10 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   RVB_CHECK_LAUNCH();
   if (g_prof_on) {
     RVB_CHECK_CUDA(cudaEventRecord(rec.b, stream));
-    g_prof.push_back(rec);
+    {
+      std::lock_guard<std::mutex> lock(g_prof_mutex);
+      g_prof.push_back(rec);
+    }
   }
   return 0;
 }
@@ -767,7 +772,10 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   RVB_CHECK_LAUNCH();
   if (g_prof_on) {
     RVB_CHECK_CUDA(cudaEventRecord(rec.b, stream));
-    g_prof.push_back(rec);
+    {
+      std::lock_guard<std::mutex> lock(g_prof_mutex);
+      g_prof.push_back(rec);
+    }
   }
   return 0;
 }

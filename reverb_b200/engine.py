@@ -85,6 +85,21 @@ class Engine:
             check(self.lib.rvb_model_finalize(self._h), "rvb_model_finalize")
         self.has_right_decoder = any(k.startswith("decoder.right_decoder.") for k in state_dict)
 
+    def fork(self) -> "Engine":
+        """A second plan over the same device weights with its own workspace (for a second stream / host thread).
+        The parent engine must stay alive as long as the fork is used."""
+        other = Engine.__new__(Engine)
+        other.lib, other.device, other.cfg = self.lib, self.device, self.cfg
+        other.d_model, other.vocab, other.num_langs = self.d_model, self.vocab, self.num_langs
+        other.has_right_decoder = self.has_right_decoder
+        other._parent = self
+        with torch.cuda.device(self.device):
+            h = self.lib.rvb_model_fork(self._h)
+        if not h:
+            raise RuntimeError("rvb_model_fork failed: " + _lib.last_error())
+        other._h = C.c_void_p(h)
+        return other
+
     def __del__(self):
         try:
             if self._h is not None and self.lib is not None:

@@ -1,0 +1,52 @@
+"""Concurrent decoding lanes: N host threads, each with its own CUDA stream and its own plan workspace
+(`Engine.fork()` — packed weights are shared), so that the latency-bound stages of one batch (CTC prefix beam
+search: one CTA per utterance; host-side n-best packing; D2H syncs) overlap with the tensor-core-bound encoder of
+another batch.  Chunks are independent units (asr/wenet/cli/reverb.py:214-234), so results are identical to the
+sequential schedule; order is preserved.
+"""
+from __future__ import annotations
+
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, List, Sequence
+
+import torch
+
+from .asr_model import ASRModel
+
+
+class Lanes:
+    def __init__(self, asr, n_lanes: int = 2):
+        assert n_lanes >= 1
+        self.asr = asr
+        self.device = asr.device
+        self.models: List[ASRModel] = [asr.model]
+        for _ in range(n_lanes - 1):
+            self.models.append(ASRModel(asr.engine.fork(), asr.configs, asr.configs["output_dim"]))
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_lanes)]
+        self.pool = ThreadPoolExecutor(max_workers=n_lanes)
+
+    def __len__(self):
+        return len(self.models)
+
+    def run(self, jobs: Sequence, fn: Callable):
+        """fn(model, job) for every job, job i on lane i % n; returns results in job order.
+        Work already queued on the caller's current stream is visible to the lanes."""
+        producer = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(producer)
+
+        def task(i, job):
+            lane = i % len(self.models)
+            torch.cuda.set_device(self.device)
+            stream = self.streams[lane]
+            with torch.cuda.stream(stream):
+                stream.wait_event(ready)
+                out = fn(self.models[lane], job)
+                stream.synchronize()
+            return out
+
+        futures = [self.pool.submit(task, i, job) for i, job in enumerate(jobs)]
+        return [f.result() for f in futures]
+
+    def close(self):
+        self.pool.shutdown(wait=True)

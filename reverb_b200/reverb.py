@@ -85,6 +85,15 @@ class ReverbASR:
         self.input_frame_length = self.test_conf["fbank_conf"]["frame_shift"]
         self.output_frame_length = self.input_frame_length * _FRAME_DOWNSAMPLING_FACTOR.get(
             self.configs["encoder_conf"]["input_layer"], 4)
+        self._lanes = None
+
+    def set_lanes(self, n_lanes: int):
+        """Decode consecutive batches on `n_lanes` concurrent streams / host threads (reverb_b200/pipeline.py).
+        1 (default) = the reference's strictly sequential batch loop.  Results do not depend on this setting."""
+        from .pipeline import Lanes
+        if self._lanes is not None:
+            self._lanes.close()
+        self._lanes = Lanes(self, n_lanes) if n_lanes > 1 else None
 
     def _make_path_absolute(self, config_path: str, alternate_path: str | None = None) -> str:
         if alternate_path:
@@ -141,14 +150,21 @@ class ReverbASR:
                                    frame_shift=fc["frame_shift"])
         with torch.no_grad():
             cat_embs = torch.tensor([verbatimicity, 1.0 - verbatimicity])
-            results = []
-            for feats_batch, feats_lengths in self.feats_batcher(feats, chunk_size, batch_size):
-                results.append(self.model.decode(
+
+            def decode_batch(model, batch):
+                feats_batch, feats_lengths = batch
+                return model.decode(
                     modes, feats_batch, feats_lengths, beam_size, decoding_chunk_size=decoding_chunk_size,
                     num_decoding_left_chunks=num_decoding_left_chunks, ctc_weight=ctc_weight,
                     simulate_streaming=simulate_streaming, reverse_weight=reverse_weight, context_graph=None,
                     blank_id=self.blank_id, blank_penalty=blank_penalty, length_penalty=length_penalty,
-                    infos={"tasks": ["transcribe"], "langs": ["en"]}, cat_embs=cat_embs))
+                    infos={"tasks": ["transcribe"], "langs": ["en"]}, cat_embs=cat_embs)
+
+            batches = self.feats_batcher(feats, chunk_size, batch_size)
+            if self._lanes is not None:
+                results = self._lanes.run(list(batches), decode_batch)
+            else:
+                results = [decode_batch(self.model, b) for b in batches]
         return [get_output(format, self.tokenizer, Path(audio_file).name,
                            list(chain(*(hyp[mode] for hyp in results))), timings_adjustment, chunk_size,
                            self.input_frame_length, self.output_frame_length) for mode in modes]
