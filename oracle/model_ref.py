@@ -91,8 +91,14 @@ def rel_attention(x, mask, pos_emb, sd: SD, p: str, H: int):
     k = _q(_lin(x, sd, p + ".linear_k")).view(B, T, H, dk).transpose(1, 2)
     v = _q(_lin(x, sd, p + ".linear_v")).view(B, T, H, dk).transpose(1, 2)
     pp = _q(F.linear(_q(pos_emb), _q(sd[p + ".linear_pos.weight"]))).view(1, -1, H, dk).transpose(1, 2)
-    qu = _q(q + sd[p + ".pos_bias_u"]).transpose(1, 2)
-    qv = _q(q + sd[p + ".pos_bias_v"]).transpose(1, 2)
+    if EMULATE_BF16:
+        # the tcgen05 attention folds the position term: s = q.(k + p) + (u.k + v.p), with K'' = bf16(k + p)
+        kpp = _q(k + pp)
+        cb = (sd[p + ".pos_bias_u"].unsqueeze(1) * k).sum(-1) + (sd[p + ".pos_bias_v"].unsqueeze(1) * pp).sum(-1)
+        scores = (torch.matmul(q.transpose(1, 2), kpp.transpose(-2, -1)) + cb.unsqueeze(-2)) / math.sqrt(dk)
+        return _attend(v, scores, mask, sd, p)
+    qu = (q + sd[p + ".pos_bias_u"]).transpose(1, 2)
+    qv = (q + sd[p + ".pos_bias_v"]).transpose(1, 2)
     ac = torch.matmul(qu, k.transpose(-2, -1))
     bd = torch.matmul(qv, pp.transpose(-2, -1))
     scores = (ac + bd) / math.sqrt(dk)

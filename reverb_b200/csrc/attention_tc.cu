@@ -1,0 +1,438 @@
+// reverb_b200 — tcgen05 / TMEM / TMA attention for the long (encoder self-attention, decoder source-attention) cases.
+//
+// Rel-pos scores without the second product.  The reference computes (asr/wenet/transformer/attention.py:378-397)
+//     s[i,j] = ((q_i + u) . k_j + (q_i + v) . p_j) / sqrt(d_k)          (p_j: ABSOLUTE key position, no rel_shift)
+// which is algebraically
+//     s[i,j] = ( q_i . (k_j + p_j)  +  (u . k_j + v . p_j) ) / sqrt(d_k) =  ( q_i . K''_j + c_j ) / sqrt(d_k)
+// so a small pre-kernel builds K'' = k + p (bf16) and the per-key bias c (fp32) once per layer, and the attention
+// itself is ONE tensor-core product per key tile plus a key bias: half the QK FLOPs and no P tiles.
+//
+// Kernel (one CTA = 128 query rows of one (group, head); 2 CTAs / SM):
+//   warp 4 / lane 0 : TMA producer (Q once, K'' tiles double-buffered, V tiles) + tcgen05.mma issuer
+//                     S[128 x 128] = Q . K''^T  (M=128, N=128, 4 x K=16)         -> TMEM columns [0,128)
+//                     O[128 x  64] += P~ . V    (M=128, N=64, 8 x K=16, V as MN-major B) -> TMEM columns [128,192)
+//   warps 0..3      : one thread per query row: tcgen05.ld of its S row, mask + key bias, exp2, row sum, P~ written
+//                     to shared memory in the SWIZZLE_128B K-major layout the PV product reads as its A operand.
+// Two passes over the key tiles (pass 1: exact row max; pass 2: P~ = exp2(s - max), accumulate O) — no running-max
+// rescale of the TMEM accumulator, at the price of computing S twice (tensor FLOPs are not the limiter here; the
+// exponentials are).  Scores / probabilities never touch HBM.
+#include <cuda.h>
+#include <math.h>
+#include <stdlib.h>
+
+#include "kernels.h"
+
+namespace rvb {
+
+constexpr int AT_BM = 128;  // query rows per CTA
+constexpr int AT_DK = 64;
+constexpr int AT_KST = 3;   // K'' stages
+constexpr uint32_t AT_Q_BYTES = 128 * AT_DK * 2;  // 16 KB Q tile (= one 64-key K-block of P~)
+
+// BN = keys per tile.  BN = 64: 2 CTAs / SM (TMEM 256 columns each) hide each other's barrier round trips;
+// BN = 128: 1 CTA / SM (512 columns).
+template <int BN>
+struct AtCfg {
+  static constexpr uint32_t KV_BYTES = BN * AT_DK * 2;   // one K'' / V tile
+  static constexpr uint32_t P_BYTES = 128 * BN * 2;      // P~: 128 rows x BN keys (BN / 64 K-blocks of 16 KB)
+  static constexpr uint32_t SMEM_FIXED = AT_Q_BYTES + AT_KST * KV_BYTES + 2 * KV_BYTES + 2 * P_BYTES + 1024 + 256;
+  static constexpr uint32_t TMEM_COLS = (BN == 128) ? 512 : 256;  // S0 [0,BN), S1 [BN,2BN), O [2BN, 2BN+64)
+  static constexpr int CTAS_PER_SM = (BN == 128) ? 1 : 2;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+struct AttnTcParams {
+  bf16* out;
+  long long ldo;
+  const float* key_bias;  // (groups_kv, H, Tk) fp32 or nullptr
+  const int* k_lens;      // per kv group, or nullptr
+  int Tq, Tk, H;
+  float scale_log2;
+};
+
+// Pipeline (1 CTA / SM, 5 warps):
+//   control thread (warp 4, lane 0): TMA loads (Q, K'' x3 stages, V x2) and all tcgen05.mma issue; S is double-buffered
+//     in TMEM so QK(i+1) runs while the softmax warps consume S(i); P~ is double-buffered in shared memory so PV(j)
+//     runs while P~(j+1) is produced.
+//   softmax warps 0..3 (thread = query row): pass 1 row max, pass 2 exp2 / row sum / P~.
+template <int BN>
+__global__ void __launch_bounds__(160, AtCfg<BN>::CTAS_PER_SM)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  using Cfg = AtCfg<BN>;
+  constexpr int AT_BN = BN;
+  constexpr uint32_t AT_TILE_BYTES = Cfg::KV_BYTES;
+  constexpr uint32_t AT_P_BYTES = Cfg::P_BYTES;
+  constexpr uint32_t AT_TMEM_COLS = Cfg::TMEM_COLS;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + AT_Q_BYTES;               // AT_KST stages
+  uint8_t* sV = sK + AT_KST * AT_TILE_BYTES;   // 2 stages
+  uint8_t* sP = sV + 2 * AT_TILE_BYTES;        // 2 buffers x (BN / 64 K-blocks of 64 keys)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;    // [3]
+  uint64_t* k_empty = bars + 4;   // [3]
+  uint64_t* v_full = bars + 7;    // [2]
+  uint64_t* v_empty = bars + 9;   // [2]
+  uint64_t* s_full = bars + 11;   // [2]
+  uint64_t* s_empty = bars + 13;  // [2]
+  uint64_t* p_full = bars + 15;   // [2]
+  uint64_t* p_empty = bars + 17;  // [2]
+  uint64_t* o_done = bars + 19;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 20);
+  float* s_bias = reinterpret_cast<float*>(bars + 32);  // [ntiles * 128]: key bias * scale*log2e, -inf when masked
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qtile = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
+  const int q0 = qtile * AT_BM;
+  int klen = p.Tk;
+  if (p.k_lens) klen = min(klen, __ldg(p.k_lens + g));
+  const int ntiles = (klen + AT_BN - 1) / AT_BN;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < AT_KST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], 4);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[i], 1);
+    }
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == 4) {
+    tmem_alloc(tmem_ptr, AT_TMEM_COLS);
+    tmem_relinquish();
+  } else {
+    // key bias row of this (group, head), pre-scaled; masked keys -> -inf
+    const float* kb = p.key_bias ? p.key_bias + ((long long)g * p.H + h) * p.Tk : nullptr;
+    for (int key = threadIdx.x; key < ntiles * AT_BN; key += 128)
+      s_bias[key] = (key < klen) ? (kb ? __ldg(kb + key) * p.scale_log2 : 0.f) : -INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_o = tmem_base + 2 * AT_BN;
+
+  if (warp == 4) {
+    if (lane == 0 && ntiles > 0) {
+      // ------------------------------------------------------------ TMA + MMA control thread
+      // instruction descriptors: D=f32, A=B=bf16.  QK: N=128, both K-major.  PV: N=64, B (V) MN-major (bit 16).
+      constexpr uint32_t idesc_qk =
+          (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BN >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t idesc_pv =
+          (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      const long long qrow = (long long)g * p.Tq + q0;
+      const long long krow0 = (long long)g * p.Tk;
+      const int total = 2 * ntiles;  // pass 1 tiles, then pass 2 tiles
+      auto load_k = [&](int n) {
+        const int st = n % AT_KST, use = n / AT_KST;
+        mbar_wait(&k_empty[st], (use & 1) ^ 1);
+        mbar_expect_tx(&k_full[st], AT_TILE_BYTES);
+        tma_load_2d(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], h * AT_DK, (int)(krow0 + (n % ntiles) * AT_BN));
+      };
+      auto load_v = [&](int j) {
+        const int st = j & 1;
+        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], AT_TILE_BYTES);
+        tma_load_2d(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], h * AT_DK, (int)(krow0 + j * AT_BN));
+      };
+      auto issue_qk = [&](int n) {
+        const int st = n % AT_KST, sb = n & 1;
+        mbar_wait(&k_full[st], (n / AT_KST) & 1);
+        mbar_wait(&s_empty[sb], ((n >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sQ));
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sK + st * AT_TILE_BYTES));
+#pragma unroll
+        for (int k = 0; k < AT_DK / 16; ++k)
+          umma_f16(tmem_base + sb * AT_BN, adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[st]);
+      };
+      mbar_expect_tx(q_full, AT_Q_BYTES);
+      tma_load_2d(sQ, &tmQ, q_full, h * AT_DK, (int)qrow);
+      for (int n = 0; n < AT_KST && n < total; ++n) load_k(n);
+      load_v(0);
+      if (ntiles > 1) load_v(1);
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      issue_qk(1);  // total >= 2 always
+      for (int i = 0; i < total; ++i) {
+        // Keep the QK products two tiles ahead: S buffer (i & 1) is free as soon as the softmax warps have pulled
+        // S(i) out of TMEM (they signal that BEFORE doing the exponentials), so QK(i+2) is queued long before it is
+        // needed and the barrier round trips never sit on the softmax warps' critical path.
+        if (i + 2 < total) {
+          issue_qk(i + 2);
+          if (i + AT_KST < total) load_k(i + AT_KST);     // K stage of QK(i): released by its commit
+        }
+        if (i >= ntiles) {
+          const int j = i - ntiles, pb = j & 1;  // pass 2: O += P~(j) . V(j)
+          if (j >= 1 && j + 1 < ntiles) load_v(j + 1);  // stage freed by PV(j-1), issued one iteration ago
+          mbar_wait(&v_full[pb], (j >> 1) & 1);
+          mbar_wait(&p_full[pb], (j >> 1) & 1);
+          tc_fence_after();
+          const uint64_t pdesc = make_sw128_kmajor_desc(smem_u32(sP + pb * AT_P_BYTES));
+          const uint64_t vdesc = make_sw128_kmajor_desc(smem_u32(sV + pb * AT_TILE_BYTES));  // MN-major view
+#pragma unroll
+          for (int ks = 0; ks < AT_BN / 16; ++ks) {
+            // A: 16 keys = 32 B inside the 64-key K-block (ks / 4); B: 16 key rows of 128 B
+            const uint64_t a = pdesc + (uint64_t)((ks >> 2) * (AT_Q_BYTES >> 4) + (ks & 3) * 2);
+            const uint64_t bd = vdesc + (uint64_t)(ks * ((16 * 128) >> 4));
+            umma_f16(tmem_o, a, bd, idesc_pv, (j | ks) != 0);
+          }
+          umma_commit(&p_empty[pb]);
+          umma_commit(&v_empty[pb]);
+          if (j + 1 == ntiles) umma_commit(o_done);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- softmax warps: thread = query row
+    const int r = warp * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(warp * 32) << 16);
+    float row_max = -INFINITY, row_sum = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+      for (int j = 0; j < ntiles; ++j) {
+        const int i = pass * ntiles + j, sb = i & 1, pb = j & 1;
+        mbar_wait(&s_full[sb], (i >> 1) & 1);
+        tc_fence_after();
+        // the whole S row (128 fp32) is pulled out of TMEM with four back-to-back loads and ONE wait, so the TMEM
+        // latency is paid once per tile and the S buffer is handed back to the MMA issuer as early as possible
+        uint32_t sv[AT_BN];
+#pragma unroll
+        for (int c = 0; c < AT_BN; c += 32) tmem_ld_32x32(tmem_base + sb * AT_BN + lane_addr + c, sv + c);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[sb]);
+        const uint32_t bias_addr = smem_u32(s_bias + j * AT_BN);
+        if (pass == 0) {
+          float mx[4] = {row_max, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
+#pragma unroll
+          for (int e = 0; e < AT_BN; e += 4) {
+            const float4 b4 = lds128(bias_addr + e * 4);
+            mx[0] = fmaxf(mx[0], fmaf(__uint_as_float(sv[e + 0]), p.scale_log2, b4.x));
+            mx[1] = fmaxf(mx[1], fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, b4.y));
+            mx[2] = fmaxf(mx[2], fmaf(__uint_as_float(sv[e + 2]), p.scale_log2, b4.z));
+            mx[3] = fmaxf(mx[3], fmaf(__uint_as_float(sv[e + 3]), p.scale_log2, b4.w));
+          }
+          row_max = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        } else {
+          const float m = (row_max == -INFINITY) ? 0.f : row_max;
+          float sm[4] = {0.f, 0.f, 0.f, 0.f};
+          mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);  // PV(j-2) has consumed this P~ buffer
+#pragma unroll
+          for (int c = 0; c < AT_BN; c += 32) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 4) {
+              const float4 b4 = lds128(bias_addr + (c + e) * 4);
+              const float p0 = fast_exp2(fmaf(__uint_as_float(sv[c + e + 0]), p.scale_log2, b4.x) - m);
+              const float p1 = fast_exp2(fmaf(__uint_as_float(sv[c + e + 1]), p.scale_log2, b4.y) - m);
+              const float p2 = fast_exp2(fmaf(__uint_as_float(sv[c + e + 2]), p.scale_log2, b4.z) - m);
+              const float p3 = fast_exp2(fmaf(__uint_as_float(sv[c + e + 3]), p.scale_log2, b4.w) - m);
+              sm[0] += p0;
+              sm[1] += p1;
+              sm[2] += p2;
+              sm[3] += p3;
+              pk[(e >> 1) + 0] = pack_bf16x2(p0, p1);
+              pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+            }
+            // 32 keys = four 16-byte chunks of this row inside K-block (c / 64); SWIZZLE_128B: chunk ^= row % 8
+            uint8_t* blk = sP + pb * AT_P_BYTES + (c >> 6) * AT_Q_BYTES + r * 128;
+            const int ch0 = (c & 63) >> 3;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int ch = (ch0 + q) ^ (r & 7);
+              *reinterpret_cast<uint4*>(blk + ch * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+            }
+          }
+          row_sum += (sm[0] + sm[1]) + (sm[2] + sm[3]);
+        }
+        if (pass == 1) {
+          fence_proxy_async();  // generic-proxy writes of P~ -> visible to the tensor-core (async) proxy
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[pb]);
+        }
+      }
+    }
+    // ---- epilogue: O / row_sum -> bf16 -> global
+    const int row = q0 + r;
+    if (ntiles > 0) {
+      mbar_wait(o_done, 0);
+      tc_fence_after();
+    }
+    const float inv = row_sum > 0.f ? 1.f / row_sum : 0.f;
+    bf16* orow = p.out + ((long long)g * p.Tq + row) * p.ldo + h * AT_DK;
+#pragma unroll 1
+    for (int c = 0; c < AT_DK; c += 32) {
+      uint32_t ov[32];
+      if (ntiles > 0) {
+        tmem_ld_32x32(tmem_o + lane_addr + c, ov);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) ov[e] = 0u;
+      }
+      if (row < p.Tq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
+          reinterpret_cast<uint4*>(orow + c)[q] = u;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
+// K'' = k + p (bf16) and c[b,h,j] = u_h . k_j + v_h . p_j (fp32): one warp per (b, t) row.
+__global__ void __launch_bounds__(256)
+relpos_prep_kernel(const bf16* __restrict__ k, long long ldk, const bf16* __restrict__ pos, long long ldp,
+                   const float* __restrict__ bias_u, const float* __restrict__ bias_v, bf16* __restrict__ kpp,
+                   float* __restrict__ cbias, int B, int T, int H, int dk) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * T) return;
+  const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+  const int d = H * dk;
+  const bf16* kr = k + row * ldk;
+  const bf16* pr = pos + (long long)t * ldp;
+  bf16* orow = kpp + row * d;
+  for (int h = 0; h < H; ++h) {
+    float acc = 0.f;
+    for (int c = 2 * lane; c < dk; c += 64) {
+      const int col = h * dk + c;
+      float2 kv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(kr + col));
+      float2 pv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pr + col));
+      *reinterpret_cast<uint32_t*>(orow + col) = pack_bf16x2(kv.x + pv.x, kv.y + pv.y);
+      acc += __ldg(bias_u + col) * kv.x + __ldg(bias_u + col + 1) * kv.y + __ldg(bias_v + col) * pv.x +
+             __ldg(bias_v + col + 1) * pv.y;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) cbias[((long long)b * H + h) * T + t] = acc;
+  }
+}
+
+int launch_relpos_prep(const bf16* k, int ldk, const bf16* pos, int ldp, const float* bias_u, const float* bias_v,
+                       bf16* kpp, float* cbias, int B, int T, int H, int dk, cudaStream_t stream) {
+  RVB_REQUIRE(dk % 2 == 0, "relpos_prep: d_k must be even");
+  const long long rows = (long long)B * T;
+  if (rows <= 0) return 0;
+  relpos_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(k, ldk, pos, ldp, bias_u, bias_v, kpp, cbias, B,
+                                                                    T, H, dk);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_att = nullptr;
+
+static int tmap_2d(CUtensorMap* m, const void* base, long long cols, long long rows, long long ld_elems,
+                   int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t str[1] = {(cuuint64_t)ld_elems * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_att(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, str, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  RVB_REQUIRE(r == CUDA_SUCCESS, "attention: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return 0;
+}
+
+// q: (groups*Tq, ldq) rows with head h at columns [h*64, h*64+64) (+ the pointer offset already applied), same for k, v.
+int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
+  RVB_REQUIRE(a.dk == AT_DK, "attention_tc: only d_k = 64 is built");
+  RVB_REQUIRE(a.ldq % 8 == 0 && a.ldk % 8 == 0 && a.ldv % 8 == 0 && a.ldo % 8 == 0, "attention_tc: ld %% 8 != 0");
+  RVB_REQUIRE(((uintptr_t)a.q & 15) == 0 && ((uintptr_t)a.k & 15) == 0 && ((uintptr_t)a.v & 15) == 0 &&
+                  ((uintptr_t)a.out & 15) == 0,
+              "attention_tc: operands must be 16-byte aligned");
+  if (a.groups <= 0 || a.Tq <= 0) return 0;
+  if (g_encode_att == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    RVB_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    RVB_REQUIRE(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    g_encode_att = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  static int bn_sel = 0;
+  if (bn_sel == 0) {
+    const char* e = getenv("RVB_ATTN_BN");
+    bn_sel = (e && atoi(e) == 128) ? 128 : 64;
+  }
+  AttnTcParams p;
+  p.out = a.out;
+  p.ldo = a.ldo;
+  p.key_bias = a.key_bias;
+  p.k_lens = a.k_lens;
+  p.Tq = a.Tq;
+  p.Tk = a.Tk;
+  p.H = a.H;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  CUtensorMap tmQ, tmK, tmV;
+  if (tmap_2d(&tmQ, a.q, (long long)a.H * AT_DK, (long long)a.groups * a.Tq, a.ldq, 128)) return -1;
+  if (tmap_2d(&tmK, a.k, (long long)a.H * AT_DK, (long long)a.groups * a.Tk, a.ldk, bn_sel)) return -1;
+  if (tmap_2d(&tmV, a.v, (long long)a.H * AT_DK, (long long)a.groups * a.Tk, a.ldv, bn_sel)) return -1;
+  dim3 grid((a.Tq + AT_BM - 1) / AT_BM, a.H, a.groups);
+  if (bn_sel == 128) {
+    const size_t smem = AtCfg<128>::SMEM_FIXED + (size_t)((a.Tk + 127) / 128) * 128 * sizeof(float);
+    RVB_REQUIRE(smem <= 227 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    attention_tc_kernel<128><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    const size_t smem = AtCfg<64>::SMEM_FIXED + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
+    RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    attention_tc_kernel<64><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  }
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // namespace rvb

@@ -228,6 +228,7 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
   __shared__ int c_node[PB_MAXBEAM], c_ts[PB_MAXBEAM], c_tns[PB_MAXBEAM], c_tnsp[PB_MAXBEAM], c_times[PB_MAXBEAM];
   __shared__ int c_last[PB_MAXBEAM], c_par[PB_MAXBEAM];
   __shared__ double n_s[PB_MAXBEAM], n_ns[PB_MAXBEAM], n_vs[PB_MAXBEAM], n_vns[PB_MAXBEAM];
+  __shared__ double n_score[PB_MAXBEAM];
   __shared__ int n_node[PB_MAXBEAM], n_ts[PB_MAXBEAM], n_tns[PB_MAXBEAM], n_tnsp[PB_MAXBEAM];
   __shared__ double s_tv[PB_MAXBEAM];
   __shared__ int s_ti[PB_MAXBEAM];
@@ -245,6 +246,7 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
     n_ns[0] = PB_NEG_INF;
     n_vs[0] = 0.0;
     n_vns[0] = 0.0;
+    n_score[0] = 0.0;  // log_add([0, -inf])
     n_ts[0] = -1;
     n_tns[0] = -1;
     n_tnsp[0] = -1;
@@ -272,7 +274,7 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
       c_tnsp[j] = n_tnsp[j];
       const int node = n_node[j];
       c_node[j] = node;
-      c_score[j] = log_add2(s, ns);
+      c_score[j] = n_score[j];  // == log_add([s, ns]); already computed when slot j was ranked
       const bool sb = vs > vns;
       c_vit[j] = sb ? vs : vns;
       c_times[j] = sb ? n_ts[j] : n_tns[j];
@@ -454,6 +456,7 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
       n_ns[rank] = s.ns;
       n_vs[rank] = s.vs;
       n_vns[rank] = s.vns;
+      n_score[rank] = sc;
       n_ts[rank] = s.times_s;
       n_tns[rank] = tns;
       n_tnsp[rank] = tnsp;
@@ -485,7 +488,7 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
     }
     out_lens[(b * beam + r) * 2 + 0] = n;
     out_lens[(b * beam + r) * 2 + 1] = nt;
-    out_scores[b * beam + r] = log_add2(n_s[r], n_ns[r]);
+    out_scores[b * beam + r] = n_score[r];
   }
 }
 

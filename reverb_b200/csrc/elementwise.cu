@@ -310,23 +310,45 @@ conv_mid_fast_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_b
   const int left = causal ? (K - 1) : (K - 1) / 2;
   const int C2 = C >> 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < ROWS * C2; i += NT) {
-    int r = i / C2, cp = i - r * C2;
-    int t = t0 - left + r;
-    uint32_t o = 0u;
-    if (t >= 0 && t < T) {
-      const bf16* xr = x + ((long long)b * T + t) * (2 * C);
-      float2 a = unpack_bf16x2(reinterpret_cast<const uint32_t*>(xr)[cp]);
-      float2 g = unpack_bf16x2(reinterpret_cast<const uint32_t*>(xr + C)[cp]);
-      o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
-    } else if (t < 0 && causal) {
-      // the reference left-pads K-1 zero frames BEFORE pointwise_conv1 (convolution.py:113-114,129-130), so the pad
-      // frames reach the depthwise conv as GLU(bias), not as zeros
-      float2 a = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + 2 * cp), __ldg(pw1_bias + 2 * cp + 1)));
-      float2 g = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + C + 2 * cp), __ldg(pw1_bias + C + 2 * cp + 1)));
-      o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
+  // staging: batches of 8 independent (row, channel-pair) items per thread so that 16 loads are in flight at once
+  constexpr int U = 8;
+  for (int base = 0; base < ROWS * C2; base += NT * U) {
+    uint32_t ra[U], rg[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT + threadIdx.x;
+      ra[u] = 0u;
+      rg[u] = 0u;
+      if (i < ROWS * C2) {
+        const int r = i / C2, cp = i - r * C2;
+        const int t = t0 - left + r;
+        if (t >= 0 && t < T) {
+          const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + ((long long)b * T + t) * (2 * C));
+          ra[u] = xr[cp];
+          rg[u] = xr[C2 + cp];
+        }
+      }
     }
-    s_glu[i] = o;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + u * NT + threadIdx.x;
+      if (i >= ROWS * C2) continue;
+      const int r = i / C2, cp = i - r * C2;
+      const int t = t0 - left + r;
+      uint32_t o = 0u;
+      if (t >= 0 && t < T) {
+        float2 a = unpack_bf16x2(ra[u]);
+        float2 g = unpack_bf16x2(rg[u]);
+        o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
+      } else if (t < 0 && causal) {
+        // the reference left-pads K-1 zero frames BEFORE pointwise_conv1 (convolution.py:113-114,129-130), so the
+        // pad frames reach the depthwise conv as GLU(bias), not as zeros
+        float2 a = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + 2 * cp), __ldg(pw1_bias + 2 * cp + 1)));
+        float2 g = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + C + 2 * cp), __ldg(pw1_bias + C + 2 * cp + 1)));
+        o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
+      }
+      s_glu[i] = o;
+    }
   }
   __syncthreads();
   float acc[NIT][CM_TT][2];

@@ -11,6 +11,7 @@
 // into the embed linear, language-specific linears folded per call with the caller's cat_embs).
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -153,7 +154,7 @@ struct rvb_model {
 
   // workspace (grow-only)
   DevBuf ws_c1, ws_c2, ws_x, ws_n, ws_h, ws_qkv, ws_att, ws_pw, ws_cm, ws_y, ws_ybf, ws_pe, ws_pall, ws_lens;
-  DevBuf ws_encbf, ws_logits, ws_dec[12], ws_search, ws_misc;
+  DevBuf ws_encbf, ws_logits, ws_dec[12], ws_search, ws_misc, ws_kpp, ws_cbias;
   HostPinned pin_a, pin_b, pin_c, pin_d, pin_e;
   int pe_T = 0;
   int lens_slot = 0;
@@ -441,6 +442,16 @@ static int gemm(const bf16* A, const Linear& W, int M, int act, int out_mode, vo
   return launch_gemm(g, stream);
 }
 
+// 1 = tcgen05 attention (default when d_k == 64), 0 = mma.sync kernel (RVB_ATTN=mma)
+static int attn_impl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RVB_ATTN");
+    v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+  }
+  return v;
+}
+
 static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
                            const float* h_cat, int n_cat, float* d_enc_out, int* h_enc_lens, cudaStream_t stream) {
   const rvb_model_config& c = m->cfg;
@@ -478,8 +489,10 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       m->ws_h.ensure((size_t)M * c.ffn_dim * 2) || m->ws_qkv.ensure((size_t)M * 3 * d * 2) ||
       m->ws_att.ensure((size_t)M * d * 2) || m->ws_pw.ensure((size_t)M * 2 * d * 2) ||
       m->ws_cm.ensure((size_t)M * d * 2) || m->ws_y.ensure((size_t)M * d * 4) || m->ws_ybf.ensure((size_t)M * d * 2) ||
-      m->ws_pall.ensure((size_t)Tp * L * d * 2))
+      m->ws_pall.ensure((size_t)Tp * L * d * 2) || m->ws_kpp.ensure((size_t)M * d * 2) ||
+      m->ws_cbias.ensure((size_t)B * H * Tp * 4))
     return -1;
+  const bool tc_attn = attn_impl() == 1 && dk == 64;
   bf16* c1 = m->ws_c1.as<bf16>();
   bf16* c2 = m->ws_c2.as<bf16>();
   float* x = m->ws_x.as<float>();
@@ -541,7 +554,32 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
     // rel-pos MHSA                                                            (encoder_layer.py:209-217)
     if (launch_layernorm(x, E.norm_mha.g, E.norm_mha.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
     if (gemm(n, E.qkv, (int)M, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
-    {
+    if (tc_attn) {
+      // s = (q . (k + p) + (u . k + v . p)) / sqrt(d_k): fold the position term into the keys and a key bias
+      bf16* kpp = m->ws_kpp.as<bf16>();
+      float* cb = m->ws_cbias.as<float>();
+      if (launch_relpos_prep(qkv + d, 3 * d, pall + (size_t)l * d, L * d, E.pos_u, E.pos_v, kpp, cb, B, Tp, H, dk,
+                             stream))
+        return -1;
+      AttnTcArgs a;
+      a.q = qkv;
+      a.k = kpp;
+      a.v = qkv + 2 * d;
+      a.out = att;
+      a.ldq = 3 * d;
+      a.ldk = d;
+      a.ldv = 3 * d;
+      a.ldo = d;
+      a.groups = B;
+      a.Tq = Tp;
+      a.Tk = Tp;
+      a.H = H;
+      a.dk = dk;
+      a.key_bias = cb;
+      a.k_lens = d_lens;
+      a.scale = att_scale;
+      if (launch_attention_tc(a, stream)) return -1;
+    } else {
       AttnArgs a;
       a.q = qkv;
       a.k = qkv + d;
@@ -670,7 +708,25 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
     if (launch_layernorm(x, Ld.n2.g, Ld.n2.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
     if (gemm(n, Ld.cq, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;  // q -> first d cols, ld = d
     if (gemm(enc_bf, Ld.ckv, (int)Mem, ACT_NONE, OUT_BF16, kv, 1.f, stream)) return -1;
-    {
+    if (attn_impl() == 1 && dk == 64) {
+      // the N hypotheses of an utterance share its keys: one group per utterance with N * Lp query rows
+      AttnTcArgs a;
+      a.q = qkv;
+      a.k = kv;
+      a.v = kv + d;
+      a.out = att;
+      a.ldq = d;
+      a.ldk = a.ldv = 2 * d;
+      a.ldo = d;
+      a.groups = B;
+      a.Tq = N * Lp;
+      a.Tk = Tp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_enc_lens;
+      a.scale = scale;
+      if (launch_attention_tc(a, stream)) return -1;
+    } else {
       AttnArgs a;
       a.q = qkv;
       a.k = kv;
@@ -874,7 +930,7 @@ RVB_API void rvb_model_destroy(rvb_model* m) {
   for (void* p : m->owned) cudaFree(p);
   DevBuf* bufs[] = {&m->ws_c1, &m->ws_c2, &m->ws_x, &m->ws_n, &m->ws_h, &m->ws_qkv, &m->ws_att, &m->ws_pw, &m->ws_cm,
                     &m->ws_y, &m->ws_ybf, &m->ws_pe, &m->ws_pall, &m->ws_lens, &m->ws_encbf, &m->ws_logits,
-                    &m->ws_search, &m->ws_misc};
+                    &m->ws_search, &m->ws_misc, &m->ws_kpp, &m->ws_cbias};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : m->ws_dec) b.release();
   m->pin_a.release();
@@ -1049,6 +1105,30 @@ RVB_API int rvb_attention(const void* d_q, const void* d_k, const void* d_v, con
   a.causal = causal;
   a.scale = scale;
   return rvb::launch_attention(a, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_attention_tc(const void* d_q, const void* d_k, const void* d_v, void* d_out, int ldq, int ldk, int ldv,
+                             int ldo, int groups, int Tq, int Tk, int H, int dk, const float* d_key_bias,
+                             const int* d_k_lens, float scale, void* stream) {
+  rvb::AttnTcArgs a;
+  a.q = reinterpret_cast<const rvb::bf16*>(d_q);
+  a.k = reinterpret_cast<const rvb::bf16*>(d_k);
+  a.v = reinterpret_cast<const rvb::bf16*>(d_v);
+  a.out = reinterpret_cast<rvb::bf16*>(d_out);
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+  a.groups = groups; a.Tq = Tq; a.Tk = Tk; a.H = H; a.dk = dk;
+  a.key_bias = d_key_bias;
+  a.k_lens = d_k_lens;
+  a.scale = scale;
+  return rvb::launch_attention_tc(a, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_relpos_prep(const void* d_k, int ldk, const void* d_pos, int ldp, const float* d_bias_u,
+                            const float* d_bias_v, void* d_kpp, float* d_cbias, int B, int T, int H, int dk,
+                            void* stream) {
+  return rvb::launch_relpos_prep(reinterpret_cast<const rvb::bf16*>(d_k), ldk, reinterpret_cast<const rvb::bf16*>(d_pos),
+                                 ldp, d_bias_u, d_bias_v, reinterpret_cast<rvb::bf16*>(d_kpp), d_cbias, B, T, H, dk,
+                                 (cudaStream_t)stream);
 }
 
 RVB_API int rvb_f32_to_bf16(const float* d_x, void* d_out, long long n, void* stream) {

@@ -103,6 +103,25 @@ struct AttnArgs {
 };
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 
+// tcgen05 attention (attention_tc.cu): d_k = 64, key-length mask, optional per-key bias (rel-pos folded, see the
+// kernel header).  Rows are grouped: group g owns query rows [g*Tq, (g+1)*Tq) and key rows [g*Tk, (g+1)*Tk);
+// the q/k/v pointers address column 0 of head 0 (heads are 64 columns apart).
+struct AttnTcArgs {
+  const bf16* q = nullptr;
+  const bf16* k = nullptr;
+  const bf16* v = nullptr;
+  bf16* out = nullptr;
+  int ldq = 0, ldk = 0, ldv = 0, ldo = 0;
+  int groups = 0, Tq = 0, Tk = 0, H = 0, dk = 0;
+  const float* key_bias = nullptr;  // (groups, H, Tk) fp32, added to q.k before scaling
+  const int* k_lens = nullptr;      // (groups) valid keys
+  float scale = 1.0f;
+};
+int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream);
+// K'' = k + pos (bf16, (B*T, H*dk) dense) and cbias[b,h,t] = u_h . k + v_h . pos
+int launch_relpos_prep(const bf16* k, int ldk, const bf16* pos, int ldp, const float* bias_u, const float* bias_v,
+                       bf16* kpp, float* cbias, int B, int T, int H, int dk, cudaStream_t stream);
+
 // ------------------------------------------------------------------ CTC head / searches (ctc.cu)
 // per row: logp = log_softmax(logits) ; top-k (k <= 16) of logp with indices ; optional full logp output.
 int launch_logsoftmax_topk(const float* logits, int ld, int M, int V, int k, float* topk_val, int* topk_idx,

@@ -168,3 +168,62 @@ def test_attention_causal_cross(lib):
     s = s.masked_fill(mask[:, None, None, :], -float("inf"))
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(S, L, d)
     torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 150, 2), (2, 748, 4), (1, 128, 1), (2, 129, 2)])
+def test_attention_tcgen05_relpos(lib, B, T, H):
+    """tcgen05 attention with the folded rel-pos term (K'' = k + p, key bias c) vs the reference formula in fp32."""
+    torch.manual_seed(B * 1000 + T)
+    dk = 64
+    d = H * dk
+    qkv = (torch.randn(B, T, 3 * d, device="cuda") * 0.7).bfloat16()
+    pos = (torch.randn(T, d, device="cuda") * 0.7).bfloat16()
+    u = torch.randn(H, dk, device="cuda") * 0.3
+    v = torch.randn(H, dk, device="cuda") * 0.3
+    klens = torch.tensor([T, max(1, T * 2 // 3), 1][:B], dtype=torch.int32, device="cuda")
+    kpp = torch.empty(B, T, d, device="cuda", dtype=torch.bfloat16)
+    cb = torch.empty(B, H, T, device="cuda")
+    _check(lib, lib.rvb_relpos_prep(C.c_void_p(qkv.data_ptr() + 2 * d), 3 * d, _p(pos), d, _p(u), _p(v), _p(kpp), _p(cb),
+                                    B, T, H, dk, _stream()))
+    out = torch.zeros(B, T, d, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dk)
+    _check(lib, lib.rvb_attention_tc(_p(qkv), _p(kpp), C.c_void_p(qkv.data_ptr() + 4 * d), _p(out), 3 * d, d, 3 * d, d,
+                                     B, T, T, H, dk, _p(cb), _p(klens), scale, _stream()))
+    torch.cuda.synchronize()
+    q = qkv[..., :d].float().view(B, T, H, dk)
+    k = qkv[..., d:2 * d].float().view(B, T, H, dk).transpose(1, 2)
+    vv = qkv[..., 2 * d:].float().view(B, T, H, dk).transpose(1, 2)
+    pp = pos.float().view(1, T, H, dk).transpose(1, 2)
+    # the pre-kernel itself: exact bf16 rounding of k + p, fp32 bias
+    torch.testing.assert_close(kpp.float().view(B, T, H, dk).transpose(1, 2), (k + pp).bfloat16().float(), rtol=0, atol=0)
+    want_cb = (u[None, :, None, :] * k).sum(-1) + (v[None, :, None, :] * pp).sum(-1)
+    torch.testing.assert_close(cb, want_cb, rtol=1e-4, atol=1e-4)
+    s = ((q + u).transpose(1, 2) @ k.transpose(-1, -2) + (q + v).transpose(1, 2) @ pp.transpose(-1, -2)) * scale
+    mask = torch.arange(T, device="cuda")[None, :] >= klens[:, None]
+    s = s.masked_fill(mask[:, None, None, :], -float("inf"))
+    a = torch.softmax(s, -1).masked_fill(mask[:, None, None, :], 0.0)
+    ref = (a @ vv).transpose(1, 2).reshape(B, T, d)
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+def test_attention_tcgen05_grouped_cross(lib):
+    """decoder source-attention form: groups of N*L query rows share one utterance's keys; no bias."""
+    torch.manual_seed(11)
+    H, dk = 2, 64
+    d = H * dk
+    G, Tq, Tk = 3, 230, 300
+    qx = (torch.randn(G, Tq, d, device="cuda") * 0.7).bfloat16()
+    kv = (torch.randn(G, Tk, 2 * d, device="cuda") * 0.7).bfloat16()
+    klens = torch.tensor([300, 41, 128], dtype=torch.int32, device="cuda")
+    out = torch.zeros(G, Tq, d, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dk)
+    _check(lib, lib.rvb_attention_tc(_p(qx), _p(kv), C.c_void_p(kv.data_ptr() + 2 * d), _p(out), d, 2 * d, 2 * d, d,
+                                     G, Tq, Tk, H, dk, None, _p(klens), scale, _stream()))
+    q = qx.float().view(G, Tq, H, dk).transpose(1, 2)
+    k = kv[..., :d].float().view(G, Tk, H, dk).transpose(1, 2)
+    v = kv[..., d:].float().view(G, Tk, H, dk).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) * scale
+    mask = torch.arange(Tk, device="cuda")[None, :] >= klens[:, None]
+    s = s.masked_fill(mask[:, None, None, :], -float("inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(G, Tq, d)
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
