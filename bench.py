@@ -171,7 +171,21 @@ def run_cpu_reference(model_dir: str, n_chunks: int, steps: int, warmup: int, th
     return n_chunks * 30.0 * steps / dt, dt / steps, threads
 
 
+def _claim_stdout():
+    """Only the JSON line may reach stdout: libraries (NCCL prints its version there) are redirected to stderr."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_fd: int, line: dict):
+    sys.stdout.flush()
+    os.write(real_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -211,7 +225,7 @@ def main():
                                  "sample": f"{args.cpu_chunks} x 30 s chunks per step, batch_size 1, torch "
                                            f"{torch.__version__} CPU fp32"},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _emit(real_stdout, line)
         return
 
     # ------------------------------------------------------------------ CUDA arm
@@ -368,7 +382,7 @@ def main():
                                 "sample": f"{args.cpu_chunks} x 30 s chunks (one timed pass after a thread-count probe), batch_size 1, "
                                           f"oracle port of the reference on torch {torch.__version__} CPU fp32, "
                                           f"{time.time() - t0:.0f} s wall"}
-    print(json.dumps(line))
+    _emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
 

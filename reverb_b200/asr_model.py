@@ -15,7 +15,8 @@ import numpy as np
 import torch
 
 from .engine import Engine
-from .search import DecodeResult, greedy_results, prefix_beam_results, rescoring_pick
+from .search import (DecodeResult, greedy_results, prefix_beam_results, rescoring_pick,
+                     rescoring_pick_batch)
 
 SUPPORTED_METHODS = ("ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring")
 
@@ -81,15 +82,24 @@ class ASRModel:
         results: Dict[str, List[DecodeResult]] = {}
         if "ctc_greedy_search" in methods:
             results["ctc_greedy_search"] = greedy_results(self.engine.greedy_search(topk_idx, encoder_lens, blank_id))
-        prefix = None
         if need_beam:
-            prefix = prefix_beam_results(
-                self.engine.prefix_beam_search(topk_val, topk_idx, encoder_lens, beam_size, blank_id))
+            raw = self.engine.prefix_beam_search_raw(topk_val, topk_idx, encoder_lens, beam_size, blank_id)
+            toks, tims, olen, scores, nhyp = raw
             if "ctc_prefix_beam_search" in methods:
-                results["ctc_prefix_beam_search"] = prefix
-        if "attention_rescoring" in methods:
-            results["attention_rescoring"] = self.attention_rescoring(
-                prefix, encoder_out, encoder_lens, ctc_weight, reverse_weight, cat_embs)
+                per_utt = []
+                for b in range(toks.shape[0]):
+                    n = int(nhyp[b])
+                    per_utt.append(([tuple(toks[b, r, :olen[b, r, 0]].tolist()) for r in range(n)],
+                                    [float(x) for x in scores[b, :n]],
+                                    [tims[b, r, :olen[b, r, 1]].tolist() for r in range(n)]))
+                results["ctc_prefix_beam_search"] = prefix_beam_results(per_utt)
+            if "attention_rescoring" in methods:
+                # straight from the n-best arrays: no per-hypothesis Python objects on this path
+                hlen = np.where(np.arange(toks.shape[1])[None, :] < nhyp[:, None], olen[:, :, 0], -1)
+                l2r, r2l = self.engine.rescoring_scores_raw(encoder_out, encoder_lens, toks, hlen, cat_embs,
+                                                            reverse_weight)
+                results["attention_rescoring"] = rescoring_pick_batch(toks, tims, olen, scores, nhyp, l2r, r2l,
+                                                                      ctc_weight, reverse_weight)
         return results
 
     def attention_rescoring(self, prefix_results: List[DecodeResult], encoder_out: torch.Tensor, encoder_lens,

@@ -463,6 +463,182 @@ conv_mid_fast_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_b
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Split version (default for K in {7,15,31}): kernel A = GLU + depthwise conv for one (batch, 16-frame tile,
+// 128-channel-pair slice) per 128-thread CTA — no block-wide phases, so the loads of one CTA overlap the FMAs of the
+// others (4+ CTAs / SM) — writes the fp32 conv result and accumulates per-frame sum / sum-of-squares with one atomic
+// pair per (frame, CTA); kernel B = LayerNorm(from the accumulated statistics) + SiLU -> bf16, one warp per frame.
+// With BatchNorm (eval) kernel A applies norm + SiLU itself and writes bf16 directly.
+template <int K>
+__global__ void __launch_bounds__(128)
+conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_bias, const float* __restrict__ dw_w,
+               const float* __restrict__ dw_b, const float* __restrict__ norm_w, const float* __restrict__ norm_b,
+               const float* __restrict__ bn_mean, const float* __restrict__ bn_var, int use_ln, float eps,
+               float* __restrict__ conv_out, float* __restrict__ stats, bf16* __restrict__ out, int T, int C,
+               int causal) {
+  constexpr int ROWS = CM_TT + K - 1;
+  __shared__ float s_part[4][CM_TT][2];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * CM_TT;
+  const int C2 = C >> 1;
+  const int cp = blockIdx.z * 128 + threadIdx.x;
+  const bool ok = cp < C2;
+  const int left = causal ? (K - 1) : (K - 1) / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t ra[ROWS], rg[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int t = t0 - left + r;
+    ra[r] = 0u;
+    rg[r] = 0u;
+    if (ok && t >= 0 && t < T) {
+      const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + ((long long)b * T + t) * (2 * C));
+      ra[r] = __ldg(xr + cp);
+      rg[r] = __ldg(xr + C2 + cp);
+    }
+  }
+  float w0[K], w1[K];
+  float b0 = 0.f, b1 = 0.f;
+  float2 padv = make_float2(0.f, 0.f);
+  if (ok) {
+    b0 = __ldg(dw_b + 2 * cp);
+    b1 = __ldg(dw_b + 2 * cp + 1);
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      w0[k] = __ldg(dw_w + (2 * cp) * K + k);
+      w1[k] = __ldg(dw_w + (2 * cp + 1) * K + k);
+    }
+    if (causal) {
+      // the reference left-pads K-1 zero frames BEFORE pointwise_conv1 (convolution.py:113-114,129-130): the pad
+      // frames reach the depthwise conv as GLU(bias), not as zeros
+      float2 a = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + 2 * cp), __ldg(pw1_bias + 2 * cp + 1)));
+      float2 g = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + C + 2 * cp), __ldg(pw1_bias + C + 2 * cp + 1)));
+      padv = unpack_bf16x2(pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y)));
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) w0[k] = w1[k] = 0.f;
+  }
+  float acc[CM_TT][2];
+#pragma unroll
+  for (int t = 0; t < CM_TT; ++t) {
+    acc[t][0] = b0;
+    acc[t][1] = b1;
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int tt = t0 - left + r;
+    float2 v;
+    if (tt >= 0 && tt < T) {
+      float2 a = unpack_bf16x2(ra[r]);
+      float2 g = unpack_bf16x2(rg[r]);
+      v = unpack_bf16x2(pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y)));  // GLU output is stored as bf16
+    } else {
+      v = (tt < 0) ? padv : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int t = r - k;  // compile-time after unrolling
+      if (t >= 0 && t < CM_TT) {
+        acc[t][0] = fmaf(w0[k], v.x, acc[t][0]);
+        acc[t][1] = fmaf(w1[k], v.y, acc[t][1]);
+      }
+    }
+  }
+  if (!use_ln) {
+    if (!ok) return;
+    const int c0 = 2 * cp, c1 = 2 * cp + 1;
+    const float g0 = __ldg(norm_w + c0), g1 = __ldg(norm_w + c1), be0 = __ldg(norm_b + c0), be1 = __ldg(norm_b + c1);
+    const float m0 = __ldg(bn_mean + c0), m1 = __ldg(bn_mean + c1);
+    const float r0 = rsqrtf(__ldg(bn_var + c0) + eps), r1 = rsqrtf(__ldg(bn_var + c1) + eps);
+#pragma unroll
+    for (int t = 0; t < CM_TT; ++t) {
+      if (t0 + t >= T) continue;
+      const float y0 = (acc[t][0] - m0) * r0 * g0 + be0, y1 = (acc[t][1] - m1) * r1 * g1 + be1;
+      reinterpret_cast<uint32_t*>(out + ((long long)b * T + t0 + t) * C)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
+    }
+    return;
+  }
+#pragma unroll
+  for (int t = 0; t < CM_TT; ++t) {
+    float s = ok ? acc[t][0] + acc[t][1] : 0.f;
+    float q = ok ? acc[t][0] * acc[t][0] + acc[t][1] * acc[t][1] : 0.f;
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane == 0) {
+      s_part[warp][t][0] = s;
+      s_part[warp][t][1] = q;
+    }
+    if (ok && t0 + t < T)
+      reinterpret_cast<float2*>(conv_out + ((long long)b * T + t0 + t) * C)[cp] = make_float2(acc[t][0], acc[t][1]);
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * CM_TT) {
+    const int t = threadIdx.x >> 1, which = threadIdx.x & 1;
+    if (t0 + t < T) {
+      const float v = s_part[0][t][which] + s_part[1][t][which] + s_part[2][t][which] + s_part[3][t][which];
+      atomicAdd(stats + ((long long)b * T + t0 + t) * 2 + which, v);
+    }
+  }
+}
+
+// y = SiLU(LN(conv_out)) with mean / variance from the accumulated (sum, sum of squares): one warp per frame
+template <int NV>
+__global__ void __launch_bounds__(256)
+conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restrict__ stats,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M, int C,
+                      bf16* __restrict__ out) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float mean = stats[row * 2] / (float)C;
+  const float var = fmaxf(stats[row * 2 + 1] / (float)C - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + eps);
+  const int nvec = C >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(conv_out + row * C);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int idx = lane + 32 * i;
+    if (idx < nvec) {
+      const float4 v = xr[idx];
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + idx);
+      uint2 u;
+      u.x = pack_bf16x2(silu_f((v.x - mean) * rstd * g.x + bb.x), silu_f((v.y - mean) * rstd * g.y + bb.y));
+      u.y = pack_bf16x2(silu_f((v.z - mean) * rstd * g.z + bb.z), silu_f((v.w - mean) * rstd * g.w + bb.w));
+      reinterpret_cast<uint2*>(out + row * C)[idx] = u;
+    }
+  }
+}
+
+template <int K>
+static int launch_conv_split(const bf16* x, const float* pw1_bias, const float* dw_w, const float* dw_b,
+                             const float* norm_w, const float* norm_b, const float* bn_mean, const float* bn_var,
+                             int use_ln, float eps, bf16* out, float* conv_tmp, float* stats, int B, int T, int C,
+                             int causal, cudaStream_t stream) {
+  const int C2 = C / 2;
+  if (use_ln) RVB_CHECK_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * T * 2 * sizeof(float), stream));
+  dim3 grid((T + CM_TT - 1) / CM_TT, B, (C2 + 127) / 128);
+  conv_dw_kernel<K><<<grid, 128, 0, stream>>>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln, eps,
+                                              conv_tmp, stats, out, T, C, causal);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  if (use_ln) {
+    const long long M = (long long)B * T;
+    const int nv = (C / 4 + 31) / 32;
+    const unsigned g2 = (unsigned)((M + 7) / 8);
+    if (nv <= 1) conv_norm_silu_kernel<1><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
+    else if (nv <= 2) conv_norm_silu_kernel<2><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
+    else if (nv <= 4) conv_norm_silu_kernel<4><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
+    else if (nv <= 8) conv_norm_silu_kernel<8><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
+    else if (nv <= 16) conv_norm_silu_kernel<16><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
+    else conv_norm_silu_kernel<32><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
+    RVB_COUNT_LAUNCH();
+    RVB_CHECK_LAUNCH();
+  }
+  return 0;
+}
+
 // Generic fallback (any K <= 64, any even C): conv results staged in shared memory.
 __global__ void __launch_bounds__(256)
 conv_mid_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_bias, const float* __restrict__ dw_w,
@@ -572,9 +748,18 @@ static int launch_conv_mid_fast(const bf16* x, const float* pw1_bias, const floa
 
 int launch_conv_mid(const bf16* x, const float* pw1_bias, const float* dw_w, const float* dw_b, const float* norm_w, const float* norm_b,
                     const float* bn_mean, const float* bn_var, int use_layer_norm, float eps, bf16* out, int B, int T,
-                    int C, int K, int causal, cudaStream_t stream) {
+                    int C, int K, int causal, cudaStream_t stream, float* conv_tmp, float* stats) {
   RVB_REQUIRE(C % 2 == 0 && K >= 1 && K <= 64, "conv_mid: unsupported C=%d K=%d", C, K);
   RVB_REQUIRE(!causal || pw1_bias != nullptr, "conv_mid: causal mode needs the pointwise_conv1 bias");
+  if (conv_tmp != nullptr && stats != nullptr && C % 4 == 0 && C <= 4096) {
+#define RVB_CS(KK)                                                                                                   \
+  return launch_conv_split<KK>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_layer_norm, eps, out,   \
+                               conv_tmp, stats, B, T, C, causal, stream)
+    if (K == 15) RVB_CS(15);
+    if (K == 31) RVB_CS(31);
+    if (K == 7) RVB_CS(7);
+#undef RVB_CS
+  }
   // one channel pair per thread when it fits a 512-thread CTA (C <= 1024), else two per thread (C <= 2048)
   const int C2 = C / 2;
 #define RVB_CM(KK, NN, TT)                                                                                        \

@@ -490,7 +490,7 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       m->ws_att.ensure((size_t)M * d * 2) || m->ws_pw.ensure((size_t)M * 2 * d * 2) ||
       m->ws_cm.ensure((size_t)M * d * 2) || m->ws_y.ensure((size_t)M * d * 4) || m->ws_ybf.ensure((size_t)M * d * 2) ||
       m->ws_pall.ensure((size_t)Tp * L * d * 2) || m->ws_kpp.ensure((size_t)M * d * 2) ||
-      m->ws_cbias.ensure((size_t)B * H * Tp * 4))
+      m->ws_cbias.ensure(((size_t)B * H * Tp + (size_t)M * 2) * 4))
     return -1;
   const bool tc_attn = attn_impl() == 1 && dk == 64;
   bf16* c1 = m->ws_c1.as<bf16>();
@@ -606,7 +606,8 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       return -1;
     if (gemm(n, E.pw1, (int)M, ACT_NONE, OUT_BF16, pw, 1.f, stream)) return -1;
     if (launch_conv_mid(pw, E.pw1.b, E.dw_w, E.dw_b, E.cnorm.g, E.cnorm.b, E.bn_mean, E.bn_var, c.cnn_layer_norm, 1e-5f, cm, B,
-                        Tp, d, c.cnn_kernel, c.causal, stream))
+                        Tp, d, c.cnn_kernel, c.causal, stream, y /*fp32 (M, d) scratch, free until the LSL mix*/,
+                        m->ws_cbias.as<float>() + (size_t)B * H * Tp))
       return -1;
     if (gemm(cm, E.pw2, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream, d_lens, Tp)) return -1;
     // FFN (+ language-specific mix on the first / last block)                   (encoder_layer.py:233-242, 372-400)

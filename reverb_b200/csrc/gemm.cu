@@ -8,11 +8,11 @@
 // Conv2d(d,d,3,stride 2) of Conv2dSubsampling4 (subsampling.py:186-189) as an implicit GEMM whose A tiles are fetched
 // straight out of the channels-last conv1 activation by 4-D TMA boxes (no im2col buffer).
 //
-// Structure per CTA (192 threads, 1 CTA / SM, grid = #SMs, static round-robin tile scheduler):
+// Structure per CTA (320 threads, 1 CTA / SM, grid = #SMs, static round-robin tile scheduler):
 //   warp 0 / lane 0 : TMA producer   — fills a STAGES-deep ring of {A 128x64, W BNx64} bf16 tiles (SWIZZLE_128B)
 //   warp 1 / lane 0 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x 4 per stage;
 //                                       tcgen05.commit frees smem stages and publishes finished accumulators
-//   warps 2..5      : epilogue       — tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x BN columns),
+//   warps 2..9      : epilogue       — tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x BN columns),
 //                                       bias / ReLU / SiLU / residual(+row mask) fused, vectorised global stores
 // so tile i's epilogue overlaps tile i+1's main loop.
 #include <cuda.h>
@@ -31,7 +31,8 @@ void set_gemm_impl(int impl) { g_gemm_impl = impl; }
 int get_gemm_impl() {
   if (g_gemm_impl < 0) {
     const char* e = getenv("RVB_GEMM");
-    g_gemm_impl = (e && strcmp(e, "simt") == 0) ? 1 : (e && strcmp(e, "tc2") == 0) ? 2 : 0;
+    // default: 2-CTA (cta_group::2) kernel; RVB_GEMM=tc1 -> 1-CTA kernel, RVB_GEMM=simt -> CUDA-core bring-up kernel
+    g_gemm_impl = (e && strcmp(e, "simt") == 0) ? 1 : (e && strcmp(e, "tc1") == 0) ? 0 : 2;
   }
   return g_gemm_impl;
 }
@@ -47,6 +48,8 @@ struct GemmKParams {
   const int* row_lens;
   int rows_per_batch;
   int conv_mode, conv_T2, conv_F2, conv_tt, conv_cblocks;
+  int f32_coalesced;  // fp32 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
+  int epi_warps;  // 4 or 8 epilogue warps drain a tile (8: short-K, epilogue-bound shapes; 4: long-K, MMA-bound)
   // simt fallback only
   const bf16* A;
   const bf16* W;
@@ -201,6 +204,113 @@ __device__ __forceinline__ long long output_row(const GemmKParams& p, const Tile
   return m;
 }
 
+// Drains columns [c0, c1) of one accumulator stage for the 32 output rows of one epilogue warp (one thread = one TMEM
+// lane = one row after tcgen05.ld).  Waits for the accumulator first.
+//
+// fp32 outputs (EPI_F32, EPI_RESID) go through a warp-private 32x32 fp32 staging tile in shared memory (XOR-swizzled
+// in 16-byte slots, conflict-free both ways) so that global accesses are coalesced: one warp instruction covers 4 rows
+// x 128 contiguous bytes (4 L1 wavefronts) instead of 32 rows x 16 bytes (32 wavefronts) — the thread-per-row pattern
+// made the LSU, not HBM, the limit of the residual GEMMs (out += alpha * (acc + bias) reads AND writes 128 B/row/chunk).
+// The residual loads are software-pipelined: the first chunk's residual is requested BEFORE the wait on the
+// accumulator barrier and chunk c+1's while chunk c is being converted.
+template <int EPI>
+__device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord& t, int q, int lane, uint32_t taddr,
+                                           int c0, int c1, uint64_t* tfull_bar, uint32_t aphase, float* stage) {
+  const long long orow = output_row(p, t, q * 32 + lane);
+  const int n0_tile = t.n0;
+  if ((EPI == EPI_RESID || EPI == EPI_F32) && p.f32_coalesced) {
+    const int slot = lane & 7, rsub = lane >> 3;
+    long long ro[8];  // element offset of (row it*4+rsub, column n0_tile + slot*4), or -1
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const long long o = __shfl_sync(0xffffffffu, orow, it * 4 + rsub);
+      ro[it] = (o >= 0) ? o * p.ldo + n0_tile + slot * 4 : -1;
+    }
+    float* out = reinterpret_cast<float*>(p.out);
+    float4 r[8];
+    if (EPI == EPI_RESID && n0_tile + c0 + slot * 4 + 4 <= p.N) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        if (ro[it] >= 0) r[it] = *reinterpret_cast<const float4*>(out + ro[it] + c0);
+    }
+    mbar_wait(tfull_bar, aphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c0; c < c1; c += 32) {
+      if (n0_tile + c >= p.N) break;
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c, acc);
+      const int n = n0_tile + c + slot * 4;       // first of this lane's 4 columns
+      const bool vec = (n + 4 <= p.N);
+      float4 rn[8];
+      const bool pre_next = EPI == EPI_RESID && (c + 32 < c1) && (n + 32 + 4 <= p.N);
+      if (pre_next) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          if (ro[it] >= 0) rn[it] = *reinterpret_cast<const float4*>(out + ro[it] + c + 32);
+      }
+      float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias != nullptr) {
+        if (vec) {
+          b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+        } else {
+          if (n + 0 < p.N) b4.x = __ldg(p.bias + n + 0);
+          if (n + 1 < p.N) b4.y = __ldg(p.bias + n + 1);
+          if (n + 2 < p.N) b4.z = __ldg(p.bias + n + 2);
+        }
+      }
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(stage + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+            make_uint4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + rsub;
+        float4 v = *reinterpret_cast<const float4*>(stage + row * 32 + ((slot ^ (row & 7)) << 2));
+        v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+        if (ro[it] < 0) continue;
+        float* o = out + ro[it] + c;
+        if (vec) {
+          if (EPI == EPI_RESID) {
+            r[it].x += p.alpha * v.x; r[it].y += p.alpha * v.y; r[it].z += p.alpha * v.z; r[it].w += p.alpha * v.w;
+            *reinterpret_cast<float4*>(o) = r[it];
+          } else {
+            *reinterpret_cast<float4*>(o) = v;
+          }
+        } else {
+          const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            if (n + k < p.N) o[k] = (EPI == EPI_RESID) ? o[k] + p.alpha * vv[k] : vv[k];
+        }
+      }
+      __syncwarp();
+      if (pre_next) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) r[it] = rn[it];
+      }
+    }
+  } else {
+    mbar_wait(tfull_bar, aphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c0; c < c1; c += 32) {
+      if (n0_tile + c >= p.N) break;
+      uint32_t acc[32];
+      tmem_ld_32x32(taddr + c, acc);
+      tmem_ld_wait();
+      if (orow >= 0) store_chunk<EPI>(p, orow, n0_tile + c, acc);
+    }
+  }
+}
+
+// warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..9: epilogue (two warps per TMEM lane quarter, each
+// draining one half of the accumulator columns, so twice the loads / stores are in flight per tile)
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+
 template <int BN>
 struct GemmCfg {
   static constexpr int BM = 128;
@@ -209,12 +319,12 @@ struct GemmCfg {
   static constexpr uint32_t A_BYTES = BM * BK * 2;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiWarps * 4096 /*epilogue staging*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKParams p) {
   using Cfg = GemmCfg<BN>;
@@ -240,7 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], p.epi_warps);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -311,24 +421,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         aphase ^= 1;
       }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < 2 + p.epi_warps) {
     // ------------------------------------------------------------ epilogue warps
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;  // which half of the accumulator columns this warp drains
+    const int ccols = (p.epi_warps == 8) ? BN / 2 : BN;
+    float* stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 1024;
     uint32_t as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile, BN);
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      const int r = q * 32 + lane;
-      const long long orow = output_row(p, t, r);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (t.n0 + c >= p.N) break;
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, acc);
-        tmem_ld_wait();
-        if (orow >= 0) store_chunk<EPI>(p, orow, t.n0 + c, acc);
-      }
+      drain_tile<EPI>(p, t, q, lane, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, chalf * ccols,
+                      (chalf + 1) * ccols, &tfull[as], aphase, stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -359,12 +462,12 @@ struct Gemm2Cfg {
   static constexpr uint32_t B_BYTES = (BN / 2) * BK * 2;
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 6 : 8;
-  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + kEpiWarps * 4096;
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
 template <int BN, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmKParams p) {
   using Cfg = Gemm2Cfg<BN>;
@@ -389,12 +492,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full[i], 2);   // one arrival per CTA's producer (on the leader's copy)
+      mbar_init(&full[i], 1);   // the leader's producer arrives with the byte count of BOTH CTAs' loads
       mbar_init(&empty[i], 1);  // multicast tcgen05.commit
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);  // 4 epilogue warps x 2 CTAs (on the leader's copy)
+      mbar_init(&tempty[i], 2 * p.epi_warps);  // epilogue warps of both CTAs (on the leader's copy)
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmA);
@@ -436,8 +539,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       TileCoord t = tile_coord(tile);
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&empty[stage], phase ^ 1);
+        // Only the leader arrives (expecting both CTAs' bytes).  The peer cannot run a phase ahead: its `empty`
+        // barrier is released by the leader's tcgen05.commit, i.e. after the leader consumed this phase.
         if (leader) mbar_expect_tx(&full[stage], 2 * Cfg::STAGE_BYTES);
-        else mbar_arrive_remote(&full[stage], 0);
         if (p.conv_mode) {
           int tap = kb / p.conv_cblocks;
           int cb = kb - tap * p.conv_cblocks;
@@ -481,24 +585,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         aphase ^= 1;
       }
     }
-  } else if (warp >= 2) {
+  } else if (warp >= 2 && warp < 2 + p.epi_warps) {
     // ------------------------------------------------------------ epilogue warps (both CTAs, own 128 rows)
     const int q = warp & 3;
+    const int chalf = (warp - 2) >> 2;
+    const int ccols = (p.epi_warps == 8) ? BN / 2 : BN;
+    float* stage = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES + 256) + (warp - 2) * 1024;
     uint32_t as = 0, aphase = 0;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
       TileCoord t = tile_coord(tile);
-      mbar_wait(&tfull[as], aphase);
-      tc_fence_after();
-      const int r = q * 32 + lane;
-      const long long orow = output_row(p, t, r);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (t.n0 + c >= p.N) break;
-        uint32_t acc[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c, acc);
-        tmem_ld_wait();
-        if (orow >= 0) store_chunk<EPI>(p, orow, t.n0 + c, acc);
-      }
+      drain_tile<EPI>(p, t, q, lane, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, chalf * ccols,
+                      (chalf + 1) * ccols, &tfull[as], aphase, stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -707,7 +804,7 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
     RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
-  kern<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   if (g_prof_on) {
@@ -767,7 +864,7 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
     RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
-  kern<<<2 * clusters, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kern<<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   if (g_prof_on) {
@@ -803,6 +900,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.row_lens = a.row_lens;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
   p.conv_mode = a.conv_mode;
+  p.epi_warps = (a.K <= 2048) ? 8 : 4;
+  p.f32_coalesced = (a.out_mode != OUT_BF16) && (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
+                    (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
   p.A = a.A;
   p.W = a.W;
   p.lda = a.lda ? a.lda : a.K;

@@ -202,9 +202,10 @@ class Engine:
                   "rvb_ctc_greedy_search")
         return [toks[b, :olen[b]].tolist() for b in range(B)]
 
-    def prefix_beam_search(self, topk_val: torch.Tensor, topk_idx: torch.Tensor, enc_lens, beam: int,
-                           blank_id: int = 0):
-        """-> per utterance (nbest tokens [tuple], nbest scores [float], nbest times [list])."""
+    def prefix_beam_search_raw(self, topk_val: torch.Tensor, topk_idx: torch.Tensor, enc_lens, beam: int,
+                               blank_id: int = 0):
+        """n-best as arrays: tokens/times (B, beam, max_len) int32, lens (B, beam, 2) = {n_tokens, n_times},
+        scores (B, beam) float64, n_hyp (B,)."""
         B, Tp, k = topk_idx.shape
         lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
         max_len = max(int(lens.max()) if B else 1, 1)
@@ -218,28 +219,29 @@ class Engine:
                                                       int(blank_id), max_len, _np_ptr(toks), _np_ptr(tims),
                                                       _np_ptr(olen), _np_ptr(scores), _np_ptr(nhyp), self._stream()),
                   "rvb_ctc_prefix_beam_search")
+        return toks, tims, olen, scores, nhyp
+
+    def prefix_beam_search(self, topk_val: torch.Tensor, topk_idx: torch.Tensor, enc_lens, beam: int,
+                           blank_id: int = 0):
+        """-> per utterance (nbest tokens [tuple], nbest scores [float], nbest times [list])."""
+        toks, tims, olen, scores, nhyp = self.prefix_beam_search_raw(topk_val, topk_idx, enc_lens, beam, blank_id)
         out = []
-        for b in range(B):
+        for b in range(toks.shape[0]):
             n = int(nhyp[b])
             nbest = [tuple(toks[b, r, :olen[b, r, 0]].tolist()) for r in range(n)]
             times = [tims[b, r, :olen[b, r, 1]].tolist() for r in range(n)]
             out.append((nbest, [float(s) for s in scores[b, :n]], times))
         return out
 
-    def rescoring_scores(self, enc_out: torch.Tensor, enc_lens, nbest: List[List[tuple]], cat_embs=None,
-                         reverse_weight: float = 0.0):
-        """Teacher-forced decoder log-probs of every hypothesis token.
-        -> (l2r, r2l): float32 arrays (B, N, Lmax+1), see rvb_attention_rescoring; r2l is None when unused."""
+    def rescoring_scores_raw(self, enc_out: torch.Tensor, enc_lens, toks: np.ndarray, hlen: np.ndarray, cat_embs=None,
+                             reverse_weight: float = 0.0):
+        """toks (B, N, L) int32 padded hypotheses, hlen (B, N) their lengths (-1 = absent).
+        -> (l2r, r2l) float32 (B, N, Lmax+1), see rvb_attention_rescoring; r2l is None when unused."""
         B, Tp, _ = enc_out.shape
-        N = max(len(h) for h in nbest)
-        max_len = max([len(h) for hs in nbest for h in hs] + [1])
-        toks = np.zeros((B, N, max_len), dtype=np.int32)
-        hlen = np.full((B, N), -1, dtype=np.int32)
-        for b, hs in enumerate(nbest):
-            for i, h in enumerate(hs):
-                hlen[b, i] = len(h)
-                if len(h):
-                    toks[b, i, :len(h)] = np.asarray(h, dtype=np.int32)
+        N = toks.shape[1]
+        max_len = max(int(hlen.max()), 1)
+        toks = np.ascontiguousarray(toks[:, :, :max_len], dtype=np.int32)
+        hlen = np.ascontiguousarray(hlen, dtype=np.int32)
         lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
         l2r = np.zeros((B, N, max_len + 1), dtype=np.float32)
         use_r = reverse_weight > 0.0 and self.has_right_decoder
@@ -251,6 +253,21 @@ class Engine:
                                                    float(reverse_weight), _np_ptr(l2r), _np_ptr(r2l), self._stream()),
                   "rvb_attention_rescoring")
         return l2r, r2l
+
+    def rescoring_scores(self, enc_out: torch.Tensor, enc_lens, nbest: List[List[tuple]], cat_embs=None,
+                         reverse_weight: float = 0.0):
+        """Teacher-forced decoder log-probs of every hypothesis token (hypotheses given as lists of tuples)."""
+        B = enc_out.shape[0]
+        N = max(len(h) for h in nbest)
+        max_len = max([len(h) for hs in nbest for h in hs] + [1])
+        toks = np.zeros((B, N, max_len), dtype=np.int32)
+        hlen = np.full((B, N), -1, dtype=np.int32)
+        for b, hs in enumerate(nbest):
+            for i, h in enumerate(hs):
+                hlen[b, i] = len(h)
+                if len(h):
+                    toks[b, i, :len(h)] = np.asarray(h, dtype=np.int32)
+        return self.rescoring_scores_raw(enc_out, enc_lens, toks, hlen, cat_embs, reverse_weight)
 
 
 def launch_count() -> int:

@@ -78,3 +78,35 @@ def rescoring_pick(hyps: Sequence[tuple], ctc_scores: Sequence[float], nbest_tim
         tc = [(tc[j] + math.exp(float(r2l[best, j]))) / 2 for j in range(U)]
     return DecodeResult(hyps[best], float(total[best]), confidence=math.exp(float(norm[best])),
                         times=nbest_times[best], tokens_confidence=tc)
+
+
+def rescoring_pick_batch(toks: np.ndarray, tims: np.ndarray, olen: np.ndarray, ctc_scores: np.ndarray,
+                         nhyp: np.ndarray, l2r: np.ndarray, r2l: Optional[np.ndarray], ctc_weight: float,
+                         reverse_weight: float) -> List[DecodeResult]:
+    """`rescoring_pick` for a whole batch straight from the prefix-beam arrays (no per-hypothesis Python objects):
+    toks/tims (B, N, L), olen (B, N, 2), ctc_scores (B, N) float64, nhyp (B,), l2r/r2l (B, N, Lmax+1) float32.
+    Same float semantics as `rescoring_pick` (sequential float32 sums, see there)."""
+    B, N = ctc_scores.shape
+    lens = olen[:, :, 0].astype(np.int64)
+    score = np.add.accumulate(l2r, axis=2, dtype=np.float32)[:, :, -1]
+    use_r = reverse_weight > 0 and r2l is not None
+    if use_r:
+        r_score = np.add.accumulate(r2l, axis=2, dtype=np.float32)[:, :, -1]
+        score = (score * np.float32(1 - reverse_weight) + r_score * np.float32(reverse_weight)).astype(np.float32)
+    norm = (score / (lens + 1).astype(np.float32)).astype(np.float32)
+    total = (score + (ctc_scores * ctc_weight).astype(np.float32)).astype(np.float32)
+    valid = np.arange(N)[None, :] < nhyp[:, None]
+    total = np.where(valid, total, -np.inf).astype(np.float32)
+    best = np.argmax(total, axis=1)                      # first maximum == the reference's strict `>` scan
+    out = []
+    for b in range(B):
+        i = int(best[b])
+        U = int(lens[b, i])
+        tc = [math.exp(float(x)) for x in l2r[b, i, :U]]
+        if use_r:
+            tc = [(tc[j] + math.exp(float(r2l[b, i, j]))) / 2 for j in range(U)]
+        nt = int(olen[b, i, 1])
+        out.append(DecodeResult(tuple(toks[b, i, :U].tolist()), float(total[b, i]),
+                                confidence=math.exp(float(norm[b, i])), times=tims[b, i, :nt].tolist(),
+                                tokens_confidence=tc))
+    return out

@@ -65,7 +65,7 @@ def test_layernorm(lib, d):
     torch.testing.assert_close(out_b.float(), ref.bfloat16().float(), rtol=2e-2, atol=2e-2)
 
 
-GEMM_SHAPES = [(128, 128, 64), (300, 256, 128), (257, 101, 128), (1000, 1024, 4096), (64, 384, 2432), (4096, 4096, 1024)]
+GEMM_SHAPES = [(128, 128, 64), (300, 256, 128), (257, 101, 128), (513, 1001, 192), (1000, 1024, 4096), (64, 384, 2432), (4096, 4096, 1024)]
 
 
 @pytest.mark.parametrize("impl", [1, 0, 2], ids=["simt", "tcgen05", "tcgen05_2cta"])
@@ -83,6 +83,7 @@ def test_gemm_bias_act_modes(lib, impl, M, N, K):
         out = torch.zeros(M, ldo, device="cuda")
         _check(lib, lib.rvb_gemm_bf16(_p(A), _p(W), _p(bias), M, N, K, 0, 1, 1.0, _p(out), ldo, _stream()))
         torch.testing.assert_close(out[:, :N], ref, rtol=1e-3, atol=1e-3)
+        assert bool((out[:, N:] == 0).all())              # row padding is never written
         # bf16 out + SiLU
         out_b = torch.zeros(M, ldo, device="cuda", dtype=torch.bfloat16)
         _check(lib, lib.rvb_gemm_bf16(_p(A), _p(W), _p(bias), M, N, K, 2, 0, 1.0, _p(out_b), ldo, _stream()))
@@ -92,9 +93,10 @@ def test_gemm_bias_act_modes(lib, impl, M, N, K):
         res0 = res.clone()
         _check(lib, lib.rvb_gemm_bf16(_p(A), _p(W), _p(bias), M, N, K, 1, 2, 0.5, _p(res), ldo, _stream()))
         torch.testing.assert_close(res[:, :N], res0[:, :N] + 0.5 * torch.relu(ref), rtol=1e-3, atol=1e-3)
+        assert torch.equal(res[:, N:], res0[:, N:])
         torch.cuda.synchronize()
     finally:
-        lib.rvb_set_gemm_impl(0)
+        lib.rvb_set_gemm_impl(-1)       # back to the default (env RVB_GEMM or the 2-CTA kernel)
 
 
 @pytest.mark.parametrize("dk,H", [(64, 2), (32, 4), (128, 1)])
