@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--cpu-chunks", type=int, default=1, help="30 s chunks per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=1, help="concurrent decoding lanes (streams + host threads) per GPU")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
     ap.add_argument("--breakdown", action="store_true", help="print a per-stage wall-clock split (synchronised) to stderr")
     args = ap.parse_args()
 
@@ -308,6 +310,15 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_resident()
 
+    if args.profile_step:
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        step_resident()
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        print("profiled one step", file=sys.stderr)
+        return
+
     if args.breakdown and rank == 0:
         from reverb_b200.search import prefix_beam_results
 
@@ -358,6 +369,16 @@ def main():
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
     achieved_tf = (gfl.value / (gms.value / 1e3)) / 1e12 if gms.value > 0 else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch, from the committed ncu pass over one step of this
+    # same command (profiles/gemm_traffic.json, written from the ncu csv by tools/summarize_dram.py); None if absent
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "gemm_traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("shape") == args.shape and tj.get("chunks") == args.chunks:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj.get("source")
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -366,9 +387,10 @@ def main():
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(pcm_host.numel() * 2),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05+TMA, all dense layers incl. conv2 implicit GEMM)",
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel (2-CTA tcgen05 + TMA, all dense layers incl. conv2 implicit GEMM)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                     "peak_source": peak_src, "traffic": None,
+                     "peak_source": peak_src, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
+                     "traffic_source": traffic_src,
                      "launches_timed": int(gn.value), "kernel_ms_per_step": gms.value / args.steps,
                      "kernel_share_of_step": gms.value / ms if ms > 0 else None,
                      "algorithmic_flops_per_step": gfl.value / args.steps},

@@ -119,7 +119,10 @@ RVB_API int rvb_attention_rescoring(rvb_model* m, const float* d_enc_out, const 
                             void* stream);
 
 /* ---- kernel-level entry points (parity tests, profiling) ----------------------------------------------------- */
-/* C[M,N] = A[M,K] W[N,K]^T + bias; act: 0 none 1 relu 2 silu; out_mode: 0 bf16, 1 f32, 2 f32 residual += alpha*(.) */
+/* C[M,N] = A[M,K] W[N,K]^T + bias; act: 0 none 1 relu 2 silu 3 glu; out_mode: 0 bf16, 1 f32, 2 f32 residual += alpha*(.)
+ * act 3 (pointwise_conv1 + GLU of the conformer conv module, convolution.py:129-130): bf16 output (M, N/2); W / bias
+ * rows interleaved in groups of 32 — rows [64j, 64j+32) are the value half of output channels [32j, 32j+32), rows
+ * [64j+32, 64j+64) their gates; out[m, c] = value * sigmoid(gate). */
 RVB_API int rvb_gemm_bf16(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int act, int out_mode,
                   float alpha, void* d_out, int ldo, void* stream);
 RVB_API int rvb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, float eps, int M, int d,

@@ -141,7 +141,8 @@ def conv_module(x, mask_pad, sd: SD, p: str, K: int, causal: bool, layer_norm: b
     x = x.masked_fill(~mask_pad, 0.0)
     if causal:
         x = F.pad(x, (K - 1, 0), "constant", 0.0)
-    x = _q(F.conv1d(_q(x), _q(sd[p + ".pointwise_conv1.weight"]), sd[p + ".pointwise_conv1.bias"]))
+    # (bf16 emulation: the CUDA path applies GLU to the fp32 accumulators in the GEMM epilogue and stores bf16 once)
+    x = F.conv1d(_q(x), _q(sd[p + ".pointwise_conv1.weight"]), sd[p + ".pointwise_conv1.bias"])
     x = _q(F.glu(x, dim=1))
     x = F.conv1d(x, sd[p + ".depthwise_conv.weight"], sd[p + ".depthwise_conv.bias"],
                  padding=0 if causal else (K - 1) // 2, groups=x.shape[1])

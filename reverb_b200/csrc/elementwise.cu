@@ -283,241 +283,46 @@ int launch_conv1(const float* feats, const float* mean, const float* istd, const
 
 // ---------------------------------------------------------------------------------------------------------------
 // Conformer convolution module, middle part (transformer/convolution.py:129-138):
-//   GLU over channels -> depthwise conv (K taps, causal left pad K-1 or symmetric (K-1)/2) + bias
+//   [pointwise_conv1 + GLU: fused into the GEMM epilogue, ACT_GLU]
+//   depthwise conv (K taps, causal left pad K-1 or symmetric (K-1)/2) + bias
 //   -> LayerNorm over channels (or BatchNorm1d eval) -> SiLU.
-// Input (B, T, 2C) bf16 = pointwise_conv1 output incl. bias; output (B, T, C) bf16 feeds pointwise_conv2.
-// One CTA per (b, 16 output frames): GLU'd halo rows staged in smem (bf16), conv results in smem (fp32),
-// then one warp per frame does the channel reduction.  Layout stays (B, T, C): no transposes.
+// Input (B, T, C) bf16 = GLU(pointwise_conv1(x)); output (B, T, C) bf16 feeds pointwise_conv2.  Layout stays
+// (B, T, C) end to end: no transposes.
+//
+// Kernel A (conv_dw_kernel): one (batch, CM_TT-frame tile, 128-channel-pair slice) per 128-thread CTA; a thread owns
+// one channel pair, loads its CM_TT+K-1 halo values straight into registers (a warp reads 128 contiguous bytes per
+// frame) and runs the fully unrolled sliding window.  No block-wide phases, several CTAs per SM, so the loads of one
+// CTA overlap the FMAs of the others.  With LayerNorm it writes the fp32 conv result and accumulates per-frame
+// sum / sum of squares with one atomic pair per (frame, CTA); kernel B (conv_norm_silu_kernel, one warp per frame)
+// normalises + SiLU -> bf16.  With BatchNorm (eval) kernel A applies norm + SiLU itself and writes bf16 directly.
+// K = 0 instantiates the generic version (run-time tap count, halo re-read through L1).
+//
+// pad_glu (C fp32, causal mode): the reference left-pads K-1 zero frames BEFORE pointwise_conv1
+// (convolution.py:113-114,129-130), so the pad frames reach the depthwise conv as GLU(bias), not zeros.
 constexpr int CM_TT = 16;
 
-// Fast path: K compile-time, each thread owns NIT channel pairs and keeps its CM_TT x 2 x NIT conv outputs in
-// registers (fully unrolled sliding window), LayerNorm statistics by two block reductions; only the GLU'd halo rows
-// live in shared memory (bf16), so 3 CTAs fit per SM at C = 1024.
-template <int K, int NIT, int NT>
-__global__ void __launch_bounds__(NT)
-conv_mid_fast_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_bias, const float* __restrict__ dw_w,
-                     const float* __restrict__ dw_b,
-                     const float* __restrict__ norm_w, const float* __restrict__ norm_b,
-                     const float* __restrict__ bn_mean, const float* __restrict__ bn_var, int use_ln, float eps,
-                     bf16* __restrict__ out, int T, int C, int causal) {
-  constexpr int ROWS = CM_TT + K - 1;
-  extern __shared__ __align__(16) uint8_t smem_cm[];
-  uint32_t* s_glu = reinterpret_cast<uint32_t*>(smem_cm);  // [ROWS][C/2] packed bf16 pairs
-  __shared__ float s_part[NT / 32][CM_TT];
-  __shared__ float s_stat[2][CM_TT];
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * CM_TT;
-  const int left = causal ? (K - 1) : (K - 1) / 2;
-  const int C2 = C >> 1;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // staging: batches of 8 independent (row, channel-pair) items per thread so that 16 loads are in flight at once
-  constexpr int U = 8;
-  for (int base = 0; base < ROWS * C2; base += NT * U) {
-    uint32_t ra[U], rg[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * NT + threadIdx.x;
-      ra[u] = 0u;
-      rg[u] = 0u;
-      if (i < ROWS * C2) {
-        const int r = i / C2, cp = i - r * C2;
-        const int t = t0 - left + r;
-        if (t >= 0 && t < T) {
-          const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + ((long long)b * T + t) * (2 * C));
-          ra[u] = xr[cp];
-          rg[u] = xr[C2 + cp];
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int i = base + u * NT + threadIdx.x;
-      if (i >= ROWS * C2) continue;
-      const int r = i / C2, cp = i - r * C2;
-      const int t = t0 - left + r;
-      uint32_t o = 0u;
-      if (t >= 0 && t < T) {
-        float2 a = unpack_bf16x2(ra[u]);
-        float2 g = unpack_bf16x2(rg[u]);
-        o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
-      } else if (t < 0 && causal) {
-        // the reference left-pads K-1 zero frames BEFORE pointwise_conv1 (convolution.py:113-114,129-130), so the
-        // pad frames reach the depthwise conv as GLU(bias), not as zeros
-        float2 a = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + 2 * cp), __ldg(pw1_bias + 2 * cp + 1)));
-        float2 g = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + C + 2 * cp), __ldg(pw1_bias + C + 2 * cp + 1)));
-        o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
-      }
-      s_glu[i] = o;
-    }
-  }
-  __syncthreads();
-  float acc[NIT][CM_TT][2];
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int cp = threadIdx.x + it * NT;
-    const bool ok = cp < C2;
-    float w0[K], w1[K];
-    float b0 = 0.f, b1 = 0.f;
-    if (ok) {
-      b0 = __ldg(dw_b + 2 * cp);
-      b1 = __ldg(dw_b + 2 * cp + 1);
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        w0[k] = __ldg(dw_w + (2 * cp) * K + k);
-        w1[k] = __ldg(dw_w + (2 * cp + 1) * K + k);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < K; ++k) w0[k] = w1[k] = 0.f;
-    }
-#pragma unroll
-    for (int t = 0; t < CM_TT; ++t) {
-      acc[it][t][0] = b0;
-      acc[it][t][1] = b1;
-    }
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r) {
-      float2 v = ok ? unpack_bf16x2(s_glu[r * C2 + cp]) : make_float2(0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        constexpr int dummy = 0;
-        (void)dummy;
-        const int t = r - k;  // compile-time after unrolling
-        if (t >= 0 && t < CM_TT) {
-          acc[it][t][0] = fmaf(w0[k], v.x, acc[it][t][0]);
-          acc[it][t][1] = fmaf(w1[k], v.y, acc[it][t][1]);
-        }
-      }
-    }
-  }
-  float mean[CM_TT], rstd[CM_TT];
-  if (use_ln) {
-    // pass 1: mean over channels
-#pragma unroll
-    for (int t = 0; t < CM_TT; ++t) {
-      float s = 0.f;
-#pragma unroll
-      for (int it = 0; it < NIT; ++it)
-        if (threadIdx.x + it * NT < C2) s += acc[it][t][0] + acc[it][t][1];
-      s = warp_sum(s);
-      if (lane == 0) s_part[warp][t] = s;
-    }
-    __syncthreads();
-    if (threadIdx.x < CM_TT) {
-      float s = 0.f;
-      for (int w = 0; w < NT / 32; ++w) s += s_part[w][threadIdx.x];
-      s_stat[0][threadIdx.x] = s / (float)C;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < CM_TT; ++t) mean[t] = s_stat[0][t];
-    // pass 2: variance (two-pass, like ATen)
-#pragma unroll
-    for (int t = 0; t < CM_TT; ++t) {
-      float q = 0.f;
-#pragma unroll
-      for (int it = 0; it < NIT; ++it)
-        if (threadIdx.x + it * NT < C2) {
-          float d0 = acc[it][t][0] - mean[t], d1 = acc[it][t][1] - mean[t];
-          q += d0 * d0 + d1 * d1;
-        }
-      q = warp_sum(q);
-      if (lane == 0) s_part[warp][t] = q;
-    }
-    __syncthreads();
-    if (threadIdx.x < CM_TT) {
-      float q = 0.f;
-      for (int w = 0; w < NT / 32; ++w) q += s_part[w][threadIdx.x];
-      s_stat[1][threadIdx.x] = rsqrtf(q / (float)C + eps);
-    }
-    __syncthreads();
-#pragma unroll
-    for (int t = 0; t < CM_TT; ++t) rstd[t] = s_stat[1][t];
-  }
-#pragma unroll
-  for (int it = 0; it < NIT; ++it) {
-    const int cp = threadIdx.x + it * NT;
-    if (cp >= C2) continue;
-    const int c0 = 2 * cp, c1 = 2 * cp + 1;
-    const float g0 = __ldg(norm_w + c0), g1 = __ldg(norm_w + c1), be0 = __ldg(norm_b + c0), be1 = __ldg(norm_b + c1);
-    float m0 = 0.f, m1 = 0.f, r0 = 1.f, r1 = 1.f;
-    if (!use_ln) {
-      m0 = __ldg(bn_mean + c0);
-      m1 = __ldg(bn_mean + c1);
-      r0 = rsqrtf(__ldg(bn_var + c0) + eps);
-      r1 = rsqrtf(__ldg(bn_var + c1) + eps);
-    }
-#pragma unroll
-    for (int t = 0; t < CM_TT; ++t) {
-      if (t0 + t >= T) continue;
-      float y0, y1;
-      if (use_ln) {
-        y0 = (acc[it][t][0] - mean[t]) * rstd[t] * g0 + be0;
-        y1 = (acc[it][t][1] - mean[t]) * rstd[t] * g1 + be1;
-      } else {
-        y0 = (acc[it][t][0] - m0) * r0 * g0 + be0;
-        y1 = (acc[it][t][1] - m1) * r1 * g1 + be1;
-      }
-      reinterpret_cast<uint32_t*>(out + ((long long)b * T + t0 + t) * C)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Split version (default for K in {7,15,31}): kernel A = GLU + depthwise conv for one (batch, 16-frame tile,
-// 128-channel-pair slice) per 128-thread CTA — no block-wide phases, so the loads of one CTA overlap the FMAs of the
-// others (4+ CTAs / SM) — writes the fp32 conv result and accumulates per-frame sum / sum-of-squares with one atomic
-// pair per (frame, CTA); kernel B = LayerNorm(from the accumulated statistics) + SiLU -> bf16, one warp per frame.
-// With BatchNorm (eval) kernel A applies norm + SiLU itself and writes bf16 directly.
 template <int K>
 __global__ void __launch_bounds__(128)
-conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_bias, const float* __restrict__ dw_w,
+conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, const float* __restrict__ dw_w,
                const float* __restrict__ dw_b, const float* __restrict__ norm_w, const float* __restrict__ norm_b,
                const float* __restrict__ bn_mean, const float* __restrict__ bn_var, int use_ln, float eps,
                float* __restrict__ conv_out, float* __restrict__ stats, bf16* __restrict__ out, int T, int C,
-               int causal) {
-  constexpr int ROWS = CM_TT + K - 1;
+               int Krt, int causal) {
   __shared__ float s_part[4][CM_TT][2];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * CM_TT;
   const int C2 = C >> 1;
   const int cp = blockIdx.z * 128 + threadIdx.x;
   const bool ok = cp < C2;
-  const int left = causal ? (K - 1) : (K - 1) / 2;
+  const int KK = (K > 0) ? K : Krt;
+  const int left = causal ? (KK - 1) : (KK - 1) / 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t ra[ROWS], rg[ROWS];
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const int t = t0 - left + r;
-    ra[r] = 0u;
-    rg[r] = 0u;
-    if (ok && t >= 0 && t < T) {
-      const uint32_t* xr = reinterpret_cast<const uint32_t*>(x + ((long long)b * T + t) * (2 * C));
-      ra[r] = __ldg(xr + cp);
-      rg[r] = __ldg(xr + C2 + cp);
-    }
-  }
-  float w0[K], w1[K];
   float b0 = 0.f, b1 = 0.f;
   float2 padv = make_float2(0.f, 0.f);
   if (ok) {
     b0 = __ldg(dw_b + 2 * cp);
     b1 = __ldg(dw_b + 2 * cp + 1);
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-      w0[k] = __ldg(dw_w + (2 * cp) * K + k);
-      w1[k] = __ldg(dw_w + (2 * cp + 1) * K + k);
-    }
-    if (causal) {
-      // the reference left-pads K-1 zero frames BEFORE pointwise_conv1 (convolution.py:113-114,129-130): the pad
-      // frames reach the depthwise conv as GLU(bias), not as zeros
-      float2 a = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + 2 * cp), __ldg(pw1_bias + 2 * cp + 1)));
-      float2 g = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + C + 2 * cp), __ldg(pw1_bias + C + 2 * cp + 1)));
-      padv = unpack_bf16x2(pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y)));
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < K; ++k) w0[k] = w1[k] = 0.f;
+    if (causal) padv = make_float2(__ldg(pad_glu + 2 * cp), __ldg(pad_glu + 2 * cp + 1));
   }
   float acc[CM_TT][2];
 #pragma unroll
@@ -525,23 +330,46 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_bias, c
     acc[t][0] = b0;
     acc[t][1] = b1;
   }
+  const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (long long)b * T * C) + cp;
+  if constexpr (K > 0) {
+    constexpr int ROWS = CM_TT + K - 1;
+    uint32_t rv[ROWS];
 #pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const int tt = t0 - left + r;
-    float2 v;
-    if (tt >= 0 && tt < T) {
-      float2 a = unpack_bf16x2(ra[r]);
-      float2 g = unpack_bf16x2(rg[r]);
-      v = unpack_bf16x2(pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y)));  // GLU output is stored as bf16
-    } else {
-      v = (tt < 0) ? padv : make_float2(0.f, 0.f);
+    for (int r = 0; r < ROWS; ++r) {
+      const int t = t0 - left + r;
+      rv[r] = 0u;
+      if (ok && t >= 0 && t < T) rv[r] = __ldg(xb + (long long)t * C2);
     }
+    float w0[K], w1[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
-      const int t = r - k;  // compile-time after unrolling
-      if (t >= 0 && t < CM_TT) {
-        acc[t][0] = fmaf(w0[k], v.x, acc[t][0]);
-        acc[t][1] = fmaf(w1[k], v.y, acc[t][1]);
+      w0[k] = ok ? __ldg(dw_w + (2 * cp) * K + k) : 0.f;
+      w1[k] = ok ? __ldg(dw_w + (2 * cp + 1) * K + k) : 0.f;
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+      const int tt = t0 - left + r;
+      const float2 v = (tt < 0) ? padv : unpack_bf16x2(rv[r]);  // rv is 0 beyond T
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int t = r - k;  // compile-time after unrolling
+        if (t >= 0 && t < CM_TT) {
+          acc[t][0] = fmaf(w0[k], v.x, acc[t][0]);
+          acc[t][1] = fmaf(w1[k], v.y, acc[t][1]);
+        }
+      }
+    }
+  } else if (ok) {  // generic tap count
+    for (int k = 0; k < KK; ++k) {
+      const float w0 = __ldg(dw_w + (2 * cp) * KK + k), w1 = __ldg(dw_w + (2 * cp + 1) * KK + k);
+#pragma unroll
+      for (int t = 0; t < CM_TT; ++t) {
+        const int tt = t0 + t - left + k;
+        float2 v = make_float2(0.f, 0.f);
+        if (tt < 0) v = padv;
+        else if (tt < T) v = unpack_bf16x2(__ldg(xb + (long long)tt * C2));
+        acc[t][0] = fmaf(w0, v.x, acc[t][0]);
+        acc[t][1] = fmaf(w1, v.y, acc[t][1]);
       }
     }
   }
@@ -611,16 +439,24 @@ conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restric
   }
 }
 
-template <int K>
-static int launch_conv_split(const bf16* x, const float* pw1_bias, const float* dw_w, const float* dw_b,
-                             const float* norm_w, const float* norm_b, const float* bn_mean, const float* bn_var,
-                             int use_ln, float eps, bf16* out, float* conv_tmp, float* stats, int B, int T, int C,
-                             int causal, cudaStream_t stream) {
+int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, const float* dw_b, const float* norm_w,
+                    const float* norm_b, const float* bn_mean, const float* bn_var, int use_ln, float eps,
+                    bf16* out, int B, int T, int C, int K, int causal, cudaStream_t stream, float* conv_tmp,
+                    float* stats) {
+  RVB_REQUIRE(C % 4 == 0 && C <= 4096 && K >= 1 && K <= 64, "conv_mid: unsupported C=%d K=%d", C, K);
+  RVB_REQUIRE(!causal || pad_glu != nullptr, "conv_mid: causal mode needs the GLU(pointwise_conv1 bias) pad row");
+  RVB_REQUIRE(!use_ln || (conv_tmp != nullptr && stats != nullptr), "conv_mid: LayerNorm needs the fp32 scratch");
   const int C2 = C / 2;
   if (use_ln) RVB_CHECK_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * T * 2 * sizeof(float), stream));
   dim3 grid((T + CM_TT - 1) / CM_TT, B, (C2 + 127) / 128);
-  conv_dw_kernel<K><<<grid, 128, 0, stream>>>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln, eps,
-                                              conv_tmp, stats, out, T, C, causal);
+#define RVB_DW(KK)                                                                                                  \
+  conv_dw_kernel<KK><<<grid, 128, 0, stream>>>(x, pad_glu, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln, eps, \
+                                               conv_tmp, stats, out, T, C, K, causal)
+  if (K == 15) RVB_DW(15);
+  else if (K == 31) RVB_DW(31);
+  else if (K == 7) RVB_DW(7);
+  else RVB_DW(0);
+#undef RVB_DW
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   if (use_ln) {
@@ -636,154 +472,6 @@ static int launch_conv_split(const bf16* x, const float* pw1_bias, const float* 
     RVB_COUNT_LAUNCH();
     RVB_CHECK_LAUNCH();
   }
-  return 0;
-}
-
-// Generic fallback (any K <= 64, any even C): conv results staged in shared memory.
-__global__ void __launch_bounds__(256)
-conv_mid_kernel(const bf16* __restrict__ x, const float* __restrict__ pw1_bias, const float* __restrict__ dw_w,
-                const float* __restrict__ dw_b, const float* __restrict__ norm_w, const float* __restrict__ norm_b, const float* __restrict__ bn_mean,
-                const float* __restrict__ bn_var, int use_ln, float eps, bf16* __restrict__ out, int T, int C, int K,
-                int causal) {
-  extern __shared__ __align__(16) uint8_t smem_cm[];
-  const int rows = CM_TT + K - 1;
-  bf16* s_glu = reinterpret_cast<bf16*>(smem_cm);                                   // [rows][C]
-  float* s_conv = reinterpret_cast<float*>(smem_cm + (size_t)rows * C * sizeof(bf16));  // [CM_TT][C]
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * CM_TT;
-  const int left = causal ? (K - 1) : (K - 1) / 2;
-  const int C2 = C >> 1;
-  for (int i = threadIdx.x; i < rows * C2; i += blockDim.x) {
-    int r = i / C2, cp = i - r * C2;
-    int t = t0 - left + r;
-    uint32_t o = 0u;
-    if (t >= 0 && t < T) {
-      const bf16* xr = x + ((long long)b * T + t) * (2 * C);
-      float2 a = unpack_bf16x2(reinterpret_cast<const uint32_t*>(xr)[cp]);
-      float2 g = unpack_bf16x2(reinterpret_cast<const uint32_t*>(xr + C)[cp]);
-      o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
-    } else if (t < 0 && causal) {
-      float2 a = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + 2 * cp), __ldg(pw1_bias + 2 * cp + 1)));
-      float2 g = unpack_bf16x2(pack_bf16x2(__ldg(pw1_bias + C + 2 * cp), __ldg(pw1_bias + C + 2 * cp + 1)));
-      o = pack_bf16x2(a.x * sigmoid_f(g.x), a.y * sigmoid_f(g.y));
-    }
-    reinterpret_cast<uint32_t*>(s_glu)[i] = o;
-  }
-  __syncthreads();
-  for (int cp = threadIdx.x; cp < C2; cp += blockDim.x) {
-    float acc0[CM_TT], acc1[CM_TT];
-    const float b0 = __ldg(dw_b + 2 * cp), b1 = __ldg(dw_b + 2 * cp + 1);
-#pragma unroll
-    for (int t = 0; t < CM_TT; ++t) {
-      acc0[t] = b0;
-      acc1[t] = b1;
-    }
-    for (int r = 0; r < rows; ++r) {
-      float2 v = unpack_bf16x2(reinterpret_cast<const uint32_t*>(s_glu)[r * C2 + cp]);
-#pragma unroll
-      for (int t = 0; t < CM_TT; ++t) {
-        int k = r - t;
-        if (k >= 0 && k < K) {
-          acc0[t] = fmaf(__ldg(dw_w + (2 * cp) * K + k), v.x, acc0[t]);
-          acc1[t] = fmaf(__ldg(dw_w + (2 * cp + 1) * K + k), v.y, acc1[t]);
-        }
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < CM_TT; ++t)
-      reinterpret_cast<float2*>(s_conv + (size_t)t * C)[cp] = make_float2(acc0[t], acc1[t]);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int t = warp; t < CM_TT; t += nwarps) {
-    if (t0 + t >= T) continue;
-    const float* row = s_conv + (size_t)t * C;
-    bf16* orow = out + ((long long)b * T + t0 + t) * C;
-    float mean = 0.f, rstd = 1.f;
-    if (use_ln) {
-      float s = 0.f;
-      for (int c = lane; c < C; c += 32) s += row[c];
-      mean = warp_sum(s) / (float)C;
-      float q = 0.f;
-      for (int c = lane; c < C; c += 32) {
-        float dlt = row[c] - mean;
-        q += dlt * dlt;
-      }
-      rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-    }
-    for (int cp = lane; cp < C2; cp += 32) {
-      float2 v = reinterpret_cast<const float2*>(row)[cp];
-      const int c0 = 2 * cp, c1 = 2 * cp + 1;
-      float y0, y1;
-      if (use_ln) {
-        y0 = (v.x - mean) * rstd * __ldg(norm_w + c0) + __ldg(norm_b + c0);
-        y1 = (v.y - mean) * rstd * __ldg(norm_w + c1) + __ldg(norm_b + c1);
-      } else {
-        y0 = (v.x - __ldg(bn_mean + c0)) * rsqrtf(__ldg(bn_var + c0) + eps) * __ldg(norm_w + c0) + __ldg(norm_b + c0);
-        y1 = (v.y - __ldg(bn_mean + c1)) * rsqrtf(__ldg(bn_var + c1) + eps) * __ldg(norm_w + c1) + __ldg(norm_b + c1);
-      }
-      reinterpret_cast<uint32_t*>(orow)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
-    }
-  }
-}
-
-template <int K, int NIT, int NT>
-static int launch_conv_mid_fast(const bf16* x, const float* pw1_bias, const float* dw_w, const float* dw_b, const float* norm_w,
-                                const float* norm_b, const float* bn_mean, const float* bn_var, int use_ln, float eps,
-                                bf16* out, int B, int T, int C, int causal, cudaStream_t stream) {
-  const size_t smem = (size_t)(CM_TT + K - 1) * C * sizeof(bf16);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    RVB_CHECK_CUDA(cudaFuncSetAttribute(conv_mid_fast_kernel<K, NIT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = smem;
-  }
-  dim3 grid((T + CM_TT - 1) / CM_TT, B);
-  conv_mid_fast_kernel<K, NIT, NT><<<grid, NT, smem, stream>>>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln,
-                                                           eps, out, T, C, causal);
-  RVB_COUNT_LAUNCH();
-  RVB_CHECK_LAUNCH();
-  return 0;
-}
-
-int launch_conv_mid(const bf16* x, const float* pw1_bias, const float* dw_w, const float* dw_b, const float* norm_w, const float* norm_b,
-                    const float* bn_mean, const float* bn_var, int use_layer_norm, float eps, bf16* out, int B, int T,
-                    int C, int K, int causal, cudaStream_t stream, float* conv_tmp, float* stats) {
-  RVB_REQUIRE(C % 2 == 0 && K >= 1 && K <= 64, "conv_mid: unsupported C=%d K=%d", C, K);
-  RVB_REQUIRE(!causal || pw1_bias != nullptr, "conv_mid: causal mode needs the pointwise_conv1 bias");
-  if (conv_tmp != nullptr && stats != nullptr && C % 4 == 0 && C <= 4096) {
-#define RVB_CS(KK)                                                                                                   \
-  return launch_conv_split<KK>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_layer_norm, eps, out,   \
-                               conv_tmp, stats, B, T, C, causal, stream)
-    if (K == 15) RVB_CS(15);
-    if (K == 31) RVB_CS(31);
-    if (K == 7) RVB_CS(7);
-#undef RVB_CS
-  }
-  // one channel pair per thread when it fits a 512-thread CTA (C <= 1024), else two per thread (C <= 2048)
-  const int C2 = C / 2;
-#define RVB_CM(KK, NN, TT)                                                                                        \
-  return launch_conv_mid_fast<KK, NN, TT>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_layer_norm, eps, out, \
-                                          B, T, C, causal, stream)
-  if (K == 15 || K == 31 || K == 7) {
-    if (C2 <= 128) { if (K == 15) RVB_CM(15, 1, 128); if (K == 31) RVB_CM(31, 1, 128); RVB_CM(7, 1, 128); }
-    if (C2 <= 256) { if (K == 15) RVB_CM(15, 1, 256); if (K == 31) RVB_CM(31, 1, 256); RVB_CM(7, 1, 256); }
-    if (C2 <= 512) { if (K == 15) RVB_CM(15, 1, 512); if (K == 31) RVB_CM(31, 1, 512); RVB_CM(7, 1, 512); }
-    if (C2 <= 1024) { if (K == 15) RVB_CM(15, 2, 512); if (K == 31) RVB_CM(31, 2, 512); RVB_CM(7, 2, 512); }
-  }
-#undef RVB_CM
-  const size_t smem = (size_t)(CM_TT + K - 1) * C * sizeof(bf16) + (size_t)CM_TT * C * sizeof(float);
-  RVB_REQUIRE(smem <= 200 * 1024, "conv_mid: C=%d K=%d needs %zu B of shared memory", C, K, smem);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    RVB_CHECK_CUDA(cudaFuncSetAttribute(conv_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
-  dim3 grid((T + CM_TT - 1) / CM_TT, B);
-  conv_mid_kernel<<<grid, 256, smem, stream>>>(x, pw1_bias, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_layer_norm, eps,
-                                               out, T, C, K, causal);
-  RVB_COUNT_LAUNCH();
-  RVB_CHECK_LAUNCH();
   return 0;
 }
 

@@ -86,6 +86,13 @@ static inline uint16_t f2bf(float f) {
   return (uint16_t)(u >> 16);
 }
 
+static inline float bf2f(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
 struct Linear {  // bf16 weight (N, K) + fp32 bias (N) on device
   bf16* w = nullptr;
   float* b = nullptr;
@@ -98,7 +105,8 @@ struct Norm {
 
 struct EncLayer {
   Norm norm_ffm, norm_mha, norm_conv, norm_ff, norm_final;
-  Linear ffm1, ffm2, ff1, ff2, qkv, out, pw1, pw2;
+  Linear ffm1, ffm2, ff1, ff2, qkv, out, pw1, pw2;  // pw1 rows interleaved for the GLU epilogue (load_linear_glu)
+  float* pad_glu = nullptr;                          // (d) GLU(pointwise_conv1 bias): value of the causal pad frames
   float* pos_u = nullptr;
   float* pos_v = nullptr;
   float* dw_w = nullptr;  // (d, K)
@@ -226,6 +234,30 @@ static int load_linear(rvb_model* m, const std::string& prefix, int N, int K, Li
       if (upload_f32(m, b->data(), N, &out->b)) return -1;
     }
   }
+  return 0;
+}
+
+// pointwise_conv1 (2C x C) for the fused GLU epilogue (ACT_GLU, kernels.h): weight / bias rows interleaved in groups of
+// 32 — [64j, 64j+32) = value rows of channels [32j, 32j+32), [64j+32, 64j+64) = their gate rows (C + 32j ...).
+// pad_glu[c] = bf16(bias_a[c] * sigmoid(bias_g[c])): what a zero input frame becomes after pointwise_conv1 + GLU.
+static int load_linear_glu(rvb_model* m, const std::string& prefix, int C, int K, Linear* out, float** pad_glu) {
+  const std::vector<float>*w, *b;
+  RVB_REQUIRE(C % 32 == 0, "model: conv module channels (%d) must be a multiple of 32", C);
+  if (need(m, prefix + ".weight", (size_t)2 * C * K, &w) || need(m, prefix + ".bias", (size_t)2 * C, &b)) return -1;
+  std::vector<float> pw((size_t)2 * C * K), pb((size_t)2 * C), pad(C);
+  for (int c = 0; c < C; ++c) {
+    const int ra = 64 * (c / 32) + (c % 32), rg = ra + 32;
+    memcpy(&pw[(size_t)ra * K], &(*w)[(size_t)c * K], (size_t)K * sizeof(float));
+    memcpy(&pw[(size_t)rg * K], &(*w)[(size_t)(C + c) * K], (size_t)K * sizeof(float));
+    pb[ra] = (*b)[c];
+    pb[rg] = (*b)[C + c];
+    pad[c] = bf2f(f2bf((*b)[c] / (1.f + expf(-(*b)[C + c]))));
+  }
+  if (upload_bf16(m, pw.data(), pw.size(), &out->w) || upload_f32(m, pb.data(), pb.size(), &out->b) ||
+      upload_f32(m, pad.data(), pad.size(), pad_glu))
+    return -1;
+  out->N = 2 * C;
+  out->K = K;
   return 0;
 }
 
@@ -371,7 +403,7 @@ static int finalize_model(rvb_model* m) {
     posw.insert(posw.end(), t->begin(), t->end());
     if (need(m, p + ".self_attn.pos_bias_u", d, &t) || upload_f32(m, t->data(), d, &E.pos_u)) return -1;
     if (need(m, p + ".self_attn.pos_bias_v", d, &t) || upload_f32(m, t->data(), d, &E.pos_v)) return -1;
-    if (load_linear(m, p + ".conv_module.pointwise_conv1", 2 * d, d, &E.pw1) ||
+    if (load_linear_glu(m, p + ".conv_module.pointwise_conv1", d, d, &E.pw1, &E.pad_glu) ||
         load_linear(m, p + ".conv_module.pointwise_conv2", d, d, &E.pw2))
       return -1;
     if (need(m, p + ".conv_module.depthwise_conv.weight", (size_t)d * K, &t) ||
@@ -487,7 +519,7 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
   if (m->ws_c1.ensure((size_t)B * 2 * T1h * F1 * d * 2) || m->ws_c2.ensure((size_t)M * F2 * d * 2) ||
       m->ws_x.ensure((size_t)M * d * 4) || m->ws_n.ensure((size_t)M * d * 2) ||
       m->ws_h.ensure((size_t)M * c.ffn_dim * 2) || m->ws_qkv.ensure((size_t)M * 3 * d * 2) ||
-      m->ws_att.ensure((size_t)M * d * 2) || m->ws_pw.ensure((size_t)M * 2 * d * 2) ||
+      m->ws_att.ensure((size_t)M * d * 2) || m->ws_pw.ensure((size_t)M * d * 2) ||
       m->ws_cm.ensure((size_t)M * d * 2) || m->ws_y.ensure((size_t)M * d * 4) || m->ws_ybf.ensure((size_t)M * d * 2) ||
       m->ws_pall.ensure((size_t)Tp * L * d * 2) || m->ws_kpp.ensure((size_t)M * d * 2) ||
       m->ws_cbias.ensure(((size_t)B * H * Tp + (size_t)M * 2) * 4))
@@ -604,8 +636,8 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
     // convolution module                                                       (encoder_layer.py:222-231)
     if (launch_layernorm(x, E.norm_conv.g, E.norm_conv.b, 1e-5f, (int)M, d, n, nullptr, d_lens, Tp, 1, stream))
       return -1;
-    if (gemm(n, E.pw1, (int)M, ACT_NONE, OUT_BF16, pw, 1.f, stream)) return -1;
-    if (launch_conv_mid(pw, E.pw1.b, E.dw_w, E.dw_b, E.cnorm.g, E.cnorm.b, E.bn_mean, E.bn_var, c.cnn_layer_norm, 1e-5f, cm, B,
+    if (gemm(n, E.pw1, (int)M, ACT_GLU, OUT_BF16, pw, 1.f, stream)) return -1;   // pw = GLU(pointwise_conv1), (M, d)
+    if (launch_conv_mid(pw, E.pad_glu, E.dw_w, E.dw_b, E.cnorm.g, E.cnorm.b, E.bn_mean, E.bn_var, c.cnn_layer_norm, 1e-5f, cm, B,
                         Tp, d, c.cnn_kernel, c.causal, stream, y /*fp32 (M, d) scratch, free until the LSL mix*/,
                         m->ws_cbias.as<float>() + (size_t)B * H * Tp))
       return -1;

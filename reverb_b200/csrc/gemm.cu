@@ -89,9 +89,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // Epilogue variants (compile-time): the hot combinations get straight-line code, everything else goes through the
 // generic runtime path.  EPI_GENERIC reads act / out_mode from the kernel parameters.
-enum Epi { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_BF16_SILU = 2, EPI_F32 = 3, EPI_RESID = 4, EPI_GENERIC = 5 };
+enum Epi { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_BF16_SILU = 2, EPI_F32 = 3, EPI_RESID = 4, EPI_GENERIC = 5, EPI_GLU = 6 };
 
 __host__ __device__ inline int select_epi(int act, int out_mode) {
+  if (act == ACT_GLU) return EPI_GLU;
   if (out_mode == OUT_BF16) return act == ACT_NONE ? EPI_BF16 : act == ACT_RELU ? EPI_BF16_RELU : EPI_BF16_SILU;
   if (act == ACT_NONE) return out_mode == OUT_F32 ? EPI_F32 : EPI_RESID;
   return EPI_GENERIC;
@@ -187,6 +188,36 @@ __device__ __forceinline__ void store_chunk(const GemmKParams& p, long long out_
   }
 }
 
+// ACT_GLU: one thread turns 32 "value" + 32 "gate" accumulator columns [n0, n0+64) of one row (interleaved weight
+// rows, see kernels.h) into 32 bf16 outputs at column n0 / 2.  N %% 64 == 0 and 16-byte aligned rows are checked at launch.
+__device__ __forceinline__ void store_glu(const GemmKParams& p, long long out_row, int n0, const uint32_t* av,
+                                          const uint32_t* gv) {
+  bf16* o = reinterpret_cast<bf16*>(p.out) + out_row * p.ldo + (n0 >> 1);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+      if (p.bias != nullptr) {
+        ba = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * j + h);
+        bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + 2 * j + h);
+      }
+      const int e = 8 * j + 4 * h;
+      v[4 * h + 0] = __fdividef(__uint_as_float(av[e + 0]) + ba.x, 1.f + __expf(-(__uint_as_float(gv[e + 0]) + bg.x)));
+      v[4 * h + 1] = __fdividef(__uint_as_float(av[e + 1]) + ba.y, 1.f + __expf(-(__uint_as_float(gv[e + 1]) + bg.y)));
+      v[4 * h + 2] = __fdividef(__uint_as_float(av[e + 2]) + ba.z, 1.f + __expf(-(__uint_as_float(gv[e + 2]) + bg.z)));
+      v[4 * h + 3] = __fdividef(__uint_as_float(av[e + 3]) + ba.w, 1.f + __expf(-(__uint_as_float(gv[e + 3]) + bg.w)));
+    }
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]);
+    u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]);
+    u.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(o)[j] = u;
+  }
+}
+
 // Maps (tile, row-in-tile) to the output row; returns -1 when the row must not be written.
 __device__ __forceinline__ long long output_row(const GemmKParams& p, const TileCoord& t, int r) {
   if (p.conv_mode) {
@@ -218,7 +249,19 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
                                            int c0, int c1, uint64_t* tfull_bar, uint32_t aphase, float* stage) {
   const long long orow = output_row(p, t, q * 32 + lane);
   const int n0_tile = t.n0;
-  if ((EPI == EPI_RESID || EPI == EPI_F32) && p.f32_coalesced) {
+  if constexpr (EPI == EPI_GLU) {
+    mbar_wait(tfull_bar, aphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c0; c < c1; c += 64) {
+      if (n0_tile + c >= p.N) break;
+      uint32_t av[32], gv[32];
+      tmem_ld_32x32(taddr + c, av);
+      tmem_ld_32x32(taddr + c + 32, gv);
+      tmem_ld_wait();
+      if (orow >= 0) store_glu(p, orow, n0_tile + c, av, gv);
+    }
+  } else if ((EPI == EPI_RESID || EPI == EPI_F32) && p.f32_coalesced) {
     const int slot = lane & 7, rsub = lane >> 3;
     long long ro[8];  // element offset of (row it*4+rsub, column n0_tile + slot*4), or -1
 #pragma unroll
@@ -636,19 +679,22 @@ __device__ __forceinline__ float load_a_elem(const GemmKParams& p, const TileCoo
 }
 
 __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmKParams p) {
-  // tile: 128 rows x 32 cols; thread (ty 0..31 , tx 0..7) -> 4 rows x 4 cols ... kept simple: 128x32 outputs,
-  // 256 threads, each thread: 16 outputs (4 rows x 4 cols)
+  // tile: 128 rows x 32 cols, 256 threads, each thread 4 rows x 4 cols.  ACT_GLU: tiles run over the N/2 OUTPUT
+  // columns; output column oc pairs weight rows 2*(oc & ~31) + (oc & 31) (value) and that + 32 (gate).
   __shared__ float sA[128][17];
   __shared__ float sW[32][17];
+  __shared__ float sG[32][17];
+  const bool glu = (p.act == ACT_GLU);
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     // here tiles_n counts 32-wide column tiles
     TileCoord t = decode_tile(p, tile, 32);
     const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
-    float acc[4][4];
+    const int wrow0 = glu ? 2 * t.n0 : t.n0;
+    float acc[4][4], accg[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[i][j] = accg[i][j] = 0.f;
     for (int k0 = 0; k0 < p.K; k0 += 16) {
       for (int e = threadIdx.x; e < 128 * 16; e += 256) {
         int r = e >> 4, kk = e & 15;
@@ -656,21 +702,28 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmKParams p) {
       }
       for (int e = threadIdx.x; e < 32 * 16; e += 256) {
         int n = e >> 4, kk = e & 15;
-        int gn = t.n0 + n, gk = k0 + kk;
+        int gn = wrow0 + n, gk = k0 + kk;
         sW[n][kk] = (gn < p.N && gk < p.K) ? __bfloat162float(p.W[(long long)gn * p.ldw + gk]) : 0.f;
+        sG[n][kk] = (glu && gn + 32 < p.N && gk < p.K) ? __bfloat162float(p.W[(long long)(gn + 32) * p.ldw + gk]) : 0.f;
       }
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < 16; ++kk) {
-        float a[4], w[4];
+        float a[4], w[4], g[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) a[i] = sA[ty * 4 + i][kk];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) w[j] = sW[tx * 4 + j][kk];
+        for (int j = 0; j < 4; ++j) {
+          w[j] = sW[tx * 4 + j][kk];
+          g[j] = sG[tx * 4 + j][kk];
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) {
+            acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+            accg[i][j] = fmaf(a[i], g[j], accg[i][j]);
+          }
       }
       __syncthreads();
     }
@@ -679,6 +732,17 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmKParams p) {
       if (orow < 0) continue;
       for (int j = 0; j < 4; ++j) {
         int n = t.n0 + tx * 4 + j;
+        if (glu) {
+          if (2 * n >= p.N) continue;
+          const int wr = wrow0 + tx * 4 + j;
+          float va = acc[i][j], vg = accg[i][j];
+          if (p.bias) {
+            va += p.bias[wr];
+            vg += p.bias[wr + 32];
+          }
+          reinterpret_cast<bf16*>(p.out)[orow * p.ldo + n] = __float2bfloat16(va / (1.f + expf(-vg)));
+          continue;
+        }
         if (n >= p.N) continue;
         float x = acc[i][j];
         if (p.bias) x += p.bias[n];
@@ -790,6 +854,7 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     case EPI_BF16_SILU: kern = gemm_tc_kernel<BN, EPI_BF16_SILU>; break;
     case EPI_F32: kern = gemm_tc_kernel<BN, EPI_F32>; break;
     case EPI_RESID: kern = gemm_tc_kernel<BN, EPI_RESID>; break;
+    case EPI_GLU: kern = gemm_tc_kernel<BN, EPI_GLU>; break;
     default: kern = gemm_tc_kernel<BN, EPI_GENERIC>; break;
   }
   RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -848,6 +913,7 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     case EPI_BF16_SILU: kern = gemm_tc2_kernel<BN, EPI_BF16_SILU>; break;
     case EPI_F32: kern = gemm_tc2_kernel<BN, EPI_F32>; break;
     case EPI_RESID: kern = gemm_tc2_kernel<BN, EPI_RESID>; break;
+    case EPI_GLU: kern = gemm_tc2_kernel<BN, EPI_GLU>; break;
     default: kern = gemm_tc2_kernel<BN, EPI_GENERIC>; break;
   }
   RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -895,7 +961,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.act = a.act;
   p.out_mode = a.out_mode;
   p.out = a.out;
-  p.ldo = a.ldo ? a.ldo : a.N;
+  p.ldo = a.ldo ? a.ldo : (a.act == ACT_GLU ? a.N / 2 : a.N);
   p.alpha = a.alpha;
   p.row_lens = a.row_lens;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
@@ -918,8 +984,14 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     p.conv_F1 = a.conv_F1;
     p.conv_C = a.conv_C;
   }
+  if (a.act == ACT_GLU) {
+    RVB_REQUIRE(a.out_mode == OUT_BF16 && a.N % 64 == 0 && !a.conv_mode, "gemm: ACT_GLU needs bf16 output and N %% 64 == 0");
+    RVB_REQUIRE((reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && p.ldo % 8 == 0 &&
+                    (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0),
+                "gemm: ACT_GLU needs 16-byte aligned output rows and bias");
+  }
   if (get_gemm_impl() == 1) {
-    p.tiles_n = (a.N + 31) / 32;
+    p.tiles_n = ((a.act == ACT_GLU ? a.N / 2 : a.N) + 31) / 32;
     int tiles_m = a.conv_mode ? a.conv_B * a.conv_F2 * p.conv_tt : (a.M + 127) / 128;
     p.num_tiles = tiles_m * p.tiles_n;
     int grid = p.num_tiles < 148 * 8 ? p.num_tiles : 148 * 8;

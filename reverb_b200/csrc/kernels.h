@@ -6,7 +6,10 @@
 namespace rvb {
 
 // ------------------------------------------------------------------ GEMM (gemm.cu)
-enum GemmAct { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
+// ACT_GLU (bf16 output only): the N = 2C weight rows are interleaved in groups of 32 — rows [64j, 64j+32) are the
+// "value" half of output channels [32j, 32j+32), rows [64j+32, 64j+64) their gates — and the kernel writes
+// out[m, 32j + i] = (acc_a + bias_a) * sigmoid(acc_g + bias_g), an (M, C) matrix (default ldo = N / 2).
+enum GemmAct { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GLU = 3 };
 enum GemmOut {
   OUT_BF16 = 0,      // out_bf16[m, n] = act(acc + bias)
   OUT_F32 = 1,       // out_f32[m, n]  = act(acc + bias)
@@ -68,12 +71,13 @@ int launch_double_layernorm(const float* x, const float* ga, const float* ba, co
 int launch_conv1(const float* feats, const float* mean, const float* istd, const float* w /*[C][9]*/,
                  const float* bias, bf16* out, int B, int T, int F, int C, int T1, int T1h, int F1,
                  cudaStream_t stream);
-// GLU + depthwise conv (K taps) + LayerNorm|BatchNorm(eval) + SiLU on (B, T, 2C) bf16 -> (B, T, C) bf16
-// pw1_bias (2C, fp32): bias of pointwise_conv1 — in causal mode the K-1 left pad frames are GLU(bias), not zeros
-int launch_conv_mid(const bf16* x, const float* pw1_bias, const float* dw_w /*[C][K]*/, const float* dw_b, const float* norm_w,
-                    const float* norm_b, const float* bn_mean, const float* bn_var, int use_layer_norm, float eps,
-                    bf16* out, int B, int T, int C, int K, int causal, cudaStream_t stream,
-                    float* conv_tmp = nullptr /*(B*T, C) fp32 scratch*/, float* stats = nullptr /*(B*T, 2)*/);
+// depthwise conv (K taps) + LayerNorm|BatchNorm(eval) + SiLU on the GLU'd pointwise_conv1 output (B, T, C) bf16
+// (GEMM epilogue ACT_GLU) -> (B, T, C) bf16.  pad_glu (C, fp32): value of the K-1 causal left pad frames =
+// GLU(pointwise_conv1 bias), not zeros.  conv_tmp (B*T, C) fp32 and stats (B*T, 2) scratch are needed with LayerNorm.
+int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w /*[C][K]*/, const float* dw_b,
+                    const float* norm_w, const float* norm_b, const float* bn_mean, const float* bn_var,
+                    int use_layer_norm, float eps, bf16* out, int B, int T, int C, int K, int causal,
+                    cudaStream_t stream, float* conv_tmp = nullptr, float* stats = nullptr);
 // x[m, :] = x[m, :] * scale   (fp32 -> fp32 in place) and optional bf16 copy
 int launch_scale_cast(const float* x, float scale, float* out_f32, bf16* out_bf16, long long n, cudaStream_t stream);
 int launch_f32_to_bf16(const float* x, bf16* out, long long n, cudaStream_t stream);

@@ -99,6 +99,30 @@ def test_gemm_bias_act_modes(lib, impl, M, N, K):
         lib.rvb_set_gemm_impl(-1)       # back to the default (env RVB_GEMM or the 2-CTA kernel)
 
 
+@pytest.mark.parametrize("impl", [1, 0, 2], ids=["simt", "tcgen05", "tcgen05_2cta"])
+@pytest.mark.parametrize("M,C,K", [(300, 64, 128), (1000, 256, 256), (4133, 1024, 1024)])
+def test_gemm_glu_epilogue(lib, impl, M, C, K):
+    """ACT_GLU: pointwise_conv1 + GLU in one GEMM (weight rows interleaved in groups of 32, include/rvb_b200.h)."""
+    torch.manual_seed(M + C)
+    lib.rvb_set_gemm_impl(impl)
+    try:
+        A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+        W = (torch.randn(2 * C, K, device="cuda") / math.sqrt(K)).bfloat16()
+        bias = torch.randn(2 * C, device="cuda")
+        ref = torch.nn.functional.glu(A.float() @ W.float().t() + bias, dim=1)
+        c = torch.arange(C, device="cuda")
+        ra = 64 * (c // 32) + (c % 32)
+        Wp = torch.empty_like(W)
+        bp = torch.empty_like(bias)
+        Wp[ra], Wp[ra + 32] = W[:C], W[C:]
+        bp[ra], bp[ra + 32] = bias[:C], bias[C:]
+        out = torch.zeros(M, C, device="cuda", dtype=torch.bfloat16)
+        _check(lib, lib.rvb_gemm_bf16(_p(A), _p(Wp), _p(bp), M, 2 * C, K, 3, 0, 1.0, _p(out), C, _stream()))
+        torch.testing.assert_close(out.float(), ref, rtol=2e-2, atol=2e-2)
+    finally:
+        lib.rvb_set_gemm_impl(-1)
+
+
 @pytest.mark.parametrize("dk,H", [(64, 2), (32, 4), (128, 1)])
 @pytest.mark.parametrize("pos", [True, False])
 def test_attention(lib, dk, H, pos):
