@@ -160,12 +160,13 @@ constexpr int PB_MAXSLOTS = PB_MAXBEAM + PB_MAXBEAM * PB_MAXBEAM;
 #define PB_NEG_INF (-INFINITY)
 
 __device__ __forceinline__ double log_add2(double a, double b) {
-  // utils/common.py:355-363 for two arguments
+  // utils/common.py:355-363 for two arguments: a_max + log(exp(a - a_max) + exp(b - a_max)).  One of the two
+  // exponentials is exp(0) == 1 exactly and IEEE addition commutes, so a single exp() gives the same double.
   if (a == PB_NEG_INF) return b;
   if (b == PB_NEG_INF) return a;
-  double mx = a > b ? a : b;
-  double sum = exp(a - mx) + exp(b - mx);
-  return mx + log(sum);
+  const double mx = a > b ? a : b;
+  const double mn = a > b ? b : a;
+  return mx + log(1.0 + exp(mn - mx));
 }
 
 struct PBLayout {
@@ -195,23 +196,33 @@ struct PBSlot {
 };
 
 constexpr int PB_THREADS = 128;
+constexpr int PB_EXT_THREADS = PB_THREADS - 32;  // warps 0..2: extension candidates; last warp: stay slots
 constexpr int PB_KEY_NONE = 0x7fffffff;
 
-// One CTA (4 warps) per utterance.  Per frame:
-//   P0  stage the frame's top-k, derive score()/viterbi_score()/times() of every beam prefix
-//   P1  "stay" slots (prefix unchanged): at most three updates land on prefix j — blank, repeat of its last token,
-//       and the one extension parent(j)+last(j) that equals j — replayed in the reference's iteration order;
-//       extension slots: one thread per (token, prefix) pair, final at once unless it collides with a stay slot
-//   P2  score() of every touched slot          P3  rank (score desc, dict insertion order asc), keep top `beam`,
-//       materialise survivors: canonical trie node (find-or-create in a shared-memory hash), times list nodes
-// Prefix identity = canonical trie node id, so dict-merge semantics of the reference hold exactly.
+// The beam entering a frame: score()/viterbi_score()/times() of every prefix are derived when the entry is created.
+struct PBBeam {
+  double s[PB_MAXBEAM], ns[PB_MAXBEAM], vs[PB_MAXBEAM], vns[PB_MAXBEAM], score[PB_MAXBEAM], vit[PB_MAXBEAM];
+  int node[PB_MAXBEAM], ts[PB_MAXBEAM], tns[PB_MAXBEAM], tnsp[PB_MAXBEAM], times[PB_MAXBEAM];
+  int last[PB_MAXBEAM], par[PB_MAXBEAM];
+};
+
+// One CTA (4 warps) per utterance, two block barriers per frame:
+//   P1  "stay" slots (prefix unchanged; last warp, a lane PAIR per prefix): at most three updates land on prefix j —
+//       blank (lane 0 of the pair: s, v_s, times_s), repeat of its last token and the one extension
+//       parent(j)+last(j) that equals j (lane 1: ns, v_ns, times_ns, replayed in the reference's iteration order);
+//       extension slots (warps 0..2): one thread per (token, prefix) pair, final at once unless it collides with a
+//       stay slot; every slot's score() is computed on the spot (extension slots have s = -inf: no transcendental)
+//   P3  rank (score desc, dict insertion order asc; branch-free count), keep top `beam`, materialise survivors into
+//       the OTHER beam buffer: canonical trie node (find-or-create in a shared-memory hash), times list nodes
+// The next frame's top-k is prefetched into registers during P1.  Prefix identity = canonical trie node id, so the
+// dict-merge semantics of the reference hold exactly.
 __global__ void __launch_bounds__(PB_THREADS)
 ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict__ topk_idx, int k,
                        const int* __restrict__ lens, int T, int beam, int blank, int* __restrict__ workspace,
                        int trie_in_smem, int max_len, int* __restrict__ out_tokens, int* __restrict__ out_times,
                        int* __restrict__ out_lens, double* __restrict__ out_scores, int* __restrict__ out_nhyp) {
   extern __shared__ int pb_dyn[];
-  const int b = blockIdx.x, tid = threadIdx.x;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const PBLayout L = pb_layout(T, beam);
   int* ws = workspace + (size_t)b * L.per_utt_ints;
   int* trie_parent = trie_in_smem ? pb_dyn : ws;
@@ -223,17 +234,13 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
   __shared__ PBSlot slots[PB_MAXSLOTS];
   __shared__ double slot_score[PB_MAXSLOTS];
   __shared__ int slot_key[PB_MAXSLOTS];
-  __shared__ double c_s[PB_MAXBEAM], c_ns[PB_MAXBEAM], c_vs[PB_MAXBEAM], c_vns[PB_MAXBEAM];
-  __shared__ double c_score[PB_MAXBEAM], c_vit[PB_MAXBEAM];
-  __shared__ int c_node[PB_MAXBEAM], c_ts[PB_MAXBEAM], c_tns[PB_MAXBEAM], c_tnsp[PB_MAXBEAM], c_times[PB_MAXBEAM];
-  __shared__ int c_last[PB_MAXBEAM], c_par[PB_MAXBEAM];
-  __shared__ double n_s[PB_MAXBEAM], n_ns[PB_MAXBEAM], n_vs[PB_MAXBEAM], n_vns[PB_MAXBEAM];
-  __shared__ double n_score[PB_MAXBEAM];
-  __shared__ int n_node[PB_MAXBEAM], n_ts[PB_MAXBEAM], n_tns[PB_MAXBEAM], n_tnsp[PB_MAXBEAM];
-  __shared__ double s_tv[PB_MAXBEAM];
-  __shared__ int s_ti[PB_MAXBEAM];
-  __shared__ int s_pool, s_times;
+  __shared__ PBBeam beams[2];
+  __shared__ double s_tv[2][PB_MAXBEAM];
+  __shared__ int s_ti[2][PB_MAXBEAM];
+  __shared__ int s_pool, s_times, s_nlive[2];
 
+  const int len = min(lens[b], T);
+  const int kk = min(k, beam);
   if (trie_in_smem)
     for (int i = tid; i < L.hash_cap; i += PB_THREADS) hash[i] = -1;
   if (tid == 0) {
@@ -241,189 +248,207 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
     trie_tok[0] = -1;
     s_pool = 1;
     s_times = 0;
-    n_node[0] = 0;
-    n_s[0] = 0.0;
-    n_ns[0] = PB_NEG_INF;
-    n_vs[0] = 0.0;
-    n_vns[0] = 0.0;
-    n_score[0] = 0.0;  // log_add([0, -inf])
-    n_ts[0] = -1;
-    n_tns[0] = -1;
-    n_tnsp[0] = -1;
+    s_nlive[0] = s_nlive[1] = 0;
+    PBBeam& C = beams[0];
+    C.node[0] = 0;
+    C.s[0] = 0.0;
+    C.ns[0] = PB_NEG_INF;
+    C.vs[0] = 0.0;
+    C.vns[0] = 0.0;
+    C.score[0] = 0.0;  // log_add([0, -inf])
+    C.vit[0] = 0.0;    // v_s > v_ns is false -> v_ns
+    C.ts[0] = -1;
+    C.tns[0] = -1;
+    C.tnsp[0] = -1;
+    C.times[0] = -1;
+    C.last[0] = -1;
+    C.par[0] = -1;
+  }
+  if (tid < kk && len > 0) {
+    s_tv[0][tid] = (double)topk_val[((long long)b * T) * k + tid];
+    s_ti[0][tid] = topk_idx[((long long)b * T) * k + tid];
   }
   int nb = 1;
-  const int len = min(lens[b], T);
-  const int kk = min(k, beam);
   __syncthreads();
 
   for (int t = 0; t < len; ++t) {
-    // ---- P0
-    if (tid < kk) {
-      s_tv[tid] = (double)topk_val[((long long)b * T + t) * k + tid];
-      s_ti[tid] = topk_idx[((long long)b * T + t) * k + tid];
+    const int cur = t & 1;
+    const PBBeam& C = beams[cur];
+    PBBeam& N = beams[cur ^ 1];
+    const double* tv = s_tv[cur];
+    const int* ti = s_ti[cur];
+    float pre_v = 0.f;
+    int pre_i = 0;
+    if (tid < kk && t + 1 < len) {
+      pre_v = topk_val[((long long)b * T + t + 1) * k + tid];
+      pre_i = topk_idx[((long long)b * T + t + 1) * k + tid];
     }
-    if (tid < nb) {
-      const int j = tid;
-      const double s = n_s[j], ns = n_ns[j], vs = n_vs[j], vns = n_vns[j];
-      c_s[j] = s;
-      c_ns[j] = ns;
-      c_vs[j] = vs;
-      c_vns[j] = vns;
-      c_ts[j] = n_ts[j];
-      c_tns[j] = n_tns[j];
-      c_tnsp[j] = n_tnsp[j];
-      const int node = n_node[j];
-      c_node[j] = node;
-      c_score[j] = n_score[j];  // == log_add([s, ns]); already computed when slot j was ranked
-      const bool sb = vs > vns;
-      c_vit[j] = sb ? vs : vns;
-      c_times[j] = sb ? n_ts[j] : n_tns[j];
-      c_last[j] = trie_tok[node];
-      c_par[j] = trie_parent[node];
-      PBSlot& sl = slots[j];
-      sl.s = sl.ns = sl.vs = sl.vns = sl.ctp = PB_NEG_INF;
-      sl.times_s = -1;
-      sl.tns_src = -1;
-      sl.tns_op = 0;
-      sl.src = j;
-      sl.tok = -1;
-      slot_key[j] = PB_KEY_NONE;
-    }
-    __syncthreads();
     const int ncand = kk * nb;
     const int nslots = nb + ncand;
-    // ---- P1a: stay slots
-    if (tid < nb) {
-      const int j = tid;
-      PBSlot& n = slots[j];
-      const int last_j = c_last[j];
-      const bool nonempty = c_node[j] != 0;
-      int ui_blank = -1, ui_last = -1, ip = -1;
-      for (int u = 0; u < kk; ++u) {
-        if (s_ti[u] == blank) ui_blank = u;
-        if (nonempty && s_ti[u] == last_j) ui_last = u;
-      }
-      if (nonempty && ui_last >= 0)
-        for (int i = 0; i < nb; ++i)
-          if (c_node[i] == c_par[j]) ip = i;
-      // events sorted by candidate index c = ui * nb + i
-      int ev_c[3], ev_type[3], ne = 0;  // type 0 blank, 1 repeat, 2 collision
-      if (ui_blank >= 0) { ev_c[ne] = ui_blank * nb + j; ev_type[ne++] = 0; }
-      if (ui_last >= 0) { ev_c[ne] = ui_last * nb + j; ev_type[ne++] = 1; }
-      if (ui_last >= 0 && ip >= 0) { ev_c[ne] = ui_last * nb + ip; ev_type[ne++] = 2; }
-      for (int a = 1; a < ne; ++a)
-        for (int q = a; q > 0 && ev_c[q] < ev_c[q - 1]; --q) {
-          int tc = ev_c[q]; ev_c[q] = ev_c[q - 1]; ev_c[q - 1] = tc;
-          int tt = ev_type[q]; ev_type[q] = ev_type[q - 1]; ev_type[q - 1] = tt;
+    int mylive = 0;
+    if (warp == PB_THREADS / 32 - 1) {
+      // ---- P1a: stay slots, lane pair (2j, 2j+1) per prefix j
+      const int j = lane >> 1, h = lane & 1;
+      const bool act = j < nb;
+      double s_new = PB_NEG_INF, vs_new = PB_NEG_INF;
+      int times_s = -1, key = PB_KEY_NONE;
+      double ns_new = PB_NEG_INF, vns_new = PB_NEG_INF, ctp = PB_NEG_INF;
+      int tns_src = -1, tns_op = 0;
+      if (act) {
+        const int last_j = C.last[j];
+        const bool nonempty = C.node[j] != 0;
+        int ui_blank = -1, ui_last = -1, ip = -1;
+        for (int u = 0; u < kk; ++u) {
+          if (ti[u] == blank) ui_blank = u;
+          if (nonempty && ti[u] == last_j) ui_last = u;
         }
-      int key = PB_KEY_NONE;
-      for (int a = 0; a < ne; ++a) {
-        const int ty = ev_type[a];
-        if (ty == 0) {
-          const double p = s_tv[ui_blank];
-          if (key == PB_KEY_NONE) key = 2 * ev_c[a];
-          n.s = log_add2(n.s, c_score[j] + p);
-          n.vs = c_vit[j] + p;
-          n.times_s = c_times[j];
-        } else if (ty == 1) {
-          const double p = s_tv[ui_last];
-          if (key == PB_KEY_NONE) key = 2 * ev_c[a];
-          n.ns = log_add2(n.ns, c_ns[j] + p);
-          if (n.vns < c_vns[j] + p) {
-            // reference typo (`vs_ns`, search.py:178): v_ns is NOT updated here
-            if (n.ctp < p) {
-              n.ctp = p;
-              n.tns_src = c_tnsp[j];  // parent of prefix j's times_ns list: "copy, then overwrite the last element"
-              n.tns_op = 2;
+        if (h == 0) {
+          if (ui_blank >= 0) {  // blank: prefix unchanged, ends in blank
+            const double p = tv[ui_blank];
+            key = 2 * (ui_blank * nb + j);
+            s_new = C.score[j] + p;  // log_add([-inf, x]) == x
+            vs_new = C.vit[j] + p;
+            times_s = C.times[j];
+          }
+        } else if (ui_last >= 0) {
+          const int par_j = C.par[j];
+          for (int i = 0; i < nb; ++i)
+            if (C.node[i] == par_j) ip = i;
+          const double p = tv[ui_last];
+          // candidate order c = ui * nb + i: the repeat (i = j) comes before the collision (i = ip) iff j < ip
+          const int nev = (ip >= 0) ? 2 : 1;
+          for (int a = 0; a < nev; ++a) {
+            const bool repeat_ev = (nev == 1) || ((a == 0) == (j < ip));
+            if (repeat_ev) {
+              if (key == PB_KEY_NONE) key = 2 * (ui_last * nb + j);
+              ns_new = log_add2(ns_new, C.ns[j] + p);
+              if (vns_new < C.vns[j] + p) {
+                // reference typo (`vs_ns`, search.py:178): v_ns is NOT updated here
+                if (ctp < p) {
+                  ctp = p;
+                  tns_src = C.tnsp[j];  // parent of prefix j's times_ns list: "copy, then overwrite the last element"
+                  tns_op = 2;
+                }
+              }
+            } else {
+              if (key == PB_KEY_NONE) key = 2 * (ui_last * nb + ip) + 1;
+              const bool rep = (last_j == C.last[ip]) && (C.node[ip] != 0);
+              const double add = rep ? C.s[ip] : C.score[ip];
+              const double vit = rep ? C.vs[ip] : C.vit[ip];
+              ns_new = log_add2(ns_new, add + p);
+              if (vns_new < vit + p) {
+                vns_new = vit + p;
+                ctp = p;
+                tns_src = rep ? C.ts[ip] : C.times[ip];
+                tns_op = 1;
+              }
             }
           }
+        }
+      }
+      // lane 1 of the pair gathers the blank half and finishes the slot
+      const double s_other = __shfl_xor_sync(0xffffffffu, s_new, 1);
+      const int key_other = __shfl_xor_sync(0xffffffffu, key, 1);
+      if (act) {
+        PBSlot& n = slots[j];
+        if (h == 0) {
+          n.s = s_new;
+          n.vs = vs_new;
+          n.times_s = times_s;
+          n.src = j;
+          n.tok = -1;
         } else {
-          const double p = s_tv[ui_last];
-          if (key == PB_KEY_NONE) key = 2 * ev_c[a] + 1;
-          const bool rep = (last_j == c_last[ip]) && (c_node[ip] != 0);
-          const double add = rep ? c_s[ip] : c_score[ip];
-          const double vit = rep ? c_vs[ip] : c_vit[ip];
-          n.ns = log_add2(n.ns, add + p);
-          if (n.vns < vit + p) {
-            n.vns = vit + p;
-            n.ctp = p;
-            n.tns_src = rep ? c_ts[ip] : c_times[ip];
-            n.tns_op = 1;
-          }
+          const int kmin = key < key_other ? key : key_other;
+          n.ns = ns_new;
+          n.vns = vns_new;
+          n.ctp = ctp;
+          n.tns_src = tns_src;
+          n.tns_op = tns_op;
+          slot_key[j] = kmin;
+          slot_score[j] = (kmin == PB_KEY_NONE) ? PB_NEG_INF : log_add2(s_other, ns_new);
+          mylive = (kmin != PB_KEY_NONE);
         }
       }
-      slot_key[j] = key;
-    }
-    // ---- P1b: extension slots, one thread per (token, prefix) candidate
-    for (int c = tid; c < ncand; c += PB_THREADS) {
-      const int ui = c / nb, i = c - ui * nb;
-      const int u = s_ti[ui];
-      const double p = s_tv[ui];
-      int key = PB_KEY_NONE;
-      if (u != blank) {
-        const int node_i = c_node[i];
-        bool collide = false;
-        for (int j = 0; j < nb; ++j) collide |= (c_par[j] == node_i && c_last[j] == u && c_node[j] != 0);
-        if (!collide) {
-          PBSlot& e = slots[nb + c];
-          const bool rep = (u == c_last[i]) && (node_i != 0);
-          // a single contribution into a fresh PrefixScore (s = ns = v_s = v_ns = -inf): log_add([-inf, x]) == x
-          const double add = rep ? c_s[i] : c_score[i];
-          const double vit = rep ? c_vs[i] : c_vit[i];
-          e.s = PB_NEG_INF;
-          e.ns = add + p;
-          e.vs = PB_NEG_INF;
-          e.vns = PB_NEG_INF;
-          e.ctp = PB_NEG_INF;
-          e.times_s = -1;
-          e.tns_src = -1;
-          e.tns_op = 0;
-          if (PB_NEG_INF < vit + p) {
-            e.vns = vit + p;
-            e.ctp = p;
-            e.tns_src = rep ? c_ts[i] : c_times[i];
-            e.tns_op = 1;
+    } else {
+      // ---- P1b: extension slots, one thread per (token, prefix) candidate
+      for (int c = tid; c < ncand; c += PB_EXT_THREADS) {
+        const int ui = c / nb, i = c - ui * nb;
+        const int u = ti[ui];
+        const double p = tv[ui];
+        int key = PB_KEY_NONE;
+        double sc = PB_NEG_INF;
+        if (u != blank) {
+          const int node_i = C.node[i];
+          bool collide = false;
+          for (int j = 0; j < nb; ++j) collide |= (C.par[j] == node_i && C.last[j] == u && C.node[j] != 0);
+          if (!collide) {
+            PBSlot& e = slots[nb + c];
+            const bool rep = (u == C.last[i]) && (node_i != 0);
+            // a single contribution into a fresh PrefixScore (s = ns = v_s = v_ns = -inf): log_add([-inf, x]) == x
+            const double add = rep ? C.s[i] : C.score[i];
+            const double vit = rep ? C.vs[i] : C.vit[i];
+            e.s = PB_NEG_INF;
+            e.ns = add + p;
+            e.vs = PB_NEG_INF;
+            e.vns = PB_NEG_INF;
+            e.ctp = PB_NEG_INF;
+            e.times_s = -1;
+            e.tns_src = -1;
+            e.tns_op = 0;
+            if (PB_NEG_INF < vit + p) {
+              e.vns = vit + p;
+              e.ctp = p;
+              e.tns_src = rep ? C.ts[i] : C.times[i];
+              e.tns_op = 1;
+            }
+            e.src = i;
+            e.tok = u;
+            key = 2 * c + 1;
+            sc = add + p;  // score() = log_add([-inf, ns]) = ns
+            ++mylive;
           }
-          e.src = i;
-          e.tok = u;
-          key = 2 * c + 1;
         }
+        slot_key[nb + c] = key;
+        slot_score[nb + c] = sc;
       }
-      slot_key[nb + c] = key;
     }
+    mylive = __reduce_add_sync(0xffffffffu, mylive);
+    if (lane == 0 && mylive) atomicAdd(&s_nlive[cur], mylive);
     __syncthreads();
-    // ---- P2: score() of every touched slot (extension slots have s = -inf: no transcendental)
-    for (int a = tid; a < nslots; a += PB_THREADS)
-      slot_score[a] = (slot_key[a] == PB_KEY_NONE) ? PB_NEG_INF : log_add2(slots[a].s, slots[a].ns);
-    __syncthreads();
-    // ---- P3: second beam prune (stable w.r.t. dict insertion order) + materialise the survivors
-    int nlive = 0;
-    for (int o = 0; o < nslots; ++o) nlive += (slot_key[o] != PB_KEY_NONE);
-    const int nnew = min(beam, nlive);
+    // ---- P3: second beam prune (stable w.r.t. dict insertion order) + materialise the survivors into beams[cur^1]
+    const int nnew = min(beam, s_nlive[cur]);
+    if (tid == 0) s_nlive[cur ^ 1] = 0;
+    if (tid < kk && t + 1 < len) {
+      s_tv[cur ^ 1][tid] = (double)pre_v;
+      s_ti[cur ^ 1][tid] = pre_i;
+    }
     for (int a = tid; a < nslots; a += PB_THREADS) {
       const int key = slot_key[a];
       if (key == PB_KEY_NONE) continue;
       const double sc = slot_score[a];
+      // dead slots carry (score -inf, key INT_MAX): they never count, so the loop needs no liveness branch
       int rank = 0;
+#pragma unroll 4
       for (int o = 0; o < nslots; ++o) {
-        const int ko = slot_key[o];
         const double so = slot_score[o];
-        rank += (ko != PB_KEY_NONE) && (so > sc || (so == sc && ko < key));
+        const int ko = slot_key[o];
+        rank += (so > sc) ? 1 : 0;
+        rank += (so == sc && ko < key) ? 1 : 0;
       }
       if (rank >= nnew) continue;
       const PBSlot& s = slots[a];
       int node;
       if (s.tok < 0) {
-        node = c_node[s.src];
+        node = C.node[s.src];
       } else {
-        const int parent = c_node[s.src];
+        const int parent = C.node[s.src];
         unsigned h = ((unsigned)parent * 2654435761u) ^ ((unsigned)s.tok * 40503u + 0x9e3779b9u);
         h &= (unsigned)(L.hash_cap - 1);
         node = -1;
         int fresh = -1;
         while (true) {
-          int cur = atomicAdd(&hash[h], 0);
-          if (cur == -1) {
+          int cur_n = atomicAdd(&hash[h], 0);
+          if (cur_n == -1) {
             if (fresh < 0) {
               fresh = atomicAdd(&s_pool, 1);
               trie_parent[fresh] = parent;
@@ -435,10 +460,10 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
               node = fresh;
               break;
             }
-            cur = old;
+            cur_n = old;
           }
-          if (trie_parent[cur] == parent && trie_tok[cur] == s.tok) {
-            node = cur;
+          if (trie_parent[cur_n] == parent && trie_tok[cur_n] == s.tok) {
+            node = cur_n;
             break;
           }
           h = (h + 1) & (unsigned)(L.hash_cap - 1);
@@ -451,34 +476,40 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
         times_parent[tns] = tnsp;
         times_t[tns] = t;
       }
-      n_node[rank] = node;
-      n_s[rank] = s.s;
-      n_ns[rank] = s.ns;
-      n_vs[rank] = s.vs;
-      n_vns[rank] = s.vns;
-      n_score[rank] = sc;
-      n_ts[rank] = s.times_s;
-      n_tns[rank] = tns;
-      n_tnsp[rank] = tnsp;
+      const bool sb = s.vs > s.vns;
+      N.node[rank] = node;
+      N.s[rank] = s.s;
+      N.ns[rank] = s.ns;
+      N.vs[rank] = s.vs;
+      N.vns[rank] = s.vns;
+      N.score[rank] = sc;
+      N.vit[rank] = sb ? s.vs : s.vns;
+      N.ts[rank] = s.times_s;
+      N.tns[rank] = tns;
+      N.tnsp[rank] = tnsp;
+      N.times[rank] = sb ? s.times_s : tns;
+      N.last[rank] = (s.tok < 0) ? C.last[s.src] : s.tok;
+      N.par[rank] = (s.tok < 0) ? C.par[s.src] : C.node[s.src];
     }
     nb = nnew;
     __syncthreads();
   }
 
   // ---- emit the n-best: tokens, score() and times() per surviving prefix, in beam order
+  const PBBeam& F = beams[len & 1];
   if (tid == 0) out_nhyp[b] = nb;
   if (tid < nb) {
     const int r = tid;
     int n = 0;
-    for (int node = n_node[r]; node > 0; node = trie_parent[node]) ++n;
+    for (int node = F.node[r]; node > 0; node = trie_parent[node]) ++n;
     int* tok_out = out_tokens + ((long long)b * beam + r) * max_len;
     int* tim_out = out_times + ((long long)b * beam + r) * max_len;
     int pos = n;
-    for (int node = n_node[r]; node > 0; node = trie_parent[node]) {
+    for (int node = F.node[r]; node > 0; node = trie_parent[node]) {
       --pos;
       if (pos < max_len) tok_out[pos] = trie_tok[node];
     }
-    const int tl = (n_vs[r] > n_vns[r]) ? n_ts[r] : n_tns[r];
+    const int tl = F.times[r];
     int nt = 0;
     for (int q = tl; q >= 0; q = times_parent[q]) ++nt;
     pos = nt;
@@ -488,7 +519,7 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
     }
     out_lens[(b * beam + r) * 2 + 0] = n;
     out_lens[(b * beam + r) * 2 + 1] = nt;
-    out_scores[b * beam + r] = n_score[r];
+    out_scores[b * beam + r] = F.score[r];
   }
 }
 
