@@ -118,6 +118,18 @@ RVB_API int rvb_attention_rescoring(rvb_model* m, const float* d_enc_out, const 
                             const float* h_cat_embs, int n_cat, float reverse_weight, float* h_l2r, float* h_r2l,
                             void* stream);
 
+/* ctc_prefix_beam_search + attention_rescoring in one call, the n-best staying on the device in between
+ * (what ASRModel.decode does for method "attention_rescoring", asr_model.py:259-308 / search.py:124-248,378-444).
+ * Host outputs are written COMPACT with row length L = *out_max_len (the longest hypothesis / times list, >= 1):
+ * h_tokens / h_times (B, beam, L), h_l2r / h_r2l (B, beam, L + 1); the caller provides room for L = cap.
+ * h_lens (B, beam, 2) = {n_tokens, n_times}, h_scores (B, beam) float64 CTC scores, h_nhyp (B).
+ * h_r2l may be NULL (or reverse_weight == 0): the right-to-left decoder is skipped. */
+RVB_API int rvb_beam_search_rescoring(rvb_model* m, const float* d_topk_val, const int* d_topk_idx, int k,
+                                      const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int beam,
+                                      int blank_id, const float* h_cat_embs, int n_cat, float reverse_weight, int cap,
+                                      int* h_tokens, int* h_times, int* h_lens, double* h_scores, int* h_nhyp,
+                                      float* h_l2r, float* h_r2l, int* out_max_len, void* stream);
+
 /* ---- kernel-level entry points (parity tests, profiling) ----------------------------------------------------- */
 /* C[M,N] = A[M,K] W[N,K]^T + bias; act: 0 none 1 relu 2 silu 3 glu; out_mode: 0 bf16, 1 f32, 2 f32 residual += alpha*(.)
  * act 3 (pointwise_conv1 + GLU of the conformer conv module, convolution.py:129-130): bf16 output (M, N/2); W / bias

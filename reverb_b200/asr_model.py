@@ -83,8 +83,14 @@ class ASRModel:
         if "ctc_greedy_search" in methods:
             results["ctc_greedy_search"] = greedy_results(self.engine.greedy_search(topk_idx, encoder_lens, blank_id))
         if need_beam:
-            raw = self.engine.prefix_beam_search_raw(topk_val, topk_idx, encoder_lens, beam_size, blank_id)
-            toks, tims, olen, scores, nhyp = raw
+            l2r = r2l = None
+            if "attention_rescoring" in methods:
+                # fused native path: the n-best stays on the device between the search and the decoder
+                toks, tims, olen, scores, nhyp, l2r, r2l = self.engine.beam_search_rescoring(
+                    topk_val, topk_idx, encoder_out, encoder_lens, beam_size, blank_id, cat_embs, reverse_weight)
+            else:
+                toks, tims, olen, scores, nhyp = self.engine.prefix_beam_search_raw(topk_val, topk_idx, encoder_lens,
+                                                                                    beam_size, blank_id)
             if "ctc_prefix_beam_search" in methods:
                 per_utt = []
                 for b in range(toks.shape[0]):
@@ -94,10 +100,6 @@ class ASRModel:
                                     [tims[b, r, :olen[b, r, 1]].tolist() for r in range(n)]))
                 results["ctc_prefix_beam_search"] = prefix_beam_results(per_utt)
             if "attention_rescoring" in methods:
-                # straight from the n-best arrays: no per-hypothesis Python objects on this path
-                hlen = np.where(np.arange(toks.shape[1])[None, :] < nhyp[:, None], olen[:, :, 0], -1)
-                l2r, r2l = self.engine.rescoring_scores_raw(encoder_out, encoder_lens, toks, hlen, cat_embs,
-                                                            reverse_weight)
                 results["attention_rescoring"] = rescoring_pick_batch(toks, tims, olen, scores, nhyp, l2r, r2l,
                                                                       ctc_weight, reverse_weight)
         return results

@@ -347,13 +347,65 @@ relpos_prep_kernel(const bf16* __restrict__ k, long long ldk, const bf16* __rest
   }
 }
 
+// Same, vectorised: a lane owns 8 consecutive columns (16-byte loads / stores), a head is dk/8 adjacent lanes, so one
+// warp pass covers 256 columns and the per-head dot products reduce with log2(dk/8) shuffles.
+template <int LPH /* lanes per head = dk / 8 */>
+__global__ void __launch_bounds__(256)
+relpos_prep_vec_kernel(const bf16* __restrict__ k, long long ldk, const bf16* __restrict__ pos, long long ldp,
+                       const float* __restrict__ bias_u, const float* __restrict__ bias_v, bf16* __restrict__ kpp,
+                       float* __restrict__ cbias, int B, int T, int H) {
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= (long long)B * T) return;
+  const int b = (int)(row / T), t = (int)(row - (long long)b * T);
+  const int d = H * LPH * 8;
+  const bf16* kr = k + row * ldk;
+  const bf16* pr = pos + (long long)t * ldp;
+  bf16* orow = kpp + row * d;
+  for (int c0 = 0; c0 < d; c0 += 256) {
+    const int col = c0 + lane * 8;
+    float acc = 0.f;
+    if (col < d) {
+      const uint4 kv = *reinterpret_cast<const uint4*>(kr + col);
+      const uint4 pv = *reinterpret_cast<const uint4*>(pr + col);
+      const float4 u0 = __ldg(reinterpret_cast<const float4*>(bias_u + col));
+      const float4 u1 = __ldg(reinterpret_cast<const float4*>(bias_u + col) + 1);
+      const float4 v0 = __ldg(reinterpret_cast<const float4*>(bias_v + col));
+      const float4 v1 = __ldg(reinterpret_cast<const float4*>(bias_v + col) + 1);
+      const float2 k0 = unpack_bf16x2(kv.x), k1 = unpack_bf16x2(kv.y), k2 = unpack_bf16x2(kv.z), k3 = unpack_bf16x2(kv.w);
+      const float2 p0 = unpack_bf16x2(pv.x), p1 = unpack_bf16x2(pv.y), p2 = unpack_bf16x2(pv.z), p3 = unpack_bf16x2(pv.w);
+      uint4 o;
+      o.x = pack_bf16x2(k0.x + p0.x, k0.y + p0.y);
+      o.y = pack_bf16x2(k1.x + p1.x, k1.y + p1.y);
+      o.z = pack_bf16x2(k2.x + p2.x, k2.y + p2.y);
+      o.w = pack_bf16x2(k3.x + p3.x, k3.y + p3.y);
+      *reinterpret_cast<uint4*>(orow + col) = o;
+      acc = u0.x * k0.x + u0.y * k0.y + u0.z * k1.x + u0.w * k1.y + u1.x * k2.x + u1.y * k2.y + u1.z * k3.x + u1.w * k3.y +
+            v0.x * p0.x + v0.y * p0.y + v0.z * p1.x + v0.w * p1.y + v1.x * p2.x + v1.y * p2.y + v1.z * p3.x + v1.w * p3.y;
+    }
+#pragma unroll
+    for (int o = LPH / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (col < d && (lane % LPH) == 0) cbias[((long long)b * H + col / (LPH * 8)) * T + t] = acc;
+  }
+}
+
 int launch_relpos_prep(const bf16* k, int ldk, const bf16* pos, int ldp, const float* bias_u, const float* bias_v,
                        bf16* kpp, float* cbias, int B, int T, int H, int dk, cudaStream_t stream) {
   RVB_REQUIRE(dk % 2 == 0, "relpos_prep: d_k must be even");
   const long long rows = (long long)B * T;
   if (rows <= 0) return 0;
-  relpos_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(k, ldk, pos, ldp, bias_u, bias_v, kpp, cbias, B,
-                                                                    T, H, dk);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const bool aligned = (ldk % 8 == 0) && (ldp % 8 == 0) && ((reinterpret_cast<uintptr_t>(k) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(pos) & 15) == 0) && ((reinterpret_cast<uintptr_t>(kpp) & 15) == 0) &&
+                       ((reinterpret_cast<uintptr_t>(bias_u) & 15) == 0) && ((reinterpret_cast<uintptr_t>(bias_v) & 15) == 0);
+  if (aligned && dk == 64)
+    relpos_prep_vec_kernel<8><<<grid, 256, 0, stream>>>(k, ldk, pos, ldp, bias_u, bias_v, kpp, cbias, B, T, H);
+  else if (aligned && dk == 128)
+    relpos_prep_vec_kernel<16><<<grid, 256, 0, stream>>>(k, ldk, pos, ldp, bias_u, bias_v, kpp, cbias, B, T, H);
+  else if (aligned && dk == 32)
+    relpos_prep_vec_kernel<4><<<grid, 256, 0, stream>>>(k, ldk, pos, ldp, bias_u, bias_v, kpp, cbias, B, T, H);
+  else
+    relpos_prep_kernel<<<grid, 256, 0, stream>>>(k, ldk, pos, ldp, bias_u, bias_v, kpp, cbias, B, T, H, dk);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;

@@ -40,7 +40,7 @@ logsoftmax_topk_kernel(const float* __restrict__ logits, long long ld, int V, in
                        int* __restrict__ topk_idx, float* __restrict__ logp_out, int apply_softmax) {
   extern __shared__ float s_row[];  // V floats
   __shared__ float s_red[8];
-  __shared__ ArgMax s_arg[8];
+  __shared__ ArgMax s_arg[2][8];
   __shared__ float s_stat[2];
   const long long row = blockIdx.x;
   const float* x = logits + row * ld;
@@ -79,8 +79,9 @@ logsoftmax_topk_kernel(const float* __restrict__ logits, long long ld, int V, in
   if (logp_out != nullptr) {
     for (int i = threadIdx.x; i < V; i += 256) logp_out[row * V + i] = (s_row[i] - lse_shift) - logsum;
   }
-  // top-k by repeated block arg-max (ties -> lowest index); values reported as log-probs
-  for (int r = 0; r < k; ++r) {
+  // top-k by k rounds of block arg-max over per-thread running maxima (ties -> lowest index): only the thread that
+  // owned the winner rescans its ~V/256 elements, one barrier per round.  Values reported as log-probs.
+  auto local_best = [&]() {
     ArgMax a;
     a.v = -INFINITY;
     a.i = 0x7fffffff;
@@ -90,19 +91,27 @@ logsoftmax_topk_kernel(const float* __restrict__ logits, long long ld, int V, in
       b.i = i;
       a = better(a, b);
     }
-    a = warp_argmax(a);
-    if (lane == 0) s_arg[warp] = a;
+    return a;
+  };
+  ArgMax mine = local_best();
+  for (int r = 0; r < k; ++r) {
+    ArgMax a = warp_argmax(mine);
+    if (lane == 0) s_arg[r & 1][warp] = a;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      ArgMax best = s_arg[0];
-      for (int w = 1; w < 8; ++w) best = better(best, s_arg[w]);
-      if (best.i == 0x7fffffff) best.i = 0;  // fewer than k finite entries
+    ArgMax best = s_arg[r & 1][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) best = better(best, s_arg[r & 1][w]);
+    if (best.i == 0x7fffffff) {  // fewer than k finite entries left: report index 0 like the scan-based version
+      if (threadIdx.x == 0) {
+        topk_val[row * k + r] = (best.v - lse_shift) - logsum;
+        topk_idx[row * k + r] = 0;
+      }
+    } else if ((best.i & 255) == (int)threadIdx.x) {
       topk_val[row * k + r] = (best.v - lse_shift) - logsum;
       topk_idx[row * k + r] = best.i;
       s_row[best.i] = -INFINITY;
-      // NaN-safe marker: a -inf entry can be re-selected only when everything left is -inf
+      mine = local_best();
     }
-    __syncthreads();
   }
 }
 
@@ -588,6 +597,40 @@ int launch_logsoftmax_gather(const float* logits, int ld, int M, int V, const in
                              cudaStream_t stream) {
   if (M <= 0) return 0;
   logsoftmax_gather_kernel<<<M, 256, 0, stream>>>(logits, ld, V, gather_idx, G, out);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Decoder inputs of attention rescoring, built on the device from the n-best the prefix beam search left there:
+// hypothesis s = (b, i) has U tokens w (0 when i >= nhyp[b]);  sos == eos == V-1 (asr_model.py:79-82)
+//   tok_l = [sos, w_1..w_U, eos..]                 tok_r = [sos, w_U..w_1, eos..]          (asr_model.py:921-949)
+//   gat_l = [w_1..w_U, eos, -1..]                  gat_r = [w_U..w_1, eos, -1..]           (search.py:417-430)
+__global__ void rescoring_inputs_kernel(const int* __restrict__ tok, int tok_stride, const int* __restrict__ olen,
+                                        const int* __restrict__ nhyp, int N, int Lp, int sos_eos,
+                                        int* __restrict__ tok_l, int* __restrict__ tok_r, int* __restrict__ gat_l,
+                                        int* __restrict__ gat_r, int* __restrict__ slen) {
+  const int s = blockIdx.x, b = s / N, i = s - b * N;
+  int U = (i < nhyp[b]) ? olen[2 * s] : 0;
+  U = min(U, Lp - 1);
+  const int* wv = tok + (size_t)s * tok_stride;
+  for (int j = threadIdx.x; j < Lp; j += blockDim.x) {
+    const size_t r = (size_t)s * Lp + j;
+    tok_l[r] = (j == 0) ? sos_eos : (j <= U ? wv[j - 1] : sos_eos);
+    tok_r[r] = (j == 0) ? sos_eos : (j <= U ? wv[U - j] : sos_eos);
+    gat_l[r] = (j < U) ? wv[j] : (j == U ? sos_eos : -1);
+    gat_r[r] = (j < U) ? wv[U - 1 - j] : (j == U ? sos_eos : -1);
+  }
+  if (threadIdx.x == 0) slen[s] = U + 1;
+}
+
+int launch_rescoring_inputs(const int* d_tokens, int tok_stride, const int* d_out_lens, const int* d_nhyp, int B, int N,
+                            int Lp, int sos_eos, int* tok_l, int* tok_r, int* gat_l, int* gat_r, int* slen,
+                            cudaStream_t stream) {
+  if (B * N <= 0) return 0;
+  rescoring_inputs_kernel<<<B * N, 128, 0, stream>>>(d_tokens, tok_stride, d_out_lens, d_nhyp, N, Lp, sos_eos, tok_l,
+                                                     tok_r, gat_l, gat_r, slen);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;

@@ -794,14 +794,43 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
   return launch_logsoftmax_gather(logits, ldv, (int)R, V, d_gather, 1, d_scores, stream);
 }
 
+// Decoder passes over device-resident inputs (all int arrays on the device):
+//   tok_l / tok_r (R = S*Lp): decoder inputs [sos, w_1..w_U, eos..] and the reversed variant (asr_model.py:921-949)
+//   gat_l / gat_r (R): per-position gather targets, -1 = none (search.py:417-430);  slen (S) = U + 1;  elen (B)
+// -> d_sc_l / d_sc_r (R) log-probabilities of the targets.
+static int rescoring_device(rvb_model* m, const float* d_enc_out, const int* d_elen, int B, int Tp, int N, int Lp,
+                            const int* tok_l, const int* tok_r, const int* gat_l, const int* gat_r, const int* slen,
+                            bool use_r, float* d_sc_l, float* d_sc_r, cudaStream_t stream) {
+  const int d = m->cfg.d_model;
+  const long long Mem = (long long)B * Tp;
+  if (m->ws_encbf.ensure((size_t)Mem * d * 2)) return -1;
+  bf16* encbf = m->ws_encbf.as<bf16>();
+  if (launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream)) return -1;
+  if (decoder_pass(m, m->dec_l, encbf, d_elen, B, Tp, N, Lp, tok_l, slen, gat_l, d_sc_l, stream)) return -1;
+  if (use_r && decoder_pass(m, m->dec_r, encbf, d_elen, B, Tp, N, Lp, tok_r, slen, gat_r, d_sc_r, stream)) return -1;
+  return 0;
+}
+
+// position pos of the reversed pass scores token w_{U-1-pos}: store it at index j = U-1-pos
+static void unreverse_r2l(const float* src_all, const int* h_len, int len_stride, int S, int Lp, float* h_r2l) {
+  for (int s = 0; s < S; ++s) {
+    const int U = h_len[(size_t)s * len_stride] < 0 ? 0 : h_len[(size_t)s * len_stride];
+    const float* src = src_all + (size_t)s * Lp;
+    float* dst = h_r2l + (size_t)s * Lp;
+    for (int j = 0; j < Lp; ++j) dst[j] = 0.f;
+    for (int j = 0; j < U; ++j) dst[j] = src[U - 1 - j];
+    dst[U] = src[U];
+  }
+}
+
 static int attention_rescoring(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp,
                                const int* h_tok, const int* h_len, int N, int max_len, const float* h_cat, int n_cat,
                                float reverse_weight, float* h_l2r, float* h_r2l, cudaStream_t stream) {
   const rvb_model_config& c = m->cfg;
   RVB_REQUIRE(m->finalized && m->dec_l.present, "attention_rescoring: model has no decoder");
-  const int d = c.d_model, eos = c.vocab - 1, sos = c.vocab - 1;  // asr_model.py:79-82
+  const int eos = c.vocab - 1, sos = c.vocab - 1;  // asr_model.py:79-82
   const int Lp = max_len + 1, S = B * N;
-  const long long R = (long long)S * Lp, Mem = (long long)B * Tp;
+  const long long R = (long long)S * Lp;
   const bool use_r = reverse_weight > 0.f && m->dec_r.present && h_r2l != nullptr;
   if (fold_lang(m, h_cat, n_cat, stream)) return -1;
   // host-side staging: decoder inputs [sos, w_1..w_U, eos..] and per-position gather targets
@@ -833,13 +862,8 @@ static int attention_rescoring(rvb_model* m, const float* d_enc_out, const int* 
   RVB_CHECK_CUDA(cudaMemcpyAsync(dp, hp, ints * sizeof(int), cudaMemcpyHostToDevice, stream));
   float* d_sc_l = reinterpret_cast<float*>(dp + ints);
   float* d_sc_r = d_sc_l + R;
-  if (m->ws_encbf.ensure((size_t)Mem * d * 2)) return -1;
-  bf16* encbf = m->ws_encbf.as<bf16>();
-  if (launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream)) return -1;
-  if (decoder_pass(m, m->dec_l, encbf, dp + 4 * R + S, B, Tp, N, Lp, dp, dp + 4 * R, dp + 2 * R, d_sc_l, stream))
-    return -1;
-  if (use_r &&
-      decoder_pass(m, m->dec_r, encbf, dp + 4 * R + S, B, Tp, N, Lp, dp + R, dp + 4 * R, dp + 3 * R, d_sc_r, stream))
+  if (rescoring_device(m, d_enc_out, dp + 4 * R + S, B, Tp, N, Lp, dp, dp + R, dp + 2 * R, dp + 3 * R, dp + 4 * R, use_r,
+                       d_sc_l, d_sc_r, stream))
     return -1;
   if (m->pin_c.ensure((size_t)R * 2 * sizeof(float))) return -1;
   float* hs = m->pin_c.as<float>();
@@ -847,16 +871,98 @@ static int attention_rescoring(rvb_model* m, const float* d_enc_out, const int* 
                                  stream));
   RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
   memcpy(h_l2r, hs, (size_t)R * sizeof(float));
-  if (use_r) {
-    // position pos of the reversed pass scores token w_{U-1-pos}: store it at index j = U-1-pos
-    for (int s = 0; s < S; ++s) {
-      const int U = h_len[s] < 0 ? 0 : h_len[s];
-      const float* src = hs + R + (size_t)s * Lp;
-      float* dst = h_r2l + (size_t)s * Lp;
-      for (int j = 0; j < Lp; ++j) dst[j] = 0.f;
-      for (int j = 0; j < U; ++j) dst[j] = src[U - 1 - j];
-      dst[U] = src[U];
+  if (use_r) unreverse_r2l(hs + R, h_len, 1, S, Lp, h_r2l);
+  return 0;
+}
+
+// ctc_prefix_beam_search + attention_rescoring with the n-best kept on the device in between (asr_model.py:259-308 does
+// the same two steps through Python lists).  One small device->host copy (hypothesis lengths) sizes the decoder
+// batch; the decoder inputs are built by a kernel; tokens / times travel to the host while the decoder runs.
+static int beam_search_rescoring(rvb_model* m, const float* d_topk_val, const int* d_topk_idx, int k,
+                                 const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int beam, int blank_id,
+                                 const float* h_cat, int n_cat, float reverse_weight, int cap, int* h_tokens,
+                                 int* h_times, int* h_lens, double* h_scores, int* h_nhyp, float* h_l2r, float* h_r2l,
+                                 int* out_max_len, DevBuf& ws, DevBuf& outb, HostPinned& pin, cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  RVB_REQUIRE(m->finalized && m->dec_l.present, "beam_search_rescoring: model has no decoder");
+  const int N = beam, S = B * N, dev_len = Tp;  // a prefix never has more tokens than frames
+  const size_t ws_bytes = prefix_beam_workspace_bytes(B, Tp, beam);
+  const size_t n_tok = (size_t)S * dev_len;
+  // device: lens(B) | tokens | times | out_lens (S*2) | nhyp (B) | pad | scores (S doubles)
+  const size_t ints = B + 2 * n_tok + (size_t)S * 2 + B;
+  const size_t ints_al = (ints + 1) & ~(size_t)1;
+  const size_t out_bytes = ints_al * sizeof(int) + (size_t)S * sizeof(double);
+  const size_t small_ints = ints_al - (B + 2 * n_tok);            // out_lens | nhyp | pad
+  const size_t small_bytes = small_ints * sizeof(int) + (size_t)S * sizeof(double);
+  if (ws.ensure(ws_bytes) || outb.ensure(out_bytes)) return -1;
+  int* d_lens = outb.as<int>();
+  int* d_tok = d_lens + B;
+  int* d_tim = d_tok + n_tok;
+  int* d_olen = d_tim + n_tok;
+  int* d_nhyp = d_olen + (size_t)S * 2;
+  double* d_sc = reinterpret_cast<double*>(outb.as<int>() + ints_al);
+  if (pin.ensure(small_bytes + sizeof(int) * B)) return -1;
+  int* hp_small = pin.as<int>();                                   // out_lens | nhyp | pad | scores
+  int* hp_elen = reinterpret_cast<int*>(reinterpret_cast<char*>(hp_small) + small_bytes);
+  memcpy(hp_elen, h_enc_lens, sizeof(int) * B);
+  if (fold_lang(m, h_cat, n_cat, stream)) return -1;
+  RVB_CHECK_CUDA(cudaMemcpyAsync(d_lens, hp_elen, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+  if (launch_ctc_prefix_beam(d_topk_val, d_topk_idx, k, d_lens, B, Tp, beam, blank_id, ws.p, ws.cap, dev_len, d_tok,
+                             d_tim, d_olen, d_sc, d_nhyp, stream))
+    return -1;
+  RVB_CHECK_CUDA(cudaMemcpyAsync(hp_small, d_olen, small_bytes, cudaMemcpyDeviceToHost, stream));
+  RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
+  const int* ol = hp_small;
+  const int* nh = hp_small + (size_t)S * 2;
+  int Lmax = 1;
+  for (int b = 0; b < B; ++b)
+    for (int i = 0; i < N; ++i) {
+      const size_t s = (size_t)b * N + i;
+      if (i < nh[b]) {
+        Lmax = ol[2 * s] > Lmax ? ol[2 * s] : Lmax;
+        Lmax = ol[2 * s + 1] > Lmax ? ol[2 * s + 1] : Lmax;
+      }
     }
+  RVB_REQUIRE(Lmax <= cap && Lmax <= dev_len, "beam_search_rescoring: hypothesis of %d tokens exceeds capacity %d", Lmax, cap);
+  *out_max_len = Lmax;
+  const int Lp = Lmax + 1;
+  const long long R = (long long)S * Lp;
+  const bool use_r = reverse_weight > 0.f && m->dec_r.present && h_r2l != nullptr;
+  const size_t rints = (size_t)R * 4 + S;
+  if (m->ws_misc.ensure(rints * sizeof(int) + (size_t)R * 2 * sizeof(float))) return -1;
+  int* dp = m->ws_misc.as<int>();
+  float* d_sc_l = reinterpret_cast<float*>(dp + rints);
+  float* d_sc_r = d_sc_l + R;
+  if (launch_rescoring_inputs(d_tok, dev_len, d_olen, d_nhyp, B, N, Lp, c.vocab - 1, dp, dp + R, dp + 2 * R, dp + 3 * R,
+                              dp + 4 * R, stream))
+    return -1;
+  // n-best tokens / times -> pinned host (compact rows of Lmax), overlapping the decoder on the copy engine
+  const size_t tt_bytes = (size_t)S * Lmax * sizeof(int);
+  if (m->pin_b.ensure(2 * tt_bytes) || m->pin_c.ensure((size_t)R * 2 * sizeof(float))) return -1;
+  RVB_CHECK_CUDA(cudaMemcpy2DAsync(m->pin_b.p, (size_t)Lmax * sizeof(int), d_tok, (size_t)dev_len * sizeof(int),
+                                   (size_t)Lmax * sizeof(int), (size_t)S, cudaMemcpyDeviceToHost, stream));
+  RVB_CHECK_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(m->pin_b.p) + tt_bytes, (size_t)Lmax * sizeof(int), d_tim,
+                                   (size_t)dev_len * sizeof(int), (size_t)Lmax * sizeof(int), (size_t)S,
+                                   cudaMemcpyDeviceToHost, stream));
+  if (rescoring_device(m, d_enc_out, d_lens, B, Tp, N, Lp, dp, dp + R, dp + 2 * R, dp + 3 * R, dp + 4 * R, use_r, d_sc_l,
+                       d_sc_r, stream))
+    return -1;
+  float* hs = m->pin_c.as<float>();
+  RVB_CHECK_CUDA(cudaMemcpyAsync(hs, d_sc_l, (size_t)R * (use_r ? 2 : 1) * sizeof(float), cudaMemcpyDeviceToHost,
+                                 stream));
+  RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
+  memcpy(h_tokens, m->pin_b.p, tt_bytes);
+  memcpy(h_times, reinterpret_cast<char*>(m->pin_b.p) + tt_bytes, tt_bytes);
+  memcpy(h_lens, ol, (size_t)S * 2 * sizeof(int));
+  memcpy(h_nhyp, nh, sizeof(int) * B);
+  memcpy(h_scores, reinterpret_cast<const char*>(hp_small) + small_ints * sizeof(int), (size_t)S * sizeof(double));
+  memcpy(h_l2r, hs, (size_t)R * sizeof(float));
+  if (use_r) {
+    // absent hypotheses (i >= nhyp) were scored as empty: length 0
+    std::vector<int> ulen(S);
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < N; ++i) ulen[(size_t)b * N + i] = (i < nh[b]) ? ol[2 * ((size_t)b * N + i)] : 0;
+    unreverse_r2l(hs + R, ulen.data(), 1, S, Lp, h_r2l);
   }
   return 0;
 }
@@ -1084,6 +1190,20 @@ RVB_API int rvb_ctc_prefix_beam_search(const float* d_topk_val, const int* d_top
                 "rvb_ctc_prefix_beam_search: hypothesis of %d tokens exceeds max_len=%d", h_lens[2 * i], max_len);
   }
   return 0;
+}
+
+RVB_API int rvb_beam_search_rescoring(rvb_model* m, const float* d_topk_val, const int* d_topk_idx, int k,
+                                      const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int beam,
+                                      int blank_id, const float* h_cat_embs, int n_cat, float reverse_weight, int cap,
+                                      int* h_tokens, int* h_times, int* h_lens, double* h_scores, int* h_nhyp,
+                                      float* h_l2r, float* h_r2l, int* out_max_len, void* stream) {
+  RVB_REQUIRE(m && d_topk_val && d_topk_idx && d_enc_out && h_enc_lens && h_tokens && h_times && h_lens && h_scores &&
+                  h_nhyp && h_l2r && out_max_len && B > 0 && Tp > 0 && cap > 0,
+              "rvb_beam_search_rescoring: bad arguments");
+  return rvb::beam_search_rescoring(m, d_topk_val, d_topk_idx, k, d_enc_out, h_enc_lens, B, Tp, beam, blank_id,
+                                    h_cat_embs, n_cat, reverse_weight, cap, h_tokens, h_times, h_lens, h_scores, h_nhyp,
+                                    h_l2r, h_r2l, out_max_len, g_search_ws, g_search_out, g_search_pin,
+                                    (cudaStream_t)stream);
 }
 
 RVB_API int rvb_attention_rescoring(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp,

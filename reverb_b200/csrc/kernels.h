@@ -145,5 +145,9 @@ int launch_ctc_prefix_beam(const float* topk_val, const int* topk_idx, int k, co
 // per row r: lse = logsumexp(logits[r, :V]); out[r, j] = logits[r, gather_idx[r*G + j]] - lse  (idx < 0 -> 0)
 int launch_logsoftmax_gather(const float* logits, int ld, int M, int V, const int* gather_idx, int G, float* out,
                              cudaStream_t stream);
+// decoder inputs / gather targets (B*N rows of Lp) from the device-resident n-best of launch_ctc_prefix_beam
+int launch_rescoring_inputs(const int* d_tokens, int tok_stride, const int* d_out_lens, const int* d_nhyp, int B, int N,
+                            int Lp, int sos_eos, int* tok_l, int* tok_r, int* gat_l, int* gat_r, int* slen,
+                            cudaStream_t stream);
 
 }  // namespace rvb

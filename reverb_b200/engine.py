@@ -233,6 +233,40 @@ class Engine:
             out.append((nbest, [float(s) for s in scores[b, :n]], times))
         return out
 
+    def beam_search_rescoring(self, topk_val: torch.Tensor, topk_idx: torch.Tensor, enc_out: torch.Tensor, enc_lens,
+                              beam: int, blank_id: int = 0, cat_embs=None, reverse_weight: float = 0.0):
+        """ctc_prefix_beam_search + attention_rescoring decoder scores in one native call (the n-best never leaves
+        the device in between).  -> (toks, tims (B, beam, L) int32, olen (B, beam, 2), ctc scores (B, beam) float64,
+        n_hyp (B,), l2r, r2l (B, beam, L+1) float32; r2l None when unused)."""
+        B, Tp, k = topk_idx.shape
+        lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
+        cap = max(int(lens.max()) if B else 1, 1)
+        toks = np.empty(B * beam * cap, dtype=np.int32)
+        tims = np.empty(B * beam * cap, dtype=np.int32)
+        olen = np.empty((B, beam, 2), dtype=np.int32)
+        scores = np.empty((B, beam), dtype=np.float64)
+        nhyp = np.empty(B, dtype=np.int32)
+        l2r = np.empty(B * beam * (cap + 1), dtype=np.float32)
+        use_r = reverse_weight > 0.0 and self.has_right_decoder
+        r2l = np.empty(B * beam * (cap + 1), dtype=np.float32) if use_r else None
+        L = C.c_int(0)
+        cat, ncat = self._cat(cat_embs)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_beam_search_rescoring(self._h, _ptr(topk_val), _ptr(topk_idx), k, _ptr(enc_out.contiguous()),
+                                                     _np_ptr(lens), B, Tp, beam, int(blank_id), _np_ptr(cat), ncat,
+                                                     float(reverse_weight), cap, _np_ptr(toks), _np_ptr(tims),
+                                                     _np_ptr(olen), _np_ptr(scores), _np_ptr(nhyp), _np_ptr(l2r),
+                                                     _np_ptr(r2l), C.byref(L), self._stream()),
+                  "rvb_beam_search_rescoring")
+        L = L.value
+        n = B * beam
+        toks = toks[:n * L].reshape(B, beam, L)
+        tims = tims[:n * L].reshape(B, beam, L)
+        l2r = l2r[:n * (L + 1)].reshape(B, beam, L + 1)
+        if r2l is not None:
+            r2l = r2l[:n * (L + 1)].reshape(B, beam, L + 1)
+        return toks, tims, olen, scores, nhyp, l2r, r2l
+
     def rescoring_scores_raw(self, enc_out: torch.Tensor, enc_lens, toks: np.ndarray, hlen: np.ndarray, cat_embs=None,
                              reverse_weight: float = 0.0):
         """toks (B, N, L) int32 padded hypotheses, hlen (B, N) their lengths (-1 = absent).

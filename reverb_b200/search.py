@@ -102,11 +102,12 @@ def rescoring_pick_batch(toks: np.ndarray, tims: np.ndarray, olen: np.ndarray, c
     for b in range(B):
         i = int(best[b])
         U = int(lens[b, i])
-        tc = [math.exp(float(x)) for x in l2r[b, i, :U]]
+        # exp in float64 of the float32 log-probs (numpy's vectorised exp; the reference's math.exp may differ by 1 ulp)
+        tc = np.exp(l2r[b, i, :U].astype(np.float64))
         if use_r:
-            tc = [(tc[j] + math.exp(float(r2l[b, i, j]))) / 2 for j in range(U)]
+            tc = (tc + np.exp(r2l[b, i, :U].astype(np.float64))) / 2
         nt = int(olen[b, i, 1])
         out.append(DecodeResult(tuple(toks[b, i, :U].tolist()), float(total[b, i]),
                                 confidence=math.exp(float(norm[b, i])), times=tims[b, i, :nt].tolist(),
-                                tokens_confidence=tc))
+                                tokens_confidence=tc.tolist()))
     return out

@@ -199,6 +199,7 @@ def test_decode_is_consistent_with_oracle_searches_on_gpu_logprobs(asr, golden_c
             gr = got["attention_rescoring"][b]
             assert tuple(gr.tokens) == tuple(want_r.tokens) and gr.times == want_r.times
             assert abs(gr.score - want_r.score) < 1e-4 and abs(gr.confidence - want_r.confidence) < 1e-6
+            np.testing.assert_allclose(gr.tokens_confidence, want_r.tokens_confidence, rtol=1e-4, atol=1e-7)
 
 
 @pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])

@@ -155,3 +155,34 @@ def test_encoder_length_formula_matches_mask_slicing():
             mask = (torch.arange(T) < ln)[None, None, :]
             want = int(mask[:, :, 2::2][:, :, 2::2].sum())
             assert lib.rvb_encoder_out_len(ln, T) == want, (T, ln)
+
+
+def test_rescoring_pick_batch_equals_per_utterance_pick():
+    """The array path used by decode() (fused native search + rescoring) picks exactly like `rescoring_pick`."""
+    from reverb_b200.search import rescoring_pick, rescoring_pick_batch
+    rng = np.random.default_rng(0)
+    B, N, L = 5, 10, 12
+    olen = np.zeros((B, N, 2), np.int32)
+    toks = rng.integers(1, 90, (B, N, L)).astype(np.int32)
+    tims = np.sort(rng.integers(0, 99, (B, N, L)), axis=2).astype(np.int32)
+    nhyp = np.array([10, 10, 7, 1, 10], np.int32)
+    l2r = np.zeros((B, N, L + 1), np.float32)
+    r2l = np.zeros((B, N, L + 1), np.float32)
+    for b in range(B):
+        for i in range(N):
+            U = int(rng.integers(0, L + 1))
+            olen[b, i] = (U, U)
+            l2r[b, i, :U + 1] = -rng.random(U + 1).astype(np.float32) * 3
+            r2l[b, i, :U + 1] = -rng.random(U + 1).astype(np.float32) * 3
+    sc = -rng.random((B, N)) * 20
+    for rw in (0.0, 0.3):
+        got = rescoring_pick_batch(toks, tims, olen, sc, nhyp, l2r, r2l if rw > 0 else None, 0.1, rw)
+        for b in range(B):
+            n = int(nhyp[b])
+            hyps = [tuple(toks[b, i, :olen[b, i, 0]].tolist()) for i in range(n)]
+            want = rescoring_pick(hyps, list(sc[b, :n]), [tims[b, i, :olen[b, i, 1]].tolist() for i in range(n)],
+                                  l2r[b], r2l[b] if rw > 0 else None, 0.1, rw)
+            g = got[b]
+            assert tuple(g.tokens) == tuple(want.tokens) and g.score == want.score and g.times == want.times
+            assert g.confidence == want.confidence
+            np.testing.assert_allclose(g.tokens_confidence, want.tokens_confidence, rtol=1e-15)
