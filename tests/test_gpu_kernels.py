@@ -253,3 +253,32 @@ def test_attention_tcgen05_grouped_cross(lib):
     s = s.masked_fill(mask[:, None, None, :], -float("inf"))
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(G, Tq, d)
     torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("ramp", [20.0, -20.0])
+def test_attention_tcgen05_running_max_rescale(lib, ramp):
+    """Scores whose magnitude grows (or shrinks) along the key axis: with ramp > 0 later key tiles exceed the running
+    maximum by far more than 2^8, so the lazy rescale of the TMEM accumulator / row sum runs many times per row."""
+    torch.manual_seed(5)
+    H, dk = 2, 64
+    d = H * dk
+    G, Tq, Tk = 2, 200, 700
+    qx = (torch.randn(G, Tq, d, device="cuda") * 0.7).bfloat16()
+    kvf = torch.randn(G, Tk, 2 * d, device="cuda") * 0.7
+    t = torch.arange(Tk, device="cuda", dtype=torch.float32) / Tk
+    gain = 1.0 + abs(ramp) * (t if ramp > 0 else (1.0 - t))
+    kvf[..., :d] *= gain[None, :, None]
+    kv = kvf.bfloat16()
+    klens = torch.tensor([700, 333], dtype=torch.int32, device="cuda")
+    out = torch.zeros(G, Tq, d, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dk)
+    _check(lib, lib.rvb_attention_tc(_p(qx), _p(kv), C.c_void_p(kv.data_ptr() + 2 * d), _p(out), d, 2 * d, 2 * d, d,
+                                     G, Tq, Tk, H, dk, None, _p(klens), scale, _stream()))
+    q = qx.float().view(G, Tq, H, dk).transpose(1, 2)
+    k = kv[..., :d].float().view(G, Tk, H, dk).transpose(1, 2)
+    v = kv[..., d:].float().view(G, Tk, H, dk).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) * scale
+    mask = torch.arange(Tk, device="cuda")[None, :] >= klens[:, None]
+    s = s.masked_fill(mask[:, None, None, :], -float("inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(G, Tq, d)
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
