@@ -211,29 +211,26 @@ int launch_double_layernorm(const float* x, const float* ga, const float* ba, co
 // ---------------------------------------------------------------------------------------------------------------
 // GlobalCMVN + Conv2d(1, C, 3, stride 2) + ReLU  (transformer/cmvn.py:36-47, subsampling.py:186-187).
 // Output is channels-last bf16 with the time axis split by parity, (B, 2, T1h, F1, C), so that the second conv's
-// implicit-GEMM A tiles (gemm.cu conv_mode) are plain unit-stride 4-D TMA boxes.  One CTA per (b, t1).
+// implicit-GEMM A tiles (gemm.cu conv_mode) are plain unit-stride 4-D TMA boxes.  One CTA per (b, C1_ROWS output
+// rows): a thread keeps the 8 x 9 weights of its channel group in registers and reuses them for every (row, f), so
+// the weight fetch is amortised over C1_ROWS * F1 outputs; the 2*C1_ROWS+1 CMVN'd input rows sit in shared memory.
+constexpr int C1_ROWS = 4;
+
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, const float* __restrict__ istd,
              const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out, int T, int F, int C,
              int T1, int T1h, int F1) {
-  extern __shared__ float s_in[];  // 3 rows x F, CMVN applied
-  const int t1 = blockIdx.x;       // 0 .. 2*T1h-1
+  extern __shared__ float s_in[];  // (2*C1_ROWS+1) rows x F, CMVN applied
+  const int t1_0 = blockIdx.x * C1_ROWS;  // first output row of this CTA, 0 .. 2*T1h-1
   const int b = blockIdx.y;
-  const int par = t1 & 1, th = t1 >> 1;
-  bf16* orow = out + (((long long)(b * 2 + par) * T1h + th) * F1) * C;
   const int CG = C >> 3;
-  if (t1 >= T1) {  // padding row (T1 odd): keep it finite
-    for (int i = threadIdx.x; i < F1 * CG; i += blockDim.x)
-      reinterpret_cast<uint4*>(orow)[i] = make_uint4(0u, 0u, 0u, 0u);
-    return;
-  }
-  for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) {
+  constexpr int IN_ROWS = 2 * C1_ROWS + 1;
+  for (int i = threadIdx.x; i < IN_ROWS * F; i += blockDim.x) {
     int kh = i / F, f = i - kh * F;
-    int t = 2 * t1 + kh;
+    int t = 2 * t1_0 + kh;
     float x = (t < T) ? feats[((long long)b * T + t) * F + f] : 0.f;
     s_in[i] = (x - __ldg(mean + f)) * __ldg(istd + f);
   }
-  __syncthreads();
   const int cg = threadIdx.x % CG;
   const int fstep = blockDim.x / CG;
   float wr[8][9], br[8];
@@ -243,39 +240,50 @@ conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, co
 #pragma unroll
     for (int k = 0; k < 9; ++k) wr[c][k] = __ldg(w + (cg * 8 + c) * 9 + k);
   }
-  for (int f = threadIdx.x / CG; f < F1; f += fstep) {
-    float in[9];
-#pragma unroll
-    for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-      for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = s_in[kh * F + 2 * f + kw];
-    float o[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float a = br[c];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) a = fmaf(wr[c][k], in[k], a);
-      o[c] = fmaxf(a, 0.f);
+  __syncthreads();
+  for (int rr = 0; rr < C1_ROWS; ++rr) {
+    const int t1 = t1_0 + rr;
+    if (t1 >= 2 * T1h) break;
+    const int par = t1 & 1, th = t1 >> 1;
+    bf16* orow = out + (((long long)(b * 2 + par) * T1h + th) * F1) * C;
+    if (t1 >= T1) {  // padding row (T1 odd): keep it finite
+      for (int i = threadIdx.x; i < F1 * CG; i += blockDim.x)
+        reinterpret_cast<uint4*>(orow)[i] = make_uint4(0u, 0u, 0u, 0u);
+      continue;
     }
-    uint4 u;
-    u.x = pack_bf16x2(o[0], o[1]);
-    u.y = pack_bf16x2(o[2], o[3]);
-    u.z = pack_bf16x2(o[4], o[5]);
-    u.w = pack_bf16x2(o[6], o[7]);
-    reinterpret_cast<uint4*>(orow + (long long)f * C)[cg] = u;
+    const float* s_r = s_in + 2 * rr * F;
+    for (int f = threadIdx.x / CG; f < F1; f += fstep) {
+      float in[9];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = s_r[kh * F + 2 * f + kw];
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float a = br[c];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) a = fmaf(wr[c][k], in[k], a);
+        o[c] = fmaxf(a, 0.f);
+      }
+      uint4 u;
+      u.x = pack_bf16x2(o[0], o[1]);
+      u.y = pack_bf16x2(o[2], o[3]);
+      u.z = pack_bf16x2(o[4], o[5]);
+      u.w = pack_bf16x2(o[6], o[7]);
+      reinterpret_cast<uint4*>(orow + (long long)f * C)[cg] = u;
+    }
   }
 }
 
 int launch_conv1(const float* feats, const float* mean, const float* istd, const float* w, const float* bias,
                  bf16* out, int B, int T, int F, int C, int T1, int T1h, int F1, cudaStream_t stream) {
-  RVB_REQUIRE(C % 8 == 0 && C / 8 <= 1024, "conv1: C=%d unsupported", C);
+  RVB_REQUIRE(C % 8 == 0 && C / 8 <= 256, "conv1: C=%d unsupported", C);
   const int CG = C / 8;
-  int threads = CG;
-  while (threads < 256 && threads * 2 <= 1024) threads *= 2;
-  if (threads > 1024) threads = CG;
-  dim3 grid(2 * T1h, B);
-  conv1_kernel<<<grid, threads, 3 * F * sizeof(float), stream>>>(feats, mean, istd, w, bias, out, T, F, C, T1, T1h,
-                                                                 F1);
+  const int threads = (256 / CG) * CG;
+  dim3 grid((2 * T1h + C1_ROWS - 1) / C1_ROWS, B);
+  conv1_kernel<<<grid, threads, (2 * C1_ROWS + 1) * F * sizeof(float), stream>>>(feats, mean, istd, w, bias, out, T, F,
+                                                                                 C, T1, T1h, F1);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;

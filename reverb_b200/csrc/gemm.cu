@@ -48,6 +48,7 @@ struct GemmKParams {
   const int* row_lens;
   int rows_per_batch;
   int conv_mode, conv_T2, conv_F2, conv_tt, conv_cblocks;
+  int bf16_coalesced;  // bf16 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
   int f32_coalesced;  // fp32 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
   int epi_warps;  // 4 or 8 epilogue warps drain a tile (8: short-K, epilogue-bound shapes; 4: long-K, MMA-bound)
   // simt fallback only
@@ -260,6 +261,70 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
       tmem_ld_32x32(taddr + c + 32, gv);
       tmem_ld_wait();
       if (orow >= 0) store_glu(p, orow, n0_tile + c, av, gv);
+    }
+  } else if ((EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_SILU) && p.bf16_coalesced) {
+    // bf16 outputs: 64 accumulator columns (= 128 bytes per row) per round through the warp's staging tile, so a
+    // warp store covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes (8x fewer LSU wavefronts)
+    const int slot = lane & 7, rsub = lane >> 3;
+    long long ro[8];  // element offset of (row it*4+rsub, column n0_tile + slot*8), or -1
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const long long o = __shfl_sync(0xffffffffu, orow, it * 4 + rsub);
+      ro[it] = (o >= 0) ? o * p.ldo + n0_tile + slot * 8 : -1;
+    }
+    bf16* out = reinterpret_cast<bf16*>(p.out);
+    uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
+    mbar_wait(tfull_bar, aphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c0; c < c1; c += 64) {
+      if (n0_tile + c >= p.N) break;
+      if (n0_tile + c + 64 <= p.N) {
+        uint32_t acc[64];
+        tmem_ld_32x32(taddr + c, acc);
+        tmem_ld_32x32(taddr + c + 32, acc + 32);
+        tmem_ld_wait();
+        const int n0 = n0_tile + c;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {  // 8 columns -> one 16-byte slot
+          float v[8];
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * j + h);
+            v[4 * h + 0] = __uint_as_float(acc[8 * j + 4 * h + 0]) + b4.x;
+            v[4 * h + 1] = __uint_as_float(acc[8 * j + 4 * h + 1]) + b4.y;
+            v[4 * h + 2] = __uint_as_float(acc[8 * j + 4 * h + 2]) + b4.z;
+            v[4 * h + 3] = __uint_as_float(acc[8 * j + 4 * h + 3]) + b4.w;
+          }
+          if (EPI == EPI_BF16_RELU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          } else if (EPI == EPI_BF16_SILU) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fast_silu(v[e]);
+          }
+          *reinterpret_cast<uint4*>(stage_u + lane * 32 + ((j ^ (lane & 7)) << 2)) =
+              make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                         pack_bf16x2(v[6], v[7]));
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + rsub;
+          const uint4 u = *reinterpret_cast<const uint4*>(stage_u + row * 32 + ((slot ^ (row & 7)) << 2));
+          if (ro[it] >= 0) *reinterpret_cast<uint4*>(out + ro[it] + c) = u;
+        }
+        __syncwarp();
+      } else {
+        for (int cc = c; cc < c + 64 && cc < c1; cc += 32) {
+          if (n0_tile + cc >= p.N) break;
+          uint32_t acc[32];
+          tmem_ld_32x32(taddr + cc, acc);
+          tmem_ld_wait();
+          if (orow >= 0) store_chunk<EPI>(p, orow, n0_tile + cc, acc);
+        }
+      }
     }
   } else if ((EPI == EPI_RESID || EPI == EPI_F32) && p.f32_coalesced) {
     const int slot = lane & 7, rsub = lane >> 3;
@@ -967,6 +1032,9 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
   p.conv_mode = a.conv_mode;
   p.epi_warps = (a.K <= 2048) ? 8 : 4;
+  p.bf16_coalesced = (a.out_mode == OUT_BF16) && (a.act != ACT_GLU) && (p.ldo % 8 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
+                     (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
   p.f32_coalesced = (a.out_mode != OUT_BF16) && (p.ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
                     (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
   p.A = a.A;
