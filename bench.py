@@ -194,6 +194,9 @@ def main():
     ap.add_argument("--chunks", type=int, default=64, help="30 s chunks per GPU per step")
     ap.add_argument("--shape", default="bench", choices=["bench", "test"])
     ap.add_argument("--reverse_weight", type=float, default=0.0)
+    ap.add_argument("--mode", default="attention_rescoring", choices=["attention_rescoring", "ctc_prefix_beam_search"],
+                    help="decode mode of the step: the metric's attention_rescoring (default; a superset of BASELINE "
+                         "configs[1]) or configs[1] exactly (encoder + ctc_prefix_beam_search)")
     ap.add_argument("--cpu-chunks", type=int, default=1, help="30 s chunks per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--lanes", type=int, default=1, help="concurrent decoding lanes (streams + host threads) per GPU")
@@ -207,9 +210,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     from reverb_b200 import synth
     shape = synth.BENCH_SHAPE if args.shape == "bench" else synth.TEST_SHAPE
-    config = {"workload": f"{args.chunks}x30s chunks per GPU, fbank+ConformerEncoder+ctc_prefix_beam_search+"
-                          f"attention_rescoring, synthetic reverb_asr_v1 shape (d={shape['d']}, L={shape['blocks']}, "
-                          f"V={shape['vocab']})",
+    stages = "fbank+ConformerEncoder+ctc_prefix_beam_search" + ("+attention_rescoring" if args.mode == "attention_rescoring" else "")
+    config = {"workload": f"BASELINE configs[1]: {args.chunks}x30s chunks per GPU, {stages}, synthetic reverb_asr_v1 shape "
+                          f"(d={shape['d']}, L={shape['blocks']}, V={shape['vocab']})", "mode": args.mode,
               "chunk_frames": CHUNK_FRAMES, "chunks_per_gpu": args.chunks, "beam_size": 10, "ctc_weight": 0.1,
               "reverse_weight": args.reverse_weight, "parallelism": f"chunk-sharded x{world}", "lanes_per_gpu": args.lanes,
               "l2_policy": "inputs larger than L2 (61 MB PCM, multi-GB activations per step); no explicit flush"}
@@ -256,9 +259,9 @@ def main():
 
     def decode_device(pcm: torch.Tensor):
         feats = eng.fbank_batch(pcm)                                                      # (B, 2998, 80)
-        res = model.decode(["attention_rescoring"], feats, lens, 10, ctc_weight=0.1,
+        res = model.decode([args.mode], feats, lens, 10, ctc_weight=0.1,
                            reverse_weight=args.reverse_weight, blank_id=asr.blank_id, cat_embs=cat)
-        return res["attention_rescoring"]
+        return res[args.mode]
 
     lanes = None
     if args.lanes > 1:
@@ -272,9 +275,9 @@ def main():
         if not pcm.is_cuda:
             pcm = pcm.to(dev, non_blocking=True)
         feats = mdl.engine.fbank_batch(pcm)
-        res = mdl.decode(["attention_rescoring"], feats, lens_lane, 10, ctc_weight=0.1,
+        res = mdl.decode([args.mode], feats, lens_lane, 10, ctc_weight=0.1,
                          reverse_weight=args.reverse_weight, blank_id=asr.blank_id, cat_embs=cat)
-        return res["attention_rescoring"]
+        return res[args.mode]
 
     def step_resident():
         if lanes is None:
@@ -354,7 +357,7 @@ def main():
     ms_e2e, hyps = timed(step_e2e, args.steps)
     e2e_val = audio_s / (ms_e2e / 1e3)
     n_tok = sum(len(h.tokens) for h in hyps)
-    d2h = args.chunks * (10 * 2 * 748 * 4 + 10 * 2 * 4 + 10 * 8 + 4) + args.chunks * 10 * (n_tok // max(len(hyps), 1) + 2) * 4
+    d2h = int(getattr(eng, "last_d2h_bytes", 0))     # counted by the engine from the arrays the native call fills
 
     if rank != 0:
         if world > 1:

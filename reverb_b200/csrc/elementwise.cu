@@ -301,7 +301,7 @@ int launch_conv1(const float* feats, const float* mean, const float* istd, const
 // one channel pair, loads its CM_TT+K-1 halo values straight into registers (a warp reads 128 contiguous bytes per
 // frame) and runs the fully unrolled sliding window.  No block-wide phases, several CTAs per SM, so the loads of one
 // CTA overlap the FMAs of the others.  With LayerNorm it writes the fp32 conv result and accumulates per-frame
-// sum / sum of squares with one atomic pair per (frame, CTA); kernel B (conv_norm_silu_kernel, one warp per frame)
+// sum / sum of squares into one slot per (frame, channel slice) — no atomics, deterministic; kernel B (conv_norm_silu_kernel, one warp per frame)
 // normalises + SiLU -> bf16.  With BatchNorm (eval) kernel A applies norm + SiLU itself and writes bf16 directly.
 // K = 0 instantiates the generic version (run-time tap count, halo re-read through L1).
 //
@@ -412,8 +412,9 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
   if (threadIdx.x < 2 * CM_TT) {
     const int t = threadIdx.x >> 1, which = threadIdx.x & 1;
     if (t0 + t < T) {
+      // one slot per (frame, channel slice): no atomics, so the statistics (and everything after) are deterministic
       const float v = s_part[0][t][which] + s_part[1][t][which] + s_part[2][t][which] + s_part[3][t][which];
-      atomicAdd(stats + ((long long)b * T + t0 + t) * 2 + which, v);
+      stats[(((long long)b * T + t0 + t) * gridDim.z + blockIdx.z) * 2 + which] = v;
     }
   }
 }
@@ -421,14 +422,19 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
 // y = SiLU(LN(conv_out)) with mean / variance from the accumulated (sum, sum of squares): one warp per frame
 template <int NV>
 __global__ void __launch_bounds__(256)
-conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restrict__ stats,
+conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restrict__ stats, int nslice,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M, int C,
                       bf16* __restrict__ out) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const float mean = stats[row * 2] / (float)C;
-  const float var = fmaxf(stats[row * 2 + 1] / (float)C - mean * mean, 0.f);
+  float sum = 0.f, sq = 0.f;
+  for (int i = 0; i < nslice; ++i) {  // fixed order: bit-reproducible
+    sum += stats[(row * nslice + i) * 2];
+    sq += stats[(row * nslice + i) * 2 + 1];
+  }
+  const float mean = sum / (float)C;
+  const float var = fmaxf(sq / (float)C - mean * mean, 0.f);
   const float rstd = rsqrtf(var + eps);
   const int nvec = C >> 2;
   const float4* xr = reinterpret_cast<const float4*>(conv_out + row * C);
@@ -455,8 +461,8 @@ int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, cons
   RVB_REQUIRE(!causal || pad_glu != nullptr, "conv_mid: causal mode needs the GLU(pointwise_conv1 bias) pad row");
   RVB_REQUIRE(!use_ln || (conv_tmp != nullptr && stats != nullptr), "conv_mid: LayerNorm needs the fp32 scratch");
   const int C2 = C / 2;
-  if (use_ln) RVB_CHECK_CUDA(cudaMemsetAsync(stats, 0, (size_t)B * T * 2 * sizeof(float), stream));
   dim3 grid((T + CM_TT - 1) / CM_TT, B, (C2 + 127) / 128);
+  const int nslice = (int)grid.z;
 #define RVB_DW(KK)                                                                                                  \
   conv_dw_kernel<KK><<<grid, 128, 0, stream>>>(x, pad_glu, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln, eps, \
                                                conv_tmp, stats, out, T, C, K, causal)
@@ -471,12 +477,12 @@ int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, cons
     const long long M = (long long)B * T;
     const int nv = (C / 4 + 31) / 32;
     const unsigned g2 = (unsigned)((M + 7) / 8);
-    if (nv <= 1) conv_norm_silu_kernel<1><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
-    else if (nv <= 2) conv_norm_silu_kernel<2><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
-    else if (nv <= 4) conv_norm_silu_kernel<4><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
-    else if (nv <= 8) conv_norm_silu_kernel<8><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
-    else if (nv <= 16) conv_norm_silu_kernel<16><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
-    else conv_norm_silu_kernel<32><<<g2, 256, 0, stream>>>(conv_tmp, stats, norm_w, norm_b, eps, M, C, out);
+    if (nv <= 1) conv_norm_silu_kernel<1><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
+    else if (nv <= 2) conv_norm_silu_kernel<2><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
+    else if (nv <= 4) conv_norm_silu_kernel<4><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
+    else if (nv <= 8) conv_norm_silu_kernel<8><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
+    else if (nv <= 16) conv_norm_silu_kernel<16><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
+    else conv_norm_silu_kernel<32><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
     RVB_COUNT_LAUNCH();
     RVB_CHECK_LAUNCH();
   }

@@ -522,7 +522,7 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       m->ws_att.ensure((size_t)M * d * 2) || m->ws_pw.ensure((size_t)M * d * 2) ||
       m->ws_cm.ensure((size_t)M * d * 2) || m->ws_y.ensure((size_t)M * d * 4) || m->ws_ybf.ensure((size_t)M * d * 2) ||
       m->ws_pall.ensure((size_t)Tp * L * d * 2) || m->ws_kpp.ensure((size_t)M * d * 2) ||
-      m->ws_cbias.ensure(((size_t)B * H * Tp + (size_t)M * 2) * 4))
+      m->ws_cbias.ensure(((size_t)B * H * Tp + (size_t)M * 2 * ((d / 2 + 127) / 128)) * 4))
     return -1;
   const bool tc_attn = attn_impl() == 1 && dk == 64;
   bf16* c1 = m->ws_c1.as<bf16>();

@@ -73,7 +73,7 @@ int launch_conv1(const float* feats, const float* mean, const float* istd, const
                  cudaStream_t stream);
 // depthwise conv (K taps) + LayerNorm|BatchNorm(eval) + SiLU on the GLU'd pointwise_conv1 output (B, T, C) bf16
 // (GEMM epilogue ACT_GLU) -> (B, T, C) bf16.  pad_glu (C, fp32): value of the K-1 causal left pad frames =
-// GLU(pointwise_conv1 bias), not zeros.  conv_tmp (B*T, C) fp32 and stats (B*T, 2) scratch are needed with LayerNorm.
+// GLU(pointwise_conv1 bias), not zeros.  conv_tmp (B*T, C) fp32 and stats (B*T, ceil(C/256), 2) scratch are needed with LayerNorm.
 int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w /*[C][K]*/, const float* dw_b,
                     const float* norm_w, const float* norm_b, const float* bn_mean, const float* bn_var,
                     int use_layer_norm, float eps, bf16* out, int B, int T, int C, int K, int causal,

@@ -260,6 +260,9 @@ class Engine:
                   "rvb_beam_search_rescoring")
         L = L.value
         n = B * beam
+        # bytes the native call copied device -> host (lengths, counts, CTC scores, tokens, times, decoder scores)
+        self.last_d2h_bytes = (olen.nbytes + nhyp.nbytes + scores.nbytes + 2 * n * L * 4
+                               + n * (L + 1) * 4 * (2 if use_r else 1))
         toks = toks[:n * L].reshape(B, beam, L)
         tims = tims[:n * L].reshape(B, beam, L)
         l2r = l2r[:n * (L + 1)].reshape(B, beam, L + 1)

@@ -117,7 +117,7 @@ class ReverbASR:
                 torch.from_numpy(pcm).to(torch.float))
             wave_dev = wav[0].contiguous().to(self.device)
         else:
-            wave_dev = torch.from_numpy(pcm[0]).pin_memory().to(self.device, non_blocking=True)
+            wave_dev = torch.from_numpy(np.array(pcm[0], copy=True)).pin_memory().to(self.device, non_blocking=True)
         if wave_dev.numel() < 400:
             raise AssertionError(f"choose a window size 400 that is [2, {wave_dev.numel()}]")  # torchaudio's check
         return self.engine.fbank(wave_dev).unsqueeze(0)
