@@ -130,6 +130,14 @@ RVB_API int rvb_beam_search_rescoring(rvb_model* m, const float* d_topk_val, con
                                       int* h_tokens, int* h_times, int* h_lens, double* h_scores, int* h_nhyp,
                                       float* h_l2r, float* h_r2l, int* out_max_len, void* stream);
 
+/* One step of the autoregressive `attention` decode mode (attention_beam_search, search.py:251-360: the
+ * decoder.forward_one_step + logp.topk(beam) pair of lines 302-306).  h_hyps (B*N, L) int32: the running hypotheses
+ * (sos first), N per utterance, all of length L; runs the LEFT decoder over them against the utterance's encoder output
+ * (keys >= h_enc_lens[b] masked) and returns log_softmax(top-k) of the last position: h_topk_val / h_topk_idx (B*N, k). */
+RVB_API int rvb_decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
+                                  const int* h_hyps, int L, const float* h_cat_embs, int n_cat, int k, float* h_topk_val,
+                                  int* h_topk_idx, void* stream);
+
 /* ---- kernel-level entry points (parity tests, profiling) ----------------------------------------------------- */
 /* C[M,N] = A[M,K] W[N,K]^T + bias; act: 0 none 1 relu 2 silu 3 glu; out_mode: 0 bf16, 1 f32, 2 f32 residual += alpha*(.)
  * act 3 (pointwise_conv1 + GLU of the conformer conv module, convolution.py:129-130): bf16 output (M, N/2); W / bias

@@ -215,10 +215,11 @@ def ctc_logprobs(enc_out, sd: SD, blank_penalty: float = 0.0, blank_id: int = 0)
     return logits.log_softmax(dim=2)
 
 
-def decoder_forward(memory, ys_in, ys_lens, sd: SD, cfg, side: str, cat_embs):
+def decoder_forward(memory, ys_in, ys_lens, sd: SD, cfg, side: str, cat_embs, mem_lens=None):
     """(LanguageSpecific)TransformerDecoder.forward (transformer/decoder.py:116-169, 308-383) with
     DecoderLayer.forward (decoder_layer.py:62-133) / LanguageSpecificDecoderLayer.forward (:251-340).
-    memory (N,T,d) with an all-ones memory mask (asr_model.py:895-900). Returns logits (N,L,V)."""
+    memory (N,T,d) with an all-ones memory mask (asr_model.py:895-900) unless mem_lens is given (attention
+    mode passes the encoder mask, search.py:268-269).  Returns logits (N,L,V)."""
     dc = cfg["decoder_conf"]
     H = dc["attention_heads"]
     nb = dc["num_blocks"] if side == "left_decoder" else dc["r_num_blocks"]
@@ -228,6 +229,8 @@ def decoder_forward(memory, ys_in, ys_lens, sd: SD, cfg, side: str, cat_embs):
     d = memory.shape[-1]
     tgt_mask = (~make_pad_mask(ys_lens, L)).unsqueeze(1) & torch.tril(torch.ones(L, L, dtype=torch.bool)).unsqueeze(0)
     mem_mask = torch.ones(N, 1, memory.shape[1], dtype=torch.bool)
+    if mem_lens is not None:
+        mem_mask = (~make_pad_mask(mem_lens, memory.shape[1])).unsqueeze(1)
     x = F.embedding(ys_in, sd[p + ".embed.0.weight"]) * math.sqrt(d) + sinusoid_pe(L, d).unsqueeze(0)
     for i in range(nb):
         q = f"{p}.decoders.{i}"
@@ -256,3 +259,15 @@ def reverse_hyps(hyps_in: torch.Tensor, hyps_lens: torch.Tensor, eos: int) -> to
     r = torch.gather(r, 1, index)
     r = torch.where(seq_mask, r, eos)
     return torch.cat([hyps_in[:, 0:1], r], dim=1)
+
+
+def decoder_step_logp(memory, mem_lens, hyps, sd: SD, cfg, cat_embs):
+    """TransformerDecoder.forward_one_step (transformer/decoder.py:191-234) of the LEFT decoder
+    (Bi / LanguageSpecificBi decoders delegate to it, :498-522, :640-664): log_softmax over the vocabulary at the
+    LAST position of every running hypothesis.  The reference caches the previous positions' layer outputs
+    (decoder_layer.py:86-103); with the causal mask that equals recomputing the whole prefix, which is what this
+    restatement does.  memory (S,T,d), mem_lens (S,), hyps (S,i) incl. sos -> (S,V)."""
+    S, L = hyps.shape
+    lens = torch.full((S,), L, dtype=torch.long)
+    logits = decoder_forward(memory, hyps, lens, sd, cfg, "left_decoder", cat_embs, mem_lens=mem_lens)
+    return torch.log_softmax(logits[:, -1], dim=-1)

@@ -72,11 +72,13 @@ class OracleASR:
     @torch.no_grad()
     def decode(self, methods: List[str], feats: torch.Tensor, lens: torch.Tensor, beam_size: int = 10,
                ctc_weight: float = 0.0, reverse_weight: float = 0.0, cat_embs=None,
-               blank_penalty: float = 0.0, return_intermediates: bool = False) -> Dict:
-        """asr/wenet/transformer/asr_model.py:331-432 (greedy / prefix / rescoring)."""
+               blank_penalty: float = 0.0, return_intermediates: bool = False, length_penalty: float = 0.0) -> Dict:
+        """asr/wenet/transformer/asr_model.py:331-432 (attention / greedy / prefix / rescoring)."""
         enc, enc_lens, _ = self.forward_encoder(feats, lens, cat_embs)
         ctc_probs = model_ref.ctc_logprobs(enc, self.sd, blank_penalty, self.blank_id)
         out = {}
+        if "attention" in methods:
+            out["attention"] = self.attention_beam_search(enc, enc_lens, beam_size, length_penalty, cat_embs)
         if "ctc_greedy_search" in methods:
             out["ctc_greedy_search"] = search_ref.ctc_greedy_search(ctc_probs, enc_lens, self.blank_id)
         prefix = None
@@ -90,6 +92,17 @@ class OracleASR:
         if return_intermediates:
             out["_encoder_out"], out["_encoder_lens"], out["_ctc_probs"] = enc, enc_lens, ctc_probs
         return out
+
+    @torch.no_grad()
+    def attention_beam_search(self, enc, enc_lens, beam_size, length_penalty, cat_embs):
+        """asr/wenet/transformer/search.py:251-360: every utterance's memory is repeated beam_size times (:266-269)."""
+        B, Tp, d = enc.shape
+        mem = enc.unsqueeze(1).repeat(1, beam_size, 1, 1).view(B * beam_size, Tp, d)
+        mem_lens = enc_lens.view(-1, 1).repeat(1, beam_size).view(-1)
+
+        def step(hyps):
+            return model_ref.decoder_step_logp(mem, mem_lens, hyps, self.sd, self.cfg, cat_embs).topk(beam_size)
+        return search_ref.attention_beam_search(step, B, Tp, beam_size, self.sos, self.eos, length_penalty)
 
     @torch.no_grad()
     def attention_rescoring(self, prefix_results, enc, enc_lens, ctc_weight, reverse_weight, cat_embs):

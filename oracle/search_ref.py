@@ -191,3 +191,54 @@ def rescoring_combine(hyps: List[tuple], ctc_scores: List[float], nbest_times, d
         tokens_confidences.append(tc)
     return DecodeResult(hyps[best_index], best_score, confidence=confidences[best_index],
                         times=nbest_times[best_index], tokens_confidence=tokens_confidences[best_index])
+
+
+def attention_beam_search(step_topk, batch_size: int, maxlen: int, beam_size: int, sos: int, eos: int,
+                          length_penalty: float = 0.0) -> List[DecodeResult]:
+    """transformer/search.py:251-360 (non-whisper branch: hyps start as [sos], prefix_len = 1).
+    step_topk(hyps (B*N, i) int64) -> (top_k_logp (B*N, N) fp32, top_k_index (B*N, N) int64): the decoder step
+    (decoder.forward_one_step + logp.topk(beam_size), :302-306) is the caller's, everything else — finished-beam
+    masking (utils/mask.py:257-303), the two-stage prune, hypothesis bookkeeping, length penalty — is restated."""
+    B, N = batch_size, beam_size
+    running = B * N
+    hyps = torch.full((running, 1), sos, dtype=torch.long)
+    prefix_len = 1
+    scores = torch.tensor([0.0] + [-float("inf")] * (N - 1), dtype=torch.float).repeat([B]).unsqueeze(1)
+    end_flag = torch.zeros_like(scores, dtype=torch.bool)
+    for i in range(prefix_len, maxlen + 1):
+        if end_flag.sum() == running:
+            break
+        top_k_logp, top_k_index = step_topk(hyps)
+        top_k_logp = top_k_logp.clone().float()
+        top_k_index = top_k_index.clone().long()
+        # mask_finished_scores / mask_finished_preds
+        if N > 1:
+            unfinished = torch.cat((torch.zeros_like(end_flag), end_flag.repeat([1, N - 1])), dim=1)
+            finished = torch.cat((end_flag, torch.zeros_like(end_flag).repeat([1, N - 1])), dim=1)
+        else:
+            unfinished, finished = torch.zeros_like(end_flag), end_flag
+        top_k_logp.masked_fill_(unfinished, -float("inf"))
+        top_k_logp.masked_fill_(finished, 0)
+        top_k_index.masked_fill_(end_flag.repeat([1, N]), eos)
+        scores = scores + top_k_logp
+        scores = scores.view(B, N * N)
+        scores, offset_k_index = scores.topk(k=N)
+        scores = scores.view(-1, 1)
+        base_k_index = torch.arange(B).view(-1, 1).repeat([1, N]) * N * N
+        best_k_index = base_k_index.view(-1) + offset_k_index.view(-1)
+        best_k_pred = torch.index_select(top_k_index.view(-1), dim=-1, index=best_k_index)
+        best_hyps_index = best_k_index // N
+        last_best_k_hyps = torch.index_select(hyps, dim=0, index=best_hyps_index)
+        hyps = torch.cat((last_best_k_hyps, best_k_pred.view(-1, 1)), dim=1)
+        end_flag = torch.eq(hyps[:, -1], eos).view(-1, 1)
+    scores = scores.view(B, N)
+    lengths = hyps.ne(eos).sum(dim=1).view(B, N).float()
+    scores = scores / lengths.pow(length_penalty)
+    best_scores, best_index = scores.max(dim=-1)
+    best_hyps_index = best_index + torch.arange(B, dtype=torch.long) * N
+    best_hyps = torch.index_select(hyps, dim=0, index=best_hyps_index)[:, prefix_len:]
+    results = []
+    for b in range(B):
+        hyp = best_hyps[b]
+        results.append(DecodeResult(hyp[hyp != eos].tolist()))
+    return results

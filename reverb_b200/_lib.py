@@ -48,6 +48,7 @@ SIGNATURES = {
     "rvb_ctc_prefix_beam_search": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rvb_beam_search_rescoring": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _vp, _vp, _vp]),
+    "rvb_decoder_step_topk": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "rvb_attention_rescoring": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp]),
     "rvb_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
     "rvb_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),

@@ -15,10 +15,10 @@ import numpy as np
 import torch
 
 from .engine import Engine
-from .search import (DecodeResult, greedy_results, prefix_beam_results, rescoring_pick,
+from .search import (DecodeResult, attention_beam_search, greedy_results, prefix_beam_results, rescoring_pick,
                      rescoring_pick_batch)
 
-SUPPORTED_METHODS = ("ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring")
+SUPPORTED_METHODS = ("attention", "ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring")
 
 
 class ASRModel:
@@ -80,6 +80,13 @@ class ASRModel:
         k = beam_size if need_beam else 1
         topk_val, topk_idx, _ = self.engine.ctc_topk(encoder_out, k, blank_penalty, blank_id)
         results: Dict[str, List[DecodeResult]] = {}
+        if "attention" in methods:
+            # autoregressive beam search with the left decoder (search.py:251-360); the decoder step runs on the GPU,
+            # the beam bookkeeping on the host like the reference's
+            def step(hyps):
+                return self.engine.decoder_step_topk(encoder_out, encoder_lens, hyps, beam_size, cat_embs, beam_size)
+            results["attention"] = attention_beam_search(step, encoder_out.shape[0], encoder_out.shape[1], beam_size,
+                                                         self.sos, self.eos, length_penalty)
         if "ctc_greedy_search" in methods:
             results["ctc_greedy_search"] = greedy_results(self.engine.greedy_search(topk_idx, encoder_lens, blank_id))
         if need_beam:

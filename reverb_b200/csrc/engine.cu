@@ -687,9 +687,12 @@ static int ctc_topk(rvb_model* m, const float* d_enc_out, int B, int Tp, int k, 
 }
 
 // One pass of a (LanguageSpecific)TransformerDecoder over R = S * Lp rows (S sequences of Lp positions).
+// Default: log-probability of the gather target at every position -> d_scores (attention rescoring).
+// step_k > 0 (autoregressive `attention` mode): only the LAST position of every sequence goes through the output
+// layer; log_softmax + top-step_k of it -> d_step_val / d_step_idx (S, step_k).
 static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int* d_enc_lens, int B, int Tp, int N,
                         int Lp, const int* d_tokens, const int* d_seq_lens, const int* d_gather, float* d_scores,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, int step_k = 0, float* d_step_val = nullptr, int* d_step_idx = nullptr) {
   const rvb_model_config& c = m->cfg;
   const int d = c.d_model, H = c.dec_heads, dk = d / H, V = c.vocab;
   const int S = B * N;
@@ -790,8 +793,65 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
     if (gemm(h, Ld.ff2, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
   }
   if (launch_layernorm(x, D.after.g, D.after.b, 1e-5f, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+  if (step_k > 0) {
+    // rows s*Lp + (Lp-1): the A operand is the strided view (S, d) with leading dimension Lp*d
+    GemmArgs g;
+    g.A = n + (size_t)(Lp - 1) * d;
+    g.lda = Lp * d;
+    g.W = D.outl.w;
+    g.bias = D.outl.b;
+    g.M = S;
+    g.N = D.outl.N;
+    g.K = D.outl.K;
+    g.act = ACT_NONE;
+    g.out_mode = OUT_F32;
+    g.out = logits;
+    g.ldo = ldv;
+    g.alpha = 1.f;
+    if (launch_gemm(g, stream)) return -1;
+    return launch_logsoftmax_topk(logits, ldv, S, V, step_k, d_step_val, d_step_idx, nullptr, 1, stream);
+  }
   if (gemm(n, D.outl, (int)R, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
   return launch_logsoftmax_gather(logits, ldv, (int)R, V, d_gather, 1, d_scores, stream);
+}
+
+// One step of the autoregressive `attention` decode mode (decoder.forward_one_step + logp.topk, search.py:302-306):
+// the left decoder runs over the S = B*N running hypotheses of length L (sos first); the reference's per-layer
+// output cache is an optimisation of the same computation, here the prefix is simply recomputed.
+static int decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
+                             const int* h_hyps, int L, const float* h_cat, int n_cat, int k, float* h_val, int* h_idx,
+                             cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  RVB_REQUIRE(m->finalized && m->dec_l.present, "decoder_step_topk: model has no decoder");
+  RVB_REQUIRE(L >= 1 && k >= 1 && k <= 16 && k <= c.vocab, "decoder_step_topk: bad L=%d / k=%d", L, k);
+  const int d = c.d_model, S = B * N;
+  const long long R = (long long)S * L, Mem = (long long)B * Tp;
+  if (fold_lang(m, h_cat, n_cat, stream)) return -1;
+  const size_t ints = (size_t)R + S + B;
+  const size_t out_bytes = (size_t)S * k * (sizeof(float) + sizeof(int));
+  if (m->pin_b.ensure(ints * sizeof(int)) || m->ws_misc.ensure(ints * sizeof(int) + out_bytes) ||
+      m->pin_c.ensure(out_bytes) || m->ws_encbf.ensure((size_t)Mem * d * 2))
+    return -1;
+  int* hp = m->pin_b.as<int>();
+  for (long long r = 0; r < R; ++r) {
+    RVB_REQUIRE(h_hyps[r] >= 0 && h_hyps[r] < c.vocab, "decoder_step_topk: token id %d out of range", h_hyps[r]);
+    hp[r] = h_hyps[r];
+  }
+  for (int s = 0; s < S; ++s) hp[R + s] = L;
+  for (int b = 0; b < B; ++b) hp[R + S + b] = h_enc_lens[b];
+  int* dp = m->ws_misc.as<int>();
+  RVB_CHECK_CUDA(cudaMemcpyAsync(dp, hp, ints * sizeof(int), cudaMemcpyHostToDevice, stream));
+  float* d_val = reinterpret_cast<float*>(dp + ints);
+  int* d_idx = reinterpret_cast<int*>(d_val + (size_t)S * k);
+  bf16* encbf = m->ws_encbf.as<bf16>();
+  if (launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream)) return -1;
+  if (decoder_pass(m, m->dec_l, encbf, dp + R + S, B, Tp, N, L, dp, dp + R, nullptr, nullptr, stream, k, d_val, d_idx))
+    return -1;
+  RVB_CHECK_CUDA(cudaMemcpyAsync(m->pin_c.p, d_val, out_bytes, cudaMemcpyDeviceToHost, stream));
+  RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
+  memcpy(h_val, m->pin_c.p, (size_t)S * k * sizeof(float));
+  memcpy(h_idx, reinterpret_cast<char*>(m->pin_c.p) + (size_t)S * k * sizeof(float), (size_t)S * k * sizeof(int));
+  return 0;
 }
 
 // Decoder passes over device-resident inputs (all int arrays on the device):
@@ -1204,6 +1264,15 @@ RVB_API int rvb_beam_search_rescoring(rvb_model* m, const float* d_topk_val, con
                                     h_cat_embs, n_cat, reverse_weight, cap, h_tokens, h_times, h_lens, h_scores, h_nhyp,
                                     h_l2r, h_r2l, out_max_len, g_search_ws, g_search_out, g_search_pin,
                                     (cudaStream_t)stream);
+}
+
+RVB_API int rvb_decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
+                                  const int* h_hyps, int L, const float* h_cat_embs, int n_cat, int k, float* h_topk_val,
+                                  int* h_topk_idx, void* stream) {
+  RVB_REQUIRE(m && d_enc_out && h_enc_lens && h_hyps && h_topk_val && h_topk_idx && B > 0 && Tp > 0 && N > 0,
+              "rvb_decoder_step_topk: bad arguments");
+  return rvb::decoder_step_topk(m, d_enc_out, h_enc_lens, B, Tp, N, h_hyps, L, h_cat_embs, n_cat, k, h_topk_val,
+                                h_topk_idx, (cudaStream_t)stream);
 }
 
 RVB_API int rvb_attention_rescoring(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp,

@@ -270,6 +270,24 @@ class Engine:
             r2l = r2l[:n * (L + 1)].reshape(B, beam, L + 1)
         return toks, tims, olen, scores, nhyp, l2r, r2l
 
+    def decoder_step_topk(self, enc_out: torch.Tensor, enc_lens, hyps: np.ndarray, n_per_utt: int, cat_embs=None,
+                          k: int = 10):
+        """One step of `attention` mode: hyps (B*N, L) running hypotheses (sos first) -> log_softmax top-k of the
+        left decoder at the last position: (val (B*N, k) float32, idx (B*N, k) int32)."""
+        B, Tp, _ = enc_out.shape
+        hyps = np.ascontiguousarray(hyps, dtype=np.int32)
+        S, L = hyps.shape
+        assert S == B * n_per_utt
+        lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
+        val = np.empty((S, k), dtype=np.float32)
+        idx = np.empty((S, k), dtype=np.int32)
+        cat, ncat = self._cat(cat_embs)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_decoder_step_topk(self._h, _ptr(enc_out.contiguous()), _np_ptr(lens), B, Tp, n_per_utt,
+                                                 _np_ptr(hyps), L, _np_ptr(cat), ncat, k, _np_ptr(val), _np_ptr(idx),
+                                                 self._stream()), "rvb_decoder_step_topk")
+        return val, idx
+
     def rescoring_scores_raw(self, enc_out: torch.Tensor, enc_lens, toks: np.ndarray, hlen: np.ndarray, cat_embs=None,
                              reverse_weight: float = 0.0):
         """toks (B, N, L) int32 padded hypotheses, hlen (B, N) their lengths (-1 = absent).

@@ -111,3 +111,50 @@ def rescoring_pick_batch(toks: np.ndarray, tims: np.ndarray, olen: np.ndarray, c
                                 confidence=math.exp(float(norm[b, i])), times=tims[b, i, :nt].tolist(),
                                 tokens_confidence=tc.tolist()))
     return out
+
+
+def attention_beam_search(step_topk, batch_size: int, maxlen: int, beam_size: int, sos: int, eos: int,
+                          length_penalty: float = 0.0) -> List[DecodeResult]:
+    """Host bookkeeping of the `attention` decode mode (transformer/search.py:251-360, non-whisper branch), numpy
+    float32 like the reference's tensors.  step_topk(hyps (B*N, i) int64) -> (logp (B*N, N), index (B*N, N)) is the
+    decoder step (Engine.decoder_step_topk).  Finished beams keep one zero-cost <eos> branch (utils/mask.py:257-303);
+    the best beam per utterance is chosen after the length penalty; returns DecodeResult(tokens) only (no times /
+    confidences: `transcribe(mode="attention")` fails in the reference for that reason)."""
+    B, N = batch_size, beam_size
+    running = B * N
+    neg_inf = np.float32(-np.inf)
+    hyps = np.full((running, 1), sos, dtype=np.int64)
+    scores = np.tile(np.array([0.0] + [-np.inf] * (N - 1), dtype=np.float32), B).reshape(-1, 1)
+    end_flag = np.zeros((running, 1), dtype=bool)
+    zeros = np.zeros((running, 1), dtype=bool)
+    for _ in range(1, maxlen + 1):
+        if int(end_flag.sum()) == running:
+            break
+        logp, index = step_topk(hyps)
+        logp = np.array(logp, dtype=np.float32, copy=True).reshape(running, N)
+        index = np.array(index, dtype=np.int64, copy=True).reshape(running, N)
+        if N > 1:
+            unfinished = np.concatenate([zeros, np.repeat(end_flag, N - 1, axis=1)], axis=1)
+            finished = np.concatenate([end_flag, np.repeat(zeros, N - 1, axis=1)], axis=1)
+        else:
+            unfinished, finished = zeros, end_flag
+        logp[unfinished] = neg_inf
+        logp[finished] = 0.0
+        index[np.repeat(end_flag, N, axis=1)] = eos
+        cand = (scores + logp).astype(np.float32).reshape(B, N * N)
+        order = np.argsort(-cand, axis=1, kind="stable")[:, :N]            # topk, sorted, ties -> lowest index
+        scores = np.take_along_axis(cand, order, axis=1).reshape(-1, 1)
+        best_k_index = (np.arange(B)[:, None] * N * N + order).reshape(-1)
+        best_k_pred = index.reshape(-1)[best_k_index]
+        hyps = np.concatenate([hyps[best_k_index // N], best_k_pred[:, None]], axis=1)
+        end_flag = hyps[:, -1:] == eos
+    final = scores.reshape(B, N)
+    lengths = (hyps != eos).sum(axis=1).reshape(B, N).astype(np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        final = (final / np.power(lengths, np.float32(length_penalty))).astype(np.float32)
+    best = np.argmax(final, axis=1)
+    out = []
+    for b in range(B):
+        hyp = hyps[b * N + int(best[b]), 1:]
+        out.append(DecodeResult(hyp[hyp != eos].tolist()))
+    return out

@@ -203,6 +203,54 @@ def test_decode_is_consistent_with_oracle_searches_on_gpu_logprobs(asr, golden_c
 
 
 @pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_attention_mode_decoder_steps_and_search(asr, golden_cases, model_dirs, case):
+    """`attention` decode mode (search.py:251-360).  (1) the GPU decoder step (left decoder, last position,
+    log_softmax + top-k) agrees with the oracle's forward_one_step restatement on the same running hypotheses;
+    (2) ASRModel.decode(['attention']) equals the oracle's beam search driven by the GPU step function (the host
+    bookkeeping is the only other ingredient); (3) tokens vs the live-reference fixture: equal whenever the bf16
+    step log-probs do not reorder a near-tie — reported, with a floor on the agreement."""
+    import json as _json
+    from oracle import model_ref, pipeline_ref, search_ref
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    gold = _json.load(open(os.path.join(os.path.dirname(__file__), "golden", "attention_mode.json")))["cases"][case]
+    orc = pipeline_ref.OracleASR(model_dirs[case][0])
+    sd, cfg = orc.sd, orc.cfg
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    N, agree, total = 10, 0, 0
+    for bi, (fb, fl) in enumerate(m.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])):
+        enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
+        B, Tp, d = enc.shape
+        # (1) step numerics on a few hand-made prefixes
+        rng = np.random.default_rng(bi)
+        for L in (1, 2, 5):
+            hyps = rng.integers(1, 100, size=(B * N, L)).astype(np.int64)
+            hyps[:, 0] = m.model.sos
+            val, idx = m.engine.decoder_step_topk(enc, enc_lens, hyps, N, cat, N)
+            mem = enc.cpu().unsqueeze(1).repeat(1, N, 1, 1).view(B * N, Tp, d)
+            mem_lens = torch.from_numpy(enc_lens.astype(np.int64)).view(-1, 1).repeat(1, N).view(-1)
+            want = model_ref.decoder_step_logp(mem, mem_lens, torch.from_numpy(hyps), sd, cfg, cat)
+            got_at = torch.gather(want, 1, torch.from_numpy(idx.astype(np.int64)))
+            assert float((got_at - torch.from_numpy(val)).abs().max()) < 0.15
+            assert float((want.topk(N).values - torch.from_numpy(val)).abs().max()) < 0.15
+        # (2) full search: GPU decode == oracle bookkeeping over the GPU step function
+        for lp in (0.0, 0.6):
+            got = m.model.decode(["attention"], fb, fl, N, length_penalty=lp, cat_embs=cat, blank_id=0)["attention"]
+
+            def step(hyps):
+                v, i = m.engine.decoder_step_topk(enc, enc_lens, hyps.numpy(), N, cat, N)
+                return torch.from_numpy(v), torch.from_numpy(i.astype(np.int64))
+            want = search_ref.attention_beam_search(step, B, Tp, N, m.model.sos, m.model.eos, lp)
+            assert [list(r.tokens) for r in got] == [list(r.tokens) for r in want]
+            assert all(r.times is None for r in got)
+            for b in range(B):
+                total += 1
+                agree += int(list(got[b].tokens) == gold[f"length_penalty_{lp}"][bi][b])
+    assert agree >= 0.5 * total, (agree, total)
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
 def test_transcribe_api_surface(asr, golden_cases, model_dirs, case):
     """Public API: CTM / TXT strings, chunk offsets, error behaviour of the reference."""
     meta, arr = golden_cases[case]

@@ -186,3 +186,29 @@ def test_rescoring_pick_batch_equals_per_utterance_pick():
             assert tuple(g.tokens) == tuple(want.tokens) and g.score == want.score and g.times == want.times
             assert g.confidence == want.confidence
             np.testing.assert_allclose(g.tokens_confidence, want.tokens_confidence, rtol=1e-15)
+
+
+def test_attention_beam_search_host_logic_equals_oracle_restatement():
+    """`attention` mode bookkeeping (numpy, reverb_b200/search.py) vs the oracle's torch restatement of
+    search.py:251-360 on the same synthetic step function (deterministic pseudo-decoder with an <eos> that becomes
+    likely after a few tokens), several beam sizes / length penalties / batch sizes."""
+    from oracle import search_ref
+    from reverb_b200.search import attention_beam_search
+    V, sos, eos = 50, 49, 49
+
+    def make_step(seed, N):
+        def logp_of(hyps):
+            rows = []
+            for h in np.asarray(hyps):
+                key = int(np.sum(np.asarray(h, dtype=np.int64) * np.arange(1, len(h) + 1))) * 7919 + seed + 131 * len(h)
+                g = np.random.default_rng(key % (2 ** 32))
+                x = g.standard_normal(V).astype(np.float32) * 2.0
+                x[eos] += 0.9 * (len(h) - 3)
+                rows.append(torch.log_softmax(torch.from_numpy(x), dim=0))
+            return torch.stack(rows)
+        return (lambda hyps: logp_of(hyps).topk(N)), (lambda hyps: tuple(t.numpy() for t in logp_of(hyps).topk(N)))
+    for seed, B, N, lp, maxlen in [(0, 3, 10, 0.0, 12), (1, 2, 4, 0.6, 9), (2, 1, 1, 0.0, 6), (3, 4, 10, 1.0, 5)]:
+        t_step, n_step = make_step(seed, N)
+        want = search_ref.attention_beam_search(t_step, B, maxlen, N, sos, eos, lp)
+        got = attention_beam_search(n_step, B, maxlen, N, sos, eos, lp)
+        assert [list(r.tokens) for r in got] == [list(r.tokens) for r in want]

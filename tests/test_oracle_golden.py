@@ -54,6 +54,24 @@ def test_oracle_pipeline_vs_reference_golden(golden_cases, model_dirs, case):
             assert r.tokens_confidence == gr["tokens_confidence"]
 
 
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_oracle_attention_mode_vs_reference_golden(golden_cases, model_dirs, case):
+    """`attention` decode mode (autoregressive beam search, search.py:251-360): the oracle's restatement returns the
+    token ids the live reference returned (tests/golden/attention_mode.json, oracle/make_golden_attention.py)."""
+    import json
+    from oracle import pipeline_ref
+    gold = json.load(open("tests/golden/attention_mode.json"))["cases"][case]
+    meta, arr = golden_cases[case]
+    d, _ = model_dirs[case]
+    orc = pipeline_ref.OracleASR(d)
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0)
+    for lp in (0.0, 0.6):
+        for bi, (fb, fl) in enumerate(orc.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])):
+            out = orc.decode(["attention"], fb, fl, 10, cat_embs=cat, length_penalty=lp)
+            assert [list(r.tokens) for r in out["attention"]] == gold[f"length_penalty_{lp}"][bi]
+
+
 def test_log_add_and_collapse_known_answers():
     from oracle import search_ref
     inf = float("inf")
