@@ -153,10 +153,11 @@ RVB_API int rvb_attention(const void* d_q, const void* d_k, const void* d_v, con
                   int H, int dk, int q_per_kv, const int* d_k_lens, const int* d_q_lens, int causal, float scale,
                   void* stream);
 /* tcgen05 attention (d_k = 64): group g owns query rows [g*Tq, ..) and key rows [g*Tk, ..); pointers address head 0;
- * d_key_bias (groups, H, Tk) fp32 optional (added to q.k before scaling), d_k_lens (groups) optional. */
+ * d_key_bias (groups, H, Tk) fp32 optional (added to q.k before scaling), d_k_lens (groups) optional; causal != 0
+ * (needs Tq == Tk): key j is visible to query i iff j <= i (decoder self-attention, utils/mask.py subsequent_mask). */
 RVB_API int rvb_attention_tc(const void* d_q, const void* d_k, const void* d_v, void* d_out, int ldq, int ldk, int ldv,
                              int ldo, int groups, int Tq, int Tk, int H, int dk, const float* d_key_bias,
-                             const int* d_k_lens, float scale, void* stream);
+                             const int* d_k_lens, int causal, float scale, void* stream);
 /* K'' = k + pos (bf16) and cbias[b,h,t] = u_h.k + v_h.pos for the folded rel-pos attention */
 RVB_API int rvb_relpos_prep(const void* d_k, int ldk, const void* d_pos, int ldp, const float* d_bias_u,
                             const float* d_bias_v, void* d_kpp, float* d_cbias, int B, int T, int H, int dk,

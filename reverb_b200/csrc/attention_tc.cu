@@ -61,6 +61,7 @@ struct AttnTcParams {
   const float* key_bias;  // (groups_kv, H, Tk) fp32 or nullptr
   const int* k_lens;      // per kv group, or nullptr
   int Tq, Tk, H;
+  int causal;  // key j visible to query row i (position inside the group) iff j <= i
   float scale_log2;
 };
 
@@ -104,7 +105,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int q0 = qtile * AT_BM;
   int klen = p.Tk;
   if (p.k_lens) klen = min(klen, __ldg(p.k_lens + g));
-  const int ntiles = (klen + AT_BN - 1) / AT_BN;
+  // causal: no key beyond the last query row of this tile is visible to any of its rows -> skip those tiles
+  const int ntiles = ((p.causal ? min(klen, q0 + AT_BM) : klen) + AT_BN - 1) / AT_BN;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -253,7 +255,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mx[2] = fmaxf(mx[2], x2);
         mx[3] = fmaxf(mx[3], x3);
       }
-      const float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      if (p.causal && j * AT_BN + AT_BN - 1 > q0 + warp * 32) {
+        // diagonal tile (warp-uniform test): hide the keys after this row's position and redo the tile maximum
+        const int lim = q0 + r - j * AT_BN;  // last visible key of the tile for this row
+        tmax = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < AT_BN; ++e) {
+          const float x = (e <= lim) ? __uint_as_float(sv[e]) : -INFINITY;
+          sv[e] = __float_as_uint(x);
+          tmax = fmaxf(tmax, x);
+        }
+      }
       if (j == 0) {
         m_run = (tmax == -INFINITY) ? 0.f : tmax;  // PV(0) overwrites O: nothing to rescale
       } else {
@@ -470,6 +483,7 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
   RVB_REQUIRE(((uintptr_t)a.q & 15) == 0 && ((uintptr_t)a.k & 15) == 0 && ((uintptr_t)a.v & 15) == 0 &&
                   ((uintptr_t)a.out & 15) == 0,
               "attention_tc: operands must be 16-byte aligned");
+  RVB_REQUIRE(!a.causal || a.Tq == a.Tk, "attention_tc: causal needs Tq == Tk");
   if (a.groups <= 0 || a.Tq <= 0) return 0;
   if (g_encode_att == nullptr) {
     void* fn = nullptr;
@@ -491,6 +505,7 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
   p.Tq = a.Tq;
   p.Tk = a.Tk;
   p.H = a.H;
+  p.causal = a.causal;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   CUtensorMap tmQ, tmK, tmV;
   if (tmap_2d(&tmQ, a.q, (long long)a.H * AT_DK, (long long)a.groups * a.Tq, a.ldq, 128)) return -1;

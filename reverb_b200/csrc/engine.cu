@@ -721,7 +721,24 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
     // masked self-attention (decoder_layer.py:95-110 / 286-301)
     if (launch_layernorm(x, Ld.n1.g, Ld.n1.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
     if (gemm(n, Ld.qkv, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
-    {
+    if (attn_impl() == 1 && dk == 64) {
+      AttnTcArgs a;  // one group per hypothesis, causal, keys beyond the hypothesis length masked
+      a.q = qkv;
+      a.k = qkv + d;
+      a.v = qkv + 2 * d;
+      a.out = att;
+      a.ldq = a.ldk = a.ldv = 3 * d;
+      a.ldo = d;
+      a.groups = S;
+      a.Tq = Lp;
+      a.Tk = Lp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_seq_lens;
+      a.causal = 1;
+      a.scale = scale;
+      if (launch_attention_tc(a, stream)) return -1;
+    } else {
       AttnArgs a;
       a.q = qkv;
       a.k = qkv + d;
@@ -1331,7 +1348,7 @@ RVB_API int rvb_attention(const void* d_q, const void* d_k, const void* d_v, con
 
 RVB_API int rvb_attention_tc(const void* d_q, const void* d_k, const void* d_v, void* d_out, int ldq, int ldk, int ldv,
                              int ldo, int groups, int Tq, int Tk, int H, int dk, const float* d_key_bias,
-                             const int* d_k_lens, float scale, void* stream) {
+                             const int* d_k_lens, int causal, float scale, void* stream) {
   rvb::AttnTcArgs a;
   a.q = reinterpret_cast<const rvb::bf16*>(d_q);
   a.k = reinterpret_cast<const rvb::bf16*>(d_k);
@@ -1341,6 +1358,7 @@ RVB_API int rvb_attention_tc(const void* d_q, const void* d_k, const void* d_v, 
   a.groups = groups; a.Tq = Tq; a.Tk = Tk; a.H = H; a.dk = dk;
   a.key_bias = d_key_bias;
   a.k_lens = d_k_lens;
+  a.causal = causal;
   a.scale = scale;
   return rvb::launch_attention_tc(a, (cudaStream_t)stream);
 }

@@ -120,6 +120,7 @@ struct AttnTcArgs {
   int groups = 0, Tq = 0, Tk = 0, H = 0, dk = 0;
   const float* key_bias = nullptr;  // (groups, H, Tk) fp32, added to q.k before scaling
   const int* k_lens = nullptr;      // (groups) valid keys
+  int causal = 0;                   // self-attention with Tq == Tk: key j visible to query i iff j <= i
   float scale = 1.0f;
 };
 int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream);

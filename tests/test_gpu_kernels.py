@@ -214,7 +214,7 @@ def test_attention_tcgen05_relpos(lib, B, T, H):
     out = torch.zeros(B, T, d, device="cuda", dtype=torch.bfloat16)
     scale = 1.0 / math.sqrt(dk)
     _check(lib, lib.rvb_attention_tc(_p(qkv), _p(kpp), C.c_void_p(qkv.data_ptr() + 4 * d), _p(out), 3 * d, d, 3 * d, d,
-                                     B, T, T, H, dk, _p(cb), _p(klens), scale, _stream()))
+                                     B, T, T, H, dk, _p(cb), _p(klens), 0, scale, _stream()))
     torch.cuda.synchronize()
     q = qkv[..., :d].float().view(B, T, H, dk)
     k = qkv[..., d:2 * d].float().view(B, T, H, dk).transpose(1, 2)
@@ -244,7 +244,7 @@ def test_attention_tcgen05_grouped_cross(lib):
     out = torch.zeros(G, Tq, d, device="cuda", dtype=torch.bfloat16)
     scale = 1.0 / math.sqrt(dk)
     _check(lib, lib.rvb_attention_tc(_p(qx), _p(kv), C.c_void_p(kv.data_ptr() + 2 * d), _p(out), d, 2 * d, 2 * d, d,
-                                     G, Tq, Tk, H, dk, None, _p(klens), scale, _stream()))
+                                     G, Tq, Tk, H, dk, None, _p(klens), 0, scale, _stream()))
     q = qx.float().view(G, Tq, H, dk).transpose(1, 2)
     k = kv[..., :d].float().view(G, Tk, H, dk).transpose(1, 2)
     v = kv[..., d:].float().view(G, Tk, H, dk).transpose(1, 2)
@@ -273,7 +273,7 @@ def test_attention_tcgen05_running_max_rescale(lib, ramp):
     out = torch.zeros(G, Tq, d, device="cuda", dtype=torch.bfloat16)
     scale = 1.0 / math.sqrt(dk)
     _check(lib, lib.rvb_attention_tc(_p(qx), _p(kv), C.c_void_p(kv.data_ptr() + 2 * d), _p(out), d, 2 * d, 2 * d, d,
-                                     G, Tq, Tk, H, dk, None, _p(klens), scale, _stream()))
+                                     G, Tq, Tk, H, dk, None, _p(klens), 0, scale, _stream()))
     q = qx.float().view(G, Tq, H, dk).transpose(1, 2)
     k = kv[..., :d].float().view(G, Tk, H, dk).transpose(1, 2)
     v = kv[..., d:].float().view(G, Tk, H, dk).transpose(1, 2)
@@ -282,3 +282,30 @@ def test_attention_tcgen05_running_max_rescale(lib, ramp):
     s = s.masked_fill(mask[:, None, None, :], -float("inf"))
     ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(G, Tq, d)
     torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("L", [164, 64, 300])
+def test_attention_tcgen05_causal_self(lib, L):
+    """decoder self-attention form: one group per hypothesis, causal mask + key-length mask (tgt_mask of
+    decoder.py:139-146 = pad mask & subsequent_mask); rows at positions >= the hypothesis length are don't-care."""
+    torch.manual_seed(L)
+    H, dk = 2, 64
+    d = H * dk
+    S = 5
+    qkv = (torch.randn(S, L, 3 * d, device="cuda") * 0.7).bfloat16()
+    lens = torch.tensor([L, max(1, L * 2 // 3), 1, min(L, 130), min(L, 64)], dtype=torch.int32, device="cuda")
+    out = torch.zeros(S, L, d, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dk)
+    _check(lib, lib.rvb_attention_tc(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d), _p(out),
+                                     3 * d, 3 * d, 3 * d, d, S, L, L, H, dk, None, _p(lens), 1, scale, _stream()))
+    q = qkv[..., :d].float().view(S, L, H, dk).transpose(1, 2)
+    k = qkv[..., d:2 * d].float().view(S, L, H, dk).transpose(1, 2)
+    v = qkv[..., 2 * d:].float().view(S, L, H, dk).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2)) * scale
+    pos = torch.arange(L, device="cuda")
+    mask = (pos[None, :] > pos[:, None])[None] | (pos[None, None, :] >= lens[:, None, None])
+    s = s.masked_fill(mask[:, None], -float("inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(S, L, d)
+    for g in range(S):
+        n = int(lens[g])
+        torch.testing.assert_close(out[g, :n].float(), ref[g, :n], rtol=3e-2, atol=3e-2)
