@@ -323,9 +323,10 @@ def main():
         return
 
     if args.breakdown and rank == 0:
-        from reverb_b200.search import prefix_beam_results
+        from reverb_b200.search import rescoring_pick_batch
 
         def tick(label, fn, acc):
+            fn()                                  # first call may allocate; time the second
             torch.cuda.synchronize(dev)
             t0 = time.perf_counter()
             out = fn()
@@ -336,8 +337,10 @@ def main():
         feats = tick("fbank", lambda: eng.fbank_batch(pcm_dev), acc)
         enc, enc_lens = tick("encoder", lambda: eng.forward_encoder(feats, lens.numpy(), cat), acc)
         tv, ti, _ = tick("ctc_head+topk", lambda: eng.ctc_topk(enc, 10, 0.0, asr.blank_id), acc)
-        pb = tick("prefix_beam (gpu+unpack)", lambda: prefix_beam_results(eng.prefix_beam_search(tv, ti, enc_lens, 10, asr.blank_id)), acc)
-        tick("rescoring (decoder+pick)", lambda: model.attention_rescoring(pb, enc, enc_lens, 0.1, args.reverse_weight, cat), acc)
+        tick("prefix_beam only (gpu+copy)", lambda: eng.prefix_beam_search_raw(tv, ti, enc_lens, 10, asr.blank_id), acc)
+        raw = tick("prefix_beam+rescoring decoder (fused native call)",
+                   lambda: eng.beam_search_rescoring(tv, ti, enc, enc_lens, 10, asr.blank_id, cat, args.reverse_weight), acc)
+        tick("host pick", lambda: rescoring_pick_batch(*raw[:5], raw[5], raw[6], 0.1, args.reverse_weight), acc)
         print("BREAKDOWN " + json.dumps({k: round(v, 2) for k, v in acc}), file=sys.stderr)
     clocks = ClockSampler(local_rank)
     if rank == 0:

@@ -35,65 +35,129 @@ __device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
   return a;
 }
 
+// One CTA per row.  Pass 1 stages the row in shared memory and keeps each thread's running (max, index); the 32
+// "lane-group" maxima (max over the threads with the same lane id, i.e. over the elements with index = lane mod 32)
+// are k <= 16 < 32 DISTINCT elements, so the k-th best of them is a lower bound of the row's k-th best: pass 2 (which
+// also accumulates sum exp(x - max)) collects the few elements that are not worse than it — typically k .. k+4 —
+// and one warp ranks those (value desc, index asc = torch.topk's order on ties).  If the candidate list overflows
+// (rows full of ties / -inf) the kernel falls back to k rounds of block arg-max.
+constexpr int TOPK_CAP = 64;
+
 __global__ void __launch_bounds__(256)
 logsoftmax_topk_kernel(const float* __restrict__ logits, long long ld, int V, int k, float* __restrict__ topk_val,
                        int* __restrict__ topk_idx, float* __restrict__ logp_out, int apply_softmax) {
   extern __shared__ float s_row[];  // V floats
   __shared__ float s_red[8];
   __shared__ ArgMax s_arg[2][8];
+  __shared__ ArgMax s_grp[8][32];
+  __shared__ ArgMax s_cand[TOPK_CAP];
+  __shared__ ArgMax s_thresh;
   __shared__ float s_stat[2];
+  __shared__ int s_ncand;
   const long long row = blockIdx.x;
   const float* x = logits + row * ld;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float m = -INFINITY;
+  ArgMax mine;
+  mine.v = -INFINITY;
+  mine.i = 0x7fffffff;
   for (int i = threadIdx.x; i < V; i += 256) {
-    float v = x[i];
-    s_row[i] = v;
-    m = fmaxf(m, v);
+    ArgMax e;
+    e.v = x[i];
+    e.i = i;
+    s_row[i] = e.v;
+    mine = better(mine, e);
+  }
+  s_grp[warp][lane] = mine;
+  float m = warp_max(mine.v);
+  if (lane == 0) s_red[warp] = m;
+  if (threadIdx.x == 0) {
+    s_ncand = 0;
+    s_thresh.v = -INFINITY;  // stays invalid when the group maxima are not all distinct (rows with < 32 entries)
+    s_thresh.i = 0x7fffffff;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    ArgMax g = s_grp[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) g = better(g, s_grp[w][lane]);
+    int cnt = 0;  // how many lane-group maxima are strictly better than mine (a total order: indices are distinct)
+    for (int o = 0; o < 32; ++o) {
+      ArgMax h;
+      h.v = __shfl_sync(0xffffffffu, g.v, o);
+      h.i = __shfl_sync(0xffffffffu, g.i, o);
+      cnt += (h.v > g.v || (h.v == g.v && h.i < g.i)) ? 1 : 0;
+    }
+    if (cnt == k - 1) s_thresh = g;
+    if (lane == 0) {
+      float mm = s_red[0];
+      for (int w = 1; w < 8; ++w) mm = fmaxf(mm, s_red[w]);
+      s_stat[0] = mm;
+    }
+  }
+  __syncthreads();
+  const ArgMax th = s_thresh;
+  const bool filter_ok = th.i != 0x7fffffff && th.v > -INFINITY;
+  m = s_stat[0];
+  float ssum = 0.f;
+  for (int i = threadIdx.x; i < V; i += 256) {
+    const float v = s_row[i];
+    if (apply_softmax) ssum += expf(v - m);
+    if (filter_ok && (v > th.v || (v == th.v && i <= th.i))) {
+      const int slot = atomicAdd(&s_ncand, 1);
+      if (slot < TOPK_CAP) {
+        s_cand[slot].v = v;
+        s_cand[slot].i = i;
+      }
+    }
   }
   float lse_shift = 0.f, logsum = 0.f;
   if (apply_softmax) {
-    m = warp_max(m);
-    if (lane == 0) s_red[warp] = m;
-    __syncthreads();
-    m = s_red[0];
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w]);
-    __syncthreads();
-    float s = 0.f;
-    for (int i = threadIdx.x; i < V; i += 256) s += expf(s_row[i] - m);
-    s = warp_sum(s);
-    if (lane == 0) s_red[warp] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      float t = 0.f;
-      for (int w = 0; w < 8; ++w) t += s_red[w];
-      s_stat[0] = m;
-      s_stat[1] = logf(t);
-    }
-    __syncthreads();
-    lse_shift = s_stat[0];
-    logsum = s_stat[1];
-  } else {
-    __syncthreads();
+    ssum = warp_sum(ssum);
+    if (lane == 0) s_red[warp] = ssum;
+  }
+  __syncthreads();
+  if (apply_softmax) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_red[w];
+    lse_shift = m;
+    logsum = logf(t);
   }
   if (logp_out != nullptr) {
     for (int i = threadIdx.x; i < V; i += 256) logp_out[row * V + i] = (s_row[i] - lse_shift) - logsum;
   }
-  // top-k by k rounds of block arg-max over per-thread running maxima (ties -> lowest index): only the thread that
-  // owned the winner rescans its ~V/256 elements, one barrier per round.  Values reported as log-probs.
+  const int nc = s_ncand;
+  if (filter_ok && nc >= k && nc <= TOPK_CAP) {
+    if (warp == 0) {
+      for (int c = lane; c < nc; c += 32) {
+        const ArgMax a = s_cand[c];
+        int rank = 0;
+        for (int o = 0; o < nc; ++o) {
+          const ArgMax h = s_cand[o];
+          rank += (h.v > a.v || (h.v == a.v && h.i < a.i)) ? 1 : 0;
+        }
+        if (rank < k) {
+          topk_val[row * k + rank] = (a.v - lse_shift) - logsum;
+          topk_idx[row * k + rank] = a.i;
+        }
+      }
+    }
+    return;
+  }
+  // fallback: k rounds of block arg-max over per-thread running maxima (ties -> lowest index); only the thread that
+  // owned the winner rescans its ~V/256 elements, one barrier per round
   auto local_best = [&]() {
     ArgMax a;
     a.v = -INFINITY;
     a.i = 0x7fffffff;
     for (int i = threadIdx.x; i < V; i += 256) {
-      ArgMax b;
-      b.v = s_row[i];
-      b.i = i;
-      a = better(a, b);
+      ArgMax e;
+      e.v = s_row[i];
+      e.i = i;
+      a = better(a, e);
     }
     return a;
   };
-  ArgMax mine = local_best();
   for (int r = 0; r < k; ++r) {
     ArgMax a = warp_argmax(mine);
     if (lane == 0) s_arg[r & 1][warp] = a;
