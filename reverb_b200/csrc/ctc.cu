@@ -500,14 +500,22 @@ ctc_prefix_beam_kernel(const float* __restrict__ topk_val, const int* __restrict
       if (key == PB_KEY_NONE) continue;
       const double sc = slot_score[a];
       // dead slots carry (score -inf, key INT_MAX): they never count, so the loop needs no liveness branch
-      int rank = 0;
-#pragma unroll 4
-      for (int o = 0; o < nslots; ++o) {
-        const double so = slot_score[o];
-        const int ko = slot_key[o];
-        rank += (so > sc) ? 1 : 0;
-        rank += (so == sc && ko < key) ? 1 : 0;
+      // four independent counters: the compare -> add chains overlap instead of serialising on one register
+      int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+      int o = 0;
+      for (; o + 4 <= nslots; o += 4) {
+        const double s0 = slot_score[o], s1 = slot_score[o + 1], s2 = slot_score[o + 2], s3 = slot_score[o + 3];
+        const int k0 = slot_key[o], k1 = slot_key[o + 1], k2 = slot_key[o + 2], k3 = slot_key[o + 3];
+        r0 += (int)((s0 > sc) | ((s0 == sc) & (k0 < key)));
+        r1 += (int)((s1 > sc) | ((s1 == sc) & (k1 < key)));
+        r2 += (int)((s2 > sc) | ((s2 == sc) & (k2 < key)));
+        r3 += (int)((s3 > sc) | ((s3 == sc) & (k3 < key)));
       }
+      for (; o < nslots; ++o) {
+        const double so = slot_score[o];
+        r0 += (int)((so > sc) | ((so == sc) & (slot_key[o] < key)));
+      }
+      const int rank = (r0 + r1) + (r2 + r3);
       if (rank >= nnew) continue;
       const PBSlot& s = slots[a];
       int node;

@@ -1031,7 +1031,14 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.row_lens = a.row_lens;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
   p.conv_mode = a.conv_mode;
-  p.epi_warps = (a.K <= 2048) ? 8 : 4;
+  {
+    static int forced = -1;  // RVB_GEMM_EPI_WARPS=4|8 overrides the K-based choice (tuning aid)
+    if (forced < 0) {
+      const char* e = getenv("RVB_GEMM_EPI_WARPS");
+      forced = (e && (atoi(e) == 4 || atoi(e) == 8)) ? atoi(e) : 0;
+    }
+    p.epi_warps = forced ? forced : ((a.K <= 2048) ? 8 : 4);
+  }
   p.bf16_coalesced = (a.out_mode == OUT_BF16) && (a.act != ACT_GLU) && (p.ldo % 8 == 0) &&
                      ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
                      (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
