@@ -125,11 +125,11 @@ def host_threads() -> int:
 
 def pick_threads(orc) -> int:
     """torch CPU throughput is not monotone in the thread count (a 128-way split of a 748-row GEMM thrashes):
-    probe the encoder on a 3 s chunk with a few counts and keep the fastest — 'all the threads it can USE'."""
+    probe the encoder on a 10 s chunk with a few counts and keep the fastest — 'all the threads it can USE'."""
     avail = host_threads()
-    cands = sorted({c for c in (avail, 32, 16) if 1 <= c <= avail}, reverse=True)
-    feats = torch.randn(1, 150, 80) * 3 + 10
-    lens = torch.tensor([150], dtype=torch.int32)
+    cands = sorted({c for c in (avail, 64, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
+    feats = torch.randn(1, 998, 80) * 3 + 10
+    lens = torch.tensor([998], dtype=torch.int32)
     cat = torch.tensor([1.0, 0.0])
     best, best_t = cands[-1], float("inf")
     for c in cands:
