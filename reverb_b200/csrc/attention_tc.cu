@@ -65,13 +65,18 @@ struct AttnTcParams {
   float scale_log2;
 };
 
-// Pipeline (5 warps per CTA):
-//   control thread (warp 4, lane 0): TMA loads (Q, K'' x AT_KST stages, V x2) and all tcgen05.mma issue; S has AT_NS
+// Pipeline (SW softmax warps + 1 control warp per CTA):
+//   control thread (warp SW, lane 0): TMA loads (Q, K'' x AT_KST stages, V x2) and all tcgen05.mma issue; S has AT_NS
 //     buffers in TMEM so QK(i+AT_NS) is queued while the softmax warps consume S(i); P~ is double-buffered in shared
 //     memory so PV(j) runs while P~(j+1) is produced.
-//   softmax warps 0..3 (thread = query row): tile max, lazy running-max update, exp2 / row sum / P~.
-template <int BN>
-__global__ void __launch_bounds__(160, AtCfg<BN>::CTAS_PER_SM)
+//   softmax warps (thread = query row): tile max, lazy running-max update, exp2 / row sum / P~.
+//     SW = 4 (default): one thread per row.  SW = 8 (RVB_ATTN_SW=8): warps w and w+4 share the 32 rows of TMEM lane quarter w%4 and
+//     each takes half of the tile's columns (and half of the O columns in the rescale / epilogue); the two partial
+//     tile maxima / row sums meet through shared memory and a 64-thread named barrier.  Measured slightly SLOWER than
+//     SW = 4 (0.403 vs 0.388 ms per encoder layer): the kernel is not short of warps; what bounds it is the
+//     ex2 + issue budget per tile and the per-tile hand-offs, which the split duplicates.
+template <int BN, int SW>
+__global__ void __launch_bounds__(32 * (SW + 1), AtCfg<BN>::CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -98,7 +103,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* o_done = p_empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
   static_assert(1 + 2 * AT_KST + 4 + 2 * AT_NS + 4 + 1 + 1 <= 32, "barrier block is 256 bytes");
-  float* s_bias = reinterpret_cast<float*>(bars + 32);  // [ntiles * 128]: key bias * scale*log2e, -inf when masked
+  constexpr bool SPLIT = (SW == 8);
+  constexpr int CW = BN * 4 / SW;   // S columns per thread and tile
+  constexpr int OW = AT_DK * 4 / SW;  // O columns per thread (rescale, epilogue)
+  static_assert(SW == 4 || (SW == 8 && BN == 64), "8 softmax warps are built for 64-key tiles");
+  float* s_xch = reinterpret_cast<float*>(bars + 32);   // SPLIT: [2 tile parity][2 halves][128 rows] partial tile maxima
+  float* s_sumx = s_xch + 512;                          // SPLIT: [2 halves][128 rows] partial row sums
+  float* s_bias = SPLIT ? s_sumx + 256 : s_xch;         // [ntiles * BN]: key bias * scale*log2e, -inf when masked
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qtile = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
@@ -116,12 +127,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int i = 0; i < AT_NS; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 4);
+      mbar_init(&s_empty[i], SW);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&v_full[i], 1);
       mbar_init(&v_empty[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], SW);
       mbar_init(&p_empty[i], 1);
     }
     mbar_init(o_done, 1);
@@ -130,13 +141,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 4) {
+  if (warp == SW) {
     tmem_alloc(tmem_ptr, AT_TMEM_COLS);
     tmem_relinquish();
   } else {
     // key bias row of this (group, head), pre-scaled; masked keys -> -inf
     const float* kb = p.key_bias ? p.key_bias + ((long long)g * p.H + h) * p.Tk : nullptr;
-    for (int key = threadIdx.x; key < ntiles * AT_BN; key += 128)
+    for (int key = threadIdx.x; key < ntiles * AT_BN; key += 32 * SW)
       s_bias[key] = (key < klen) ? (kb ? __ldg(kb + key) * p.scale_log2 : 0.f) : -INFINITY;
   }
   tc_fence_before();
@@ -146,7 +157,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_o = tmem_base + 2 * AT_BN;
   auto s_col = [&](int sb) -> uint32_t { return tmem_base + (sb < 2 ? sb * AT_BN : 2 * AT_BN + 64); };
 
-  if (warp == 4) {
+  if (warp == SW) {
     if (lane == 0 && ntiles > 0) {
       // ------------------------------------------------------------ TMA + MMA control thread
       // instruction descriptors: D=f32, A=B=bf16.  QK: N=128, both K-major.  PV: N=64, B (V) MN-major (bit 16).
@@ -219,28 +230,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
     }
   } else {
-    // ---------------------------------------------------------------- softmax warps: thread = query row
-    const int r = warp * 32 + lane;
-    const uint32_t lane_addr = ((uint32_t)(warp * 32) << 16);
+    // ---------------------------------------------------------------- softmax warps: thread = query row (x column half)
+    const int wq = warp & 3, hh = warp >> 2;   // TMEM lane quarter; column half (always 0 when SW == 4)
+    const int r = wq * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(wq * 32) << 16);
+    const int c0 = hh * CW, ob = hh * OW;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory"); };
     float m_run = 0.f, row_sum = 0.f;
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j % AT_NS, pb = j & 1;
       mbar_wait(&s_full[sb], (j / AT_NS) & 1);
       tc_fence_after();
-      // the whole S row is pulled out of TMEM with back-to-back loads and ONE wait, so the TMEM latency is paid once
-      // per tile and the S buffer is handed back to the MMA issuer as early as possible
-      uint32_t sv[AT_BN];
+      // the thread's part of the S row is pulled out of TMEM with back-to-back loads and ONE wait, so the TMEM latency
+      // is paid once per tile and the S buffer is handed back to the MMA issuer as early as possible
+      uint32_t sv[CW];
 #pragma unroll
-      for (int c = 0; c < AT_BN; c += 32) tmem_ld_32x32(s_col(sb) + lane_addr + c, sv + c);
+      for (int c = 0; c < CW; c += 32) tmem_ld_32x32(s_col(sb) + lane_addr + c0 + c, sv + c);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
-      const uint32_t bias_addr = smem_u32(s_bias + j * AT_BN);
+      const uint32_t bias_addr = smem_u32(s_bias + j * AT_BN + c0);
       // x = s * scale*log2e + key bias (masked keys: -inf), kept in place of the raw scores; tile maximum
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
 #pragma unroll
-      for (int e = 0; e < AT_BN; e += 4) {
+      for (int e = 0; e < CW; e += 4) {
         const float4 b4 = lds128(bias_addr + e * 4);
         const float x0 = fmaf(__uint_as_float(sv[e + 0]), p.scale_log2, b4.x);
         const float x1 = fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, b4.y);
@@ -256,16 +270,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mx[3] = fmaxf(mx[3], x3);
       }
       float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      if (p.causal && j * AT_BN + AT_BN - 1 > q0 + warp * 32) {
+      if (p.causal && j * AT_BN + c0 + CW - 1 > q0 + wq * 32) {
         // diagonal tile (warp-uniform test): hide the keys after this row's position and redo the tile maximum
-        const int lim = q0 + r - j * AT_BN;  // last visible key of the tile for this row
+        const int lim = q0 + r - j * AT_BN - c0;  // last visible column of this thread's part
         tmax = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < AT_BN; ++e) {
+        for (int e = 0; e < CW; ++e) {
           const float x = (e <= lim) ? __uint_as_float(sv[e]) : -INFINITY;
           sv[e] = __float_as_uint(x);
           tmax = fmaxf(tmax, x);
         }
+      }
+      if (SPLIT) {  // the row's tile maximum = max of the two halves (both halves must move m_run identically)
+        s_xch[(j & 1) * 256 + hh * 128 + r] = tmax;
+        pair_sync();
+        tmax = fmaxf(tmax, s_xch[(j & 1) * 256 + (hh ^ 1) * 128 + r]);
       }
       if (j == 0) {
         m_run = (tmax == -INFINITY) ? 0.f : tmax;  // PV(0) overwrites O: nothing to rescale
@@ -273,7 +292,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const bool raise = tmax > m_run + 8.f;
         if (__any_sync(0xffffffffu, raise)) {
           // Lazy rescale (rare): O and the row sum move to the new maximum.  The last product issued, PV(j-1), must
-          // have retired before O is touched; PV(j) is not issued before this warp arrives on p_full(j) below.
+          // have retired before O is touched; PV(j) is not issued before every softmax warp arrives on p_full(j).
           mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
           tc_fence_after();
           const float m_new = raise ? tmax : m_run;
@@ -281,7 +300,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           m_run = m_new;
           row_sum *= f;
 #pragma unroll 1
-          for (int c = 0; c < AT_DK; c += 32) {
+          for (int c = ob; c < ob + OW; c += 32) {
             uint32_t ov[32];
             tmem_ld_32x32(tmem_o + lane_addr + c, ov);
             tmem_ld_wait();
@@ -294,9 +313,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       float sm[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[AT_BN / 2];
+      uint32_t pk[CW / 2];
 #pragma unroll
-      for (int e = 0; e < AT_BN; e += 4) {
+      for (int e = 0; e < CW; e += 4) {
         const float p0 = fast_exp2(__uint_as_float(sv[e + 0]) - m_run);
         const float p1 = fast_exp2(__uint_as_float(sv[e + 1]) - m_run);
         const float p2 = fast_exp2(__uint_as_float(sv[e + 2]) - m_run);
@@ -312,10 +331,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // the P~ buffer is only needed now: PV(j-2), which read it last, has had a whole tile of exponentials to retire
       mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
 #pragma unroll
-      for (int c = 0; c < AT_BN; c += 32) {
-        // 32 keys = four 16-byte chunks of this row inside K-block (c / 64); SWIZZLE_128B: chunk ^= row % 8
-        uint8_t* blk = sP + pb * AT_P_BYTES + (c >> 6) * AT_Q_BYTES + r * 128;
-        const int ch0 = (c & 63) >> 3;
+      for (int c = 0; c < CW; c += 32) {
+        // 32 keys = four 16-byte chunks of this row inside K-block (key / 64); SWIZZLE_128B: chunk ^= row % 8
+        const int kc = c0 + c;
+        uint8_t* blk = sP + pb * AT_P_BYTES + (kc >> 6) * AT_Q_BYTES + r * 128;
+        const int ch0 = (kc & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int ch = (ch0 + q) ^ (r & 7);
@@ -328,6 +348,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) mbar_arrive(&p_full[pb]);
     }
     // ---- epilogue: O / row_sum -> bf16 -> global
+    if (SPLIT) {
+      s_sumx[hh * 128 + r] = row_sum;
+      pair_sync();
+      row_sum += s_sumx[(hh ^ 1) * 128 + r];
+    }
     const int row = q0 + r;
     if (ntiles > 0) {
       mbar_wait(o_done, 0);
@@ -336,7 +361,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float inv = row_sum > 0.f ? 1.f / row_sum : 0.f;
     bf16* orow = p.out + ((long long)g * p.Tq + row) * p.ldo + h * AT_DK;
 #pragma unroll 1
-    for (int c = 0; c < AT_DK; c += 32) {
+    for (int c = ob; c < ob + OW; c += 32) {
       uint32_t ov[32];
       if (ntiles > 0) {
         tmem_ld_32x32(tmem_o + lane_addr + c, ov);
@@ -360,7 +385,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == SW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, AT_TMEM_COLS);
   }
@@ -512,24 +537,38 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
   if (tmap_2d(&tmK, a.k, (long long)a.H * AT_DK, (long long)a.groups * a.Tk, a.ldk, bn_sel)) return -1;
   if (tmap_2d(&tmV, a.v, (long long)a.H * AT_DK, (long long)a.groups * a.Tk, a.ldv, bn_sel)) return -1;
   dim3 grid((a.Tq + AT_BM - 1) / AT_BM, a.H, a.groups);
+  static int sw_sel = 0;
+  if (sw_sel == 0) {
+    const char* e = getenv("RVB_ATTN_SW");
+    sw_sel = (e && atoi(e) == 8) ? 8 : 4;  // measured: 4 warps 0.388 ms / encoder layer, 8 warps 0.403 ms
+  }
   if (bn_sel == 128) {
     const size_t smem = AtCfg<128>::SMEM_FIXED + (size_t)((a.Tk + 127) / 128) * 128 * sizeof(float);
     RVB_REQUIRE(smem <= 227 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
     static size_t configured = 0;
     if (smem > configured) {
-      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    attention_tc_kernel<128><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
-  } else {
+    attention_tc_kernel<128, 4><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else if (sw_sel == 4) {
     const size_t smem = AtCfg<64>::SMEM_FIXED + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
     RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
     static size_t configured = 0;
     if (smem > configured) {
-      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
     }
-    attention_tc_kernel<64><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    attention_tc_kernel<64, 4><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+  } else {
+    const size_t smem = AtCfg<64>::SMEM_FIXED + 3072 + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
+    RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
+    static size_t configured = 0;
+    if (smem > configured) {
+      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    attention_tc_kernel<64, 8><<<grid, 288, smem, stream>>>(tmQ, tmK, tmV, p);
   }
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
