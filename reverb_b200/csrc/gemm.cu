@@ -9,12 +9,21 @@
 // straight out of the channels-last conv1 activation by 4-D TMA boxes (no im2col buffer).
 //
 // Structure per CTA (320 threads, 1 CTA / SM, grid = #SMs, static round-robin tile scheduler):
-//   warp 0 / lane 0 : TMA producer   — fills a STAGES-deep ring of {A 128x64, W BNx64} bf16 tiles (SWIZZLE_128B)
-//   warp 1 / lane 0 : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x 4 per stage;
-//                                       tcgen05.commit frees smem stages and publishes finished accumulators
+//   warp 0 / lane 0 : TMA producer   — fills a STAGES-deep ring of {A 128x64, W tile} bf16 tiles (SWIZZLE_128B)
+//   warp 1 / lane 0 : MMA issuer     — tcgen05.mma kind::f16, K=16 x 4 per stage; tcgen05.commit frees smem stages and
+//                                       publishes finished accumulators
 //   warps 2..9      : epilogue       — tcgen05.ld 32x32b from a double-buffered TMEM accumulator (2 x BN columns),
-//                                       bias / ReLU / SiLU / residual(+row mask) fused, vectorised global stores
+//                                       bias / ReLU / SiLU / GLU / residual(+row mask) fused; outputs pass through a
+//                                       warp-private XOR-swizzled staging tile so global accesses are coalesced
 // so tile i's epilogue overlaps tile i+1's main loop.
+//   gemm_tc2_kernel (default): a CLUSTER of two CTAs works on a 256 x BN tile with tcgen05.mma.cta_group::2 — each
+//     CTA loads its own 128 A rows and HALF of the W tile, the leader CTA issues the MMAs for both, commits are
+//     multicast to both CTAs' barriers; both CTAs run epilogue warps on their own 128 accumulator rows.
+//   gemm_tc_kernel (RVB_GEMM=tc1): the single-CTA version, M = 128 per tile.
+// Tuning aids (environment, read once): RVB_GEMM_EPI_WARPS=4|8, RVB_GEMM_SKIP_EPI=1|2|3 (main loop only / no global
+// stores / TMEM loads + math only — results are wrong by construction; tools/gemm_bench.py).  Measured on the FFN-w1
+// shape (M=47872, N=4096, K=1024, bf16+SiLU): main loop alone 1696 TFLOP/s, + TMEM loads and math 1548, + staging
+// 1416, + global stores 1353 (cuBLAS without activation: 1450).
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -48,6 +57,7 @@ struct GemmKParams {
   const int* row_lens;
   int rows_per_batch;
   int conv_mode, conv_T2, conv_F2, conv_tt, conv_cblocks;
+  int debug_skip_epi;  // RVB_GEMM_SKIP_EPI=1 (tuning aid): epilogue warps only hand the accumulator back, no stores
   int bf16_coalesced;  // bf16 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
   int f32_coalesced;  // fp32 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
   int epi_warps;  // 4 or 8 epilogue warps drain a tile (8: short-K, epilogue-bound shapes; 4: long-K, MMA-bound)
@@ -250,6 +260,11 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
                                            int c0, int c1, uint64_t* tfull_bar, uint32_t aphase, float* stage) {
   const long long orow = output_row(p, t, q * 32 + lane);
   const int n0_tile = t.n0;
+  if (p.debug_skip_epi == 1) {  // main-loop-only timing: wrong results by construction (2: everything but the stores)
+    mbar_wait(tfull_bar, aphase);
+    tc_fence_after();
+    return;
+  }
   if constexpr (EPI == EPI_GLU) {
     mbar_wait(tfull_bar, aphase);
     tc_fence_after();
@@ -304,16 +319,18 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fast_silu(v[e]);
           }
+          if (p.debug_skip_epi == 3 && v[0] != 123.456f) continue;  // tuning aid: TMEM loads + math only
           *reinterpret_cast<uint4*>(stage_u + lane * 32 + ((j ^ (lane & 7)) << 2)) =
               make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
                          pack_bf16x2(v[6], v[7]));
         }
+        if (p.debug_skip_epi == 3) continue;
         __syncwarp();
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + rsub;
           const uint4 u = *reinterpret_cast<const uint4*>(stage_u + row * 32 + ((slot ^ (row & 7)) << 2));
-          if (ro[it] >= 0) *reinterpret_cast<uint4*>(out + ro[it] + c) = u;
+          if (ro[it] >= 0 && p.debug_skip_epi != 2) *reinterpret_cast<uint4*>(out + ro[it] + c) = u;
         }
         __syncwarp();
       } else {
@@ -1038,6 +1055,12 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
       forced = (e && (atoi(e) == 4 || atoi(e) == 8)) ? atoi(e) : 0;
     }
     p.epi_warps = forced ? forced : ((a.K <= 2048) ? 8 : 4);
+    static int skip = -1;
+    if (skip < 0) {
+      const char* e = getenv("RVB_GEMM_SKIP_EPI");
+      skip = e ? atoi(e) : 0;
+    }
+    p.debug_skip_epi = skip;
   }
   p.bf16_coalesced = (a.out_mode == OUT_BF16) && (a.act != ACT_GLU) && (p.ldo % 8 == 0) &&
                      ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
