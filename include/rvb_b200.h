@@ -79,6 +79,11 @@ RVB_API int rvb_encoder_out_frames(int T);
 RVB_API int rvb_encoder_out_len(int feat_len, int T);
 
 /* ---- hot path ----------------------------------------------------------------------------------------------- */
+/* Sample-rate conversion (torchaudio.transforms.Resample as called at cli/reverb.py:125-128): orig / new_ are the two
+ * rates divided by their gcd, d_kernel the (new_, 2*width + orig) fp32 polyphase windowed-sinc table
+ * (reverb_b200/resample.py builds it the way torchaudio does), n_out = ceil(new_ * n_in / orig). */
+RVB_API int rvb_resample(const void* d_wave, int is_i16, long long n_in, const float* d_kernel, int orig, int new_, int width,
+                         float* d_out, long long n_out, void* stream);
 /* number of fbank frames for n_samples (snip_edges): 0 if n < 400 else 1 + (n - 400) / 160 */
 RVB_API long long rvb_fbank_num_frames(long long n_samples);
 RVB_API int rvb_fbank_f32(const float* d_wave, long long n_samples, float* d_feats, long long n_frames, void* stream);

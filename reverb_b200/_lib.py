@@ -45,6 +45,7 @@ SIGNATURES = {
     "rvb_ctc_topk": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
     "rvb_logp_topk": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "rvb_ctc_greedy_search": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rvb_resample": (_i, [_vp, _i, _ll, _vp, _i, _i, _i, _vp, _ll, _vp]),
     "rvb_ctc_prefix_beam_search": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rvb_beam_search_rescoring": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _vp, _vp, _vp]),

@@ -1193,6 +1193,12 @@ RVB_API int rvb_encoder_forward(rvb_model* m, const float* d_feats, const int* h
                               (cudaStream_t)stream);
 }
 
+RVB_API int rvb_resample(const void* d_wave, int is_i16, long long n_in, const float* d_kernel, int orig, int new_, int width,
+                         float* d_out, long long n_out, void* stream) {
+  RVB_REQUIRE(d_wave && d_kernel && d_out && n_in >= 0, "rvb_resample: bad arguments");
+  return rvb::launch_resample(d_wave, is_i16, n_in, d_kernel, orig, new_, width, d_out, n_out, (cudaStream_t)stream);
+}
+
 RVB_API int rvb_ctc_topk(rvb_model* m, const float* d_enc_out, int B, int Tp, int k, float blank_penalty, int blank_id,
                  float* d_topk_val, int* d_topk_idx, float* d_logp, void* stream) {
   RVB_REQUIRE(m && m->finalized && d_enc_out && d_topk_val && d_topk_idx && B > 0 && Tp > 0, "rvb_ctc_topk: bad arguments");

@@ -50,6 +50,9 @@ void gemm_profile_begin();
 int gemm_profile_end(double* total_ms, double* total_flops, long long* launches);
 
 // ------------------------------------------------------------------ fbank (fbank.cu)
+// polyphase sinc resampling (torchaudio.transforms.Resample semantics; table from reverb_b200/resample.py), resample.cu
+int launch_resample(const void* x, int is_i16, long long n_in, const float* kern /*(new, 2*width+orig)*/, int orig, int new_,
+                    int width, float* y, long long n_out, cudaStream_t stream);
 int launch_fbank(const float* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream);
 // int16 PCM input variant (the host API's H2D format)
 int launch_fbank_i16(const short* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream);

@@ -139,6 +139,27 @@ class Engine:
                 raise TypeError(f"fbank: unsupported dtype {wave.dtype}")
         return feats
 
+    def resample(self, wave: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
+        """(N,) float32 or int16 on the device -> (ceil(N * new / orig),) float32: torchaudio.transforms.Resample
+        semantics (cli/reverb.py:125-128) with the convolution on the GPU."""
+        from .resample import resampled_length, sinc_resample_kernel
+        assert wave.is_cuda and wave.dim() == 1 and wave.stride(0) == 1
+        if wave.dtype not in (torch.int16, torch.float32):
+            raise TypeError(f"resample: unsupported dtype {wave.dtype}")
+        kern, orig, new, width = sinc_resample_kernel(int(orig_freq), int(new_freq))
+        key = (int(orig_freq), int(new_freq))
+        if not hasattr(self, "_resample_tables"):
+            self._resample_tables = {}
+        if key not in self._resample_tables:
+            self._resample_tables[key] = torch.from_numpy(kern).to(self.device)
+        n_in = wave.shape[0]
+        n_out = resampled_length(n_in, orig, new)
+        out = torch.empty(n_out, dtype=torch.float32, device=wave.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_resample(_ptr(wave), int(wave.dtype == torch.int16), n_in, _ptr(self._resample_tables[key]),
+                                        orig, new, width, _ptr(out), n_out, self._stream()), "rvb_resample")
+        return out
+
     def fbank_batch(self, waves: torch.Tensor) -> torch.Tensor:
         """(B, N) equal-length recordings (float32 or int16, on the device) -> (B, m, 80) float32, one launch."""
         assert waves.is_cuda and waves.dim() == 2 and waves.stride(1) == 1

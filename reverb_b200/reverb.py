@@ -5,8 +5,9 @@ behaviour), running on the native B200 engine.
 Differences that are deliberate and documented in DESIGN.md:
   * the model always runs on a CUDA device (`gpu < 0` selects the current device; there
     is no CPU path), whereas the reference's `load_model()` is CPU-only (reverb.py:354-357);
-  * audio is read with the standard-library `wave` module (16-bit PCM); resampling is
-    done with torchaudio when the file is not 16 kHz, like the reference.
+  * audio is read with the standard-library `wave` module (16-bit PCM); a file that is not
+    16 kHz is resampled on the GPU with torchaudio.transforms.Resample's algorithm
+    (csrc/resample.cu + resample.py), where the reference calls torchaudio on the CPU.
 """
 from __future__ import annotations
 
@@ -111,13 +112,10 @@ class ReverbASR:
             raise NotImplementedError("reverb_b200 fbank kernel is built for 80 bins / 25 ms / 10 ms / no dither @16 kHz")
         pcm, sample_rate = _read_wav(audio_file)
         logging.info(f"detected sample rate: {sample_rate}")
+        wave_dev = torch.from_numpy(np.array(pcm[0], copy=True)).pin_memory().to(self.device, non_blocking=True)
         if sample_rate != resample_rate:
-            import torchaudio
-            wav = torchaudio.transforms.Resample(orig_freq=sample_rate, new_freq=resample_rate)(
-                torch.from_numpy(pcm).to(torch.float))
-            wave_dev = wav[0].contiguous().to(self.device)
-        else:
-            wave_dev = torch.from_numpy(np.array(pcm[0], copy=True)).pin_memory().to(self.device, non_blocking=True)
+            # torchaudio.transforms.Resample on channel 0 (the reference resamples every channel, then keeps the first)
+            wave_dev = self.engine.resample(wave_dev, sample_rate, resample_rate)
         if wave_dev.numel() < 400:
             raise AssertionError(f"choose a window size 400 that is [2, {wave_dev.numel()}]")  # torchaudio's check
         return self.engine.fbank(wave_dev).unsqueeze(0)

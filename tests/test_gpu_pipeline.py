@@ -284,6 +284,22 @@ def test_transcribe_api_surface(asr, golden_cases, model_dirs, case):
         m.transcribe(wav, mode="joint_decoding")
 
 
+def test_compute_feats_resamples_non_16k_audio_on_the_gpu(asr, model_dirs, tmp_path):
+    """cli/reverb.py:120-138: a WAV at another rate is resampled to 16 kHz (torchaudio Resample semantics) before
+    fbank; here both steps run on the GPU and must agree with the oracle chain resample_ref -> fbank_np."""
+    from oracle import fbank_np, resample_ref
+    from reverb_b200 import synth
+    m = asr["causal_ln"]
+    for rate in (8000, 44100):
+        pcm = synth.synth_audio(1.3, seed=31)[: int(1.3 * rate)]
+        wav = synth.write_wav(str(tmp_path / f"r{rate}.wav"), pcm, sample_rate=rate)
+        feats = m.compute_feats(wav, num_mel_bins=80, frame_length=25, frame_shift=10)
+        want_wave = resample_ref.resample(torch.from_numpy(pcm.astype(np.float32)).unsqueeze(0), rate, 16000)[0].numpy()
+        want = fbank_np.fbank(want_wave)
+        assert tuple(feats.shape) == (1,) + want.shape
+        np.testing.assert_allclose(feats[0].cpu().numpy(), want, rtol=0, atol=5e-3)
+
+
 def test_launch_counter_and_no_cpu_path():
     from reverb_b200.engine import launch_count
     assert launch_count() > 0

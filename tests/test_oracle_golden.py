@@ -72,6 +72,33 @@ def test_oracle_attention_mode_vs_reference_golden(golden_cases, model_dirs, cas
             assert [list(r.tokens) for r in out["attention"]] == gold[f"length_penalty_{lp}"][bi]
 
 
+def _resample_cases():
+    gold = dict(np.load("tests/golden/resample.npz"))
+    for key, ref in gold.items():
+        rate = int(key.split("_")[0][1:])
+        n = int(key.split("_")[1][1:])
+        seed = int(key.split("seed")[1])
+        yield rate, n, seed, ref
+
+
+def test_resample_oracle_and_host_table_vs_torchaudio_golden():
+    """Resampling front-end (cli/reverb.py:125-128): the oracle's restatement reproduces torchaudio's output bit for
+    bit; the product's numpy filter table (reverb_b200/resample.py, the only host math of the GPU resampler) equals
+    the oracle's to float32 round-off."""
+    from oracle import resample_ref
+    from reverb_b200 import synth
+    from reverb_b200.resample import resampled_length, sinc_resample_kernel
+    for rate, n, seed, ref in _resample_cases():
+        pcm = synth.synth_audio(n / 16000.0 + 1e-9, seed=seed)[:n]
+        got = resample_ref.resample(torch.from_numpy(pcm.astype(np.float32)).unsqueeze(0), rate, 16000)[0].numpy()
+        np.testing.assert_array_equal(got, ref)
+        kern_o, orig_o, new_o, width_o = resample_ref.sinc_resample_kernel(rate, 16000)
+        kern, orig, new, width = sinc_resample_kernel(rate, 16000)
+        assert (orig, new, width) == (orig_o, new_o, width_o) and kern.shape == tuple(kern_o.shape[::2])
+        np.testing.assert_allclose(kern, kern_o[:, 0].numpy(), rtol=0, atol=2e-7)
+        assert resampled_length(n, orig, new) == ref.shape[0]
+
+
 def test_log_add_and_collapse_known_answers():
     from oracle import search_ref
     inf = float("inf")
