@@ -4,8 +4,9 @@
  * with ctypes to replace, one for one, the operator-level calls of the reference's hot path:
  *
  *   rvb_fbank_*                 <- torchaudio.compliance.kaldi.fbank call   asr/wenet/cli/reverb.py:130-138
- *   rvb_encoder_forward         <- ASRModel._forward_encoder                asr/wenet/transformer/asr_model.py:288-316
- *                                  (BaseEncoder.forward, transformer/encoder.py:117-149)
+ *   rvb_resample                <- torchaudio.transforms.Resample call      asr/wenet/cli/reverb.py:125-128
+ *   rvb_encoder_forward[_chunked] <- ASRModel._forward_encoder              asr/wenet/transformer/asr_model.py:288-316
+ *                                  (BaseEncoder.forward, transformer/encoder.py:117-149; chunk masks utils/mask.py:88-197)
  *   rvb_ctc_topk                <- ASRModel.ctc_logprobs + logp.topk        asr_model.py:318-329, search.py:111,155
  *   rvb_ctc_greedy_search       <- ctc_greedy_search                        transformer/search.py:106-121
  *   rvb_ctc_prefix_beam_search  <- ctc_prefix_beam_search                   transformer/search.py:124-248
@@ -97,6 +98,12 @@ RVB_API int rvb_fbank_batch(const void* d_wave, int is_i16, int batch, long long
  * num_langs == 0. */
 RVB_API int rvb_encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
                         const float* h_cat_embs, int n_cat, float* d_enc_out, int* h_enc_lens, void* stream);
+/* Same with bounded attention context — BaseEncoder.forward with decoding_chunk_size > 0 (encoder.py:117-149,
+ * add_optional_chunk_mask / subsequent_chunk_mask, utils/mask.py:88-197): encoder frame i attends the keys of its own
+ * chunk and of num_left_chunks chunks before it (all previous ones when < 0), chunk_size in encoder frames. */
+RVB_API int rvb_encoder_forward_chunked(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
+                                        const float* h_cat_embs, int n_cat, int chunk_size, int num_left_chunks,
+                                        float* d_enc_out, int* h_enc_lens, void* stream);
 
 /* CTC head: logits = ctc_lo(enc_out) (blank_penalty subtracted from the blank column), log_softmax, top-k.
  * d_topk_val/d_topk_idx: (B*Tp, k) sorted descending; d_logp (B*Tp, vocab) optional (NULL to skip the write). */
@@ -163,6 +170,11 @@ RVB_API int rvb_attention(const void* d_q, const void* d_k, const void* d_v, con
 RVB_API int rvb_attention_tc(const void* d_q, const void* d_k, const void* d_v, void* d_out, int ldq, int ldk, int ldv,
                              int ldo, int groups, int Tq, int Tk, int H, int dk, const float* d_key_bias,
                              const int* d_k_lens, int causal, float scale, void* stream);
+/* same with the streaming chunk mask of utils/mask.py:88-123 (Tq == Tk): query i sees keys
+ * [max(0, (i/chunk - left_chunks) * chunk) (0 when left_chunks < 0), (i/chunk + 1) * chunk) */
+RVB_API int rvb_attention_tc_chunked(const void* d_q, const void* d_k, const void* d_v, void* d_out, int ldq, int ldk,
+                                     int ldv, int ldo, int groups, int Tq, int Tk, int H, int dk, const float* d_key_bias,
+                                     const int* d_k_lens, int chunk, int left_chunks, float scale, void* stream);
 /* K'' = k + pos (bf16) and cbias[b,h,t] = u_h.k + v_h.pos for the folded rel-pos attention */
 RVB_API int rvb_relpos_prep(const void* d_k, int ldk, const void* d_pos, int ldp, const float* d_bias_u,
                             const float* d_bias_v, void* d_kpp, float* d_cbias, int B, int T, int H, int dk,

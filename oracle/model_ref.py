@@ -193,16 +193,38 @@ def encoder_block(x, mask, pos_emb, mask_pad, sd: SD, p: str, cfg, cat_embs, lsl
     return _ln(x, sd, p + ".norm_final", 1e-5)
 
 
-def encoder_forward(feats, lens, sd: SD, cfg, cat_embs: Optional[torch.Tensor]):
-    """BaseEncoder.forward (transformer/encoder.py:117-149), full-context decode
-    (decoding_chunk_size=-1 => key-padding mask only, utils/mask.py:161-187).
-    Returns (encoder_out (B,T',d), encoder_lens (B,), masks (B,1,T'))."""
+def subsequent_chunk_mask(size: int, chunk_size: int, num_left_chunks: int = -1) -> torch.Tensor:
+    """utils/mask.py:88-123."""
+    ret = torch.zeros(size, size, dtype=torch.bool)
+    for i in range(size):
+        start = 0 if num_left_chunks < 0 else max((i // chunk_size - num_left_chunks) * chunk_size, 0)
+        ending = min((i // chunk_size + 1) * chunk_size, size)
+        ret[i, start:ending] = True
+    return ret
+
+
+def encoder_forward(feats, lens, sd: SD, cfg, cat_embs: Optional[torch.Tensor], decoding_chunk_size: int = -1,
+                    num_decoding_left_chunks: int = -1):
+    """BaseEncoder.forward (transformer/encoder.py:117-149).  decoding_chunk_size < 0: full-context decode
+    (key-padding mask only, utils/mask.py:161-187); > 0: add_optional_chunk_mask's fixed chunk mask & pad mask for
+    the attention (utils/mask.py:126-197; use_dynamic_chunk configs, else static_chunk_size), the pad mask alone for
+    the convolution module.  Returns (encoder_out (B,T',d), encoder_lens (B,), masks (B,1,T'))."""
     x, pos_emb, masks = subsample4(feats, lens, sd)
+    ec = cfg["encoder_conf"]
+    att_masks = masks
+    chunk = left = -1
+    if ec.get("use_dynamic_chunk", False):
+        if decoding_chunk_size > 0:
+            chunk, left = decoding_chunk_size, num_decoding_left_chunks
+    elif ec.get("static_chunk_size", 0) > 0:
+        chunk, left = ec["static_chunk_size"], num_decoding_left_chunks
+    if chunk > 0:
+        att_masks = masks & subsequent_chunk_mask(x.shape[1], chunk, left).unsqueeze(0)
     L = cfg["encoder_conf"]["num_blocks"]
     has_lsl = bool(cfg["dataset_conf"].get("pass_cat_emb", False))
     for i in range(L):
         lsl = has_lsl and (i == 0 or i == L - 1)
-        x = encoder_block(x, masks, pos_emb, masks, sd, f"encoder.encoders.{i}", cfg, cat_embs, lsl)
+        x = encoder_block(x, att_masks, pos_emb, masks, sd, f"encoder.encoders.{i}", cfg, cat_embs, lsl)
     x = _ln(x, sd, "encoder.after_norm", 1e-5)
     return x, masks.squeeze(1).sum(1), masks
 

@@ -66,15 +66,17 @@ class OracleASR:
             yield fb.reshape(-1, chunk_size, feats.shape[2]), lens
 
     @torch.no_grad()
-    def forward_encoder(self, feats, lens, cat_embs):
-        return model_ref.encoder_forward(feats, lens, self.sd, self.cfg, cat_embs)
+    def forward_encoder(self, feats, lens, cat_embs, decoding_chunk_size: int = -1, num_decoding_left_chunks: int = -1):
+        return model_ref.encoder_forward(feats, lens, self.sd, self.cfg, cat_embs, decoding_chunk_size,
+                                         num_decoding_left_chunks)
 
     @torch.no_grad()
     def decode(self, methods: List[str], feats: torch.Tensor, lens: torch.Tensor, beam_size: int = 10,
                ctc_weight: float = 0.0, reverse_weight: float = 0.0, cat_embs=None,
-               blank_penalty: float = 0.0, return_intermediates: bool = False, length_penalty: float = 0.0) -> Dict:
+               blank_penalty: float = 0.0, return_intermediates: bool = False, length_penalty: float = 0.0,
+               decoding_chunk_size: int = -1, num_decoding_left_chunks: int = -1) -> Dict:
         """asr/wenet/transformer/asr_model.py:331-432 (attention / greedy / prefix / rescoring)."""
-        enc, enc_lens, _ = self.forward_encoder(feats, lens, cat_embs)
+        enc, enc_lens, _ = self.forward_encoder(feats, lens, cat_embs, decoding_chunk_size, num_decoding_left_chunks)
         ctc_probs = model_ref.ctc_logprobs(enc, self.sd, blank_penalty, self.blank_id)
         out = {}
         if "attention" in methods:

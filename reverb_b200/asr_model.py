@@ -48,10 +48,26 @@ class ASRModel:
         return self
 
     # -- pieces of decode(), exposed for tests / profiling ---------------------------------------
-    def _forward_encoder(self, speech: torch.Tensor, speech_lengths, cat_embs=None):
+    def attention_context(self, decoding_chunk_size: int, num_decoding_left_chunks: int):
+        """The (chunk, left) pair add_optional_chunk_mask (utils/mask.py:126-197) would apply for this model's
+        encoder_conf; (-1, -1) = full context."""
+        ec = self.configs.get("encoder_conf", {})
+        if ec.get("use_dynamic_chunk", False):
+            if decoding_chunk_size < 0:
+                return -1, -1
+            if decoding_chunk_size > 0:
+                return int(decoding_chunk_size), int(num_decoding_left_chunks)
+            raise AssertionError("decoding_chunk_size == 0 selects the random training chunks")   # asr_model.py:377
+        if ec.get("static_chunk_size", 0) > 0:
+            return int(ec["static_chunk_size"]), int(num_decoding_left_chunks)
+        return -1, -1
+
+    def _forward_encoder(self, speech: torch.Tensor, speech_lengths, cat_embs=None, decoding_chunk_size: int = -1,
+                         num_decoding_left_chunks: int = -1):
         """-> (encoder_out (B, T', d) fp32 cuda, encoder_lens np.int32 (B,))."""
         lens = speech_lengths.detach().cpu().numpy() if torch.is_tensor(speech_lengths) else np.asarray(speech_lengths)
-        return self.engine.forward_encoder(speech, lens, cat_embs)
+        chunk, left = self.attention_context(decoding_chunk_size, num_decoding_left_chunks)
+        return self.engine.forward_encoder(speech, lens, cat_embs, chunk, left)
 
     def ctc_logprobs(self, encoder_out: torch.Tensor, blank_penalty: float = 0.0, blank_id: int = 0) -> torch.Tensor:
         return self.engine.ctc_topk(encoder_out, 1, blank_penalty, blank_id, want_logp=True)[2]
@@ -65,8 +81,10 @@ class ASRModel:
                cv=None, cv_lengths=None) -> Dict[str, List[DecodeResult]]:
         assert speech.shape[0] == speech_lengths.shape[0]
         assert decoding_chunk_size != 0
-        if decoding_chunk_size > 0 or simulate_streaming:
-            raise NotImplementedError("reverb_b200: only full-context decoding (decoding_chunk_size < 0) is built")
+        if simulate_streaming and decoding_chunk_size > 0:
+            # encoder.forward_chunk_by_chunk (encoder.py:231-402): chunk-by-chunk with att / cnn caches
+            raise NotImplementedError("reverb_b200: simulate_streaming (cache-based chunk-by-chunk encoding) is not built; "
+                                      "decoding_chunk_size > 0 without it applies the same bounded attention context")
         if context_graph is not None:
             raise NotImplementedError("reverb_b200: context biasing is out of scope (SURVEY.md §2)")
         unknown = [m for m in methods if m not in SUPPORTED_METHODS]
@@ -75,7 +93,8 @@ class ASRModel:
         if not speech.is_cuda:
             speech = speech.to(self.engine.device, non_blocking=True)
         speech = speech.to(torch.float32)
-        encoder_out, encoder_lens = self._forward_encoder(speech, speech_lengths, cat_embs)
+        encoder_out, encoder_lens = self._forward_encoder(speech, speech_lengths, cat_embs, decoding_chunk_size,
+                                                          num_decoding_left_chunks)
         need_beam = "ctc_prefix_beam_search" in methods or "attention_rescoring" in methods
         k = beam_size if need_beam else 1
         topk_val, topk_idx, _ = self.engine.ctc_topk(encoder_out, k, blank_penalty, blank_id)

@@ -61,7 +61,9 @@ struct AttnTcParams {
   const float* key_bias;  // (groups_kv, H, Tk) fp32 or nullptr
   const int* k_lens;      // per kv group, or nullptr
   int Tq, Tk, H;
-  int causal;  // key j visible to query row i (position inside the group) iff j <= i
+  int chunk;   // > 0: chunk mask (utils/mask.py subsequent_chunk_mask): key j visible to query row i iff
+               //      max(0, (i/chunk - left) * chunk) [0 when left < 0] <= j < (i/chunk + 1) * chunk; chunk 1 = causal
+  int left;    // number of left chunks, < 0 = all
   float scale_log2;
 };
 
@@ -116,8 +118,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int q0 = qtile * AT_BM;
   int klen = p.Tk;
   if (p.k_lens) klen = min(klen, __ldg(p.k_lens + g));
-  // causal: no key beyond the last query row of this tile is visible to any of its rows -> skip those tiles
-  const int ntiles = ((p.causal ? min(klen, q0 + AT_BM) : klen) + AT_BN - 1) / AT_BN;
+  // chunk mask: only the key tiles some row of this query tile can see are visited: [jt0, jt0 + ntiles)
+  auto vis_lo = [&](int i) { return (p.chunk > 0 && p.left >= 0) ? max(0, (i / p.chunk - p.left) * p.chunk) : 0; };
+  auto vis_hi = [&](int i) { return p.chunk > 0 ? min(klen, (i / p.chunk + 1) * p.chunk) : klen; };
+  const int jt0 = vis_lo(q0) / AT_BN;
+  const int ntiles = max(0, (vis_hi(q0 + AT_BM - 1) + AT_BN - 1) / AT_BN - jt0);
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -147,8 +152,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   } else {
     // key bias row of this (group, head), pre-scaled; masked keys -> -inf
     const float* kb = p.key_bias ? p.key_bias + ((long long)g * p.H + h) * p.Tk : nullptr;
-    for (int key = threadIdx.x; key < ntiles * AT_BN; key += 32 * SW)
-      s_bias[key] = (key < klen) ? (kb ? __ldg(kb + key) * p.scale_log2 : 0.f) : -INFINITY;
+    for (int kk = threadIdx.x; kk < ntiles * AT_BN; kk += 32 * SW) {
+      const int key = jt0 * AT_BN + kk;
+      s_bias[kk] = (key < klen) ? (kb ? __ldg(kb + key) * p.scale_log2 : 0.f) : -INFINITY;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -172,13 +179,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int st = n % AT_KST, use = n / AT_KST;
         mbar_wait(&k_empty[st], (use & 1) ^ 1);
         mbar_expect_tx(&k_full[st], AT_TILE_BYTES);
-        tma_load_2d(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], h * AT_DK, (int)(krow0 + n * AT_BN));
+        tma_load_2d(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], h * AT_DK, (int)(krow0 + (jt0 + n) * AT_BN));
       };
       auto load_v = [&](int j) {
         const int st = j & 1;
         mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
         mbar_expect_tx(&v_full[st], AT_TILE_BYTES);
-        tma_load_2d(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], h * AT_DK, (int)(krow0 + j * AT_BN));
+        tma_load_2d(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], h * AT_DK, (int)(krow0 + (jt0 + j) * AT_BN));
       };
       auto issue_qk = [&](int n) {
         const int st = n % AT_KST, sb = n % AT_NS;
@@ -236,7 +243,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t lane_addr = ((uint32_t)(wq * 32) << 16);
     const int c0 = hh * CW, ob = hh * OW;
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory"); };
-    float m_run = 0.f, row_sum = 0.f;
+    float m_run = -INFINITY, row_sum = 0.f;  // m_run stays -inf until the row has seen a visible key
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j % AT_NS, pb = j & 1;
       mbar_wait(&s_full[sb], (j / AT_NS) & 1);
@@ -270,15 +277,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mx[3] = fmaxf(mx[3], x3);
       }
       float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      if (p.causal && j * AT_BN + c0 + CW - 1 > q0 + wq * 32) {
-        // diagonal tile (warp-uniform test): hide the keys after this row's position and redo the tile maximum
-        const int lim = q0 + r - j * AT_BN - c0;  // last visible column of this thread's part
-        tmax = -INFINITY;
+      if (p.chunk > 0) {
+        // boundary tiles of the chunk mask (warp-uniform test over the warp's 32 rows; visibility bounds are
+        // non-decreasing in the row index): hide the keys outside [lo, hi) of this row and redo the tile maximum
+        const int kbase = (jt0 + j) * AT_BN + c0;           // key index of this thread's column 0
+        const int i0 = q0 + wq * 32;
+        if (kbase < vis_lo(i0 + 31) || kbase + CW > vis_hi(i0)) {
+          const int lo = vis_lo(q0 + r) - kbase, hi = vis_hi(q0 + r) - kbase;  // visible columns: lo <= e < hi
+          tmax = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < CW; ++e) {
-          const float x = (e <= lim) ? __uint_as_float(sv[e]) : -INFINITY;
-          sv[e] = __float_as_uint(x);
-          tmax = fmaxf(tmax, x);
+          for (int e = 0; e < CW; ++e) {
+            const float x = (e >= lo && e < hi) ? __uint_as_float(sv[e]) : -INFINITY;
+            sv[e] = __float_as_uint(x);
+            tmax = fmaxf(tmax, x);
+          }
         }
       }
       if (SPLIT) {  // the row's tile maximum = max of the two halves (both halves must move m_run identically)
@@ -287,7 +299,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tmax = fmaxf(tmax, s_xch[(j & 1) * 256 + (hh ^ 1) * 128 + r]);
       }
       if (j == 0) {
-        m_run = (tmax == -INFINITY) ? 0.f : tmax;  // PV(0) overwrites O: nothing to rescale
+        m_run = tmax;  // PV(0) overwrites O: nothing to rescale
       } else {
         const bool raise = tmax > m_run + 8.f;
         if (__any_sync(0xffffffffu, raise)) {
@@ -296,7 +308,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
           tc_fence_after();
           const float m_new = raise ? tmax : m_run;
-          const float f = fast_exp2(m_run - m_new);  // 1 for the rows that keep their maximum
+          // 1 for the rows that keep their maximum; 0 for rows that see their first visible key only now (their O
+          // row and row sum are zero so far) — never exp2(-inf - -inf)
+          const float f = (m_new == -INFINITY) ? 1.f : fast_exp2(m_run - m_new);
           m_run = m_new;
           row_sum *= f;
 #pragma unroll 1
@@ -314,12 +328,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       float sm[4] = {0.f, 0.f, 0.f, 0.f};
       uint32_t pk[CW / 2];
+      const float m_eff = (m_run == -INFINITY) ? 0.f : m_run;  // no visible key yet: every x is -inf -> p = 0
 #pragma unroll
       for (int e = 0; e < CW; e += 4) {
-        const float p0 = fast_exp2(__uint_as_float(sv[e + 0]) - m_run);
-        const float p1 = fast_exp2(__uint_as_float(sv[e + 1]) - m_run);
-        const float p2 = fast_exp2(__uint_as_float(sv[e + 2]) - m_run);
-        const float p3 = fast_exp2(__uint_as_float(sv[e + 3]) - m_run);
+        const float p0 = fast_exp2(__uint_as_float(sv[e + 0]) - m_eff);
+        const float p1 = fast_exp2(__uint_as_float(sv[e + 1]) - m_eff);
+        const float p2 = fast_exp2(__uint_as_float(sv[e + 2]) - m_eff);
+        const float p3 = fast_exp2(__uint_as_float(sv[e + 3]) - m_eff);
         sm[0] += p0;
         sm[1] += p1;
         sm[2] += p2;
@@ -508,7 +523,8 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
   RVB_REQUIRE(((uintptr_t)a.q & 15) == 0 && ((uintptr_t)a.k & 15) == 0 && ((uintptr_t)a.v & 15) == 0 &&
                   ((uintptr_t)a.out & 15) == 0,
               "attention_tc: operands must be 16-byte aligned");
-  RVB_REQUIRE(!a.causal || a.Tq == a.Tk, "attention_tc: causal needs Tq == Tk");
+  RVB_REQUIRE((!a.causal && a.chunk <= 0) || a.Tq == a.Tk, "attention_tc: causal / chunk masks need Tq == Tk");
+  RVB_REQUIRE(!(a.causal && a.chunk > 0), "attention_tc: causal and chunk mask are exclusive");
   if (a.groups <= 0 || a.Tq <= 0) return 0;
   if (g_encode_att == nullptr) {
     void* fn = nullptr;
@@ -530,7 +546,8 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
   p.Tq = a.Tq;
   p.Tk = a.Tk;
   p.H = a.H;
-  p.causal = a.causal;
+  p.chunk = a.causal ? 1 : (a.chunk > 0 ? a.chunk : 0);
+  p.left = a.causal ? -1 : a.left_chunks;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   CUtensorMap tmQ, tmK, tmV;
   if (tmap_2d(&tmQ, a.q, (long long)a.H * AT_DK, (long long)a.groups * a.Tq, a.ldq, 128)) return -1;

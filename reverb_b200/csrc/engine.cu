@@ -484,8 +484,11 @@ static int attn_impl() {
   return v;
 }
 
+// att_chunk > 0: bounded-context attention (add_optional_chunk_mask, utils/mask.py:126-197, with a fixed decoding chunk):
+// query frame i attends keys [max(0, (i/chunk - left) * chunk) (0 when left < 0), (i/chunk + 1) * chunk) & pad mask.
 static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
-                           const float* h_cat, int n_cat, float* d_enc_out, int* h_enc_lens, cudaStream_t stream) {
+                           const float* h_cat, int n_cat, float* d_enc_out, int* h_enc_lens, cudaStream_t stream,
+                           int att_chunk = 0, int att_left = -1) {
   const rvb_model_config& c = m->cfg;
   RVB_REQUIRE(m->finalized, "encoder_forward: model not finalized");
   const int d = c.d_model, F = c.input_dim, H = c.heads, dk = d / H, L = c.num_blocks;
@@ -609,9 +612,12 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       a.dk = dk;
       a.key_bias = cb;
       a.k_lens = d_lens;
+      a.chunk = att_chunk;
+      a.left_chunks = att_left;
       a.scale = att_scale;
       if (launch_attention_tc(a, stream)) return -1;
     } else {
+      RVB_REQUIRE(att_chunk <= 0, "encoder_forward: chunk-masked attention needs the tcgen05 kernel (d_k = 64)");
       AttnArgs a;
       a.q = qkv;
       a.k = qkv + d;
@@ -1193,6 +1199,15 @@ RVB_API int rvb_encoder_forward(rvb_model* m, const float* d_feats, const int* h
                               (cudaStream_t)stream);
 }
 
+RVB_API int rvb_encoder_forward_chunked(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
+                                        const float* h_cat_embs, int n_cat, int chunk_size, int num_left_chunks,
+                                        float* d_enc_out, int* h_enc_lens, void* stream) {
+  RVB_REQUIRE(m && d_feats && h_feat_lens && d_enc_out && B > 0 && chunk_size > 0,
+              "rvb_encoder_forward_chunked: bad arguments");
+  return rvb::encoder_forward(m, d_feats, h_feat_lens, B, T, h_cat_embs, n_cat, d_enc_out, h_enc_lens,
+                              (cudaStream_t)stream, chunk_size, num_left_chunks);
+}
+
 RVB_API int rvb_resample(const void* d_wave, int is_i16, long long n_in, const float* d_kernel, int orig, int new_, int width,
                          float* d_out, long long n_out, void* stream) {
   RVB_REQUIRE(d_wave && d_kernel && d_out && n_in >= 0, "rvb_resample: bad arguments");
@@ -1365,6 +1380,24 @@ RVB_API int rvb_attention_tc(const void* d_q, const void* d_k, const void* d_v, 
   a.key_bias = d_key_bias;
   a.k_lens = d_k_lens;
   a.causal = causal;
+  a.scale = scale;
+  return rvb::launch_attention_tc(a, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_attention_tc_chunked(const void* d_q, const void* d_k, const void* d_v, void* d_out, int ldq, int ldk,
+                                     int ldv, int ldo, int groups, int Tq, int Tk, int H, int dk, const float* d_key_bias,
+                                     const int* d_k_lens, int chunk, int left_chunks, float scale, void* stream) {
+  rvb::AttnTcArgs a;
+  a.q = reinterpret_cast<const rvb::bf16*>(d_q);
+  a.k = reinterpret_cast<const rvb::bf16*>(d_k);
+  a.v = reinterpret_cast<const rvb::bf16*>(d_v);
+  a.out = reinterpret_cast<rvb::bf16*>(d_out);
+  a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
+  a.groups = groups; a.Tq = Tq; a.Tk = Tk; a.H = H; a.dk = dk;
+  a.key_bias = d_key_bias;
+  a.k_lens = d_k_lens;
+  a.chunk = chunk;
+  a.left_chunks = left_chunks;
   a.scale = scale;
   return rvb::launch_attention_tc(a, (cudaStream_t)stream);
 }

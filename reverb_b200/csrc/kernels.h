@@ -124,6 +124,7 @@ struct AttnTcArgs {
   const float* key_bias = nullptr;  // (groups, H, Tk) fp32, added to q.k before scaling
   const int* k_lens = nullptr;      // (groups) valid keys
   int causal = 0;                   // self-attention with Tq == Tk: key j visible to query i iff j <= i
+  int chunk = 0, left_chunks = -1;  // chunk > 0: streaming chunk mask (utils/mask.py:88-123), left_chunks < 0 = all
   float scale = 1.0f;
 };
 int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream);

@@ -329,3 +329,34 @@ def test_resample_matches_torchaudio_golden(lib):
             got = eng.resample(torch.from_numpy(pcm.astype(dtype)).cuda(), rate, 16000).cpu().numpy()
             assert got.shape == ref.shape
             np.testing.assert_allclose(got, ref, rtol=0, atol=32768 * 2e-5)
+
+
+@pytest.mark.parametrize("chunk,left", [(16, -1), (8, 2), (50, 0), (1, 3), (200, 1)])
+def test_attention_tcgen05_chunk_mask(lib, chunk, left):
+    """bounded attention context (subsequent_chunk_mask, utils/mask.py:88-123) & key-length mask, with the rel-pos
+    key bias: only the visible key tiles are visited, boundary tiles are masked per element."""
+    torch.manual_seed(chunk * 7 + left)
+    B, T, H, dk = 3, 300, 2, 64
+    d = H * dk
+    qkv = (torch.randn(B, T, 3 * d, device="cuda") * 0.7).bfloat16()
+    cb = torch.randn(B, H, T, device="cuda") * 0.5
+    klens = torch.tensor([T, 211, 37], dtype=torch.int32, device="cuda")
+    out = torch.zeros(B, T, d, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dk)
+    _check(lib, lib.rvb_attention_tc_chunked(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d),
+                                             _p(out), 3 * d, 3 * d, 3 * d, d, B, T, T, H, dk, _p(cb), _p(klens), chunk,
+                                             left, scale, _stream()))
+    q = qkv[..., :d].float().view(B, T, H, dk).transpose(1, 2)
+    k = qkv[..., d:2 * d].float().view(B, T, H, dk).transpose(1, 2)
+    v = qkv[..., 2 * d:].float().view(B, T, H, dk).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2) + cb[:, :, None, :]) * scale
+    i = torch.arange(T, device="cuda")
+    lo = torch.zeros_like(i) if left < 0 else torch.clamp((i // chunk - left) * chunk, min=0)
+    hi = torch.clamp((i // chunk + 1) * chunk, max=T)
+    vis = (i[None, :] >= lo[:, None]) & (i[None, :] < hi[:, None])
+    mask = ~vis[None] | (i[None, None, :] >= klens[:, None, None])
+    s = s.masked_fill(mask[:, None], -float("inf"))
+    ref = (torch.softmax(s, -1).nan_to_num(0.0) @ v).transpose(1, 2).reshape(B, T, d)
+    for g in range(B):
+        n = int(klens[g])
+        torch.testing.assert_close(out[g, :n].float(), ref[g, :n], rtol=3e-2, atol=3e-2)

@@ -284,6 +284,35 @@ def test_transcribe_api_surface(asr, golden_cases, model_dirs, case):
         m.transcribe(wav, mode="joint_decoding")
 
 
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_bounded_context_encoder_vs_reference_fixture(asr, golden_cases, case):
+    """decoding_chunk_size > 0: chunk-masked attention (utils/mask.py:88-197) inside the tcgen05 attention kernel;
+    encoder_out vs the live-reference fixture with the same bf16 tolerance as the full-context encoder, and the
+    chunked output must differ from the full-context one (the mask is really applied)."""
+    import json as _json
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    gold = _json.load(open(os.path.join(gdir, "chunked.json")))
+    arr_c = dict(np.load(os.path.join(gdir, "chunked.npz")))
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    for cs, left in gold["settings"]:
+        for bi, (fb, fl) in enumerate(m.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])):
+            enc, lens = m.model._forward_encoder(fb, fl, cat, decoding_chunk_size=cs, num_decoding_left_chunks=left)
+            full, _ = m.model._forward_encoder(fb, fl, cat)
+            want = arr_c[f"{case}_c{cs}_l{left}_enc_{bi}"]
+            for b in range(fb.shape[0]):
+                n = int(lens[b])
+                assert _rel_rms(enc[b, :n].cpu().numpy(), want[b, :n]) < 6e-3
+                assert _rel_rms(full[b, :n].cpu().numpy(), want[b, :n]) > 2e-2
+            res = m.model.decode(["ctc_greedy_search"], fb, fl, 10, decoding_chunk_size=cs,
+                                 num_decoding_left_chunks=left, cat_embs=cat, blank_id=0)
+            assert len(res["ctc_greedy_search"]) == fb.shape[0]
+    with pytest.raises(NotImplementedError):
+        m.model.decode(["ctc_greedy_search"], fb, fl, 10, decoding_chunk_size=16, simulate_streaming=True, cat_embs=cat)
+
+
 def test_compute_feats_resamples_non_16k_audio_on_the_gpu(asr, model_dirs, tmp_path):
     """cli/reverb.py:120-138: a WAV at another rate is resampled to 16 kHz (torchaudio Resample semantics) before
     fbank; here both steps run on the GPU and must agree with the oracle chain resample_ref -> fbank_np."""

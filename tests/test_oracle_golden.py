@@ -72,6 +72,28 @@ def test_oracle_attention_mode_vs_reference_golden(golden_cases, model_dirs, cas
             assert [list(r.tokens) for r in out["attention"]] == gold[f"length_penalty_{lp}"][bi]
 
 
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_oracle_bounded_context_encoder_vs_reference_golden(golden_cases, model_dirs, case):
+    """decoding_chunk_size > 0 (utils/mask.py:88-197): the oracle's chunk-masked encoder and the searches on top of it
+    reproduce the live reference (tests/golden/chunked.*, oracle/make_golden_chunked.py) bit for bit."""
+    import json
+    from oracle import pipeline_ref
+    gold = json.load(open("tests/golden/chunked.json"))
+    arr_c = dict(np.load("tests/golden/chunked.npz"))
+    meta, arr = golden_cases[case]
+    orc = pipeline_ref.OracleASR(model_dirs[case][0])
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0)
+    for cs, left in gold["settings"]:
+        for bi, (fb, fl) in enumerate(orc.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])):
+            out = orc.decode(["ctc_greedy_search", "ctc_prefix_beam_search"], fb, fl, 10, cat_embs=cat,
+                             return_intermediates=True, decoding_chunk_size=cs, num_decoding_left_chunks=left)
+            np.testing.assert_array_equal(out["_encoder_out"].numpy(), arr_c[f"{case}_c{cs}_l{left}_enc_{bi}"])
+            g = gold["cases"][case][f"c{cs}_l{left}"][bi]
+            assert [list(r.tokens) for r in out["ctc_greedy_search"]] == g["greedy"]
+            assert [list(r.tokens) for r in out["ctc_prefix_beam_search"]] == g["prefix"]
+
+
 def _resample_cases():
     gold = dict(np.load("tests/golden/resample.npz"))
     for key, ref in gold.items():
