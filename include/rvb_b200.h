@@ -11,6 +11,8 @@
  *   rvb_ctc_greedy_search       <- ctc_greedy_search                        transformer/search.py:106-121
  *   rvb_ctc_prefix_beam_search  <- ctc_prefix_beam_search                   transformer/search.py:124-248
  *   rvb_attention_rescoring     <- forward_attention_decoder + the gather   asr_model.py:868-978, search.py:410-436
+ *   rvb_beam_search_rescoring   <- the two calls above back to back          asr_model.py:403-424 (n-best stays on the device)
+ *   rvb_decoder_step_topk       <- decoder.forward_one_step + logp.topk     search.py:302-306 (`attention` mode)
  *   rvb_model_*                 <- init_model / load_checkpoint             utils/init_model.py:99-277,
  *                                                                           utils/checkpoint.py:29-80
  *
