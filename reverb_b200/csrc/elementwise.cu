@@ -395,19 +395,28 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
     }
     return;
   }
+  // per-frame sum / sum of squares over the warp's 64 channels: the 2 x CM_TT partials of a lane are reduced with a
+  // transposing butterfly (31 shuffles instead of 10 per value): afterwards lane l holds the total of value l
+  static_assert(CM_TT == 16, "the statistics butterfly assumes 32 values per lane");
+  float sv[32];
 #pragma unroll
   for (int t = 0; t < CM_TT; ++t) {
-    float s = ok ? acc[t][0] + acc[t][1] : 0.f;
-    float q = ok ? acc[t][0] * acc[t][0] + acc[t][1] * acc[t][1] : 0.f;
-    s = warp_sum(s);
-    q = warp_sum(q);
-    if (lane == 0) {
-      s_part[warp][t][0] = s;
-      s_part[warp][t][1] = q;
-    }
+    sv[t] = ok ? acc[t][0] + acc[t][1] : 0.f;
+    sv[CM_TT + t] = ok ? acc[t][0] * acc[t][0] + acc[t][1] * acc[t][1] : 0.f;
     if (ok && t0 + t < T)
       reinterpret_cast<float2*>(conv_out + ((long long)b * T + t0 + t) * C)[cp] = make_float2(acc[t][0], acc[t][1]);
   }
+#pragma unroll
+  for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+    const bool up = (lane & ofs) != 0;
+#pragma unroll
+    for (int i = 0; i < ofs; ++i) {
+      const float send = up ? sv[i] : sv[i + ofs];
+      const float keep = up ? sv[i + ofs] : sv[i];
+      sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+    }
+  }
+  s_part[warp][lane & (CM_TT - 1)][lane >> 4] = sv[0];   // lanes 0..15: sums of frames 0..15, lanes 16..31: squares
   __syncthreads();
   if (threadIdx.x < 2 * CM_TT) {
     const int t = threadIdx.x >> 1, which = threadIdx.x & 1;

@@ -58,6 +58,7 @@ struct GemmKParams {
   int rows_per_batch;
   int conv_mode, conv_T2, conv_F2, conv_tt, conv_cblocks;
   int debug_skip_epi;  // RVB_GEMM_SKIP_EPI=1 (tuning aid): epilogue warps only hand the accumulator back, no stores
+  int glu_coalesced;   // ACT_GLU with 16-byte aligned output rows (always true after the launch checks)
   int bf16_coalesced;  // bf16 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
   int f32_coalesced;  // fp32 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
   int epi_warps;  // 4 or 8 epilogue warps drain a tile (8: short-K, epilogue-bound shapes; 4: long-K, MMA-bound)
@@ -266,6 +267,62 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
     return;
   }
   if constexpr (EPI == EPI_GLU) {
+    if (p.glu_coalesced && ((c1 - c0) & 127) == 0) {
+      // 128 accumulator columns = 64 outputs = 128 bytes per row per round through the staging tile (as for bf16)
+      const int slot = lane & 7, rsub = lane >> 3;
+      long long ro[8];  // element offset of (row it*4+rsub, output column n0_tile/2 + slot*8), or -1
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long o = __shfl_sync(0xffffffffu, orow, it * 4 + rsub);
+        ro[it] = (o >= 0) ? o * p.ldo + (n0_tile >> 1) + slot * 8 : -1;
+      }
+      bf16* out = reinterpret_cast<bf16*>(p.out);
+      uint32_t* stage_u = reinterpret_cast<uint32_t*>(stage);
+      mbar_wait(tfull_bar, aphase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = c0; c < c1; c += 128) {
+        if (n0_tile + c >= p.N) break;
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {  // two groups of 32 value + 32 gate columns -> 16-byte slots 4*hf .. 4*hf+3
+          uint32_t av[32], gv[32];
+          tmem_ld_32x32(taddr + c + 64 * hf, av);
+          tmem_ld_32x32(taddr + c + 64 * hf + 32, gv);
+          tmem_ld_wait();
+          const int n0 = n0_tile + c + 64 * hf;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float v[8];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+              float4 ba = make_float4(0.f, 0.f, 0.f, 0.f), bg = ba;
+              if (p.bias != nullptr) {
+                ba = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * j + h2);
+                bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + 2 * j + h2);
+              }
+              const int e = 8 * j + 4 * h2;
+              v[4 * h2 + 0] = __fdividef(__uint_as_float(av[e + 0]) + ba.x, 1.f + __expf(-(__uint_as_float(gv[e + 0]) + bg.x)));
+              v[4 * h2 + 1] = __fdividef(__uint_as_float(av[e + 1]) + ba.y, 1.f + __expf(-(__uint_as_float(gv[e + 1]) + bg.y)));
+              v[4 * h2 + 2] = __fdividef(__uint_as_float(av[e + 2]) + ba.z, 1.f + __expf(-(__uint_as_float(gv[e + 2]) + bg.z)));
+              v[4 * h2 + 3] = __fdividef(__uint_as_float(av[e + 3]) + ba.w, 1.f + __expf(-(__uint_as_float(gv[e + 3]) + bg.w)));
+            }
+            const int sl = 4 * hf + j;
+            *reinterpret_cast<uint4*>(stage_u + lane * 32 + ((sl ^ (lane & 7)) << 2)) =
+                make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                           pack_bf16x2(v[6], v[7]));
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + rsub;
+          const uint4 u = *reinterpret_cast<const uint4*>(stage_u + row * 32 + ((slot ^ (row & 7)) << 2));
+          if (ro[it] >= 0) *reinterpret_cast<uint4*>(out + ro[it] + (c >> 1)) = u;
+        }
+        __syncwarp();
+      }
+      return;
+    }
     mbar_wait(tfull_bar, aphase);
     tc_fence_after();
 #pragma unroll 1
@@ -1062,6 +1119,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
     }
     p.debug_skip_epi = skip;
   }
+  p.glu_coalesced = (a.act == ACT_GLU);
   p.bf16_coalesced = (a.out_mode == OUT_BF16) && (a.act != ACT_GLU) && (p.ldo % 8 == 0) &&
                      ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0) &&
                      (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
