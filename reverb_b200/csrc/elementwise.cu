@@ -212,15 +212,26 @@ int launch_double_layernorm(const float* x, const float* ga, const float* ba, co
 // GlobalCMVN + Conv2d(1, C, 3, stride 2) + ReLU  (transformer/cmvn.py:36-47, subsampling.py:186-187).
 // Output is channels-last bf16 with the time axis split by parity, (B, 2, T1h, F1, C), so that the second conv's
 // implicit-GEMM A tiles (gemm.cu conv_mode) are plain unit-stride 4-D TMA boxes.  One CTA per (b, C1_ROWS output
-// rows): a thread keeps the 8 x 9 weights of its channel group in registers and reuses them for every (row, f), so
-// the weight fetch is amortised over C1_ROWS * F1 outputs; the 2*C1_ROWS+1 CMVN'd input rows sit in shared memory.
+// rows): a thread keeps the 8 x 9 weights of its channel group in registers (as 4 x 9 channel PAIRS for the packed
+// FFMA2) and reuses them for every (row, f), so the weight fetch is amortised over C1_ROWS * F1 outputs; the
+// 2*C1_ROWS+1 CMVN'd input rows sit in shared memory, each value duplicated {x, x} as the second FFMA2 operand.
 constexpr int C1_ROWS = 4;
+
+// Blackwell packed fp32 FMA (SASS FFMA2): two independent fp32 FMAs per instruction, bit-identical to two FFMAs
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  ra = *reinterpret_cast<unsigned long long*>(&a);
+  rb = *reinterpret_cast<unsigned long long*>(&b);
+  rc = *reinterpret_cast<unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
 
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, const float* __restrict__ istd,
              const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out, int T, int F, int C,
              int T1, int T1h, int F1) {
-  extern __shared__ float s_in[];  // (2*C1_ROWS+1) rows x F, CMVN applied
+  extern __shared__ float2 s_in2[];  // (2*C1_ROWS+1) rows x F, CMVN applied, every value DUPLICATED {x, x} (FFMA2 operand)
   const int t1_0 = blockIdx.x * C1_ROWS;  // first output row of this CTA, 0 .. 2*T1h-1
   const int b = blockIdx.y;
   const int CG = C >> 3;
@@ -229,16 +240,19 @@ conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, co
     int kh = i / F, f = i - kh * F;
     int t = 2 * t1_0 + kh;
     float x = (t < T) ? feats[((long long)b * T + t) * F + f] : 0.f;
-    s_in[i] = (x - __ldg(mean + f)) * __ldg(istd + f);
+    x = (x - __ldg(mean + f)) * __ldg(istd + f);
+    s_in2[i] = make_float2(x, x);
   }
   const int cg = threadIdx.x % CG;
   const int fstep = blockDim.x / CG;
-  float wr[8][9], br[8];
+  // channel pairs (2p, 2p+1) of this thread's 8 channels share one packed accumulator
+  float2 wr[4][9], br[4];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    br[c] = __ldg(bias + cg * 8 + c);
+  for (int pc = 0; pc < 4; ++pc) {
+    const int c = cg * 8 + 2 * pc;
+    br[pc] = make_float2(__ldg(bias + c), __ldg(bias + c + 1));
 #pragma unroll
-    for (int k = 0; k < 9; ++k) wr[c][k] = __ldg(w + (cg * 8 + c) * 9 + k);
+    for (int k = 0; k < 9; ++k) wr[pc][k] = make_float2(__ldg(w + c * 9 + k), __ldg(w + (c + 1) * 9 + k));
   }
   __syncthreads();
   for (int rr = 0; rr < C1_ROWS; ++rr) {
@@ -251,26 +265,26 @@ conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, co
         reinterpret_cast<uint4*>(orow)[i] = make_uint4(0u, 0u, 0u, 0u);
       continue;
     }
-    const float* s_r = s_in + 2 * rr * F;
+    const float2* s_r = s_in2 + 2 * rr * F;
     for (int f = threadIdx.x / CG; f < F1; f += fstep) {
-      float in[9];
+      float2 in[9];
 #pragma unroll
       for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw) in[kh * 3 + kw] = s_r[kh * F + 2 * f + kw];
-      float o[8];
+      float2 o[4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float a = br[c];
+      for (int pc = 0; pc < 4; ++pc) {
+        float2 a = br[pc];
 #pragma unroll
-        for (int k = 0; k < 9; ++k) a = fmaf(wr[c][k], in[k], a);
-        o[c] = fmaxf(a, 0.f);
+        for (int k = 0; k < 9; ++k) a = ffma2(wr[pc][k], in[k], a);
+        o[pc] = make_float2(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f));
       }
       uint4 u;
-      u.x = pack_bf16x2(o[0], o[1]);
-      u.y = pack_bf16x2(o[2], o[3]);
-      u.z = pack_bf16x2(o[4], o[5]);
-      u.w = pack_bf16x2(o[6], o[7]);
+      u.x = pack_bf16x2(o[0].x, o[0].y);
+      u.y = pack_bf16x2(o[1].x, o[1].y);
+      u.z = pack_bf16x2(o[2].x, o[2].y);
+      u.w = pack_bf16x2(o[3].x, o[3].y);
       reinterpret_cast<uint4*>(orow + (long long)f * C)[cg] = u;
     }
   }
@@ -282,7 +296,7 @@ int launch_conv1(const float* feats, const float* mean, const float* istd, const
   const int CG = C / 8;
   const int threads = (256 / CG) * CG;
   dim3 grid((2 * T1h + C1_ROWS - 1) / C1_ROWS, B);
-  conv1_kernel<<<grid, threads, (2 * C1_ROWS + 1) * F * sizeof(float), stream>>>(feats, mean, istd, w, bias, out, T, F,
+  conv1_kernel<<<grid, threads, (2 * C1_ROWS + 1) * F * sizeof(float2), stream>>>(feats, mean, istd, w, bias, out, T, F,
                                                                                  C, T1, T1h, F1);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
@@ -362,8 +376,10 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
       for (int k = 0; k < K; ++k) {
         const int t = r - k;  // compile-time after unrolling
         if (t >= 0 && t < CM_TT) {
-          acc[t][0] = fmaf(w0[k], v.x, acc[t][0]);
-          acc[t][1] = fmaf(w1[k], v.y, acc[t][1]);
+          // the channel pair's two FMAs as one packed FFMA2
+          const float2 a2 = ffma2(make_float2(w0[k], w1[k]), v, make_float2(acc[t][0], acc[t][1]));
+          acc[t][0] = a2.x;
+          acc[t][1] = a2.y;
         }
       }
     }
