@@ -260,21 +260,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const uint32_t bias_addr = smem_u32(s_bias + j * AT_BN + c0);
       // x = s * scale*log2e + key bias (masked keys: -inf), kept in place of the raw scores; tile maximum
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
+      const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
 #pragma unroll
       for (int e = 0; e < CW; e += 4) {
         const float4 b4 = lds128(bias_addr + e * 4);
-        const float x0 = fmaf(__uint_as_float(sv[e + 0]), p.scale_log2, b4.x);
-        const float x1 = fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, b4.y);
-        const float x2 = fmaf(__uint_as_float(sv[e + 2]), p.scale_log2, b4.z);
-        const float x3 = fmaf(__uint_as_float(sv[e + 3]), p.scale_log2, b4.w);
-        sv[e + 0] = __float_as_uint(x0);
-        sv[e + 1] = __float_as_uint(x1);
-        sv[e + 2] = __float_as_uint(x2);
-        sv[e + 3] = __float_as_uint(x3);
-        mx[0] = fmaxf(mx[0], x0);
-        mx[1] = fmaxf(mx[1], x1);
-        mx[2] = fmaxf(mx[2], x2);
-        mx[3] = fmaxf(mx[3], x3);
+        // packed FFMA2: two scores per instruction
+        const float2 x01 = ffma2(make_float2(__uint_as_float(sv[e + 0]), __uint_as_float(sv[e + 1])), sc2,
+                                 make_float2(b4.x, b4.y));
+        const float2 x23 = ffma2(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), sc2,
+                                 make_float2(b4.z, b4.w));
+        sv[e + 0] = __float_as_uint(x01.x);
+        sv[e + 1] = __float_as_uint(x01.y);
+        sv[e + 2] = __float_as_uint(x23.x);
+        sv[e + 3] = __float_as_uint(x23.y);
+        mx[0] = fmaxf(mx[0], x01.x);
+        mx[1] = fmaxf(mx[1], x01.y);
+        mx[2] = fmaxf(mx[2], x23.x);
+        mx[3] = fmaxf(mx[3], x23.y);
       }
       float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       if (p.chunk > 0) {
@@ -326,22 +328,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tc_fence_before();
         }
       }
-      float sm[4] = {0.f, 0.f, 0.f, 0.f};
+      float2 sm01 = make_float2(0.f, 0.f), sm23 = make_float2(0.f, 0.f);
       uint32_t pk[CW / 2];
       const float m_eff = (m_run == -INFINITY) ? 0.f : m_run;  // no visible key yet: every x is -inf -> p = 0
+      const float2 one2 = make_float2(1.f, 1.f), negm2 = make_float2(-m_eff, -m_eff);
 #pragma unroll
       for (int e = 0; e < CW; e += 4) {
-        const float p0 = fast_exp2(__uint_as_float(sv[e + 0]) - m_eff);
-        const float p1 = fast_exp2(__uint_as_float(sv[e + 1]) - m_eff);
-        const float p2 = fast_exp2(__uint_as_float(sv[e + 2]) - m_eff);
-        const float p3 = fast_exp2(__uint_as_float(sv[e + 3]) - m_eff);
-        sm[0] += p0;
-        sm[1] += p1;
-        sm[2] += p2;
-        sm[3] += p3;
-        pk[(e >> 1) + 0] = pack_bf16x2(p0, p1);
-        pk[(e >> 1) + 1] = pack_bf16x2(p2, p3);
+        // x - m and the running sums as packed FFMA2 (x * 1 + (-m), p * 1 + sum: exact)
+        const float2 d01 = ffma2(make_float2(__uint_as_float(sv[e + 0]), __uint_as_float(sv[e + 1])), one2, negm2);
+        const float2 d23 = ffma2(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), one2, negm2);
+        const float2 p01 = make_float2(fast_exp2(d01.x), fast_exp2(d01.y));
+        const float2 p23 = make_float2(fast_exp2(d23.x), fast_exp2(d23.y));
+        sm01 = ffma2(p01, one2, sm01);
+        sm23 = ffma2(p23, one2, sm23);
+        pk[(e >> 1) + 0] = pack_bf16x2(p01.x, p01.y);
+        pk[(e >> 1) + 1] = pack_bf16x2(p23.x, p23.y);
       }
+      const float sm[4] = {sm01.x, sm01.y, sm23.x, sm23.y};
       row_sum += (sm[0] + sm[1]) + (sm[2] + sm[3]);
       // the P~ buffer is only needed now: PV(j-2), which read it last, has had a whole tile of exponentials to retire
       mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);

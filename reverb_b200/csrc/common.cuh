@@ -43,6 +43,16 @@ extern std::atomic<unsigned long long> g_launch_count;
 typedef __nv_bfloat16 bf16;
 
 // ---------------------------------------------------------------- small device helpers
+// Blackwell packed fp32 FMA (SASS FFMA2): two independent fp32 FMAs per instruction, bit-identical to two FFMAs
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  ra = *reinterpret_cast<unsigned long long*>(&a);
+  rb = *reinterpret_cast<unsigned long long*>(&b);
+  rc = *reinterpret_cast<unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

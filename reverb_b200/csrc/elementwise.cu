@@ -217,16 +217,6 @@ int launch_double_layernorm(const float* x, const float* ga, const float* ba, co
 // 2*C1_ROWS+1 CMVN'd input rows sit in shared memory, each value duplicated {x, x} as the second FFMA2 operand.
 constexpr int C1_ROWS = 4;
 
-// Blackwell packed fp32 FMA (SASS FFMA2): two independent fp32 FMAs per instruction, bit-identical to two FFMAs
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long ra, rb, rc, rd;
-  ra = *reinterpret_cast<unsigned long long*>(&a);
-  rb = *reinterpret_cast<unsigned long long*>(&b);
-  rc = *reinterpret_cast<unsigned long long*>(&c);
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  return *reinterpret_cast<float2*>(&rd);
-}
-
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, const float* __restrict__ istd,
              const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out, int T, int F, int C,
