@@ -112,6 +112,25 @@ __host__ __device__ inline int select_epi(int act, int out_mode) {
 
 __device__ __forceinline__ float fast_silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// x * sigmoid(g) for two lanes at once with packed fp32 math (FMUL2 / FADD2 around the two MUFU pairs); x == g gives SiLU
+__device__ __forceinline__ float2 gated2(float2 x, float2 g) {
+  const float2 zero2 = make_float2(0.f, 0.f), one2 = make_float2(1.f, 1.f);
+  const float2 t = ffma2(g, make_float2(-1.4426950408889634f, -1.4426950408889634f), zero2);
+  const float2 e = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+  const float2 den = ffma2(e, one2, one2);
+  return ffma2(x, make_float2(rcp_approx(den.x), rcp_approx(den.y)), zero2);
+}
+
 // One thread stores 32 consecutive output columns [n0, n0+32) of one output row (n0 % 32 == 0).
 template <int EPI>
 __device__ __forceinline__ void store_chunk(const GemmKParams& p, long long out_row, int n0, const uint32_t* acc) {
@@ -301,10 +320,16 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
                 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + 32) + 2 * j + h2);
               }
               const int e = 8 * j + 4 * h2;
-              v[4 * h2 + 0] = __fdividef(__uint_as_float(av[e + 0]) + ba.x, 1.f + __expf(-(__uint_as_float(gv[e + 0]) + bg.x)));
-              v[4 * h2 + 1] = __fdividef(__uint_as_float(av[e + 1]) + ba.y, 1.f + __expf(-(__uint_as_float(gv[e + 1]) + bg.y)));
-              v[4 * h2 + 2] = __fdividef(__uint_as_float(av[e + 2]) + ba.z, 1.f + __expf(-(__uint_as_float(gv[e + 2]) + bg.z)));
-              v[4 * h2 + 3] = __fdividef(__uint_as_float(av[e + 3]) + ba.w, 1.f + __expf(-(__uint_as_float(gv[e + 3]) + bg.w)));
+              const float2 one2 = make_float2(1.f, 1.f);
+              const float2 a01 = ffma2(make_float2(__uint_as_float(av[e + 0]), __uint_as_float(av[e + 1])), one2, make_float2(ba.x, ba.y));
+              const float2 a23 = ffma2(make_float2(__uint_as_float(av[e + 2]), __uint_as_float(av[e + 3])), one2, make_float2(ba.z, ba.w));
+              const float2 g01 = ffma2(make_float2(__uint_as_float(gv[e + 0]), __uint_as_float(gv[e + 1])), one2, make_float2(bg.x, bg.y));
+              const float2 g23 = ffma2(make_float2(__uint_as_float(gv[e + 2]), __uint_as_float(gv[e + 3])), one2, make_float2(bg.z, bg.w));
+              const float2 o01 = gated2(a01, g01), o23 = gated2(a23, g23);
+              v[4 * h2 + 0] = o01.x;
+              v[4 * h2 + 1] = o01.y;
+              v[4 * h2 + 2] = o23.x;
+              v[4 * h2 + 3] = o23.y;
             }
             const int sl = 4 * hf + j;
             *reinterpret_cast<uint4*>(stage_u + lane * 32 + ((sl ^ (lane & 7)) << 2)) =
@@ -360,21 +385,28 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // 8 columns -> one 16-byte slot
           float v[8];
+          const float2 one2 = make_float2(1.f, 1.f);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + 2 * j + h);
-            v[4 * h + 0] = __uint_as_float(acc[8 * j + 4 * h + 0]) + b4.x;
-            v[4 * h + 1] = __uint_as_float(acc[8 * j + 4 * h + 1]) + b4.y;
-            v[4 * h + 2] = __uint_as_float(acc[8 * j + 4 * h + 2]) + b4.z;
-            v[4 * h + 3] = __uint_as_float(acc[8 * j + 4 * h + 3]) + b4.w;
+            // bias add (and SiLU) on column pairs with packed fp32 instructions
+            float2 lo = ffma2(make_float2(__uint_as_float(acc[8 * j + 4 * h + 0]), __uint_as_float(acc[8 * j + 4 * h + 1])),
+                              one2, make_float2(b4.x, b4.y));
+            float2 hi = ffma2(make_float2(__uint_as_float(acc[8 * j + 4 * h + 2]), __uint_as_float(acc[8 * j + 4 * h + 3])),
+                              one2, make_float2(b4.z, b4.w));
+            if (EPI == EPI_BF16_SILU) {
+              lo = gated2(lo, lo);
+              hi = gated2(hi, hi);
+            }
+            v[4 * h + 0] = lo.x;
+            v[4 * h + 1] = lo.y;
+            v[4 * h + 2] = hi.x;
+            v[4 * h + 3] = hi.y;
           }
           if (EPI == EPI_BF16_RELU) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-          } else if (EPI == EPI_BF16_SILU) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fast_silu(v[e]);
           }
           if (p.debug_skip_epi == 3 && v[0] != 123.456f) continue;  // tuning aid: TMEM loads + math only
           *reinterpret_cast<uint4*>(stage_u + lane * 32 + ((j ^ (lane & 7)) << 2)) =
