@@ -58,6 +58,42 @@ def test_oracle_equals_live_reference(wenet_ref, model_dirs, golden_cases, case)
             assert a.confidence == c.confidence and a.tokens_confidence == c.tokens_confidence
 
 
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_oracle_attention_mode_and_bounded_context_equal_live_reference(wenet_ref, model_dirs, golden_cases, case):
+    """The later restatements — `attention` decode mode (search.py:251-360) and decoding_chunk_size > 0
+    (utils/mask.py:88-197) — against the live reference with settings the committed fixtures do not use."""
+    from oracle import pipeline_ref
+    d, wav = model_dirs[case]
+    m = wenet_ref.load_model(d)
+    orc = pipeline_ref.OracleASR(d)
+    feats = m.compute_feats(wav, num_mel_bins=80, frame_length=25, frame_shift=10)
+    cat = torch.tensor([0.4, 0.6])
+    for fb, fl in m.feats_batcher(feats, 300, 2):
+        with torch.no_grad():
+            want = m.model.decode(["attention"], fb, fl, 5, length_penalty=0.3, cat_embs=cat,
+                                  infos={"tasks": ["transcribe"], "langs": ["en"]})
+            enc_ref, _ = m.model._forward_encoder(fb, fl, decoding_chunk_size=12, num_decoding_left_chunks=1, cat_embs=cat)
+            want_c = m.model.decode(["ctc_prefix_beam_search"], fb, fl, 6, decoding_chunk_size=12, num_decoding_left_chunks=1,
+                                    cat_embs=cat, infos={"tasks": ["transcribe"], "langs": ["en"]})
+        got = orc.decode(["attention"], fb, fl, 5, cat_embs=cat, length_penalty=0.3)
+        assert [list(r.tokens) for r in got["attention"]] == [list(r.tokens) for r in want["attention"]]
+        got_c = orc.decode(["ctc_prefix_beam_search"], fb, fl, 6, cat_embs=cat, return_intermediates=True,
+                           decoding_chunk_size=12, num_decoding_left_chunks=1)
+        assert torch.equal(enc_ref, got_c["_encoder_out"])
+        for a, c in zip(want_c["ctc_prefix_beam_search"], got_c["ctc_prefix_beam_search"]):
+            assert a.nbest == c.nbest and a.nbest_scores == c.nbest_scores and a.nbest_times == c.nbest_times
+
+
+def test_oracle_resample_equals_torchaudio():
+    import torchaudio
+    from oracle import resample_ref
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 7777, generator=g) * 3000
+    for rate in (8000, 32000, 44100):
+        want = torchaudio.transforms.Resample(orig_freq=rate, new_freq=16000)(x)
+        assert torch.equal(resample_ref.resample(x, rate, 16000), want)
+
+
 def test_host_post_processing_equals_live_reference(wenet_ref, golden_cases, model_dirs):
     """reverb_b200's ctc_align / CTM rendering vs the reference's, on the reference's own hypotheses."""
     from wenet.bin.ctc_align import adjust_model_time_offset as ref_adjust, ctc_align as ref_align
