@@ -159,6 +159,13 @@ RVB_API int rvb_decoder_step_topk(rvb_model* m, const float* d_enc_out, const in
  * [64j+32, 64j+64) their gates; out[m, c] = value * sigmoid(gate). */
 RVB_API int rvb_gemm_bf16(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int act, int out_mode,
                   float alpha, void* d_out, int ldo, void* stream);
+/* out[m] = log_softmax(A W^T + bias)[m, gather[m]] (0 where gather[m] < 0) without materialising the (M, N) logits:
+ * the GEMM epilogue emits per-slab (max, sum-exp) partials + the gathered logit into d_ws
+ * (rvb_gemm_logsoftmax_gather_ws_bytes(M, N) bytes), a second kernel merges them.  This is the output layer +
+ * log_softmax + per-token indexing of attention rescoring (asr_model.py:868-978, search.py:413-436).  N > 128. */
+RVB_API long long rvb_gemm_logsoftmax_gather_ws_bytes(int M, int N);
+RVB_API int rvb_gemm_logsoftmax_gather(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K,
+                                       const int* d_gather, void* d_ws, float* d_out, void* stream);
 RVB_API int rvb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, float eps, int M, int d,
                   void* d_out_bf16, float* d_out_f32, void* stream);
 /* q/k/v/out bf16, (B, T, H, dk) with the given row strides; p (Tk, H, dk) optional rel-pos keys */

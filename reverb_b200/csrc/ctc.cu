@@ -708,4 +708,34 @@ int launch_rescoring_inputs(const int* d_tokens, int tok_stride, const int* d_ou
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Second half of the fused log_softmax + gather (GEMM epilogue OUT_LSE, gemm.cu): combine the per-slab partials
+// (max, sum exp(x - max)) of a row into logsumexp and subtract it from the gathered logit.  One warp per row.
+__global__ void __launch_bounds__(256)
+lse_merge_kernel(const float2* __restrict__ part, int slabs, const float* __restrict__ tgt, const int* __restrict__ gather,
+                 int M, float* __restrict__ out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float2* pr = part + (size_t)row * slabs;
+  float m = -INFINITY;
+  for (int i = lane; i < slabs; i += 32) m = fmaxf(m, pr[i].x);
+  m = warp_max(m);
+  float s = 0.f;
+  for (int i = lane; i < slabs; i += 32) {
+    const float2 v = pr[i];
+    s += (v.x == -INFINITY) ? 0.f : v.y * expf(v.x - m);
+  }
+  s = warp_sum(s);
+  if (lane == 0) out[row] = (gather[row] >= 0) ? tgt[row] - (m + logf(s)) : 0.f;
+}
+
+int launch_lse_merge(const float2* part, int slabs, const float* tgt, const int* gather, int M, float* out,
+                     cudaStream_t stream) {
+  if (M <= 0) return 0;
+  lse_merge_kernel<<<(M * 32 + 255) / 256, 256, 0, stream>>>(part, slabs, tgt, gather, M, out);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace rvb

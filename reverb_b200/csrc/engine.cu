@@ -709,8 +709,7 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
   DevBuf* w = m->ws_dec;
   if (w[0].ensure((size_t)R * d * 4) || w[1].ensure((size_t)R * d * 2) || w[2].ensure((size_t)R * 3 * d * 2) ||
       w[3].ensure((size_t)R * d * 2) || w[4].ensure((size_t)Mem * 2 * d * 2) ||
-      w[5].ensure((size_t)R * c.dec_ffn_dim * 2) || w[6].ensure((size_t)R * d * 2) ||
-      m->ws_logits.ensure((size_t)R * ldv * 4))
+      w[5].ensure((size_t)R * c.dec_ffn_dim * 2) || w[6].ensure((size_t)R * d * 2))
     return -1;
   float* x = w[0].as<float>();
   bf16* n = w[1].as<bf16>();
@@ -719,7 +718,7 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
   bf16* kv = w[4].as<bf16>();
   bf16* h = w[5].as<bf16>();
   bf16* ybf = w[6].as<bf16>();
-  float* logits = m->ws_logits.as<float>();
+  float* logits = nullptr;
   const float scale = 1.0f / sqrtf((float)dk);
   if (launch_embed_posenc(d_tokens, D.emb, S, Lp, d, x, stream)) return -1;
   for (size_t l = 0; l < D.layers.size(); ++l) {
@@ -818,6 +817,8 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
   if (launch_layernorm(x, D.after.g, D.after.b, 1e-5f, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
   if (step_k > 0) {
     // rows s*Lp + (Lp-1): the A operand is the strided view (S, d) with leading dimension Lp*d
+    if (m->ws_logits.ensure((size_t)S * ldv * 4)) return -1;
+    logits = m->ws_logits.as<float>();
     GemmArgs g;
     g.A = n + (size_t)(Lp - 1) * d;
     g.lda = Lp * d;
@@ -834,6 +835,29 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
     if (launch_gemm(g, stream)) return -1;
     return launch_logsoftmax_topk(logits, ldv, S, V, step_k, d_step_val, d_step_idx, nullptr, 1, stream);
   }
+  if (get_gemm_impl() != 1 && V > 128) {
+    // log_softmax + gather fused into the output-layer GEMM: the (R, V) fp32 logits (4.2 GB at B = 64) are never
+    // written; the epilogue leaves per-slab (max, sum-exp) partials and the target logit, a small kernel merges them
+    const int slabs = lse_slabs(V);
+    if (w[7].ensure((size_t)R * slabs * sizeof(float2) + (size_t)R * sizeof(float))) return -1;
+    float2* part = w[7].as<float2>();
+    float* tgt = reinterpret_cast<float*>(part + (size_t)R * slabs);
+    GemmArgs g;
+    g.A = n;
+    g.W = D.outl.w;
+    g.bias = D.outl.b;
+    g.M = (int)R;
+    g.N = D.outl.N;
+    g.K = D.outl.K;
+    g.out_mode = OUT_LSE;
+    g.lse_gather = d_gather;
+    g.lse_part = part;
+    g.lse_tgt = tgt;
+    if (launch_gemm(g, stream)) return -1;
+    return launch_lse_merge(part, slabs, tgt, d_gather, (int)R, d_scores, stream);
+  }
+  if (m->ws_logits.ensure((size_t)R * ldv * 4)) return -1;
+  logits = m->ws_logits.as<float>();
   if (gemm(n, D.outl, (int)R, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
   return launch_logsoftmax_gather(logits, ldv, (int)R, V, d_gather, 1, d_scores, stream);
 }
@@ -1338,6 +1362,29 @@ RVB_API int rvb_gemm_bf16(const void* d_A, const void* d_W, const float* d_bias,
   g.out = d_out;
   g.ldo = ldo;
   return rvb::launch_gemm(g, (cudaStream_t)stream);
+}
+
+RVB_API long long rvb_gemm_logsoftmax_gather_ws_bytes(int M, int N) {
+  return (long long)M * rvb::lse_slabs(N) * (long long)sizeof(float2) + (long long)M * (long long)sizeof(float);
+}
+
+RVB_API int rvb_gemm_logsoftmax_gather(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K,
+                                       const int* d_gather, void* d_ws, float* d_out, void* stream) {
+  RVB_REQUIRE(d_A && d_W && d_gather && d_ws && d_out, "rvb_gemm_logsoftmax_gather: bad arguments");
+  const int slabs = rvb::lse_slabs(N);
+  rvb::GemmArgs g;
+  g.A = reinterpret_cast<const rvb::bf16*>(d_A);
+  g.W = reinterpret_cast<const rvb::bf16*>(d_W);
+  g.bias = d_bias;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.out_mode = rvb::OUT_LSE;
+  g.lse_gather = d_gather;
+  g.lse_part = reinterpret_cast<float2*>(d_ws);
+  g.lse_tgt = reinterpret_cast<float*>(g.lse_part + (size_t)M * slabs);
+  if (rvb::launch_gemm(g, (cudaStream_t)stream)) return -1;
+  return rvb::launch_lse_merge(g.lse_part, slabs, g.lse_tgt, d_gather, M, d_out, (cudaStream_t)stream);
 }
 
 RVB_API int rvb_layernorm(const float* d_x, const float* d_gamma, const float* d_beta, float eps, int M, int d,

@@ -57,6 +57,10 @@ struct GemmKParams {
   const int* row_lens;
   int rows_per_batch;
   int conv_mode, conv_T2, conv_F2, conv_tt, conv_cblocks;
+  const int* lse_gather;  // OUT_LSE (kernels.h)
+  float2* lse_part;
+  float* lse_tgt;
+  int lse_nslab;
   int debug_skip_epi;  // RVB_GEMM_SKIP_EPI=1 (tuning aid): epilogue warps only hand the accumulator back, no stores
   int glu_coalesced;   // ACT_GLU with 16-byte aligned output rows (always true after the launch checks)
   int bf16_coalesced;  // bf16 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
@@ -101,10 +105,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 
 // Epilogue variants (compile-time): the hot combinations get straight-line code, everything else goes through the
 // generic runtime path.  EPI_GENERIC reads act / out_mode from the kernel parameters.
-enum Epi { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_BF16_SILU = 2, EPI_F32 = 3, EPI_RESID = 4, EPI_GENERIC = 5, EPI_GLU = 6 };
+enum Epi { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_BF16_SILU = 2, EPI_F32 = 3, EPI_RESID = 4, EPI_GENERIC = 5, EPI_GLU = 6,
+           EPI_LSE = 7 };
 
 __host__ __device__ inline int select_epi(int act, int out_mode) {
   if (act == ACT_GLU) return EPI_GLU;
+  if (out_mode == OUT_LSE) return EPI_LSE;
   if (out_mode == OUT_BF16) return act == ACT_NONE ? EPI_BF16 : act == ACT_RELU ? EPI_BF16_RELU : EPI_BF16_SILU;
   if (act == ACT_NONE) return out_mode == OUT_F32 ? EPI_F32 : EPI_RESID;
   return EPI_GENERIC;
@@ -285,7 +291,49 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
     tc_fence_after();
     return;
   }
-  if constexpr (EPI == EPI_GLU) {
+  if constexpr (EPI == EPI_LSE) {
+    // log-sum-exp partial of x = acc + bias over this thread's columns [c0, c1) of the tile (one 128-column slab when
+    // 8 warps drain a 256-wide tile, two slabs with 4 warps) + the gather target if it falls inside
+    mbar_wait(tfull_bar, aphase);
+    tc_fence_after();
+    const int g = (orow >= 0) ? __ldg(p.lse_gather + orow) : -1;
+#pragma unroll 1
+    for (int cs = c0; cs < c1; cs += 128) {
+      float m = -INFINITY, ssum = 0.f;
+#pragma unroll 1
+      for (int c = cs; c < cs + 128 && c < c1; c += 32) {
+        const int n0 = n0_tile + c;
+        if (n0 >= p.N) break;
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + c, acc);
+        tmem_ld_wait();
+        float x[32];
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const bool in = n0 + j < p.N;
+          x[j] = in ? __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f) : -INFINITY;
+          cm = fmaxf(cm, x[j]);
+        }
+        if (g >= n0 && g < n0 + 32) {
+          float tg = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tg = (g == n0 + j) ? x[j] : tg;
+          p.lse_tgt[orow] = tg;
+        }
+        if (cm > m) {
+          ssum *= ex2_approx((m - cm) * 1.4426950408889634f);  // exp2(-inf) = 0 on the first chunk
+          m = cm;
+        }
+        float part = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) part += ex2_approx((x[j] - m) * 1.4426950408889634f);
+        ssum += part;
+      }
+      if (orow >= 0 && n0_tile + cs < ((p.N + 255) / 256) * 256)
+        p.lse_part[(size_t)orow * p.lse_nslab + ((n0_tile + cs) >> 7)] = make_float2(m, ssum);
+    }
+  } else if constexpr (EPI == EPI_GLU) {
     if (p.glu_coalesced && ((c1 - c0) & 127) == 0) {
       // 128 accumulator columns = 64 outputs = 128 bytes per row per round through the staging tile (as for bf16)
       const int slot = lane & 7, rsub = lane >> 3;
@@ -1026,6 +1074,7 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     case EPI_F32: kern = gemm_tc_kernel<BN, EPI_F32>; break;
     case EPI_RESID: kern = gemm_tc_kernel<BN, EPI_RESID>; break;
     case EPI_GLU: kern = gemm_tc_kernel<BN, EPI_GLU>; break;
+    case EPI_LSE: kern = gemm_tc_kernel<BN, EPI_LSE>; break;
     default: kern = gemm_tc_kernel<BN, EPI_GENERIC>; break;
   }
   RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -1085,6 +1134,7 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     case EPI_F32: kern = gemm_tc2_kernel<BN, EPI_F32>; break;
     case EPI_RESID: kern = gemm_tc2_kernel<BN, EPI_RESID>; break;
     case EPI_GLU: kern = gemm_tc2_kernel<BN, EPI_GLU>; break;
+    case EPI_LSE: kern = gemm_tc2_kernel<BN, EPI_LSE>; break;
     default: kern = gemm_tc2_kernel<BN, EPI_GENERIC>; break;
   }
   RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -1115,7 +1165,7 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
 }
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
-  RVB_REQUIRE(a.A && a.W && a.out, "gemm: null pointer");
+  RVB_REQUIRE(a.A && a.W && (a.out || a.out_mode == OUT_LSE), "gemm: null pointer");
   RVB_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0, "gemm: bad shape M=%d N=%d K=%d", a.M, a.N, a.K);
   if (g_num_sms == 0) {
     int dev = 0;
@@ -1137,6 +1187,15 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.row_lens = a.row_lens;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
   p.conv_mode = a.conv_mode;
+  p.lse_gather = a.lse_gather;
+  p.lse_part = a.lse_part;
+  p.lse_tgt = a.lse_tgt;
+  p.lse_nslab = lse_slabs(a.N);
+  if (a.out_mode == OUT_LSE) {
+    RVB_REQUIRE(a.lse_gather && a.lse_part && a.lse_tgt && a.act == ACT_NONE && !a.conv_mode && a.N > 128,
+                "gemm: OUT_LSE needs gather / partial / target buffers, no activation and N > 128");
+    RVB_REQUIRE(get_gemm_impl() != 1, "gemm: OUT_LSE is not built for the simt bring-up kernel");
+  }
   {
     static int forced = -1;  // RVB_GEMM_EPI_WARPS=4|8 overrides the K-based choice (tuning aid)
     if (forced < 0) {

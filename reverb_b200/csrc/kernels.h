@@ -13,8 +13,14 @@ enum GemmAct { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2, ACT_GLU = 3 };
 enum GemmOut {
   OUT_BF16 = 0,      // out_bf16[m, n] = act(acc + bias)
   OUT_F32 = 1,       // out_f32[m, n]  = act(acc + bias)
-  OUT_RESID_F32 = 2  // out_f32[m, n] += alpha * act(acc + bias)   (rows masked by row_lens are left untouched)
+  OUT_RESID_F32 = 2, // out_f32[m, n] += alpha * act(acc + bias)   (rows masked by row_lens are left untouched)
+  // no C matrix at all: per row m and per column slab (lse_slab(N) slabs of 128 columns) the epilogue emits the
+  // partial (max, sum exp(x - max)) of x = acc + bias over the slab -> lse_part[m, slab], and x[m, lse_gather[m]]
+  // -> lse_tgt[m] (rows with a negative gather index are skipped).  launch_lse_merge turns the partials into
+  // out[m] = x[m, gather[m]] - logsumexp_n x[m, n]: log_softmax + gather without ever writing the logits.
+  OUT_LSE = 3
 };
+inline int lse_slabs(int N) { return ((N + 255) / 256) * 2; }
 
 struct GemmArgs {
   // C[M,N] = A[M,K] * W[N,K]^T ; A, W bf16 row-major (K contiguous)
@@ -39,7 +45,14 @@ struct GemmArgs {
   //   K = 9*C ordered (kh, kw, c); output row (b, t', f) -> out[((b*T2 + t')*F2 + f) * ldo + n]
   int conv_mode = 0;
   int conv_B = 0, conv_T1h = 0, conv_F1 = 0, conv_C = 0, conv_T2 = 0, conv_F2 = 0;
+  // OUT_LSE
+  const int* lse_gather = nullptr;   // (M) column index per row, < 0 = none
+  float2* lse_part = nullptr;        // (M, lse_slabs(N)) {max, sum exp(x - max)}; slabs without columns hold {-inf, 0}
+  float* lse_tgt = nullptr;          // (M) the gathered x
 };
+// out[m] = gather[m] >= 0 ? tgt[m] - logsumexp(partials of row m) : 0
+int launch_lse_merge(const float2* part, int slabs, const float* tgt, const int* gather, int M, float* out,
+                     cudaStream_t stream);
 
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 // 0 = tcgen05/TMA kernel (default), 1 = plain CUDA-core debug kernel (env RVB_GEMM=simt)

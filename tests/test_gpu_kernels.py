@@ -360,3 +360,28 @@ def test_attention_tcgen05_chunk_mask(lib, chunk, left):
     for g in range(B):
         n = int(klens[g])
         torch.testing.assert_close(out[g, :n].float(), ref[g, :n], rtol=3e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("impl", [0, 2], ids=["tcgen05", "tcgen05_2cta"])
+@pytest.mark.parametrize("M,N,K", [(300, 1001, 128), (4133, 10001, 1024), (129, 257, 4096)])
+def test_gemm_fused_logsoftmax_gather(lib, impl, M, N, K):
+    """OUT_LSE epilogue + merge kernel: log_softmax(A W^T + b)[m, gather[m]] without writing the logits."""
+    torch.manual_seed(M + N)
+    lib.rvb_set_gemm_impl(impl)
+    try:
+        A = (torch.randn(M, K, device="cuda") * 0.5).bfloat16()
+        W = (torch.randn(N, K, device="cuda") * (3.0 / math.sqrt(K))).bfloat16()
+        bias = torch.randn(N, device="cuda")
+        gather = torch.randint(0, N, (M,), device="cuda", dtype=torch.int32)
+        gather[::7] = -1
+        gather[1] = N - 1
+        gather[2] = 0
+        ws = torch.empty(int(lib.rvb_gemm_logsoftmax_gather_ws_bytes(M, N)), device="cuda", dtype=torch.uint8)
+        out = torch.full((M,), 123.0, device="cuda")
+        _check(lib, lib.rvb_gemm_logsoftmax_gather(_p(A), _p(W), _p(bias), M, N, K, _p(gather), _p(ws), _p(out), _stream()))
+        logp = torch.log_softmax(A.float() @ W.float().t() + bias, dim=-1)
+        g = gather.long().clamp(min=0)
+        want = torch.where(gather >= 0, logp.gather(1, g[:, None])[:, 0], torch.zeros(M, device="cuda"))
+        torch.testing.assert_close(out, want, rtol=1e-3, atol=2e-3)
+    finally:
+        lib.rvb_set_gemm_impl(-1)
