@@ -309,11 +309,34 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
         tmem_ld_wait();
         float x[32];
         float cm = -INFINITY;
+        if (n0 + 32 <= p.N && p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+          // full chunk: vector bias loads, packed adds
+          const float2 one2 = make_float2(1.f, 1.f);
+          float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const bool in = n0 + j < p.N;
-          x[j] = in ? __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f) : -INFINITY;
-          cm = fmaxf(cm, x[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0) + j);
+            const float2 lo = ffma2(make_float2(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1])), one2,
+                                    make_float2(b4.x, b4.y));
+            const float2 hi = ffma2(make_float2(__uint_as_float(acc[4 * j + 2]), __uint_as_float(acc[4 * j + 3])), one2,
+                                    make_float2(b4.z, b4.w));
+            x[4 * j] = lo.x;
+            x[4 * j + 1] = lo.y;
+            x[4 * j + 2] = hi.x;
+            x[4 * j + 3] = hi.y;
+            mx[0] = fmaxf(mx[0], lo.x);
+            mx[1] = fmaxf(mx[1], lo.y);
+            mx[2] = fmaxf(mx[2], hi.x);
+            mx[3] = fmaxf(mx[3], hi.y);
+          }
+          cm = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const bool in = n0 + j < p.N;
+            x[j] = in ? __uint_as_float(acc[j]) + (p.bias ? __ldg(p.bias + n0 + j) : 0.f) : -INFINITY;
+            cm = fmaxf(cm, x[j]);
+          }
         }
         if (g >= n0 && g < n0 + 32) {
           float tg = 0.f;
@@ -325,10 +348,18 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
           ssum *= ex2_approx((m - cm) * 1.4426950408889634f);  // exp2(-inf) = 0 on the first chunk
           m = cm;
         }
-        float part = 0.f;
+        // sum exp(x - m) = sum exp2(x * log2e - m * log2e): one packed FFMA2 + two ex2 + one packed add per pair
+        const float2 l2 = make_float2(1.4426950408889634f, 1.4426950408889634f);
+        const float2 nm = make_float2(-m * 1.4426950408889634f, -m * 1.4426950408889634f);
+        float2 part01 = make_float2(0.f, 0.f), part23 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) part += ex2_approx((x[j] - m) * 1.4426950408889634f);
-        ssum += part;
+        for (int j = 0; j < 32; j += 4) {
+          const float2 t01 = ffma2(make_float2(x[j], x[j + 1]), l2, nm);
+          const float2 t23 = ffma2(make_float2(x[j + 2], x[j + 3]), l2, nm);
+          part01 = ffma2(make_float2(ex2_approx(t01.x), ex2_approx(t01.y)), make_float2(1.f, 1.f), part01);
+          part23 = ffma2(make_float2(ex2_approx(t23.x), ex2_approx(t23.y)), make_float2(1.f, 1.f), part23);
+        }
+        ssum += (part01.x + part01.y) + (part23.x + part23.y);
       }
       if (orow >= 0 && n0_tile + cs < ((p.N + 255) / 256) * 256)
         p.lse_part[(size_t)orow * p.lse_nslab + ((n0_tile + cs) >> 7)] = make_float2(m, ssum);
