@@ -212,3 +212,29 @@ def test_attention_beam_search_host_logic_equals_oracle_restatement():
         want = search_ref.attention_beam_search(t_step, B, maxlen, N, sos, eos, lp)
         got = attention_beam_search(n_step, B, maxlen, N, sos, eos, lp)
         assert [list(r.tokens) for r in got] == [list(r.tokens) for r in want]
+
+
+def test_attention_context_follows_add_optional_chunk_mask_rules():
+    """Which (chunk, left) the encoder applies (utils/mask.py:126-197): dynamic-chunk configs use the call's
+    decoding_chunk_size, static-chunk configs their own size, everything else full context."""
+    from reverb_b200.asr_model import ASRModel
+    m = ASRModel.__new__(ASRModel)
+    m.configs = {"encoder_conf": {"use_dynamic_chunk": True}}
+    assert m.attention_context(-1, -1) == (-1, -1)
+    assert m.attention_context(16, -1) == (16, -1)
+    assert m.attention_context(8, 2) == (8, 2)
+    with pytest.raises(AssertionError):
+        m.attention_context(0, -1)
+    m.configs = {"encoder_conf": {"use_dynamic_chunk": False, "static_chunk_size": 12}}
+    assert m.attention_context(-1, 3) == (12, 3)
+    assert m.attention_context(5, -1) == (12, -1)
+    m.configs = {"encoder_conf": {}}
+    assert m.attention_context(16, 2) == (-1, -1)
+
+
+def test_resample_table_shapes_and_lengths():
+    from reverb_b200.resample import resampled_length, sinc_resample_kernel
+    for rate, (o, n) in {8000: (1, 2), 48000: (3, 1), 44100: (441, 160), 22050: (441, 320)}.items():
+        kern, orig, new, width = sinc_resample_kernel(rate, 16000)
+        assert (orig, new) == (o, n) and kern.shape == (new, 2 * width + orig) and kern.dtype == np.float32
+        assert resampled_length(1000, orig, new) == -(-1000 * new // orig)
