@@ -1,5 +1,6 @@
 """N>1 path on CPU: world_size-2 gloo run of the chunk sharding + single all-gather (reverb_b200/dist.py)."""
 import os
+import pytest
 import socket
 import subprocess
 import sys
@@ -55,7 +56,8 @@ WORKER = textwrap.dedent("""
         return [DecodeResult([c, c + 1, 100 + c][: 1 + c %% 3], -float(c) - 0.5, 0.01 * c, [0.5] * (1 + c %% 3),
                              list(range(1 + c %% 3))) for c in range(c0, c1)]
     out = decode_sharded(decode_chunks, n_chunks, 16, torch.device("cpu"))
-    assert calls == [shard_range(n_chunks, rank, world)]
+    c0, c1 = shard_range(n_chunks, rank, world)
+    assert calls == ([(c0, c1)] if c1 > c0 else [])        # an empty shard decodes nothing but still gathers
     assert len(out) == n_chunks
     for c, r in enumerate(out):
         assert r.tokens == [c, c + 1, 100 + c][: 1 + c %% 3] and r.score == -float(c) - 0.5
@@ -65,13 +67,16 @@ WORKER = textwrap.dedent("""
 """)
 
 
-def test_world_size_2_gloo_gather(tmp_path):
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_gloo_gather_over_ranks(tmp_path, world):
+    """world 2 is the contract's minimum; 4 and 8 = the scaling run's process counts (8 ranks > the 7 chunks of the
+    worker, so one rank owns an EMPTY shard and must still take part in the all-gather)."""
     script = tmp_path / "worker.py"
     script.write_text(WORKER % ROOT)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)]
     env = dict(os.environ, OMP_NUM_THREADS="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
