@@ -5,12 +5,18 @@ decode of 30 s chunks (BASELINE.json metric), one process per GPU.
     python bench.py --gpus N --steps K --warmup W             # this repo's CUDA path
     python bench.py --impl reference --steps K --warmup W      # the reference algorithm on the host cores
 
-A "step" = one batch of `--chunks` (default 64) 30 s chunks per GPU through
-    fbank -> Conformer encoder -> CTC head -> ctc_prefix_beam_search -> attention_rescoring.
-`value`: int16 PCM already resident in HBM when the timed region starts.  `e2e`: the same step through the public
-host API with pinned HOST buffers — H2D of the PCM and D2H of the hypotheses inside the timed region.
-Weak scaling: every rank decodes its own `--chunks` chunks (chunks are independent units, no data-path collective;
-the only collective is the barrier / max-over-ranks of the timing contract).
+A "step" = one recording of N x `--chunks` (default 64) 30 s chunks, chunk-sharded over the N ranks (contiguous
+blocks, reverb_b200/dist.py): every rank runs
+    fbank -> Conformer encoder -> CTC head -> ctc_prefix_beam_search -> attention_rescoring
+on its 64 chunks and the step ENDS with the path's single collective, the NCCL all-gather of the per-chunk result
+records (tokens / times / confidences) — inside the timed region.  The K steps are software-pipelined on one stream by
+one host thread (ASRModel.decode_stream), the all-gathers run on a side stream.
+`value`: int16 PCM already resident in HBM when the timed region starts.  `e2e`: the same through the public host API
+with pinned HOST PCM — H2D of the PCM and D2H of the hypotheses inside the timed region.  Per-GPU work is fixed as N
+grows ("scaling": "weak").  `strong_scaling` (same JSON line): BASELINE configs[2] — ONE 3600 s recording = 121 chunks
+(120 x 2998 frames + a 238-frame tail) sharded over the N ranks through dist.transcribe_sharded (fbank per rank on its
+own sample range with the 240-sample overlap, all-gather at the end), the gathered CTM compared with a 1-GPU decode of
+the same recording on rank 0.
 """
 from __future__ import annotations
 
@@ -144,31 +150,91 @@ def pick_threads(orc) -> int:
     return best
 
 
-def run_cpu_reference(model_dir: str, n_chunks: int, steps: int, warmup: int, threads: int):
+def run_cpu_reference(model_dir: str, n_chunks: int, steps: int, warmup: int, threads: int, batch8: bool = False):
     """The reference algorithm (oracle port: same ATen CPU operators as the reference's torch.nn graph, same Python
-    searches) on the host cores.  One step = `n_chunks` 30 s chunks, batch_size 1 like the reference default.
-    Returns (RTFx, seconds per step, threads used)."""
-    from oracle import pipeline_ref
+    searches) on the host cores.  One step = `n_chunks` 30 s chunks, batch_size 1 like the reference default; the
+    reported time is the MEDIAN over the timed steps, with a per-stage split.  `batch8`: one extra
+    pass with 8 chunks stacked in one batch (the reference's --batch_size 8).
+    Returns a dict: rtfx, sec_per_step, threads, stages (seconds per step), results (chunk 0), batch8_rtfx."""
+    from oracle import fbank_np, model_ref, pipeline_ref, search_ref
     orc = pipeline_ref.OracleASR(model_dir)
     threads = pick_threads(orc) if threads <= 0 else threads
     torch.set_num_threads(threads)
-    pcm = make_pcm(n_chunks, seed=4321)
+    pcm = make_pcm(max(n_chunks, 8 if batch8 else 1), seed=4321)
     cat = torch.tensor([1.0, 0.0])
-    from oracle import fbank_np
+    keep = {}
 
-    def step():
-        for c in range(n_chunks):
-            feats = torch.from_numpy(fbank_np.fbank(pcm[c].astype(np.float32))).unsqueeze(0)
-            lens = torch.tensor([feats.shape[1]], dtype=torch.int32)
-            orc.decode(["attention_rescoring"], feats, lens, 10, ctc_weight=0.1, reverse_weight=0.0, cat_embs=cat)
+    def run(chunks, acc):
+        t0 = time.perf_counter()
+        feats = torch.from_numpy(np.stack([fbank_np.fbank(pcm[c].astype(np.float32)) for c in chunks]))
+        lens = torch.full((len(chunks),), feats.shape[1], dtype=torch.int32)
+        t1 = time.perf_counter()
+        with torch.no_grad():
+            enc, enc_lens, _ = orc.forward_encoder(feats, lens, cat)
+            t2 = time.perf_counter()
+            ctc = model_ref.ctc_logprobs(enc, orc.sd, 0.0, 0)
+            t3 = time.perf_counter()
+            prefix = search_ref.ctc_prefix_beam_search(ctc, enc_lens, 10, 0)
+            t4 = time.perf_counter()
+            resc = orc.attention_rescoring(prefix, enc, enc_lens, 0.1, 0.0, cat)
+        t5 = time.perf_counter()
+        for k, v in zip(("fbank", "encoder", "ctc_head", "prefix_beam", "rescoring"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            acc[k] = acc.get(k, 0.0) + v
+        if chunks[0] == 0:
+            keep.update(feats=feats[:1], enc=enc[:1], ctc=ctc[:1], prefix=prefix[0], resc=resc[0], pcm=pcm[0])
+        return t5 - t0
+
+    def step(acc):
+        return sum(run([c], acc) for c in range(n_chunks))
 
     for _ in range(warmup):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    return n_chunks * 30.0 * steps / dt, dt / steps, threads
+        step({})
+    times, stages = [], []
+    for _ in range(max(steps, 1)):
+        acc = {}
+        times.append(step(acc))
+        stages.append(acc)
+    med = statistics.median(times)
+    mean = sum(times) / len(times)
+    st = stages[times.index(sorted(times)[len(times) // 2])]
+    out = {"rtfx": n_chunks * 30.0 / med, "sec_per_step": med, "threads": threads, "passes": len(times), "mean_sec_per_step": mean,
+           "stages": {k: round(v, 4) for k, v in st.items()}, "results": keep, "batch8_rtfx": None}
+    if batch8:
+        out["batch8_rtfx"] = 8 * 30.0 / run(list(range(8)), {})
+    return out
+
+
+def parity_vs_cpu(asr, eng, model, cpu) -> dict:
+    """The CUDA path against the oracle pass the CPU baseline just timed (chunk 0 of its sample): measured tolerances
+    for the JSON line.  Tokens on IDENTICAL fbank features (the oracle's), fbank compared separately."""
+    k = cpu["results"]
+    if not k:
+        return {}
+    dev = asr.device
+    cat = torch.tensor([1.0, 0.0])
+    gf = eng.fbank_batch(torch.from_numpy(k["pcm"][None]).to(dev))
+    feats = k["feats"].to(dev)
+    lens = torch.full((1,), feats.shape[1], dtype=torch.int32)
+    enc, enc_lens = model._forward_encoder(feats, lens, cat)
+    logp = model.ctc_logprobs(enc).cpu()
+    res = model.decode(["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"], feats, lens, 10,
+                       ctc_weight=0.1, reverse_weight=0.0, blank_id=asr.blank_id, cat_embs=cat)
+    from oracle import search_ref
+    want_greedy = search_ref.ctc_greedy_search(k["ctc"], torch.tensor([int(enc_lens[0])]), 0)[0].tokens
+    a, b = enc[0].cpu().double(), k["enc"][0].double()
+    sel = k["ctc"] > -12
+    return {
+        "against": "oracle port (pinned bit-identical to the live reference), 1 x 30 s chunk, identical fbank features",
+        "fbank_max_abs": float((gf[0].cpu() - k["feats"][0]).abs().max()),
+        "encoder_rel_rms": float(((a - b) ** 2).mean().sqrt() / (b ** 2).mean().sqrt()),
+        "ctc_logp_max_abs": float((logp - k["ctc"])[sel].abs().max()),
+        "ctc_argmax_agreement": float((logp.argmax(-1) == k["ctc"].argmax(-1)).float().mean()),
+        "greedy_ids_equal": list(res["ctc_greedy_search"][0].tokens) == list(want_greedy),
+        "prefix_best_equal": list(res["ctc_prefix_beam_search"][0].tokens) == list(k["prefix"].tokens),
+        "rescoring_tokens_equal": list(res["attention_rescoring"][0].tokens) == list(k["resc"].tokens),
+        "rescoring_score_abs_diff": abs(float(res["attention_rescoring"][0].score) - float(k["resc"].score)),
+        "tokens": len(k["resc"].tokens),
+    }
 
 
 def _claim_stdout():
@@ -202,6 +268,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=1, help="concurrent decoding lanes (streams + host threads) per GPU")
     ap.add_argument("--profile-step", action="store_true",
                     help="after warm-up run ONE step between cudaProfilerStart/Stop and exit (for `ncu --profile-from-start off`)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (configs[2]) record")
     ap.add_argument("--breakdown", action="store_true", help="print a per-stage wall-clock split (synchronised) to stderr")
     args = ap.parse_args()
 
@@ -214,7 +281,9 @@ def main():
     config = {"workload": f"BASELINE configs[1]: {args.chunks}x30s chunks per GPU, {stages}, synthetic reverb_asr_v1 shape "
                           f"(d={shape['d']}, L={shape['blocks']}, V={shape['vocab']})", "mode": args.mode,
               "chunk_frames": CHUNK_FRAMES, "chunks_per_gpu": args.chunks, "beam_size": 10, "ctc_weight": 0.1,
-              "reverse_weight": args.reverse_weight, "parallelism": f"chunk-sharded x{world}", "lanes_per_gpu": args.lanes,
+              "reverse_weight": args.reverse_weight, "parallelism": f"chunk-sharded x{world} + all-gather of the result records per step",
+              "pipelining": "software-pipelined on one stream (decode_stream)" if args.lanes <= 1 else f"{args.lanes} lanes",
+              "lanes_per_gpu": args.lanes,
               "l2_policy": "inputs larger than L2 (61 MB PCM, multi-GB activations per step); no explicit flush"}
 
     # ------------------------------------------------------------------ reference arm (host cores)
@@ -222,13 +291,16 @@ def main():
         if rank != 0:
             return
         mdir = model_dir_for(args.shape)
-        val, sec, threads = run_cpu_reference(mdir, args.cpu_chunks, max(args.steps, 1), max(args.warmup, 0), 0)
+        cpu = run_cpu_reference(mdir, args.cpu_chunks, max(args.steps, 1), max(args.warmup, 0), 0)
+        sec = cpu["mean_sec_per_step"]                      # exactly K timed steps: total / K
+        val = args.cpu_chunks * 30.0 / sec
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu["threads"], "kind": "port",
                                  "sample": f"{args.cpu_chunks} x 30 s chunks per step, batch_size 1, torch "
-                                           f"{torch.__version__} CPU fp32"},
+                                           f"{torch.__version__} CPU fp32, {cpu['passes']} timed steps",
+                                 "median_value": cpu["rtfx"], "stages_s_per_step": cpu["stages"]},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         _emit(real_stdout, line)
         return
@@ -247,6 +319,7 @@ def main():
     mdir = model_dir_for(args.shape)
     import reverb_b200
     from reverb_b200 import _lib
+    from reverb_b200 import dist as rdist
     from reverb_b200.engine import launch_count
     asr = reverb_b200.ReverbASR(os.path.join(mdir, "config.yaml"), os.path.join(mdir, "synth.pt"), gpu=local_rank)
     lib = _lib.load()
@@ -255,41 +328,48 @@ def main():
     pcm_dev = pcm_host.to(dev)
     cat = torch.tensor([1.0, 0.0])
     lens = torch.full((args.chunks,), CHUNK_FRAMES, dtype=torch.int32)
-    stats = {"d2h": 0, "tokens": 0}
+    max_tok = eng.encoder_out_frames(CHUNK_FRAMES)
+    gatherer = rdist.RecordGatherer(dev, args.chunks, max_tok)
+    dkw = dict(ctc_weight=0.1, reverse_weight=args.reverse_weight, blank_id=asr.blank_id, cat_embs=cat)
 
-    def decode_device(pcm: torch.Tensor):
-        feats = eng.fbank_batch(pcm)                                                      # (B, 2998, 80)
-        res = model.decode([args.mode], feats, lens, 10, ctc_weight=0.1,
-                           reverse_weight=args.reverse_weight, blank_id=asr.blank_id, cat_embs=cat)
-        return res[args.mode]
+    def batches(n, e2e):
+        # one batch per step: (this rank's 64 chunks of) one recording; fbank on the device
+        for _ in range(n):
+            pcm = pcm_host.to(dev, non_blocking=True) if e2e else pcm_dev
+            yield eng.fbank_batch(pcm), lens
+
+    def run_steps(n, e2e):
+        """n steps, software-pipelined; every step's records are all-gathered (side stream); returns the last step's
+        local hypotheses and the gathered records of every step."""
+        hyps, handles = None, []
+        for res in model.decode_stream(batches(n, e2e), [args.mode], 10, **dkw):
+            hyps = res[args.mode]
+            handles.append(gatherer.submit(hyps))
+        recs = [gatherer.wait(h) for h in handles]
+        return hyps, recs
 
     lanes = None
     if args.lanes > 1:
         from reverb_b200.pipeline import Lanes
         lanes = Lanes(asr, args.lanes)
         assert args.chunks % args.lanes == 0
-    per = args.chunks // max(args.lanes, 1)
-    lens_lane = lens[:per]
+        per = args.chunks // args.lanes
+        lens_lane = lens[:per]
 
-    def lane_job(mdl, pcm):     # pcm: (per, samples) int16, device or pinned host
-        if not pcm.is_cuda:
-            pcm = pcm.to(dev, non_blocking=True)
-        feats = mdl.engine.fbank_batch(pcm)
-        res = mdl.decode([args.mode], feats, lens_lane, 10, ctc_weight=0.1,
-                         reverse_weight=args.reverse_weight, blank_id=asr.blank_id, cat_embs=cat)
-        return res[args.mode]
+        def lane_job(mdl, pcm):     # pcm: (per, samples) int16, device or pinned host
+            if not pcm.is_cuda:
+                pcm = pcm.to(dev, non_blocking=True)
+            feats = mdl.engine.fbank_batch(pcm)
+            return mdl.decode([args.mode], feats, lens_lane, 10, **dkw)[args.mode]
 
-    def step_resident():
-        if lanes is None:
-            return decode_device(pcm_dev)
-        outs = lanes.run([pcm_dev[i * per:(i + 1) * per] for i in range(args.lanes)], lane_job)
-        return [h for o in outs for h in o]
-
-    def step_e2e():
-        if lanes is None:
-            return decode_device(pcm_host.to(dev, non_blocking=True))
-        outs = lanes.run([pcm_host[i * per:(i + 1) * per] for i in range(args.lanes)], lane_job)
-        return [h for o in outs for h in o]
+        def run_steps(n, e2e):       # noqa: F811 — thread-per-lane variant (--lanes > 1)
+            hyps, handles = None, []
+            src = pcm_host if e2e else pcm_dev
+            for _ in range(n):
+                outs = lanes.run([src[i * per:(i + 1) * per] for i in range(args.lanes)], lane_job)
+                hyps = [h for o in outs for h in o]
+                handles.append(gatherer.submit(hyps))
+            return hyps, [gatherer.wait(h) for h in handles]
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -297,12 +377,11 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    def timed(fn, steps):
+    def timed(fn):
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            out = fn()
+        out = fn()
         e1.record()
         sync_all()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -310,13 +389,12 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), out
 
-    for _ in range(max(args.warmup, 3)):
-        step_resident()
+    run_steps(max(args.warmup, 3), False)
 
     if args.profile_step:
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.start()
-        step_resident()
+        run_steps(1, False)
         torch.cuda.synchronize(dev)
         torch.cuda.profiler.stop()
         print("profiled one step", file=sys.stderr)
@@ -340,27 +418,39 @@ def main():
         tick("prefix_beam only (gpu+copy)", lambda: eng.prefix_beam_search_raw(tv, ti, enc_lens, 10, asr.blank_id), acc)
         raw = tick("prefix_beam+rescoring decoder (fused native call)",
                    lambda: eng.beam_search_rescoring(tv, ti, enc, enc_lens, 10, asr.blank_id, cat, args.reverse_weight), acc)
-        tick("host pick", lambda: rescoring_pick_batch(*raw[:5], raw[5], raw[6], 0.1, args.reverse_weight), acc)
+        hy = tick("host pick", lambda: rescoring_pick_batch(*raw[:5], raw[5], raw[6], 0.1, args.reverse_weight), acc)
+        tick("pack records", lambda: rdist.pack_results(hy, args.chunks, max_tok), acc)
+        tick("whole step, not pipelined", lambda: model.decode([args.mode], eng.fbank_batch(pcm_dev), lens, 10, **dkw), acc)
         print("BREAKDOWN " + json.dumps({k: round(v, 2) for k, v in acc}), file=sys.stderr)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     l0 = launch_count()
     lib.rvb_gemm_profile_begin()
-    ms, hyps = timed(step_resident, args.steps)
+    ms, (hyps, recs) = timed(lambda: run_steps(args.steps, False))
     gms, gfl, gn = C.c_double(), C.c_double(), C.c_longlong()
     lib.rvb_gemm_profile_end(C.byref(gms), C.byref(gfl), C.byref(gn))
     launches = launch_count() - l0
     clk = clocks.stop() if rank == 0 else None
     audio_s = args.chunks * 30.0 * args.steps * world
     value = audio_s / (ms / 1e3)
+    # the gathered records of the last step must hold every rank's chunks, this rank's block at its place
+    got = rdist.unpack_results(recs[-1], max_tok)
+    assert len(recs) == args.steps and len(got) == args.chunks * world, (len(recs), len(got))
+    mine = got[rank * args.chunks:(rank + 1) * args.chunks]
+    assert all(list(a.tokens) == list(b.tokens) and a.times == b.times for a, b in zip(mine, hyps)), "all-gather corrupted the records"
 
     # end-to-end through the host API (pinned host PCM in, host hypotheses out)
-    step_e2e()
-    ms_e2e, hyps = timed(step_e2e, args.steps)
+    run_steps(1, True)
+    ms_e2e, (hyps, recs) = timed(lambda: run_steps(args.steps, True))
     e2e_val = audio_s / (ms_e2e / 1e3)
     n_tok = sum(len(h.tokens) for h in hyps)
     d2h = int(getattr(eng, "last_d2h_bytes", 0))     # counted by the engine from the arrays the native call fills
+    gather_bytes = int(recs[-1].nbytes) if world > 1 else 0
+
+    strong = None
+    if not args.no_strong:
+        strong = run_strong_scaling(asr, rdist, dev, rank, world, args, sync_all)
 
     if rank != 0:
         if world > 1:
@@ -391,7 +481,7 @@ def main():
         "dtype": "bf16", "data": "synthetic", "config": config,
         "clocks": clk,
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(pcm_host.numel() * 2),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps},
+                "d2h_bytes_per_step": int(d2h) + gather_bytes, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel (2-CTA tcgen05 + TMA, all dense layers incl. conv2 implicit GEMM)",
                      "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
@@ -399,20 +489,98 @@ def main():
                      "traffic_source": traffic_src,
                      "launches_timed": int(gn.value), "kernel_ms_per_step": gms.value / args.steps,
                      "kernel_share_of_step": gms.value / ms if ms > 0 else None,
-                     "algorithmic_flops_per_step": gfl.value / args.steps},
+                     "algorithmic_flops_per_step": gfl.value / args.steps,
+                     "whole_step_tflops": (gfl.value / (ms / 1e3)) / 1e12 if ms > 0 else None,
+                     "whole_step_frac_of_peak": (gfl.value / (ms / 1e3)) / 1e12 / peak_tf if ms > 0 else None},
+        "collective": {"op": "all_gather_into_tensor of per-chunk records, one per step, inside the timed region",
+                       "bytes_per_rank_per_step": int(args.chunks * rdist.record_words(max_tok) * 4), "ranks": world},
         "tokens_per_step": n_tok,
         "encoder_ctc_tflop_per_step": algorithmic_flops_per_chunk(shape) * args.chunks / 1e12,
     }
+    if strong is not None:
+        line["strong_scaling"] = strong
     if not args.no_cpu_baseline and world == 1:
         t0 = time.time()
-        val, sec, threads = run_cpu_reference(mdir, args.cpu_chunks, 1, 0, 0)
-        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{args.cpu_chunks} x 30 s chunks (one timed pass after a thread-count probe), batch_size 1, "
-                                          f"oracle port of the reference on torch {torch.__version__} CPU fp32, "
-                                          f"{time.time() - t0:.0f} s wall"}
+        cpu = run_cpu_reference(mdir, args.cpu_chunks, 3, 1, 0, batch8=True)
+        line["cpu_baseline"] = {"value": cpu["rtfx"], "unit": UNIT, "cores": cpu["threads"], "kind": "port",
+                                "sample": f"{args.cpu_chunks} x 30 s chunks per pass, batch_size 1: median of 3 passes after 1 "
+                                          f"warm-up and a thread-count probe; oracle port of the reference on torch "
+                                          f"{torch.__version__} CPU fp32, {time.time() - t0:.0f} s wall",
+                                "stages_s_per_pass": cpu["stages"],
+                                "batch_size_8_value": cpu["batch8_rtfx"]}
+        try:
+            line["parity"] = parity_vs_cpu(asr, eng, model, cpu)
+        except Exception as e:      # the parity read-out must never cost the bench line
+            line["parity"] = {"error": repr(e)}
     _emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()
+
+
+STRONG_SECONDS = 3600.0
+
+
+def run_strong_scaling(asr, rdist, dev, rank, world, args, sync_all):
+    """BASELINE configs[2]: ONE 1 h recording, 121 chunks of 30 s (the last one 238 frames), sharded over the ranks
+    (dist.transcribe_sharded: contiguous chunk blocks, fbank per rank on its own samples, ONE all-gather of the result
+    records).  Timed with CUDA events, max over ranks, host PCM -> gathered DecodeResults on every rank."""
+    import torch.distributed as dist
+    n_samples = int(STRONG_SECONDS * 16000)
+    base = make_pcm(5, seed=977)
+    reps = -(-n_samples // base.size)
+    pcm = np.tile(base.reshape(-1), reps)[:n_samples].copy()
+    g = 1.0 - 0.04 * ((np.arange(n_samples) // CHUNK_SAMPLES // 5) % 8)          # chunks differ
+    pcm = (pcm.astype(np.float32) * g.astype(np.float32)).astype(np.int16)
+    total_frames, n_chunks = rdist.chunk_plan(n_samples, CHUNK_FRAMES)
+    kw = dict(mode="attention_rescoring", chunk_size=CHUNK_FRAMES, batch_size=args.chunks, beam_size=10, ctc_weight=0.1,
+              reverse_weight=args.reverse_weight)
+
+    def once():
+        return rdist.transcribe_sharded(asr, pcm, **kw)
+
+    once()
+    times = []
+    for _ in range(3):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hyps = once()
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        times.append(float(ms.item()))
+    ms = statistics.median(times)
+    assert len(hyps) == n_chunks
+    out = {"workload": f"BASELINE configs[2]: one {STRONG_SECONDS:.0f} s recording = {n_chunks} chunks of 30 s (last: "
+                       f"{total_frames - (n_chunks - 1) * CHUNK_FRAMES} frames), attention_rescoring, chunk-sharded x{world}, "
+                       f"batches of <= {args.chunks}",
+           "scaling": "strong", "value": STRONG_SECONDS / (ms / 1e3), "unit": UNIT, "ms": ms, "runs_ms": times,
+           "n_gpus": world, "chunks": n_chunks, "chunks_per_rank": -(-n_chunks // world),
+           "collective": "one all_gather_into_tensor of the per-chunk records, inside the timed region",
+           "timed": "host int16 PCM -> fbank per rank -> decode -> all-gather -> DecodeResults on every rank"}
+    if world > 1 and rank == 0:
+        # the same recording decoded by rank 0 alone (no process group involved) must give the same CTM
+        from reverb_b200.reverb import get_output
+        total, nch = rdist.chunk_plan(n_samples, CHUNK_FRAMES)
+        wave = torch.from_numpy(pcm).pin_memory().to(dev, non_blocking=True)
+        feats = asr.engine.fbank(wave)[:total].unsqueeze(0)
+        cat = torch.tensor([1.0, 0.0])
+        solo = []
+        for res in asr.model.decode_stream(asr.feats_batcher(feats, CHUNK_FRAMES, args.chunks), ["attention_rescoring"], 10,
+                                           ctc_weight=0.1, reverse_weight=args.reverse_weight, blank_id=asr.blank_id,
+                                           cat_embs=cat):
+            solo.extend(res["attention_rescoring"])
+        fmt = lambda hs: get_output("ctm", asr.tokenizer, "strong.wav", hs, 230, CHUNK_FRAMES, asr.input_frame_length,
+                                    asr.output_frame_length)
+        a, b = fmt(hyps), fmt(solo)
+        words = lambda t: [ln.split(" ")[:5] for ln in t.split("\n")]
+        out["ctm_equal_to_1gpu"] = (a == b)
+        out["ctm_words_times_equal_to_1gpu"] = (words(a) == words(b))
+        out["ctm_lines"] = a.count("\n") + 1
+        assert words(a) == words(b), "sharded decode changed the transcript"
+    return out
 
 
 if __name__ == "__main__":

@@ -52,6 +52,8 @@ typedef struct rvb_model_config {
   int dec_ffn_dim;      /* decoder_conf.linear_units */
   int dec_blocks;       /* decoder_conf.num_blocks */
   int r_dec_blocks;     /* decoder_conf.r_num_blocks (0: no right-to-left decoder) */
+  int sos_id;           /* tokenizer_conf.special_tokens["<sos>"]; <= 0: vocab - 1 (asr_model.py:79-82) */
+  int eos_id;           /* tokenizer_conf.special_tokens["<eos>"]; <= 0: vocab - 1 */
 } rvb_model_config;
 
 /* ---- diagnostics -------------------------------------------------------------------------------------------- */
@@ -143,6 +145,26 @@ RVB_API int rvb_beam_search_rescoring(rvb_model* m, const float* d_topk_val, con
                                       int blank_id, const float* h_cat_embs, int n_cat, float reverse_weight, int cap,
                                       int* h_tokens, int* h_times, int* h_lens, double* h_scores, int* h_nhyp,
                                       float* h_l2r, float* h_r2l, int* out_max_len, void* stream);
+
+/* The same three stages as separate calls around a ticket (0 .. 3 per plan), so that ONE host thread can software-
+ * pipeline consecutive batches on one stream: between the calls it enqueues the next batch's encoder, and the GPU never
+ * waits for the host (the decoder batch is padded to the longest hypothesis, which the host must learn first).
+ *   rvb_search_submit     enqueues the prefix beam search (+ the small copy of lengths / counts / CTC scores);
+ *                         returns the ticket (>= 0) or < 0.  d_enc_out must stay valid until the ticket is collected.
+ *   rvb_rescoring_submit  blocks until that small copy has landed, then enqueues the decoder passes (run_decoder != 0)
+ *                         and the copies of tokens / times / decoder scores INTO THE CALLER'S h_ buffers, which must be
+ *                         page-locked for the call to stay asynchronous and must stay valid until collect;
+ *                         *out_max_len = L as in rvb_beam_search_rescoring.  run_decoder == 0: prefix beam search only.
+ *   rvb_rescoring_collect blocks until those copies are done, fills h_lens / h_scores / h_nhyp, re-indexes h_r2l to
+ *                         hypothesis order and frees the ticket. */
+RVB_API int rvb_search_submit(rvb_model* m, const float* d_topk_val, const int* d_topk_idx, int k, const float* d_enc_out,
+                              const int* h_enc_lens, int B, int Tp, int beam, int blank_id, void* stream);
+RVB_API int rvb_rescoring_submit(rvb_model* m, int ticket, const float* h_cat_embs, int n_cat, float reverse_weight, int cap,
+                                 int run_decoder, int* h_tokens, int* h_times, float* h_l2r, float* h_r2l,
+                                 int* out_max_len, void* stream);
+RVB_API int rvb_rescoring_collect(rvb_model* m, int ticket, int* h_lens, double* h_scores, int* h_nhyp);
+/* abandon a ticket in any state (waits for its pending copies; used on error paths) */
+RVB_API int rvb_ticket_release(rvb_model* m, int ticket);
 
 /* One step of the autoregressive `attention` decode mode (attention_beam_search, search.py:251-360: the
  * decoder.forward_one_step + logp.topk(beam) pair of lines 302-306).  h_hyps (B*N, L) int32: the running hypotheses

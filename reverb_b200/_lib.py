@@ -17,7 +17,8 @@ class ModelConfig(C.Structure):
     """Mirror of `rvb_model_config` (include/rvb_b200.h)."""
     _fields_ = [(n, C.c_int) for n in (
         "input_dim", "d_model", "heads", "ffn_dim", "num_blocks", "cnn_kernel", "causal",
-        "cnn_layer_norm", "num_langs", "vocab", "dec_heads", "dec_ffn_dim", "dec_blocks", "r_dec_blocks")]
+        "cnn_layer_norm", "num_langs", "vocab", "dec_heads", "dec_ffn_dim", "dec_blocks", "r_dec_blocks",
+        "sos_id", "eos_id")]
 
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -50,6 +51,10 @@ SIGNATURES = {
     "rvb_ctc_prefix_beam_search": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rvb_beam_search_rescoring": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _f, _i, _vp, _vp, _vp, _vp, _vp,
                                        _vp, _vp, _vp, _vp]),
+    "rvb_search_submit": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "rvb_rescoring_submit": (_i, [_vp, _i, _vp, _i, _f, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rvb_rescoring_collect": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "rvb_ticket_release": (_i, [_vp, _i]),
     "rvb_decoder_step_topk": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "rvb_attention_rescoring": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp]),
     "rvb_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),

@@ -14,7 +14,7 @@ from typing import Dict, List, Optional
 import numpy as np
 import torch
 
-from .engine import Engine
+from .engine import Engine, check_beam_size
 from .search import (DecodeResult, attention_beam_search, greedy_results, prefix_beam_results, rescoring_pick,
                      rescoring_pick_batch)
 
@@ -72,15 +72,18 @@ class ASRModel:
     def ctc_logprobs(self, encoder_out: torch.Tensor, blank_penalty: float = 0.0, blank_id: int = 0) -> torch.Tensor:
         return self.engine.ctc_topk(encoder_out, 1, blank_penalty, blank_id, want_logp=True)[2]
 
-    @torch.no_grad()
-    def decode(self, methods: List[str], speech: torch.Tensor, speech_lengths: torch.Tensor, beam_size: int,
-               decoding_chunk_size: int = -1, num_decoding_left_chunks: int = -1, ctc_weight: float = 0.0,
-               simulate_streaming: bool = False, reverse_weight: float = 0.0, context_graph=None,
-               blank_id: int = 0, blank_penalty: float = 0.0, length_penalty: float = 0.0,
-               infos: Optional[Dict[str, List[str]]] = None, cat_embs: Optional[torch.Tensor] = None,
-               cv=None, cv_lengths=None) -> Dict[str, List[DecodeResult]]:
+    # -- decode() in three stages (A: everything that can be enqueued without looking at a result; B: the decoder
+    # passes, which need the n-best lengths on the host; C: collect + host-side score combination), so that
+    # decode_stream can overlap the host work of one batch with the GPU work of the next ones ----------------------
+    def _stage_a(self, methods: List[str], speech: torch.Tensor, speech_lengths: torch.Tensor, beam_size: int,
+                 decoding_chunk_size: int = -1, num_decoding_left_chunks: int = -1, ctc_weight: float = 0.0,
+                 simulate_streaming: bool = False, reverse_weight: float = 0.0, context_graph=None,
+                 blank_id: int = 0, blank_penalty: float = 0.0, length_penalty: float = 0.0,
+                 infos: Optional[Dict[str, List[str]]] = None, cat_embs: Optional[torch.Tensor] = None,
+                 cv=None, cv_lengths=None) -> dict:
         assert speech.shape[0] == speech_lengths.shape[0]
         assert decoding_chunk_size != 0
+        check_beam_size(beam_size)
         if simulate_streaming and decoding_chunk_size > 0:
             # encoder.forward_chunk_by_chunk (encoder.py:231-402): chunk-by-chunk with att / cnn caches
             raise NotImplementedError("reverb_b200: simulate_streaming (cache-based chunk-by-chunk encoding) is not built; "
@@ -98,7 +101,9 @@ class ASRModel:
         need_beam = "ctc_prefix_beam_search" in methods or "attention_rescoring" in methods
         k = beam_size if need_beam else 1
         topk_val, topk_idx, _ = self.engine.ctc_topk(encoder_out, k, blank_penalty, blank_id)
-        results: Dict[str, List[DecodeResult]] = {}
+        st = {"methods": list(methods), "results": {}, "ticket": None, "cat_embs": cat_embs, "ctc_weight": ctc_weight,
+              "reverse_weight": reverse_weight, "stage": 1}
+        results = st["results"]
         if "attention" in methods:
             # autoregressive beam search with the left decoder (search.py:251-360); the decoder step runs on the GPU,
             # the beam bookkeeping on the host like the reference's
@@ -109,14 +114,23 @@ class ASRModel:
         if "ctc_greedy_search" in methods:
             results["ctc_greedy_search"] = greedy_results(self.engine.greedy_search(topk_idx, encoder_lens, blank_id))
         if need_beam:
-            l2r = r2l = None
-            if "attention_rescoring" in methods:
-                # fused native path: the n-best stays on the device between the search and the decoder
-                toks, tims, olen, scores, nhyp, l2r, r2l = self.engine.beam_search_rescoring(
-                    topk_val, topk_idx, encoder_out, encoder_lens, beam_size, blank_id, cat_embs, reverse_weight)
-            else:
-                toks, tims, olen, scores, nhyp = self.engine.prefix_beam_search_raw(topk_val, topk_idx, encoder_lens,
-                                                                                    beam_size, blank_id)
+            # the n-best stays on the device between the search and the decoder (native ticket, include/rvb_b200.h)
+            st["ticket"] = self.engine.search_submit(topk_val, topk_idx, encoder_out, encoder_lens, beam_size, blank_id)
+        return st
+
+    def _stage_b(self, st: dict) -> None:
+        if st["stage"] != 1:
+            return
+        st["stage"] = 2
+        if st["ticket"] is not None:
+            self.engine.rescoring_submit(st["ticket"], st["cat_embs"], st["reverse_weight"],
+                                         run_decoder="attention_rescoring" in st["methods"])
+
+    def _stage_c(self, st: dict) -> Dict[str, List[DecodeResult]]:
+        self._stage_b(st)
+        results, methods = st["results"], st["methods"]
+        if st["ticket"] is not None:
+            toks, tims, olen, scores, nhyp, l2r, r2l = self.engine.rescoring_collect(st["ticket"])
             if "ctc_prefix_beam_search" in methods:
                 per_utt = []
                 for b in range(toks.shape[0]):
@@ -127,8 +141,49 @@ class ASRModel:
                 results["ctc_prefix_beam_search"] = prefix_beam_results(per_utt)
             if "attention_rescoring" in methods:
                 results["attention_rescoring"] = rescoring_pick_batch(toks, tims, olen, scores, nhyp, l2r, r2l,
-                                                                      ctc_weight, reverse_weight)
+                                                                      st["ctc_weight"], st["reverse_weight"])
+            st["ticket"] = None
+        st["stage"] = 3
         return results
+
+    @torch.no_grad()
+    def decode(self, methods: List[str], speech: torch.Tensor, speech_lengths: torch.Tensor, beam_size: int,
+               decoding_chunk_size: int = -1, num_decoding_left_chunks: int = -1, ctc_weight: float = 0.0,
+               simulate_streaming: bool = False, reverse_weight: float = 0.0, context_graph=None,
+               blank_id: int = 0, blank_penalty: float = 0.0, length_penalty: float = 0.0,
+               infos: Optional[Dict[str, List[str]]] = None, cat_embs: Optional[torch.Tensor] = None,
+               cv=None, cv_lengths=None) -> Dict[str, List[DecodeResult]]:
+        st = self._stage_a(methods, speech, speech_lengths, beam_size, decoding_chunk_size, num_decoding_left_chunks,
+                           ctc_weight, simulate_streaming, reverse_weight, context_graph, blank_id, blank_penalty,
+                           length_penalty, infos, cat_embs, cv, cv_lengths)
+        try:
+            return self._stage_c(st)
+        finally:
+            self.engine.ticket_release(st["ticket"])
+
+    @torch.no_grad()
+    def decode_stream(self, batches, methods: List[str], beam_size: int, **kwargs):
+        """decode() over an iterable of (speech, speech_lengths) batches, software-pipelined on the current stream by
+        this one host thread; yields the per-batch result dicts in order.  Chunks are independent units
+        (cli/reverb.py:214-234), so the results equal the batch-by-batch loop of the reference.
+
+        Schedule (A = encoder + CTC head + prefix beam, B = decoder passes, C = collect + host score combination):
+            A(0) | A(1) B(0) | A(2) B(1) C(0) | A(3) B(2) C(1) | ...
+        B(n-1) is enqueued right after A(n), so while the host waits for the n-best lengths of batch n-1 (they size
+        the decoder batch) or combines the scores of batch n-2, the GPU still has a whole encoder pass queued."""
+        inflight = []
+        try:
+            for speech, speech_lengths in batches:
+                inflight.append(self._stage_a(methods, speech, speech_lengths, beam_size, **kwargs))
+                if len(inflight) >= 2:
+                    self._stage_b(inflight[-2])
+                if len(inflight) >= 3:
+                    yield self._stage_c(inflight.pop(0))
+            while inflight:
+                yield self._stage_c(inflight.pop(0))
+        finally:
+            for st in inflight:          # only non-empty when a stage raised or the consumer stopped early
+                self.engine.ticket_release(st["ticket"])
 
     def attention_rescoring(self, prefix_results: List[DecodeResult], encoder_out: torch.Tensor, encoder_lens,
                             ctc_weight: float = 0.0, reverse_weight: float = 0.0, cat_embs=None) -> List[DecodeResult]:

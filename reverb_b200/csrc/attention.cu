@@ -265,12 +265,8 @@ template <int DK, bool HAS_POS>
 static int launch_attn_t(const AttnKParams& p, int Bq, cudaStream_t stream) {
   constexpr int NMAT = HAS_POS ? 3 : 2;
   const size_t smem = (size_t)2 * NMAT * ATT_BN * (DK + ATT_PAD) * sizeof(bf16);
-  static bool configured = false;
-  if (!configured && smem > 48 * 1024) {
-    RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_kernel<DK, HAS_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)smem));
-    configured = true;
-  }
+  static DynSmemOptIn optin;
+  if (optin.ensure(attention_kernel<DK, HAS_POS>, smem)) return -1;
   dim3 grid((p.Tq + ATT_BM - 1) / ATT_BM, p.H, Bq);
   attention_kernel<DK, HAS_POS><<<grid, ATT_THREADS, smem, stream>>>(p);
   RVB_COUNT_LAUNCH();

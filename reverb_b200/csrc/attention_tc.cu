@@ -565,29 +565,20 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
   if (bn_sel == 128) {
     const size_t smem = AtCfg<128>::SMEM_FIXED + (size_t)((a.Tk + 127) / 128) * 128 * sizeof(float);
     RVB_REQUIRE(smem <= 227 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    static DynSmemOptIn optin;
+    if (optin.ensure(attention_tc_kernel<128, 4>, smem)) return -1;
     attention_tc_kernel<128, 4><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
   } else if (sw_sel == 4) {
     const size_t smem = AtCfg<64>::SMEM_FIXED + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
     RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    static DynSmemOptIn optin;
+    if (optin.ensure(attention_tc_kernel<64, 4>, smem)) return -1;
     attention_tc_kernel<64, 4><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
   } else {
     const size_t smem = AtCfg<64>::SMEM_FIXED + 3072 + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
     RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-      RVB_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<64, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
+    static DynSmemOptIn optin;
+    if (optin.ensure(attention_tc_kernel<64, 8>, smem)) return -1;
     attention_tc_kernel<64, 8><<<grid, 288, smem, stream>>>(tmQ, tmK, tmV, p);
   }
   RVB_COUNT_LAUNCH();

@@ -42,6 +42,26 @@ extern std::atomic<unsigned long long> g_launch_count;
 
 typedef __nv_bfloat16 bf16;
 
+// Opt-in to > 48 KB of dynamic shared memory.  cudaFuncSetAttribute applies to the CURRENT device only, so the size
+// already configured is remembered per device (a second model on another GPU of the same process must opt in again).
+struct DynSmemOptIn {
+  static constexpr int kMaxDev = 64;
+  std::atomic<size_t> cfg[kMaxDev];
+  DynSmemOptIn() {
+    for (auto& c : cfg) c.store(0);
+  }
+  template <typename K>
+  int ensure(K kernel, size_t bytes) {
+    if (bytes <= 48 * 1024) return 0;
+    int dev = 0;
+    RVB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < kMaxDev && cfg[dev].load(std::memory_order_relaxed) >= bytes) return 0;
+    RVB_CHECK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev >= 0 && dev < kMaxDev) cfg[dev].store(bytes, std::memory_order_relaxed);
+    return 0;
+  }
+};
+
 // ---------------------------------------------------------------- small device helpers
 // Blackwell packed fp32 FMA (SASS FFMA2): two independent fp32 FMAs per instruction, bit-identical to two FFMAs
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {

@@ -185,11 +185,8 @@ int launch_logsoftmax_topk(const float* logits, int ld, int M, int V, int k, flo
   if (M <= 0) return 0;
   const size_t smem = (size_t)V * sizeof(float);
   RVB_REQUIRE(smem <= 200 * 1024, "logsoftmax_topk: V=%d too large for the shared-memory row cache", V);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    RVB_CHECK_CUDA(cudaFuncSetAttribute(logsoftmax_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  static DynSmemOptIn optin;
+  if (optin.ensure(logsoftmax_topk_kernel, smem)) return -1;
   logsoftmax_topk_kernel<<<M, 256, smem, stream>>>(logits, ld, V, k, topk_val, topk_idx, logp_out, apply_softmax);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
@@ -617,11 +614,8 @@ int launch_ctc_prefix_beam(const float* topk_val, const int* topk_idx, int k, co
   const int trie_in_smem = trie_bytes <= 150 * 1024;
   if (!trie_in_smem) RVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0xFF, need, stream));  // hash tables = -1
   const size_t dyn = trie_in_smem ? trie_bytes : 0;
-  static size_t configured = 0;
-  if (dyn > configured) {
-    RVB_CHECK_CUDA(cudaFuncSetAttribute(ctc_prefix_beam_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    configured = dyn;
-  }
+  static DynSmemOptIn optin;
+  if (optin.ensure(ctc_prefix_beam_kernel, dyn)) return -1;
   ctc_prefix_beam_kernel<<<B, PB_THREADS, dyn, stream>>>(topk_val, topk_idx, k, lens, T, beam, blank,
                                                         reinterpret_cast<int*>(workspace), trie_in_smem, max_len,
                                                         out_tokens, out_times, out_lens, out_scores, out_nhyp);
@@ -676,11 +670,11 @@ int launch_logsoftmax_gather(const float* logits, int ld, int M, int V, const in
 
 // ---------------------------------------------------------------------------------------------------------------
 // Decoder inputs of attention rescoring, built on the device from the n-best the prefix beam search left there:
-// hypothesis s = (b, i) has U tokens w (0 when i >= nhyp[b]);  sos == eos == V-1 (asr_model.py:79-82)
+// hypothesis s = (b, i) has U tokens w (0 when i >= nhyp[b]);  sos / eos from the model config (asr_model.py:79-82)
 //   tok_l = [sos, w_1..w_U, eos..]                 tok_r = [sos, w_U..w_1, eos..]          (asr_model.py:921-949)
 //   gat_l = [w_1..w_U, eos, -1..]                  gat_r = [w_U..w_1, eos, -1..]           (search.py:417-430)
 __global__ void rescoring_inputs_kernel(const int* __restrict__ tok, int tok_stride, const int* __restrict__ olen,
-                                        const int* __restrict__ nhyp, int N, int Lp, int sos_eos,
+                                        const int* __restrict__ nhyp, int N, int Lp, int sos, int eos,
                                         int* __restrict__ tok_l, int* __restrict__ tok_r, int* __restrict__ gat_l,
                                         int* __restrict__ gat_r, int* __restrict__ slen) {
   const int s = blockIdx.x, b = s / N, i = s - b * N;
@@ -689,19 +683,19 @@ __global__ void rescoring_inputs_kernel(const int* __restrict__ tok, int tok_str
   const int* wv = tok + (size_t)s * tok_stride;
   for (int j = threadIdx.x; j < Lp; j += blockDim.x) {
     const size_t r = (size_t)s * Lp + j;
-    tok_l[r] = (j == 0) ? sos_eos : (j <= U ? wv[j - 1] : sos_eos);
-    tok_r[r] = (j == 0) ? sos_eos : (j <= U ? wv[U - j] : sos_eos);
-    gat_l[r] = (j < U) ? wv[j] : (j == U ? sos_eos : -1);
-    gat_r[r] = (j < U) ? wv[U - 1 - j] : (j == U ? sos_eos : -1);
+    tok_l[r] = (j == 0) ? sos : (j <= U ? wv[j - 1] : eos);
+    tok_r[r] = (j == 0) ? sos : (j <= U ? wv[U - j] : eos);
+    gat_l[r] = (j < U) ? wv[j] : (j == U ? eos : -1);
+    gat_r[r] = (j < U) ? wv[U - 1 - j] : (j == U ? eos : -1);
   }
   if (threadIdx.x == 0) slen[s] = U + 1;
 }
 
 int launch_rescoring_inputs(const int* d_tokens, int tok_stride, const int* d_out_lens, const int* d_nhyp, int B, int N,
-                            int Lp, int sos_eos, int* tok_l, int* tok_r, int* gat_l, int* gat_r, int* slen,
+                            int Lp, int sos, int eos, int* tok_l, int* tok_r, int* gat_l, int* gat_r, int* slen,
                             cudaStream_t stream) {
   if (B * N <= 0) return 0;
-  rescoring_inputs_kernel<<<B * N, 128, 0, stream>>>(d_tokens, tok_stride, d_out_lens, d_nhyp, N, Lp, sos_eos, tok_l,
+  rescoring_inputs_kernel<<<B * N, 128, 0, stream>>>(d_tokens, tok_stride, d_out_lens, d_nhyp, N, Lp, sos, eos, tok_l,
                                                      tok_r, gat_l, gat_r, slen);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();

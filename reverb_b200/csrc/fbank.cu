@@ -27,17 +27,20 @@ struct FbankTables {
   float* mel_w = nullptr;    // [80][FB_MAXW]
   int* mel_start = nullptr;  // [80]
   int* mel_len = nullptr;    // [80]
-  int device = -1;
 };
-static FbankTables g_fb;
-
+// one table set per device (a process may hold models on several GPUs); entries are written once under the mutex
+constexpr int FB_MAXDEV = 64;
+static FbankTables g_fb_dev[FB_MAXDEV];
 static std::mutex g_fb_mutex;
 
-static int init_fbank_tables() {
+static int init_fbank_tables(const FbankTables** out) {
   std::lock_guard<std::mutex> lock(g_fb_mutex);
   int dev = 0;
   RVB_CHECK_CUDA(cudaGetDevice(&dev));
-  if (g_fb.window != nullptr && g_fb.device == dev) return 0;
+  RVB_REQUIRE(dev >= 0 && dev < FB_MAXDEV, "fbank: device index %d out of range", dev);
+  *out = &g_fb_dev[dev];
+  if (g_fb_dev[dev].window != nullptr) return 0;
+  FbankTables g_fb;  // published to g_fb_dev[dev] only when complete
   std::vector<float> win(FB_WIN);
   for (int i = 0; i < FB_WIN; ++i) {
     double h = 0.5 - 0.5 * cos(2.0 * M_PI * i / (FB_WIN - 1));
@@ -84,7 +87,7 @@ static int init_fbank_tables() {
   RVB_CHECK_CUDA(cudaMemcpy(g_fb.mel_w, w.data(), sizeof(float) * FB_NBIN * FB_MAXW, cudaMemcpyHostToDevice));
   RVB_CHECK_CUDA(cudaMemcpy(g_fb.mel_start, st.data(), sizeof(int) * FB_NBIN, cudaMemcpyHostToDevice));
   RVB_CHECK_CUDA(cudaMemcpy(g_fb.mel_len, ln.data(), sizeof(int) * FB_NBIN, cudaMemcpyHostToDevice));
-  g_fb.device = dev;
+  g_fb_dev[dev] = g_fb;
   return 0;
 }
 
@@ -185,7 +188,9 @@ fbank_kernel(const TIn* __restrict__ wave_all, long long wave_stride, long long 
 template <typename TIn>
 static int launch_fbank_t(const TIn* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream,
                           int batch = 1, long long wave_stride = 0) {
-  if (init_fbank_tables()) return -1;
+  const FbankTables* fb = nullptr;
+  if (init_fbank_tables(&fb)) return -1;
+  const FbankTables& g_fb = *fb;
   long long expect = n_samples < FB_WIN ? 0 : 1 + (n_samples - FB_WIN) / FB_SHIFT;
   RVB_REQUIRE(n_frames <= expect, "fbank: %lld frames requested but only %lld fit %lld samples", n_frames, expect,
               n_samples);

@@ -165,7 +165,7 @@ int launch_logsoftmax_gather(const float* logits, int ld, int M, int V, const in
                              cudaStream_t stream);
 // decoder inputs / gather targets (B*N rows of Lp) from the device-resident n-best of launch_ctc_prefix_beam
 int launch_rescoring_inputs(const int* d_tokens, int tok_stride, const int* d_out_lens, const int* d_nhyp, int B, int N,
-                            int Lp, int sos_eos, int* tok_l, int* tok_r, int* gat_l, int* gat_r, int* slen,
+                            int Lp, int sos, int eos, int* tok_l, int* tok_r, int* gat_l, int* gat_r, int* slen,
                             cudaStream_t stream);
 
 }  // namespace rvb

@@ -97,18 +97,63 @@ def unpack_results(rec: np.ndarray, max_tokens: int) -> List[DecodeResult]:
     return out
 
 
+def gather_records(rec: np.ndarray, device: torch.device) -> np.ndarray:
+    """all-gather of every rank's (per, W) int32 record block -> (world * per, W), rank order == chunk order."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return rec
+    if device.type == "cuda":
+        src = torch.from_numpy(rec).pin_memory().to(device, non_blocking=True)
+    else:
+        src = torch.from_numpy(rec)
+    out = torch.empty((world * rec.shape[0], rec.shape[1]), dtype=torch.int32, device=src.device)
+    dist.all_gather_into_tensor(out, src.contiguous())
+    return out.cpu().numpy()
+
+
 def gather_chunk_results(local: Sequence[DecodeResult], n_chunks: int, max_tokens: int,
                          device: torch.device) -> List[DecodeResult]:
     """The single collective of the path: all-gather of the per-chunk records, in chunk order."""
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     per = -(-n_chunks // world) if n_chunks > 0 else 0
-    rec = torch.from_numpy(pack_results(local, per, max_tokens)).to(device)
-    if world == 1:
-        return unpack_results(rec.cpu().numpy(), max_tokens)
-    out = torch.empty((world * per, rec.shape[1]), dtype=torch.int32, device=device)
-    dist.all_gather_into_tensor(out, rec.contiguous())
-    return unpack_results(out.cpu().numpy(), max_tokens)
+    return unpack_results(gather_records(pack_results(local, per, max_tokens), device), max_tokens)
+
+
+class RecordGatherer:
+    """The same all-gather, asynchronous: packs on the host, then H2D -> NCCL all-gather -> D2H on a SIDE stream, so a
+    pipelined decoder (ASRModel.decode_stream) keeps enqueueing the next batches on the main stream; `wait` returns
+    the gathered records.  One instance per fixed (chunks per rank, max_tokens) shape."""
+
+    def __init__(self, device: torch.device, per_rank: int, max_tokens: int):
+        import torch.distributed as dist
+        self.dist = dist
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.device, self.per, self.max_tokens = device, per_rank, max_tokens
+        self.side = torch.cuda.Stream(device=device) if device.type == "cuda" else None
+
+    def submit(self, local: Sequence[DecodeResult]):
+        rec = pack_results(local, self.per, self.max_tokens)
+        if self.world == 1:
+            return {"host": torch.from_numpy(rec), "ev": None}
+        if self.side is None:                       # CPU process group (gloo, tests): synchronous
+            return {"host": torch.from_numpy(gather_records(rec, self.device)), "ev": None}
+        src_h = torch.from_numpy(rec).pin_memory()
+        out_h = torch.empty((self.world * self.per, rec.shape[1]), dtype=torch.int32, pin_memory=True)
+        with torch.cuda.stream(self.side):
+            src = src_h.to(self.device, non_blocking=True)
+            out = torch.empty(out_h.shape, dtype=torch.int32, device=self.device)
+            self.dist.all_gather_into_tensor(out, src)
+            out_h.copy_(out, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+        return {"host": out_h, "ev": ev, "keep": (src_h, src, out)}
+
+    def wait(self, h) -> np.ndarray:
+        if h["ev"] is not None:
+            h["ev"].synchronize()
+        return h["host"].numpy()
 
 
 def decode_sharded(decode_chunks: Callable[[int, int], List[DecodeResult]], n_chunks: int, max_tokens: int,
@@ -138,9 +183,9 @@ def transcribe_sharded(asr, pcm: np.ndarray, mode: str = "attention_rescoring", 
         wave = torch.from_numpy(np.ascontiguousarray(pcm[s0:s1])).pin_memory().to(asr.device, non_blocking=True)
         feats = asr.engine.fbank(wave)[:nfr].unsqueeze(0)
         out: List[DecodeResult] = []
-        for fb, fl in asr.feats_batcher(feats, chunk_size, batch_size):
-            res = asr.model.decode([mode], fb, fl, beam_size, ctc_weight=ctc_weight, reverse_weight=reverse_weight,
-                                   blank_id=asr.blank_id, blank_penalty=blank_penalty, cat_embs=cat)
+        for res in asr.model.decode_stream(asr.feats_batcher(feats, chunk_size, batch_size), [mode], beam_size,
+                                           ctc_weight=ctc_weight, reverse_weight=reverse_weight, blank_id=asr.blank_id,
+                                           blank_penalty=blank_penalty, cat_embs=cat):
             out.extend(res[mode])
         return out
 

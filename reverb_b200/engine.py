@@ -14,6 +14,17 @@ from . import _lib
 from ._lib import ModelConfig, check
 
 
+# beam width the search kernels are built for (PB_MAXBEAM in csrc/ctc.cu; top-k <= 16 in logsoftmax_topk_kernel).
+# The reference accepts any --beam_size; its CLI default is 10.
+MAX_BEAM_SIZE = 16
+
+
+def check_beam_size(beam_size: int) -> None:
+    if not 1 <= int(beam_size) <= MAX_BEAM_SIZE:
+        raise ValueError(f"reverb_b200: beam_size={beam_size} is outside the supported range 1..{MAX_BEAM_SIZE} "
+                         "(the GPU prefix-beam / top-k kernels keep the beam in shared memory)")
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -55,6 +66,10 @@ def model_config_from_yaml(configs: Dict, vocab: int) -> ModelConfig:
     cfg.dec_ffn_dim = dc.get("linear_units", 2048)
     cfg.dec_blocks = dc.get("num_blocks", 6)
     cfg.r_dec_blocks = r_blocks
+    # asr_model.py:79-82: <sos>/<eos> from tokenizer_conf.special_tokens, else vocab - 1 for both
+    st = (configs.get("tokenizer_conf") or {}).get("special_tokens") or {}
+    cfg.sos_id = int(st.get("<sos>", vocab - 1))
+    cfg.eos_id = int(st.get("<eos>", vocab - 1))
     return cfg
 
 
@@ -262,42 +277,74 @@ class Engine:
             out.append((nbest, [float(s) for s in scores[b, :n]], times))
         return out
 
-    def beam_search_rescoring(self, topk_val: torch.Tensor, topk_idx: torch.Tensor, enc_out: torch.Tensor, enc_lens,
-                              beam: int, blank_id: int = 0, cat_embs=None, reverse_weight: float = 0.0):
-        """ctc_prefix_beam_search + attention_rescoring decoder scores in one native call (the n-best never leaves
-        the device in between).  -> (toks, tims (B, beam, L) int32, olen (B, beam, 2), ctc scores (B, beam) float64,
-        n_hyp (B,), l2r, r2l (B, beam, L+1) float32; r2l None when unused)."""
+    # ---- prefix beam search (+ attention rescoring) as three stages around a native ticket, so that one host thread
+    # can software-pipeline consecutive batches (asr_model.ASRModel.decode_stream): see include/rvb_b200.h
+    def search_submit(self, topk_val: torch.Tensor, topk_idx: torch.Tensor, enc_out: torch.Tensor, enc_lens, beam: int,
+                      blank_id: int = 0) -> dict:
+        """Enqueue ctc_prefix_beam_search; returns the ticket (a dict that keeps every buffer of the batch alive)."""
         B, Tp, k = topk_idx.shape
         lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
-        cap = max(int(lens.max()) if B else 1, 1)
-        toks = np.empty(B * beam * cap, dtype=np.int32)
-        tims = np.empty(B * beam * cap, dtype=np.int32)
+        enc_out = enc_out.contiguous()
+        with torch.cuda.device(self.device):
+            tid = self.lib.rvb_search_submit(self._h, _ptr(topk_val), _ptr(topk_idx), k, _ptr(enc_out), _np_ptr(lens), B, Tp,
+                                             beam, int(blank_id), self._stream())
+        if tid < 0:
+            raise RuntimeError("rvb_search_submit failed: " + _lib.last_error())
+        return {"id": tid, "B": B, "Tp": Tp, "beam": beam, "cap": max(int(lens.max()) if B else 1, 1),
+                "keep": (topk_val, topk_idx, enc_out, lens), "stage": 1}
+
+    def rescoring_submit(self, t: dict, cat_embs=None, reverse_weight: float = 0.0, run_decoder: bool = True) -> None:
+        """Wait for the hypothesis lengths of ticket `t`, then enqueue the decoder passes (attention rescoring) and the
+        device -> host copies of the results into page-locked buffers owned by the ticket."""
+        B, beam, cap = t["B"], t["beam"], t["cap"]
+        n = B * beam
+        use_r = run_decoder and reverse_weight > 0.0 and self.has_right_decoder
+        # page-locked result buffers: the native call copies straight into them (no staging copy)
+        t["toks"] = torch.empty(n * cap, dtype=torch.int32, pin_memory=True)
+        t["tims"] = torch.empty(n * cap, dtype=torch.int32, pin_memory=True)
+        t["l2r"] = torch.empty(n * (cap + 1), dtype=torch.float32, pin_memory=True) if run_decoder else None
+        t["r2l"] = torch.empty(n * (cap + 1), dtype=torch.float32, pin_memory=True) if use_r else None
+        L = C.c_int(0)
+        cat, ncat = self._cat(cat_embs) if run_decoder else (None, 0)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_rescoring_submit(self._h, t["id"], _np_ptr(cat), ncat, float(reverse_weight), cap,
+                                                int(bool(run_decoder)), _ptr(t["toks"]), _ptr(t["tims"]), _ptr(t["l2r"]),
+                                                _ptr(t["r2l"]), C.byref(L), self._stream()), "rvb_rescoring_submit")
+        t["L"], t["use_r"], t["run_decoder"], t["stage"] = L.value, use_r, bool(run_decoder), 2
+
+    def rescoring_collect(self, t: dict):
+        """-> (toks, tims (B, beam, L) int32, olen (B, beam, 2), ctc scores (B, beam) float64, n_hyp (B,), l2r, r2l
+        (B, beam, L+1) float32; l2r / r2l None when unused)."""
+        B, beam, L = t["B"], t["beam"], t["L"]
+        n = B * beam
         olen = np.empty((B, beam, 2), dtype=np.int32)
         scores = np.empty((B, beam), dtype=np.float64)
         nhyp = np.empty(B, dtype=np.int32)
-        l2r = np.empty(B * beam * (cap + 1), dtype=np.float32)
-        use_r = reverse_weight > 0.0 and self.has_right_decoder
-        r2l = np.empty(B * beam * (cap + 1), dtype=np.float32) if use_r else None
-        L = C.c_int(0)
-        cat, ncat = self._cat(cat_embs)
-        with torch.cuda.device(self.device):
-            check(self.lib.rvb_beam_search_rescoring(self._h, _ptr(topk_val), _ptr(topk_idx), k, _ptr(enc_out.contiguous()),
-                                                     _np_ptr(lens), B, Tp, beam, int(blank_id), _np_ptr(cat), ncat,
-                                                     float(reverse_weight), cap, _np_ptr(toks), _np_ptr(tims),
-                                                     _np_ptr(olen), _np_ptr(scores), _np_ptr(nhyp), _np_ptr(l2r),
-                                                     _np_ptr(r2l), C.byref(L), self._stream()),
-                  "rvb_beam_search_rescoring")
-        L = L.value
-        n = B * beam
-        # bytes the native call copied device -> host (lengths, counts, CTC scores, tokens, times, decoder scores)
+        check(self.lib.rvb_rescoring_collect(self._h, t["id"], _np_ptr(olen), _np_ptr(scores), _np_ptr(nhyp)),
+              "rvb_rescoring_collect")
+        t["stage"] = 3
+        # bytes copied device -> host for this batch (lengths, counts, CTC scores, tokens, times, decoder scores)
         self.last_d2h_bytes = (olen.nbytes + nhyp.nbytes + scores.nbytes + 2 * n * L * 4
-                               + n * (L + 1) * 4 * (2 if use_r else 1))
-        toks = toks[:n * L].reshape(B, beam, L)
-        tims = tims[:n * L].reshape(B, beam, L)
-        l2r = l2r[:n * (L + 1)].reshape(B, beam, L + 1)
-        if r2l is not None:
-            r2l = r2l[:n * (L + 1)].reshape(B, beam, L + 1)
+                               + (n * (L + 1) * 4 * (2 if t["use_r"] else 1) if t["run_decoder"] else 0))
+        toks = t["toks"].numpy()[:n * L].reshape(B, beam, L)
+        tims = t["tims"].numpy()[:n * L].reshape(B, beam, L)
+        l2r = t["l2r"].numpy()[:n * (L + 1)].reshape(B, beam, L + 1) if t["l2r"] is not None else None
+        r2l = t["r2l"].numpy()[:n * (L + 1)].reshape(B, beam, L + 1) if t["r2l"] is not None else None
         return toks, tims, olen, scores, nhyp, l2r, r2l
+
+    def ticket_release(self, t: Optional[dict]) -> None:
+        """Abandon a ticket that will not be collected (error paths)."""
+        if t is not None and t.get("stage", 3) < 3:
+            self.lib.rvb_ticket_release(self._h, t["id"])
+            t["stage"] = 3
+
+    def beam_search_rescoring(self, topk_val: torch.Tensor, topk_idx: torch.Tensor, enc_out: torch.Tensor, enc_lens,
+                              beam: int, blank_id: int = 0, cat_embs=None, reverse_weight: float = 0.0):
+        """ctc_prefix_beam_search + attention_rescoring decoder scores, the n-best never leaving the device in between
+        (the three stages above back to back).  -> see rescoring_collect."""
+        t = self.search_submit(topk_val, topk_idx, enc_out, enc_lens, beam, blank_id)
+        self.rescoring_submit(t, cat_embs, reverse_weight, True)
+        return self.rescoring_collect(t)
 
     def decoder_step_topk(self, enc_out: torch.Tensor, enc_lens, hyps: np.ndarray, n_per_utt: int, cat_embs=None,
                           k: int = 10):

@@ -23,30 +23,37 @@ class Lanes:
         for _ in range(n_lanes - 1):
             self.models.append(ASRModel(asr.engine.fork(), asr.configs, asr.configs["output_dim"]))
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_lanes)]
+        # one worker PER LANE: a lane's plan (workspace, pinned staging, CUDA stream) is only ever driven by the one
+        # host thread that owns it, whatever the number of jobs
         self.pool = ThreadPoolExecutor(max_workers=n_lanes)
 
     def __len__(self):
         return len(self.models)
 
     def run(self, jobs: Sequence, fn: Callable):
-        """fn(model, job) for every job, job i on lane i % n; returns results in job order.
-        Work already queued on the caller's current stream is visible to the lanes."""
+        """fn(model, job) for every job; lane l processes jobs l, l + n, l + 2n, ... sequentially on its own stream
+        and plan; returns results in job order.  Work already queued on the caller's current stream is visible to
+        the lanes."""
+        jobs = list(jobs)
+        n = len(self.models)
         producer = torch.cuda.current_stream(self.device)
         ready = torch.cuda.Event()
         ready.record(producer)
+        results = [None] * len(jobs)
 
-        def task(i, job):
-            lane = i % len(self.models)
+        def lane_task(lane):
             torch.cuda.set_device(self.device)
             stream = self.streams[lane]
             with torch.cuda.stream(stream):
                 stream.wait_event(ready)
-                out = fn(self.models[lane], job)
+                for i in range(lane, len(jobs), n):
+                    results[i] = fn(self.models[lane], jobs[i])
                 stream.synchronize()
-            return out
 
-        futures = [self.pool.submit(task, i, job) for i, job in enumerate(jobs)]
-        return [f.result() for f in futures]
+        futures = [self.pool.submit(lane_task, lane) for lane in range(min(n, len(jobs)))]
+        for f in futures:
+            f.result()
+        return results
 
     def close(self):
         self.pool.shutdown(wait=True)

@@ -27,7 +27,7 @@ import yaml
 
 from .asr_model import ASRModel
 from .ctc_align import adjust_model_time_offset, ctc_align, hyps_to_ctm, hyps_to_txt
-from .engine import Engine
+from .engine import Engine, check_beam_size
 from .search import DecodeResult
 from .text import get_blank_id, init_tokenizer
 
@@ -75,11 +75,27 @@ class ReverbASR:
         self.configs["output_dim"] = len(self.tokenizer.symbol_table)
 
         sd = _load_state_dict(checkpoint)
-        if overwrite_cmvn or "encoder.global_cmvn.mean" not in sd:
+        # utils/init_model.py:102-117 + load_checkpoint: GlobalCMVN exists only when `cmvn: global_cmvn`; it is built
+        # from the stats file and then overwritten by the checkpoint's buffers when the checkpoint holds them.
+        # cli/reverb.py:80-85: `overwrite_cmvn` puts the file's stats back (the reference reads the top-level
+        # `cmvn_file` / `is_json_cmvn` keys there; the cmvn_conf entries are accepted as well).
+        input_dim = self.configs.get("input_dim", 80)
+        if self.configs.get("cmvn", None) == "global_cmvn":
             from .cmvn import load_cmvn
-            mean, istd = load_cmvn(self.configs["cmvn_conf"]["cmvn_file"], self.configs["cmvn_conf"]["is_json_cmvn"])
-            sd["encoder.global_cmvn.mean"] = torch.from_numpy(mean).float()
-            sd["encoder.global_cmvn.istd"] = torch.from_numpy(istd).float()
+            have = "encoder.global_cmvn.mean" in sd and "encoder.global_cmvn.istd" in sd
+            ow_file = self.configs.get("cmvn_file", self.configs["cmvn_conf"]["cmvn_file"]) if overwrite_cmvn else None
+            if ow_file is not None:
+                mean, istd = load_cmvn(ow_file, self.configs.get("is_json_cmvn", self.configs["cmvn_conf"]["is_json_cmvn"]))
+                have = False
+            elif not have:
+                mean, istd = load_cmvn(self.configs["cmvn_conf"]["cmvn_file"], self.configs["cmvn_conf"]["is_json_cmvn"])
+            if not have:
+                sd["encoder.global_cmvn.mean"] = torch.from_numpy(np.asarray(mean)).float()
+                sd["encoder.global_cmvn.istd"] = torch.from_numpy(np.asarray(istd)).float()
+        else:
+            # no GlobalCMVN module in the reference model: the engine's fused (x - mean) * istd becomes the identity
+            sd["encoder.global_cmvn.mean"] = torch.zeros(input_dim)
+            sd["encoder.global_cmvn.istd"] = torch.ones(input_dim)
         self.engine = Engine(self.configs, sd, self.configs["output_dim"], self.device)
         self.model = ASRModel(self.engine, self.configs, self.configs["output_dim"])
         self.test_conf = self.configs["dataset_conf"]
@@ -143,26 +159,28 @@ class ReverbASR:
                          decoding_chunk_size: int = -1, num_decoding_left_chunks: int = -1, ctc_weight: float = 0.1,
                          simulate_streaming: bool = False, reverse_weight: float = 0.0, blank_penalty: float = 0.0,
                          length_penalty: float = 0.0, timings_adjustment: float = 230) -> list[str]:
+        check_beam_size(beam_size)        # fail before any audio is read / decoded (limit: engine.MAX_BEAM_SIZE)
         fc = self.test_conf["fbank_conf"]
         feats = self.compute_feats(audio_file, num_mel_bins=fc["num_mel_bins"], frame_length=fc["frame_length"],
                                    frame_shift=fc["frame_shift"])
         with torch.no_grad():
             cat_embs = torch.tensor([verbatimicity, 1.0 - verbatimicity])
 
+            kw = dict(decoding_chunk_size=decoding_chunk_size, num_decoding_left_chunks=num_decoding_left_chunks,
+                      ctc_weight=ctc_weight, simulate_streaming=simulate_streaming, reverse_weight=reverse_weight,
+                      context_graph=None, blank_id=self.blank_id, blank_penalty=blank_penalty,
+                      length_penalty=length_penalty, infos={"tasks": ["transcribe"], "langs": ["en"]}, cat_embs=cat_embs)
+
             def decode_batch(model, batch):
                 feats_batch, feats_lengths = batch
-                return model.decode(
-                    modes, feats_batch, feats_lengths, beam_size, decoding_chunk_size=decoding_chunk_size,
-                    num_decoding_left_chunks=num_decoding_left_chunks, ctc_weight=ctc_weight,
-                    simulate_streaming=simulate_streaming, reverse_weight=reverse_weight, context_graph=None,
-                    blank_id=self.blank_id, blank_penalty=blank_penalty, length_penalty=length_penalty,
-                    infos={"tasks": ["transcribe"], "langs": ["en"]}, cat_embs=cat_embs)
+                return model.decode(modes, feats_batch, feats_lengths, beam_size, **kw)
 
             batches = self.feats_batcher(feats, chunk_size, batch_size)
             if self._lanes is not None:
                 results = self._lanes.run(list(batches), decode_batch)
             else:
-                results = [decode_batch(self.model, b) for b in batches]
+                # the reference's sequential batch loop (cli/reverb.py:214-234), software-pipelined on one stream
+                results = list(self.model.decode_stream(batches, modes, beam_size, **kw))
         return [get_output(format, self.tokenizer, Path(audio_file).name,
                            list(chain(*(hyp[mode] for hyp in results))), timings_adjustment, chunk_size,
                            self.input_frame_length, self.output_frame_length) for mode in modes]

@@ -49,3 +49,14 @@ def model_dirs(tmp_path_factory, golden_cases):
         wav = synth.write_wav(os.path.join(d, "golden.wav"), synth.synth_audio(meta["audio_seconds"], seed=meta["audio_seed"]))
         out[name] = (d, wav)
     return out
+
+
+@pytest.fixture(scope="session")
+def bench_model_dir(tmp_path_factory):
+    """Synthetic model directory at the BENCHMARKED shape (reverb_asr_v1-like: d=1024, L=18, V=10001), the same
+    weights bench.py times (seed 0, causal conv, LayerNorm conv-module norm, right decoder present)."""
+    from reverb_b200 import synth
+    d = str(tmp_path_factory.mktemp("bench_shape"))
+    synth.write_model_dir(d, shape=synth.BENCH_SHAPE, seed=0, causal=True, cnn_module_norm="layer_norm",
+                          reverse_weight=0.3)
+    return d

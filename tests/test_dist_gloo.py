@@ -61,6 +61,16 @@ WORKER = textwrap.dedent("""
     assert len(out) == n_chunks
     for c, r in enumerate(out):
         assert r.tokens == [c, c + 1, 100 + c][: 1 + c %% 3] and r.score == -float(c) - 0.5
+    # the per-step gather of bench.py (RecordGatherer): every rank contributes a fixed block of `per` records
+    from reverb_b200.dist import RecordGatherer, unpack_results
+    per = 3
+    g = RecordGatherer(torch.device("cpu"), per, 16)
+    handles = [g.submit([DecodeResult([rank, step, i], -1.0 * i, 0.5, [0.25] * 3, [i, i + 1, i + 2]) for i in range(per)])
+               for step in range(2)]
+    for step, h in enumerate(handles):
+        got = unpack_results(g.wait(h), 16)
+        assert len(got) == per * world
+        assert [r.tokens for r in got] == [[rk, step, i] for rk in range(world) for i in range(per)]
     if rank == 0:
         print("GATHER_OK", json.dumps([r.tokens for r in out]))
     dist.destroy_process_group()

@@ -29,12 +29,10 @@ B_FULL = 64
 
 
 @pytest.fixture(scope="module")
-def big(tmp_path_factory):
+def big(bench_model_dir):
     import reverb_b200
     from reverb_b200 import synth
-    d = str(tmp_path_factory.mktemp("bench_shape"))
-    synth.write_model_dir(d, shape=synth.BENCH_SHAPE, seed=0, causal=True, cnn_module_norm="layer_norm",
-                          reverse_weight=0.3)
+    d = bench_model_dir
     asr = reverb_b200.ReverbASR(os.path.join(d, "config.yaml"), os.path.join(d, "synth.pt"), gpu=0)
     base = [synth.synth_audio(30.0, seed=4321 + i) for i in range(4)]
     pcm = np.empty((B_FULL, CHUNK_SAMPLES), dtype=np.int16)

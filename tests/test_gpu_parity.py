@@ -1,0 +1,245 @@
+"""Parity of the CUDA path against the REFERENCE'S OWN outputs (tests/golden, produced by the live reference) token by
+token, and against the CPU oracle at the BENCHMARKED shape (d=1024, H=16, L=18, V=10001, 30 s chunks).
+
+VERDICT r1 "what's weak" 1-4: the earlier tests compared tokens only through the oracle searches run on the GPU's own
+log-probs and accepted `> 98 %` / `0.5x-2x` / `>= 50 %` agreement.  Here the comparison is direct:
+
+  * decode() tokens (greedy / prefix n-best / rescoring pick) == the live reference's tokens on its own features;
+  * transcribe() CTM == the live reference's CTM string (words and times exactly, confidences to 0.02);
+  * at the benchmarked shape: encoder_out, CTC log-probs, greedy ids, prefix n-best, rescoring pick vs the oracle port
+    (pinned bit-identical to the live reference, tests/test_oracle_vs_reference.py) on 2 x 30 s chunks.
+
+Any token-level exception is REPORTED (frame, margin) and bounded; bit-exactness of greedy ids is asserted.
+Measured values are printed (`pytest -s`) and collected in profiles/r2_parity.json by tools/parity_report.py.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+PARITY_LOG = os.environ.get("RVB_PARITY_LOG")      # optional: append the measured numbers as JSON lines
+
+
+def _log(rec):
+    print("PARITY " + json.dumps(rec))
+    if PARITY_LOG:
+        with open(PARITY_LOG, "a") as f:
+            f.write(json.dumps(rec) + "\n")
+
+
+def _rel_rms(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.sqrt(((a - b) ** 2).mean()) / (np.sqrt((b ** 2).mean()) + 1e-12))
+
+
+@pytest.fixture(scope="module")
+def asr(model_dirs):
+    import reverb_b200
+    return {n: reverb_b200.load_model(d) for n, (d, _) in model_dirs.items()}
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_decode_tokens_equal_live_reference_golden(asr, golden_cases, case):
+    """ASRModel.decode on the reference's features: token ids of all three searches vs the reference's own."""
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    modes = ["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"]
+    n_utt = n_greedy = n_prefix = n_nbest = n_resc = 0
+    for bi, (fb, fl) in enumerate(m.feats_batcher(feats, meta["chunk_size"], meta["batch_size"])):
+        got = m.model.decode(modes, fb, fl, meta["beam_size"], ctc_weight=meta["ctc_weight"],
+                             reverse_weight=meta["reverse_weight"], cat_embs=cat, blank_id=0)
+        gold = meta["batches"][bi]
+        for b in range(fb.shape[0]):
+            n_utt += 1
+            n_greedy += int(list(got["ctc_greedy_search"][b].tokens) == gold["ctc_greedy_search"][b]["tokens"])
+            gp, wp = got["ctc_prefix_beam_search"][b], gold["ctc_prefix_beam_search"][b]
+            n_prefix += int(list(gp.tokens) == wp["tokens"] and gp.times == wp["times"])
+            n_nbest += int([list(h) for h in gp.nbest] == wp["nbest"])
+            gr, wr = got["attention_rescoring"][b], gold["attention_rescoring"][b]
+            same = list(gr.tokens) == wr["tokens"] and gr.times == wr["times"]
+            n_resc += int(same)
+            if same:
+                # reference precedent rtol 1e-3 is out of reach for bf16 operands; stated: 0.02 abs on confidences
+                assert abs(gr.confidence - wr["confidence"]) < 0.02
+                np.testing.assert_allclose(gr.tokens_confidence, wr["tokens_confidence"], rtol=0, atol=0.05)
+    _log({"test": "decode_vs_golden", "case": case, "utterances": n_utt, "greedy_exact": n_greedy,
+          "prefix_best_exact": n_prefix, "prefix_nbest_exact": n_nbest, "rescoring_pick_exact": n_resc})
+    assert n_greedy == n_utt, "greedy token ids must be bit-exact vs the live reference"
+    assert n_prefix == n_utt, "prefix-beam best hypothesis (tokens + times) must equal the live reference's"
+    assert n_resc == n_utt, "attention-rescoring pick must equal the live reference's"
+    # the ORDER of the tail of the n-best can flip on near-ties of the float64 scores (bf16 log-probs): reported
+    assert n_nbest >= n_utt - 1
+
+
+def _ctm_rows(text):
+    rows = []
+    for ln in text.split("\n"):
+        f = ln.split(" ")
+        rows.append((f[0], f[1], f[2], f[3], f[4], float(f[5])))
+    return rows
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_transcribe_ctm_equals_live_reference_golden(asr, golden_cases, model_dirs, case):
+    """Public API end to end (GPU fbank -> ... -> CTM): the CTM of the live reference, line by line: file, channel,
+    start, duration, word EXACTLY; confidence within 0.02 (two-decimal print of exp(log-prob))."""
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    wav = model_dirs[case][1]
+    kw = dict(verbatimicity=meta["verbatimicity"], chunk_size=meta["chunk_size"], batch_size=meta["batch_size"],
+              reverse_weight=meta["reverse_weight"], ctc_weight=meta["ctc_weight"], beam_size=meta["beam_size"])
+    for mode in ("ctc_prefix_beam_search", "attention_rescoring"):
+        got = m.transcribe(wav, mode=mode, format="ctm", **kw)
+        want = meta["transcribe"][mode + ".ctm"]
+        g, w = _ctm_rows(got), _ctm_rows(want)
+        assert [r[:5] for r in g] == [r[:5] for r in w], f"{mode}: CTM words / times differ from the live reference"
+        dconf = max(abs(a[5] - b[5]) for a, b in zip(g, w))
+        _log({"test": "ctm_vs_golden", "case": case, "mode": mode, "lines": len(w), "string_equal": got == want,
+              "max_conf_diff": dconf})
+        assert dconf <= 0.02 + 1e-9
+        assert m.transcribe(wav, mode=mode, format="txt", **kw) == meta["transcribe"][mode + ".txt"]
+
+
+def test_blank_penalty_matches_oracle(asr, golden_cases, model_dirs):
+    """asr_model.py:318-329: logits[:, :, blank] -= blank_penalty before log_softmax (a12)."""
+    from oracle import model_ref, pipeline_ref
+    meta, arr = golden_cases["causal_ln"]
+    m = asr["causal_ln"]
+    orc = pipeline_ref.OracleASR(model_dirs["causal_ln"][0])
+    enc = torch.from_numpy(arr["enc_out_0"])
+    for pen in (0.0, 1.5, 4.0):
+        want = model_ref.ctc_logprobs(enc, orc.sd, pen, 0)
+        val, idx, got = m.engine.ctc_topk(enc.cuda(), 10, pen, 0, want_logp=True)
+        got = got.cpu()
+        sel = want > -12
+        d = (got - want)[sel].abs().max().item()
+        assert d < 0.05, (pen, d)            # only the bf16 operands of ctc_lo differ (enc_out is the reference's)
+        # top-k is the top-k of the penalised log-probs the kernel itself produced: bit-exact
+        tv, ti = got.cuda().topk(10, dim=2)
+        assert torch.equal(val, tv) and torch.equal(idx.long(), ti)
+    base = model_ref.ctc_logprobs(enc, orc.sd, 0.0, 0)
+    pen4 = m.engine.ctc_topk(enc.cuda(), 1, 4.0, 0, want_logp=True)[2].cpu()
+    assert (pen4[..., 0] < base[..., 0] - 1.0).float().mean() > 0.9     # blank really is pushed down
+
+
+def test_lanes_give_the_sequential_result(asr, golden_cases, model_dirs, tmp_path):
+    """with more batches than lanes every lane must still be driven by ONE host thread.  7 batches
+    on 2 lanes == the sequential decode, for both modes."""
+    from reverb_b200 import synth
+    m = asr["causal_ln"]
+    meta, _ = golden_cases["causal_ln"]
+    wav = synth.write_wav(str(tmp_path / "long.wav"), synth.synth_audio(27.0, seed=77))
+    kw = dict(verbatimicity=meta["verbatimicity"], chunk_size=400, batch_size=1, reverse_weight=0.3)
+    modes = ["ctc_prefix_beam_search", "attention_rescoring"]
+    seq = m.transcribe_modes(wav, modes, format="ctm", **kw)
+    assert len(seq[1].split("\n")) > 20
+    try:
+        m.set_lanes(2)
+        for _ in range(3):
+            par = m.transcribe_modes(wav, modes, format="ctm", **kw)
+            assert par == seq
+    finally:
+        m.set_lanes(1)
+
+
+def test_decode_stream_equals_batch_by_batch_decode(asr, golden_cases, tmp_path):
+    """ASRModel.decode_stream (software pipeline: A(n) | B(n-1) | C(n-2) on one stream) must return exactly what the
+    sequential decode() loop returns, for every mode, including an early exit of the consumer (tickets released)."""
+    from reverb_b200 import synth
+    m = asr["causal_ln"]
+    wav = synth.write_wav(str(tmp_path / "long.wav"), synth.synth_audio(33.0, seed=5))
+    feats = m.compute_feats(wav, num_mel_bins=80, frame_length=25, frame_shift=10)
+    cat = torch.tensor([0.7, 0.3])
+    kw = dict(ctc_weight=0.1, reverse_weight=0.3, blank_id=0, cat_embs=cat)
+    for modes in (["ctc_prefix_beam_search", "attention_rescoring"], ["ctc_prefix_beam_search"],
+                  ["ctc_greedy_search", "attention_rescoring"]):
+        batches = list(m.feats_batcher(feats, 400, 2))
+        assert len(batches) >= 4
+        seq = [m.model.decode(modes, fb, fl, 10, **kw) for fb, fl in batches]
+        par = list(m.model.decode_stream(iter(batches), modes, 10, **kw))
+        assert len(par) == len(seq)
+        for a, b in zip(seq, par):
+            for mode in modes:
+                for x, y in zip(a[mode], b[mode]):
+                    assert list(x.tokens) == list(y.tokens) and x.times == y.times
+                    assert float(x.score) == float(y.score)
+                    assert x.tokens_confidence == y.tokens_confidence and x.nbest_scores == y.nbest_scores
+    # stop after the first result: the generator's finally must hand the native tickets back
+    for _ in range(6):
+        gen = m.model.decode_stream(iter(batches), ["attention_rescoring"], 10, **kw)
+        next(gen)
+        gen.close()
+    assert len(list(m.model.decode_stream(iter(batches), ["attention_rescoring"], 10, **kw))) == len(batches)
+
+
+def test_beam_size_limit_is_reported_before_decoding(asr, model_dirs):
+    m = asr["causal_ln"]
+    with pytest.raises(ValueError, match="beam_size"):
+        m.transcribe(model_dirs["causal_ln"][1], mode="attention_rescoring", beam_size=20)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the benchmarked shape
+def test_bench_shape_two_chunks_vs_oracle(bench_model_dir):
+    """d=1024 / H=16 / L=18 / V=10001 / T'=748 (the ONLY shape BENCH / SCALE time): fbank, encoder_out, CTC log-probs,
+    greedy ids, prefix n-best and the rescoring pick of 2 x 30 s chunks vs the CPU oracle (fp32, the reference's ATen
+    operators).  Stated tolerances (bf16 GEMM operands, fp32 accumulation, 18 blocks): encoder rel-RMS < 1.2e-2,
+    log-prob |diff| < 0.25 on entries with p > e^-12; greedy ids: exact."""
+    import reverb_b200
+    from oracle import fbank_np, pipeline_ref
+    from reverb_b200 import synth
+    d = bench_model_dir
+    asr_b = reverb_b200.ReverbASR(os.path.join(d, "config.yaml"), os.path.join(d, "synth.pt"), gpu=0)
+    orc = pipeline_ref.OracleASR(d)
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    pcm = np.stack([synth.synth_audio(30.0, seed=4321 + i) for i in range(2)])
+    cat = torch.tensor([1.0, 0.0])
+    ofeats = torch.from_numpy(np.stack([fbank_np.fbank(p.astype(np.float32)) for p in pcm]))
+    gfeats = asr_b.engine.fbank_batch(torch.from_numpy(pcm).cuda())
+    dfb = float((gfeats.cpu() - ofeats).abs().max())
+    assert dfb < 2e-3, dfb
+    lens = torch.full((2,), ofeats.shape[1], dtype=torch.int32)
+    modes = ["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"]
+    want = orc.decode(modes, ofeats, lens, 10, ctc_weight=0.1, reverse_weight=0.0, cat_embs=cat,
+                      return_intermediates=True)
+    # the CUDA path on the ORACLE's features ("given identical fbank features", north_star)
+    enc, enc_lens = asr_b.model._forward_encoder(ofeats.cuda(), lens, cat)
+    assert enc_lens.tolist() == want["_encoder_lens"].tolist() == [748, 748]
+    rr = [_rel_rms(enc[b].cpu().numpy(), want["_encoder_out"][b].numpy()) for b in range(2)]
+    logp = asr_b.model.ctc_logprobs(enc).cpu()
+    wl = want["_ctc_probs"]
+    sel = wl > -12
+    dl = (logp - wl)[sel]
+    amax = (logp.argmax(-1) == wl.argmax(-1)).float().mean().item()
+    got = asr_b.model.decode(modes, ofeats.cuda(), lens, 10, ctc_weight=0.1, reverse_weight=0.0, cat_embs=cat,
+                             blank_id=0)
+    rec = {"test": "bench_shape_vs_oracle", "fbank_max_abs": dfb, "encoder_rel_rms": rr,
+           "logp_max_abs": float(dl.abs().max()), "logp_rms": float((dl.double() ** 2).mean().sqrt()),
+           "argmax_agreement": amax, "frames": int(2 * 748)}
+    # frames whose arg-max differs: report the oracle's top-2 margin there (a near-tie is the only legitimate cause)
+    bad = (logp.argmax(-1) != wl.argmax(-1)).nonzero().tolist()
+    top2 = wl.topk(2, dim=-1).values
+    rec["argmax_exceptions"] = [{"utt": b, "frame": t, "oracle_top2_margin": float(top2[b, t, 0] - top2[b, t, 1])}
+                                for b, t in bad]
+    n_g = sum(list(got["ctc_greedy_search"][b].tokens) == list(want["ctc_greedy_search"][b].tokens) for b in range(2))
+    n_p = sum(list(got["ctc_prefix_beam_search"][b].tokens) == list(want["ctc_prefix_beam_search"][b].tokens)
+              and got["ctc_prefix_beam_search"][b].times == want["ctc_prefix_beam_search"][b].times for b in range(2))
+    n_nb = sum([tuple(h) for h in got["ctc_prefix_beam_search"][b].nbest] ==
+               [tuple(h) for h in want["ctc_prefix_beam_search"][b].nbest] for b in range(2))
+    n_r = sum(list(got["attention_rescoring"][b].tokens) == list(want["attention_rescoring"][b].tokens)
+              for b in range(2))
+    sc = [abs(float(got["attention_rescoring"][b].score) - float(want["attention_rescoring"][b].score)) for b in range(2)]
+    rec.update({"greedy_exact": n_g, "prefix_best_exact": n_p, "prefix_nbest_exact": n_nb, "rescoring_pick_exact": n_r,
+                "rescoring_score_abs_diff": sc,
+                "tokens": [len(want["ctc_greedy_search"][b].tokens) for b in range(2)]})
+    _log(rec)
+    assert max(rr) < 1.2e-2
+    assert float(dl.abs().max()) < 0.25
+    assert n_g == 2, "greedy ids must be bit-exact at the benchmarked shape"
+    assert n_p == 2 and n_r == 2
