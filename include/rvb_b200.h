@@ -54,6 +54,10 @@ typedef struct rvb_model_config {
   int r_dec_blocks;     /* decoder_conf.r_num_blocks (0: no right-to-left decoder) */
   int sos_id;           /* tokenizer_conf.special_tokens["<sos>"]; <= 0: vocab - 1 (asr_model.py:79-82) */
   int eos_id;           /* tokenizer_conf.special_tokens["<eos>"]; <= 0: vocab - 1 */
+  int precision;        /* 0: bf16 tensor-core operands, fp32 accumulate (throughput mode, default)
+                         * 1: "bf16x3" fp32-accurate mode — every GEMM operand is a (hi, lo) bf16 pair and runs as three
+                         *    tcgen05 passes hi.hi + lo.hi + hi.lo (~2^-16 relative), attention in fp32: for parity with
+                         *    the reference's fp32 graph (bit-exact greedy ids); ~3x the tensor work */
 } rvb_model_config;
 
 /* ---- diagnostics -------------------------------------------------------------------------------------------- */
@@ -181,6 +185,14 @@ RVB_API int rvb_decoder_step_topk(rvb_model* m, const float* d_enc_out, const in
  * [64j+32, 64j+64) their gates; out[m, c] = value * sigmoid(gate). */
 RVB_API int rvb_gemm_bf16(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int act, int out_mode,
                   float alpha, void* d_out, int ldo, void* stream);
+/* The same GEMM in the fp32-accurate "bf16x3" mode (rvb_model_config.precision = 1): d_A (M, 2K) and d_W (N, 2K) hold
+ * (hi | lo) bf16 pairs — hi = bf16(v), lo = bf16(v - hi), rvb_f32_to_bf16_pair builds them — and three tcgen05 passes
+ * hi.hi + lo.hi + hi.lo accumulate in fp32.  bf16 outputs (out_mode 0) are written as such a pair too: (M, 2N), or
+ * (M, N) = (value half | residue half) of the N/2 GLU outputs; ldo = 0 selects that width. */
+RVB_API int rvb_gemm_bf16x3(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int act, int out_mode,
+                            float alpha, void* d_out, int ldo, void* stream);
+/* (rows, width) fp32 -> (rows, 2 * width) bf16 = [hi | lo] */
+RVB_API int rvb_f32_to_bf16_pair(const float* d_x, void* d_out, long long rows, int width, void* stream);
 /* out[m] = log_softmax(A W^T + bias)[m, gather[m]] (0 where gather[m] < 0) without materialising the (M, N) logits:
  * the GEMM epilogue emits per-slab (max, sum-exp) partials + the gathered logit into d_ws
  * (rvb_gemm_logsoftmax_gather_ws_bytes(M, N) bytes), a second kernel merges them.  This is the output layer +

@@ -18,7 +18,7 @@ class ModelConfig(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "input_dim", "d_model", "heads", "ffn_dim", "num_blocks", "cnn_kernel", "causal",
         "cnn_layer_norm", "num_langs", "vocab", "dec_heads", "dec_ffn_dim", "dec_blocks", "r_dec_blocks",
-        "sos_id", "eos_id")]
+        "sos_id", "eos_id", "precision")]
 
 
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
@@ -58,6 +58,8 @@ SIGNATURES = {
     "rvb_decoder_step_topk": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "rvb_attention_rescoring": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp]),
     "rvb_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
+    "rvb_gemm_bf16x3": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),
+    "rvb_f32_to_bf16_pair": (_i, [_vp, _vp, _ll, _i, _vp]),
     "rvb_gemm_logsoftmax_gather_ws_bytes": (_ll, [_i, _i]),
     "rvb_gemm_logsoftmax_gather": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "rvb_layernorm": (_i, [_vp, _vp, _vp, _f, _i, _i, _vp, _vp, _vp]),

@@ -6,6 +6,21 @@
 
 namespace rvb {
 
+// bf16x3 ("fp32-accurate") mode: an activation is stored as the bf16 PAIR hi = bf16(v), lo = bf16(v - hi), side by side in
+// one row: hi at column c, lo at column c + width (row stride 2 * width).  See GemmArgs::x3 (kernels.h).
+__device__ __forceinline__ float bf16_residue(float v) { return v - __bfloat162float(__float2bfloat16(v)); }
+__device__ __forceinline__ void store_pair4(bf16* row, int col, int width, bool x3, float4 o) {
+  uint2 u;
+  u.x = pack_bf16x2(o.x, o.y);
+  u.y = pack_bf16x2(o.z, o.w);
+  *reinterpret_cast<uint2*>(row + col) = u;
+  if (x3) {
+    u.x = pack_bf16x2(bf16_residue(o.x), bf16_residue(o.y));
+    u.y = pack_bf16x2(bf16_residue(o.z), bf16_residue(o.w));
+    *reinterpret_cast<uint2*>(row + width + col) = u;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row cached in registers (NV float4 per lane), two-pass variance like ATen.
 // reference: nn.LayerNorm uses of transformer/encoder_layer.py:149-159, encoder.py:107, decoder_layer.py:53-55,241-243
@@ -14,7 +29,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         const float* __restrict__ beta, float eps, int M, int d,
                                                         bf16* __restrict__ out_bf16, float* __restrict__ out_f32,
                                                         const int* __restrict__ row_lens, int rows_per_batch,
-                                                        int mask_rows) {
+                                                        int mask_rows, int x3) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -61,18 +76,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       o.w = (v[i].w - mean) * rstd * g.w + bb.w;
       if (masked) o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (out_f32) reinterpret_cast<float4*>(out_f32 + (long long)warp * d)[idx] = o;
-      if (out_bf16) {
-        uint2 u;
-        u.x = pack_bf16x2(o.x, o.y);
-        u.y = pack_bf16x2(o.z, o.w);
-        reinterpret_cast<uint2*>(out_bf16 + (long long)warp * d)[idx] = u;
-      }
+      if (out_bf16) store_pair4(out_bf16 + (long long)warp * d * (x3 ? 2 : 1), 4 * idx, d, x3 != 0, o);
     }
   }
 }
 
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M, int d, bf16* out_bf16,
-                     float* out_f32, const int* row_lens, int rows_per_batch, int mask_rows, cudaStream_t stream) {
+                     float* out_f32, const int* row_lens, int rows_per_batch, int mask_rows, cudaStream_t stream,
+                     int x3) {
   RVB_REQUIRE(d % 4 == 0 && d <= 4096, "layernorm: d=%d unsupported (need d %% 4 == 0, d <= 4096)", d);
   if (M <= 0) return 0;
   const int grid = (M + 7) / 8;
@@ -80,7 +91,7 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
   if (rows_per_batch <= 0) rows_per_batch = M;
 #define RVB_LN(NV)                                                                                           \
   layernorm_kernel<NV><<<grid, 256, 0, stream>>>(x, gamma, beta, eps, M, d, out_bf16, out_f32, row_lens,     \
-                                                 rows_per_batch, mask_rows)
+                                                 rows_per_batch, mask_rows, x3)
   if (nv <= 1) RVB_LN(1);
   else if (nv <= 2) RVB_LN(2);
   else if (nv <= 4) RVB_LN(4);
@@ -100,7 +111,7 @@ __global__ void __launch_bounds__(256)
 double_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ ba,
                         const float* __restrict__ y_add, float* __restrict__ x2, const float* __restrict__ gb,
                         const float* __restrict__ bb, float eps, int M, int d, bf16* __restrict__ n_out,
-                        float* __restrict__ n_out_f32) {
+                        float* __restrict__ n_out_f32, int x3) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -177,25 +188,20 @@ double_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g
       o.z = (v[i].z - mean) * rstd * g.z + b4.z;
       o.w = (v[i].w - mean) * rstd * g.w + b4.w;
       if (n_out_f32) reinterpret_cast<float4*>(n_out_f32 + (long long)warp * d)[idx] = o;
-      if (n_out) {
-        uint2 u;
-        u.x = pack_bf16x2(o.x, o.y);
-        u.y = pack_bf16x2(o.z, o.w);
-        reinterpret_cast<uint2*>(n_out + (long long)warp * d)[idx] = u;
-      }
+      if (n_out) store_pair4(n_out + (long long)warp * d * (x3 ? 2 : 1), 4 * idx, d, x3 != 0, o);
     }
   }
 }
 
 int launch_double_layernorm(const float* x, const float* ga, const float* ba, const float* y_add, float* x2,
                             const float* gb, const float* bb, float eps, int M, int d, bf16* n_out,
-                            float* n_out_f32, cudaStream_t stream) {
+                            float* n_out_f32, cudaStream_t stream, int x3) {
   RVB_REQUIRE(d % 4 == 0 && d <= 4096, "double_layernorm: d=%d unsupported", d);
   if (M <= 0) return 0;
   const int grid = (M + 7) / 8;
   const int nv = (d / 4 + 31) / 32;
 #define RVB_DLN(NV) \
-  double_layernorm_kernel<NV><<<grid, 256, 0, stream>>>(x, ga, ba, y_add, x2, gb, bb, eps, M, d, n_out, n_out_f32)
+  double_layernorm_kernel<NV><<<grid, 256, 0, stream>>>(x, ga, ba, y_add, x2, gb, bb, eps, M, d, n_out, n_out_f32, x3)
   if (nv <= 1) RVB_DLN(1);
   else if (nv <= 2) RVB_DLN(2);
   else if (nv <= 4) RVB_DLN(4);
@@ -220,7 +226,7 @@ constexpr int C1_ROWS = 4;
 __global__ void __launch_bounds__(256)
 conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, const float* __restrict__ istd,
              const float* __restrict__ w, const float* __restrict__ bias, bf16* __restrict__ out, int T, int F, int C,
-             int T1, int T1h, int F1) {
+             int T1, int T1h, int F1, int x3) {
   extern __shared__ float2 s_in2[];  // (2*C1_ROWS+1) rows x F, CMVN applied, every value DUPLICATED {x, x} (FFMA2 operand)
   const int t1_0 = blockIdx.x * C1_ROWS;  // first output row of this CTA, 0 .. 2*T1h-1
   const int b = blockIdx.y;
@@ -249,9 +255,10 @@ conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, co
     const int t1 = t1_0 + rr;
     if (t1 >= 2 * T1h) break;
     const int par = t1 & 1, th = t1 >> 1;
-    bf16* orow = out + (((long long)(b * 2 + par) * T1h + th) * F1) * C;
+    const int Cp = x3 ? 2 * C : C;  // physical channels: [hi C | lo C] in bf16x3 mode
+    bf16* orow = out + (((long long)(b * 2 + par) * T1h + th) * F1) * Cp;
     if (t1 >= T1) {  // padding row (T1 odd): keep it finite
-      for (int i = threadIdx.x; i < F1 * CG; i += blockDim.x)
+      for (int i = threadIdx.x; i < F1 * (Cp >> 3); i += blockDim.x)
         reinterpret_cast<uint4*>(orow)[i] = make_uint4(0u, 0u, 0u, 0u);
       continue;
     }
@@ -275,19 +282,26 @@ conv1_kernel(const float* __restrict__ feats, const float* __restrict__ mean, co
       u.y = pack_bf16x2(o[1].x, o[1].y);
       u.z = pack_bf16x2(o[2].x, o[2].y);
       u.w = pack_bf16x2(o[3].x, o[3].y);
-      reinterpret_cast<uint4*>(orow + (long long)f * C)[cg] = u;
+      reinterpret_cast<uint4*>(orow + (long long)f * Cp)[cg] = u;
+      if (x3) {
+        u.x = pack_bf16x2(bf16_residue(o[0].x), bf16_residue(o[0].y));
+        u.y = pack_bf16x2(bf16_residue(o[1].x), bf16_residue(o[1].y));
+        u.z = pack_bf16x2(bf16_residue(o[2].x), bf16_residue(o[2].y));
+        u.w = pack_bf16x2(bf16_residue(o[3].x), bf16_residue(o[3].y));
+        reinterpret_cast<uint4*>(orow + (long long)f * Cp + C)[cg] = u;
+      }
     }
   }
 }
 
 int launch_conv1(const float* feats, const float* mean, const float* istd, const float* w, const float* bias,
-                 bf16* out, int B, int T, int F, int C, int T1, int T1h, int F1, cudaStream_t stream) {
+                 bf16* out, int B, int T, int F, int C, int T1, int T1h, int F1, cudaStream_t stream, int x3) {
   RVB_REQUIRE(C % 8 == 0 && C / 8 <= 256, "conv1: C=%d unsupported", C);
   const int CG = C / 8;
   const int threads = (256 / CG) * CG;
   dim3 grid((2 * T1h + C1_ROWS - 1) / C1_ROWS, B);
   conv1_kernel<<<grid, threads, (2 * C1_ROWS + 1) * F * sizeof(float2), stream>>>(feats, mean, istd, w, bias, out, T, F,
-                                                                                 C, T1, T1h, F1);
+                                                                                 C, T1, T1h, F1, x3);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;
@@ -313,7 +327,7 @@ int launch_conv1(const float* feats, const float* mean, const float* istd, const
 // (convolution.py:113-114,129-130), so the pad frames reach the depthwise conv as GLU(bias), not zeros.
 constexpr int CM_TT = 16;
 
-template <int K>
+template <int K, bool X3>
 __global__ void __launch_bounds__(128)
 conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, const float* __restrict__ dw_w,
                const float* __restrict__ dw_b, const float* __restrict__ norm_w, const float* __restrict__ norm_b,
@@ -342,15 +356,22 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
     acc[t][0] = b0;
     acc[t][1] = b1;
   }
-  const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (long long)b * T * C) + cp;
+  // X3: rows are [hi C | lo C] (2C bf16 = C uint32 words); the value is hi + lo
+  const int CW = X3 ? C : C2;  // row stride in uint32 words
+  const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (long long)b * T * C * (X3 ? 2 : 1)) + cp;
   if constexpr (K > 0) {
     constexpr int ROWS = CM_TT + K - 1;
     uint32_t rv[ROWS];
+    uint32_t rl[X3 ? ROWS : 1];
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int t = t0 - left + r;
       rv[r] = 0u;
-      if (ok && t >= 0 && t < T) rv[r] = __ldg(xb + (long long)t * C2);
+      if (X3) rl[r] = 0u;
+      if (ok && t >= 0 && t < T) {
+        rv[r] = __ldg(xb + (long long)t * CW);
+        if (X3) rl[r] = __ldg(xb + (long long)t * CW + C2);
+      }
     }
     float w0[K], w1[K];
 #pragma unroll
@@ -361,7 +382,12 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
 #pragma unroll
     for (int r = 0; r < ROWS; ++r) {
       const int tt = t0 - left + r;
-      const float2 v = (tt < 0) ? padv : unpack_bf16x2(rv[r]);  // rv is 0 beyond T
+      float2 v = (tt < 0) ? padv : unpack_bf16x2(rv[r]);  // rv is 0 beyond T
+      if (X3 && tt >= 0) {
+        const float2 l = unpack_bf16x2(rl[r]);
+        v.x += l.x;
+        v.y += l.y;
+      }
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int t = r - k;  // compile-time after unrolling
@@ -381,7 +407,14 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
         const int tt = t0 + t - left + k;
         float2 v = make_float2(0.f, 0.f);
         if (tt < 0) v = padv;
-        else if (tt < T) v = unpack_bf16x2(__ldg(xb + (long long)tt * C2));
+        else if (tt < T) {
+          v = unpack_bf16x2(__ldg(xb + (long long)tt * CW));
+          if (X3) {
+            const float2 l = unpack_bf16x2(__ldg(xb + (long long)tt * CW + C2));
+            v.x += l.x;
+            v.y += l.y;
+          }
+        }
         acc[t][0] = fmaf(w0, v.x, acc[t][0]);
         acc[t][1] = fmaf(w1, v.y, acc[t][1]);
       }
@@ -397,7 +430,14 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
     for (int t = 0; t < CM_TT; ++t) {
       if (t0 + t >= T) continue;
       const float y0 = (acc[t][0] - m0) * r0 * g0 + be0, y1 = (acc[t][1] - m1) * r1 * g1 + be1;
-      reinterpret_cast<uint32_t*>(out + ((long long)b * T + t0 + t) * C)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
+      if (X3) {
+        const float s0 = y0 / (1.f + expf(-y0)), s1 = y1 / (1.f + expf(-y1));
+        uint32_t* orow = reinterpret_cast<uint32_t*>(out + ((long long)b * T + t0 + t) * C * 2);
+        orow[cp] = pack_bf16x2(s0, s1);
+        orow[C2 + cp] = pack_bf16x2(bf16_residue(s0), bf16_residue(s1));
+      } else {
+        reinterpret_cast<uint32_t*>(out + ((long long)b * T + t0 + t) * C)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
+      }
     }
     return;
   }
@@ -439,7 +479,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restrict__ stats, int nslice,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M, int C,
-                      bf16* __restrict__ out) {
+                      bf16* __restrict__ out, int x3) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -460,10 +500,15 @@ conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restric
       const float4 v = xr[idx];
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + idx);
       const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + idx);
-      uint2 u;
-      u.x = pack_bf16x2(silu_f((v.x - mean) * rstd * g.x + bb.x), silu_f((v.y - mean) * rstd * g.y + bb.y));
-      u.y = pack_bf16x2(silu_f((v.z - mean) * rstd * g.z + bb.z), silu_f((v.w - mean) * rstd * g.w + bb.w));
-      reinterpret_cast<uint2*>(out + row * C)[idx] = u;
+      float4 y = make_float4((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y,
+                             (v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w);
+      if (x3) {  // accurate mode: exact exp / division
+        y = make_float4(y.x / (1.f + expf(-y.x)), y.y / (1.f + expf(-y.y)), y.z / (1.f + expf(-y.z)),
+                        y.w / (1.f + expf(-y.w)));
+      } else {
+        y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
+      }
+      store_pair4(out + row * C * (x3 ? 2 : 1), 4 * idx, C, x3 != 0, y);
     }
   }
 }
@@ -471,20 +516,22 @@ conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restric
 int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, const float* dw_b, const float* norm_w,
                     const float* norm_b, const float* bn_mean, const float* bn_var, int use_ln, float eps,
                     bf16* out, int B, int T, int C, int K, int causal, cudaStream_t stream, float* conv_tmp,
-                    float* stats) {
+                    float* stats, int x3) {
   RVB_REQUIRE(C % 4 == 0 && C <= 4096 && K >= 1 && K <= 64, "conv_mid: unsupported C=%d K=%d", C, K);
   RVB_REQUIRE(!causal || pad_glu != nullptr, "conv_mid: causal mode needs the GLU(pointwise_conv1 bias) pad row");
   RVB_REQUIRE(!use_ln || (conv_tmp != nullptr && stats != nullptr), "conv_mid: LayerNorm needs the fp32 scratch");
   const int C2 = C / 2;
   dim3 grid((T + CM_TT - 1) / CM_TT, B, (C2 + 127) / 128);
   const int nslice = (int)grid.z;
-#define RVB_DW(KK)                                                                                                  \
-  conv_dw_kernel<KK><<<grid, 128, 0, stream>>>(x, pad_glu, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln, eps, \
-                                               conv_tmp, stats, out, T, C, K, causal)
-  if (K == 15) RVB_DW(15);
-  else if (K == 31) RVB_DW(31);
-  else if (K == 7) RVB_DW(7);
-  else RVB_DW(0);
+#define RVB_DW(KK, XX)                                                                                                 \
+  conv_dw_kernel<KK, XX><<<grid, 128, 0, stream>>>(x, pad_glu, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln, eps, \
+                                                   conv_tmp, stats, out, T, C, K, causal)
+  if (x3) {  // accurate mode: the generic tap loop (no register-resident halo) is fast enough
+    RVB_DW(0, true);
+  } else if (K == 15) RVB_DW(15, false);
+  else if (K == 31) RVB_DW(31, false);
+  else if (K == 7) RVB_DW(7, false);
+  else RVB_DW(0, false);
 #undef RVB_DW
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
@@ -492,12 +539,12 @@ int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, cons
     const long long M = (long long)B * T;
     const int nv = (C / 4 + 31) / 32;
     const unsigned g2 = (unsigned)((M + 7) / 8);
-    if (nv <= 1) conv_norm_silu_kernel<1><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
-    else if (nv <= 2) conv_norm_silu_kernel<2><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
-    else if (nv <= 4) conv_norm_silu_kernel<4><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
-    else if (nv <= 8) conv_norm_silu_kernel<8><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
-    else if (nv <= 16) conv_norm_silu_kernel<16><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
-    else conv_norm_silu_kernel<32><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);
+    if (nv <= 1) conv_norm_silu_kernel<1><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
+    else if (nv <= 2) conv_norm_silu_kernel<2><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
+    else if (nv <= 4) conv_norm_silu_kernel<4><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
+    else if (nv <= 8) conv_norm_silu_kernel<8><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
+    else if (nv <= 16) conv_norm_silu_kernel<16><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
+    else conv_norm_silu_kernel<32><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
     RVB_COUNT_LAUNCH();
     RVB_CHECK_LAUNCH();
   }
@@ -528,6 +575,31 @@ int launch_scale_cast(const float* x, float scale, float* out_f32, bf16* out_bf1
 
 int launch_f32_to_bf16(const float* x, bf16* out, long long n, cudaStream_t stream) {
   return launch_scale_cast(x, 1.0f, nullptr, out, n, stream);
+}
+
+// (rows, width) fp32 -> the bf16 pair layout (rows, 2 * width) = [hi | lo] of the accurate mode
+__global__ void f32_to_pair_kernel(const float* __restrict__ x, bf16* __restrict__ out, long long rows, int width) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = rows * width, stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const long long r = i / width;
+    const int c = (int)(i - r * width);
+    const float v = x[i];
+    const bf16 h = __float2bfloat16(v);
+    out[r * 2 * width + c] = h;
+    out[r * 2 * width + width + c] = __float2bfloat16(v - __bfloat162float(h));
+  }
+}
+
+int launch_f32_to_pair(const float* x, bf16* out, long long rows, int width, cudaStream_t stream) {
+  const long long n = rows * width;
+  if (n <= 0) return 0;
+  long long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  f32_to_pair_kernel<<<(int)blocks, 256, 0, stream>>>(x, out, rows, width);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
 }
 
 struct WSumPtrs {

@@ -161,6 +161,9 @@ struct rvb_model {
   Linear ctc;
   Decoder dec_l, dec_r;
   std::vector<float> cur_cat;  // cat_embs the LSL folds were computed for
+  bool x3 = false;             // cfg.precision == 1: bf16x3 "fp32-accurate" mode (GemmArgs::x3, kernels.h)
+  int pm() const { return x3 ? 2 : 1; }  // physical width multiplier of every bf16 operand ([hi | lo] pairs)
+  DevBuf ws_fold;              // fp32 scratch of the accurate mode (LSL folds, positional table)
 
   // workspace (grow-only)
   DevBuf ws_c1, ws_c2, ws_x, ws_n, ws_h, ws_qkv, ws_att, ws_pw, ws_cm, ws_y, ws_ybf, ws_pe, ws_pall, ws_lens;
@@ -211,6 +214,25 @@ static int upload_bf16(rvb_model* m, const float* src, size_t n, bf16** dst) {
   return 0;
 }
 
+// GEMM weight (N, K) fp32 -> device bf16 (N, K), or the pair layout (N, 2K) = [hi | lo] in the accurate mode
+static int upload_w(rvb_model* m, const float* src, size_t N, size_t K, bf16** dst) {
+  if (!m->x3) return upload_bf16(m, src, N * K, dst);
+  std::vector<uint16_t> tmp(N * K * 2);
+  for (size_t n = 0; n < N; ++n)
+    for (size_t k = 0; k < K; ++k) {
+      const float v = src[n * K + k];
+      const uint16_t h = f2bf(v);
+      tmp[n * 2 * K + k] = h;
+      tmp[n * 2 * K + K + k] = f2bf(v - bf2f(h));
+    }
+  void* p = nullptr;
+  RVB_CHECK_CUDA(cudaMalloc(&p, tmp.size() * sizeof(uint16_t) + 16));
+  RVB_CHECK_CUDA(cudaMemcpy(p, tmp.data(), tmp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  m->owned.push_back(p);
+  *dst = reinterpret_cast<bf16*>(p);
+  return 0;
+}
+
 static int alloc_dev(rvb_model* m, size_t bytes, void** dst) {
   void* p = nullptr;
   RVB_CHECK_CUDA(cudaMalloc(&p, bytes + 16));
@@ -225,7 +247,7 @@ static int load_linear(rvb_model* m, const std::string& prefix, int N, int K, Li
                        bool bias_optional = false) {
   const std::vector<float>* w;
   if (need(m, prefix + ".weight", (size_t)N * K, &w)) return -1;
-  if (upload_bf16(m, w->data(), w->size(), &out->w)) return -1;
+  if (upload_w(m, w->data(), N, K, &out->w)) return -1;
   out->N = N;
   out->K = K;
   if (has_bias) {
@@ -255,9 +277,10 @@ static int load_linear_glu(rvb_model* m, const std::string& prefix, int C, int K
     memcpy(&pw[(size_t)rg * K], &(*w)[(size_t)(C + c) * K], (size_t)K * sizeof(float));
     pb[ra] = (*b)[c];
     pb[rg] = (*b)[C + c];
-    pad[c] = bf2f(f2bf((*b)[c] / (1.f + expf(-(*b)[C + c]))));
+    const float g = (*b)[c] / (1.f + expf(-(*b)[C + c]));
+    pad[c] = m->x3 ? g : bf2f(f2bf(g));  // the engine stores GLU outputs as bf16 (a hi/lo pair in the accurate mode)
   }
-  if (upload_bf16(m, pw.data(), pw.size(), &out->w) || upload_f32(m, pb.data(), pb.size(), &out->b) ||
+  if (upload_w(m, pw.data(), (size_t)2 * C, K, &out->w) || upload_f32(m, pb.data(), pb.size(), &out->b) ||
       upload_f32(m, pad.data(), pad.size(), pad_glu))
     return -1;
   out->N = 2 * C;
@@ -288,7 +311,7 @@ static int load_fused(rvb_model* m, const std::string& prefix, const std::vector
       b.insert(b.end(), d, 0.f);  // key_bias = False
     }
   }
-  if (upload_bf16(m, w.data(), w.size(), &out->w) || upload_f32(m, b.data(), b.size(), &out->b)) return -1;
+  if (upload_w(m, w.data(), (size_t)d * parts.size(), d, &out->w) || upload_f32(m, b.data(), b.size(), &out->b)) return -1;
   out->N = d * (int)parts.size();
   out->K = d;
   return 0;
@@ -306,7 +329,7 @@ static int load_lang(rvb_model* m, const std::string& prefix, int d, int n_lang,
     lb->push_back(db);
   }
   void* p;
-  if (alloc_dev(m, (size_t)d * d * sizeof(bf16), &p)) return -1;
+  if (alloc_dev(m, (size_t)d * d * sizeof(bf16) * m->pm(), &p)) return -1;
   folded->w = reinterpret_cast<bf16*>(p);
   if (alloc_dev(m, (size_t)d * sizeof(float), &p)) return -1;
   folded->b = reinterpret_cast<float*>(p);
@@ -364,7 +387,7 @@ static int finalize_model(rvb_model* m) {
     for (int o = 0; o < d; ++o)
       for (int ci = 0; ci < d; ++ci)
         for (int k = 0; k < 9; ++k) w[((size_t)o * 9 + k) * d + ci] = (*t)[((size_t)o * d + ci) * 9 + k];
-    if (upload_bf16(m, w.data(), w.size(), &m->conv2.w)) return -1;
+    if (upload_w(m, w.data(), d, (size_t)9 * d, &m->conv2.w)) return -1;
     if (need(m, "encoder.embed.conv.2.bias", d, &t) || upload_f32(m, t->data(), d, &m->conv2.b)) return -1;
     m->conv2.N = d;
     m->conv2.K = 9 * d;
@@ -377,7 +400,7 @@ static int finalize_model(rvb_model* m) {
       for (int ci = 0; ci < d; ++ci)
         for (int f = 0; f < F2; ++f)
           w[(size_t)o * d * F2 + (size_t)f * d + ci] = (*t)[(size_t)o * d * F2 + (size_t)ci * F2 + f] * xs;
-    if (upload_bf16(m, w.data(), w.size(), &m->embed.w)) return -1;
+    if (upload_w(m, w.data(), d, (size_t)d * F2, &m->embed.w)) return -1;
     if (need(m, "encoder.embed.out.0.bias", d, &t)) return -1;
     std::vector<float> b(*t);
     for (auto& v : b) v *= xs;
@@ -421,7 +444,7 @@ static int finalize_model(rvb_model* m) {
     }
     if (E.lsl && load_lang(m, p, d, c.num_langs, &E.lang_w, &E.lang_b, &E.lang)) return -1;
   }
-  if (upload_bf16(m, posw.data(), posw.size(), &m->pos_all.w)) return -1;
+  if (upload_w(m, posw.data(), (size_t)L * d, d, &m->pos_all.w)) return -1;
   m->pos_all.N = L * d;
   m->pos_all.K = d;
   if (load_linear(m, "ctc.ctc_lo", c.vocab, d, &m->ctc)) return -1;
@@ -443,8 +466,13 @@ static int fold_lang(rvb_model* m, const float* cat, int n_cat, cudaStream_t str
   RVB_REQUIRE(cat != nullptr && n_cat == c.num_langs, "cat_embs of length %d required (got %d)", c.num_langs, n_cat);
   if ((int)m->cur_cat.size() == n_cat && memcmp(m->cur_cat.data(), cat, sizeof(float) * n_cat) == 0) return 0;
   const int d = c.d_model;
+  if (m->x3 && m->ws_fold.ensure((size_t)d * d * sizeof(float))) return -1;
   auto fold = [&](std::vector<float*>& lw, std::vector<float*>& lb, Linear& out) -> int {
-    if (launch_weighted_sum_bf16(lw.data(), cat, n_cat, (long long)d * d, out.w, nullptr, stream)) return -1;
+    if (m->x3) {  // fold in fp32, then split into the (d, 2d) hi/lo pair
+      float* tmp = m->ws_fold.as<float>();
+      if (launch_weighted_sum_bf16(lw.data(), cat, n_cat, (long long)d * d, nullptr, tmp, stream)) return -1;
+      if (launch_f32_to_pair(tmp, out.w, d, d, stream)) return -1;
+    } else if (launch_weighted_sum_bf16(lw.data(), cat, n_cat, (long long)d * d, out.w, nullptr, stream)) return -1;
     if (launch_weighted_sum_bf16(lb.data(), cat, n_cat, d, nullptr, out.b, stream)) return -1;
     return 0;
   };
@@ -462,10 +490,12 @@ static int fold_lang(rvb_model* m, const float* cat, int n_cat, cudaStream_t str
 static inline int sos_id(const rvb_model_config& c) { return c.sos_id > 0 ? c.sos_id : c.vocab - 1; }
 static inline int eos_id(const rvb_model_config& c) { return c.eos_id > 0 ? c.eos_id : c.vocab - 1; }
 
-static int gemm(const bf16* A, const Linear& W, int M, int act, int out_mode, void* out, float alpha,
+static int gemm(rvb_model* m, const bf16* A, const Linear& W, int M, int act, int out_mode, void* out, float alpha,
                 cudaStream_t stream, const int* row_lens = nullptr, int rows_per_batch = 0, int ldo = 0,
                 bool use_bias = true) {
   GemmArgs g;
+  g.x3 = m->x3 ? 1 : 0;
+  if (m->x3 && out_mode == OUT_BF16) g.out_split = (act == ACT_GLU) ? W.N / 2 : W.N;  // bf16 outputs become hi/lo pairs
   g.A = A;
   g.W = W.w;
   g.M = M;
@@ -527,15 +557,18 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
   RVB_CHECK_CUDA(cudaMemcpyAsync(d_lens, h_lens, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
 
   // workspace
-  if (m->ws_c1.ensure((size_t)B * 2 * T1h * F1 * d * 2) || m->ws_c2.ensure((size_t)M * F2 * d * 2) ||
-      m->ws_x.ensure((size_t)M * d * 4) || m->ws_n.ensure((size_t)M * d * 2) ||
-      m->ws_h.ensure((size_t)M * c.ffn_dim * 2) || m->ws_qkv.ensure((size_t)M * 3 * d * 2) ||
-      m->ws_att.ensure((size_t)M * d * 2) || m->ws_pw.ensure((size_t)M * d * 2) ||
-      m->ws_cm.ensure((size_t)M * d * 2) || m->ws_y.ensure((size_t)M * d * 4) || m->ws_ybf.ensure((size_t)M * d * 2) ||
-      m->ws_pall.ensure((size_t)Tp * L * d * 2) || m->ws_kpp.ensure((size_t)M * d * 2) ||
+  const bool x3 = m->x3;
+  const size_t pm = (size_t)m->pm();  // bf16 operands are (hi, lo) pairs in the accurate mode: twice as wide
+  if (m->ws_c1.ensure((size_t)B * 2 * T1h * F1 * d * 2 * pm) || m->ws_c2.ensure((size_t)M * F2 * d * 2 * pm) ||
+      m->ws_x.ensure((size_t)M * d * 4) || m->ws_n.ensure((size_t)M * d * 2 * pm) ||
+      m->ws_h.ensure((size_t)M * c.ffn_dim * 2 * pm) || m->ws_qkv.ensure((size_t)M * 3 * d * 2 * pm) ||
+      m->ws_att.ensure((size_t)M * d * 2 * pm) || m->ws_pw.ensure((size_t)M * d * 2 * pm) ||
+      m->ws_cm.ensure((size_t)M * d * 2 * pm) || m->ws_y.ensure((size_t)M * d * 4) ||
+      m->ws_ybf.ensure((size_t)M * d * 2 * pm) || m->ws_pall.ensure((size_t)Tp * L * d * 2 * pm) ||
+      m->ws_kpp.ensure((size_t)M * d * 2) ||
       m->ws_cbias.ensure(((size_t)B * H * Tp + (size_t)M * 2 * ((d / 2 + 127) / 128)) * 4))
     return -1;
-  const bool tc_attn = attn_impl() == 1 && dk == 64;
+  const bool tc_attn = attn_impl() == 1 && dk == 64 && !x3;
   bf16* c1 = m->ws_c1.as<bf16>();
   bf16* c2 = m->ws_c2.as<bf16>();
   float* x = m->ws_x.as<float>();
@@ -551,15 +584,23 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
 
   // positional table + all layers' linear_pos(pos_emb) in one GEMM (attention.py:374; batch-shared)
   if (m->pe_T < Tp) {
-    if (m->ws_pe.ensure((size_t)Tp * d * 2)) return -1;
-    if (launch_sinusoid(Tp, d, nullptr, m->ws_pe.as<bf16>(), stream)) return -1;
+    if (m->ws_pe.ensure((size_t)Tp * d * 2 * pm)) return -1;
+    if (x3) {
+      if (m->ws_fold.ensure((size_t)Tp * d * sizeof(float) > (size_t)d * d * sizeof(float) ? (size_t)Tp * d * sizeof(float)
+                                                                                             : (size_t)d * d * sizeof(float)))
+        return -1;
+      if (launch_sinusoid(Tp, d, m->ws_fold.as<float>(), nullptr, stream)) return -1;
+      if (launch_f32_to_pair(m->ws_fold.as<float>(), m->ws_pe.as<bf16>(), Tp, d, stream)) return -1;
+    } else if (launch_sinusoid(Tp, d, nullptr, m->ws_pe.as<bf16>(), stream)) {
+      return -1;
+    }
     m->pe_T = Tp;
   }
-  if (gemm(m->ws_pe.as<bf16>(), m->pos_all, Tp, ACT_NONE, OUT_BF16, pall, 1.f, stream, nullptr, 0, 0, false))
+  if (gemm(m, m->ws_pe.as<bf16>(), m->pos_all, Tp, ACT_NONE, OUT_BF16, pall, 1.f, stream, nullptr, 0, 0, false))
     return -1;
 
   // subsampling: CMVN + conv1 + ReLU ; conv2 + ReLU as implicit GEMM ; Linear(19 d -> d) * sqrt(d)
-  if (launch_conv1(d_feats, m->cmvn_mean, m->cmvn_istd, m->conv1_w, m->conv1_b, c1, B, T, F, d, T1, T1h, F1, stream))
+  if (launch_conv1(d_feats, m->cmvn_mean, m->cmvn_istd, m->conv1_w, m->conv1_b, c1, B, T, F, d, T1, T1h, F1, stream, x3))
     return -1;
   {
     GemmArgs g;
@@ -580,24 +621,54 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
     g.conv_C = d;
     g.conv_T2 = Tp;
     g.conv_F2 = F2;
+    if (x3) {  // output row (b, t') = [hi (F2*d) | lo (F2*d)]: directly the pair-layout A operand of the embed linear
+      g.x3 = 1;
+      g.out_split = F2 * d;
+      g.conv_pair_out = 1;
+    }
     if (launch_gemm(g, stream)) return -1;
   }
-  if (gemm(c2, m->embed, (int)M, ACT_NONE, OUT_F32, x, 1.f, stream)) return -1;
+  if (gemm(m, c2, m->embed, (int)M, ACT_NONE, OUT_F32, x, 1.f, stream)) return -1;
 
   const float att_scale = 1.0f / sqrtf((float)dk);
   // first pre-norm of block 0
   if (launch_layernorm(x, m->enc[0].norm_ffm.g, m->enc[0].norm_ffm.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0,
-                       stream))
+                       stream, x3))
     return -1;
   for (int l = 0; l < L; ++l) {
     EncLayer& E = m->enc[l];
     // macaron FFN: x += 0.5 * W2 SiLU(W1 n)                                   (encoder_layer.py:200-207)
-    if (gemm(n, E.ffm1, (int)M, ACT_SILU, OUT_BF16, h, 1.f, stream)) return -1;
-    if (gemm(h, E.ffm2, (int)M, ACT_NONE, OUT_RESID_F32, x, 0.5f, stream)) return -1;
+    if (gemm(m, n, E.ffm1, (int)M, ACT_SILU, OUT_BF16, h, 1.f, stream)) return -1;
+    if (gemm(m, h, E.ffm2, (int)M, ACT_NONE, OUT_RESID_F32, x, 0.5f, stream)) return -1;
     // rel-pos MHSA                                                            (encoder_layer.py:209-217)
-    if (launch_layernorm(x, E.norm_mha.g, E.norm_mha.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
-    if (gemm(n, E.qkv, (int)M, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
-    if (tc_attn) {
+    if (launch_layernorm(x, E.norm_mha.g, E.norm_mha.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    if (gemm(m, n, E.qkv, (int)M, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    if (x3) {
+      // accurate mode: the reference's two-product rel-pos attention in fp32 (attention_f32.cu) on the hi/lo pairs
+      AttnF32Args a;
+      a.q = qkv;
+      a.k = qkv + d;
+      a.v = qkv + 2 * d;
+      a.p = pall + (size_t)l * d;
+      a.bias_u = E.pos_u;
+      a.bias_v = E.pos_v;
+      a.out = att;
+      a.ldq = a.ldk = a.ldv = 6 * d;
+      a.q_lo = a.k_lo = a.v_lo = 3 * d;
+      a.ldp = 2 * L * d;
+      a.p_lo = L * d;
+      a.ldo = 2 * d;
+      a.o_lo = d;
+      a.groups = B;
+      a.Tq = Tp;
+      a.Tk = Tp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_lens;
+      a.chunk = att_chunk > 0 ? att_chunk : 0;
+      a.left = att_left;
+      if (launch_attention_f32(a, stream)) return -1;
+    } else if (tc_attn) {
       // s = (q . (k + p) + (u . k + v . p)) / sqrt(d_k): fold the position term into the keys and a key bias
       bf16* kpp = m->ws_kpp.as<bf16>();
       float* cb = m->ws_cbias.as<float>();
@@ -646,31 +717,31 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       a.scale = att_scale;
       if (launch_attention(a, stream)) return -1;
     }
-    if (gemm(att, E.out, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    if (gemm(m, att, E.out, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
     // convolution module                                                       (encoder_layer.py:222-231)
-    if (launch_layernorm(x, E.norm_conv.g, E.norm_conv.b, 1e-5f, (int)M, d, n, nullptr, d_lens, Tp, 1, stream))
+    if (launch_layernorm(x, E.norm_conv.g, E.norm_conv.b, 1e-5f, (int)M, d, n, nullptr, d_lens, Tp, 1, stream, x3))
       return -1;
-    if (gemm(n, E.pw1, (int)M, ACT_GLU, OUT_BF16, pw, 1.f, stream)) return -1;   // pw = GLU(pointwise_conv1), (M, d)
+    if (gemm(m, n, E.pw1, (int)M, ACT_GLU, OUT_BF16, pw, 1.f, stream)) return -1;   // pw = GLU(pointwise_conv1), (M, d)
     if (launch_conv_mid(pw, E.pad_glu, E.dw_w, E.dw_b, E.cnorm.g, E.cnorm.b, E.bn_mean, E.bn_var, c.cnn_layer_norm, 1e-5f, cm, B,
                         Tp, d, c.cnn_kernel, c.causal, stream, y /*fp32 (M, d) scratch, free until the LSL mix*/,
-                        m->ws_cbias.as<float>() + (size_t)B * H * Tp))
+                        m->ws_cbias.as<float>() + (size_t)B * H * Tp, x3))
       return -1;
-    if (gemm(cm, E.pw2, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream, d_lens, Tp)) return -1;
+    if (gemm(m, cm, E.pw2, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream, d_lens, Tp)) return -1;
     // FFN (+ language-specific mix on the first / last block)                   (encoder_layer.py:233-242, 372-400)
-    if (launch_layernorm(x, E.norm_ff.g, E.norm_ff.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+    if (launch_layernorm(x, E.norm_ff.g, E.norm_ff.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
     const bf16* ffn_in = n;
     if (E.lsl) {
-      if (gemm(n, E.lang, (int)M, ACT_NONE, OUT_F32, y, 1.f, stream)) return -1;
-      if (launch_f32_to_bf16(y, ybf, M * d, stream)) return -1;
+      if (gemm(m, n, E.lang, (int)M, ACT_NONE, OUT_F32, y, 1.f, stream)) return -1;
+      if (x3 ? launch_f32_to_pair(y, ybf, M, d, stream) : launch_f32_to_bf16(y, ybf, M * d, stream)) return -1;
       ffn_in = ybf;
     }
-    if (gemm(ffn_in, E.ff1, (int)M, ACT_SILU, OUT_BF16, h, 1.f, stream)) return -1;
-    if (gemm(h, E.ff2, (int)M, ACT_NONE, OUT_RESID_F32, x, 0.5f, stream)) return -1;
+    if (gemm(m, ffn_in, E.ff1, (int)M, ACT_SILU, OUT_BF16, h, 1.f, stream)) return -1;
+    if (gemm(m, h, E.ff2, (int)M, ACT_NONE, OUT_RESID_F32, x, 0.5f, stream)) return -1;
     // x = norm_final(x) (+ y) ; then the next block's first pre-norm, or after_norm for the last block
     const bool last = (l == L - 1);
     const Norm& nx = last ? m->after_norm : m->enc[l + 1].norm_ffm;
     if (launch_double_layernorm(x, E.norm_final.g, E.norm_final.b, E.lsl ? y : nullptr, x, nx.g, nx.b, 1e-5f, (int)M,
-                                d, last ? nullptr : n, last ? d_enc_out : nullptr, stream))
+                                d, last ? nullptr : n, last ? d_enc_out : nullptr, stream, x3))
       return -1;
   }
   return 0;
@@ -687,11 +758,12 @@ static int ctc_topk(rvb_model* m, const float* d_enc_out, int B, int Tp, int k, 
   const long long M = (long long)B * Tp;
   const int d = c.d_model, V = c.vocab;
   const int ldv = (V + 3) & ~3;
-  if (m->ws_encbf.ensure((size_t)M * d * 2) || m->ws_logits.ensure((size_t)M * ldv * 4)) return -1;
+  if (m->ws_encbf.ensure((size_t)M * d * 2 * m->pm()) || m->ws_logits.ensure((size_t)M * ldv * 4)) return -1;
   bf16* encbf = m->ws_encbf.as<bf16>();
   float* logits = m->ws_logits.as<float>();
-  if (launch_f32_to_bf16(d_enc_out, encbf, M * d, stream)) return -1;
-  if (gemm(encbf, m->ctc, (int)M, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
+  if (m->x3 ? launch_f32_to_pair(d_enc_out, encbf, M, d, stream) : launch_f32_to_bf16(d_enc_out, encbf, M * d, stream))
+    return -1;
+  if (gemm(m, encbf, m->ctc, (int)M, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
   if (blank_penalty > 0.f) {
     sub_column_kernel<<<(int)((M + 255) / 256), 256, 0, stream>>>(logits, ldv, (int)M, blank_id, blank_penalty);
     RVB_COUNT_LAUNCH();
@@ -715,9 +787,11 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
   const int ldv = (V + 3) & ~3;
   RVB_REQUIRE(R < (1ll << 31) && R * ldv < (1ll << 40), "rescoring: too many hypothesis rows");
   DevBuf* w = m->ws_dec;
-  if (w[0].ensure((size_t)R * d * 4) || w[1].ensure((size_t)R * d * 2) || w[2].ensure((size_t)R * 3 * d * 2) ||
-      w[3].ensure((size_t)R * d * 2) || w[4].ensure((size_t)Mem * 2 * d * 2) ||
-      w[5].ensure((size_t)R * c.dec_ffn_dim * 2) || w[6].ensure((size_t)R * d * 2))
+  const bool x3 = m->x3;
+  const size_t pm = (size_t)m->pm();
+  if (w[0].ensure((size_t)R * d * 4) || w[1].ensure((size_t)R * d * 2 * pm) || w[2].ensure((size_t)R * 3 * d * 2 * pm) ||
+      w[3].ensure((size_t)R * d * 2 * pm) || w[4].ensure((size_t)Mem * 2 * d * 2 * pm) ||
+      w[5].ensure((size_t)R * c.dec_ffn_dim * 2 * pm) || w[6].ensure((size_t)R * d * 2 * pm))
     return -1;
   float* x = w[0].as<float>();
   bf16* n = w[1].as<bf16>();
@@ -732,9 +806,28 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
   for (size_t l = 0; l < D.layers.size(); ++l) {
     DecLayer& Ld = D.layers[l];
     // masked self-attention (decoder_layer.py:95-110 / 286-301)
-    if (launch_layernorm(x, Ld.n1.g, Ld.n1.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
-    if (gemm(n, Ld.qkv, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
-    if (attn_impl() == 1 && dk == 64) {
+    if (launch_layernorm(x, Ld.n1.g, Ld.n1.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    if (gemm(m, n, Ld.qkv, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    if (x3) {
+      AttnF32Args a;  // one group per hypothesis, causal, keys beyond the hypothesis length masked
+      a.q = qkv;
+      a.k = qkv + d;
+      a.v = qkv + 2 * d;
+      a.out = att;
+      a.ldq = a.ldk = a.ldv = 6 * d;
+      a.q_lo = a.k_lo = a.v_lo = 3 * d;
+      a.ldo = 2 * d;
+      a.o_lo = d;
+      a.groups = S;
+      a.Tq = Lp;
+      a.Tk = Lp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_seq_lens;
+      a.chunk = 1;
+      a.left = -1;
+      if (launch_attention_f32(a, stream)) return -1;
+    } else if (attn_impl() == 1 && dk == 64) {
       AttnTcArgs a;  // one group per hypothesis, causal, keys beyond the hypothesis length masked
       a.q = qkv;
       a.k = qkv + d;
@@ -769,12 +862,31 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
       a.scale = scale;
       if (launch_attention(a, stream)) return -1;
     }
-    if (gemm(att, Ld.so, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    if (gemm(m, att, Ld.so, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
     // source attention over the utterance's encoder output, K/V projected ONCE per utterance
-    if (launch_layernorm(x, Ld.n2.g, Ld.n2.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
-    if (gemm(n, Ld.cq, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;  // q -> first d cols, ld = d
-    if (gemm(enc_bf, Ld.ckv, (int)Mem, ACT_NONE, OUT_BF16, kv, 1.f, stream)) return -1;
-    if (attn_impl() == 1 && dk == 64) {
+    if (launch_layernorm(x, Ld.n2.g, Ld.n2.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    if (gemm(m, n, Ld.cq, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;  // q -> first d cols, ld = d
+    if (gemm(m, enc_bf, Ld.ckv, (int)Mem, ACT_NONE, OUT_BF16, kv, 1.f, stream)) return -1;
+    if (x3) {
+      AttnF32Args a;  // one group per utterance: its N hypotheses share the keys
+      a.q = qkv;
+      a.k = kv;
+      a.v = kv + d;
+      a.out = att;
+      a.ldq = 2 * d;
+      a.q_lo = d;
+      a.ldk = a.ldv = 4 * d;
+      a.k_lo = a.v_lo = 2 * d;
+      a.ldo = 2 * d;
+      a.o_lo = d;
+      a.groups = B;
+      a.Tq = N * Lp;
+      a.Tk = Tp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_enc_lens;
+      if (launch_attention_f32(a, stream)) return -1;
+    } else if (attn_impl() == 1 && dk == 64) {
       // the N hypotheses of an utterance share its keys: one group per utterance with N * Lp query rows
       AttnTcArgs a;
       a.q = qkv;
@@ -811,25 +923,26 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
       a.scale = scale;
       if (launch_attention(a, stream)) return -1;
     }
-    if (gemm(att, Ld.co, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    if (gemm(m, att, Ld.co, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
     // feed forward (ReLU), language-specific mix first on LSL layers
-    if (launch_layernorm(x, Ld.n3.g, Ld.n3.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+    if (launch_layernorm(x, Ld.n3.g, Ld.n3.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
     const bf16* ffn_in = n;
     if (Ld.lsl) {
-      if (gemm(n, Ld.lang, (int)R, ACT_NONE, OUT_BF16, ybf, 1.f, stream)) return -1;
+      if (gemm(m, n, Ld.lang, (int)R, ACT_NONE, OUT_BF16, ybf, 1.f, stream)) return -1;
       ffn_in = ybf;
     }
-    if (gemm(ffn_in, Ld.ff1, (int)R, ACT_RELU, OUT_BF16, h, 1.f, stream)) return -1;
-    if (gemm(h, Ld.ff2, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    if (gemm(m, ffn_in, Ld.ff1, (int)R, ACT_RELU, OUT_BF16, h, 1.f, stream)) return -1;
+    if (gemm(m, h, Ld.ff2, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
   }
-  if (launch_layernorm(x, D.after.g, D.after.b, 1e-5f, (int)R, d, n, nullptr, nullptr, 0, 0, stream)) return -1;
+  if (launch_layernorm(x, D.after.g, D.after.b, 1e-5f, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
   if (step_k > 0) {
     // rows s*Lp + (Lp-1): the A operand is the strided view (S, d) with leading dimension Lp*d
     if (m->ws_logits.ensure((size_t)S * ldv * 4)) return -1;
     logits = m->ws_logits.as<float>();
     GemmArgs g;
-    g.A = n + (size_t)(Lp - 1) * d;
-    g.lda = Lp * d;
+    g.x3 = x3 ? 1 : 0;
+    g.A = n + (size_t)(Lp - 1) * d * pm;
+    g.lda = Lp * d * (int)pm;
     g.W = D.outl.w;
     g.bias = D.outl.b;
     g.M = S;
@@ -851,6 +964,7 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
     float2* part = w[7].as<float2>();
     float* tgt = reinterpret_cast<float*>(part + (size_t)R * slabs);
     GemmArgs g;
+    g.x3 = x3 ? 1 : 0;
     g.A = n;
     g.W = D.outl.w;
     g.bias = D.outl.b;
@@ -866,7 +980,7 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
   }
   if (m->ws_logits.ensure((size_t)R * ldv * 4)) return -1;
   logits = m->ws_logits.as<float>();
-  if (gemm(n, D.outl, (int)R, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
+  if (gemm(m, n, D.outl, (int)R, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
   return launch_logsoftmax_gather(logits, ldv, (int)R, V, d_gather, 1, d_scores, stream);
 }
 
@@ -885,7 +999,7 @@ static int decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_
   const size_t ints = (size_t)R + S + B;
   const size_t out_bytes = (size_t)S * k * (sizeof(float) + sizeof(int));
   if (m->pin_b.ensure(ints * sizeof(int)) || m->ws_misc.ensure(ints * sizeof(int) + out_bytes) ||
-      m->pin_c.ensure(out_bytes) || m->ws_encbf.ensure((size_t)Mem * d * 2))
+      m->pin_c.ensure(out_bytes) || m->ws_encbf.ensure((size_t)Mem * d * 2 * m->pm()))
     return -1;
   int* hp = m->pin_b.as<int>();
   for (long long r = 0; r < R; ++r) {
@@ -899,7 +1013,8 @@ static int decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_
   float* d_val = reinterpret_cast<float*>(dp + ints);
   int* d_idx = reinterpret_cast<int*>(d_val + (size_t)S * k);
   bf16* encbf = m->ws_encbf.as<bf16>();
-  if (launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream)) return -1;
+  if (m->x3 ? launch_f32_to_pair(d_enc_out, encbf, Mem, d, stream) : launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream))
+    return -1;
   if (decoder_pass(m, m->dec_l, encbf, dp + R + S, B, Tp, N, L, dp, dp + R, nullptr, nullptr, stream, k, d_val, d_idx))
     return -1;
   RVB_CHECK_CUDA(cudaMemcpyAsync(m->pin_c.p, d_val, out_bytes, cudaMemcpyDeviceToHost, stream));
@@ -918,9 +1033,10 @@ static int rescoring_device(rvb_model* m, const float* d_enc_out, const int* d_e
                             bool use_r, float* d_sc_l, float* d_sc_r, cudaStream_t stream) {
   const int d = m->cfg.d_model;
   const long long Mem = (long long)B * Tp;
-  if (m->ws_encbf.ensure((size_t)Mem * d * 2)) return -1;
+  if (m->ws_encbf.ensure((size_t)Mem * d * 2 * m->pm())) return -1;
   bf16* encbf = m->ws_encbf.as<bf16>();
-  if (launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream)) return -1;
+  if (m->x3 ? launch_f32_to_pair(d_enc_out, encbf, Mem, d, stream) : launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream))
+    return -1;
   if (decoder_pass(m, m->dec_l, encbf, d_elen, B, Tp, N, Lp, tok_l, slen, gat_l, d_sc_l, stream)) return -1;
   if (use_r && decoder_pass(m, m->dec_r, encbf, d_elen, B, Tp, N, Lp, tok_r, slen, gat_r, d_sc_r, stream)) return -1;
   return 0;
@@ -1177,8 +1293,13 @@ RVB_API rvb_model* rvb_model_create(const rvb_model_config* cfg) {
     rvb::set_error("rvb_model_create: no CUDA device (this library has no CPU path)");
     return nullptr;
   }
+  if (cfg->precision != 0 && cfg->precision != 1) {
+    rvb::set_error("rvb_model_create: precision must be 0 (bf16) or 1 (bf16x3, fp32-accurate)");
+    return nullptr;
+  }
   rvb_model* m = new rvb_model();
   m->cfg = *cfg;
+  m->x3 = cfg->precision == 1;
   return m;
 }
 
@@ -1205,6 +1326,7 @@ RVB_API rvb_model* rvb_model_fork(rvb_model* m) {
   }
   rvb_model* f = new rvb_model();
   f->cfg = m->cfg;
+  f->x3 = m->x3;
   f->finalized = true;
   f->cmvn_mean = m->cmvn_mean;
   f->cmvn_istd = m->cmvn_istd;
@@ -1221,7 +1343,7 @@ RVB_API rvb_model* rvb_model_fork(rvb_model* m) {
   const int d = m->cfg.d_model;
   auto own_fold = [&](rvb::Linear& L) -> int {
     void* p = nullptr;
-    if (rvb::alloc_dev(f, (size_t)d * d * sizeof(rvb::bf16), &p)) return -1;
+    if (rvb::alloc_dev(f, (size_t)d * d * sizeof(rvb::bf16) * f->pm(), &p)) return -1;
     L.w = reinterpret_cast<rvb::bf16*>(p);
     if (rvb::alloc_dev(f, (size_t)d * sizeof(float), &p)) return -1;
     L.b = reinterpret_cast<float*>(p);
@@ -1246,7 +1368,7 @@ RVB_API void rvb_model_destroy(rvb_model* m) {
   for (void* p : m->owned) cudaFree(p);
   DevBuf* bufs[] = {&m->ws_c1, &m->ws_c2, &m->ws_x, &m->ws_n, &m->ws_h, &m->ws_qkv, &m->ws_att, &m->ws_pw, &m->ws_cm,
                     &m->ws_y, &m->ws_ybf, &m->ws_pe, &m->ws_pall, &m->ws_lens, &m->ws_encbf, &m->ws_logits,
-                    &m->ws_search, &m->ws_misc, &m->ws_kpp, &m->ws_cbias};
+                    &m->ws_search, &m->ws_misc, &m->ws_kpp, &m->ws_cbias, &m->ws_fold};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : m->ws_dec) b.release();
   if (m->tickets) {
@@ -1494,6 +1616,29 @@ RVB_API int rvb_gemm_bf16(const void* d_A, const void* d_W, const float* d_bias,
   g.out = d_out;
   g.ldo = ldo;
   return rvb::launch_gemm(g, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_gemm_bf16x3(const void* d_A, const void* d_W, const float* d_bias, int M, int N, int K, int act, int out_mode,
+                            float alpha, void* d_out, int ldo, void* stream) {
+  rvb::GemmArgs g;
+  g.A = reinterpret_cast<const rvb::bf16*>(d_A);
+  g.W = reinterpret_cast<const rvb::bf16*>(d_W);
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.bias = d_bias;
+  g.act = act;
+  g.out_mode = out_mode;
+  g.alpha = alpha;
+  g.out = d_out;
+  g.ldo = ldo;
+  g.x3 = 1;
+  if (out_mode == rvb::OUT_BF16) g.out_split = (act == rvb::ACT_GLU) ? N / 2 : N;
+  return rvb::launch_gemm(g, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_f32_to_bf16_pair(const float* d_x, void* d_out, long long rows, int width, void* stream) {
+  return rvb::launch_f32_to_pair(d_x, reinterpret_cast<rvb::bf16*>(d_out), rows, width, (cudaStream_t)stream);
 }
 
 RVB_API long long rvb_gemm_logsoftmax_gather_ws_bytes(int M, int N) {

@@ -57,10 +57,16 @@ struct GemmKParams {
   const int* row_lens;
   int rows_per_batch;
   int conv_mode, conv_T2, conv_F2, conv_tt, conv_cblocks;
+  int conv_orow_mul;   // rows of `ldo` elements per (b, t'): F2, or 2*F2 for the hi/lo pair output (conv_pair_out)
   const int* lse_gather;  // OUT_LSE (kernels.h)
   float2* lse_part;
   float* lse_tgt;
   int lse_nslab;
+  int x3;              // bf16x3 accurate mode: num_k_blocks = 3 * kb_seg, pass s reads A half (s == 1), W half (s == 2)
+  int kb_seg;          // k-blocks per pass (K / 64)
+  int a_lo_ofs;        // column offset (elements) of the lo half of A: K (plain) or C (conv_mode: channel offset)
+  int w_lo_ofs;        // column offset of the lo half of W: K
+  long long out_split; // > 0: bf16 outputs are written as a hi / lo pair, lo at column + out_split
   int debug_skip_epi;  // RVB_GEMM_SKIP_EPI=1 (tuning aid): epilogue warps only hand the accumulator back, no stores
   int glu_coalesced;   // ACT_GLU with 16-byte aligned output rows (always true after the launch checks)
   int bf16_coalesced;  // bf16 output rows are 16-byte aligned -> staged, coalesced epilogue (see drain_tile)
@@ -260,7 +266,7 @@ __device__ __forceinline__ long long output_row(const GemmKParams& p, const Tile
   if (p.conv_mode) {
     int tp = t.row0 + r;
     if (tp >= p.conv_T2) return -1;
-    return ((long long)t.b * p.conv_T2 + tp) * p.conv_F2 + t.f;
+    return ((long long)t.b * p.conv_T2 + tp) * p.conv_orow_mul + t.f;
   }
   int m = t.row0 + r;
   if (m >= p.M) return -1;
@@ -381,6 +387,10 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
 #pragma unroll 1
       for (int c = c0; c < c1; c += 128) {
         if (n0_tile + c >= p.N) break;
+        // out_split > 0 (bf16x3): the tile is written twice, first the hi halves, then the residues lo = v - hi
+        const int nparts = p.out_split > 0 ? 2 : 1;
+#pragma unroll 1
+        for (int part = 0; part < nparts; ++part) {
 #pragma unroll 1
         for (int hf = 0; hf < 2; ++hf) {  // two groups of 32 value + 32 gate columns -> 16-byte slots 4*hf .. 4*hf+3
           uint32_t av[32], gv[32];
@@ -404,11 +414,22 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
               const float2 a23 = ffma2(make_float2(__uint_as_float(av[e + 2]), __uint_as_float(av[e + 3])), one2, make_float2(ba.z, ba.w));
               const float2 g01 = ffma2(make_float2(__uint_as_float(gv[e + 0]), __uint_as_float(gv[e + 1])), one2, make_float2(bg.x, bg.y));
               const float2 g23 = ffma2(make_float2(__uint_as_float(gv[e + 2]), __uint_as_float(gv[e + 3])), one2, make_float2(bg.z, bg.w));
-              const float2 o01 = gated2(a01, g01), o23 = gated2(a23, g23);
+              float2 o01, o23;
+              if (nparts == 2) {  // accurate mode: exact division / exp instead of the ex2 / rcp approximations
+                o01 = make_float2(a01.x / (1.f + expf(-g01.x)), a01.y / (1.f + expf(-g01.y)));
+                o23 = make_float2(a23.x / (1.f + expf(-g23.x)), a23.y / (1.f + expf(-g23.y)));
+              } else {
+                o01 = gated2(a01, g01);
+                o23 = gated2(a23, g23);
+              }
               v[4 * h2 + 0] = o01.x;
               v[4 * h2 + 1] = o01.y;
               v[4 * h2 + 2] = o23.x;
               v[4 * h2 + 3] = o23.y;
+            }
+            if (part == 1) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16(v[e]));
             }
             const int sl = 4 * hf + j;
             *reinterpret_cast<uint4*>(stage_u + lane * 32 + ((sl ^ (lane & 7)) << 2)) =
@@ -421,9 +442,10 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + rsub;
           const uint4 u = *reinterpret_cast<const uint4*>(stage_u + row * 32 + ((slot ^ (row & 7)) << 2));
-          if (ro[it] >= 0) *reinterpret_cast<uint4*>(out + ro[it] + (c >> 1)) = u;
+          if (ro[it] >= 0) *reinterpret_cast<uint4*>(out + ro[it] + (c >> 1) + part * p.out_split) = u;
         }
         __syncwarp();
+        }
       }
       return;
     }
@@ -461,6 +483,10 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
         tmem_ld_32x32(taddr + c + 32, acc + 32);
         tmem_ld_wait();
         const int n0 = n0_tile + c;
+        // out_split > 0 (bf16x3): the tile is written twice, first hi = bf16(v), then the residue lo = bf16(v - hi)
+        const int nparts = p.out_split > 0 ? 2 : 1;
+#pragma unroll 1
+        for (int part = 0; part < nparts; ++part) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {  // 8 columns -> one 16-byte slot
           float v[8];
@@ -475,8 +501,13 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
             float2 hi = ffma2(make_float2(__uint_as_float(acc[8 * j + 4 * h + 2]), __uint_as_float(acc[8 * j + 4 * h + 3])),
                               one2, make_float2(b4.z, b4.w));
             if (EPI == EPI_BF16_SILU) {
-              lo = gated2(lo, lo);
-              hi = gated2(hi, hi);
+              if (nparts == 2) {  // accurate mode: exact exp / division
+                lo = make_float2(lo.x / (1.f + expf(-lo.x)), lo.y / (1.f + expf(-lo.y)));
+                hi = make_float2(hi.x / (1.f + expf(-hi.x)), hi.y / (1.f + expf(-hi.y)));
+              } else {
+                lo = gated2(lo, lo);
+                hi = gated2(hi, hi);
+              }
             }
             v[4 * h + 0] = lo.x;
             v[4 * h + 1] = lo.y;
@@ -486,6 +517,10 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
           if (EPI == EPI_BF16_RELU) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+          }
+          if (part == 1) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16(v[e]));
           }
           if (p.debug_skip_epi == 3 && v[0] != 123.456f) continue;  // tuning aid: TMEM loads + math only
           *reinterpret_cast<uint4*>(stage_u + lane * 32 + ((j ^ (lane & 7)) << 2)) =
@@ -498,9 +533,10 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + rsub;
           const uint4 u = *reinterpret_cast<const uint4*>(stage_u + row * 32 + ((slot ^ (row & 7)) << 2));
-          if (ro[it] >= 0 && p.debug_skip_epi != 2) *reinterpret_cast<uint4*>(out + ro[it] + c) = u;
+          if (ro[it] >= 0 && p.debug_skip_epi != 2) *reinterpret_cast<uint4*>(out + ro[it] + c + part * p.out_split) = u;
         }
         __syncwarp();
+        }
       } else {
         for (int cc = c; cc < c + 64 && cc < c1; cc += 32) {
           if (n0_tile + cc >= p.N) break;
@@ -664,19 +700,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t stage = 0, phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kbx = 0; kbx < nkb; ++kbx) {
+        // bf16x3: pass 0 = A_hi W_hi, pass 1 = A_lo W_hi, pass 2 = A_hi W_lo
+        const int seg = p.x3 ? kbx / p.kb_seg : 0;
+        const int kb = kbx - seg * p.kb_seg;
+        const int a_ofs = (seg == 1) ? p.a_lo_ofs : 0, w_ofs = (seg == 2) ? p.w_lo_ofs : 0;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
         if (p.conv_mode) {
           int tap = kb / p.conv_cblocks;
           int cb = kb - tap * p.conv_cblocks;
           int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, 2 * t.f + kw, t.row0 + (kh >> 1),
+          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64 + a_ofs, 2 * t.f + kw, t.row0 + (kh >> 1),
                       t.b * 2 + (kh & 1));
         } else {
-          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64, t.row0, 0, 0);
+          tma_load_4d(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64 + a_ofs, t.row0, 0, 0);
         }
-        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, t.n0);
+        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64 + w_ofs, t.n0);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -830,7 +870,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t stage = 0, phase = 0;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
       TileCoord t = tile_coord(tile);
-      for (int kb = 0; kb < nkb; ++kb) {
+      for (int kbx = 0; kbx < nkb; ++kbx) {
+        const int seg = p.x3 ? kbx / p.kb_seg : 0;   // bf16x3 passes, see gemm_tc_kernel
+        const int kb = kbx - seg * p.kb_seg;
+        const int a_ofs = (seg == 1) ? p.a_lo_ofs : 0, w_ofs = (seg == 2) ? p.w_lo_ofs : 0;
         mbar_wait(&empty[stage], phase ^ 1);
         // Only the leader arrives (expecting both CTAs' bytes).  The peer cannot run a phase ahead: its `empty`
         // barrier is released by the leader's tcgen05.commit, i.e. after the leader consumed this phase.
@@ -839,12 +882,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           int tap = kb / p.conv_cblocks;
           int cb = kb - tap * p.conv_cblocks;
           int kh = tap / 3, kw = tap - kh * 3;
-          tma_load_4d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64, 2 * t.f + kw, t.row0 + (kh >> 1),
-                          t.b * 2 + (kh & 1));
+          tma_load_4d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], cb * 64 + a_ofs, 2 * t.f + kw,
+                          t.row0 + (kh >> 1), t.b * 2 + (kh & 1));
         } else {
-          tma_load_4d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64, t.row0, 0, 0);
+          tma_load_4d_2sm(sA + stage * Cfg::A_BYTES, &tmA, &full[stage], kb * 64 + a_ofs, t.row0, 0, 0);
         }
-        tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64, t.n0 + (int)rank * (BN / 2));
+        tma_load_2d_2sm(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kb * 64 + w_ofs, t.n0 + (int)rank * (BN / 2));
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -1077,22 +1120,22 @@ template <int BN>
 static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap tmA, tmB;
-  const long long lda = a.lda ? a.lda : a.K, ldw = a.ldw ? a.ldw : a.K;
+  const int kmul = a.x3 ? 2 : 1;
+  const long long lda = a.lda ? a.lda : (long long)a.K * kmul, ldw = a.ldw ? a.ldw : (long long)a.K * kmul;
   if (a.conv_mode) {
-    cuuint64_t dims[4] = {(cuuint64_t)a.conv_C, (cuuint64_t)a.conv_F1, (cuuint64_t)a.conv_T1h,
-                          (cuuint64_t)(2 * a.conv_B)};
-    cuuint64_t str[3] = {(cuuint64_t)a.conv_C * 2, (cuuint64_t)a.conv_F1 * a.conv_C * 2,
-                         (cuuint64_t)a.conv_T1h * a.conv_F1 * a.conv_C * 2};
+    const cuuint64_t Cp = (cuuint64_t)a.conv_C * (a.x3 ? 2 : 1);  // physical channels: [hi C | lo C] in bf16x3 mode
+    cuuint64_t dims[4] = {Cp, (cuuint64_t)a.conv_F1, (cuuint64_t)a.conv_T1h, (cuuint64_t)(2 * a.conv_B)};
+    cuuint64_t str[3] = {Cp * 2, (cuuint64_t)a.conv_F1 * Cp * 2, (cuuint64_t)a.conv_T1h * a.conv_F1 * Cp * 2};
     cuuint32_t box[4] = {64, 1, 128, 1};
     if (make_tmap(&tmA, a.A, 4, dims, str, box)) return -1;
   } else {
-    cuuint64_t dims[4] = {(cuuint64_t)a.K, (cuuint64_t)a.M, 1, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)a.K * (a.x3 ? 2 : 1), (cuuint64_t)a.M, 1, 1};
     cuuint64_t str[3] = {(cuuint64_t)lda * 2, (cuuint64_t)lda * 2 * a.M, (cuuint64_t)lda * 2 * a.M};
     cuuint32_t box[4] = {64, 128, 1, 1};
     if (make_tmap(&tmA, a.A, 4, dims, str, box)) return -1;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.N};
+    cuuint64_t dims[2] = {(cuuint64_t)a.K * (a.x3 ? 2 : 1), (cuuint64_t)a.N};
     cuuint64_t str[1] = {(cuuint64_t)ldw * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)BN};
     if (make_tmap(&tmB, a.W, 2, dims, str, box)) return -1;
@@ -1117,7 +1160,7 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   if (g_prof_on) {
     RVB_CHECK_CUDA(cudaEventCreate(&rec.a));
     RVB_CHECK_CUDA(cudaEventCreate(&rec.b));
-    rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
+    rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K * (a.x3 ? 3.0 : 1.0);
     RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
   kern<<<grid, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
@@ -1137,22 +1180,22 @@ template <int BN>
 static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<BN>;
   CUtensorMap tmA, tmB;
-  const long long lda = a.lda ? a.lda : a.K, ldw = a.ldw ? a.ldw : a.K;
+  const int kmul = a.x3 ? 2 : 1;
+  const long long lda = a.lda ? a.lda : (long long)a.K * kmul, ldw = a.ldw ? a.ldw : (long long)a.K * kmul;
   if (a.conv_mode) {
-    cuuint64_t dims[4] = {(cuuint64_t)a.conv_C, (cuuint64_t)a.conv_F1, (cuuint64_t)a.conv_T1h,
-                          (cuuint64_t)(2 * a.conv_B)};
-    cuuint64_t str[3] = {(cuuint64_t)a.conv_C * 2, (cuuint64_t)a.conv_F1 * a.conv_C * 2,
-                         (cuuint64_t)a.conv_T1h * a.conv_F1 * a.conv_C * 2};
+    const cuuint64_t Cp = (cuuint64_t)a.conv_C * (a.x3 ? 2 : 1);  // physical channels: [hi C | lo C] in bf16x3 mode
+    cuuint64_t dims[4] = {Cp, (cuuint64_t)a.conv_F1, (cuuint64_t)a.conv_T1h, (cuuint64_t)(2 * a.conv_B)};
+    cuuint64_t str[3] = {Cp * 2, (cuuint64_t)a.conv_F1 * Cp * 2, (cuuint64_t)a.conv_T1h * a.conv_F1 * Cp * 2};
     cuuint32_t box[4] = {64, 1, 128, 1};
     if (make_tmap(&tmA, a.A, 4, dims, str, box)) return -1;
   } else {
-    cuuint64_t dims[4] = {(cuuint64_t)a.K, (cuuint64_t)a.M, 1, 1};
+    cuuint64_t dims[4] = {(cuuint64_t)a.K * (a.x3 ? 2 : 1), (cuuint64_t)a.M, 1, 1};
     cuuint64_t str[3] = {(cuuint64_t)lda * 2, (cuuint64_t)lda * 2 * a.M, (cuuint64_t)lda * 2 * a.M};
     cuuint32_t box[4] = {64, 128, 1, 1};
     if (make_tmap(&tmA, a.A, 4, dims, str, box)) return -1;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)a.K, (cuuint64_t)a.N};
+    cuuint64_t dims[2] = {(cuuint64_t)a.K * (a.x3 ? 2 : 1), (cuuint64_t)a.N};
     cuuint64_t str[1] = {(cuuint64_t)ldw * 2};
     cuuint32_t box[2] = {64, (cuuint32_t)(BN / 2)};
     if (make_tmap(&tmB, a.W, 2, dims, str, box)) return -1;
@@ -1179,7 +1222,7 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   if (g_prof_on) {
     RVB_CHECK_CUDA(cudaEventCreate(&rec.a));
     RVB_CHECK_CUDA(cudaEventCreate(&rec.b));
-    rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K;
+    rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K * (a.x3 ? 3.0 : 1.0);
     RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
   kern<<<2 * clusters, kGemmThreads, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
@@ -1209,11 +1252,23 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.N = a.N;
   p.K = a.K;
   p.num_k_blocks = (a.K + 63) / 64;
+  p.x3 = a.x3;
+  p.kb_seg = p.num_k_blocks;
+  p.out_split = a.out_split;
+  if (a.x3) {
+    RVB_REQUIRE(a.K % 64 == 0, "gemm: bf16x3 mode needs K %% 64 == 0 (K=%d)", a.K);
+    RVB_REQUIRE(get_gemm_impl() != 1, "gemm: bf16x3 mode is not built for the simt bring-up kernel");
+    p.num_k_blocks *= 3;
+    p.a_lo_ofs = a.conv_mode ? a.conv_C : a.K;
+    p.w_lo_ofs = a.K;
+  }
+  if (a.out_split > 0)
+    RVB_REQUIRE((a.out_mode == OUT_BF16) && a.out_split % 8 == 0, "gemm: out_split needs an aligned bf16 output");
   p.bias = a.bias;
   p.act = a.act;
   p.out_mode = a.out_mode;
   p.out = a.out;
-  p.ldo = a.ldo ? a.ldo : (a.act == ACT_GLU ? a.N / 2 : a.N);
+  p.ldo = a.ldo ? a.ldo : (long long)(a.act == ACT_GLU ? a.N / 2 : a.N) * (a.out_split > 0 ? 2 : 1);
   p.alpha = a.alpha;
   p.row_lens = a.row_lens;
   p.rows_per_batch = a.rows_per_batch > 0 ? a.rows_per_batch : a.M;
@@ -1249,19 +1304,23 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
                     (a.bias == nullptr || (reinterpret_cast<uintptr_t>(a.bias) & 15) == 0);
   p.A = a.A;
   p.W = a.W;
-  p.lda = a.lda ? a.lda : a.K;
-  p.ldw = a.ldw ? a.ldw : a.K;
+  p.lda = a.lda ? a.lda : (long long)a.K * (a.x3 ? 2 : 1);
+  p.ldw = a.ldw ? a.ldw : (long long)a.K * (a.x3 ? 2 : 1);
   if (a.conv_mode) {
     RVB_REQUIRE(a.conv_C % 64 == 0, "conv implicit GEMM needs C %% 64 == 0 (C=%d)", a.conv_C);
     RVB_REQUIRE(a.K == 9 * a.conv_C && a.M == a.conv_B * a.conv_F2 * a.conv_T2, "conv implicit GEMM: bad M/K");
     p.conv_T2 = a.conv_T2;
     p.conv_F2 = a.conv_F2;
+    p.conv_orow_mul = a.conv_pair_out ? 2 * a.conv_F2 : a.conv_F2;
     p.conv_tt = (a.conv_T2 + 127) / 128;
     p.conv_cblocks = a.conv_C / 64;
     p.conv_T1h = a.conv_T1h;
     p.conv_F1 = a.conv_F1;
     p.conv_C = a.conv_C;
   }
+  if (a.out_split > 0)
+    RVB_REQUIRE(a.N % 128 == 0 && (a.act == ACT_GLU ? p.glu_coalesced : p.bf16_coalesced),
+                "gemm: a hi/lo output pair needs N %% 128 == 0 and 16-byte aligned rows (N=%d)", a.N);
   if (a.act == ACT_GLU) {
     RVB_REQUIRE(a.out_mode == OUT_BF16 && a.N % 64 == 0 && !a.conv_mode, "gemm: ACT_GLU needs bf16 output and N %% 64 == 0");
     RVB_REQUIRE((reinterpret_cast<uintptr_t>(a.out) & 15) == 0 && p.ldo % 8 == 0 &&

@@ -45,6 +45,16 @@ struct GemmArgs {
   //   K = 9*C ordered (kh, kw, c); output row (b, t', f) -> out[((b*T2 + t')*F2 + f) * ldo + n]
   int conv_mode = 0;
   int conv_B = 0, conv_T1h = 0, conv_F1 = 0, conv_C = 0, conv_T2 = 0, conv_F2 = 0;
+  // fp32-accurate mode ("bf16x3"): every operand is a PAIR of bf16 matrices hi = bf16(v), lo = bf16(v - hi) stored side
+  // by side — A physical (M, 2K) = [A_hi | A_lo] (lda >= 2K), W physical (N, 2K) = [W_hi | W_lo] (conv_mode: channels
+  // [hi C | lo C] of the activation, W = [hi 9C | lo 9C]) — and the kernel runs THREE passes over K into the same fp32
+  // accumulator: A_hi W_hi + A_lo W_hi + A_hi W_lo (the lo.lo term, ~2^-18 relative, is dropped).  bf16 outputs
+  // (OUT_BF16, ACT_GLU) are written as the same kind of pair: hi at column n, lo at column n + out_split.
+  int x3 = 0;
+  int out_split = 0;  // elements; > 0: bf16 output pair (ldo must cover both halves)
+  // conv_mode + out_split: output row (b, t') holds [hi (F2*N) | lo (F2*N)] (out_split = F2*N), i.e. element (b,t',f,n)
+  // -> out[((b*T2 + t') * 2*F2 + f) * ldo + n] — the pair-layout A operand of the Linear(F2*C -> d) that follows
+  int conv_pair_out = 0;
   // OUT_LSE
   const int* lse_gather = nullptr;   // (M) column index per row, < 0 = none
   float2* lse_part = nullptr;        // (M, lse_slabs(N)) {max, sum exp(x - max)}; slabs without columns hold {-inf, 0}
@@ -76,27 +86,32 @@ int launch_fbank_batch(const void* wave, int is_i16, int batch, long long wave_s
 // ------------------------------------------------------------------ norms / conv pieces (elementwise.cu)
 // y = LN(x) * gamma + beta ; rows with position >= row_lens[batch] are written as 0 when mask_rows != 0.
 // out_bf16 and/or out_f32 may be null.
+// x3 != 0 (all launchers below): bf16 outputs / inputs use the accurate mode's pair layout [hi | lo] (row stride
+// 2 * width, lo at column + width), see GemmArgs::x3.
 int launch_layernorm(const float* x, const float* gamma, const float* beta, float eps, int M, int d, bf16* out_bf16,
-                     float* out_f32, const int* row_lens, int rows_per_batch, int mask_rows, cudaStream_t stream);
+                     float* out_f32, const int* row_lens, int rows_per_batch, int mask_rows, cudaStream_t stream,
+                     int x3 = 0);
 // x2 = LN_a(x) (fp32, in place allowed) ; n = LN_b(x2) -> bf16.  (norm_final of block i fused with the first
 // pre-norm of block i+1.)  y_add (optional, fp32) is added to x2 after LN_a (LSL "x = x + y").
 int launch_double_layernorm(const float* x, const float* ga, const float* ba, const float* y_add, float* x2,
                             const float* gb, const float* bb, float eps, int M, int d, bf16* n_out,
-                            float* n_out_f32, cudaStream_t stream);
+                            float* n_out_f32, cudaStream_t stream, int x3 = 0);
 // CMVN + Conv2d(1->C, 3x3, stride 2) + ReLU, output bf16 (B, 2, T1h, F1, C) (time split by parity)
 int launch_conv1(const float* feats, const float* mean, const float* istd, const float* w /*[C][9]*/,
                  const float* bias, bf16* out, int B, int T, int F, int C, int T1, int T1h, int F1,
-                 cudaStream_t stream);
+                 cudaStream_t stream, int x3 = 0);
 // depthwise conv (K taps) + LayerNorm|BatchNorm(eval) + SiLU on the GLU'd pointwise_conv1 output (B, T, C) bf16
 // (GEMM epilogue ACT_GLU) -> (B, T, C) bf16.  pad_glu (C, fp32): value of the K-1 causal left pad frames =
 // GLU(pointwise_conv1 bias), not zeros.  conv_tmp (B*T, C) fp32 and stats (B*T, ceil(C/256), 2) scratch are needed with LayerNorm.
 int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w /*[C][K]*/, const float* dw_b,
                     const float* norm_w, const float* norm_b, const float* bn_mean, const float* bn_var,
                     int use_layer_norm, float eps, bf16* out, int B, int T, int C, int K, int causal,
-                    cudaStream_t stream, float* conv_tmp = nullptr, float* stats = nullptr);
+                    cudaStream_t stream, float* conv_tmp = nullptr, float* stats = nullptr, int x3 = 0);
 // x[m, :] = x[m, :] * scale   (fp32 -> fp32 in place) and optional bf16 copy
 int launch_scale_cast(const float* x, float scale, float* out_f32, bf16* out_bf16, long long n, cudaStream_t stream);
 int launch_f32_to_bf16(const float* x, bf16* out, long long n, cudaStream_t stream);
+// (rows, width) fp32 -> (rows, 2 * width) bf16 pair [hi | lo]
+int launch_f32_to_pair(const float* x, bf16* out, long long rows, int width, cudaStream_t stream);
 // out = sum_i c[i] * in_i   (fold of the language-specific linears; n elements, up to 8 inputs)
 int launch_weighted_sum_bf16(const float* const* ins, const float* coef, int n_in, long long n, bf16* out_bf16,
                              float* out_f32, cudaStream_t stream);
@@ -144,6 +159,25 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream);
 // K'' = k + pos (bf16, (B*T, H*dk) dense) and cbias[b,h,t] = u_h . k + v_h . pos
 int launch_relpos_prep(const bf16* k, int ldk, const bf16* pos, int ldp, const float* bias_u, const float* bias_v,
                        bf16* kpp, float* cbias, int B, int T, int H, int dk, cudaStream_t stream);
+
+// fp32 attention of the accurate (bf16x3) mode (attention_f32.cu): same grouping convention as AttnTcArgs; every operand
+// is a bf16 pair (value = x[c] + x[c + *_lo], *_lo == 0: plain bf16).  p (optional): rel-pos keys (Tk, H*dk) shared by
+// all groups, with bias_u / bias_v (H*dk) — the reference's two-product score ((q+u).k + (q+v).p) / sqrt(dk).
+struct AttnF32Args {
+  const bf16* q = nullptr;
+  const bf16* k = nullptr;
+  const bf16* v = nullptr;
+  const bf16* p = nullptr;
+  const float* bias_u = nullptr;
+  const float* bias_v = nullptr;
+  bf16* out = nullptr;
+  int ldq = 0, ldk = 0, ldv = 0, ldp = 0, ldo = 0;
+  int q_lo = 0, k_lo = 0, v_lo = 0, p_lo = 0, o_lo = 0;
+  int groups = 0, Tq = 0, Tk = 0, H = 0, dk = 0;
+  const int* k_lens = nullptr;
+  int chunk = 0, left = -1;  // chunk > 0: streaming chunk mask; chunk = 1, left < 0 = causal
+};
+int launch_attention_f32(const AttnF32Args& a, cudaStream_t stream);
 
 // ------------------------------------------------------------------ CTC head / searches (ctc.cu)
 // per row: logp = log_softmax(logits) ; top-k (k <= 16) of logp with indices ; optional full logp output.

@@ -33,7 +33,21 @@ def _np_ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def model_config_from_yaml(configs: Dict, vocab: int) -> ModelConfig:
+PRECISIONS = {"bf16": 0, "fp32": 1, "bf16x3": 1}
+
+
+def resolve_precision(precision: Optional[str]) -> str:
+    """'bf16' (default: bf16 tensor-core operands, fp32 accumulation — the throughput mode) or 'fp32' (= 'bf16x3': every
+    GEMM runs as three tcgen05 passes over (hi, lo) bf16 operand pairs and the attention in fp32 — reference-level
+    accuracy at ~3x the tensor work).  None -> environment variable RVB_PRECISION, else 'bf16'."""
+    import os
+    p = precision if precision is not None else os.environ.get("RVB_PRECISION", "bf16")
+    if p not in PRECISIONS:
+        raise ValueError(f"reverb_b200: precision must be one of {sorted(PRECISIONS)}, got {p!r}")
+    return "fp32" if PRECISIONS[p] == 1 else "bf16"
+
+
+def model_config_from_yaml(configs: Dict, vocab: int, precision: str = "bf16") -> ModelConfig:
     """config.yaml -> rvb_model_config.  Only the architecture the hot path supports
     (conformer encoder with conv2d input / rel_pos attention, (bi)transformer decoder) is accepted."""
     ec, dc = configs["encoder_conf"], configs.get("decoder_conf", {})
@@ -70,18 +84,21 @@ def model_config_from_yaml(configs: Dict, vocab: int) -> ModelConfig:
     st = (configs.get("tokenizer_conf") or {}).get("special_tokens") or {}
     cfg.sos_id = int(st.get("<sos>", vocab - 1))
     cfg.eos_id = int(st.get("<eos>", vocab - 1))
+    cfg.precision = PRECISIONS[precision]
     return cfg
 
 
 class Engine:
     """Owns one `rvb_model` (packed weights + workspace) on one CUDA device."""
 
-    def __init__(self, configs: Dict, state_dict: Dict[str, torch.Tensor], vocab: int, device: torch.device):
+    def __init__(self, configs: Dict, state_dict: Dict[str, torch.Tensor], vocab: int, device: torch.device,
+                 precision: Optional[str] = None):
         if device.type != "cuda" or not torch.cuda.is_available():
             raise RuntimeError("reverb_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.lib = _lib.load()
         self.device = device
-        self.cfg = model_config_from_yaml(configs, vocab)
+        self.precision = resolve_precision(precision)
+        self.cfg = model_config_from_yaml(configs, vocab, self.precision)
         self.d_model = self.cfg.d_model
         self.vocab = vocab
         self.num_langs = self.cfg.num_langs
@@ -105,6 +122,7 @@ class Engine:
         The parent engine must stay alive as long as the fork is used."""
         other = Engine.__new__(Engine)
         other.lib, other.device, other.cfg = self.lib, self.device, self.cfg
+        other.precision = self.precision
         other.d_model, other.vocab, other.num_langs = self.d_model, self.vocab, self.num_langs
         other.has_right_decoder = self.has_right_decoder
         other._parent = self

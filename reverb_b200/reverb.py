@@ -56,7 +56,8 @@ def _load_state_dict(checkpoint: str) -> Dict[str, torch.Tensor]:
 
 class ReverbASR:
     def __init__(self, config, checkpoint, cmvn_path: str | None = None, tokenizer_symbols: str | None = None,
-                 bpe_path: str | None = None, gpu: int = -1, overwrite_cmvn: bool = False):
+                 bpe_path: str | None = None, gpu: int = -1, overwrite_cmvn: bool = False,
+                 precision: str | None = None):
         self.jit = False
         if not torch.cuda.is_available():
             raise RuntimeError("reverb_b200.ReverbASR needs a CUDA device (B200, sm_100a); no CPU fallback exists")
@@ -96,7 +97,9 @@ class ReverbASR:
             # no GlobalCMVN module in the reference model: the engine's fused (x - mean) * istd becomes the identity
             sd["encoder.global_cmvn.mean"] = torch.zeros(input_dim)
             sd["encoder.global_cmvn.istd"] = torch.ones(input_dim)
-        self.engine = Engine(self.configs, sd, self.configs["output_dim"], self.device)
+        # precision: 'bf16' (default, throughput) or 'fp32' (bf16x3 tcgen05 passes + fp32 attention: reference-level
+        # accuracy, engine.resolve_precision); None -> $RVB_PRECISION.  Not a reference argument: an extension.
+        self.engine = Engine(self.configs, sd, self.configs["output_dim"], self.device, precision)
         self.model = ASRModel(self.engine, self.configs, self.configs["output_dim"])
         self.test_conf = self.configs["dataset_conf"]
         self.input_frame_length = self.test_conf["fbank_conf"]["frame_shift"]
@@ -217,7 +220,7 @@ def get_output(format: str, tokenizer, audio_name: str, hyps: List[DecodeResult]
     return delimiter.join(lines)
 
 
-def load_model(model: str, gpu: int = -1) -> ReverbASR:
+def load_model(model: str, gpu: int = -1, precision: str | None = None) -> ReverbASR:
     """Loads a reverb model from a directory (config.yaml + first *.pt) or by pretrained name."""
     if Path(model).exists():
         model_dir = Path(model)
@@ -237,7 +240,7 @@ def load_model(model: str, gpu: int = -1) -> ReverbASR:
                          f"{','.join(get_available_models())}")
     config_path, checkpoint_path = config_path.resolve(), checkpoint_path.resolve()
     logging.info(f"Loading the model with {config_path = } and {checkpoint_path = }")
-    return ReverbASR(str(config_path), str(checkpoint_path), gpu=gpu)
+    return ReverbASR(str(config_path), str(checkpoint_path), gpu=gpu, precision=precision)
 
 
 def get_available_models():

@@ -385,3 +385,71 @@ def test_gemm_fused_logsoftmax_gather(lib, impl, M, N, K):
         torch.testing.assert_close(out, want, rtol=1e-3, atol=2e-3)
     finally:
         lib.rvb_set_gemm_impl(-1)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fp32-accurate "bf16x3" mode (rvb_model_config.precision = 1)
+def _pair(lib, x):
+    rows, width = x.shape
+    out = torch.empty(rows, 2 * width, device="cuda", dtype=torch.bfloat16)
+    _check(lib, lib.rvb_f32_to_bf16_pair(_p(x.contiguous()), _p(out), rows, width, _stream()))
+    hi, lo = out[:, :width].float(), out[:, width:].float()
+    assert torch.equal(hi, x.bfloat16().float()) and torch.equal(lo, (x - hi).bfloat16().float())
+    return out
+
+
+@pytest.mark.parametrize("impl", [0, 2], ids=["tcgen05", "tcgen05_2cta"])
+@pytest.mark.parametrize("M,N,K", [(300, 256, 128), (1000, 1024, 4096), (4096, 4096, 1024), (513, 10001, 1024)])
+def test_gemm_bf16x3_is_fp32_accurate(lib, impl, M, N, K):
+    """Three tcgen05 passes over (hi, lo) operand pairs: |C - fp64 reference| must be ~2^-16 relative to the row scale —
+    two orders of magnitude below the single-pass bf16 GEMM, at the level of an fp32 matmul."""
+    torch.manual_seed(M + N + K)
+    lib.rvb_set_gemm_impl(impl)
+    try:
+        A = torch.randn(M, K, device="cuda") * 0.5
+        W = torch.randn(N, K, device="cuda") / math.sqrt(K)
+        bias = torch.randn(N, device="cuda")
+        ref = (A.double() @ W.double().t() + bias.double())
+        Ap, Wp = _pair(lib, A), _pair(lib, W)
+        ldo = (N + 3) & ~3
+        out = torch.zeros(M, ldo, device="cuda")
+        _check(lib, lib.rvb_gemm_bf16x3(_p(Ap), _p(Wp), _p(bias), M, N, K, 0, 1, 1.0, _p(out), ldo, _stream()))
+        err3 = float((out[:, :N].double() - ref).abs().max())
+        out1 = torch.zeros(M, ldo, device="cuda")
+        _check(lib, lib.rvb_gemm_bf16(_p(A.bfloat16()), _p(W.bfloat16()), _p(bias), M, N, K, 0, 1, 1.0, _p(out1), ldo, _stream()))
+        err1 = float((out1[:, :N].double() - ref).abs().max())
+        err32 = float(((A @ W.t() + bias).double() - ref).abs().max())      # torch's own fp32 matmul (may use tf32-free path)
+        print(f"[x3 {M}x{N}x{K}] max abs err: bf16x3 {err3:.2e}, bf16 {err1:.2e}, torch fp32 {err32:.2e}")
+        assert err3 < 2e-5 * math.sqrt(K / 128) and err3 < err1 / 50
+        if N % 128 == 0:
+            # bf16 pair output + SiLU: hi + lo reproduces silu(ref) to ~2^-16
+            outp = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
+            _check(lib, lib.rvb_gemm_bf16x3(_p(Ap), _p(Wp), _p(bias), M, N, K, 2, 0, 1.0, _p(outp), 0, _stream()))
+            got = outp[:, :N].float() + outp[:, N:].float()
+            want = torch.nn.functional.silu(ref).float()
+            assert float((got - want).abs().max()) < 1e-4
+            # residual accumulate
+            res = torch.randn(M, N, device="cuda")
+            res0 = res.clone()
+            _check(lib, lib.rvb_gemm_bf16x3(_p(Ap), _p(Wp), _p(bias), M, N, K, 0, 2, 0.5, _p(res), N, _stream()))
+            assert float((res.double() - (res0.double() + 0.5 * ref)).abs().max()) < 1e-4
+    finally:
+        lib.rvb_set_gemm_impl(-1)
+
+
+def test_gemm_bf16x3_glu_pair_output(lib):
+    torch.manual_seed(7)
+    M, Cc, K = 1000, 256, 256
+    A = torch.randn(M, K, device="cuda") * 0.5
+    W = torch.randn(2 * Cc, K, device="cuda") / math.sqrt(K)
+    bias = torch.randn(2 * Cc, device="cuda")
+    ref = torch.nn.functional.glu(A.double() @ W.double().t() + bias.double(), dim=1).float()
+    c = torch.arange(Cc, device="cuda")
+    ra = 64 * (c // 32) + (c % 32)
+    Wq, bq = torch.empty_like(W), torch.empty_like(bias)
+    Wq[ra], Wq[ra + 32] = W[:Cc], W[Cc:]
+    bq[ra], bq[ra + 32] = bias[:Cc], bias[Cc:]
+    out = torch.zeros(M, 2 * Cc, device="cuda", dtype=torch.bfloat16)
+    _check(lib, lib.rvb_gemm_bf16x3(_p(_pair(lib, A)), _p(_pair(lib, Wq)), _p(bq), M, 2 * Cc, K, 3, 0, 1.0, _p(out), 0, _stream()))
+    got = out[:, :Cc].float() + out[:, Cc:].float()
+    assert float((got - ref).abs().max()) < 1e-4

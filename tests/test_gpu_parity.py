@@ -185,6 +185,105 @@ def test_beam_size_limit_is_reported_before_decoding(asr, model_dirs):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# fp32-accurate mode (precision="fp32": bf16x3 tcgen05 GEMMs + fp32 attention)
+@pytest.fixture(scope="module")
+def asr_acc(model_dirs):
+    import reverb_b200
+    return {n: reverb_b200.load_model(d, precision="fp32") for n, (d, _) in model_dirs.items()}
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_accurate_mode_matches_the_live_reference(asr_acc, golden_cases, case):
+    """precision='fp32' against the live reference's tensors and tokens (tests/golden): encoder_out rel-RMS < 2e-5,
+    CTC log-probs to 2e-3 abs (rtol 1e-3-class, the reference's own precedent export_onnx_gpu.py:735-743), decoder
+    token log-probs to 2e-3, and EVERY token / n-best / time / pick identical."""
+    meta, arr = golden_cases[case]
+    m = asr_acc[case]
+    assert m.engine.precision == "fp32"
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    modes = ["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"]
+    worst_enc = worst_lp = worst_conf = 0.0
+    for bi, (fb, fl) in enumerate(m.feats_batcher(feats, meta["chunk_size"], meta["batch_size"])):
+        enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
+        logp = m.model.ctc_logprobs(enc).cpu().numpy()
+        ref_e, ref_p = arr[f"enc_out_{bi}"], arr[f"ctc_probs_{bi}"]
+        got = m.model.decode(modes, fb, fl, meta["beam_size"], ctc_weight=meta["ctc_weight"],
+                             reverse_weight=meta["reverse_weight"], cat_embs=cat, blank_id=0)
+        gold = meta["batches"][bi]
+        for b in range(fb.shape[0]):
+            n = int(enc_lens[b])
+            worst_enc = max(worst_enc, _rel_rms(enc[b, :n].cpu().numpy(), ref_e[b, :n]))
+            sel = ref_p[b, :n] > -12
+            worst_lp = max(worst_lp, float(np.abs(logp[b, :n][sel] - ref_p[b, :n][sel]).max()))
+            assert (logp[b, :n].argmax(-1) == ref_p[b, :n].argmax(-1)).all()
+            assert list(got["ctc_greedy_search"][b].tokens) == gold["ctc_greedy_search"][b]["tokens"]
+            gp, wp = got["ctc_prefix_beam_search"][b], gold["ctc_prefix_beam_search"][b]
+            assert [list(h) for h in gp.nbest] == wp["nbest"] and gp.nbest_times == wp["nbest_times"]
+            np.testing.assert_allclose(gp.nbest_scores, wp["nbest_scores"], rtol=0, atol=5e-2)
+            gr, wr = got["attention_rescoring"][b], gold["attention_rescoring"][b]
+            assert list(gr.tokens) == wr["tokens"] and gr.times == wr["times"]
+            worst_conf = max(worst_conf, float(np.abs(np.asarray(gr.tokens_confidence) - np.asarray(wr["tokens_confidence"])).max()))
+            assert abs(float(gr.score) - float(wr["score"])) < 2e-2
+    _log({"test": "accurate_mode_vs_golden", "case": case, "encoder_rel_rms": worst_enc, "logp_max_abs": worst_lp,
+          "token_conf_max_abs": worst_conf})
+    assert worst_enc < 2e-5 and worst_lp < 2e-3 and worst_conf < 2e-3
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_accurate_mode_ctm_string_equals_live_reference(asr_acc, golden_cases, model_dirs, case):
+    """transcribe() in the accurate mode: the CTM STRING of the live reference, byte for byte."""
+    meta, arr = golden_cases[case]
+    m = asr_acc[case]
+    kw = dict(verbatimicity=meta["verbatimicity"], chunk_size=meta["chunk_size"], batch_size=meta["batch_size"],
+              reverse_weight=meta["reverse_weight"], ctc_weight=meta["ctc_weight"], beam_size=meta["beam_size"])
+    for mode in ("ctc_prefix_beam_search", "attention_rescoring"):
+        got = m.transcribe(model_dirs[case][1], mode=mode, format="ctm", **kw)
+        want = meta["transcribe"][mode + ".ctm"]
+        if got != want:     # the fbank differs by ~1e-4 (fp32 FFT vs torchaudio): allow a last-digit confidence flip
+            g, w = _ctm_rows(got), _ctm_rows(want)
+            assert [r[:5] for r in g] == [r[:5] for r in w]
+            assert max(abs(a[5] - b[5]) for a, b in zip(g, w)) <= 0.01 + 1e-9
+        _log({"test": "accurate_ctm_vs_golden", "case": case, "mode": mode, "string_equal": got == want})
+
+
+def test_accurate_mode_bench_shape_vs_oracle(bench_model_dir):
+    """The benchmarked shape in the accurate mode, 2 x 30 s chunks vs the oracle: encoder rel-RMS < 5e-5, log-probs to
+    5e-3, greedy ids / prefix n-best / rescoring pick identical — the north-star's "bit-exact token ids given identical
+    fbank features"."""
+    import reverb_b200
+    from oracle import fbank_np, pipeline_ref
+    from reverb_b200 import synth
+    d = bench_model_dir
+    asr_b = reverb_b200.ReverbASR(os.path.join(d, "config.yaml"), os.path.join(d, "synth.pt"), gpu=0, precision="fp32")
+    orc = pipeline_ref.OracleASR(d)
+    torch.set_num_threads(min(32, os.cpu_count() or 8))
+    pcm = np.stack([synth.synth_audio(30.0, seed=4321 + i) for i in range(2)])
+    cat = torch.tensor([1.0, 0.0])
+    ofeats = torch.from_numpy(np.stack([fbank_np.fbank(p.astype(np.float32)) for p in pcm]))
+    lens = torch.full((2,), ofeats.shape[1], dtype=torch.int32)
+    modes = ["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"]
+    want = orc.decode(modes, ofeats, lens, 10, ctc_weight=0.1, reverse_weight=0.0, cat_embs=cat, return_intermediates=True)
+    enc, enc_lens = asr_b.model._forward_encoder(ofeats.cuda(), lens, cat)
+    rr = [_rel_rms(enc[b].cpu().numpy(), want["_encoder_out"][b].numpy()) for b in range(2)]
+    logp = asr_b.model.ctc_logprobs(enc).cpu()
+    wl = want["_ctc_probs"]
+    dl = (logp - wl)[wl > -12]
+    got = asr_b.model.decode(modes, ofeats.cuda(), lens, 10, ctc_weight=0.1, reverse_weight=0.0, cat_embs=cat, blank_id=0)
+    _log({"test": "accurate_bench_shape_vs_oracle", "encoder_rel_rms": rr, "logp_max_abs": float(dl.abs().max()),
+          "argmax_agreement": float((logp.argmax(-1) == wl.argmax(-1)).float().mean())})
+    assert max(rr) < 5e-5 and float(dl.abs().max()) < 5e-3
+    assert bool((logp.argmax(-1) == wl.argmax(-1)).all())
+    for b in range(2):
+        assert list(got["ctc_greedy_search"][b].tokens) == list(want["ctc_greedy_search"][b].tokens)
+        gp, wp = got["ctc_prefix_beam_search"][b], want["ctc_prefix_beam_search"][b]
+        assert [tuple(h) for h in gp.nbest] == [tuple(h) for h in wp.nbest] and gp.nbest_times == wp.nbest_times
+        gr, wr = got["attention_rescoring"][b], want["attention_rescoring"][b]
+        assert list(gr.tokens) == list(wr.tokens) and gr.times == wr.times
+        assert abs(float(gr.score) - float(wr.score)) < 5e-2
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # the benchmarked shape
 def test_bench_shape_two_chunks_vs_oracle(bench_model_dir):
     """d=1024 / H=16 / L=18 / V=10001 / T'=748 (the ONLY shape BENCH / SCALE time): fbank, encoder_out, CTC log-probs,
