@@ -178,6 +178,13 @@ RVB_API int rvb_decoder_step_topk(rvb_model* m, const float* d_enc_out, const in
                                   const int* h_hyps, int L, const float* h_cat_embs, int n_cat, int k, float* h_topk_val,
                                   int* h_topk_idx, void* stream);
 
+/* The same decoder step returning the FULL log_softmax row of the last position, h_logp (B*N, vocab) — what
+ * decoder.forward_one_step_with_attn (transformer/decoder.py:236-281) hands to BeamSearchTimeSync
+ * (espnet/beam_search_timesync.py:156-164, 211-218: `joint_decoding`, search.py:450-496). */
+RVB_API int rvb_decoder_step_logp(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
+                                  const int* h_hyps, int L, const float* h_cat_embs, int n_cat, float* h_logp,
+                                  void* stream);
+
 /* ---- kernel-level entry points (parity tests, profiling) ----------------------------------------------------- */
 /* C[M,N] = A[M,K] W[N,K]^T + bias; act: 0 none 1 relu 2 silu 3 glu; out_mode: 0 bf16, 1 f32, 2 f32 residual += alpha*(.)
  * act 3 (pointwise_conv1 + GLU of the conformer conv module, convolution.py:129-130): bf16 output (M, N/2); W / bias

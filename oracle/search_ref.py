@@ -242,3 +242,102 @@ def attention_beam_search(step_topk, batch_size: int, maxlen: int, beam_size: in
         hyp = best_hyps[b]
         results.append(DecodeResult(hyp[hyp != eos].tolist()))
     return results
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def _log_add_list(args) -> float:
+    """espnet/beam_search_timesync.py:29-37."""
+    if all(a == -float("inf") for a in args):
+        return -float("inf")
+    a_max = max(args)
+    return a_max + math.log(sum(math.exp(a - a_max) for a in args))
+
+
+def joint_decoding(decoder_row, ctc_probs: torch.Tensor, enc_lens: torch.Tensor, ctc_weight: float = 0.5,
+                   beam_size: int = 4, pre_beam_ratio: float = 1.5, length_bonus: float = 0.5,
+                   sos: int = 10000, blank: int = 0) -> List[DecodeResult]:
+    """transformer/search.py:450-496 + espnet/beam_search_timesync.py:87-508 (BeamSearchTimeSync without lexicon / LM).
+    decoder_row(b, prefix list) -> (V,) fp32 log_softmax of the LEFT decoder after `prefix` on utterance b's valid
+    encoder frames (forward_one_step_with_attn, decoder.py:236-281) is the caller's; the search — CTC prefix scores
+    (p_nb, p_b) per hypothesis, the pre-beam candidate set of each frame, re-entry of pruned hypotheses, start / end
+    times, (ctc, attention) confidences, the joint score with length bonus and the score-keyed prune — is restated on
+    the FULL log-prob rows, python floats like the reference."""
+    inf = float("inf")
+    pre_beam = int(pre_beam_ratio * beam_size)
+    dec_w = 1.0 - ctc_weight
+    results = []
+    for bi in range(ctc_probs.shape[0]):
+        lpz = ctc_probs[bi, :int(enc_lens[bi])]
+        first = (sos,)
+        att = {first: (decoder_row(bi, [sos]), 0.0)}
+        hyps = [first]
+        scores = {}
+        times = {first: ([0], [0])}
+        confs = {first: [(-inf, -inf)]}
+        dp = {first: (-inf, 0.0)}
+        for t in range(lpz.shape[0]):
+            p = lpz[t]
+            best_cand = int(torch.argmax(p[0]))                 # :284 — argmax of a 0-d tensor: always 0
+            if best_cand == blank and float(p[best_cand]) >= math.log(1.0):
+                continue
+            thr = torch.sort(p)[0][-pre_beam]
+            cands = [z[0] for z in (p >= thr).nonzero().tolist()]
+            new_hyps, nxt = [], {}
+            for h in hyps:
+                prev = _log_add_list(list(dp[h]))
+                for c in cands:
+                    pc = float(p[c])
+                    if c == blank:
+                        nb, b = nxt.get(h, (-inf, -inf))
+                        nxt[h] = (nb, _log_add_list([b, pc + prev]))
+                        if h not in new_hyps:
+                            new_hyps.append(h)
+                        continue
+                    lp_ = h + (int(c),)
+                    nb, b = nxt.get(lp_, (-inf, -inf))
+                    if lp_ not in times:
+                        times[lp_] = (times[h][0] + [t], times[h][1] + [t + 1])
+                    else:
+                        times[lp_][1][-1] = t + 1
+                    if lp_ not in confs:
+                        confs[lp_] = confs[h] + [(-inf, -inf)]
+                    confs[lp_][-1] = (max([float(confs[lp_][-1][0]), pc]), confs[lp_][-1][1])
+                    if c == h[-1]:
+                        nb_prev, b_prev = dp[h]
+                        nb = _log_add_list([nb, pc + b_prev])
+                        nb_l, b_l = nxt.get(h, (-inf, -inf))
+                        nxt[h] = (_log_add_list([nb_l, pc + nb_prev]), b_l)
+                        times[h][1][-1] = t + 1
+                        confs[h][-1] = (max([float(confs[h][-1][0]), pc]), confs[h][-1][1])
+                    else:
+                        nb = _log_add_list([nb, pc + prev])
+                    if lp_ not in hyps and lp_ in dp:
+                        b = _log_add_list([b, float(p[blank]) + _log_add_list(list(dp[lp_]))])
+                        nb = _log_add_list([nb, pc + dp[lp_][0]])
+                    nxt[lp_] = (nb, b)
+                    if lp_ not in new_hyps:
+                        new_hyps.append(lp_)
+            scores = {}
+            for h in new_hyps:
+                sc = ctc_weight * _log_add_list(list(nxt[h]))
+                if len(h) > 1 and dec_w > 0:
+                    root = h[:-1]
+                    if root not in att:
+                        rr = root[:-1]
+                        att[root] = (decoder_row(bi, list(root)), att[rr][1] + float(att[rr][0][root[-1]]))
+                    sc += (att[root][1] + float(att[root][0][h[-1]])) * dec_w
+                    confs[h][-1] = (confs[h][-1][0], float(att[root][0][h[-1]]))
+                sc += length_bonus * (len(h) - 1)
+                scores[h] = sc
+            rev = {}
+            for k, v in scores.items():
+                rev[v] = k
+            keys = sorted(rev.keys())
+            keys.reverse()
+            hyps = [rev[s] for s in keys[:beam_size]]
+            dp = dict(nxt)
+        best = hyps[0]
+        conf = torch.tensor([max(c[0], c[1]) for c in confs[best]])
+        results.append(DecodeResult(list(best[1:]), torch.tensor([scores[best]]).item(), times=list(times[best][0][1:]),
+                                    tokens_confidence=[math.exp(c.item()) for c in conf[1:]]))
+    return results

@@ -15,10 +15,12 @@ import numpy as np
 import torch
 
 from .engine import Engine, check_beam_size
-from .search import (DecodeResult, attention_beam_search, greedy_results, prefix_beam_results, rescoring_pick,
-                     rescoring_pick_batch)
+from .search import (DecodeResult, attention_beam_search, greedy_results, joint_decoding_results, prefix_beam_results,
+                     rescoring_pick, rescoring_pick_batch, time_sync_joint_search)
 
-SUPPORTED_METHODS = ("attention", "ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring")
+SUPPORTED_METHODS = ("attention", "ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring", "joint_decoding")
+JOINT_DECODING_SOS = 10000        # hard-coded in the reference (transformer/search.py:480)
+JOINT_PRE_BEAM_RATIO = 1.5        # joint_decoding's default (search.py:457)
 
 
 class ASRModel:
@@ -100,7 +102,17 @@ class ASRModel:
                                                           num_decoding_left_chunks)
         need_beam = "ctc_prefix_beam_search" in methods or "attention_rescoring" in methods
         k = beam_size if need_beam else 1
-        topk_val, topk_idx, _ = self.engine.ctc_topk(encoder_out, k, blank_penalty, blank_id)
+        joint = "joint_decoding" in methods
+        if joint:
+            # BeamSearchTimeSync looks at the int(1.5 * beam) best tokens of every frame (+ the blank's log-prob)
+            pre_beam = int(JOINT_PRE_BEAM_RATIO * beam_size)
+            if not 1 <= pre_beam <= 16:
+                raise ValueError(f"reverb_b200: joint_decoding needs int(1.5 * beam_size) <= 16 (beam_size={beam_size})")
+            if JOINT_DECODING_SOS >= self.vocab_size:
+                # the reference indexes the embedding with sos = 10000 (IndexError there)
+                raise IndexError(f"joint_decoding hard-codes sos={JOINT_DECODING_SOS}; vocabulary has {self.vocab_size} entries")
+            k = max(k, pre_beam)
+        topk_val, topk_idx, logp_full = self.engine.ctc_topk(encoder_out, k, blank_penalty, blank_id, want_logp=joint)
         st = {"methods": list(methods), "results": {}, "ticket": None, "cat_embs": cat_embs, "ctc_weight": ctc_weight,
               "reverse_weight": reverse_weight, "stage": 1}
         results = st["results"]
@@ -113,10 +125,35 @@ class ASRModel:
                                                          self.sos, self.eos, length_penalty)
         if "ctc_greedy_search" in methods:
             results["ctc_greedy_search"] = greedy_results(self.engine.greedy_search(topk_idx, encoder_lens, blank_id))
+        if joint:
+            results["joint_decoding"] = self._joint_decoding(encoder_out, encoder_lens, topk_val, topk_idx, logp_full,
+                                                             pre_beam, beam_size, ctc_weight, length_penalty, cat_embs)
+            if need_beam and k != beam_size:                  # the searches below expect exactly beam_size candidates
+                topk_val, topk_idx = topk_val[:, :, :beam_size].contiguous(), topk_idx[:, :, :beam_size].contiguous()
         if need_beam:
             # the n-best stays on the device between the search and the decoder (native ticket, include/rvb_b200.h)
             st["ticket"] = self.engine.search_submit(topk_val, topk_idx, encoder_out, encoder_lens, beam_size, blank_id)
         return st
+
+    def _joint_decoding(self, encoder_out, encoder_lens, topk_val, topk_idx, logp_full, pre_beam, beam_size,
+                        ctc_weight, length_bonus, cat_embs) -> List[DecodeResult]:
+        """transformer/search.py:450-496: per utterance, BeamSearchTimeSync over its valid frames with the LEFT decoder;
+        decoder weight 1 - ctc_weight, `length_penalty` acts as the length bonus (asr_model.py:426-429)."""
+        val = topk_val[:, :, :pre_beam].cpu().numpy()
+        idx = topk_idx[:, :, :pre_beam].cpu().numpy()
+        blank_lp = logp_full[:, :, 0].cpu().numpy()           # BeamSearchTimeSync's blank index is 0 (its default)
+        per_utt = []
+        for b in range(encoder_out.shape[0]):
+            n = int(encoder_lens[b])
+            mem = encoder_out[b:b + 1]
+            mem_len = encoder_lens[b:b + 1]
+
+            def rows(prefixes, mem=mem, mem_len=mem_len):
+                hy = np.asarray(prefixes, dtype=np.int32)
+                return self.engine.decoder_step_logp(mem, mem_len, hy, hy.shape[0], cat_embs)
+            per_utt.append(time_sync_joint_search(val[b, :n], idx[b, :n], blank_lp[b, :n], rows, beam_size, ctc_weight,
+                                                  length_bonus, JOINT_DECODING_SOS))
+        return joint_decoding_results(per_utt)
 
     def _stage_b(self, st: dict) -> None:
         if st["stage"] != 1:

@@ -778,7 +778,8 @@ static int ctc_topk(rvb_model* m, const float* d_enc_out, int B, int Tp, int k, 
 // layer; log_softmax + top-step_k of it -> d_step_val / d_step_idx (S, step_k).
 static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int* d_enc_lens, int B, int Tp, int N,
                         int Lp, const int* d_tokens, const int* d_seq_lens, const int* d_gather, float* d_scores,
-                        cudaStream_t stream, int step_k = 0, float* d_step_val = nullptr, int* d_step_idx = nullptr) {
+                        cudaStream_t stream, int step_k = 0, float* d_step_val = nullptr, int* d_step_idx = nullptr,
+                        float* d_step_logp = nullptr /* (S, V): full log_softmax rows of the last position */) {
   const rvb_model_config& c = m->cfg;
   const int d = c.d_model, H = c.dec_heads, dk = d / H, V = c.vocab;
   const int S = B * N;
@@ -954,7 +955,7 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
     g.ldo = ldv;
     g.alpha = 1.f;
     if (launch_gemm(g, stream)) return -1;
-    return launch_logsoftmax_topk(logits, ldv, S, V, step_k, d_step_val, d_step_idx, nullptr, 1, stream);
+    return launch_logsoftmax_topk(logits, ldv, S, V, step_k, d_step_val, d_step_idx, d_step_logp, 1, stream);
   }
   if (get_gemm_impl() != 1 && V > 128) {
     // log_softmax + gather fused into the output-layer GEMM: the (R, V) fp32 logits (4.2 GB at B = 64) are never
@@ -989,7 +990,7 @@ static int decoder_pass(rvb_model* m, Decoder& D, const bf16* enc_bf, const int*
 // output cache is an optimisation of the same computation, here the prefix is simply recomputed.
 static int decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
                              const int* h_hyps, int L, const float* h_cat, int n_cat, int k, float* h_val, int* h_idx,
-                             cudaStream_t stream) {
+                             cudaStream_t stream, float* h_logp = nullptr /* (S, V) full rows, optional */) {
   const rvb_model_config& c = m->cfg;
   RVB_REQUIRE(m->finalized && m->dec_l.present, "decoder_step_topk: model has no decoder");
   RVB_REQUIRE(L >= 1 && k >= 1 && k <= 16 && k <= c.vocab, "decoder_step_topk: bad L=%d / k=%d", L, k);
@@ -998,8 +999,10 @@ static int decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_
   if (fold_lang(m, h_cat, n_cat, stream)) return -1;
   const size_t ints = (size_t)R + S + B;
   const size_t out_bytes = (size_t)S * k * (sizeof(float) + sizeof(int));
+  const size_t row_bytes = h_logp ? (size_t)S * c.vocab * sizeof(float) : 0;
   if (m->pin_b.ensure(ints * sizeof(int)) || m->ws_misc.ensure(ints * sizeof(int) + out_bytes) ||
-      m->pin_c.ensure(out_bytes) || m->ws_encbf.ensure((size_t)Mem * d * 2 * m->pm()))
+      m->pin_c.ensure(out_bytes + row_bytes) || m->ws_encbf.ensure((size_t)Mem * d * 2 * m->pm()) ||
+      (h_logp && m->ws_dec[8].ensure(row_bytes)))
     return -1;
   int* hp = m->pin_b.as<int>();
   for (long long r = 0; r < R; ++r) {
@@ -1015,12 +1018,18 @@ static int decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_
   bf16* encbf = m->ws_encbf.as<bf16>();
   if (m->x3 ? launch_f32_to_pair(d_enc_out, encbf, Mem, d, stream) : launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream))
     return -1;
-  if (decoder_pass(m, m->dec_l, encbf, dp + R + S, B, Tp, N, L, dp, dp + R, nullptr, nullptr, stream, k, d_val, d_idx))
+  float* d_rows = h_logp ? m->ws_dec[8].as<float>() : nullptr;
+  if (decoder_pass(m, m->dec_l, encbf, dp + R + S, B, Tp, N, L, dp, dp + R, nullptr, nullptr, stream, k, d_val, d_idx,
+                   d_rows))
     return -1;
   RVB_CHECK_CUDA(cudaMemcpyAsync(m->pin_c.p, d_val, out_bytes, cudaMemcpyDeviceToHost, stream));
+  if (h_logp)
+    RVB_CHECK_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(m->pin_c.p) + out_bytes, d_rows, row_bytes,
+                                   cudaMemcpyDeviceToHost, stream));
   RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
   memcpy(h_val, m->pin_c.p, (size_t)S * k * sizeof(float));
   memcpy(h_idx, reinterpret_cast<char*>(m->pin_c.p) + (size_t)S * k * sizeof(float), (size_t)S * k * sizeof(int));
+  if (h_logp) memcpy(h_logp, reinterpret_cast<char*>(m->pin_c.p) + out_bytes, row_bytes);
   return 0;
 }
 
@@ -1589,6 +1598,17 @@ RVB_API int rvb_decoder_step_topk(rvb_model* m, const float* d_enc_out, const in
               "rvb_decoder_step_topk: bad arguments");
   return rvb::decoder_step_topk(m, d_enc_out, h_enc_lens, B, Tp, N, h_hyps, L, h_cat_embs, n_cat, k, h_topk_val,
                                 h_topk_idx, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_decoder_step_logp(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
+                                  const int* h_hyps, int L, const float* h_cat_embs, int n_cat, float* h_logp,
+                                  void* stream) {
+  RVB_REQUIRE(m && d_enc_out && h_enc_lens && h_hyps && h_logp && B > 0 && Tp > 0 && N > 0,
+              "rvb_decoder_step_logp: bad arguments");
+  std::vector<float> val((size_t)B * N);
+  std::vector<int> idx((size_t)B * N);
+  return rvb::decoder_step_topk(m, d_enc_out, h_enc_lens, B, Tp, N, h_hyps, L, h_cat_embs, n_cat, 1, val.data(), idx.data(),
+                                (cudaStream_t)stream, h_logp);
 }
 
 RVB_API int rvb_attention_rescoring(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp,

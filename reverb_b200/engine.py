@@ -382,6 +382,22 @@ class Engine:
                                                  self._stream()), "rvb_decoder_step_topk")
         return val, idx
 
+    def decoder_step_logp(self, enc_out: torch.Tensor, enc_lens, hyps: np.ndarray, n_per_utt: int, cat_embs=None):
+        """hyps (B*N, L) running hypotheses (sos first) -> the full log_softmax rows of the left decoder at the last
+        position, (B*N, vocab) float32 (decoder.forward_one_step_with_attn of the reference, for joint_decoding)."""
+        B, Tp, _ = enc_out.shape
+        hyps = np.ascontiguousarray(hyps, dtype=np.int32)
+        S, L = hyps.shape
+        assert S == B * n_per_utt
+        lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
+        out = np.empty((S, self.vocab), dtype=np.float32)
+        cat, ncat = self._cat(cat_embs)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_decoder_step_logp(self._h, _ptr(enc_out.contiguous()), _np_ptr(lens), B, Tp, n_per_utt,
+                                                 _np_ptr(hyps), L, _np_ptr(cat), ncat, _np_ptr(out), self._stream()),
+                  "rvb_decoder_step_logp")
+        return out
+
     def rescoring_scores_raw(self, enc_out: torch.Tensor, enc_lens, toks: np.ndarray, hlen: np.ndarray, cat_embs=None,
                              reverse_weight: float = 0.0):
         """toks (B, N, L) int32 padded hypotheses, hlen (B, N) their lengths (-1 = absent).

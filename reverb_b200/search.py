@@ -158,3 +158,141 @@ def attention_beam_search(step_topk, batch_size: int, maxlen: int, beam_size: in
         hyp = hyps[b * N + int(best[b]), 1:]
         out.append(DecodeResult(hyp[hyp != eos].tolist()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# joint_decoding: time-synchronous one-pass CTC / attention beam search
+_NEG_INF = float("-inf")
+
+
+def _lse(values) -> float:
+    """Stable log-sum-exp over python floats, -inf when all are -inf (espnet/beam_search_timesync.py:29-37)."""
+    top = max(values)
+    if top == _NEG_INF:
+        return _NEG_INF
+    return top + math.log(sum(math.exp(v - top) for v in values))
+
+
+def time_sync_joint_search(cand_val: np.ndarray, cand_idx: np.ndarray, blank_logp: np.ndarray, decoder_rows,
+                           beam_size: int, ctc_weight: float, length_bonus: float, sos: int, blank: int = 0,
+                           blank_threshold: float = 1.0):
+    """One utterance of the reference's `joint_decoding` (transformer/search.py:450-496): the time-synchronous joint
+    CTC / attention beam search `BeamSearchTimeSync.__call__` (espnet/beam_search_timesync.py:433-508, time_step
+    :262-431, joint_score :221-260, cached_score :171-219), host bookkeeping in double precision like the reference's
+    Python floats.  Hypotheses are tuples starting with `sos`.
+
+    cand_val / cand_idx (T, P): the P = int(pre_beam_ratio * beam) best CTC log-probs of every frame and their token
+        ids (the reference thresholds the frame at its P-th largest value and keeps `p >= threshold`, :288-290 — the
+        same set unless the P-th value is tied);  blank_logp (T,): log p(blank) per frame.
+    decoder_rows(list of prefixes, all of one length) -> (n, V) float32: log_softmax of the left decoder at the last
+        position of each prefix (decoder.forward_one_step_with_attn; the engine recomputes the prefix, the reference
+        carries a per-layer cache — same values).
+    Returns (hyps, scores, start_times, end_times, confs) of the final beam, best first; confs = per token
+    max(ctc log-prob, attention log-prob) (`confs_type = "max"`, :498-500).
+    """
+    dec_w = 1.0 - ctc_weight
+    root0 = (sos,)
+    cache = {root0: (decoder_rows([root0])[0], 0.0)}         # prefix -> (log_softmax row after it, log p_att(prefix))
+    hyps = [root0]
+    scores = {}
+    times = {root0: ([0], [0])}
+    confs = {root0: [(_NEG_INF, _NEG_INF)]}
+    dp = {root0: (_NEG_INF, 0.0)}                             # (log p_nonblank, log p_blank)
+    log_thr = math.log(blank_threshold)
+
+    def ensure_cached(roots):
+        missing = []
+        for r in roots:
+            if r not in cache and r not in missing:
+                missing.append(r)
+        by_len = {}
+        for r in missing:
+            by_len.setdefault(len(r), []).append(r)
+        for _, group in sorted(by_len.items()):
+            rows = decoder_rows(group)
+            for r, row in zip(group, rows):
+                parent_row, parent_sum = cache[r[:-1]]
+                cache[r] = (row, parent_sum + float(parent_row[r[-1]]))
+
+    for t in range(cand_val.shape[0]):
+        # :284-286 — `argmax(p_ctc[0])` of a 0-d value is 0, so the frame is skipped only when token 0 is the blank and
+        # its log-prob reaches log(blank_threshold) (= 0, i.e. never in practice)
+        if blank == 0 and float(blank_logp[t]) >= log_thr:
+            continue
+        order = np.argsort(cand_idx[t], kind="stable")         # `.nonzero()` lists the candidates by ascending id
+        cands = [(int(cand_idx[t, i]), float(cand_val[t, i])) for i in order]
+        p_blank = float(blank_logp[t])
+        in_beam = set(hyps)
+        new_hyps, seen_new, nxt = [], set(), {}
+
+        def push(h):
+            if h not in seen_new:
+                seen_new.add(h)
+                new_hyps.append(h)
+
+        for hyp in hyps:
+            p_prev = _lse(dp[hyp])
+            for c, lp in cands:
+                if c == blank:
+                    nb, b = nxt.get(hyp, (_NEG_INF, _NEG_INF))
+                    nxt[hyp] = (nb, _lse([b, lp + p_prev]))
+                    push(hyp)
+                    continue
+                ext = hyp + (c,)
+                nb, b = nxt.get(ext, (_NEG_INF, _NEG_INF))
+                if ext not in times:                           # first sighting: start and end frame
+                    times[ext] = (times[hyp][0] + [t], times[hyp][1] + [t + 1])
+                else:
+                    times[ext][1][-1] = t + 1
+                if ext not in confs:
+                    confs[ext] = confs[hyp] + [(_NEG_INF, _NEG_INF)]
+                confs[ext][-1] = (max(confs[ext][-1][0], lp), confs[ext][-1][1])
+                if c == hyp[-1]:
+                    # repeated token: the extension needs a blank in between; the hypothesis itself absorbs the repeat
+                    nb_prev, b_prev = dp[hyp]
+                    nb = _lse([nb, lp + b_prev])
+                    nb_h, b_h = nxt.get(hyp, (_NEG_INF, _NEG_INF))
+                    nxt[hyp] = (_lse([nb_h, lp + nb_prev]), b_h)
+                    times[hyp][1][-1] = t + 1
+                    confs[hyp][-1] = (max(confs[hyp][-1][0], lp), confs[hyp][-1][1])
+                else:
+                    nb = _lse([nb, lp + p_prev])
+                if ext not in in_beam and ext in dp:
+                    # proposed in the previous frame but pruned from the beam: fold its mass back in
+                    b = _lse([b, p_blank + _lse(dp[ext])])
+                    nb = _lse([nb, lp + dp[ext][0]])
+                nxt[ext] = (nb, b)
+                push(ext)
+
+        # joint score of every proposal (no lexicon constraint: `words` is empty in joint_decoding)
+        if dec_w > 0:
+            ensure_cached([h[:-1] for h in new_hyps if len(h) > 1])
+        scores = {}
+        for h in new_hyps:
+            sc = ctc_weight * _lse(nxt[h])
+            if len(h) > 1 and dec_w > 0:
+                row, log_sum = cache[h[:-1]]
+                att = float(row[h[-1]])
+                sc += (log_sum + att) * dec_w
+                confs[h][-1] = (confs[h][-1][0], att)
+            sc += length_bonus * (len(h) - 1)
+            scores[h] = sc
+        # the reference sorts through a {score: hypothesis} dict: equal scores collapse onto the LAST such hypothesis
+        by_score = {}
+        for h, sc in scores.items():
+            by_score[sc] = h
+        hyps = [by_score[sc] for sc in sorted(by_score, reverse=True)[:beam_size]]
+        dp = dict(nxt)
+
+    out_conf = [[max(c0, c1) for c0, c1 in confs[h]] for h in hyps]
+    return hyps, [scores[h] for h in hyps], [times[h][0] for h in hyps], [times[h][1] for h in hyps], out_conf
+
+
+def joint_decoding_results(per_utt) -> List[DecodeResult]:
+    """search.py:484-494: the best hypothesis of every utterance without its <sos>; times = start frames."""
+    out = []
+    for hyps, scores, starts, _ends, confs in per_utt:
+        # the reference passes score / confidences through float32 tensors before `.item()` (search.py:489-493)
+        out.append(DecodeResult(list(hyps[0][1:]), float(np.float32(scores[0])), times=list(starts[0][1:]),
+                                tokens_confidence=[math.exp(float(np.float32(c))) for c in confs[0][1:]]))
+    return out

@@ -280,8 +280,8 @@ def test_transcribe_api_surface(asr, golden_cases, model_dirs, case):
         m.transcribe(wav, format="json")
     with pytest.raises((AssertionError, TypeError)):
         m.transcribe(wav, mode="ctc_greedy_search")          # reference quirk 1: greedy has no times
-    with pytest.raises(NotImplementedError):
-        m.transcribe(wav, mode="joint_decoding")
+    with pytest.raises(IndexError):
+        m.transcribe(wav, mode="joint_decoding")              # reference quirk 3: sos=10000 is hard-coded, V = 101 here
 
 
 @pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])

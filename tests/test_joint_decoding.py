@@ -1,0 +1,102 @@
+"""`joint_decoding` (time-synchronous joint CTC / attention beam search; reference: asr/wenet/transformer/search.py:450-496
++ espnet/beam_search_timesync.py).  tests/golden/joint.json holds the LIVE reference's outputs on a V = 10001 synthetic
+model (oracle/make_golden_joint.py, which also asserted that the oracle restatement reproduces them).
+
+CPU: the oracle restatement and the product's host search (reverb_b200/search.time_sync_joint_search, driven by the
+oracle's decoder rows) both reproduce the golden tokens / times / scores / confidences.
+GPU: ASRModel.decode(['joint_decoding']) through the native decoder step, fp32-accurate mode = golden tokens exactly.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "joint.json")))
+
+
+@pytest.fixture(scope="module")
+def joint_dirs(tmp_path_factory):
+    from reverb_b200 import synth
+    out = {}
+    for name, rec in GOLD["cases"].items():
+        d = str(tmp_path_factory.mktemp("joint_" + name))
+        synth.write_model_dir(d, shape=GOLD["shape"], causal=rec["causal"], cnn_module_norm=rec["cnn_module_norm"],
+                              seed=rec["model_seed"], blank_rate=rec["blank_rate"])
+        wav = synth.write_wav(os.path.join(d, "joint.wav"), synth.synth_audio(GOLD["audio_seconds"], seed=GOLD["audio_seed"]))
+        out[name] = (d, wav)
+    return out
+
+
+def _check(res, gold, tol_score=1e-4, tol_conf=1e-5, exact=True):
+    n_ok = 0
+    for r, g in zip(res, gold):
+        same = list(r.tokens) == g["tokens"] and list(r.times) == g["times"]
+        n_ok += int(same)
+        if exact:
+            assert same, (list(r.tokens), g["tokens"])
+        if same:
+            assert abs(r.score - g["score"]) <= tol_score * max(1.0, abs(g["score"]))
+            if g["tokens"]:
+                assert max(abs(a - b) for a, b in zip(r.tokens_confidence, g["tokens_confidence"])) <= tol_conf
+    return n_ok
+
+
+@pytest.mark.parametrize("case", list(GOLD["cases"]))
+def test_host_search_and_oracle_reproduce_the_live_reference(joint_dirs, case):
+    from oracle import model_ref, pipeline_ref, search_ref
+    from reverb_b200.search import joint_decoding_results, time_sync_joint_search
+    d, wav = joint_dirs[case]
+    orc = pipeline_ref.OracleASR(d)
+    feats = orc.compute_feats(wav)
+    cat = torch.tensor([1.0, 0.0])
+    batches = list(orc.feats_batcher(feats, GOLD["chunk_size"], GOLD["batch_size"]))
+    for si, st in enumerate(GOLD["settings"]):
+        for bi, (fb, fl) in enumerate(batches):
+            enc, enc_lens, _ = orc.forward_encoder(fb, fl, cat)
+            ctc = model_ref.ctc_logprobs(enc, orc.sd)
+            gold = GOLD["cases"][case]["runs"][si][bi]
+
+            def row(b, prefix):
+                mem = enc[b:b + 1, :int(enc_lens[b])]
+                with torch.no_grad():
+                    return model_ref.decoder_step_logp(mem, enc_lens[b:b + 1], torch.tensor([prefix]), orc.sd, orc.cfg, cat)[0]
+            want = search_ref.joint_decoding(row, ctc, enc_lens, st["ctc_weight"], st["beam_size"], 1.5, st["length_penalty"])
+            _check(want, gold)
+            # the product's host search on top-k arrays, decoder rows from the oracle
+            P = int(1.5 * st["beam_size"])
+            per_utt = []
+            for b in range(fb.shape[0]):
+                n = int(enc_lens[b])
+                val, idx = ctc[b, :n].topk(P, dim=-1)
+                rows = lambda prefixes, b=b: np.stack([row(b, list(p)).numpy() for p in prefixes])
+                per_utt.append(time_sync_joint_search(val.numpy(), idx.numpy(), ctc[b, :n, 0].numpy(), rows, st["beam_size"],
+                                                      st["ctc_weight"], st["length_penalty"], 10000))
+            _check(joint_decoding_results(per_utt), gold)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(GOLD["cases"]))
+def test_joint_decoding_on_the_gpu_equals_the_live_reference(joint_dirs, case):
+    import reverb_b200
+    d, wav = joint_dirs[case]
+    cat = torch.tensor([1.0, 0.0])
+    for precision, exact in (("fp32", True), ("bf16", False)):
+        m = reverb_b200.load_model(d, precision=precision)
+        feats = m.compute_feats(wav, num_mel_bins=80, frame_length=25, frame_shift=10)
+        total = ok = 0
+        for si, st in enumerate(GOLD["settings"]):
+            for bi, (fb, fl) in enumerate(m.feats_batcher(feats, GOLD["chunk_size"], GOLD["batch_size"])):
+                res = m.model.decode(["joint_decoding"], fb, fl, st["beam_size"], ctc_weight=st["ctc_weight"],
+                                     length_penalty=st["length_penalty"], cat_embs=cat, blank_id=0)["joint_decoding"]
+                gold = GOLD["cases"][case]["runs"][si][bi]
+                # GPU fbank differs from torchaudio's by ~1e-4, scores by the decoder's rounding: 2e-3 relative
+                ok += _check(res, gold, tol_score=2e-3, tol_conf=5e-3 if exact else 5e-2, exact=exact)
+                total += len(gold)
+        print(f"[joint_decoding {case} {precision}] hypotheses identical to the live reference: {ok}/{total}")
+        assert ok >= (total if exact else total - 2)
+    # CTM through the public API: joint_decoding has times and confidences, so transcribe() works (unlike greedy)
+    out = m.transcribe(wav, mode="joint_decoding", format="ctm", chunk_size=GOLD["chunk_size"], batch_size=2,
+                       beam_size=4, ctc_weight=0.9, length_penalty=1.5)
+    assert len(out.split("\n")) >= 5
