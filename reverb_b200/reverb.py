@@ -5,7 +5,9 @@ behaviour), running on the native B200 engine.
 Differences that are deliberate and documented in DESIGN.md:
   * the model always runs on a CUDA device (`gpu < 0` selects the current device; there
     is no CPU path), whereas the reference's `load_model()` is CPU-only (reverb.py:354-357);
-  * audio is read with the standard-library `wave` module (16-bit PCM); a file that is not
+  * RIFF/WAVE audio (PCM 8/16/24/32 bit, float, extensible, multi-channel) is parsed by
+    reverb_b200/audio_io.py with torchaudio.load(normalize=False) value conventions, other
+    containers go through torchaudio when it has a decoder backend; a file that is not
     16 kHz is resampled on the GPU with torchaudio.transforms.Resample's algorithm
     (csrc/resample.cu + resample.py), where the reference calls torchaudio on the CPU.
 """
@@ -13,7 +15,6 @@ from __future__ import annotations
 
 import logging
 import shutil
-import wave
 from functools import partial
 from itertools import chain
 from math import ceil
@@ -37,13 +38,9 @@ _MODELS = {"reverb_asr_v1": "https://huggingface.co/Revai/reverb-asr"}
 
 
 def _read_wav(path: str) -> Tuple[np.ndarray, int]:
-    """int16 samples (channels, n) + sample rate — the `torchaudio.load(normalize=False)` contract."""
-    with wave.open(str(path), "rb") as w:
-        if w.getsampwidth() != 2:
-            raise ValueError(f"{path}: only 16-bit PCM WAV is supported")
-        sr, nch = w.getframerate(), w.getnchannels()
-        pcm = np.frombuffer(w.readframes(w.getnframes()), dtype=np.int16)
-    return np.ascontiguousarray(pcm.reshape(-1, nch).T), sr
+    """samples (channels, n) + sample rate — the `torchaudio.load(normalize=False)` contract (audio_io.py)."""
+    from .audio_io import load_audio
+    return load_audio(path)
 
 
 def _load_state_dict(checkpoint: str) -> Dict[str, torch.Tensor]:
@@ -131,7 +128,12 @@ class ReverbASR:
             raise NotImplementedError("reverb_b200 fbank kernel is built for 80 bins / 25 ms / 10 ms / no dither @16 kHz")
         pcm, sample_rate = _read_wav(audio_file)
         logging.info(f"detected sample rate: {sample_rate}")
-        wave_dev = torch.from_numpy(np.array(pcm[0], copy=True)).pin_memory().to(self.device, non_blocking=True)
+        ch0 = np.array(pcm[0], copy=True)                      # channel 0 (kaldi.fbank channel=-1 -> 0)
+        if ch0.dtype != np.int16:
+            # `waveform.to(torch.float)` of the reference (cli/reverb.py:124): the sample VALUES as they are (uint8 /
+            # int32 / float32) — the kernels take int16 or float32 input
+            ch0 = ch0.astype(np.float32)
+        wave_dev = torch.from_numpy(ch0).pin_memory().to(self.device, non_blocking=True)
         if sample_rate != resample_rate:
             # torchaudio.transforms.Resample on channel 0 (the reference resamples every channel, then keeps the first)
             wave_dev = self.engine.resample(wave_dev, sample_rate, resample_rate)
