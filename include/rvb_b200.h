@@ -113,6 +113,13 @@ RVB_API int rvb_encoder_forward_chunked(rvb_model* m, const float* d_feats, cons
                                         const float* h_cat_embs, int n_cat, int chunk_size, int num_left_chunks,
                                         float* d_enc_out, int* h_enc_lens, void* stream);
 
+/* The cache-based streaming simulation — BaseEncoder.forward_chunk_by_chunk (encoder.py:341-402; `simulate_streaming`) —
+ * evaluated in one batched pass: identical results to feeding the chunks one by one with attention / convolution
+ * caches (every frame of d_feats (B, T, input_dim) is taken as real: that path has no padding masks). */
+RVB_API int rvb_encoder_forward_streaming(rvb_model* m, const float* d_feats, int B, int T, const float* h_cat_embs,
+                                          int n_cat, int chunk_size, int num_left_chunks, float* d_enc_out,
+                                          int* h_enc_lens, void* stream);
+
 /* CTC head: logits = ctc_lo(enc_out) (blank_penalty subtracted from the blank column), log_softmax, top-k.
  * d_topk_val/d_topk_idx: (B*Tp, k) sorted descending; d_logp (B*Tp, vocab) optional (NULL to skip the write). */
 RVB_API int rvb_ctc_topk(rvb_model* m, const float* d_enc_out, int B, int Tp, int k, float blank_penalty, int blank_id,

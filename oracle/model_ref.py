@@ -229,6 +229,86 @@ def encoder_forward(feats, lens, sd: SD, cfg, cat_embs: Optional[torch.Tensor], 
     return x, masks.squeeze(1).sum(1), masks
 
 
+def encoder_forward_chunk_by_chunk(feats, sd: SD, cfg, cat_embs: Optional[torch.Tensor], decoding_chunk_size: int,
+                                   num_decoding_left_chunks: int = -1):
+    """BaseEncoder.forward_chunk_by_chunk (transformer/encoder.py:341-402) with forward_chunk (:231-339) — the
+    CACHE-based streaming simulation, restated literally: overlapping feature windows through the subsampling, per layer
+    an attention cache of the last `chunk * left` keys / values (attention.py:356-366) and, for causal models, a
+    convolution cache of the last K - 1 conv-module inputs (convolution.py:113-123); no masks at all (att_mask and
+    mask_pad are the (0, 0, 0) fakes).  feats (1, T, 80) -> (1, T', d).
+    (ASRModel._forward_encoder forgets to pass cat_embs on this path, asr_model.py:299-303, so `decode(...,
+    simulate_streaming=True)` asserts on models with language-specific layers; the encoder method itself takes it.)"""
+    assert feats.shape[0] == 1 and decoding_chunk_size > 0
+    ec = cfg["encoder_conf"]
+    H, K, L, d = ec["attention_heads"], ec["cnn_module_kernel"], ec["num_blocks"], ec["output_size"]
+    causal = ec.get("causal", False)
+    layer_norm = ec.get("cnn_module_norm", "batch_norm") == "layer_norm"
+    has_lsl = bool(cfg["dataset_conf"].get("pass_cat_emb", False))
+    dk = d // H
+    lorder = K - 1 if causal else 0
+    context, stride = 7, 4 * decoding_chunk_size
+    window = (decoding_chunk_size - 1) * 4 + context
+    T = feats.shape[1]
+    required = decoding_chunk_size * num_decoding_left_chunks
+    pe = sinusoid_pe(5000, d)
+    att_cache = [None] * L        # per layer (k, v): (1, H, t, dk)
+    cnn_cache = [None] * L        # per layer (1, d, lorder)
+    outs, offset = [], 0
+    for cur in range(0, T - context + 1, stride):
+        xs = feats[:, cur:min(cur + window, T)]
+        x, _, _ = subsample4(xs, torch.tensor([xs.shape[1]]), sd)
+        cache_t1 = 0 if att_cache[0] is None else att_cache[0][0].shape[2]
+        key_size = cache_t1 + x.shape[1]
+        pos_emb = pe[offset - cache_t1:offset - cache_t1 + key_size].unsqueeze(0)     # embedding.py position_encoding
+        start = 0 if required < 0 else (key_size if required == 0 else max(key_size - required, 0))
+        for i in range(L):
+            p = f"encoder.encoders.{i}"
+            lsl = has_lsl and (i == 0 or i == L - 1)
+            x = x + 0.5 * ffn(_ln(x, sd, p + ".norm_ff_macaron", 1e-5), sd, p + ".feed_forward_macaron", F.silu)
+            # rel-pos attention over [cache | chunk], no mask (attention.py:344-399)
+            n = _ln(x, sd, p + ".norm_mha", 1e-5)
+            q = _lin(n, sd, p + ".self_attn.linear_q").view(1, -1, H, dk)
+            k = _lin(n, sd, p + ".self_attn.linear_k").view(1, -1, H, dk).transpose(1, 2)
+            v = _lin(n, sd, p + ".self_attn.linear_v").view(1, -1, H, dk).transpose(1, 2)
+            if att_cache[i] is not None:
+                k = torch.cat([att_cache[i][0], k], dim=2)
+                v = torch.cat([att_cache[i][1], v], dim=2)
+            att_cache[i] = (k[:, :, start:], v[:, :, start:])
+            pp = F.linear(pos_emb, sd[p + ".self_attn.linear_pos.weight"]).view(1, -1, H, dk).transpose(1, 2)
+            qu = (q + sd[p + ".self_attn.pos_bias_u"]).transpose(1, 2)
+            qv = (q + sd[p + ".self_attn.pos_bias_v"]).transpose(1, 2)
+            scores = (torch.matmul(qu, k.transpose(-2, -1)) + torch.matmul(qv, pp.transpose(-2, -1))) / math.sqrt(dk)
+            a = torch.matmul(torch.softmax(scores, dim=-1), v).transpose(1, 2).contiguous().view(1, -1, d)
+            x = x + _lin(a, sd, p + ".self_attn.linear_out")
+            # convolution module with the left-context cache (convolution.py:107-144), no padding mask
+            c = _ln(x, sd, p + ".norm_conv", 1e-5).transpose(1, 2)
+            if lorder > 0:
+                c = F.pad(c, (lorder, 0), "constant", 0.0) if cnn_cache[i] is None else torch.cat((cnn_cache[i], c), dim=2)
+                cnn_cache[i] = c[:, :, -lorder:]
+            q_ = p + ".conv_module"
+            c = F.glu(F.conv1d(c, sd[q_ + ".pointwise_conv1.weight"], sd[q_ + ".pointwise_conv1.bias"]), dim=1)
+            c = F.conv1d(c, sd[q_ + ".depthwise_conv.weight"], sd[q_ + ".depthwise_conv.bias"],
+                         padding=0 if causal else (K - 1) // 2, groups=c.shape[1])
+            if layer_norm:
+                c = F.silu(_ln(c.transpose(1, 2), sd, q_ + ".norm", 1e-5)).transpose(1, 2)
+            else:
+                c = F.silu(F.batch_norm(c, sd[q_ + ".norm.running_mean"], sd[q_ + ".norm.running_var"],
+                                        sd[q_ + ".norm.weight"], sd[q_ + ".norm.bias"], False, 0.0, 1e-5))
+            c = F.conv1d(c, sd[q_ + ".pointwise_conv2.weight"], sd[q_ + ".pointwise_conv2.bias"])
+            x = x + c.transpose(1, 2)
+            n = _ln(x, sd, p + ".norm_ff", 1e-5)
+            if lsl:
+                y = lsl_mix(n, sd, p, cat_embs)
+                x = x + 0.5 * ffn(y, sd, p + ".feed_forward", F.silu)
+                x = _ln(x, sd, p + ".norm_final", 1e-5) + y
+            else:
+                x = x + 0.5 * ffn(n, sd, p + ".feed_forward", F.silu)
+                x = _ln(x, sd, p + ".norm_final", 1e-5)
+        outs.append(_ln(x, sd, "encoder.after_norm", 1e-5))
+        offset += x.shape[1]
+    return torch.cat(outs, dim=1)
+
+
 def ctc_logprobs(enc_out, sd: SD, blank_penalty: float = 0.0, blank_id: int = 0):
     """ASRModel.ctc_logprobs (transformer/asr_model.py:318-329) / CTC.log_softmax (ctc.py:106-114)."""
     logits = _lin(enc_out, sd, "ctc.ctc_lo")

@@ -44,6 +44,7 @@ SIGNATURES = {
     "rvb_fbank_batch": (_i, [_vp, _i, _i, _ll, _ll, _vp, _ll, _vp]),
     "rvb_encoder_forward": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp]),
     "rvb_encoder_forward_chunked": (_i, [_vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "rvb_encoder_forward_streaming": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "rvb_ctc_topk": (_i, [_vp, _vp, _i, _i, _i, _f, _i, _vp, _vp, _vp, _vp]),
     "rvb_logp_topk": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "rvb_ctc_greedy_search": (_i, [_vp, _i, _vp, _i, _i, _i, _vp, _vp, _vp]),

@@ -65,9 +65,19 @@ class ASRModel:
         return -1, -1
 
     def _forward_encoder(self, speech: torch.Tensor, speech_lengths, cat_embs=None, decoding_chunk_size: int = -1,
-                         num_decoding_left_chunks: int = -1):
-        """-> (encoder_out (B, T', d) fp32 cuda, encoder_lens np.int32 (B,))."""
+                         num_decoding_left_chunks: int = -1, simulate_streaming: bool = False):
+        """-> (encoder_out (B, T', d) fp32 cuda, encoder_lens np.int32 (B,)).
+        simulate_streaming with decoding_chunk_size > 0: encoder.forward_chunk_by_chunk (encoder.py:341-402), the
+        cache-based chunk-by-chunk pass, evaluated as ONE masked pass with identical results (engine.cu
+        rvb_encoder_forward_streaming).  Like the reference's it has no padding masks (every input frame counts) and
+        serves one utterance at a time (`assert xs.size(0) == 1`, encoder.py:284).  The reference's decode() does not
+        forward cat_embs on this path (asr_model.py:299-303) and therefore asserts on models with language-specific
+        layers; here cat_embs is passed on, as encoder.forward_chunk_by_chunk itself expects."""
         lens = speech_lengths.detach().cpu().numpy() if torch.is_tensor(speech_lengths) else np.asarray(speech_lengths)
+        if simulate_streaming and decoding_chunk_size > 0:
+            assert speech.shape[0] == 1, "simulate_streaming decodes one utterance at a time (encoder.py:284)"
+            return self.engine.forward_encoder(speech, lens, cat_embs, int(decoding_chunk_size),
+                                               int(num_decoding_left_chunks), streaming=True)
         chunk, left = self.attention_context(decoding_chunk_size, num_decoding_left_chunks)
         return self.engine.forward_encoder(speech, lens, cat_embs, chunk, left)
 
@@ -86,10 +96,6 @@ class ASRModel:
         assert speech.shape[0] == speech_lengths.shape[0]
         assert decoding_chunk_size != 0
         check_beam_size(beam_size)
-        if simulate_streaming and decoding_chunk_size > 0:
-            # encoder.forward_chunk_by_chunk (encoder.py:231-402): chunk-by-chunk with att / cnn caches
-            raise NotImplementedError("reverb_b200: simulate_streaming (cache-based chunk-by-chunk encoding) is not built; "
-                                      "decoding_chunk_size > 0 without it applies the same bounded attention context")
         if context_graph is not None:
             raise NotImplementedError("reverb_b200: context biasing is out of scope (SURVEY.md §2)")
         unknown = [m for m in methods if m not in SUPPORTED_METHODS]
@@ -99,7 +105,7 @@ class ASRModel:
             speech = speech.to(self.engine.device, non_blocking=True)
         speech = speech.to(torch.float32)
         encoder_out, encoder_lens = self._forward_encoder(speech, speech_lengths, cat_embs, decoding_chunk_size,
-                                                          num_decoding_left_chunks)
+                                                          num_decoding_left_chunks, simulate_streaming)
         need_beam = "ctc_prefix_beam_search" in methods or "attention_rescoring" in methods
         k = beam_size if need_beam else 1
         joint = "joint_decoding" in methods

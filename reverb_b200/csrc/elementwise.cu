@@ -333,7 +333,7 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
                const float* __restrict__ dw_b, const float* __restrict__ norm_w, const float* __restrict__ norm_b,
                const float* __restrict__ bn_mean, const float* __restrict__ bn_var, int use_ln, float eps,
                float* __restrict__ conv_out, float* __restrict__ stats, bf16* __restrict__ out, int T, int C,
-               int Krt, int causal) {
+               int Krt, int causal, int conv_chunk) {
   __shared__ float s_part[4][CM_TT][2];
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * CM_TT;
@@ -406,7 +406,10 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
       for (int t = 0; t < CM_TT; ++t) {
         const int tt = t0 + t - left + k;
         float2 v = make_float2(0.f, 0.f);
-        if (tt < 0) v = padv;
+        // conv_chunk > 0 (cache-based streaming simulation of a NON-causal model, encoder.py:341-402): every chunk is
+        // convolved on its own, zero padded at its edges — taps outside the output frame's chunk contribute nothing
+        if (conv_chunk > 0 && (tt < 0 || tt / conv_chunk != (t0 + t) / conv_chunk)) {
+        } else if (tt < 0) v = padv;
         else if (tt < T) {
           v = unpack_bf16x2(__ldg(xb + (long long)tt * CW));
           if (X3) {
@@ -516,7 +519,7 @@ conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restric
 int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, const float* dw_b, const float* norm_w,
                     const float* norm_b, const float* bn_mean, const float* bn_var, int use_ln, float eps,
                     bf16* out, int B, int T, int C, int K, int causal, cudaStream_t stream, float* conv_tmp,
-                    float* stats, int x3) {
+                    float* stats, int x3, int conv_chunk) {
   RVB_REQUIRE(C % 4 == 0 && C <= 4096 && K >= 1 && K <= 64, "conv_mid: unsupported C=%d K=%d", C, K);
   RVB_REQUIRE(!causal || pad_glu != nullptr, "conv_mid: causal mode needs the GLU(pointwise_conv1 bias) pad row");
   RVB_REQUIRE(!use_ln || (conv_tmp != nullptr && stats != nullptr), "conv_mid: LayerNorm needs the fp32 scratch");
@@ -525,9 +528,12 @@ int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, cons
   const int nslice = (int)grid.z;
 #define RVB_DW(KK, XX)                                                                                                 \
   conv_dw_kernel<KK, XX><<<grid, 128, 0, stream>>>(x, pad_glu, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln, eps, \
-                                                   conv_tmp, stats, out, T, C, K, causal)
+                                                   conv_tmp, stats, out, T, C, K, causal, conv_chunk)
+  RVB_REQUIRE(conv_chunk <= 0 || !causal, "conv_mid: chunk-local convolution is the non-causal streaming mode");
   if (x3) {  // accurate mode: the generic tap loop (no register-resident halo) is fast enough
     RVB_DW(0, true);
+  } else if (conv_chunk > 0) {
+    RVB_DW(0, false);
   } else if (K == 15) RVB_DW(15, false);
   else if (K == 31) RVB_DW(31, false);
   else if (K == 7) RVB_DW(7, false);

@@ -526,7 +526,7 @@ static int attn_impl() {
 // query frame i attends keys [max(0, (i/chunk - left) * chunk) (0 when left < 0), (i/chunk + 1) * chunk) & pad mask.
 static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat_lens, int B, int T,
                            const float* h_cat, int n_cat, float* d_enc_out, int* h_enc_lens, cudaStream_t stream,
-                           int att_chunk = 0, int att_left = -1) {
+                           int att_chunk = 0, int att_left = -1, bool streaming = false) {
   const rvb_model_config& c = m->cfg;
   RVB_REQUIRE(m->finalized, "encoder_forward: model not finalized");
   const int d = c.d_model, F = c.input_dim, H = c.heads, dk = d / H, L = c.num_blocks;
@@ -724,7 +724,8 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
     if (gemm(m, n, E.pw1, (int)M, ACT_GLU, OUT_BF16, pw, 1.f, stream)) return -1;   // pw = GLU(pointwise_conv1), (M, d)
     if (launch_conv_mid(pw, E.pad_glu, E.dw_w, E.dw_b, E.cnorm.g, E.cnorm.b, E.bn_mean, E.bn_var, c.cnn_layer_norm, 1e-5f, cm, B,
                         Tp, d, c.cnn_kernel, c.causal, stream, y /*fp32 (M, d) scratch, free until the LSL mix*/,
-                        m->ws_cbias.as<float>() + (size_t)B * H * Tp, x3))
+                        m->ws_cbias.as<float>() + (size_t)B * H * Tp, x3,
+                        (streaming && !c.causal) ? att_chunk : 0))
       return -1;
     if (gemm(m, cm, E.pw2, (int)M, ACT_NONE, OUT_RESID_F32, x, 1.f, stream, d_lens, Tp)) return -1;
     // FFN (+ language-specific mix on the first / last block)                   (encoder_layer.py:233-242, 372-400)
@@ -1435,6 +1436,19 @@ RVB_API int rvb_encoder_forward_chunked(rvb_model* m, const float* d_feats, cons
               "rvb_encoder_forward_chunked: bad arguments");
   return rvb::encoder_forward(m, d_feats, h_feat_lens, B, T, h_cat_embs, n_cat, d_enc_out, h_enc_lens,
                               (cudaStream_t)stream, chunk_size, num_left_chunks);
+}
+
+// BaseEncoder.forward_chunk_by_chunk (encoder.py:341-402) in ONE batched pass: the chunk mask inside the attention
+// kernel reproduces the attention cache (a query sees the `left` previous chunks + its own), causal convolutions see
+// the same left context as through the reference's cnn cache, non-causal ones are evaluated chunk by chunk (zero
+// padded at the chunk edges); there are no padding masks on this path — every frame of the (B, T, .) input is real.
+RVB_API int rvb_encoder_forward_streaming(rvb_model* m, const float* d_feats, int B, int T, const float* h_cat_embs,
+                                          int n_cat, int chunk_size, int num_left_chunks, float* d_enc_out,
+                                          int* h_enc_lens, void* stream) {
+  RVB_REQUIRE(m && d_feats && d_enc_out && B > 0 && chunk_size > 0, "rvb_encoder_forward_streaming: bad arguments");
+  std::vector<int> lens(B, T);
+  return rvb::encoder_forward(m, d_feats, lens.data(), B, T, h_cat_embs, n_cat, d_enc_out, h_enc_lens,
+                              (cudaStream_t)stream, chunk_size, num_left_chunks, true);
 }
 
 RVB_API int rvb_resample(const void* d_wave, int is_i16, long long n_in, const float* d_kernel, int orig, int new_, int width,

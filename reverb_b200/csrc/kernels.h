@@ -106,7 +106,8 @@ int launch_conv1(const float* feats, const float* mean, const float* istd, const
 int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w /*[C][K]*/, const float* dw_b,
                     const float* norm_w, const float* norm_b, const float* bn_mean, const float* bn_var,
                     int use_layer_norm, float eps, bf16* out, int B, int T, int C, int K, int causal,
-                    cudaStream_t stream, float* conv_tmp = nullptr, float* stats = nullptr, int x3 = 0);
+                    cudaStream_t stream, float* conv_tmp = nullptr, float* stats = nullptr, int x3 = 0,
+                    int conv_chunk = 0 /* > 0: non-causal, every chunk of conv_chunk frames convolved on its own */);
 // x[m, :] = x[m, :] * scale   (fp32 -> fp32 in place) and optional bf16 copy
 int launch_scale_cast(const float* x, float scale, float* out_f32, bf16* out_bf16, long long n, cudaStream_t stream);
 int launch_f32_to_bf16(const float* x, bf16* out, long long n, cudaStream_t stream);

@@ -207,7 +207,7 @@ class Engine:
         return feats
 
     def forward_encoder(self, feats: torch.Tensor, feat_lens: Sequence[int], cat_embs=None, chunk_size: int = -1,
-                        num_left_chunks: int = -1):
+                        num_left_chunks: int = -1, streaming: bool = False):
         """(B, T, 80) fp32 cuda -> (encoder_out (B, T', d) fp32 cuda, encoder_lens np.int32 (B,)).
         chunk_size > 0: bounded attention context (decoding_chunk_size / num_decoding_left_chunks of the reference)."""
         assert feats.is_cuda and feats.dtype == torch.float32 and feats.dim() == 3
@@ -220,7 +220,14 @@ class Engine:
         out = torch.empty((B, Tp, self.d_model), dtype=torch.float32, device=feats.device)
         cat, ncat = self._cat(cat_embs)
         with torch.cuda.device(self.device):
-            if chunk_size > 0:
+            if streaming:
+                # forward_chunk_by_chunk semantics (simulate_streaming): no padding masks, chunk-local context
+                assert chunk_size > 0
+                check(self.lib.rvb_encoder_forward_streaming(self._h, _ptr(feats), B, T, _np_ptr(cat), ncat,
+                                                             int(chunk_size), int(num_left_chunks), _ptr(out),
+                                                             _np_ptr(enc_lens), self._stream()),
+                      "rvb_encoder_forward_streaming")
+            elif chunk_size > 0:
                 check(self.lib.rvb_encoder_forward_chunked(self._h, _ptr(feats), _np_ptr(lens), B, T, _np_ptr(cat), ncat,
                                                            int(chunk_size), int(num_left_chunks), _ptr(out),
                                                            _np_ptr(enc_lens), self._stream()),

@@ -309,8 +309,33 @@ def test_bounded_context_encoder_vs_reference_fixture(asr, golden_cases, case):
             res = m.model.decode(["ctc_greedy_search"], fb, fl, 10, decoding_chunk_size=cs,
                                  num_decoding_left_chunks=left, cat_embs=cat, blank_id=0)
             assert len(res["ctc_greedy_search"]) == fb.shape[0]
-    with pytest.raises(NotImplementedError):
-        m.model.decode(["ctc_greedy_search"], fb, fl, 10, decoding_chunk_size=16, simulate_streaming=True, cat_embs=cat)
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_simulate_streaming_equals_the_cache_based_reference(asr, golden_cases, case):
+    """simulate_streaming: the reference's CACHE-based chunk-by-chunk encoder (encoder.forward_chunk_by_chunk,
+    encoder.py:341-402; golden from the live reference, oracle/make_golden_streaming.py) vs this engine's single masked
+    pass — attention cache == chunk mask, causal cnn cache == left context, non-causal conv == chunk-local conv."""
+    import json as _json
+    import reverb_b200
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    gold = _json.load(open(os.path.join(gdir, "streaming.json")))
+    arr_s = dict(np.load(os.path.join(gdir, "streaming.npz")))
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    feats = torch.from_numpy(arr["feats"][:gold["frames"]]).unsqueeze(0).cuda()
+    lens = torch.tensor([gold["frames"]], dtype=torch.int32)
+    for cs, left in gold["settings"]:
+        want = arr_s[f"{case}_c{cs}_l{left}"]
+        enc, enc_lens = m.model._forward_encoder(feats, lens, cat, cs, left, simulate_streaming=True)
+        assert enc.shape[1] == want.shape[0] == int(enc_lens[0])
+        rr = _rel_rms(enc[0].cpu().numpy(), want)
+        print(f"[{case}] simulate_streaming chunk {cs} left {left}: rel-rms vs the cache-based reference {rr:.2e}")
+        assert rr < 6e-3
+        res = m.model.decode(["ctc_greedy_search", "attention_rescoring"], feats, lens, 10, decoding_chunk_size=cs,
+                             num_decoding_left_chunks=left, simulate_streaming=True, cat_embs=cat, ctc_weight=0.1, blank_id=0)
+        assert len(res["attention_rescoring"]) == 1
 
 
 def test_compute_feats_resamples_non_16k_audio_on_the_gpu(asr, model_dirs, tmp_path):

@@ -139,3 +139,28 @@ def test_reverse_hyps_docstring_example():
     lens = torch.tensor([4, 4, 2])
     r = model_ref.reverse_hyps(hyps, lens, eos)
     assert r.tolist() == [[sos, 3, 2, 1], [sos, 4, 8, 9], [sos, 2, eos, eos]]
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_oracle_streaming_cache_pass_vs_reference_golden(golden_cases, model_dirs, case):
+    """The literal cache-based chunk-by-chunk restatement (model_ref.encoder_forward_chunk_by_chunk) reproduces the live
+    reference's encoder.forward_chunk_by_chunk (tests/golden/streaming.npz); and for a CAUSAL model the single masked
+    pass (chunk mask, all frames valid) is the same function — the identity the engine's simulate_streaming relies on."""
+    import json
+    from oracle import model_ref, pipeline_ref
+    gold = json.load(open("tests/golden/streaming.json"))
+    arr_s = dict(np.load("tests/golden/streaming.npz"))
+    meta, arr = golden_cases[case]
+    orc = pipeline_ref.OracleASR(model_dirs[case][0])
+    feats = torch.from_numpy(arr["feats"][:gold["frames"]]).unsqueeze(0)
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    for cs, left in gold["settings"]:
+        want = arr_s[f"{case}_c{cs}_l{left}"]
+        with torch.no_grad():
+            got = model_ref.encoder_forward_chunk_by_chunk(feats, orc.sd, orc.cfg, cat, cs, left)[0].numpy()
+            masked = model_ref.encoder_forward(feats, torch.tensor([gold["frames"]]), orc.sd, orc.cfg, cat, cs, left)[0][0].numpy()
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-6)
+        if meta["causal"]:
+            np.testing.assert_allclose(masked, want, rtol=0, atol=2e-5)
+        else:
+            assert np.abs(masked - want).max() > 1e-2       # non-causal: the chunk-local convolution matters
