@@ -510,8 +510,14 @@ def main():
                                 "batch_size_8_value": cpu["batch8_rtfx"]}
         try:
             line["parity"] = parity_vs_cpu(asr, eng, model, cpu)
+            line["parity"]["mode"] = "bf16 (the timed configuration)"
+            # the same read-out in the fp32-accurate mode (precision="fp32": bf16x3 tcgen05 passes + fp32 attention)
+            acc = reverb_b200.ReverbASR(os.path.join(mdir, "config.yaml"), os.path.join(mdir, "synth.pt"), gpu=local_rank,
+                                        precision="fp32")
+            line["parity_fp32_mode"] = parity_vs_cpu(acc, acc.engine, acc.model, cpu)
+            del acc
         except Exception as e:      # the parity read-out must never cost the bench line
-            line["parity"] = {"error": repr(e)}
+            line.setdefault("parity", {})["error"] = repr(e)
     _emit(real_stdout, line)
     if world > 1:
         dist.destroy_process_group()

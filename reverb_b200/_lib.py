@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librvb_b200.so")
+# RVB_LIB_PATH: A/B tuning aid (tools/gemm_bench.py against an older build); the product always loads the in-tree library
+LIB_PATH = os.environ.get("RVB_LIB_PATH") or os.path.join(_HERE, "librvb_b200.so")
 
 
 class ModelConfig(C.Structure):
@@ -87,6 +88,8 @@ def load() -> C.CDLL:
             "(or __graft_entry__.build()). reverb_b200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
+        if os.environ.get("RVB_LIB_PATH") and not hasattr(lib, name):
+            continue                                  # an older build lacks the newer entry points
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
