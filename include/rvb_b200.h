@@ -185,6 +185,21 @@ RVB_API int rvb_decoder_step_topk(rvb_model* m, const float* d_enc_out, const in
                                   const int* h_hyps, int L, const float* h_cat_embs, int n_cat, int k, float* h_topk_val,
                                   int* h_topk_idx, void* stream);
 
+/* The decoder step with a per-layer KEY / VALUE cache (decoder.forward_one_step with its `cache`, decoder.py:191-234, as
+ * driven by attention_beam_search, search.py:290-346):
+ *   begin  projects the source-attention keys / values of the encoder output once and sizes the caches for
+ *          max_steps positions of B * N hypotheses;
+ *   step   takes the LAST token of every running hypothesis (h_tokens (B*N)) and, from the second step on, the index
+ *          of the hypothesis each one extends (h_parents (B*N): the caches are gathered accordingly — the
+ *          torch.index_select of search.py:341-346; NULL = identity), runs ONE position through the left decoder and
+ *          returns log_softmax top-k: h_topk_val / h_topk_idx (B*N, k);
+ *   end    frees the caches.  Same values as rvb_decoder_step_topk, which recomputes the whole prefix every step. */
+RVB_API int rvb_decoder_cache_begin(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
+                                    int max_steps, const float* h_cat_embs, int n_cat, void* stream);
+RVB_API int rvb_decoder_cache_step(rvb_model* m, const int* h_tokens, const int* h_parents, int k, float* h_topk_val,
+                                   int* h_topk_idx, void* stream);
+RVB_API int rvb_decoder_cache_end(rvb_model* m);
+
 /* The same decoder step returning the FULL log_softmax row of the last position, h_logp (B*N, vocab) — what
  * decoder.forward_one_step_with_attn (transformer/decoder.py:236-281) hands to BeamSearchTimeSync
  * (espnet/beam_search_timesync.py:156-164, 211-218: `joint_decoding`, search.py:450-496). */

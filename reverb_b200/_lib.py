@@ -58,6 +58,9 @@ SIGNATURES = {
     "rvb_rescoring_collect": (_i, [_vp, _i, _vp, _vp, _vp]),
     "rvb_ticket_release": (_i, [_vp, _i]),
     "rvb_decoder_step_topk": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "rvb_decoder_cache_begin": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]),
+    "rvb_decoder_cache_step": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "rvb_decoder_cache_end": (_i, [_vp]),
     "rvb_decoder_step_logp": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "rvb_attention_rescoring": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _i, _vp, _i, _f, _vp, _vp, _vp]),
     "rvb_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _f, _vp, _i, _vp]),

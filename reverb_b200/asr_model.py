@@ -125,10 +125,23 @@ class ASRModel:
         if "attention" in methods:
             # autoregressive beam search with the left decoder (search.py:251-360); the decoder step runs on the GPU,
             # the beam bookkeeping on the host like the reference's
-            def step(hyps):
-                return self.engine.decoder_step_topk(encoder_out, encoder_lens, hyps, beam_size, cat_embs, beam_size)
-            results["attention"] = attention_beam_search(step, encoder_out.shape[0], encoder_out.shape[1], beam_size,
-                                                         self.sos, self.eos, length_penalty)
+            # KV-cached step: one new position per hypothesis and step (the reference carries a per-layer cache too,
+            # decoder.py:191-234); RVB_ATTENTION_STEP=recompute selects the cache-free step that re-runs the prefix
+            import os as _os
+            if _os.environ.get("RVB_ATTENTION_STEP", "cache") == "recompute":
+                def step(hyps, parents=None):
+                    return self.engine.decoder_step_topk(encoder_out, encoder_lens, hyps, beam_size, cat_embs, beam_size)
+                results["attention"] = attention_beam_search(step, encoder_out.shape[0], encoder_out.shape[1],
+                                                             beam_size, self.sos, self.eos, length_penalty)
+            else:
+                self.engine.decoder_cache_begin(encoder_out, encoder_lens, beam_size, encoder_out.shape[1], cat_embs)
+                try:
+                    def step(hyps, parents=None):
+                        return self.engine.decoder_cache_step(hyps[:, -1], parents, beam_size)
+                    results["attention"] = attention_beam_search(step, encoder_out.shape[0], encoder_out.shape[1],
+                                                                 beam_size, self.sos, self.eos, length_penalty)
+                finally:
+                    self.engine.decoder_cache_end()
         if "ctc_greedy_search" in methods:
             results["ctc_greedy_search"] = greedy_results(self.engine.greedy_search(topk_idx, encoder_lens, blank_id))
         if joint:

@@ -69,9 +69,9 @@ attention_f32_kernel(AttnF32Args a) {
   __syncwarp();
   const float rs = sqrtf((float)a.dk);
   float m = -INFINITY;
-  for (int j = lane; j < a.Tk; j += 32) {
+  for (int j = lo + lane; j < hi; j += 32) {   // only the visible keys [lo, hi) are ever touched
     float s = -INFINITY;
-    if (j >= lo && j < hi) {
+    {
       const bf16* krow = a.k + ((long long)g * a.Tk + j) * a.ldk + h * a.dk;
       float ac = 0.f, bd = 0.f;
       for (int c = 0; c < a.dk; c += 8) ac = dot8_pair(qu + c, krow + c, a.k_lo, ac);
@@ -86,8 +86,8 @@ attention_f32_kernel(AttnF32Args a) {
   }
   m = warp_max(m);
   float sum = 0.f;
-  for (int j = lane; j < a.Tk; j += 32) {
-    const float e = (m == -INFINITY) ? 0.f : expf(sc[j] - m);  // exp(-inf) = 0: masked keys drop out
+  for (int j = lo + lane; j < hi; j += 32) {
+    const float e = (m == -INFINITY) ? 0.f : expf(sc[j] - m);
     sc[j] = e;
     sum += e;
   }

@@ -667,9 +667,9 @@ int launch_sinusoid(int T, int d, float* out_f32, bf16* out_bf16, cudaStream_t s
 // decoder embedding + absolute positional encoding (transformer/decoder.py:147 `self.embed`,
 // embedding.py:58-76: x * sqrt(d) + pe[:L])
 __global__ void embed_posenc_kernel(const int* __restrict__ tok, const float* __restrict__ emb, int L, int d,
-                                    float nlod, float* __restrict__ out) {
+                                    float nlod, float* __restrict__ out, int pos0) {
   const int r = blockIdx.x;
-  const int pos = r % L;
+  const int pos = pos0 + r % L;
   const int id = tok[r];
   const float xs = sqrtf((float)d);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -681,9 +681,64 @@ __global__ void embed_posenc_kernel(const int* __restrict__ tok, const float* __
   }
 }
 
-int launch_embed_posenc(const int* tokens, const float* emb, int N, int L, int d, float* out, cudaStream_t stream) {
+int launch_embed_posenc(const int* tokens, const float* emb, int N, int L, int d, float* out, cudaStream_t stream,
+                        int pos0) {
   if (N * L <= 0) return 0;
-  embed_posenc_kernel<<<N * L, 128, 0, stream>>>(tokens, emb, L, d, (float)(-(log(10000.0) / (double)d)), out);
+  embed_posenc_kernel<<<N * L, 128, 0, stream>>>(tokens, emb, L, d, (float)(-(log(10000.0) / (double)d)), out, pos0);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// KV cache of the autoregressive decoder step (engine.cu decoder_cache_step; reference decoder.py:191-234 keeps the layer
+// OUTPUTS of the previous positions and re-projects their keys / values each step — a key / value cache holds the
+// same information with less work).  Rows are `width` bf16 wide ([k | v], or its hi/lo pair layout).
+//   kv_append : cache[s, pos, 0..width) = kv[s, col0 .. col0 + width)   (kv: (S, ld); cache rows are row_stride wide)
+//   kv_reorder: dst[s, 0..npos, :] = src[parent[s], 0..npos, :]   (beam reordering, torch.index_select in the reference)
+__global__ void kv_append_kernel(const bf16* __restrict__ kv, long long ld, int col0, bf16* __restrict__ cache, int Lcap,
+                                 int pos, int width, int row_stride) {
+  const int s = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(kv + (long long)s * ld + col0);
+  uint4* dst = reinterpret_cast<uint4*>(cache + ((long long)s * Lcap + pos) * row_stride);
+  for (int i = threadIdx.x; i < width / 8; i += blockDim.x) dst[i] = src[i];
+}
+
+int launch_kv_append(const bf16* kv, long long ld, int col0, bf16* cache, int S, int Lcap, int pos, int width,
+                     int row_stride, cudaStream_t stream) {
+  RVB_REQUIRE(width % 8 == 0 && ld % 8 == 0 && col0 % 8 == 0 && row_stride % 8 == 0, "kv_append: rows must be 16-byte aligned");
+  if (S <= 0) return 0;
+  kv_append_kernel<<<S, 128, 0, stream>>>(kv, ld, col0, cache, Lcap, pos, width, row_stride);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void kv_reorder_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, const int* __restrict__ parent,
+                                  int Lcap, int npos, int width) {
+  const int s = blockIdx.x, p = parent[s];
+  const uint4* a = reinterpret_cast<const uint4*>(src + (long long)p * Lcap * width);
+  uint4* b = reinterpret_cast<uint4*>(dst + (long long)s * Lcap * width);
+  const long long n = (long long)npos * width / 8;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) b[i] = a[i];
+}
+
+int launch_kv_reorder(const bf16* src, bf16* dst, const int* parent, int S, int Lcap, int npos, int width,
+                      cudaStream_t stream) {
+  if (S <= 0 || npos <= 0) return 0;
+  kv_reorder_kernel<<<S, 256, 0, stream>>>(src, dst, parent, Lcap, npos, width);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void fill_int_kernel(int* p, int n, int v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int launch_fill_int(int* p, int n, int v, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  fill_int_kernel<<<(n + 255) / 256, 256, 0, stream>>>(p, n, v);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;

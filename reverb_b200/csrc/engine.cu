@@ -129,6 +129,7 @@ struct DecLayer {
 };
 
 struct SearchTicket;
+struct DecCache;
 
 struct Decoder {
   float* emb = nullptr;  // (V, d) fp32
@@ -174,6 +175,7 @@ struct rvb_model {
   int lens_B = 0;
   static constexpr int kTickets = 4;
   rvb::SearchTicket* tickets = nullptr;  // [kTickets], created on first use (engine.cu search_submit)
+  rvb::DecCache* dcache = nullptr;        // KV cache of the autoregressive decoder (decoder_cache_begin / _step)
 
   int F1() const { return (cfg.input_dim - 1) / 2; }
   int F2() const { return (F1() - 1) / 2; }
@@ -1034,6 +1036,188 @@ static int decoder_step_topk(rvb_model* m, const float* d_enc_out, const int* h_
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Autoregressive decoding with a KEY / VALUE cache (`attention` mode, search.py:251-360).  The reference's
+// decoder.forward_one_step (decoder.py:191-234) caches each layer's OUTPUT for the previous positions and re-projects
+// their self-attention keys / values every step; here the projected keys / values themselves are cached per layer
+// ((S, Lcap, [k | v])), the source-attention keys / values of the encoder output are projected ONCE per utterance, and a
+// step touches exactly one new position per hypothesis: every GEMM has M = S = B * N rows.  Beam reordering
+// (torch.index_select of the caches, search.py:341-346) is a gather between two cache buffers.
+struct DecCache {
+  int B = 0, Tp = 0, N = 0, S = 0, Lcap = 0, step = 0;
+  bool flip = false;
+  std::vector<DevBuf> self_a, self_b, cross;  // per layer
+  DevBuf ints;   // enc lens (B) | key counts (S) | tokens (S) | parents (S)
+  DevBuf x, n, qkv, att, h, ybf, logits, outv;
+  HostPinned pin;
+  void release() {
+    for (auto* v : {&self_a, &self_b, &cross})
+      for (auto& b : *v) b.release();
+    for (DevBuf* b : {&ints, &x, &n, &qkv, &att, &h, &ybf, &logits, &outv}) b->release();
+    pin.release();
+  }
+};
+
+static int decoder_cache_begin(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
+                               int Lcap, const float* h_cat, int n_cat, cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  RVB_REQUIRE(m->finalized && m->dec_l.present, "decoder_cache_begin: model has no decoder");
+  RVB_REQUIRE(B > 0 && Tp > 0 && N > 0 && Lcap > 0, "decoder_cache_begin: bad shape");
+  if (m->dcache == nullptr) m->dcache = new DecCache();
+  DecCache& dc = *m->dcache;
+  Decoder& D = m->dec_l;
+  const int d = c.d_model, S = B * N;
+  const size_t pm = (size_t)m->pm(), nl = D.layers.size();
+  const long long Mem = (long long)B * Tp;
+  if (fold_lang(m, h_cat, n_cat, stream)) return -1;
+  dc.B = B; dc.Tp = Tp; dc.N = N; dc.S = S; dc.Lcap = Lcap; dc.step = 0; dc.flip = false;
+  dc.self_a.resize(nl); dc.self_b.resize(nl); dc.cross.resize(nl);
+  const size_t kvw = (size_t)2 * d * pm;  // cache row: [k | v] (x2 for the hi / lo pair layout)
+  for (size_t l = 0; l < nl; ++l)
+    if (dc.self_a[l].ensure((size_t)S * Lcap * kvw * 2) || dc.self_b[l].ensure((size_t)S * Lcap * kvw * 2) ||
+        dc.cross[l].ensure((size_t)Mem * kvw * 2))
+      return -1;
+  const int ldv = (c.vocab + 3) & ~3;
+  if (dc.ints.ensure(sizeof(int) * ((size_t)B + 3 * S)) || dc.x.ensure((size_t)S * d * 4) ||
+      dc.n.ensure((size_t)S * d * 2 * pm) || dc.qkv.ensure((size_t)S * 3 * d * 2 * pm) ||
+      dc.att.ensure((size_t)S * d * 2 * pm) || dc.h.ensure((size_t)S * c.dec_ffn_dim * 2 * pm) ||
+      dc.ybf.ensure((size_t)S * d * 2 * pm) || dc.logits.ensure((size_t)S * ldv * 4) ||
+      dc.outv.ensure((size_t)S * 16 * 8) || dc.pin.ensure(sizeof(int) * ((size_t)B + 2 * S) + (size_t)S * 16 * 8) ||
+      m->ws_encbf.ensure((size_t)Mem * d * 2 * pm))
+    return -1;
+  int* hp = dc.pin.as<int>();
+  memcpy(hp, h_enc_lens, sizeof(int) * B);
+  RVB_CHECK_CUDA(cudaMemcpyAsync(dc.ints.p, hp, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+  bf16* encbf = m->ws_encbf.as<bf16>();
+  if (m->x3 ? launch_f32_to_pair(d_enc_out, encbf, Mem, d, stream) : launch_f32_to_bf16(d_enc_out, encbf, Mem * d, stream))
+    return -1;
+  for (size_t l = 0; l < nl; ++l)   // source-attention keys / values: once per utterance, not once per step
+    if (gemm(m, encbf, D.layers[l].ckv, (int)Mem, ACT_NONE, OUT_BF16, dc.cross[l].p, 1.f, stream)) return -1;
+  return 0;
+}
+
+// One position for every running hypothesis: tokens[s] = last token of hypothesis s, parents[s] = index (in the previous
+// step's order) of the hypothesis it extends (nullptr / ignored at step 0).  -> log_softmax top-k of the new position.
+static int decoder_cache_step(rvb_model* m, const int* h_tokens, const int* h_parents, int k, float* h_val, int* h_idx,
+                              cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  RVB_REQUIRE(m->dcache != nullptr && m->dcache->S > 0, "decoder_cache_step: call decoder_cache_begin first");
+  DecCache& dc = *m->dcache;
+  Decoder& D = m->dec_l;
+  const int d = c.d_model, H = c.dec_heads, dk = d / H, V = c.vocab, S = dc.S, B = dc.B, N = dc.N, pos = dc.step;
+  RVB_REQUIRE(pos < dc.Lcap, "decoder_cache_step: step %d exceeds the cache capacity %d", pos, dc.Lcap);
+  RVB_REQUIRE(k >= 1 && k <= 16 && k <= V, "decoder_cache_step: bad k=%d", k);
+  const bool x3 = m->x3;
+  const int pm = m->pm();
+  const int kvw = 2 * d * pm;
+  int* d_elen = dc.ints.as<int>();
+  int* d_klen = d_elen + B;
+  int* d_tok = d_klen + S;
+  int* d_par = d_tok + S;
+  int* hp = dc.pin.as<int>() + B;
+  for (int s = 0; s < S; ++s) {
+    RVB_REQUIRE(h_tokens[s] >= 0 && h_tokens[s] < V, "decoder_cache_step: token id %d out of range", h_tokens[s]);
+    hp[s] = h_tokens[s];
+    hp[S + s] = (h_parents && pos > 0) ? h_parents[s] : s;
+    RVB_REQUIRE(hp[S + s] >= 0 && hp[S + s] < S, "decoder_cache_step: bad parent index");
+  }
+  RVB_CHECK_CUDA(cudaMemcpyAsync(d_tok, hp, sizeof(int) * 2 * S, cudaMemcpyHostToDevice, stream));
+  if (launch_fill_int(d_klen, S, pos + 1, stream)) return -1;
+  std::vector<DevBuf>& cur = dc.flip ? dc.self_b : dc.self_a;
+  std::vector<DevBuf>& nxt = dc.flip ? dc.self_a : dc.self_b;
+  const bool reorder = h_parents != nullptr && pos > 0;
+  float* x = dc.x.as<float>();
+  bf16* n = dc.n.as<bf16>();
+  bf16* qkv = dc.qkv.as<bf16>();
+  bf16* att = dc.att.as<bf16>();
+  bf16* h = dc.h.as<bf16>();
+  bf16* ybf = dc.ybf.as<bf16>();
+  if (launch_embed_posenc(d_tok, D.emb, S, 1, d, x, stream, pos)) return -1;
+  for (size_t l = 0; l < D.layers.size(); ++l) {
+    DecLayer& Ld = D.layers[l];
+    bf16* cache = cur[l].as<bf16>();
+    if (reorder) {  // the hypotheses were re-ranked: their histories follow (search.py:341-346)
+      if (launch_kv_reorder(cache, nxt[l].as<bf16>(), d_par, S, dc.Lcap, pos, kvw, stream)) return -1;
+      cache = nxt[l].as<bf16>();
+    }
+    // self-attention of the new position over its own history
+    if (launch_layernorm(x, Ld.n1.g, Ld.n1.b, Ld.eps, S, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    if (gemm(m, n, Ld.qkv, S, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    // cache row = [k | v] = columns [d, 3d) of the projection (and their lo halves at +3d in the pair layout)
+    if (launch_kv_append(qkv, 3 * d * pm, d, cache, S, dc.Lcap, pos, 2 * d, kvw, stream)) return -1;
+    if (x3 && launch_kv_append(qkv, 3 * d * pm, 3 * d + d, cache + 2 * d, S, dc.Lcap, pos, 2 * d, kvw, stream)) return -1;
+    {
+      AttnF32Args a;
+      a.q = qkv;
+      a.ldq = 3 * d * pm;
+      a.q_lo = x3 ? 3 * d : 0;
+      a.k = cache;
+      a.v = cache + d;
+      a.ldk = a.ldv = kvw;
+      a.k_lo = a.v_lo = x3 ? 2 * d : 0;
+      a.out = att;
+      a.ldo = d * pm;
+      a.o_lo = x3 ? d : 0;
+      a.groups = S;
+      a.Tq = 1;
+      a.Tk = dc.Lcap;      // group stride; the visible keys are [0, pos]
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_klen;
+      if (launch_attention_f32(a, stream)) return -1;
+    }
+    if (gemm(m, att, Ld.so, S, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    // source attention over the utterance's encoder output
+    if (launch_layernorm(x, Ld.n2.g, Ld.n2.b, Ld.eps, S, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    if (gemm(m, n, Ld.cq, S, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    {
+      AttnF32Args a;
+      a.q = qkv;
+      a.ldq = d * pm;
+      a.q_lo = x3 ? d : 0;
+      a.k = dc.cross[l].as<bf16>();
+      a.v = a.k + d;
+      a.ldk = a.ldv = kvw;
+      a.k_lo = a.v_lo = x3 ? 2 * d : 0;
+      a.out = att;
+      a.ldo = d * pm;
+      a.o_lo = x3 ? d : 0;
+      a.groups = B;
+      a.Tq = N;
+      a.Tk = dc.Tp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_elen;
+      if (launch_attention_f32(a, stream)) return -1;
+    }
+    if (gemm(m, att, Ld.co, S, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    if (launch_layernorm(x, Ld.n3.g, Ld.n3.b, Ld.eps, S, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    const bf16* ffn_in = n;
+    if (Ld.lsl) {
+      if (gemm(m, n, Ld.lang, S, ACT_NONE, OUT_BF16, ybf, 1.f, stream)) return -1;
+      ffn_in = ybf;
+    }
+    if (gemm(m, ffn_in, Ld.ff1, S, ACT_RELU, OUT_BF16, h, 1.f, stream)) return -1;
+    if (gemm(m, h, Ld.ff2, S, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+  }
+  if (reorder) dc.flip = !dc.flip;
+  if (launch_layernorm(x, D.after.g, D.after.b, 1e-5f, S, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+  const int ldv = (V + 3) & ~3;
+  float* logits = dc.logits.as<float>();
+  if (gemm(m, n, D.outl, S, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
+  float* d_val = dc.outv.as<float>();
+  int* d_idx = reinterpret_cast<int*>(d_val + (size_t)S * k);
+  if (launch_logsoftmax_topk(logits, ldv, S, V, k, d_val, d_idx, nullptr, 1, stream)) return -1;
+  char* hout = reinterpret_cast<char*>(dc.pin.as<int>() + B + 2 * S);
+  const size_t out_bytes = (size_t)S * k * (sizeof(float) + sizeof(int));
+  RVB_CHECK_CUDA(cudaMemcpyAsync(hout, d_val, out_bytes, cudaMemcpyDeviceToHost, stream));
+  RVB_CHECK_CUDA(cudaStreamSynchronize(stream));
+  memcpy(h_val, hout, (size_t)S * k * sizeof(float));
+  memcpy(h_idx, hout + (size_t)S * k * sizeof(float), (size_t)S * k * sizeof(int));
+  dc.step = pos + 1;
+  return 0;
+}
+
 // Decoder passes over device-resident inputs (all int arrays on the device):
 //   tok_l / tok_r (R = S*Lp): decoder inputs [sos, w_1..w_U, eos..] and the reversed variant (asr_model.py:921-949)
 //   gat_l / gat_r (R): per-position gather targets, -1 = none (search.py:417-430);  slen (S) = U + 1;  elen (B)
@@ -1292,6 +1476,7 @@ RVB_API int rvb_gemm_profile_end(double* total_ms, double* total_flops, long lon
 }
 
 RVB_API void rvb_model_destroy(rvb_model* m);
+RVB_API int rvb_decoder_cache_end(rvb_model* m);
 
 RVB_API rvb_model* rvb_model_create(const rvb_model_config* cfg) {
   if (cfg == nullptr) {
@@ -1385,6 +1570,7 @@ RVB_API void rvb_model_destroy(rvb_model* m) {
     for (int i = 0; i < rvb_model::kTickets; ++i) m->tickets[i].release();
     delete[] m->tickets;
   }
+  rvb_decoder_cache_end(m);
   m->pin_a.release();
   m->pin_b.release();
   m->pin_c.release();
@@ -1612,6 +1798,27 @@ RVB_API int rvb_decoder_step_topk(rvb_model* m, const float* d_enc_out, const in
               "rvb_decoder_step_topk: bad arguments");
   return rvb::decoder_step_topk(m, d_enc_out, h_enc_lens, B, Tp, N, h_hyps, L, h_cat_embs, n_cat, k, h_topk_val,
                                 h_topk_idx, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_decoder_cache_begin(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,
+                                    int max_steps, const float* h_cat_embs, int n_cat, void* stream) {
+  RVB_REQUIRE(m && d_enc_out && h_enc_lens, "rvb_decoder_cache_begin: bad arguments");
+  return rvb::decoder_cache_begin(m, d_enc_out, h_enc_lens, B, Tp, N, max_steps, h_cat_embs, n_cat, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_decoder_cache_step(rvb_model* m, const int* h_tokens, const int* h_parents, int k, float* h_topk_val,
+                                   int* h_topk_idx, void* stream) {
+  RVB_REQUIRE(m && h_tokens && h_topk_val && h_topk_idx, "rvb_decoder_cache_step: bad arguments");
+  return rvb::decoder_cache_step(m, h_tokens, h_parents, k, h_topk_val, h_topk_idx, (cudaStream_t)stream);
+}
+
+RVB_API int rvb_decoder_cache_end(rvb_model* m) {
+  if (m && m->dcache) {
+    m->dcache->release();
+    delete m->dcache;
+    m->dcache = nullptr;
+  }
+  return 0;
 }
 
 RVB_API int rvb_decoder_step_logp(rvb_model* m, const float* d_enc_out, const int* h_enc_lens, int B, int Tp, int N,

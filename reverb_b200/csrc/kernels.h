@@ -117,7 +117,14 @@ int launch_f32_to_pair(const float* x, bf16* out, long long rows, int width, cud
 int launch_weighted_sum_bf16(const float* const* ins, const float* coef, int n_in, long long n, bf16* out_bf16,
                              float* out_f32, cudaStream_t stream);
 // decoder input: x[r, :] = emb[tok[r], :] * sqrt(d) + pe[pos(r), :]   (fp32), r over (N, L)
-int launch_embed_posenc(const int* tokens, const float* emb, int N, int L, int d, float* out, cudaStream_t stream);
+int launch_embed_posenc(const int* tokens, const float* emb, int N, int L, int d, float* out, cudaStream_t stream,
+                        int pos0 = 0 /* position of column 0 */);
+// decoder KV cache helpers (elementwise.cu): rows of `width` bf16, caches (S, Lcap, width)
+int launch_kv_append(const bf16* kv, long long ld, int col0, bf16* cache, int S, int Lcap, int pos, int width,
+                     int row_stride, cudaStream_t stream);
+int launch_kv_reorder(const bf16* src, bf16* dst, const int* parent, int S, int Lcap, int npos, int width,
+                      cudaStream_t stream);
+int launch_fill_int(int* p, int n, int v, cudaStream_t stream);
 // sinusoidal table pe[pos, :] for pos < T (fp32 (T, d) and bf16 copy)
 int launch_sinusoid(int T, int d, float* out_f32, bf16* out_bf16, cudaStream_t stream);
 

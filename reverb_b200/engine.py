@@ -389,6 +389,37 @@ class Engine:
                                                  self._stream()), "rvb_decoder_step_topk")
         return val, idx
 
+    # ---- KV-cached autoregressive decoder step (`attention` mode)
+    def decoder_cache_begin(self, enc_out: torch.Tensor, enc_lens, n_per_utt: int, max_steps: int, cat_embs=None) -> None:
+        """Project the source-attention keys / values of enc_out once and size the per-layer self-attention caches for
+        `max_steps` positions of B * n_per_utt hypotheses (include/rvb_b200.h rvb_decoder_cache_*)."""
+        B, Tp, _ = enc_out.shape
+        lens = np.ascontiguousarray(np.asarray(enc_lens, dtype=np.int32))
+        cat, ncat = self._cat(cat_embs)
+        self._cache_keep = enc_out.contiguous()
+        self._cache_S = B * n_per_utt
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_decoder_cache_begin(self._h, _ptr(self._cache_keep), _np_ptr(lens), B, Tp, n_per_utt,
+                                                   int(max_steps), _np_ptr(cat), ncat, self._stream()),
+                  "rvb_decoder_cache_begin")
+
+    def decoder_cache_step(self, last_tokens: np.ndarray, parents: Optional[np.ndarray], k: int):
+        """last_tokens (S,): the newest token of every hypothesis; parents (S,): the hypothesis (previous order) each
+        one extends, None at the first step.  -> (val (S, k) float32, idx (S, k) int32) log_softmax top-k."""
+        tok = np.ascontiguousarray(last_tokens, dtype=np.int32).reshape(-1)
+        assert tok.shape[0] == self._cache_S
+        par = None if parents is None else np.ascontiguousarray(parents, dtype=np.int32).reshape(-1)
+        val = np.empty((self._cache_S, k), dtype=np.float32)
+        idx = np.empty((self._cache_S, k), dtype=np.int32)
+        with torch.cuda.device(self.device):
+            check(self.lib.rvb_decoder_cache_step(self._h, _np_ptr(tok), _np_ptr(par), k, _np_ptr(val), _np_ptr(idx),
+                                                  self._stream()), "rvb_decoder_cache_step")
+        return val, idx
+
+    def decoder_cache_end(self) -> None:
+        self.lib.rvb_decoder_cache_end(self._h)
+        self._cache_keep = None
+
     def decoder_step_logp(self, enc_out: torch.Tensor, enc_lens, hyps: np.ndarray, n_per_utt: int, cat_embs=None):
         """hyps (B*N, L) running hypotheses (sos first) -> the full log_softmax rows of the left decoder at the last
         position, (B*N, vocab) float32 (decoder.forward_one_step_with_attn of the reference, for joint_decoding)."""

@@ -116,8 +116,10 @@ def rescoring_pick_batch(toks: np.ndarray, tims: np.ndarray, olen: np.ndarray, c
 def attention_beam_search(step_topk, batch_size: int, maxlen: int, beam_size: int, sos: int, eos: int,
                           length_penalty: float = 0.0) -> List[DecodeResult]:
     """Host bookkeeping of the `attention` decode mode (transformer/search.py:251-360, non-whisper branch), numpy
-    float32 like the reference's tensors.  step_topk(hyps (B*N, i) int64) -> (logp (B*N, N), index (B*N, N)) is the
-    decoder step (Engine.decoder_step_topk).  Finished beams keep one zero-cost <eos> branch (utils/mask.py:257-303);
+    float32 like the reference's tensors.  step_topk(hyps (B*N, i) int64, parents (B*N,) or None) -> (logp (B*N, N),
+    index (B*N, N)) is the decoder step: `parents[s]` = row (of the previous call's hyps) that row s extends — what the
+    reference uses to re-index its decoder cache (:341-346) and what the KV-cached native step needs
+    (Engine.decoder_cache_step); a step function that recomputes the prefix (Engine.decoder_step_topk) ignores it.  Finished beams keep one zero-cost <eos> branch (utils/mask.py:257-303);
     the best beam per utterance is chosen after the length penalty; returns DecodeResult(tokens) only (no times /
     confidences: `transcribe(mode="attention")` fails in the reference for that reason)."""
     B, N = batch_size, beam_size
@@ -127,10 +129,11 @@ def attention_beam_search(step_topk, batch_size: int, maxlen: int, beam_size: in
     scores = np.tile(np.array([0.0] + [-np.inf] * (N - 1), dtype=np.float32), B).reshape(-1, 1)
     end_flag = np.zeros((running, 1), dtype=bool)
     zeros = np.zeros((running, 1), dtype=bool)
+    parents = None
     for _ in range(1, maxlen + 1):
         if int(end_flag.sum()) == running:
             break
-        logp, index = step_topk(hyps)
+        logp, index = step_topk(hyps, parents)
         logp = np.array(logp, dtype=np.float32, copy=True).reshape(running, N)
         index = np.array(index, dtype=np.int64, copy=True).reshape(running, N)
         if N > 1:
@@ -146,7 +149,8 @@ def attention_beam_search(step_topk, batch_size: int, maxlen: int, beam_size: in
         scores = np.take_along_axis(cand, order, axis=1).reshape(-1, 1)
         best_k_index = (np.arange(B)[:, None] * N * N + order).reshape(-1)
         best_k_pred = index.reshape(-1)[best_k_index]
-        hyps = np.concatenate([hyps[best_k_index // N], best_k_pred[:, None]], axis=1)
+        parents = best_k_index // N
+        hyps = np.concatenate([hyps[parents], best_k_pred[:, None]], axis=1)
         end_flag = hyps[:, -1:] == eos
     final = scores.reshape(B, N)
     lengths = (hyps != eos).sum(axis=1).reshape(B, N).astype(np.float32)

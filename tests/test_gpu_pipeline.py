@@ -236,7 +236,11 @@ def test_attention_mode_decoder_steps_and_search(asr, golden_cases, model_dirs, 
             assert float((want.topk(N).values - torch.from_numpy(val)).abs().max()) < 0.15
         # (2) full search: GPU decode == oracle bookkeeping over the GPU step function
         for lp in (0.0, 0.6):
-            got = m.model.decode(["attention"], fb, fl, N, length_penalty=lp, cat_embs=cat, blank_id=0)["attention"]
+            os.environ["RVB_ATTENTION_STEP"] = "recompute"      # the cache-free step, same function as `step` below
+            try:
+                got = m.model.decode(["attention"], fb, fl, N, length_penalty=lp, cat_embs=cat, blank_id=0)["attention"]
+            finally:
+                del os.environ["RVB_ATTENTION_STEP"]
 
             def step(hyps):
                 v, i = m.engine.decoder_step_topk(enc, enc_lens, hyps.numpy(), N, cat, N)
@@ -248,6 +252,53 @@ def test_attention_mode_decoder_steps_and_search(asr, golden_cases, model_dirs, 
                 total += 1
                 agree += int(list(got[b].tokens) == gold[f"length_penalty_{lp}"][bi][b])
     assert agree >= 0.5 * total, (agree, total)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_kv_cached_decoder_step_equals_prefix_recompute(model_dirs, golden_cases, precision):
+    """rvb_decoder_cache_* (one new position per step, per-layer key / value cache, beam reordering by gather) against
+    rvb_decoder_step_topk (recomputes the prefix): the same log_softmax top-k, step after step, under random beam
+    re-rankings.  Then `attention` mode end to end: in the fp32-accurate mode the tokens of the live reference
+    (tests/golden/attention_mode.json) exactly."""
+    import json as _json
+    import reverb_b200
+    case = "causal_ln"
+    meta, arr = golden_cases[case]
+    m = reverb_b200.load_model(model_dirs[case][0], precision=precision)
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    fb, fl = next(iter(m.feats_batcher(feats, meta["chunk_size"], meta["batch_size"])))
+    enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
+    B, N = enc.shape[0], 4
+    S = B * N
+    rng = np.random.default_rng(5)
+    hyps = np.full((S, 1), m.model.sos, dtype=np.int64)
+    m.engine.decoder_cache_begin(enc, enc_lens, N, 12, cat)
+    tol = 2e-3 if precision == "fp32" else 0.12
+    try:
+        parents = None
+        for step in range(8):
+            v_c, i_c = m.engine.decoder_cache_step(hyps[:, -1], parents, 6)
+            v_r, i_r = m.engine.decoder_step_topk(enc, enc_lens, hyps, N, cat, 6)
+            assert float(np.abs(v_c - v_r).max()) < tol, (step, float(np.abs(v_c - v_r).max()))
+            if precision == "fp32":
+                assert (i_c == i_r).mean() > 0.97
+            # re-rank: every utterance's hypotheses pick random parents among its own N, and extend them
+            parents = (np.arange(S) // N) * N + rng.integers(0, N, size=S)
+            new_tok = i_r[parents, rng.integers(0, 6, size=S)]
+            hyps = np.concatenate([hyps[parents], new_tok[:, None]], axis=1)
+    finally:
+        m.engine.decoder_cache_end()
+    gold = _json.load(open(os.path.join(os.path.dirname(__file__), "golden", "attention_mode.json")))["cases"][case]
+    agree = total = 0
+    for bi, (fb, fl) in enumerate(m.feats_batcher(feats, meta["chunk_size"], meta["batch_size"])):
+        for lp in (0.0, 0.6):
+            got = m.model.decode(["attention"], fb, fl, 10, length_penalty=lp, cat_embs=cat, blank_id=0)["attention"]
+            for b, r in enumerate(got):
+                total += 1
+                agree += int(list(r.tokens) == gold[f"length_penalty_{lp}"][bi][b])
+    print(f"[attention mode, KV-cached, {precision}] hypotheses identical to the live reference: {agree}/{total}")
+    assert agree == total or precision == "bf16"
 
 
 @pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
