@@ -206,7 +206,16 @@ def test_attention_beam_search_host_logic_equals_oracle_restatement():
                 x[eos] += 0.9 * (len(h) - 3)
                 rows.append(torch.log_softmax(torch.from_numpy(x), dim=0))
             return torch.stack(rows)
-        return (lambda hyps: logp_of(hyps).topk(N)), (lambda hyps: tuple(t.numpy() for t in logp_of(hyps).topk(N)))
+        prev = {}
+
+        def n_step(hyps, parents=None):
+            # the product passes `parents` (row of the previous call's hyps each row extends): check the contract
+            hyps = np.asarray(hyps)
+            if parents is not None:
+                assert np.array_equal(prev["hyps"][np.asarray(parents)], hyps[:, :-1])
+            prev["hyps"] = hyps.copy()
+            return tuple(t.numpy() for t in logp_of(hyps).topk(N))
+        return (lambda hyps: logp_of(hyps).topk(N)), n_step
     for seed, B, N, lp, maxlen in [(0, 3, 10, 0.0, 12), (1, 2, 4, 0.6, 9), (2, 1, 1, 0.0, 6), (3, 4, 10, 1.0, 5)]:
         t_step, n_step = make_step(seed, N)
         want = search_ref.attention_beam_search(t_step, B, maxlen, N, sos, eos, lp)
