@@ -176,6 +176,8 @@ struct rvb_model {
   static constexpr int kTickets = 4;
   rvb::SearchTicket* tickets = nullptr;  // [kTickets], created on first use (engine.cu search_submit)
   rvb::DecCache* dcache = nullptr;        // KV cache of the autoregressive decoder (decoder_cache_begin / _step)
+  cudaStream_t s_search = nullptr;        // side stream of the prefix beam search (search_submit)
+  cudaEvent_t ev_topk = nullptr;
 
   int F1() const { return (cfg.input_dim - 1) / 2; }
   int F2() const { return (F1() - 1) / 2; }
@@ -1358,12 +1360,28 @@ static int search_submit(rvb_model* m, SearchTicket& t, const float* d_topk_val,
   int* hp_small = t.small.as<int>();
   int* hp_elen = reinterpret_cast<int*>(reinterpret_cast<char*>(hp_small) + t.small_bytes);
   memcpy(hp_elen, h_enc_lens, sizeof(int) * B);
-  RVB_CHECK_CUDA(cudaMemcpyAsync(t.d_lens(), hp_elen, sizeof(int) * B, cudaMemcpyHostToDevice, stream));
+  // The search runs on a SIDE stream: it is one CTA per utterance (64 of 148 SMs, latency-bound, ~2.7 ms at B = 64), so
+  // in a pipelined decode the next batch's fbank / conv1 (bandwidth-bound, small CTAs) share the GPU with it instead of
+  // queueing behind it.  The side stream starts after everything enqueued so far on `stream` (the CTC top-k);
+  // rescoring_submit makes `stream` wait for ev_search before it touches the n-best.
+  if (m->s_search == nullptr) RVB_CHECK_CUDA(cudaStreamCreateWithFlags(&m->s_search, cudaStreamNonBlocking));
+  if (m->ev_topk == nullptr) RVB_CHECK_CUDA(cudaEventCreateWithFlags(&m->ev_topk, cudaEventDisableTiming));
+  static int side = -1;
+  if (side < 0) {
+    const char* e = getenv("RVB_SEARCH_STREAM");   // RVB_SEARCH_STREAM=main: keep the search on the caller's stream
+    side = (e && strcmp(e, "main") == 0) ? 0 : 1;
+  }
+  cudaStream_t ss = side ? m->s_search : stream;
+  if (side) {
+    RVB_CHECK_CUDA(cudaEventRecord(m->ev_topk, stream));
+    RVB_CHECK_CUDA(cudaStreamWaitEvent(ss, m->ev_topk, 0));
+  }
+  RVB_CHECK_CUDA(cudaMemcpyAsync(t.d_lens(), hp_elen, sizeof(int) * B, cudaMemcpyHostToDevice, ss));
   if (launch_ctc_prefix_beam(d_topk_val, d_topk_idx, k, t.d_lens(), B, Tp, beam, blank_id, ws.p, ws.cap, dev_len,
-                             t.d_tok(), t.d_tim(), t.d_olen(), t.d_sc(), t.d_nhyp(), stream))
+                             t.d_tok(), t.d_tim(), t.d_olen(), t.d_sc(), t.d_nhyp(), ss))
     return -1;
-  RVB_CHECK_CUDA(cudaMemcpyAsync(hp_small, t.d_olen(), t.small_bytes, cudaMemcpyDeviceToHost, stream));
-  RVB_CHECK_CUDA(cudaEventRecord(t.ev_search, stream));
+  RVB_CHECK_CUDA(cudaMemcpyAsync(hp_small, t.d_olen(), t.small_bytes, cudaMemcpyDeviceToHost, ss));
+  RVB_CHECK_CUDA(cudaEventRecord(t.ev_search, ss));
   t.state = 1;
   return 0;
 }
@@ -1376,6 +1394,7 @@ static int rescoring_submit(rvb_model* m, SearchTicket& t, const float* h_cat, i
   RVB_REQUIRE(t.state == 1, "rescoring_submit: ticket has no submitted search");
   const int B = t.B, N = t.beam, S = B * N, dev_len = t.Tp, Tp = t.Tp;
   RVB_CHECK_CUDA(cudaEventSynchronize(t.ev_search));
+  RVB_CHECK_CUDA(cudaStreamWaitEvent(stream, t.ev_search, 0));   // the n-best was produced on the side stream
   const int* ol = t.small.as<int>();
   const int* nh = ol + (size_t)S * 2;
   int Lmax = 1;
@@ -1571,6 +1590,8 @@ RVB_API void rvb_model_destroy(rvb_model* m) {
     delete[] m->tickets;
   }
   rvb_decoder_cache_end(m);
+  if (m->s_search) cudaStreamDestroy(m->s_search);
+  if (m->ev_topk) cudaEventDestroy(m->ev_topk);
   m->pin_a.release();
   m->pin_b.release();
   m->pin_c.release();
