@@ -24,12 +24,12 @@ __device__ __forceinline__ void store_pair4(bf16* row, int col, int width, bool 
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row cached in registers (NV float4 per lane), two-pass variance like ATen.
 // reference: nn.LayerNorm uses of transformer/encoder_layer.py:149-159, encoder.py:107, decoder_layer.py:53-55,241-243
-template <int NV>
+template <int NV, bool X3>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps, int M, int d,
                                                         bf16* __restrict__ out_bf16, float* __restrict__ out_f32,
                                                         const int* __restrict__ row_lens, int rows_per_batch,
-                                                        int mask_rows, int x3) {
+                                                        int mask_rows) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       o.w = (v[i].w - mean) * rstd * g.w + bb.w;
       if (masked) o = make_float4(0.f, 0.f, 0.f, 0.f);
       if (out_f32) reinterpret_cast<float4*>(out_f32 + (long long)warp * d)[idx] = o;
-      if (out_bf16) store_pair4(out_bf16 + (long long)warp * d * (x3 ? 2 : 1), 4 * idx, d, x3 != 0, o);
+      if (out_bf16) store_pair4(out_bf16 + (long long)warp * d * (X3 ? 2 : 1), 4 * idx, d, X3, o);
     }
   }
 }
@@ -89,9 +89,13 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
   const int grid = (M + 7) / 8;
   const int nv = (d / 4 + 31) / 32;
   if (rows_per_batch <= 0) rows_per_batch = M;
-#define RVB_LN(NV)                                                                                           \
-  layernorm_kernel<NV><<<grid, 256, 0, stream>>>(x, gamma, beta, eps, M, d, out_bf16, out_f32, row_lens,     \
-                                                 rows_per_batch, mask_rows, x3)
+#define RVB_LN(NV)                                                                                                  \
+  do {                                                                                                              \
+    if (x3) layernorm_kernel<NV, true><<<grid, 256, 0, stream>>>(x, gamma, beta, eps, M, d, out_bf16, out_f32, row_lens, \
+                                                                 rows_per_batch, mask_rows);                        \
+    else layernorm_kernel<NV, false><<<grid, 256, 0, stream>>>(x, gamma, beta, eps, M, d, out_bf16, out_f32, row_lens,   \
+                                                               rows_per_batch, mask_rows);                          \
+  } while (0)
   if (nv <= 1) RVB_LN(1);
   else if (nv <= 2) RVB_LN(2);
   else if (nv <= 4) RVB_LN(4);
@@ -106,12 +110,12 @@ int launch_layernorm(const float* x, const float* gamma, const float* beta, floa
 
 // x2 = LN_a(x) (+ y_add) ; n = LN_b(x2).  Fuses `norm_final` of block i (and the LSL `x = x + y`,
 // encoder_layer.py:397-400) with the first pre-norm of block i+1 (or encoder.after_norm): one read, two writes.
-template <int NV>
+template <int NV, bool X3>
 __global__ void __launch_bounds__(256)
 double_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ ba,
                         const float* __restrict__ y_add, float* __restrict__ x2, const float* __restrict__ gb,
                         const float* __restrict__ bb, float eps, int M, int d, bf16* __restrict__ n_out,
-                        float* __restrict__ n_out_f32, int x3) {
+                        float* __restrict__ n_out_f32) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= M) return;
@@ -188,7 +192,7 @@ double_layernorm_kernel(const float* __restrict__ x, const float* __restrict__ g
       o.z = (v[i].z - mean) * rstd * g.z + b4.z;
       o.w = (v[i].w - mean) * rstd * g.w + b4.w;
       if (n_out_f32) reinterpret_cast<float4*>(n_out_f32 + (long long)warp * d)[idx] = o;
-      if (n_out) store_pair4(n_out + (long long)warp * d * (x3 ? 2 : 1), 4 * idx, d, x3 != 0, o);
+      if (n_out) store_pair4(n_out + (long long)warp * d * (X3 ? 2 : 1), 4 * idx, d, X3, o);
     }
   }
 }
@@ -200,8 +204,11 @@ int launch_double_layernorm(const float* x, const float* ga, const float* ba, co
   if (M <= 0) return 0;
   const int grid = (M + 7) / 8;
   const int nv = (d / 4 + 31) / 32;
-#define RVB_DLN(NV) \
-  double_layernorm_kernel<NV><<<grid, 256, 0, stream>>>(x, ga, ba, y_add, x2, gb, bb, eps, M, d, n_out, n_out_f32, x3)
+#define RVB_DLN(NV)                                                                                                     \
+  do {                                                                                                                  \
+    if (x3) double_layernorm_kernel<NV, true><<<grid, 256, 0, stream>>>(x, ga, ba, y_add, x2, gb, bb, eps, M, d, n_out, n_out_f32); \
+    else double_layernorm_kernel<NV, false><<<grid, 256, 0, stream>>>(x, ga, ba, y_add, x2, gb, bb, eps, M, d, n_out, n_out_f32);   \
+  } while (0)
   if (nv <= 1) RVB_DLN(1);
   else if (nv <= 2) RVB_DLN(2);
   else if (nv <= 4) RVB_DLN(4);
@@ -478,11 +485,11 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
 }
 
 // y = SiLU(LN(conv_out)) with mean / variance from the accumulated (sum, sum of squares): one warp per frame
-template <int NV>
+template <int NV, bool X3>
 __global__ void __launch_bounds__(256)
 conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restrict__ stats, int nslice,
                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, long long M, int C,
-                      bf16* __restrict__ out, int x3) {
+                      bf16* __restrict__ out) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -505,13 +512,13 @@ conv_norm_silu_kernel(const float* __restrict__ conv_out, const float* __restric
       const float4 bb = __ldg(reinterpret_cast<const float4*>(beta) + idx);
       float4 y = make_float4((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y,
                              (v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w);
-      if (x3) {  // accurate mode: exact exp / division
+      if constexpr (X3) {  // accurate mode: exact exp / division
         y = make_float4(y.x / (1.f + expf(-y.x)), y.y / (1.f + expf(-y.y)), y.z / (1.f + expf(-y.z)),
                         y.w / (1.f + expf(-y.w)));
       } else {
         y = make_float4(silu_f(y.x), silu_f(y.y), silu_f(y.z), silu_f(y.w));
       }
-      store_pair4(out + row * C * (x3 ? 2 : 1), 4 * idx, C, x3 != 0, y);
+      store_pair4(out + row * C * (X3 ? 2 : 1), 4 * idx, C, X3, y);
     }
   }
 }
@@ -545,12 +552,18 @@ int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, cons
     const long long M = (long long)B * T;
     const int nv = (C / 4 + 31) / 32;
     const unsigned g2 = (unsigned)((M + 7) / 8);
-    if (nv <= 1) conv_norm_silu_kernel<1><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
-    else if (nv <= 2) conv_norm_silu_kernel<2><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
-    else if (nv <= 4) conv_norm_silu_kernel<4><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
-    else if (nv <= 8) conv_norm_silu_kernel<8><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
-    else if (nv <= 16) conv_norm_silu_kernel<16><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
-    else conv_norm_silu_kernel<32><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out, x3);
+#define RVB_CNS(NV)                                                                                                        \
+  do {                                                                                                                    \
+    if (x3) conv_norm_silu_kernel<NV, true><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);  \
+    else conv_norm_silu_kernel<NV, false><<<g2, 256, 0, stream>>>(conv_tmp, stats, nslice, norm_w, norm_b, eps, M, C, out);    \
+  } while (0)
+    if (nv <= 1) RVB_CNS(1);
+    else if (nv <= 2) RVB_CNS(2);
+    else if (nv <= 4) RVB_CNS(4);
+    else if (nv <= 8) RVB_CNS(8);
+    else if (nv <= 16) RVB_CNS(16);
+    else RVB_CNS(32);
+#undef RVB_CNS
     RVB_COUNT_LAUNCH();
     RVB_CHECK_LAUNCH();
   }

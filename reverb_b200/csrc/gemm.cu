@@ -287,7 +287,10 @@ __device__ __forceinline__ long long output_row(const GemmKParams& p, const Tile
 // made the LSU, not HBM, the limit of the residual GEMMs (out += alpha * (acc + bias) reads AND writes 128 B/row/chunk).
 // The residual loads are software-pipelined: the first chunk's residual is requested BEFORE the wait on the
 // accumulator barrier and chunk c+1's while chunk c is being converted.
-template <int EPI>
+// PAIR (compile time): bf16 outputs are written as the accurate mode's (hi, lo) pair, lo at column + p.out_split, and
+// SiLU / GLU use exact exp / division — kept out of the throughput kernels (PAIR = false) so that their epilogue is the
+// straight-line code it was before the accurate mode existed (a run-time flag cost the SiLU GEMM 28 %).
+template <int EPI, bool PAIR>
 __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord& t, int q, int lane, uint32_t taddr,
                                            int c0, int c1, uint64_t* tfull_bar, uint32_t aphase, float* stage) {
   const long long orow = output_row(p, t, q * 32 + lane);
@@ -387,8 +390,8 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
 #pragma unroll 1
       for (int c = c0; c < c1; c += 128) {
         if (n0_tile + c >= p.N) break;
-        // out_split > 0 (bf16x3): the tile is written twice, first the hi halves, then the residues lo = v - hi
-        const int nparts = p.out_split > 0 ? 2 : 1;
+        // PAIR (bf16x3): the tile is written twice, first the hi halves, then the residues lo = v - hi
+        constexpr int nparts = PAIR ? 2 : 1;
 #pragma unroll 1
         for (int part = 0; part < nparts; ++part) {
 #pragma unroll 1
@@ -415,7 +418,7 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
               const float2 g01 = ffma2(make_float2(__uint_as_float(gv[e + 0]), __uint_as_float(gv[e + 1])), one2, make_float2(bg.x, bg.y));
               const float2 g23 = ffma2(make_float2(__uint_as_float(gv[e + 2]), __uint_as_float(gv[e + 3])), one2, make_float2(bg.z, bg.w));
               float2 o01, o23;
-              if (nparts == 2) {  // accurate mode: exact division / exp instead of the ex2 / rcp approximations
+              if constexpr (PAIR) {  // accurate mode: exact division / exp instead of the ex2 / rcp approximations
                 o01 = make_float2(a01.x / (1.f + expf(-g01.x)), a01.y / (1.f + expf(-g01.y)));
                 o23 = make_float2(a23.x / (1.f + expf(-g23.x)), a23.y / (1.f + expf(-g23.y)));
               } else {
@@ -427,7 +430,7 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
               v[4 * h2 + 2] = o23.x;
               v[4 * h2 + 3] = o23.y;
             }
-            if (part == 1) {
+            if (PAIR && part == 1) {
 #pragma unroll
               for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16(v[e]));
             }
@@ -442,7 +445,7 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + rsub;
           const uint4 u = *reinterpret_cast<const uint4*>(stage_u + row * 32 + ((slot ^ (row & 7)) << 2));
-          if (ro[it] >= 0) *reinterpret_cast<uint4*>(out + ro[it] + (c >> 1) + part * p.out_split) = u;
+          if (ro[it] >= 0) *reinterpret_cast<uint4*>(out + ro[it] + (c >> 1) + (PAIR ? part * p.out_split : 0)) = u;
         }
         __syncwarp();
         }
@@ -483,8 +486,8 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
         tmem_ld_32x32(taddr + c + 32, acc + 32);
         tmem_ld_wait();
         const int n0 = n0_tile + c;
-        // out_split > 0 (bf16x3): the tile is written twice, first hi = bf16(v), then the residue lo = bf16(v - hi)
-        const int nparts = p.out_split > 0 ? 2 : 1;
+        // PAIR (bf16x3): the tile is written twice, first hi = bf16(v), then the residue lo = bf16(v - hi)
+        constexpr int nparts = PAIR ? 2 : 1;
 #pragma unroll 1
         for (int part = 0; part < nparts; ++part) {
 #pragma unroll
@@ -501,7 +504,7 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
             float2 hi = ffma2(make_float2(__uint_as_float(acc[8 * j + 4 * h + 2]), __uint_as_float(acc[8 * j + 4 * h + 3])),
                               one2, make_float2(b4.z, b4.w));
             if (EPI == EPI_BF16_SILU) {
-              if (nparts == 2) {  // accurate mode: exact exp / division
+              if constexpr (PAIR) {  // accurate mode: exact exp / division
                 lo = make_float2(lo.x / (1.f + expf(-lo.x)), lo.y / (1.f + expf(-lo.y)));
                 hi = make_float2(hi.x / (1.f + expf(-hi.x)), hi.y / (1.f + expf(-hi.y)));
               } else {
@@ -518,7 +521,7 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
-          if (part == 1) {
+          if (PAIR && part == 1) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16(v[e]));
           }
@@ -533,7 +536,8 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
         for (int it = 0; it < 8; ++it) {
           const int row = it * 4 + rsub;
           const uint4 u = *reinterpret_cast<const uint4*>(stage_u + row * 32 + ((slot ^ (row & 7)) << 2));
-          if (ro[it] >= 0 && p.debug_skip_epi != 2) *reinterpret_cast<uint4*>(out + ro[it] + c + part * p.out_split) = u;
+          if (ro[it] >= 0 && p.debug_skip_epi != 2)
+            *reinterpret_cast<uint4*>(out + ro[it] + c + (PAIR ? part * p.out_split : 0)) = u;
         }
         __syncwarp();
         }
@@ -652,7 +656,7 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const GemmKParams p) {
@@ -763,7 +767,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t as = 0, aphase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       TileCoord t = decode_tile(p, tile, BN);
-      drain_tile<EPI>(p, t, q, lane, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, chalf * ccols,
+      drain_tile<EPI, PAIR>(p, t, q, lane, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, chalf * ccols,
                       (chalf + 1) * ccols, &tfull[as], aphase, stage);
       tc_fence_before();
       __syncwarp();
@@ -799,7 +803,7 @@ struct Gemm2Cfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool PAIR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const GemmKParams p) {
@@ -930,7 +934,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t as = 0, aphase = 0;
     for (int tile = cluster_id; tile < p.num_tiles; tile += num_clusters) {
       TileCoord t = tile_coord(tile);
-      drain_tile<EPI>(p, t, q, lane, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, chalf * ccols,
+      drain_tile<EPI, PAIR>(p, t, q, lane, tmem_base + ((uint32_t)(q * 32) << 16) + as * BN, chalf * ccols,
                       (chalf + 1) * ccols, &tfull[as], aphase, stage);
       tc_fence_before();
       __syncwarp();
@@ -1141,15 +1145,16 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     if (make_tmap(&tmB, a.W, 2, dims, str, box)) return -1;
   }
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmKParams) = nullptr;
+  const bool pair = a.out_split > 0;
   switch (select_epi(a.act, a.out_mode)) {
-    case EPI_BF16: kern = gemm_tc_kernel<BN, EPI_BF16>; break;
-    case EPI_BF16_RELU: kern = gemm_tc_kernel<BN, EPI_BF16_RELU>; break;
-    case EPI_BF16_SILU: kern = gemm_tc_kernel<BN, EPI_BF16_SILU>; break;
-    case EPI_F32: kern = gemm_tc_kernel<BN, EPI_F32>; break;
-    case EPI_RESID: kern = gemm_tc_kernel<BN, EPI_RESID>; break;
-    case EPI_GLU: kern = gemm_tc_kernel<BN, EPI_GLU>; break;
-    case EPI_LSE: kern = gemm_tc_kernel<BN, EPI_LSE>; break;
-    default: kern = gemm_tc_kernel<BN, EPI_GENERIC>; break;
+    case EPI_BF16: kern = pair ? gemm_tc_kernel<BN, EPI_BF16, true> : gemm_tc_kernel<BN, EPI_BF16, false>; break;
+    case EPI_BF16_RELU: kern = pair ? gemm_tc_kernel<BN, EPI_BF16_RELU, true> : gemm_tc_kernel<BN, EPI_BF16_RELU, false>; break;
+    case EPI_BF16_SILU: kern = pair ? gemm_tc_kernel<BN, EPI_BF16_SILU, true> : gemm_tc_kernel<BN, EPI_BF16_SILU, false>; break;
+    case EPI_F32: kern = gemm_tc_kernel<BN, EPI_F32, false>; break;
+    case EPI_RESID: kern = gemm_tc_kernel<BN, EPI_RESID, false>; break;
+    case EPI_GLU: kern = pair ? gemm_tc_kernel<BN, EPI_GLU, true> : gemm_tc_kernel<BN, EPI_GLU, false>; break;
+    case EPI_LSE: kern = gemm_tc_kernel<BN, EPI_LSE, false>; break;
+    default: kern = gemm_tc_kernel<BN, EPI_GENERIC, false>; break;
   }
   RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
   p.tiles_n = (a.N + BN - 1) / BN;
@@ -1201,15 +1206,16 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     if (make_tmap(&tmB, a.W, 2, dims, str, box)) return -1;
   }
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmKParams) = nullptr;
+  const bool pair = a.out_split > 0;
   switch (select_epi(a.act, a.out_mode)) {
-    case EPI_BF16: kern = gemm_tc2_kernel<BN, EPI_BF16>; break;
-    case EPI_BF16_RELU: kern = gemm_tc2_kernel<BN, EPI_BF16_RELU>; break;
-    case EPI_BF16_SILU: kern = gemm_tc2_kernel<BN, EPI_BF16_SILU>; break;
-    case EPI_F32: kern = gemm_tc2_kernel<BN, EPI_F32>; break;
-    case EPI_RESID: kern = gemm_tc2_kernel<BN, EPI_RESID>; break;
-    case EPI_GLU: kern = gemm_tc2_kernel<BN, EPI_GLU>; break;
-    case EPI_LSE: kern = gemm_tc2_kernel<BN, EPI_LSE>; break;
-    default: kern = gemm_tc2_kernel<BN, EPI_GENERIC>; break;
+    case EPI_BF16: kern = pair ? gemm_tc2_kernel<BN, EPI_BF16, true> : gemm_tc2_kernel<BN, EPI_BF16, false>; break;
+    case EPI_BF16_RELU: kern = pair ? gemm_tc2_kernel<BN, EPI_BF16_RELU, true> : gemm_tc2_kernel<BN, EPI_BF16_RELU, false>; break;
+    case EPI_BF16_SILU: kern = pair ? gemm_tc2_kernel<BN, EPI_BF16_SILU, true> : gemm_tc2_kernel<BN, EPI_BF16_SILU, false>; break;
+    case EPI_F32: kern = gemm_tc2_kernel<BN, EPI_F32, false>; break;
+    case EPI_RESID: kern = gemm_tc2_kernel<BN, EPI_RESID, false>; break;
+    case EPI_GLU: kern = pair ? gemm_tc2_kernel<BN, EPI_GLU, true> : gemm_tc2_kernel<BN, EPI_GLU, false>; break;
+    case EPI_LSE: kern = gemm_tc2_kernel<BN, EPI_LSE, false>; break;
+    default: kern = gemm_tc2_kernel<BN, EPI_GENERIC, false>; break;
   }
   RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
   p.tiles_n = (a.N + BN - 1) / BN;

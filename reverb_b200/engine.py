@@ -197,6 +197,8 @@ class Engine:
         """(B, N) equal-length recordings (float32 or int16, on the device) -> (B, m, 80) float32, one launch."""
         assert waves.is_cuda and waves.dim() == 2 and waves.stride(1) == 1
         B, n = waves.shape
+        if B == 1 and waves.stride(0) < n:        # a size-1 dimension may carry any stride
+            waves = waves.reshape(-1).view(1, n)
         m = int(self.lib.rvb_fbank_num_frames(n))
         feats = torch.empty((B, m, 80), dtype=torch.float32, device=waves.device)
         if waves.dtype not in (torch.int16, torch.float32):
