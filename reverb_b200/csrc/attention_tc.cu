@@ -49,6 +49,13 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
+// Blackwell FMNMX3: max of three in one ALU instruction (halves the instruction count of the row maximum)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -77,7 +84,7 @@ struct AttnTcParams {
 //     tile maxima / row sums meet through shared memory and a 64-thread named barrier.  Measured slightly SLOWER than
 //     SW = 4 (0.403 vs 0.388 ms per encoder layer): the kernel is not short of warps; what bounds it is the
 //     ex2 + issue budget per tile and the per-tile hand-offs, which the split duplicates.
-template <int BN, int SW>
+template <int BN, int SW, bool PF>
 __global__ void __launch_bounds__(32 * (SW + 1), AtCfg<BN>::CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -244,19 +251,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int c0 = hh * CW, ob = hh * OW;
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory"); };
     float m_run = -INFINITY, row_sum = 0.f;  // m_run stays -inf until the row has seen a visible key
-    for (int j = 0; j < ntiles; ++j) {
-      const int sb = j % AT_NS, pb = j & 1;
+    // The thread's part of an S row is pulled out of TMEM with back-to-back loads and ONE wait.  PF (prefetch): the loads
+    // of tile j+1 are issued BEFORE the arithmetic of tile j (two register copies of the row, swapped every tile), so the
+    // TMEM latency and the wait for QK(j+1) overlap the exponentials of tile j instead of preceding those of tile j+1.
+    auto pull = [&](int j, uint32_t(&dst)[CW]) {
+      const int sb = j % AT_NS;
       mbar_wait(&s_full[sb], (j / AT_NS) & 1);
       tc_fence_after();
-      // the thread's part of the S row is pulled out of TMEM with back-to-back loads and ONE wait, so the TMEM latency
-      // is paid once per tile and the S buffer is handed back to the MMA issuer as early as possible
-      uint32_t sv[CW];
 #pragma unroll
-      for (int c = 0; c < CW; c += 32) tmem_ld_32x32(s_col(sb) + lane_addr + c0 + c, sv + c);
+      for (int c = 0; c < CW; c += 32) tmem_ld_32x32(s_col(sb) + lane_addr + c0 + c, dst + c);
+    };
+    auto tile = [&](int j, uint32_t(&sv)[CW], uint32_t(&nx)[CW]) {
+      const int sb = j % AT_NS, pb = j & 1;
+      if (!PF) pull(j, sv);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      if (lane == 0) mbar_arrive(&s_empty[sb]);   // the S buffer goes back to the MMA issuer as early as possible
+      if (PF && j + 1 < ntiles) pull(j + 1, nx);
       const uint32_t bias_addr = smem_u32(s_bias + j * AT_BN + c0);
       // x = s * scale*log2e + key bias (masked keys: -inf), kept in place of the raw scores; tile maximum
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
@@ -273,10 +285,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         sv[e + 1] = __float_as_uint(x01.y);
         sv[e + 2] = __float_as_uint(x23.x);
         sv[e + 3] = __float_as_uint(x23.y);
-        mx[0] = fmaxf(mx[0], x01.x);
-        mx[1] = fmaxf(mx[1], x01.y);
-        mx[2] = fmaxf(mx[2], x23.x);
-        mx[3] = fmaxf(mx[3], x23.y);
+        mx[(e >> 2) & 3] = fmax3(mx[(e >> 2) & 3], x01.x, x01.y);
+        mx[((e >> 2) + 2) & 3] = fmax3(mx[((e >> 2) + 2) & 3], x23.x, x23.y);
       }
       float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       if (p.chunk > 0) {
@@ -329,41 +339,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       float2 sm01 = make_float2(0.f, 0.f), sm23 = make_float2(0.f, 0.f);
-      uint32_t pk[CW / 2];
       const float m_eff = (m_run == -INFINITY) ? 0.f : m_run;  // no visible key yet: every x is -inf -> p = 0
       const float2 one2 = make_float2(1.f, 1.f), negm2 = make_float2(-m_eff, -m_eff);
+      // P~ goes to shared memory chunk by chunk (8 keys = 16 bytes) as it is produced, so only one chunk of packed
+      // probabilities is ever live in registers.  The buffer was last read by PV(j-2), which has had a whole tile of
+      // exponentials to retire: this wait is practically free.
+      mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
 #pragma unroll
-      for (int e = 0; e < CW; e += 4) {
-        // x - m and the running sums as packed FFMA2 (x * 1 + (-m), p * 1 + sum: exact)
-        const float2 d01 = ffma2(make_float2(__uint_as_float(sv[e + 0]), __uint_as_float(sv[e + 1])), one2, negm2);
-        const float2 d23 = ffma2(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), one2, negm2);
-        const float2 p01 = make_float2(fast_exp2(d01.x), fast_exp2(d01.y));
-        const float2 p23 = make_float2(fast_exp2(d23.x), fast_exp2(d23.y));
-        sm01 = ffma2(p01, one2, sm01);
-        sm23 = ffma2(p23, one2, sm23);
-        pk[(e >> 1) + 0] = pack_bf16x2(p01.x, p01.y);
-        pk[(e >> 1) + 1] = pack_bf16x2(p23.x, p23.y);
+      for (int e = 0; e < CW; e += 8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          // x - m and the running sums as packed FFMA2 (x * 1 + (-m), p * 1 + sum: exact)
+          const int f = e + 4 * q;
+          const float2 d01 = ffma2(make_float2(__uint_as_float(sv[f + 0]), __uint_as_float(sv[f + 1])), one2, negm2);
+          const float2 d23 = ffma2(make_float2(__uint_as_float(sv[f + 2]), __uint_as_float(sv[f + 3])), one2, negm2);
+          const float2 p01 = make_float2(fast_exp2(d01.x), fast_exp2(d01.y));
+          const float2 p23 = make_float2(fast_exp2(d23.x), fast_exp2(d23.y));
+          sm01 = ffma2(p01, one2, sm01);
+          sm23 = ffma2(p23, one2, sm23);
+          w[2 * q + 0] = pack_bf16x2(p01.x, p01.y);
+          w[2 * q + 1] = pack_bf16x2(p23.x, p23.y);
+        }
+        // 8 keys = one 16-byte chunk of this row inside K-block (key / 64); SWIZZLE_128B: chunk ^= row % 8
+        const int kc = c0 + e;
+        uint8_t* blk = sP + pb * AT_P_BYTES + (kc >> 6) * AT_Q_BYTES + r * 128;
+        const int ch = ((kc & 63) >> 3) ^ (r & 7);
+        *reinterpret_cast<uint4*>(blk + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       const float sm[4] = {sm01.x, sm01.y, sm23.x, sm23.y};
       row_sum += (sm[0] + sm[1]) + (sm[2] + sm[3]);
-      // the P~ buffer is only needed now: PV(j-2), which read it last, has had a whole tile of exponentials to retire
-      mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
-#pragma unroll
-      for (int c = 0; c < CW; c += 32) {
-        // 32 keys = four 16-byte chunks of this row inside K-block (key / 64); SWIZZLE_128B: chunk ^= row % 8
-        const int kc = c0 + c;
-        uint8_t* blk = sP + pb * AT_P_BYTES + (kc >> 6) * AT_Q_BYTES + r * 128;
-        const int ch0 = (kc & 63) >> 3;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int ch = (ch0 + q) ^ (r & 7);
-          const uint32_t* w = pk + (c >> 1) + 4 * q;
-          *reinterpret_cast<uint4*>(blk + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-      }
       fence_proxy_async();  // generic-proxy writes of P~ -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[pb]);
+    };
+    {
+      uint32_t sva[CW], svb[CW];
+      if (PF && ntiles > 0) pull(0, sva);
+#pragma unroll 1
+      for (int j = 0; j < ntiles; j += 2) {
+        tile(j, sva, svb);
+        if (j + 1 < ntiles) tile(j + 1, svb, sva);
+      }
     }
     // ---- epilogue: O / row_sum -> bf16 -> global
     if (SPLIT) {
@@ -566,20 +583,31 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
     const size_t smem = AtCfg<128>::SMEM_FIXED + (size_t)((a.Tk + 127) / 128) * 128 * sizeof(float);
     RVB_REQUIRE(smem <= 227 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
     static DynSmemOptIn optin;
-    if (optin.ensure(attention_tc_kernel<128, 4>, smem)) return -1;
-    attention_tc_kernel<128, 4><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    if (optin.ensure(attention_tc_kernel<128, 4, false>, smem)) return -1;
+    attention_tc_kernel<128, 4, false><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
   } else if (sw_sel == 4) {
     const size_t smem = AtCfg<64>::SMEM_FIXED + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
     RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
-    static DynSmemOptIn optin;
-    if (optin.ensure(attention_tc_kernel<64, 4>, smem)) return -1;
-    attention_tc_kernel<64, 4><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    static int pf_sel = -1;   // RVB_ATTN_PF=1: S-tile prefetch variant (A/B aid; off until it wins on the GPU)
+    if (pf_sel < 0) {
+      const char* e = getenv("RVB_ATTN_PF");
+      pf_sel = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    if (pf_sel) {
+      static DynSmemOptIn optin;
+      if (optin.ensure(attention_tc_kernel<64, 4, true>, smem)) return -1;
+      attention_tc_kernel<64, 4, true><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    } else {
+      static DynSmemOptIn optin;
+      if (optin.ensure(attention_tc_kernel<64, 4, false>, smem)) return -1;
+      attention_tc_kernel<64, 4, false><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    }
   } else {
     const size_t smem = AtCfg<64>::SMEM_FIXED + 3072 + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
     RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
     static DynSmemOptIn optin;
-    if (optin.ensure(attention_tc_kernel<64, 8>, smem)) return -1;
-    attention_tc_kernel<64, 8><<<grid, 288, smem, stream>>>(tmQ, tmK, tmV, p);
+    if (optin.ensure(attention_tc_kernel<64, 8, false>, smem)) return -1;
+    attention_tc_kernel<64, 8, false><<<grid, 288, smem, stream>>>(tmQ, tmK, tmV, p);
   }
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
