@@ -56,6 +56,11 @@ attention_f32_kernel(AttnF32Args a) {
   if (a.k_lens) klen = min(klen, a.k_lens[g]);
   // visible keys [lo, hi): key-length mask, causal (chunk = 1) or streaming chunk mask (utils/mask.py:88-123)
   int lo = 0, hi = klen;
+  const int* klist = nullptr;  // prefix-tree attention: explicit key rows (the node's ancestors)
+  if (a.key_list) {
+    klist = a.key_list + ((long long)g * a.Tq + i) * a.key_list_ld;
+    hi = min(a.Tk, a.key_list_len[(long long)g * a.Tq + i]);
+  }
   if (a.chunk > 0) {
     hi = min(hi, (i / a.chunk + 1) * a.chunk);
     if (a.left >= 0) lo = max(0, (i / a.chunk - a.left) * a.chunk);
@@ -72,7 +77,8 @@ attention_f32_kernel(AttnF32Args a) {
   for (int j = lo + lane; j < hi; j += 32) {   // only the visible keys [lo, hi) are ever touched
     float s = -INFINITY;
     {
-      const bf16* krow = a.k + ((long long)g * a.Tk + j) * a.ldk + h * a.dk;
+      const long long kr = klist ? (long long)klist[j] : (long long)g * a.Tk + j;
+      const bf16* krow = a.k + kr * a.ldk + h * a.dk;
       float ac = 0.f, bd = 0.f;
       for (int c = 0; c < a.dk; c += 8) ac = dot8_pair(qu + c, krow + c, a.k_lo, ac);
       if (a.p) {
@@ -98,7 +104,8 @@ attention_f32_kernel(AttnF32Args a) {
   for (int c = lane; c < a.dk; c += 32) {
     float o = 0.f;
     for (int j = lo; j < hi; ++j) {
-      const bf16* vrow = a.v + ((long long)g * a.Tk + j) * a.ldv + h * a.dk;
+      const long long vr = klist ? (long long)klist[j] : (long long)g * a.Tk + j;
+      const bf16* vrow = a.v + vr * a.ldv + h * a.dk;
       o = fmaf(sc[j] * inv, ld_pair(vrow + c, a.v_lo), o);
     }
     const bf16 hh = __float2bfloat16(o);

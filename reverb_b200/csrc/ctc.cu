@@ -732,4 +732,203 @@ int launch_lse_merge(const float2* part, int slabs, const float* tgt, const int*
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Prefix-TREE attention rescoring.  The reference decodes each of the N hypotheses of an utterance on its own
+// (search.py:382-411, asr_model.py:895 repeats the memory N times), although the n-best of a prefix beam search share
+// most of their prefixes and a causal decoder gives identical outputs for identical prefixes.  Here the decoder runs
+// once per DISTINCT prefix ("node" of the utterance's prefix tree): rows = nodes (~6x fewer than hypotheses x positions
+// on real n-best lists), self-attention over the node's ancestors, and every (hypothesis, position) score is read from
+// the edge it walks.  Same arithmetic per row as the flat path, so the scores agree to rounding.
+//
+// trie_build_kernel — one CTA per utterance.  Hypotheses are inserted in n-best order; hypothesis i shares the nodes of
+// the earlier hypothesis with the longest common prefix and appends new nodes for the rest.
+//   node 0 = the empty prefix (decoder input <sos>, depth 0); a node at depth j carries token w_j.
+//   node_of[(b*N + i) * nstride + j] = node of the first j tokens of hypothesis i (j = 0 .. U_i).
+// reverse != 0: the hypotheses are read back to front (right-to-left decoder, asr_model.py:921-949).
+__global__ void __launch_bounds__(128)
+trie_build_kernel(const int* __restrict__ tok, int tok_stride, const int* __restrict__ olen,
+                  const int* __restrict__ nhyp, int N, int reverse, int sos, int* __restrict__ node_of, int nstride,
+                  int* __restrict__ node_tok, int* __restrict__ node_par, int* __restrict__ node_dep, int cap,
+                  int* __restrict__ n_nodes) {
+  __shared__ int s_lcp[16];
+  __shared__ int s_next, s_best, s_bestlen;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n = min(nhyp[b], N);
+  int* ntok = node_tok + (size_t)b * cap;
+  int* npar = node_par + (size_t)b * cap;
+  int* ndep = node_dep + (size_t)b * cap;
+  if (tid == 0) {
+    ntok[0] = sos;
+    npar[0] = -1;
+    ndep[0] = 0;
+    s_next = 1;
+  }
+  __syncthreads();
+  auto len_of = [&](int i) { return i < n ? olen[2 * ((size_t)b * N + i)] : 0; };
+  auto tok_of = [&](int i, int U, int j) {  // j-th token (0-based) of hypothesis i in decoding order
+    const int* w = tok + ((size_t)b * N + i) * tok_stride;
+    return reverse ? w[U - 1 - j] : w[j];
+  };
+  for (int i = 0; i < N; ++i) {
+    const int U = len_of(i);
+    int* mine = node_of + ((size_t)b * N + i) * nstride;
+    // longest common prefix with every earlier hypothesis (one warp per earlier hypothesis)
+    for (int ip = warp; ip < i; ip += 4) {
+      const int Up = len_of(ip), lim = min(U, Up);
+      int first = lim;
+      for (int j = lane; j < lim; j += 32)
+        if (tok_of(i, U, j) != tok_of(ip, Up, j)) {
+          first = j;
+          break;
+        }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+      if (lane == 0) s_lcp[ip] = first;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int best = -1, bl = 0;
+      for (int ip = 0; ip < i; ++ip)
+        if (s_lcp[ip] > bl) {
+          bl = s_lcp[ip];
+          best = ip;
+        }
+      s_best = best;
+      s_bestlen = bl;
+    }
+    __syncthreads();
+    const int L = s_bestlen, base = s_next;
+    const int* theirs = node_of + ((size_t)b * N + (s_best < 0 ? 0 : s_best)) * nstride;
+    for (int j = tid; j <= U; j += blockDim.x) {
+      if (j == 0) mine[0] = 0;
+      else if (j <= L) mine[j] = theirs[j];
+      else {
+        const int id = base + (j - L - 1);
+        mine[j] = id;
+        ntok[id] = tok_of(i, U, j - 1);
+        ndep[id] = j;
+        npar[id] = (j == L + 1) ? (L == 0 ? 0 : theirs[L]) : id - 1;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) s_next = base + (U - L);
+    __syncthreads();
+  }
+  if (tid == 0) n_nodes[b] = s_next;
+}
+
+int launch_trie_build(const int* tok, int tok_stride, const int* olen, const int* nhyp, int B, int N, int reverse, int sos,
+                      int* node_of, int nstride, int* node_tok, int* node_par, int* node_dep, int cap, int* n_nodes,
+                      cudaStream_t stream) {
+  RVB_REQUIRE(N >= 1 && N <= 16, "trie_build: beam %d unsupported", N);
+  if (B <= 0) return 0;
+  trie_build_kernel<<<B, 128, 0, stream>>>(tok, tok_stride, olen, nhyp, N, reverse, sos, node_of, nstride, node_tok,
+                                           node_par, node_dep, cap, n_nodes);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+// trie_inputs_kernel — one CTA per utterance, once the host knows P (node slots per utterance) and Lp:
+//   rows r = b*P + node:   tok_in[r], pos[r] (depth), anc[r*Lp + t] = row of the ancestor at depth t (t <= depth),
+//                          alen[r] = depth + 1;  unused slots: <eos> at position 0 attending only themselves
+//   score rows e = b*(P+N) + slot:  slot < P: the edge INTO node `slot` (src = its parent's row, target = its token),
+//                          slot P + i: hypothesis i ends (src = its last node, target = <eos>);  -1 target = unused
+//   smap[(b*N + i)*Lp + j] = score row of position j of hypothesis i (j <= U_i), else -1
+__global__ void __launch_bounds__(256)
+trie_inputs_kernel(const int* __restrict__ node_of, int nstride, const int* __restrict__ node_tok,
+                   const int* __restrict__ node_par, const int* __restrict__ node_dep, int cap,
+                   const int* __restrict__ n_nodes, const int* __restrict__ olen, const int* __restrict__ nhyp, int N,
+                   int P, int Lp, int eos, int* __restrict__ tok_in, int* __restrict__ pos, int* __restrict__ anc,
+                   int* __restrict__ alen, int* __restrict__ src, int* __restrict__ tgt, int* __restrict__ smap) {
+  const int b = blockIdx.x;
+  const int nn = n_nodes[b], n = min(nhyp[b], N);
+  const int* ntok = node_tok + (size_t)b * cap;
+  const int* npar = node_par + (size_t)b * cap;
+  const int* ndep = node_dep + (size_t)b * cap;
+  for (int node = threadIdx.x; node < P; node += blockDim.x) {
+    const size_t r = (size_t)b * P + node;
+    if (node < nn) {
+      const int dep = ndep[node];
+      tok_in[r] = ntok[node];
+      pos[r] = dep;
+      alen[r] = dep + 1;
+      int cur = node;
+      for (int t = dep; t >= 0; --t) {
+        anc[r * Lp + t] = b * P + cur;
+        cur = npar[cur];
+      }
+    } else {
+      tok_in[r] = eos;
+      pos[r] = 0;
+      alen[r] = 1;
+      anc[r * Lp] = (int)r;
+    }
+  }
+  for (int e = threadIdx.x; e < P + N; e += blockDim.x) {
+    const size_t sr = (size_t)b * (P + N) + e;
+    int s_ = b * P, t_ = -1;
+    if (e >= 1 && e < nn) {
+      s_ = b * P + npar[e];
+      t_ = ntok[e];
+    } else if (e >= P) {
+      const int i = e - P;
+      const int U = i < n ? olen[2 * ((size_t)b * N + i)] : 0;
+      s_ = b * P + node_of[((size_t)b * N + i) * nstride + U];
+      t_ = eos;
+    }
+    src[sr] = s_;
+    tgt[sr] = t_;
+  }
+  for (int q = threadIdx.x; q < N * Lp; q += blockDim.x) {
+    const int i = q / Lp, j = q - i * Lp;
+    const int U = i < n ? olen[2 * ((size_t)b * N + i)] : 0;
+    int mrow = -1;
+    if (j < U) mrow = b * (P + N) + node_of[((size_t)b * N + i) * nstride + j + 1];
+    else if (j == U) mrow = b * (P + N) + P + i;
+    smap[((size_t)b * N + i) * Lp + j] = mrow;
+  }
+}
+
+int launch_trie_inputs(const int* node_of, int nstride, const int* node_tok, const int* node_par, const int* node_dep,
+                       int cap, const int* n_nodes, const int* olen, const int* nhyp, int B, int N, int P, int Lp, int eos,
+                       int* tok_in, int* pos, int* anc, int* alen, int* src, int* tgt, int* smap, cudaStream_t stream) {
+  if (B <= 0) return 0;
+  trie_inputs_kernel<<<B, 256, 0, stream>>>(node_of, nstride, node_tok, node_par, node_dep, cap, n_nodes, olen, nhyp, N,
+                                            P, Lp, eos, tok_in, pos, anc, alen, src, tgt, smap);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+// out[r, :] = in[idx[r], :]  (rows of `width` bf16, 16-byte aligned)
+__global__ void gather_rows_kernel(const bf16* __restrict__ in, const int* __restrict__ idx, bf16* __restrict__ out,
+                                   int width) {
+  const uint4* a = reinterpret_cast<const uint4*>(in + (size_t)idx[blockIdx.x] * width);
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)blockIdx.x * width);
+  for (int i = threadIdx.x; i < width / 8; i += blockDim.x) o[i] = a[i];
+}
+int launch_gather_rows(const bf16* in, const int* idx, bf16* out, int rows, int width, cudaStream_t stream) {
+  RVB_REQUIRE(width % 8 == 0, "gather_rows: width %% 8 != 0");
+  if (rows <= 0) return 0;
+  gather_rows_kernel<<<rows, 128, 0, stream>>>(in, idx, out, width);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
+// out[i] = map[i] >= 0 ? vals[map[i]] : 0
+__global__ void gather_scores_kernel(const float* __restrict__ vals, const int* __restrict__ map, float* __restrict__ out,
+                                     long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = map[i] >= 0 ? vals[map[i]] : 0.f;
+}
+int launch_gather_scores(const float* vals, const int* map, float* out, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  gather_scores_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(vals, map, out, n);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
 }  // namespace rvb

@@ -703,6 +703,30 @@ int launch_embed_posenc(const int* tokens, const float* emb, int N, int L, int d
   return 0;
 }
 
+__global__ void embed_posenc_rows_kernel(const int* __restrict__ tok, const int* __restrict__ posv,
+                                         const float* __restrict__ emb, int d, float nlod, float* __restrict__ out) {
+  const int r = blockIdx.x;
+  const int pos = posv[r];
+  const int id = tok[r];
+  const float xs = sqrtf((float)d);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    int i2 = c & ~1;
+    float div = expf((float)i2 * nlod);
+    float ang = (float)pos * div;
+    float pe = (c & 1) ? cosf(ang) : sinf(ang);
+    out[(long long)r * d + c] = emb[(long long)id * d + c] * xs + pe;
+  }
+}
+
+int launch_embed_posenc_rows(const int* tokens, const int* pos, const float* emb, int R, int d, float* out,
+                             cudaStream_t stream) {
+  if (R <= 0) return 0;
+  embed_posenc_rows_kernel<<<R, 128, 0, stream>>>(tokens, pos, emb, d, (float)(-(log(10000.0) / (double)d)), out);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // KV cache of the autoregressive decoder step (engine.cu decoder_cache_step; reference decoder.py:191-234 keeps the layer
 // OUTPUTS of the previous positions and re-projects their keys / values each step — a key / value cache holds the

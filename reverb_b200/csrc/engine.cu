@@ -1220,6 +1220,170 @@ static int decoder_cache_step(rvb_model* m, const int* h_tokens, const int* h_pa
   return 0;
 }
 
+// 1 = prefix-tree rescoring (default), 0 = one decoder row per (hypothesis, position) (RVB_RESCORE=flat)
+static int rescore_trie() {
+  const char* e = getenv("RVB_RESCORE");   // read per call: tests / benchmarks flip it between calls
+  return (e && strcmp(e, "flat") == 0) ? 0 : 1;
+}
+
+// The teacher-forced decoder over the PREFIX TREE of every utterance's n-best (ctc.cu trie_build_kernel): R = B * P rows,
+// one per distinct prefix (P = node slots per utterance), instead of B * N * Lp.  d_scores (B*N, Lp): the same
+// per-(hypothesis, position) log-probabilities decoder_pass produces.
+struct TrieView {
+  const int* node_of;
+  int nstride;
+  const int* node_tok;
+  const int* node_par;
+  const int* node_dep;
+  int cap;
+  const int* n_nodes;
+};
+
+static int decoder_pass_trie(rvb_model* m, Decoder& D, const bf16* enc_bf, const int* d_enc_lens, int B, int Tp, int N,
+                             int Lp, int P, const TrieView& tv, const int* d_olen, const int* d_nhyp, float* d_scores,
+                             cudaStream_t stream) {
+  const rvb_model_config& c = m->cfg;
+  const int d = c.d_model, H = c.dec_heads, dk = d / H, V = c.vocab;
+  const long long R = (long long)B * P, E = (long long)B * (P + N), Mem = (long long)B * Tp;
+  const long long S = (long long)B * N;
+  const bool x3 = m->x3;
+  const size_t pm = (size_t)m->pm();
+  const int ldv = (V + 3) & ~3;
+  DevBuf* w = m->ws_dec;
+  const size_t n_int = (size_t)R * 3 + (size_t)R * Lp + (size_t)E * 2 + (size_t)S * Lp;
+  if (w[0].ensure((size_t)R * d * 4) || w[1].ensure((size_t)R * d * 2 * pm) || w[2].ensure((size_t)R * 3 * d * 2 * pm) ||
+      w[3].ensure((size_t)R * d * 2 * pm) || w[4].ensure((size_t)Mem * 2 * d * 2 * pm) ||
+      w[5].ensure((size_t)R * c.dec_ffn_dim * 2 * pm) || w[6].ensure((size_t)R * d * 2 * pm) ||
+      w[9].ensure(n_int * sizeof(int)) || w[10].ensure((size_t)E * d * 2 * pm) || w[11].ensure((size_t)E * sizeof(float)))
+    return -1;
+  float* x = w[0].as<float>();
+  bf16* n = w[1].as<bf16>();
+  bf16* qkv = w[2].as<bf16>();
+  bf16* att = w[3].as<bf16>();
+  bf16* kv = w[4].as<bf16>();
+  bf16* h = w[5].as<bf16>();
+  bf16* ybf = w[6].as<bf16>();
+  int* tok_in = w[9].as<int>();
+  int* pos = tok_in + R;
+  int* alen = pos + R;
+  int* anc = alen + R;
+  int* src = anc + (size_t)R * Lp;
+  int* tgt = src + E;
+  int* smap = tgt + E;
+  bf16* a_out = w[10].as<bf16>();
+  float* e_sc = w[11].as<float>();
+  if (launch_trie_inputs(tv.node_of, tv.nstride, tv.node_tok, tv.node_par, tv.node_dep, tv.cap, tv.n_nodes, d_olen, d_nhyp,
+                         B, N, P, Lp, eos_id(c), tok_in, pos, anc, alen, src, tgt, smap, stream))
+    return -1;
+  if (launch_embed_posenc_rows(tok_in, pos, D.emb, (int)R, d, x, stream)) return -1;
+  for (size_t l = 0; l < D.layers.size(); ++l) {
+    DecLayer& Ld = D.layers[l];
+    // self-attention of every node over its ancestors (= the causal mask of the flat layout)
+    if (launch_layernorm(x, Ld.n1.g, Ld.n1.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    if (gemm(m, n, Ld.qkv, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    {
+      AttnF32Args a;
+      a.q = qkv;
+      a.k = qkv + d;
+      a.v = qkv + 2 * d;
+      a.out = att;
+      a.ldq = a.ldk = a.ldv = 3 * d * (int)pm;
+      a.q_lo = a.k_lo = a.v_lo = x3 ? 3 * d : 0;
+      a.ldo = d * (int)pm;
+      a.o_lo = x3 ? d : 0;
+      a.groups = 1;
+      a.Tq = (int)R;
+      a.Tk = Lp;
+      a.H = H;
+      a.dk = dk;
+      a.key_list = anc;
+      a.key_list_len = alen;
+      a.key_list_ld = Lp;
+      if (launch_attention_f32(a, stream)) return -1;
+    }
+    if (gemm(m, att, Ld.so, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    // source attention over the utterance's encoder output (K/V projected once per utterance)
+    if (launch_layernorm(x, Ld.n2.g, Ld.n2.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    if (gemm(m, n, Ld.cq, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    if (gemm(m, enc_bf, Ld.ckv, (int)Mem, ACT_NONE, OUT_BF16, kv, 1.f, stream)) return -1;
+    if (!x3 && attn_impl() == 1 && dk == 64) {
+      AttnTcArgs a;
+      a.q = qkv;
+      a.k = kv;
+      a.v = kv + d;
+      a.out = att;
+      a.ldq = d;
+      a.ldk = a.ldv = 2 * d;
+      a.ldo = d;
+      a.groups = B;
+      a.Tq = P;
+      a.Tk = Tp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_enc_lens;
+      a.scale = 1.0f / sqrtf((float)dk);
+      if (launch_attention_tc(a, stream)) return -1;
+    } else {
+      AttnF32Args a;
+      a.q = qkv;
+      a.k = kv;
+      a.v = kv + d;
+      a.out = att;
+      a.ldq = d * (int)pm;
+      a.q_lo = x3 ? d : 0;
+      a.ldk = a.ldv = 2 * d * (int)pm;
+      a.k_lo = a.v_lo = x3 ? 2 * d : 0;
+      a.ldo = d * (int)pm;
+      a.o_lo = x3 ? d : 0;
+      a.groups = B;
+      a.Tq = P;
+      a.Tk = Tp;
+      a.H = H;
+      a.dk = dk;
+      a.k_lens = d_enc_lens;
+      if (launch_attention_f32(a, stream)) return -1;
+    }
+    if (gemm(m, att, Ld.co, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+    if (launch_layernorm(x, Ld.n3.g, Ld.n3.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+    const bf16* ffn_in = n;
+    if (Ld.lsl) {
+      if (gemm(m, n, Ld.lang, (int)R, ACT_NONE, OUT_BF16, ybf, 1.f, stream)) return -1;
+      ffn_in = ybf;
+    }
+    if (gemm(m, ffn_in, Ld.ff1, (int)R, ACT_RELU, OUT_BF16, h, 1.f, stream)) return -1;
+    if (gemm(m, h, Ld.ff2, (int)R, ACT_NONE, OUT_RESID_F32, x, 1.f, stream)) return -1;
+  }
+  if (launch_layernorm(x, D.after.g, D.after.b, 1e-5f, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
+  // output layer on one row per EDGE of the tree (+ one per hypothesis end): hidden state of the edge's source node
+  if (launch_gather_rows(n, src, a_out, (int)E, d * (int)pm, stream)) return -1;
+  if (get_gemm_impl() != 1 && V > 128) {
+    const int slabs = lse_slabs(V);
+    if (w[7].ensure((size_t)E * slabs * sizeof(float2) + (size_t)E * sizeof(float))) return -1;
+    float2* part = w[7].as<float2>();
+    float* tg = reinterpret_cast<float*>(part + (size_t)E * slabs);
+    GemmArgs g;
+    g.x3 = x3 ? 1 : 0;
+    g.A = a_out;
+    g.W = D.outl.w;
+    g.bias = D.outl.b;
+    g.M = (int)E;
+    g.N = D.outl.N;
+    g.K = D.outl.K;
+    g.out_mode = OUT_LSE;
+    g.lse_gather = tgt;
+    g.lse_part = part;
+    g.lse_tgt = tg;
+    if (launch_gemm(g, stream)) return -1;
+    if (launch_lse_merge(part, slabs, tg, tgt, (int)E, e_sc, stream)) return -1;
+  } else {
+    if (m->ws_logits.ensure((size_t)E * ldv * 4)) return -1;
+    float* logits = m->ws_logits.as<float>();
+    if (gemm(m, a_out, D.outl, (int)E, ACT_NONE, OUT_F32, logits, 1.f, stream, nullptr, 0, ldv)) return -1;
+    if (launch_logsoftmax_gather(logits, ldv, (int)E, V, tgt, 1, e_sc, stream)) return -1;
+  }
+  return launch_gather_scores(e_sc, smap, d_scores, S * Lp, stream);
+}
+
 // Decoder passes over device-resident inputs (all int arrays on the device):
 //   tok_l / tok_r (R = S*Lp): decoder inputs [sos, w_1..w_U, eos..] and the reversed variant (asr_model.py:921-949)
 //   gat_l / gat_r (R): per-position gather targets, -1 = none (search.py:417-430);  slen (S) = U + 1;  elen (B)
@@ -1315,7 +1479,24 @@ static int attention_rescoring(rvb_model* m, const float* d_enc_out, const int* 
 struct SearchTicket {
   int state = 0;      // 0 free, 1 search submitted, 2 decoder submitted
   DevBuf out;         // lens(B) | tokens | times | out_lens (S*2) | nhyp (B) | pad | scores (S doubles)
-  HostPinned small;   // out_lens | nhyp | pad | scores | enc lens(B)
+  DevBuf trie;        // prefix trees of the n-best (left-to-right and reversed): node_of | node_tok | par | dep | n_nodes
+  HostPinned small;   // out_lens | nhyp | pad | scores | enc lens(B) | n_nodes (2 B)
+  int trie_cap = 0, trie_stride = 0;
+  bool has_trie = false, has_rtrie = false;
+  int* tr_node_of(int dir) { return trie.as<int>() + (size_t)dir * trie_ints(); }
+  size_t trie_ints() const { return (size_t)B * beam * trie_stride + (size_t)3 * B * trie_cap + B; }
+  TrieView trie_view(int dir) {
+    int* base = tr_node_of(dir);
+    TrieView v;
+    v.node_of = base;
+    v.nstride = trie_stride;
+    v.node_tok = base + (size_t)B * beam * trie_stride;
+    v.node_par = const_cast<int*>(v.node_tok) + (size_t)B * trie_cap;
+    v.node_dep = const_cast<int*>(v.node_par) + (size_t)B * trie_cap;
+    v.cap = trie_cap;
+    v.n_nodes = const_cast<int*>(v.node_dep) + (size_t)B * trie_cap;
+    return v;
+  }
   cudaEvent_t ev_search = nullptr, ev_done = nullptr;
   int B = 0, Tp = 0, beam = 0;
   size_t n_tok = 0, ints_al = 0, small_ints = 0, small_bytes = 0;
@@ -1331,6 +1512,7 @@ struct SearchTicket {
   double* d_sc() { return reinterpret_cast<double*>(out.as<int>() + ints_al); }
   void release() {
     out.release();
+    trie.release();
     small.release();
     if (ev_search) cudaEventDestroy(ev_search);
     if (ev_done) cudaEventDestroy(ev_done);
@@ -1354,7 +1536,16 @@ static int search_submit(rvb_model* m, SearchTicket& t, const float* d_topk_val,
   t.small_ints = t.ints_al - (B + 2 * t.n_tok);            // out_lens | nhyp | pad
   t.small_bytes = t.small_ints * sizeof(int) + (size_t)S * sizeof(double);
   const size_t ws_bytes = prefix_beam_workspace_bytes(B, Tp, beam);
-  if (ws.ensure(ws_bytes) || t.out.ensure(out_bytes) || t.small.ensure(t.small_bytes + sizeof(int) * B)) return -1;
+  // prefix trees of the n-best for the tree-structured rescoring decoder (left-to-right, and reversed when the model
+  // has a right-to-left decoder): built right behind the search, their node counts travel with the lengths
+  t.has_trie = rescore_trie() && m->dec_l.present && beam <= 16;
+  t.has_rtrie = t.has_trie && m->dec_r.present;
+  t.trie_stride = dev_len + 1;
+  t.trie_cap = beam * dev_len + 1;
+  const int ndir = t.has_trie ? (t.has_rtrie ? 2 : 1) : 0;
+  if (ws.ensure(ws_bytes) || t.out.ensure(out_bytes) || t.small.ensure(t.small_bytes + sizeof(int) * B * 3) ||
+      (ndir && t.trie.ensure(t.trie_ints() * ndir * sizeof(int))))
+    return -1;
   if (!t.ev_search) RVB_CHECK_CUDA(cudaEventCreateWithFlags(&t.ev_search, cudaEventDisableTiming));
   if (!t.ev_done) RVB_CHECK_CUDA(cudaEventCreateWithFlags(&t.ev_done, cudaEventDisableTiming));
   int* hp_small = t.small.as<int>();
@@ -1381,6 +1572,14 @@ static int search_submit(rvb_model* m, SearchTicket& t, const float* d_topk_val,
                              t.d_tok(), t.d_tim(), t.d_olen(), t.d_sc(), t.d_nhyp(), ss))
     return -1;
   RVB_CHECK_CUDA(cudaMemcpyAsync(hp_small, t.d_olen(), t.small_bytes, cudaMemcpyDeviceToHost, ss));
+  for (int dir = 0; dir < ndir; ++dir) {
+    TrieView v = t.trie_view(dir);
+    if (launch_trie_build(t.d_tok(), dev_len, t.d_olen(), t.d_nhyp(), B, beam, dir, sos_id(m->cfg), const_cast<int*>(v.node_of),
+                          v.nstride, const_cast<int*>(v.node_tok), const_cast<int*>(v.node_par),
+                          const_cast<int*>(v.node_dep), v.cap, const_cast<int*>(v.n_nodes), ss))
+      return -1;
+    RVB_CHECK_CUDA(cudaMemcpyAsync(hp_elen + B * (1 + dir), v.n_nodes, sizeof(int) * B, cudaMemcpyDeviceToHost, ss));
+  }
   RVB_CHECK_CUDA(cudaEventRecord(t.ev_search, ss));
   t.state = 1;
   return 0;
@@ -1427,12 +1626,32 @@ static int rescoring_submit(rvb_model* m, SearchTicket& t, const float* h_cat, i
     int* dp = m->ws_misc.as<int>();
     float* d_sc_l = reinterpret_cast<float*>(dp + rints);
     float* d_sc_r = d_sc_l + R;
-    if (launch_rescoring_inputs(t.d_tok(), dev_len, t.d_olen(), t.d_nhyp(), B, N, Lp, sos_id(c), eos_id(c), dp, dp + R,
-                                dp + 2 * R, dp + 3 * R, dp + 4 * R, stream))
-      return -1;
-    if (rescoring_device(m, t.d_enc_out, t.d_lens(), B, Tp, N, Lp, dp, dp + R, dp + 2 * R, dp + 3 * R, dp + 4 * R, use_r,
-                         d_sc_l, d_sc_r, stream))
-      return -1;
+    if (t.has_trie && (!use_r || t.has_rtrie)) {
+      // tree-structured decoder: one row per distinct prefix of the utterance's n-best
+      const int* hp_nodes = reinterpret_cast<const int*>(reinterpret_cast<const char*>(t.small.p) + t.small_bytes) + B;
+      const int d = c.d_model;
+      const long long Mem = (long long)B * Tp;
+      if (m->ws_encbf.ensure((size_t)Mem * d * 2 * m->pm())) return -1;
+      bf16* encbf = m->ws_encbf.as<bf16>();
+      if (m->x3 ? launch_f32_to_pair(t.d_enc_out, encbf, Mem, d, stream)
+                : launch_f32_to_bf16(t.d_enc_out, encbf, Mem * d, stream))
+        return -1;
+      for (int dir = 0; dir < (use_r ? 2 : 1); ++dir) {
+        int P = 1;
+        for (int b = 0; b < B; ++b) P = hp_nodes[dir * B + b] > P ? hp_nodes[dir * B + b] : P;
+        P = (P + 7) & ~7;
+        if (decoder_pass_trie(m, dir ? m->dec_r : m->dec_l, encbf, t.d_lens(), B, Tp, N, Lp, P, t.trie_view(dir),
+                              t.d_olen(), t.d_nhyp(), dir ? d_sc_r : d_sc_l, stream))
+          return -1;
+      }
+    } else {
+      if (launch_rescoring_inputs(t.d_tok(), dev_len, t.d_olen(), t.d_nhyp(), B, N, Lp, sos_id(c), eos_id(c), dp, dp + R,
+                                  dp + 2 * R, dp + 3 * R, dp + 4 * R, stream))
+        return -1;
+      if (rescoring_device(m, t.d_enc_out, t.d_lens(), B, Tp, N, Lp, dp, dp + R, dp + 2 * R, dp + 3 * R, dp + 4 * R, use_r,
+                           d_sc_l, d_sc_r, stream))
+        return -1;
+    }
     RVB_CHECK_CUDA(cudaMemcpyAsync(h_l2r, d_sc_l, (size_t)R * sizeof(float), cudaMemcpyDeviceToHost, stream));
     if (use_r) {
       RVB_CHECK_CUDA(cudaMemcpyAsync(h_r2l, d_sc_r, (size_t)R * sizeof(float), cudaMemcpyDeviceToHost, stream));

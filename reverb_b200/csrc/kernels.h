@@ -184,6 +184,11 @@ struct AttnF32Args {
   int groups = 0, Tq = 0, Tk = 0, H = 0, dk = 0;
   const int* k_lens = nullptr;
   int chunk = 0, left = -1;  // chunk > 0: streaming chunk mask; chunk = 1, left < 0 = causal
+  // key lists (prefix-tree self-attention): query row i of group g attends the key_list_len[g*Tq + i] key ROWS listed at
+  // key_list[(g*Tq + i) * key_list_ld ...] (absolute row indices into k / v); Tk = the longest list
+  const int* key_list = nullptr;
+  const int* key_list_len = nullptr;
+  int key_list_ld = 0;
 };
 int launch_attention_f32(const AttnF32Args& a, cudaStream_t stream);
 
@@ -209,5 +214,18 @@ int launch_logsoftmax_gather(const float* logits, int ld, int M, int V, const in
 int launch_rescoring_inputs(const int* d_tokens, int tok_stride, const int* d_out_lens, const int* d_nhyp, int B, int N,
                             int Lp, int sos, int eos, int* tok_l, int* tok_r, int* gat_l, int* gat_r, int* slen,
                             cudaStream_t stream);
+
+// prefix-tree rescoring (ctc.cu): see trie_build_kernel / trie_inputs_kernel
+int launch_trie_build(const int* tok, int tok_stride, const int* olen, const int* nhyp, int B, int N, int reverse, int sos,
+                      int* node_of, int nstride, int* node_tok, int* node_par, int* node_dep, int cap, int* n_nodes,
+                      cudaStream_t stream);
+int launch_trie_inputs(const int* node_of, int nstride, const int* node_tok, const int* node_par, const int* node_dep,
+                       int cap, const int* n_nodes, const int* olen, const int* nhyp, int B, int N, int P, int Lp, int eos,
+                       int* tok_in, int* pos, int* anc, int* alen, int* src, int* tgt, int* smap, cudaStream_t stream);
+int launch_gather_rows(const bf16* in, const int* idx, bf16* out, int rows, int width, cudaStream_t stream);
+int launch_gather_scores(const float* vals, const int* map, float* out, long long n, cudaStream_t stream);
+// decoder input with a per-row position: x[r, :] = emb[tok[r], :] * sqrt(d) + pe[pos[r], :]
+int launch_embed_posenc_rows(const int* tokens, const int* pos, const float* emb, int R, int d, float* out,
+                             cudaStream_t stream);
 
 }  // namespace rvb

@@ -177,6 +177,44 @@ def test_decode_stream_equals_batch_by_batch_decode(asr, golden_cases, tmp_path)
     assert len(list(m.model.decode_stream(iter(batches), ["attention_rescoring"], 10, **kw))) == len(batches)
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_prefix_tree_rescoring_equals_the_flat_decoder(model_dirs, golden_cases, precision):
+    """Attention rescoring on the prefix TREE of the n-best (one decoder row per distinct prefix, ctc.cu
+    trie_build_kernel) must give every (hypothesis, position) the log-probability the flat layout gives it (one row per
+    hypothesis and position, RVB_RESCORE=flat) — left-to-right and right-to-left decoders — and the same picks."""
+    import reverb_b200
+    from reverb_b200.search import rescoring_pick_batch
+    for case in ("causal_ln", "sym_bn"):
+        meta, arr = golden_cases[case]
+        m = reverb_b200.load_model(model_dirs[case][0], precision=precision)
+        cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+        feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+        tol = 2e-3 if precision == "fp32" else 0.06
+        for fb, fl in m.feats_batcher(feats, meta["chunk_size"], meta["batch_size"]):
+            enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
+            tv, ti, _ = m.engine.ctc_topk(enc, 10, 0.0, 0)
+            out = {}
+            for mode in ("tree", "flat"):
+                os.environ["RVB_RESCORE"] = mode
+                try:
+                    out[mode] = m.engine.beam_search_rescoring(tv, ti, enc, enc_lens, 10, 0, cat, 0.3)
+                finally:
+                    del os.environ["RVB_RESCORE"]
+            a, b = out["tree"], out["flat"]
+            for i in range(5):
+                assert np.array_equal(a[i], b[i])                       # tokens, times, lengths, CTC scores, counts
+            olen, nhyp = a[2], a[4]
+            for bb in range(a[0].shape[0]):
+                for i in range(int(nhyp[bb])):
+                    U = int(olen[bb, i, 0])
+                    assert np.abs(a[5][bb, i, :U + 1] - b[5][bb, i, :U + 1]).max() < tol
+                    assert np.abs(a[6][bb, i, :U + 1] - b[6][bb, i, :U + 1]).max() < tol
+            pa = rescoring_pick_batch(*a[:5], a[5], a[6], 0.1, 0.3)
+            pb = rescoring_pick_batch(*b[:5], b[5], b[6], 0.1, 0.3)
+            if precision == "fp32":
+                assert [tuple(x.tokens) for x in pa] == [tuple(x.tokens) for x in pb]
+
+
 def test_beam_size_limit_is_reported_before_decoding(asr, model_dirs):
     m = asr["causal_ln"]
     with pytest.raises(ValueError, match="beam_size"):
