@@ -416,11 +416,12 @@ def test_gemm_bf16x3_is_fp32_accurate(lib, impl, M, N, K):
         _check(lib, lib.rvb_gemm_bf16x3(_p(Ap), _p(Wp), _p(bias), M, N, K, 0, 1, 1.0, _p(out), ldo, _stream()))
         err3 = float((out[:, :N].double() - ref).abs().max())
         out1 = torch.zeros(M, ldo, device="cuda")
-        _check(lib, lib.rvb_gemm_bf16(_p(A.bfloat16()), _p(W.bfloat16()), _p(bias), M, N, K, 0, 1, 1.0, _p(out1), ldo, _stream()))
+        Ab, Wb = A.bfloat16(), W.bfloat16()                       # keep the operands alive across the launch
+        _check(lib, lib.rvb_gemm_bf16(_p(Ab), _p(Wb), _p(bias), M, N, K, 0, 1, 1.0, _p(out1), ldo, _stream()))
         err1 = float((out1[:, :N].double() - ref).abs().max())
         err32 = float(((A @ W.t() + bias).double() - ref).abs().max())      # torch's own fp32 matmul (may use tf32-free path)
         print(f"[x3 {M}x{N}x{K}] max abs err: bf16x3 {err3:.2e}, bf16 {err1:.2e}, torch fp32 {err32:.2e}")
-        assert err3 < 2e-5 * math.sqrt(K / 128) and err3 < err1 / 50
+        assert err3 < 2e-5 * math.sqrt(K / 128) and err3 < err1 / 50 and err3 < 30 * err32 + 1e-5
         if N % 128 == 0:
             # bf16 pair output + SiLU: hi + lo reproduces silu(ref) to ~2^-16
             outp = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
