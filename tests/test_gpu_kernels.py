@@ -451,6 +451,8 @@ def test_gemm_bf16x3_glu_pair_output(lib):
     Wq[ra], Wq[ra + 32] = W[:Cc], W[Cc:]
     bq[ra], bq[ra + 32] = bias[:Cc], bias[Cc:]
     out = torch.zeros(M, 2 * Cc, device="cuda", dtype=torch.bfloat16)
-    _check(lib, lib.rvb_gemm_bf16x3(_p(_pair(lib, A)), _p(_pair(lib, Wq)), _p(bq), M, 2 * Cc, K, 3, 0, 1.0, _p(out), 0, _stream()))
+    Ap, Wp = _pair(lib, A), _pair(lib, Wq)                       # keep the operands alive across the launch
+    _check(lib, lib.rvb_gemm_bf16x3(_p(Ap), _p(Wp), _p(bq), M, 2 * Cc, K, 3, 0, 1.0, _p(out), 0, _stream()))
+    torch.cuda.synchronize()
     got = out[:, :Cc].float() + out[:, Cc:].float()
     assert float((got - ref).abs().max()) < 1e-4

@@ -179,7 +179,14 @@ def test_decode_is_consistent_with_oracle_searches_on_gpu_logprobs(asr, golden_c
     ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
     modes = ["ctc_greedy_search", "ctc_prefix_beam_search", "attention_rescoring"]
     for fb, fl in m.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"]):
-        got = m.model.decode(modes, fb, fl, 10, ctc_weight=cw, reverse_weight=rw, cat_embs=cat, blank_id=0)
+        # the flat rescoring decoder (one row per hypothesis and position) is the same function as
+        # engine.rescoring_scores below; the default prefix-tree decoder agrees with it to rounding
+        # (tests/test_gpu_parity.py::test_prefix_tree_rescoring_equals_the_flat_decoder)
+        os.environ["RVB_RESCORE"] = "flat"
+        try:
+            got = m.model.decode(modes, fb, fl, 10, ctc_weight=cw, reverse_weight=rw, cat_embs=cat, blank_id=0)
+        finally:
+            del os.environ["RVB_RESCORE"]
         enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
         logp = m.model.ctc_logprobs(enc).cpu()
         lens_t = torch.from_numpy(enc_lens.astype(np.int64))
