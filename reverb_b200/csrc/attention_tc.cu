@@ -57,6 +57,24 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   return r;
 }
 
+// 2^x for a PAIR of arguments on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, |f| <= 1/2, degree-3
+// minimax polynomial for 2^f (max relative error 7.5e-5, far below the bf16 quantisation of P~), 2^n through the exponent
+// field.  x is clamped at -126 (2^-126 ~ 1e-38 underflows to nothing in the sums).  Used for a FRACTION of the
+// exponentials of interior tiles so that MUFU.EX2 (XU pipe, 16 / clk / SM) is not the only unit doing them.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float2 magic = make_float2(12582912.f, 12582912.f), one2 = make_float2(1.f, 1.f);
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 xf = ffma2(x, one2, magic);                                   // n in the low mantissa bits
+  const float2 n = ffma2(xf, one2, make_float2(-12582912.f, -12582912.f));
+  const float2 f = ffma2(n, make_float2(-1.f, -1.f), x);
+  float2 p = ffma2(f, make_float2(0.05517164617776871f, 0.05517164617776871f), make_float2(0.2426111251115799f, 0.2426111251115799f));
+  p = ffma2(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = ffma2(p, f, make_float2(0.9999280571937561f, 0.9999280571937561f));
+  return make_float2(__uint_as_float(__float_as_uint(p.x) + (__float_as_uint(xf.x) << 23)),
+                     __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(xf.y) << 23)));
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -85,7 +103,7 @@ struct AttnTcParams {
 //     tile maxima / row sums meet through shared memory and a 64-thread named barrier.  Measured slightly SLOWER than
 //     SW = 4 (0.403 vs 0.388 ms per encoder layer): the kernel is not short of warps; what bounds it is the
 //     ex2 + issue budget per tile and the per-tile hand-offs, which the split duplicates.
-template <int BN, int SW, bool PF>
+template <int BN, int SW, int POLY>
 __global__ void __launch_bounds__(32 * (SW + 1), AtCfg<BN>::CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -252,9 +270,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int c0 = hh * CW, ob = hh * OW;
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory"); };
     float m_run = -INFINITY, row_sum = 0.f;  // m_run stays -inf until the row has seen a visible key
-    // The thread's part of an S row is pulled out of TMEM with back-to-back loads and ONE wait.  PF (prefetch): the loads
-    // of tile j+1 are issued BEFORE the arithmetic of tile j (two register copies of the row, swapped every tile), so the
-    // TMEM latency and the wait for QK(j+1) overlap the exponentials of tile j instead of preceding those of tile j+1.
+    // The thread's part of an S row is pulled out of TMEM with back-to-back loads and ONE wait.  (A variant that
+    // prefetched tile j+1 into a second register copy before the arithmetic of tile j needed ~230 registers, spilled at
+    // the 168 available with 2 CTAs / SM and measured 0.62 ms instead of 0.43 ms per encoder layer: removed.)
     auto pull = [&](int j, uint32_t(&dst)[CW]) {
       const int sb = j % AT_NS;
       mbar_wait(&s_full[sb], (j / AT_NS) & 1);
@@ -262,14 +280,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
       for (int c = 0; c < CW; c += 32) tmem_ld_32x32(s_col(sb) + lane_addr + c0 + c, dst + c);
     };
-    auto tile = [&](int j, uint32_t(&sv)[CW], uint32_t(&nx)[CW]) {
+    auto tile = [&](int j, uint32_t(&sv)[CW]) {
       const int sb = j % AT_NS, pb = j & 1;
-      if (!PF) pull(j, sv);
+      pull(j, sv);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);   // the S buffer goes back to the MMA issuer as early as possible
-      if (PF && j + 1 < ntiles) pull(j + 1, nx);
       const uint32_t bias_addr = smem_u32(s_bias + j * AT_BN + c0);
       // x = s * scale*log2e + key bias (masked keys: -inf), kept in place of the raw scores; tile maximum
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
@@ -342,6 +359,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float2 sm01 = make_float2(0.f, 0.f), sm23 = make_float2(0.f, 0.f);
       const float m_eff = (m_run == -INFINITY) ? 0.f : m_run;  // no visible key yet: every x is -inf -> p = 0
       const float2 one2 = make_float2(1.f, 1.f), negm2 = make_float2(-m_eff, -m_eff);
+      // the polynomial exp2 path needs finite arguments: tiles fully inside [0, klen) without a chunk-mask boundary
+      const bool poly_ok = (p.chunk == 0) && ((jt0 + j + 1) * AT_BN <= klen) && (m_run != -INFINITY) &&
+                           __all_sync(0xffffffffu, m_run != -INFINITY);
       // P~ goes to shared memory chunk by chunk (8 keys = 16 bytes) as it is produced, so only one chunk of packed
       // probabilities is ever live in registers.  The buffer was last read by PV(j-2), which has had a whole tile of
       // exponentials to retire: this wait is practically free.
@@ -356,7 +376,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float2 d01 = ffma2(make_float2(__uint_as_float(sv[f + 0]), __uint_as_float(sv[f + 1])), one2, negm2);
           const float2 d23 = ffma2(make_float2(__uint_as_float(sv[f + 2]), __uint_as_float(sv[f + 3])), one2, negm2);
           float2 p01 = make_float2(fast_exp2(d01.x), fast_exp2(d01.y));
-          float2 p23 = make_float2(fast_exp2(d23.x), fast_exp2(d23.y));
+          // POLY > 0: in every POLY-th group of four (POLY = 1: half, 2: a quarter of all exponentials) the second pair on the FMA pipe instead of MUFU (only when every key
+          // of the tile is visible: masked keys carry -inf, which the polynomial path does not produce exact zeros for)
+          float2 p23;
+          if (POLY > 0 && poly_ok && ((f >> 2) % (POLY > 0 ? POLY : 1)) == 0) p23 = exp2_poly2(d23);
+          else p23 = make_float2(fast_exp2(d23.x), fast_exp2(d23.y));
           if (AT_TRUNC_P) {
             // P~ = the exponentials TRUNCATED to bf16 (upper 16 bits: one ALU byte-permute per pair) instead of rounded
             // by F2FP — the conversion shares the XU pipe with MUFU.EX2, the pipe that bounds this kernel (ncu: xu 54 %,
@@ -388,13 +412,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (lane == 0) mbar_arrive(&p_full[pb]);
     };
     {
-      uint32_t sva[CW], svb[CW];
-      if (PF && ntiles > 0) pull(0, sva);
+      uint32_t sv[CW];
 #pragma unroll 1
-      for (int j = 0; j < ntiles; j += 2) {
-        tile(j, sva, svb);
-        if (j + 1 < ntiles) tile(j + 1, svb, sva);
-      }
+      for (int j = 0; j < ntiles; ++j) tile(j, sv);
     }
     // ---- epilogue: O / row_sum -> bf16 -> global
     if (SPLIT) {
@@ -597,31 +617,34 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
     const size_t smem = AtCfg<128>::SMEM_FIXED + (size_t)((a.Tk + 127) / 128) * 128 * sizeof(float);
     RVB_REQUIRE(smem <= 227 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
     static DynSmemOptIn optin;
-    if (optin.ensure(attention_tc_kernel<128, 4, false>, smem)) return -1;
-    attention_tc_kernel<128, 4, false><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    if (optin.ensure(attention_tc_kernel<128, 4, 0>, smem)) return -1;
+    attention_tc_kernel<128, 4, 0><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
   } else if (sw_sel == 4) {
     const size_t smem = AtCfg<64>::SMEM_FIXED + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
     RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
-    static int pf_sel = -1;   // RVB_ATTN_PF=1: S-tile prefetch variant (A/B aid; off until it wins on the GPU)
-    if (pf_sel < 0) {
-      const char* e = getenv("RVB_ATTN_PF");
-      pf_sel = (e && atoi(e) == 1) ? 1 : 0;
+    static int poly_sel = -1;   // RVB_ATTN_POLY=0|1|2: share of the exponentials on the FMA pipe (0 none, 1 half, 2 quarter)
+    if (poly_sel < 0) {
+      const char* e = getenv("RVB_ATTN_POLY");
+      poly_sel = e ? atoi(e) : 0;
+      if (poly_sel < 0 || poly_sel > 2) poly_sel = 0;
     }
-    if (pf_sel) {
-      static DynSmemOptIn optin;
-      if (optin.ensure(attention_tc_kernel<64, 4, true>, smem)) return -1;
-      attention_tc_kernel<64, 4, true><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    static DynSmemOptIn optin[3];
+    if (poly_sel == 1) {
+      if (optin[1].ensure(attention_tc_kernel<64, 4, 1>, smem)) return -1;
+      attention_tc_kernel<64, 4, 1><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    } else if (poly_sel == 2) {
+      if (optin[2].ensure(attention_tc_kernel<64, 4, 2>, smem)) return -1;
+      attention_tc_kernel<64, 4, 2><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
     } else {
-      static DynSmemOptIn optin;
-      if (optin.ensure(attention_tc_kernel<64, 4, false>, smem)) return -1;
-      attention_tc_kernel<64, 4, false><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+      if (optin[0].ensure(attention_tc_kernel<64, 4, 0>, smem)) return -1;
+      attention_tc_kernel<64, 4, 0><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
     }
   } else {
     const size_t smem = AtCfg<64>::SMEM_FIXED + 3072 + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);
     RVB_REQUIRE(smem <= 113 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
     static DynSmemOptIn optin;
-    if (optin.ensure(attention_tc_kernel<64, 8, false>, smem)) return -1;
-    attention_tc_kernel<64, 8, false><<<grid, 288, smem, stream>>>(tmQ, tmK, tmV, p);
+    if (optin.ensure(attention_tc_kernel<64, 8, 0>, smem)) return -1;
+    attention_tc_kernel<64, 8, 0><<<grid, 288, smem, stream>>>(tmQ, tmK, tmV, p);
   }
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
