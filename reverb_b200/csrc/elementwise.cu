@@ -484,6 +484,106 @@ conv_dw_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, co
   }
 }
 
+// Fused variant for LayerNorm when one CTA can hold the whole channel dimension (C / 2 <= 512 threads, i.e. d <= 1024): depthwise conv,
+// per-frame statistics (warp butterfly + one shared-memory reduction across the CTA's warps), normalise + SiLU, bf16 out —
+// the fp32 conv result never goes to HBM (conv_dw_kernel + conv_norm_silu_kernel move 588 MB per layer at the benchmark
+// shape, this kernel 196 MB: read the GLU output once, write the bf16 operand of pointwise_conv2 once).
+template <int K>
+__global__ void __launch_bounds__(512)
+conv_dw_ln_fused_kernel(const bf16* __restrict__ x, const float* __restrict__ pad_glu, const float* __restrict__ dw_w,
+                        const float* __restrict__ dw_b, const float* __restrict__ norm_w,
+                        const float* __restrict__ norm_b, float eps, bf16* __restrict__ out, int T, int C, int causal) {
+  __shared__ float s_part[16][32];   // [warp][16 frame sums | 16 frame sums of squares]
+  __shared__ float s_tot[32];
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * CM_TT;
+  const int C2 = C >> 1;
+  const int cp = threadIdx.x;
+  const bool ok = cp < C2;
+  const int left = causal ? (K - 1) : (K - 1) / 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  float b0 = 0.f, b1 = 0.f;
+  float2 padv = make_float2(0.f, 0.f);
+  if (ok) {
+    b0 = __ldg(dw_b + 2 * cp);
+    b1 = __ldg(dw_b + 2 * cp + 1);
+    if (causal) padv = make_float2(__ldg(pad_glu + 2 * cp), __ldg(pad_glu + 2 * cp + 1));
+  }
+  float acc[CM_TT][2];
+#pragma unroll
+  for (int t = 0; t < CM_TT; ++t) {
+    acc[t][0] = b0;
+    acc[t][1] = b1;
+  }
+  const uint32_t* xb = reinterpret_cast<const uint32_t*>(x + (long long)b * T * C) + cp;
+  constexpr int ROWS = CM_TT + K - 1;
+  uint32_t rv[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int t = t0 - left + r;
+    rv[r] = 0u;
+    if (ok && t >= 0 && t < T) rv[r] = __ldg(xb + (long long)t * C2);
+  }
+  float w0[K], w1[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    w0[k] = ok ? __ldg(dw_w + (2 * cp) * K + k) : 0.f;
+    w1[k] = ok ? __ldg(dw_w + (2 * cp + 1) * K + k) : 0.f;
+  }
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    const int tt = t0 - left + r;
+    const float2 v = (tt < 0) ? padv : unpack_bf16x2(rv[r]);  // rv is 0 beyond T
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int t = r - k;  // compile-time after unrolling
+      if (t >= 0 && t < CM_TT) {
+        const float2 a2 = ffma2(make_float2(w0[k], w1[k]), v, make_float2(acc[t][0], acc[t][1]));
+        acc[t][0] = a2.x;
+        acc[t][1] = a2.y;
+      }
+    }
+  }
+  // per-frame sum / sum of squares over the CTA's channels
+  static_assert(CM_TT == 16, "the statistics butterfly assumes 32 values per lane");
+  float sv[32];
+#pragma unroll
+  for (int t = 0; t < CM_TT; ++t) {
+    sv[t] = ok ? acc[t][0] + acc[t][1] : 0.f;
+    sv[CM_TT + t] = ok ? acc[t][0] * acc[t][0] + acc[t][1] * acc[t][1] : 0.f;
+  }
+#pragma unroll
+  for (int ofs = 16; ofs >= 1; ofs >>= 1) {
+    const bool up = (lane & ofs) != 0;
+#pragma unroll
+    for (int i = 0; i < ofs; ++i) {
+      const float send = up ? sv[i] : sv[i + ofs];
+      const float keep = up ? sv[i + ofs] : sv[i];
+      sv[i] = keep + __shfl_xor_sync(0xffffffffu, send, ofs);
+    }
+  }
+  s_part[warp][lane] = sv[0];   // lane l: value l (l < 16: sum of frame l, l >= 16: sum of squares of frame l - 16)
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float tot = 0.f;
+    for (int w = 0; w < nwarps; ++w) tot += s_part[w][threadIdx.x];   // fixed order: bit-reproducible
+    s_tot[threadIdx.x] = tot;
+  }
+  __syncthreads();
+  if (!ok) return;
+  const float g0 = __ldg(norm_w + 2 * cp), g1 = __ldg(norm_w + 2 * cp + 1);
+  const float be0 = __ldg(norm_b + 2 * cp), be1 = __ldg(norm_b + 2 * cp + 1);
+#pragma unroll
+  for (int t = 0; t < CM_TT; ++t) {
+    if (t0 + t >= T) break;
+    const float mean = s_tot[t] / (float)C;
+    const float var = fmaxf(s_tot[CM_TT + t] / (float)C - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float y0 = (acc[t][0] - mean) * rstd * g0 + be0, y1 = (acc[t][1] - mean) * rstd * g1 + be1;
+    reinterpret_cast<uint32_t*>(out + ((long long)b * T + t0 + t) * C)[cp] = pack_bf16x2(silu_f(y0), silu_f(y1));
+  }
+}
+
 // y = SiLU(LN(conv_out)) with mean / variance from the accumulated (sum, sum of squares): one warp per frame
 template <int NV, bool X3>
 __global__ void __launch_bounds__(256)
@@ -537,6 +637,24 @@ int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, cons
   conv_dw_kernel<KK, XX><<<grid, 128, 0, stream>>>(x, pad_glu, dw_w, dw_b, norm_w, norm_b, bn_mean, bn_var, use_ln, eps, \
                                                    conv_tmp, stats, out, T, C, K, causal, conv_chunk)
   RVB_REQUIRE(conv_chunk <= 0 || !causal, "conv_mid: chunk-local convolution is the non-causal streaming mode");
+  {
+    static int fused_sel = -1;   // RVB_CONV_FUSED=0: the two-kernel LayerNorm path (A/B aid)
+    if (fused_sel < 0) {
+      const char* e = getenv("RVB_CONV_FUSED");
+      fused_sel = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    if (fused_sel && use_ln && !x3 && conv_chunk <= 0 && (K == 15 || K == 7) && C2 <= 512) {
+      const int threads = ((C2 + 31) / 32) * 32;
+      dim3 g1((T + CM_TT - 1) / CM_TT, B);
+      if (K == 15)
+        conv_dw_ln_fused_kernel<15><<<g1, threads, 0, stream>>>(x, pad_glu, dw_w, dw_b, norm_w, norm_b, eps, out, T, C, causal);
+      else
+        conv_dw_ln_fused_kernel<7><<<g1, threads, 0, stream>>>(x, pad_glu, dw_w, dw_b, norm_w, norm_b, eps, out, T, C, causal);
+      RVB_COUNT_LAUNCH();
+      RVB_CHECK_LAUNCH();
+      return 0;
+    }
+  }
   if (x3) {  // accurate mode: the generic tap loop (no register-resident halo) is fast enough
     RVB_DW(0, true);
   } else if (conv_chunk > 0) {
