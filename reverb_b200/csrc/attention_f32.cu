@@ -101,16 +101,43 @@ attention_f32_kernel(AttnF32Args a) {
   __syncwarp();
   const float inv = sum > 0.f ? 1.f / sum : 0.f;  // fully masked row -> zeros (softmax NaN -> masked_fill 0 in the reference)
   bf16* orow = a.out + ((long long)g * a.Tq + i) * a.ldo + h * a.dk;
-  for (int c = lane; c < a.dk; c += 32) {
-    float o = 0.f;
-    for (int j = lo; j < hi; ++j) {
+  // o = sum_j a_j v_j: a lane owns two adjacent columns (one 4-byte load per key row, the warp reads the row's d_k * 2 bytes
+  // contiguously); four keys in flight per lane
+  for (int c = 2 * lane; c < a.dk; c += 64) {
+    float o0 = 0.f, o1 = 0.f;
+    auto vrow_of = [&](int j) -> const bf16* {
       const long long vr = klist ? (long long)klist[j] : (long long)g * a.Tk + j;
-      const bf16* vrow = a.v + vr * a.ldv + h * a.dk;
-      o = fmaf(sc[j] * inv, ld_pair(vrow + c, a.v_lo), o);
+      return a.v + vr * a.ldv + h * a.dk + c;
+    };
+    auto ld2 = [&](const bf16* vp) -> float2 {
+      float2 t = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vp));
+      if (a.v_lo) {
+        const float2 u = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(vp + a.v_lo));
+        t.x += u.x;
+        t.y += u.y;
+      }
+      return t;
+    };
+    int j = lo;
+    for (; j + 4 <= hi; j += 4) {
+      const float2 v0 = ld2(vrow_of(j)), v1 = ld2(vrow_of(j + 1)), v2 = ld2(vrow_of(j + 2)), v3 = ld2(vrow_of(j + 3));
+      const float w0 = sc[j] * inv, w1 = sc[j + 1] * inv, w2 = sc[j + 2] * inv, w3 = sc[j + 3] * inv;
+      o0 = fmaf(w0, v0.x, o0); o1 = fmaf(w0, v0.y, o1);
+      o0 = fmaf(w1, v1.x, o0); o1 = fmaf(w1, v1.y, o1);
+      o0 = fmaf(w2, v2.x, o0); o1 = fmaf(w2, v2.y, o1);
+      o0 = fmaf(w3, v3.x, o0); o1 = fmaf(w3, v3.y, o1);
     }
-    const bf16 hh = __float2bfloat16(o);
-    orow[c] = hh;
-    if (a.o_lo) orow[a.o_lo + c] = __float2bfloat16(o - __bfloat162float(hh));
+    for (; j < hi; ++j) {
+      const float2 v0 = ld2(vrow_of(j));
+      const float w0 = sc[j] * inv;
+      o0 = fmaf(w0, v0.x, o0);
+      o1 = fmaf(w0, v0.y, o1);
+    }
+    const bf16 h0 = __float2bfloat16(o0), h1 = __float2bfloat16(o1);
+    *reinterpret_cast<__nv_bfloat162*>(orow + c) = __nv_bfloat162(h0, h1);
+    if (a.o_lo)
+      *reinterpret_cast<__nv_bfloat162*>(orow + a.o_lo + c) =
+          __nv_bfloat162(__float2bfloat16(o0 - __bfloat162float(h0)), __float2bfloat16(o1 - __bfloat162float(h1)));
   }
 }
 
@@ -119,6 +146,9 @@ int launch_attention_f32(const AttnF32Args& a, cudaStream_t stream) {
   RVB_REQUIRE(a.ldk % 8 == 0 && a.ldp % 8 == 0 && a.k_lo % 8 == 0 && a.p_lo % 8 == 0 &&
                   ((uintptr_t)a.k & 15) == 0 && ((uintptr_t)a.p & 15) == 0,
               "attention_f32: key rows must be 16-byte aligned");
+  RVB_REQUIRE(a.ldv % 2 == 0 && a.v_lo % 2 == 0 && a.ldo % 2 == 0 && a.o_lo % 2 == 0 && ((uintptr_t)a.v & 3) == 0 &&
+                  ((uintptr_t)a.out & 3) == 0,
+              "attention_f32: value / output rows must be 4-byte aligned");
   RVB_REQUIRE((a.chunk <= 0) || a.Tq == a.Tk, "attention_f32: causal / chunk masks need Tq == Tk");
   if (a.groups <= 0 || a.Tq <= 0) return 0;
   const size_t smem = (size_t)AF_WARPS * (a.Tk + 2 * a.dk) * sizeof(float);

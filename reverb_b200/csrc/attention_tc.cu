@@ -530,6 +530,32 @@ relpos_prep_vec_kernel(const bf16* __restrict__ k, long long ldk, const bf16* __
   }
 }
 
+__global__ void relpos_vp_kernel(const bf16* __restrict__ pos, long long ldp, const float* __restrict__ bias_v,
+                                 float* __restrict__ vp, int T, int L, int H, int dk) {
+  // one warp per (l, h, t)
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (w >= (long long)L * H * T) return;
+  const int t = (int)(w % T), h = (int)((w / T) % H), l = (int)(w / ((long long)T * H));
+  const int d = H * dk;
+  const bf16* pr = pos + (long long)t * ldp + (long long)l * d + h * dk;
+  const float* v = bias_v + (long long)l * d + h * dk;
+  float acc = 0.f;
+  for (int c = lane; c < dk; c += 32) acc += v[c] * __bfloat162float(pr[c]);
+  acc = warp_sum(acc);
+  if (lane == 0) vp[w] = acc;
+}
+
+int launch_relpos_vp(const bf16* pos, int ldp, const float* bias_v_all, float* vp, int T, int L, int H, int dk,
+                     cudaStream_t stream) {
+  const long long warps = (long long)L * H * T;
+  if (warps <= 0) return 0;
+  relpos_vp_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, stream>>>(pos, ldp, bias_v_all, vp, T, L, H, dk);
+  RVB_COUNT_LAUNCH();
+  RVB_CHECK_LAUNCH();
+  return 0;
+}
+
 int launch_relpos_prep(const bf16* k, int ldk, const bf16* pos, int ldp, const float* bias_u, const float* bias_v,
                        bf16* kpp, float* cbias, int B, int T, int H, int dk, cudaStream_t stream) {
   RVB_REQUIRE(dk % 2 == 0, "relpos_prep: d_k must be even");

@@ -157,6 +157,7 @@ struct rvb_model {
   Linear conv2;    // (d, 9*d) ordered (kh, kw, c)
   Linear embed;    // (d, F2*d) ordered (f, c), scaled by sqrt(d)
   Linear pos_all;  // (L*d, d) stacked linear_pos weights, no bias
+  float* pos_v_all = nullptr;  // (L, d) stacked pos_bias_v (for the input-independent v . pos table)
   std::vector<EncLayer> enc;
   Norm after_norm;
   Linear ctc;
@@ -171,6 +172,9 @@ struct rvb_model {
   DevBuf ws_encbf, ws_logits, ws_dec[12], ws_search, ws_misc, ws_kpp, ws_cbias;
   HostPinned pin_a, pin_b, pin_c, pin_d, pin_e;
   int pe_T = 0;
+  int pall_T = 0;               // ws_pall / ws_vp hold linear_pos(pos_emb) and v . pos for this many frames
+  const void* pall_ptr = nullptr;
+  DevBuf ws_vp;
   int lens_slot = 0;
   int lens_B = 0;
   static constexpr int kTickets = 4;
@@ -414,7 +418,7 @@ static int finalize_model(rvb_model* m) {
   }
   if (load_norm(m, "encoder.after_norm", d, &m->after_norm)) return -1;
   m->enc.resize(L);
-  std::vector<float> posw;
+  std::vector<float> posw, posv;
   for (int i = 0; i < L; ++i) {
     EncLayer& E = m->enc[i];
     const std::string p = "encoder.encoders." + std::to_string(i);
@@ -434,6 +438,7 @@ static int finalize_model(rvb_model* m) {
     posw.insert(posw.end(), t->begin(), t->end());
     if (need(m, p + ".self_attn.pos_bias_u", d, &t) || upload_f32(m, t->data(), d, &E.pos_u)) return -1;
     if (need(m, p + ".self_attn.pos_bias_v", d, &t) || upload_f32(m, t->data(), d, &E.pos_v)) return -1;
+    posv.insert(posv.end(), t->begin(), t->end());
     if (load_linear_glu(m, p + ".conv_module.pointwise_conv1", d, d, &E.pw1, &E.pad_glu) ||
         load_linear(m, p + ".conv_module.pointwise_conv2", d, d, &E.pw2))
       return -1;
@@ -451,6 +456,7 @@ static int finalize_model(rvb_model* m) {
   if (upload_w(m, posw.data(), (size_t)L * d, d, &m->pos_all.w)) return -1;
   m->pos_all.N = L * d;
   m->pos_all.K = d;
+  if (upload_f32(m, posv.data(), posv.size(), &m->pos_v_all)) return -1;
   if (load_linear(m, "ctc.ctc_lo", c.vocab, d, &m->ctc)) return -1;
   if (c.dec_blocks > 0 && find_host(m, "decoder.left_decoder.embed.0.weight")) {
     if (load_decoder(m, "left_decoder", c.dec_blocks, &m->dec_l)) return -1;
@@ -569,10 +575,13 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       m->ws_att.ensure((size_t)M * d * 2 * pm) || m->ws_pw.ensure((size_t)M * d * 2 * pm) ||
       m->ws_cm.ensure((size_t)M * d * 2 * pm) || m->ws_y.ensure((size_t)M * d * 4) ||
       m->ws_ybf.ensure((size_t)M * d * 2 * pm) || m->ws_pall.ensure((size_t)Tp * L * d * 2 * pm) ||
-      m->ws_kpp.ensure((size_t)M * d * 2) ||
+      m->ws_kpp.ensure((size_t)M * d * 2) || m->ws_vp.ensure((size_t)L * H * Tp * sizeof(float)) ||
       m->ws_cbias.ensure(((size_t)B * H * Tp + (size_t)M * 2 * ((d / 2 + 127) / 128)) * 4))
     return -1;
   const bool tc_attn = attn_impl() == 1 && dk == 64 && !x3;
+  // rel-pos key transform inside the [q; k; v] projection's epilogue (default); RVB_RELPOS=prep keeps the separate kernel
+  const char* rp_env = getenv("RVB_RELPOS");   // read per call: tests A/B the two paths in one process
+  const bool relpos_fused = tc_attn && !(rp_env && strcmp(rp_env, "prep") == 0) && get_gemm_impl() != 1;
   bf16* c1 = m->ws_c1.as<bf16>();
   bf16* c2 = m->ws_c2.as<bf16>();
   float* x = m->ws_x.as<float>();
@@ -600,8 +609,14 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
     }
     m->pe_T = Tp;
   }
-  if (gemm(m, m->ws_pe.as<bf16>(), m->pos_all, Tp, ACT_NONE, OUT_BF16, pall, 1.f, stream, nullptr, 0, 0, false))
-    return -1;
+  // ... which depends on the frame count only: kept across calls of the same shape, with the table v_h . pos[t]
+  if (m->pall_T != Tp || m->pall_ptr != (const void*)pall) {
+    if (gemm(m, m->ws_pe.as<bf16>(), m->pos_all, Tp, ACT_NONE, OUT_BF16, pall, 1.f, stream, nullptr, 0, 0, false))
+      return -1;
+    if (!x3 && launch_relpos_vp(pall, L * d, m->pos_v_all, m->ws_vp.as<float>(), Tp, L, H, dk, stream)) return -1;
+    m->pall_T = Tp;
+    m->pall_ptr = pall;
+  }
 
   // subsampling: CMVN + conv1 + ReLU ; conv2 + ReLU as implicit GEMM ; Linear(19 d -> d) * sqrt(d)
   if (launch_conv1(d_feats, m->cmvn_mean, m->cmvn_istd, m->conv1_w, m->conv1_b, c1, B, T, F, d, T1, T1h, F1, stream, x3))
@@ -646,7 +661,29 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
     if (gemm(m, h, E.ffm2, (int)M, ACT_NONE, OUT_RESID_F32, x, 0.5f, stream)) return -1;
     // rel-pos MHSA                                                            (encoder_layer.py:209-217)
     if (launch_layernorm(x, E.norm_mha.g, E.norm_mha.b, 1e-5f, (int)M, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
-    if (gemm(m, n, E.qkv, (int)M, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
+    if (relpos_fused) {
+      GemmArgs g;
+      g.A = n;
+      g.W = E.qkv.w;
+      g.M = (int)M;
+      g.N = E.qkv.N;
+      g.K = E.qkv.K;
+      g.bias = E.qkv.b;
+      g.act = ACT_NONE;
+      g.out_mode = OUT_BF16;
+      g.out = qkv;
+      g.rp_pos = pall + (size_t)l * d;
+      g.rp_ldp = L * d;
+      g.rp_T = Tp;
+      g.rp_H = H;
+      g.rp_col0 = d;
+      g.rp_u = E.pos_u;
+      g.rp_vp = m->ws_vp.as<float>() + (size_t)l * H * Tp;
+      g.rp_cb = m->ws_cbias.as<float>();
+      if (launch_gemm(g, stream)) return -1;
+    } else if (gemm(m, n, E.qkv, (int)M, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) {
+      return -1;
+    }
     if (x3) {
       // accurate mode: the reference's two-product rel-pos attention in fp32 (attention_f32.cu) on the hi/lo pairs
       AttnF32Args a;
@@ -676,16 +713,16 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       // s = (q . (k + p) + (u . k + v . p)) / sqrt(d_k): fold the position term into the keys and a key bias
       bf16* kpp = m->ws_kpp.as<bf16>();
       float* cb = m->ws_cbias.as<float>();
-      if (launch_relpos_prep(qkv + d, 3 * d, pall + (size_t)l * d, L * d, E.pos_u, E.pos_v, kpp, cb, B, Tp, H, dk,
-                             stream))
+      if (!relpos_fused && launch_relpos_prep(qkv + d, 3 * d, pall + (size_t)l * d, L * d, E.pos_u, E.pos_v, kpp, cb, B, Tp, H,
+                                              dk, stream))
         return -1;
       AttnTcArgs a;
       a.q = qkv;
-      a.k = kpp;
+      a.k = relpos_fused ? qkv + d : kpp;   // fused: the projection already wrote K'' over the key columns
       a.v = qkv + 2 * d;
       a.out = att;
       a.ldq = 3 * d;
-      a.ldk = d;
+      a.ldk = relpos_fused ? 3 * d : d;
       a.ldv = 3 * d;
       a.ldo = d;
       a.groups = B;
@@ -1768,6 +1805,7 @@ RVB_API rvb_model* rvb_model_fork(rvb_model* m) {
   f->conv2 = m->conv2;
   f->embed = m->embed;
   f->pos_all = m->pos_all;
+  f->pos_v_all = m->pos_v_all;
   f->enc = m->enc;
   f->after_norm = m->after_norm;
   f->ctc = m->ctc;
@@ -1801,7 +1839,7 @@ RVB_API void rvb_model_destroy(rvb_model* m) {
   for (void* p : m->owned) cudaFree(p);
   DevBuf* bufs[] = {&m->ws_c1, &m->ws_c2, &m->ws_x, &m->ws_n, &m->ws_h, &m->ws_qkv, &m->ws_att, &m->ws_pw, &m->ws_cm,
                     &m->ws_y, &m->ws_ybf, &m->ws_pe, &m->ws_pall, &m->ws_lens, &m->ws_encbf, &m->ws_logits,
-                    &m->ws_search, &m->ws_misc, &m->ws_kpp, &m->ws_cbias, &m->ws_fold};
+                    &m->ws_search, &m->ws_misc, &m->ws_kpp, &m->ws_cbias, &m->ws_fold, &m->ws_vp};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : m->ws_dec) b.release();
   if (m->tickets) {

@@ -62,6 +62,12 @@ struct GemmKParams {
   float2* lse_part;
   float* lse_tgt;
   int lse_nslab;
+  const bf16* rp_pos;   // EPI_BF16_RELPOS (GemmArgs::rp_*)
+  long long rp_ldp;
+  int rp_T, rp_H, rp_col0;
+  const float* rp_u;
+  const float* rp_vp;
+  float* rp_cb;
   int x3;              // bf16x3 accurate mode: num_k_blocks = 3 * kb_seg, pass s reads A half (s == 1), W half (s == 2)
   int kb_seg;          // k-blocks per pass (K / 64)
   int a_lo_ofs;        // column offset (elements) of the lo half of A: K (plain) or C (conv_mode: channel offset)
@@ -112,7 +118,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // Epilogue variants (compile-time): the hot combinations get straight-line code, everything else goes through the
 // generic runtime path.  EPI_GENERIC reads act / out_mode from the kernel parameters.
 enum Epi { EPI_BF16 = 0, EPI_BF16_RELU = 1, EPI_BF16_SILU = 2, EPI_F32 = 3, EPI_RESID = 4, EPI_GENERIC = 5, EPI_GLU = 6,
-           EPI_LSE = 7 };
+           EPI_LSE = 7, EPI_BF16_RELPOS = 8 };
 
 __host__ __device__ inline int select_epi(int act, int out_mode) {
   if (act == ACT_GLU) return EPI_GLU;
@@ -463,7 +469,8 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
       tmem_ld_wait();
       if (orow >= 0) store_glu(p, orow, n0_tile + c, av, gv);
     }
-  } else if ((EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_SILU) && p.bf16_coalesced) {
+  } else if ((EPI == EPI_BF16 || EPI == EPI_BF16_RELU || EPI == EPI_BF16_SILU || EPI == EPI_BF16_RELPOS) &&
+             p.bf16_coalesced) {
     // bf16 outputs: 64 accumulator columns (= 128 bytes per row) per round through the warp's staging tile, so a
     // warp store covers 4 rows x 128 contiguous bytes instead of 32 rows x 16 bytes (8x fewer LSU wavefronts)
     const int slot = lane & 7, rsub = lane >> 3;
@@ -486,6 +493,15 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
         tmem_ld_32x32(taddr + c + 32, acc + 32);
         tmem_ld_wait();
         const int n0 = n0_tile + c;
+        // EPI_BF16_RELPOS: this 64-column chunk is one head of the KEY block -> K'' = k + pos[t], key bias u.k + vp
+        bool kcols = false;
+        int rp_t = 0, rp_hc = 0;
+        float rp_acc = 0.f;
+        if constexpr (EPI == EPI_BF16_RELPOS) {
+          kcols = n0 >= p.rp_col0 && n0 < p.rp_col0 + p.rp_H * 64;
+          rp_hc = n0 - p.rp_col0;
+          rp_t = orow >= 0 ? (int)(orow % p.rp_T) : 0;
+        }
         // PAIR (bf16x3): the tile is written twice, first hi = bf16(v), then the residue lo = bf16(v - hi)
         constexpr int nparts = PAIR ? 2 : 1;
 #pragma unroll 1
@@ -521,6 +537,22 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
           }
+          if constexpr (EPI == EPI_BF16_RELPOS) {
+            if (kcols) {
+              const uint4 pv = *reinterpret_cast<const uint4*>(p.rp_pos + (long long)rp_t * p.rp_ldp + rp_hc + 8 * j);
+              const float4 u0 = __ldg(reinterpret_cast<const float4*>(p.rp_u + rp_hc + 8 * j));
+              const float4 u1 = __ldg(reinterpret_cast<const float4*>(p.rp_u + rp_hc + 8 * j) + 1);
+              const float uu[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+              const float2 p0 = unpack_bf16x2(pv.x), p1 = unpack_bf16x2(pv.y), p2 = unpack_bf16x2(pv.z), p3 = unpack_bf16x2(pv.w);
+              const float pp[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float kq = __bfloat162float(__float2bfloat16(v[e]));   // the key as the projection would store it
+                rp_acc = fmaf(uu[e], kq, rp_acc);
+                v[e] = kq + pp[e];
+              }
+            }
+          }
           if (PAIR && part == 1) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[e] -= __bfloat162float(__float2bfloat16(v[e]));
@@ -540,6 +572,12 @@ __device__ __forceinline__ void drain_tile(const GemmKParams& p, const TileCoord
             *reinterpret_cast<uint4*>(out + ro[it] + c + (PAIR ? part * p.out_split : 0)) = u;
         }
         __syncwarp();
+        }
+        if constexpr (EPI == EPI_BF16_RELPOS) {
+          if (kcols && orow >= 0) {
+            const int hh = rp_hc >> 6;
+            p.rp_cb[((orow / p.rp_T) * p.rp_H + hh) * (long long)p.rp_T + rp_t] = rp_acc + __ldg(p.rp_vp + (long long)hh * p.rp_T + rp_t);
+          }
         }
       } else {
         for (int cc = c; cc < c + 64 && cc < c1; cc += 32) {
@@ -1146,7 +1184,7 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   }
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmKParams) = nullptr;
   const bool pair = a.out_split > 0;
-  switch (select_epi(a.act, a.out_mode)) {
+  switch (a.rp_pos ? (int)EPI_BF16_RELPOS : select_epi(a.act, a.out_mode)) {
     case EPI_BF16: kern = pair ? gemm_tc_kernel<BN, EPI_BF16, true> : gemm_tc_kernel<BN, EPI_BF16, false>; break;
     case EPI_BF16_RELU: kern = pair ? gemm_tc_kernel<BN, EPI_BF16_RELU, true> : gemm_tc_kernel<BN, EPI_BF16_RELU, false>; break;
     case EPI_BF16_SILU: kern = pair ? gemm_tc_kernel<BN, EPI_BF16_SILU, true> : gemm_tc_kernel<BN, EPI_BF16_SILU, false>; break;
@@ -1154,6 +1192,7 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     case EPI_RESID: kern = gemm_tc_kernel<BN, EPI_RESID, false>; break;
     case EPI_GLU: kern = pair ? gemm_tc_kernel<BN, EPI_GLU, true> : gemm_tc_kernel<BN, EPI_GLU, false>; break;
     case EPI_LSE: kern = gemm_tc_kernel<BN, EPI_LSE, false>; break;
+    case EPI_BF16_RELPOS: kern = gemm_tc_kernel<BN, EPI_BF16_RELPOS, false>; break;
     default: kern = gemm_tc_kernel<BN, EPI_GENERIC, false>; break;
   }
   RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -1207,7 +1246,7 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   }
   void (*kern)(const CUtensorMap, const CUtensorMap, const GemmKParams) = nullptr;
   const bool pair = a.out_split > 0;
-  switch (select_epi(a.act, a.out_mode)) {
+  switch (a.rp_pos ? (int)EPI_BF16_RELPOS : select_epi(a.act, a.out_mode)) {
     case EPI_BF16: kern = pair ? gemm_tc2_kernel<BN, EPI_BF16, true> : gemm_tc2_kernel<BN, EPI_BF16, false>; break;
     case EPI_BF16_RELU: kern = pair ? gemm_tc2_kernel<BN, EPI_BF16_RELU, true> : gemm_tc2_kernel<BN, EPI_BF16_RELU, false>; break;
     case EPI_BF16_SILU: kern = pair ? gemm_tc2_kernel<BN, EPI_BF16_SILU, true> : gemm_tc2_kernel<BN, EPI_BF16_SILU, false>; break;
@@ -1215,6 +1254,7 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
     case EPI_RESID: kern = gemm_tc2_kernel<BN, EPI_RESID, false>; break;
     case EPI_GLU: kern = pair ? gemm_tc2_kernel<BN, EPI_GLU, true> : gemm_tc2_kernel<BN, EPI_GLU, false>; break;
     case EPI_LSE: kern = gemm_tc2_kernel<BN, EPI_LSE, false>; break;
+    case EPI_BF16_RELPOS: kern = gemm_tc2_kernel<BN, EPI_BF16_RELPOS, false>; break;
     default: kern = gemm_tc2_kernel<BN, EPI_GENERIC, false>; break;
   }
   RVB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
@@ -1283,6 +1323,21 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   p.lse_part = a.lse_part;
   p.lse_tgt = a.lse_tgt;
   p.lse_nslab = lse_slabs(a.N);
+  p.rp_pos = a.rp_pos;
+  p.rp_ldp = a.rp_ldp;
+  p.rp_T = a.rp_T;
+  p.rp_H = a.rp_H;
+  p.rp_col0 = a.rp_col0;
+  p.rp_u = a.rp_u;
+  p.rp_vp = a.rp_vp;
+  p.rp_cb = a.rp_cb;
+  if (a.rp_pos) {
+    RVB_REQUIRE(a.out_mode == OUT_BF16 && a.act == ACT_NONE && a.out_split == 0 && !a.conv_mode && a.rp_T > 0 &&
+                    a.rp_col0 % 64 == 0 && a.rp_ldp % 8 == 0 && a.N % 64 == 0 && a.rp_u && a.rp_vp && a.rp_cb &&
+                    (reinterpret_cast<uintptr_t>(a.rp_pos) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.rp_u) & 15) == 0,
+                "gemm: rel-pos epilogue needs a plain bf16 output, 64-aligned key columns and 16-byte aligned tables");
+    RVB_REQUIRE(get_gemm_impl() != 1, "gemm: rel-pos epilogue is not built for the simt bring-up kernel");
+  }
   if (a.out_mode == OUT_LSE) {
     RVB_REQUIRE(a.lse_gather && a.lse_part && a.lse_tgt && a.act == ACT_NONE && !a.conv_mode && a.N > 128,
                 "gemm: OUT_LSE needs gather / partial / target buffers, no activation and N > 128");

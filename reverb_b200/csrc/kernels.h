@@ -55,6 +55,16 @@ struct GemmArgs {
   // conv_mode + out_split: output row (b, t') holds [hi (F2*N) | lo (F2*N)] (out_split = F2*N), i.e. element (b,t',f,n)
   // -> out[((b*T2 + t') * 2*F2 + f) * ldo + n] — the pair-layout A operand of the Linear(F2*C -> d) that follows
   int conv_pair_out = 0;
+  // rel-pos attention folded into the fused [q; k; v] projection (OUT_BF16, no activation, d_k = 64): the epilogue
+  // replaces the key columns [rp_col0, rp_col0 + rp_H*64) by K'' = bf16(k + pos[t]) (t = row % rp_T, pos row stride
+  // rp_ldp) and writes the per-key bias rp_cb[(row / rp_T) * rp_H + h, t] = u_h . k + rp_vp[h, t] — what the separate
+  // relpos_prep kernel (attention_tc.cu) computes from the stored projection; rp_vp[h, t] = v_h . pos[t, h] is
+  // input-independent (launch_relpos_vp).
+  const bf16* rp_pos = nullptr;
+  int rp_ldp = 0, rp_T = 0, rp_H = 0, rp_col0 = 0;
+  const float* rp_u = nullptr;
+  const float* rp_vp = nullptr;
+  float* rp_cb = nullptr;
   // OUT_LSE
   const int* lse_gather = nullptr;   // (M) column index per row, < 0 = none
   float2* lse_part = nullptr;        // (M, lse_slabs(N)) {max, sum exp(x - max)}; slabs without columns hold {-inf, 0}
@@ -164,6 +174,9 @@ struct AttnTcArgs {
   float scale = 1.0f;
 };
 int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream);
+// vp[l, h, t] = v_{l,h} . pos[t, l*d + h*dk ...]  (pos: (T, L*d) bf16 = all layers' linear_pos(pos_emb); bias_v: (L, d))
+int launch_relpos_vp(const bf16* pos, int ldp, const float* bias_v_all, float* vp, int T, int L, int H, int dk,
+                     cudaStream_t stream);
 // K'' = k + pos (bf16, (B*T, H*dk) dense) and cbias[b,h,t] = u_h . k + v_h . pos
 int launch_relpos_prep(const bf16* k, int ldk, const bf16* pos, int ldp, const float* bias_u, const float* bias_v,
                        bf16* kpp, float* cbias, int B, int T, int H, int dk, cudaStream_t stream);

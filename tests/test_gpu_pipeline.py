@@ -89,6 +89,29 @@ def test_fbank_and_encoder_vs_reference_fixture(asr, golden_cases, model_dirs, c
 
 
 @pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_relpos_in_projection_epilogue_equals_the_separate_kernel(asr, golden_cases, case):
+    """The rel-pos key transform (K'' = k + pos, key bias u.k + v.pos) runs in the [q; k; v] GEMM epilogue; RVB_RELPOS=prep
+    keeps the separate relpos_prep kernel.  Same bf16 roundings, fp32 sums in a different order: encoder_out must agree
+    far inside the bf16 tolerance."""
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    fb, fl = next(iter(m.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])))
+    enc_fused, _ = m.model._forward_encoder(fb, fl, cat)
+    enc_fused = enc_fused.clone()
+    os.environ["RVB_RELPOS"] = "prep"
+    try:
+        enc_prep, _ = m.model._forward_encoder(fb, fl, cat)
+        enc_prep = enc_prep.clone()
+    finally:
+        del os.environ["RVB_RELPOS"]
+    rr = _rel_rms(enc_fused.float().cpu().numpy(), enc_prep.float().cpu().numpy())
+    print(f"[{case}] fused vs separate rel-pos: encoder_out rel-rms {rr:.2e}")
+    assert rr < 5e-4
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
 def test_encoder_and_decoder_vs_bf16_emulating_oracle(asr, golden_cases, model_dirs, case):
     """Tight check of the kernels' logic: against the oracle with EMULATE_BF16 (it rounds to bf16 exactly where the
     engine stores bf16, everything else fp32) the only difference left is accumulation order, so the tolerance is
