@@ -90,6 +90,8 @@ struct AttnTcParams {
   int chunk;   // > 0: chunk mask (utils/mask.py subsequent_chunk_mask): key j visible to query row i iff
                //      max(0, (i/chunk - left) * chunk) [0 when left < 0] <= j < (i/chunk + 1) * chunk; chunk 1 = causal
   int left;    // number of left chunks, < 0 = all
+  const uint32_t* key_bits;  // optional per-(query row, key) visibility bits (AttnTcArgs::key_bits)
+  int bits_ld;
   float scale_log2;
 };
 
@@ -323,6 +325,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
+      if (p.key_bits) {
+        // arbitrary visibility (prefix-tree self-attention: a node sees its ancestors): one bit per key of this row
+        const int kbase = (jt0 + j) * AT_BN + c0;
+        const uint32_t* mw = p.key_bits + ((long long)g * p.Tq + min(q0 + r, p.Tq - 1)) * p.bits_ld + (kbase >> 5);
+        tmax = -INFINITY;
+#pragma unroll
+        for (int wi = 0; wi < CW / 32; ++wi) {
+          const uint32_t word = __ldg(mw + wi);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const float x = ((word >> e) & 1u) ? __uint_as_float(sv[wi * 32 + e]) : -INFINITY;
+            sv[wi * 32 + e] = __float_as_uint(x);
+            tmax = fmaxf(tmax, x);
+          }
+        }
+      }
       if (SPLIT) {  // the row's tile maximum = max of the two halves (both halves must move m_run identically)
         s_xch[(j & 1) * 256 + hh * 128 + r] = tmax;
         pair_sync();
@@ -360,7 +378,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_eff = (m_run == -INFINITY) ? 0.f : m_run;  // no visible key yet: every x is -inf -> p = 0
       const float2 one2 = make_float2(1.f, 1.f), negm2 = make_float2(-m_eff, -m_eff);
       // the polynomial exp2 path needs finite arguments: tiles fully inside [0, klen) without a chunk-mask boundary
-      const bool poly_ok = (p.chunk == 0) && ((jt0 + j + 1) * AT_BN <= klen) && (m_run != -INFINITY) &&
+      const bool poly_ok = (p.chunk == 0) && (p.key_bits == nullptr) && ((jt0 + j + 1) * AT_BN <= klen) && (m_run != -INFINITY) &&
                            __all_sync(0xffffffffu, m_run != -INFINITY);
       // P~ goes to shared memory chunk by chunk (8 keys = 16 bytes) as it is produced, so only one chunk of packed
       // probabilities is ever live in registers.  The buffer was last read by PV(j-2), which has had a whole tile of
@@ -628,6 +646,9 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
   p.H = a.H;
   p.chunk = a.causal ? 1 : (a.chunk > 0 ? a.chunk : 0);
   p.left = a.causal ? -1 : a.left_chunks;
+  p.key_bits = a.key_bits;
+  p.bits_ld = a.bits_ld;
+  RVB_REQUIRE(a.key_bits == nullptr || a.bits_ld >= 2 * ((a.Tk + 63) / 64), "attention_tc: key_bits rows are too short");
   p.scale_log2 = a.scale * 1.4426950408889634f;
   CUtensorMap tmQ, tmK, tmV;
   if (tmap_2d(&tmQ, a.q, (long long)a.H * AT_DK, (long long)a.groups * a.Tq, a.ldq, 128)) return -1;

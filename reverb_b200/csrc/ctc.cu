@@ -840,7 +840,8 @@ trie_inputs_kernel(const int* __restrict__ node_of, int nstride, const int* __re
                    const int* __restrict__ node_par, const int* __restrict__ node_dep, int cap,
                    const int* __restrict__ n_nodes, const int* __restrict__ olen, const int* __restrict__ nhyp, int N,
                    int P, int Lp, int eos, int* __restrict__ tok_in, int* __restrict__ pos, int* __restrict__ anc,
-                   int* __restrict__ alen, int* __restrict__ src, int* __restrict__ tgt, int* __restrict__ smap) {
+                   int* __restrict__ alen, int* __restrict__ src, int* __restrict__ tgt, int* __restrict__ smap,
+                   uint32_t* __restrict__ anc_bits, int bits_ld) {
   const int b = blockIdx.x;
   const int nn = n_nodes[b], n = min(nhyp[b], N);
   const int* ntok = node_tok + (size_t)b * cap;
@@ -848,6 +849,18 @@ trie_inputs_kernel(const int* __restrict__ node_of, int nstride, const int* __re
   const int* ndep = node_dep + (size_t)b * cap;
   for (int node = threadIdx.x; node < P; node += blockDim.x) {
     const size_t r = (size_t)b * P + node;
+    if (anc_bits) {  // the same ancestor set as a bit row over the utterance's node slots (tcgen05 attention mask)
+      uint32_t* br = anc_bits + r * bits_ld;
+      for (int w = 0; w < bits_ld; ++w) br[w] = 0u;
+      int cur = node;
+      if (node < nn)
+        for (int t = ndep[node]; t >= 0; --t) {
+          br[cur >> 5] |= 1u << (cur & 31);
+          cur = npar[cur];
+        }
+      else
+        br[node >> 5] = 1u << (node & 31);
+    }
     if (node < nn) {
       const int dep = ndep[node];
       tok_in[r] = ntok[node];
@@ -892,10 +905,12 @@ trie_inputs_kernel(const int* __restrict__ node_of, int nstride, const int* __re
 
 int launch_trie_inputs(const int* node_of, int nstride, const int* node_tok, const int* node_par, const int* node_dep,
                        int cap, const int* n_nodes, const int* olen, const int* nhyp, int B, int N, int P, int Lp, int eos,
-                       int* tok_in, int* pos, int* anc, int* alen, int* src, int* tgt, int* smap, cudaStream_t stream) {
+                       int* tok_in, int* pos, int* anc, int* alen, int* src, int* tgt, int* smap, cudaStream_t stream,
+                       uint32_t* anc_bits, int bits_ld) {
   if (B <= 0) return 0;
+  RVB_REQUIRE(anc_bits == nullptr || bits_ld * 32 >= P, "trie_inputs: %d mask words cannot hold %d node slots", bits_ld, P);
   trie_inputs_kernel<<<B, 256, 0, stream>>>(node_of, nstride, node_tok, node_par, node_dep, cap, n_nodes, olen, nhyp, N,
-                                            P, Lp, eos, tok_in, pos, anc, alen, src, tgt, smap);
+                                            P, Lp, eos, tok_in, pos, anc, alen, src, tgt, smap, anc_bits, bits_ld);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
   return 0;

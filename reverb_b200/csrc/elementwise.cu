@@ -638,10 +638,13 @@ int launch_conv_mid(const bf16* x, const float* pad_glu, const float* dw_w, cons
                                                    conv_tmp, stats, out, T, C, K, causal, conv_chunk)
   RVB_REQUIRE(conv_chunk <= 0 || !causal, "conv_mid: chunk-local convolution is the non-causal streaming mode");
   {
-    static int fused_sel = -1;   // RVB_CONV_FUSED=0: the two-kernel LayerNorm path (A/B aid)
+    // RVB_CONV_FUSED=1: the single-kernel variant.  Measured SLOWER at the benchmark shape (0.226 ms vs 0.094 + 0.059 ms
+    // per layer, profiles/r2f_launches_summary.md): 512 threads x 98 registers leave one CTA per SM and the three phases
+    // (taps, statistics, normalise) run back to back instead of overlapping across CTAs.  Kept as an option.
+    static int fused_sel = -1;
     if (fused_sel < 0) {
       const char* e = getenv("RVB_CONV_FUSED");
-      fused_sel = (e && atoi(e) == 0) ? 0 : 1;
+      fused_sel = (e && atoi(e) == 1) ? 1 : 0;
     }
     if (fused_sel && use_ln && !x3 && conv_chunk <= 0 && (K == 15 || K == 7) && C2 <= 512) {
       const int threads = ((C2 + 31) / 32) * 32;

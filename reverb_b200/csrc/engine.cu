@@ -1287,7 +1287,11 @@ static int decoder_pass_trie(rvb_model* m, Decoder& D, const bf16* enc_bf, const
   const size_t pm = (size_t)m->pm();
   const int ldv = (V + 3) & ~3;
   DevBuf* w = m->ws_dec;
-  const size_t n_int = (size_t)R * 3 + (size_t)R * Lp + (size_t)E * 2 + (size_t)S * Lp;
+  // bf16 mode: self-attention of the tree on the tcgen05 kernel (dense over the utterance's P node slots, causal tile
+  // range — a parent always precedes its children — plus an ancestor bit mask); accurate mode: fp32 over ancestor lists
+  const bool tc_self = !x3 && attn_impl() == 1 && dk == 64 && !(getenv("RVB_TRIE_ATTN") && strcmp(getenv("RVB_TRIE_ATTN"), "list") == 0);
+  const int bits_ld = 2 * ((P + 63) / 64);
+  const size_t n_int = (size_t)R * 3 + (size_t)R * Lp + (size_t)E * 2 + (size_t)S * Lp + (tc_self ? (size_t)R * bits_ld : 0);
   if (w[0].ensure((size_t)R * d * 4) || w[1].ensure((size_t)R * d * 2 * pm) || w[2].ensure((size_t)R * 3 * d * 2 * pm) ||
       w[3].ensure((size_t)R * d * 2 * pm) || w[4].ensure((size_t)Mem * 2 * d * 2 * pm) ||
       w[5].ensure((size_t)R * c.dec_ffn_dim * 2 * pm) || w[6].ensure((size_t)R * d * 2 * pm) ||
@@ -1307,10 +1311,11 @@ static int decoder_pass_trie(rvb_model* m, Decoder& D, const bf16* enc_bf, const
   int* src = anc + (size_t)R * Lp;
   int* tgt = src + E;
   int* smap = tgt + E;
+  uint32_t* anc_bits = tc_self ? reinterpret_cast<uint32_t*>(smap + (size_t)S * Lp) : nullptr;
   bf16* a_out = w[10].as<bf16>();
   float* e_sc = w[11].as<float>();
   if (launch_trie_inputs(tv.node_of, tv.nstride, tv.node_tok, tv.node_par, tv.node_dep, tv.cap, tv.n_nodes, d_olen, d_nhyp,
-                         B, N, P, Lp, eos_id(c), tok_in, pos, anc, alen, src, tgt, smap, stream))
+                         B, N, P, Lp, eos_id(c), tok_in, pos, anc, alen, src, tgt, smap, stream, anc_bits, bits_ld))
     return -1;
   if (launch_embed_posenc_rows(tok_in, pos, D.emb, (int)R, d, x, stream)) return -1;
   for (size_t l = 0; l < D.layers.size(); ++l) {
@@ -1318,7 +1323,25 @@ static int decoder_pass_trie(rvb_model* m, Decoder& D, const bf16* enc_bf, const
     // self-attention of every node over its ancestors (= the causal mask of the flat layout)
     if (launch_layernorm(x, Ld.n1.g, Ld.n1.b, Ld.eps, (int)R, d, n, nullptr, nullptr, 0, 0, stream, x3)) return -1;
     if (gemm(m, n, Ld.qkv, (int)R, ACT_NONE, OUT_BF16, qkv, 1.f, stream)) return -1;
-    {
+    if (tc_self) {
+      AttnTcArgs a;
+      a.q = qkv;
+      a.k = qkv + d;
+      a.v = qkv + 2 * d;
+      a.out = att;
+      a.ldq = a.ldk = a.ldv = 3 * d;
+      a.ldo = d;
+      a.groups = B;
+      a.Tq = P;
+      a.Tk = P;
+      a.H = H;
+      a.dk = dk;
+      a.causal = 1;
+      a.key_bits = anc_bits;
+      a.bits_ld = bits_ld;
+      a.scale = 1.0f / sqrtf((float)dk);
+      if (launch_attention_tc(a, stream)) return -1;
+    } else {
       AttnF32Args a;
       a.q = qkv;
       a.k = qkv + d;

@@ -171,6 +171,10 @@ struct AttnTcArgs {
   const int* k_lens = nullptr;      // (groups) valid keys
   int causal = 0;                   // self-attention with Tq == Tk: key j visible to query i iff j <= i
   int chunk = 0, left_chunks = -1;  // chunk > 0: streaming chunk mask (utils/mask.py:88-123), left_chunks < 0 = all
+  // arbitrary visibility on top of the masks above (prefix-tree self-attention): bit (j & 31) of
+  // key_bits[(group*Tq + i) * bits_ld + (j >> 5)] set <=> key j visible to query row i; bits_ld >= 2 * ceil(Tk / 64)
+  const uint32_t* key_bits = nullptr;
+  int bits_ld = 0;
   float scale = 1.0f;
 };
 int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream);
@@ -234,7 +238,8 @@ int launch_trie_build(const int* tok, int tok_stride, const int* olen, const int
                       cudaStream_t stream);
 int launch_trie_inputs(const int* node_of, int nstride, const int* node_tok, const int* node_par, const int* node_dep,
                        int cap, const int* n_nodes, const int* olen, const int* nhyp, int B, int N, int P, int Lp, int eos,
-                       int* tok_in, int* pos, int* anc, int* alen, int* src, int* tgt, int* smap, cudaStream_t stream);
+                       int* tok_in, int* pos, int* anc, int* alen, int* src, int* tgt, int* smap, cudaStream_t stream,
+                       uint32_t* anc_bits = nullptr, int bits_ld = 0);
 int launch_gather_rows(const bf16* in, const int* idx, bf16* out, int rows, int width, cudaStream_t stream);
 int launch_gather_scores(const float* vals, const int* map, float* out, long long n, cudaStream_t stream);
 // decoder input with a per-row position: x[r, :] = emb[tok[r], :] * sqrt(d) + pe[pos[r], :]
