@@ -22,6 +22,13 @@ class ModelConfig(C.Structure):
         "sos_id", "eos_id", "precision")]
 
 
+class SegConfig(C.Structure):
+    """Mirror of `rvb_seg_config` (include/rvb_diar.h)."""
+    _fields_ = [(n, C.c_int) for n in (
+        "sample_rate", "sinc_filters", "sinc_kernel", "sinc_stride", "conv_channels", "conv_kernel", "lstm_hidden",
+        "lstm_layers", "linear_dim", "linear_layers", "num_classes")]
+
+
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> (restype, argtypes); must list every symbol the header declares (tests/test_abi.py checks)
@@ -75,6 +82,13 @@ SIGNATURES = {
     "rvb_attention_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp, _i, _f, _vp]),
     "rvb_relpos_prep": (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rvb_f32_to_bf16": (_i, [_vp, _vp, _ll, _vp]),
+    # include/rvb_diar.h
+    "rvb_seg_create": (_vp, [C.POINTER(SegConfig)]),
+    "rvb_seg_set_tensor": (_i, [_vp, C.c_char_p, _vp, _ll]),
+    "rvb_seg_finalize": (_i, [_vp]),
+    "rvb_seg_destroy": (None, [_vp]),
+    "rvb_seg_num_frames": (_i, [_vp, _i]),
+    "rvb_seg_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -1,4 +1,4 @@
-"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/rvb_b200.h declares."""
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/*.h declares."""
 import ctypes
 import os
 import re
@@ -7,8 +7,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    with open(os.path.join(ROOT, "include", "rvb_b200.h")) as f:
-        text = f.read()
+    text = ""
+    for h in ("rvb_b200.h", "rvb_diar.h"):
+        with open(os.path.join(ROOT, "include", h)) as f:
+            text += f.read()
     return sorted(set(re.findall(r"RVB_API[^;(]*?\b(rvb_[a-z0-9_]+)\s*\(", text)))
 
 
