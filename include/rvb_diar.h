@@ -53,6 +53,36 @@ RVB_API int rvb_seg_num_frames(const rvb_seg_model* m, int num_samples);
 RVB_API int rvb_seg_forward(rvb_seg_model* m, const float* d_wave, int B, int num_samples, float* d_logp,
                             float* d_sincnet, void* stream);
 
+/* ---- WeSpeaker ResNet34 speaker embedding ------------------------------------------------------------------------
+ * waveform window in [-1, 1] -> x 2^15 -> Kaldi fbank (80 mel, hamming window, 25 / 10 ms, no dither) -> minus the mean
+ * over time -> ResNet34 (BasicBlock [3, 4, 6, 3], m_channels .. 8 m_channels, BatchNorm folded, ReLU) -> weighted
+ * statistics pooling (mean, std over time per (channel, frequency)) -> Linear(embed_dim).
+ * The trunk runs ONCE per window; the S weight rows of a window (the local speakers' activity masks, nearest-
+ * interpolated to the trunk's frame rate like pyannote's StatsPool) only change the pooling. */
+typedef struct rvb_emb_model rvb_emb_model;
+
+typedef struct rvb_emb_config {
+  int sample_rate;   /* 16000 */
+  int num_mel_bins;  /* 80 */
+  int m_channels;    /* 32 */
+  int embed_dim;     /* 256 */
+  int blocks[4];     /* 3, 4, 6, 3 */
+} rvb_emb_config;
+
+RVB_API rvb_emb_model* rvb_emb_create(const rvb_emb_config* cfg);
+/* fp32 host tensors under pyannote's state_dict names: resnet.conv1.weight, resnet.bn1.{weight,bias,running_mean,
+ * running_var}, resnet.layer{1..4}.{i}.{conv1,conv2}.weight, .bn{1,2}.*, .shortcut.0.weight, .shortcut.1.*,
+ * resnet.seg_1.{weight,bias} */
+RVB_API int rvb_emb_set_tensor(rvb_emb_model* m, const char* name, const float* host, long long count);
+RVB_API int rvb_emb_finalize(rvb_emb_model* m);
+RVB_API void rvb_emb_destroy(rvb_emb_model* m);
+/* fbank frames of a window (160000 samples -> 998) */
+RVB_API int rvb_emb_num_frames(const rvb_emb_model* m, int num_samples);
+/* d_wave (B, num_samples) fp32 in [-1, 1]; d_weights (B, S, Tw) fp32 pooling weights or NULL (S = 1, unweighted);
+ * d_emb (B, S, embed_dim) fp32.  d_fbank (optional, B x frames x num_mel_bins): the mean-normalised features. */
+RVB_API int rvb_emb_forward(rvb_emb_model* m, const float* d_wave, int B, int num_samples, const float* d_weights, int S,
+                            int Tw, float* d_emb, float* d_fbank, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -24,6 +24,7 @@ constexpr int FB_WARPS = 8;
 
 struct FbankTables {
   float* window = nullptr;   // [400] povey
+  float* window_hamming = nullptr;   // [400] hamming (WeSpeaker embedding front-end, diar_emb.cu)
   float2* twiddle = nullptr; // [256] (cos, -sin)(2 pi k / 512)
   float2* tw256 = nullptr;   // [256] (cos, -sin)(2 pi j / 256)
   float* mel_w = nullptr;    // [80][FB_MAXW]
@@ -48,6 +49,8 @@ static int init_fbank_tables(const FbankTables** out) {
     double h = 0.5 - 0.5 * cos(2.0 * M_PI * i / (FB_WIN - 1));
     win[i] = (float)pow(h, 0.85);
   }
+  std::vector<float> win_h(FB_WIN);
+  for (int i = 0; i < FB_WIN; ++i) win_h[i] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * i / (FB_WIN - 1)));
   std::vector<float2> tw(FB_NFFT / 2);
   for (int k = 0; k < FB_NFFT / 2; ++k) {
     double a = 2.0 * M_PI * k / FB_NFFT;
@@ -85,6 +88,8 @@ static int init_fbank_tables(const FbankTables** out) {
     for (int k = first; k <= last; ++k) w[b * FB_MAXW + (k - first)] = row[k];
   }
   RVB_CHECK_CUDA(cudaMalloc(&g_fb.window, sizeof(float) * FB_WIN));
+  RVB_CHECK_CUDA(cudaMalloc(&g_fb.window_hamming, sizeof(float) * FB_WIN));
+  RVB_CHECK_CUDA(cudaMemcpy(g_fb.window_hamming, win_h.data(), sizeof(float) * FB_WIN, cudaMemcpyHostToDevice));
   RVB_CHECK_CUDA(cudaMalloc(&g_fb.twiddle, sizeof(float2) * FB_NFFT / 2));
   RVB_CHECK_CUDA(cudaMalloc(&g_fb.tw256, sizeof(float2) * FB_NFFT / 2));
   RVB_CHECK_CUDA(cudaMemcpy(g_fb.tw256, tw2.data(), sizeof(float2) * FB_NFFT / 2, cudaMemcpyHostToDevice));
@@ -278,7 +283,7 @@ fbank_kernel(const TIn* __restrict__ wave_all, long long wave_stride, long long 
 
 template <typename TIn>
 static int launch_fbank_t(const TIn* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream,
-                          int batch = 1, long long wave_stride = 0) {
+                          int batch = 1, long long wave_stride = 0, int window_type = 0) {
   const FbankTables* fb = nullptr;
   if (init_fbank_tables(&fb)) return -1;
   const FbankTables& g_fb = *fb;
@@ -288,7 +293,7 @@ static int launch_fbank_t(const TIn* wave, long long n_samples, float* feats, lo
   if (n_frames <= 0) return 0;
   const long long blocks = (n_frames + FB_WARPS * FB_FPW - 1) / (FB_WARPS * FB_FPW);
   dim3 grid((unsigned)blocks, (unsigned)batch);
-  fbank_kernel<TIn><<<grid, FB_WARPS * 32, 0, stream>>>(wave, wave_stride, n_frames, feats, g_fb.window, g_fb.twiddle,
+  fbank_kernel<TIn><<<grid, FB_WARPS * 32, 0, stream>>>(wave, wave_stride, n_frames, feats, window_type == 1 ? g_fb.window_hamming : g_fb.window, g_fb.twiddle,
                                                        g_fb.tw256, g_fb.mel_w, g_fb.mel_start, g_fb.mel_len);
   RVB_COUNT_LAUNCH();
   RVB_CHECK_LAUNCH();
@@ -302,13 +307,13 @@ int launch_fbank_i16(const short* wave, long long n_samples, float* feats, long 
   return launch_fbank_t<short>(wave, n_samples, feats, n_frames, stream);
 }
 int launch_fbank_batch(const void* wave, int is_i16, int batch, long long wave_stride, long long n_samples,
-                       float* feats, long long n_frames, cudaStream_t stream) {
+                       float* feats, long long n_frames, cudaStream_t stream, int window_type) {
   RVB_REQUIRE(batch >= 1 && batch <= 65535 && wave_stride >= n_samples, "fbank_batch: bad batch/stride");
   if (is_i16)
     return launch_fbank_t<short>(reinterpret_cast<const short*>(wave), n_samples, feats, n_frames, stream, batch,
-                                 wave_stride);
+                                 wave_stride, window_type);
   return launch_fbank_t<float>(reinterpret_cast<const float*>(wave), n_samples, feats, n_frames, stream, batch,
-                               wave_stride);
+                               wave_stride, window_type);
 }
 
 }  // namespace rvb

@@ -90,8 +90,14 @@ int launch_fbank(const float* wave, long long n_samples, float* feats, long long
 // int16 PCM input variant (the host API's H2D format)
 int launch_fbank_i16(const short* wave, long long n_samples, float* feats, long long n_frames, cudaStream_t stream);
 // `batch` equal-length recordings `wave_stride` samples apart -> feats (batch, n_frames, 80)
+// window_type: 0 = povey (ASR front-end), 1 = hamming (WeSpeaker embedding front-end)
 int launch_fbank_batch(const void* wave, int is_i16, int batch, long long wave_stride, long long n_samples,
-                       float* feats, long long n_frames, cudaStream_t stream);
+                       float* feats, long long n_frames, cudaStream_t stream, int window_type = 0);
+
+// ------------------------------------------------------------------ diarization (diar_seg.cu / diar_emb.cu)
+// C[m, n] = act(sum_k A[m, k] W[n, k] + bias[n]) in fp32 on the CUDA cores; act 1 = LeakyReLU(0.01)
+int launch_sgemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M, int N,
+                 int K, int act, cudaStream_t stream);
 
 // ------------------------------------------------------------------ norms / conv pieces (elementwise.cu)
 // y = LN(x) * gamma + beta ; rows with position >= row_lens[batch] are written as 0 when mask_rows != 0.
