@@ -29,6 +29,12 @@ class SegConfig(C.Structure):
         "lstm_layers", "linear_dim", "linear_layers", "num_classes")]
 
 
+class EmbConfig(C.Structure):
+    """Mirror of `rvb_emb_config` (include/rvb_diar.h)."""
+    _fields_ = [("sample_rate", C.c_int), ("num_mel_bins", C.c_int), ("m_channels", C.c_int), ("embed_dim", C.c_int),
+                ("blocks", C.c_int * 4)]
+
+
 _vp, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 
 # name -> (restype, argtypes); must list every symbol the header declares (tests/test_abi.py checks)
@@ -89,6 +95,12 @@ SIGNATURES = {
     "rvb_seg_destroy": (None, [_vp]),
     "rvb_seg_num_frames": (_i, [_vp, _i]),
     "rvb_seg_forward": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "rvb_emb_create": (_vp, [C.POINTER(EmbConfig)]),
+    "rvb_emb_set_tensor": (_i, [_vp, C.c_char_p, _vp, _ll]),
+    "rvb_emb_finalize": (_i, [_vp]),
+    "rvb_emb_destroy": (None, [_vp]),
+    "rvb_emb_num_frames": (_i, [_vp, _i]),
+    "rvb_emb_forward": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp, _vp, _vp]),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -93,3 +93,50 @@ def synthetic_speech(seconds: float, seed: int = 0, sample_rate: int = 16000, tu
         pos = end + int(rng.uniform(0.1, 0.5) * sample_rate)
         seg += 1
     return np.clip(out, -1, 1)
+
+
+EMB_SHAPE = dict(sample_rate=16000, num_mel_bins=80, m_channels=32, embed_dim=256, blocks=(3, 4, 6, 3))
+
+
+def embedding_state_dict(seed: int = 0, shape: Dict = EMB_SHAPE) -> Dict[str, np.ndarray]:
+    """WeSpeaker ResNet34 weights: Kaiming-normal convolutions, BatchNorm statistics / affine terms away from the
+    identity so that the folding is exercised."""
+    rng = np.random.default_rng(seed)
+    sd: Dict[str, np.ndarray] = {}
+
+    def conv(name, cout, cin, k):
+        std = math.sqrt(2.0 / (cin * k * k))
+        sd[name] = rng.normal(0, std, (cout, cin, k, k)).astype(np.float32)
+
+    def bn(name, c):
+        sd[name + ".weight"] = rng.uniform(0.6, 1.2, c).astype(np.float32)
+        sd[name + ".bias"] = rng.uniform(-0.1, 0.1, c).astype(np.float32)
+        sd[name + ".running_mean"] = rng.uniform(-0.1, 0.1, c).astype(np.float32)
+        sd[name + ".running_var"] = rng.uniform(0.6, 1.4, c).astype(np.float32)
+
+    c0 = shape["m_channels"]
+    conv("resnet.conv1.weight", c0, 1, 3)
+    bn("resnet.bn1", c0)
+    cin = c0
+    for li, nb in enumerate(shape["blocks"]):
+        cout = c0 << li
+        for bi in range(nb):
+            p = f"resnet.layer{li + 1}.{bi}"
+            stride = 2 if (li > 0 and bi == 0) else 1
+            conv(p + ".conv1.weight", cout, cin, 3)
+            bn(p + ".bn1", cout)
+            conv(p + ".conv2.weight", cout, cout, 3)
+            bn(p + ".bn2", cout)
+            sd[p + ".bn2.weight"] *= 0.5          # keeps the residual stream from growing over 16 blocks
+            if stride != 1 or cin != cout:
+                conv(p + ".shortcut.0.weight", cout, cin, 1)
+                bn(p + ".shortcut.1", cout)
+            cin = cout
+    fq = shape["num_mel_bins"]
+    for _ in range(3):
+        fq = (fq - 1) // 2 + 1
+    d = 2 * cin * fq
+    bound = 1.0 / math.sqrt(d)
+    sd["resnet.seg_1.weight"] = _uniform(rng, (shape["embed_dim"], d), bound)
+    sd["resnet.seg_1.bias"] = _uniform(rng, (shape["embed_dim"],), bound)
+    return sd

@@ -66,3 +66,67 @@ def test_segmentation_rejects_bad_input(seg):
     _, model = seg
     with pytest.raises(ValueError):
         model.forward(torch.zeros(1, 100, device="cuda"))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# speaker embedding (WeSpeaker ResNet34): bf16 tensor-core convolutions vs the fp32 torch restatement.
+# Tolerance: 33 bf16 GEMM layers -> relative L2 error of the embedding < 2e-2 and cosine similarity > 0.9995
+# (measured values are printed); the fbank + mean normalisation front-end is fp32: 3e-3 abs on log-mel values O(10).
+
+
+@pytest.fixture(scope="module")
+def emb():
+    from reverb_b200.diarization import synth
+    from reverb_b200.diarization.embedding import EmbeddingModel
+    sd = synth.embedding_state_dict(0)
+    return sd, EmbeddingModel(sd)
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / (np.linalg.norm(b) + 1e-12))
+
+
+def test_embedding_forward_vs_torch_oracle(emb):
+    from oracle import diar_ref
+    sd, model = emb
+    wav = _windows(3, seconds=10.0)
+    w = torch.from_numpy(wav)
+    ref_net = diar_ref.ResNet34Ref(sd)
+    ref_fb = torch.stack([diar_ref.wespeaker_fbank(x) for x in w])
+    got, fb = model.forward(w.cuda(), return_fbank=True)
+    assert fb.shape == ref_fb.shape == (3, 998, 80)
+    print("fbank max abs diff", float((fb.cpu() - ref_fb).abs().max()))
+    assert float((fb.cpu() - ref_fb).abs().max()) < 3e-3
+    ref = ref_net(ref_fb).numpy()
+    got = got.cpu().numpy()[:, 0]
+    for i in range(3):
+        cos = float(np.dot(got[i], ref[i]) / (np.linalg.norm(got[i]) * np.linalg.norm(ref[i])))
+        print(f"window {i}: rel L2 {_rel(got[i], ref[i]):.2e}, cosine {cos:.6f}")
+        assert _rel(got[i], ref[i]) < 2e-2 and cos > 0.9995
+
+
+def test_embedding_weighted_pooling_matches_oracle(emb):
+    """three activity masks per window at the segmentation frame rate (589), nearest-interpolated inside the pooling"""
+    from oracle import diar_ref
+    sd, model = emb
+    wav = _windows(2, seconds=10.0)
+    w = torch.from_numpy(wav)
+    rng = np.random.default_rng(0)
+    masks = np.zeros((2, 3, 589), np.float32)
+    for b in range(2):
+        for s in range(3):
+            a, e = sorted(rng.integers(0, 589, 2))
+            masks[b, s, a:max(e, a + 40)] = 1.0
+    masks[1, 2] = 0.0                                              # an inactive local speaker
+    ref_net = diar_ref.ResNet34Ref(sd)
+    ref_fb = torch.stack([diar_ref.wespeaker_fbank(x) for x in w])
+    got = model.forward(w.cuda(), torch.from_numpy(masks).cuda()).cpu().numpy()
+    assert got.shape == (2, 3, 256) and np.isfinite(got).all()
+    for b in range(2):
+        for s in range(3):
+            ref = ref_net(ref_fb[b:b + 1], torch.from_numpy(masks[b:b + 1, s])).numpy()[0]
+            assert _rel(got[b, s], ref) < 2e-2, (b, s, _rel(got[b, s], ref))
+    # unit weights == no weights
+    ones = model.forward(w.cuda(), torch.ones(2, 1, 589, device="cuda")).cpu().numpy()
+    none = model.forward(w.cuda()).cpu().numpy()
+    assert _rel(ones, none) < 1e-5
