@@ -92,6 +92,7 @@ struct AttnTcParams {
   int left;    // number of left chunks, < 0 = all
   const uint32_t* key_bits;  // optional per-(query row, key) visibility bits (AttnTcArgs::key_bits)
   int bits_ld;
+  int pipe;    // 1: pull S(j+1) inside tile j's exponential loop (RVB_ATTN_PIPE=0 disables)
   float scale_log2;
 };
 
@@ -268,6 +269,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     // ---------------------------------------------------------------- softmax warps: thread = query row (x column half)
     const int wq = warp & 3, hh = warp >> 2;   // TMEM lane quarter; column half (always 0 when SW == 4)
     const int r = wq * 32 + lane;
+    const bool pipe = (p.pipe != 0) && (CW == 64);
     const uint32_t lane_addr = ((uint32_t)(wq * 32) << 16);
     const int c0 = hh * CW, ob = hh * OW;
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory"); };
@@ -282,9 +284,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
       for (int c = 0; c < CW; c += 32) tmem_ld_32x32(s_col(sb) + lane_addr + c0 + c, dst + c);
     };
+    // PIPE (CW == 64 only): S(j+1) is pulled in two halves INSIDE tile j's exponential loop, each half into the registers
+    // the loop has just finished with — the tcgen05.ld latency hides behind the other half's exponentials without a
+    // second register copy of the tile (the full-copy prefetch variant spilled).
+    auto pull_half = [&](int j, int half, uint32_t(&dst)[CW]) {
+      const int sb = j % AT_NS;
+      if (half == 0) {
+        mbar_wait(&s_full[sb], (j / AT_NS) & 1);
+        tc_fence_after();
+      }
+      tmem_ld_32x32(s_col(sb) + lane_addr + c0 + 32 * half, dst + 32 * half);
+    };
     auto tile = [&](int j, uint32_t(&sv)[CW]) {
       const int sb = j % AT_NS, pb = j & 1;
-      pull(j, sv);
+      if (!pipe || j == 0) pull(j, sv);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -422,6 +435,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint8_t* blk = sP + pb * AT_P_BYTES + (kc >> 6) * AT_Q_BYTES + r * 128;
         const int ch = ((kc & 63) >> 3) ^ (r & 7);
         *reinterpret_cast<uint4*>(blk + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        if constexpr (CW == 64) {
+          if (pipe && j + 1 < ntiles) {
+            if (e == 24) pull_half(j + 1, 0, sv);   // columns [0, 32) of this tile are consumed
+            if (e == 56) pull_half(j + 1, 1, sv);
+          }
+        }
       }
       const float sm[4] = {sm01.x, sm01.y, sm23.x, sm23.y};
       row_sum += (sm[0] + sm[1]) + (sm[2] + sm[3]);
@@ -648,6 +667,14 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
   p.left = a.causal ? -1 : a.left_chunks;
   p.key_bits = a.key_bits;
   p.bits_ld = a.bits_ld;
+  {
+    static int pipe_sel = -1;
+    if (pipe_sel < 0) {
+      const char* e = getenv("RVB_ATTN_PIPE");
+      pipe_sel = (e && atoi(e) == 0) ? 0 : 1;
+    }
+    p.pipe = pipe_sel;
+  }
   RVB_REQUIRE(a.key_bits == nullptr || a.bits_ld >= 2 * ((a.Tk + 63) / 64), "attention_tc: key_bits rows are too short");
   p.scale_log2 = a.scale * 1.4426950408889634f;
   CUtensorMap tmQ, tmK, tmV;
