@@ -135,6 +135,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
   static_assert(1 + 2 * AT_KST + 4 + 2 * AT_NS + 4 + 1 + 1 <= 32, "barrier block is 256 bytes");
   constexpr bool SPLIT = (SW == 8);
+  // timing ablations (RVB_ATTN_POLY = 8 | 9 | 10 | 11, WRONG RESULTS by construction; tools/attn_bench.py): which part of
+  // the softmax warps' tile loop costs what
+  constexpr bool ABL_NOEXP = (POLY == 8 || POLY == 11);   // no MUFU.EX2: P~ = x - m
+  constexpr bool ABL_NOSTS = (POLY == 9 || POLY == 11);   // P~ is not written to shared memory
+  constexpr bool ABL_NOMAX = (POLY == 10 || POLY == 11);  // no scale / key bias / tile maximum
   constexpr int CW = BN * 4 / SW;   // S columns per thread and tile
   constexpr int OW = AT_DK * 4 / SW;  // O columns per thread (rescale, epilogue)
   static_assert(SW == 4 || (SW == 8 && BN == 64), "8 softmax warps are built for 64-key tiles");
@@ -307,7 +312,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
       const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
 #pragma unroll
-      for (int e = 0; e < CW; e += 4) {
+      for (int e = 0; e < (ABL_NOMAX ? 0 : CW); e += 4) {
         const float4 b4 = lds128(bias_addr + e * 4);
         // packed FFMA2: two scores per instruction
         const float2 x01 = ffma2(make_float2(__uint_as_float(sv[e + 0]), __uint_as_float(sv[e + 1])), sc2,
@@ -321,7 +326,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mx[(e >> 2) & 3] = fmax3(mx[(e >> 2) & 3], x01.x, x01.y);
         mx[((e >> 2) + 2) & 3] = fmax3(mx[((e >> 2) + 2) & 3], x23.x, x23.y);
       }
-      float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      float tmax = ABL_NOMAX ? 0.f : fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       if (p.chunk > 0) {
         // boundary tiles of the chunk mask (warp-uniform test over the warp's 32 rows; visibility bounds are
         // non-decreasing in the row index): hide the keys outside [lo, hi) of this row and redo the tile maximum
@@ -391,7 +396,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const float m_eff = (m_run == -INFINITY) ? 0.f : m_run;  // no visible key yet: every x is -inf -> p = 0
       const float2 one2 = make_float2(1.f, 1.f), negm2 = make_float2(-m_eff, -m_eff);
       // the polynomial exp2 path needs finite arguments: tiles fully inside [0, klen) without a chunk-mask boundary
-      const bool poly_ok = (p.chunk == 0) && (p.key_bits == nullptr) && ((jt0 + j + 1) * AT_BN <= klen) && (m_run != -INFINITY) &&
+      const bool poly_ok = (POLY < 8) && (p.chunk == 0) && (p.key_bits == nullptr) && ((jt0 + j + 1) * AT_BN <= klen) && (m_run != -INFINITY) &&
                            __all_sync(0xffffffffu, m_run != -INFINITY);
       // P~ goes to shared memory chunk by chunk (8 keys = 16 bytes) as it is produced, so only one chunk of packed
       // probabilities is ever live in registers.  The buffer was last read by PV(j-2), which has had a whole tile of
@@ -406,11 +411,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int f = e + 4 * q;
           const float2 d01 = ffma2(make_float2(__uint_as_float(sv[f + 0]), __uint_as_float(sv[f + 1])), one2, negm2);
           const float2 d23 = ffma2(make_float2(__uint_as_float(sv[f + 2]), __uint_as_float(sv[f + 3])), one2, negm2);
-          float2 p01 = make_float2(fast_exp2(d01.x), fast_exp2(d01.y));
+          float2 p01 = ABL_NOEXP ? d01 : make_float2(fast_exp2(d01.x), fast_exp2(d01.y));
           // POLY > 0: in every POLY-th group of four (POLY = 1: half, 2: a quarter of all exponentials) the second pair on the FMA pipe instead of MUFU (only when every key
           // of the tile is visible: masked keys carry -inf, which the polynomial path does not produce exact zeros for)
           float2 p23;
-          if (POLY > 0 && poly_ok && ((f >> 2) % (POLY > 0 ? POLY : 1)) == 0) p23 = exp2_poly2(d23);
+          if (ABL_NOEXP) p23 = d23;
+          else if (POLY > 0 && POLY < 8 && poly_ok && ((f >> 2) % (POLY > 0 ? POLY : 1)) == 0) p23 = exp2_poly2(d23);
           else p23 = make_float2(fast_exp2(d23.x), fast_exp2(d23.y));
           if (AT_TRUNC_P) {
             // P~ = the exponentials TRUNCATED to bf16 (upper 16 bits: one ALU byte-permute per pair) instead of rounded
@@ -434,7 +440,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int kc = c0 + e;
         uint8_t* blk = sP + pb * AT_P_BYTES + (kc >> 6) * AT_Q_BYTES + r * 128;
         const int ch = ((kc & 63) >> 3) ^ (r & 7);
-        *reinterpret_cast<uint4*>(blk + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (!ABL_NOSTS) *reinterpret_cast<uint4*>(blk + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        else if (w[0] == 0x12345678u && w[1] == w[2] + w[3]) *reinterpret_cast<uint4*>(blk) = make_uint4(w[0], w[1], w[2], w[3]);
         if constexpr (CW == 64) {
           if (pipe && j + 1 < ntiles) {
             if (e == 24) pull_half(j + 1, 0, sv);   // columns [0, 32) of this tile are consumed
@@ -700,9 +707,22 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
     if (poly_sel < 0) {
       const char* e = getenv("RVB_ATTN_POLY");
       poly_sel = e ? atoi(e) : 0;
-      if (poly_sel < 0 || poly_sel > 2) poly_sel = 0;
+      if (poly_sel < 0 || (poly_sel > 2 && poly_sel < 8) || poly_sel > 11) poly_sel = 0;
     }
     static DynSmemOptIn optin[3];
+    static DynSmemOptIn optin_abl[4];
+    if (poly_sel >= 8) {   // timing ablations, wrong results (see the kernel)
+#define RVB_ABL(V)                                                                     \
+  do {                                                                                 \
+    if (optin_abl[V - 8].ensure(attention_tc_kernel<64, 4, V>, smem)) return -1;       \
+    attention_tc_kernel<64, 4, V><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);      \
+  } while (0)
+      if (poly_sel == 8) RVB_ABL(8);
+      else if (poly_sel == 9) RVB_ABL(9);
+      else if (poly_sel == 10) RVB_ABL(10);
+      else RVB_ABL(11);
+#undef RVB_ABL
+    } else
     if (poly_sel == 1) {
       if (optin[1].ensure(attention_tc_kernel<64, 4, 1>, smem)) return -1;
       attention_tc_kernel<64, 4, 1><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);

@@ -140,31 +140,38 @@ def binarize(activity: np.ndarray, frames: SlidingWindow, onset: float = 0.5, of
     n, K = activity.shape
     if n == 0:
         return out
-    ts = [frames.middle(i) for i in range(n)]
+    ts = frames.start + np.arange(n) * frames.step + 0.5 * frames.duration
     for k in range(K):
         col = activity[:, k]
-        regions: List[List[float]] = []
-        start = ts[0]
-        active = col[0] > onset
-        t = ts[0]
-        for t, y in zip(ts[1:], col[1:]):
-            if active:
-                if y < offset:
-                    regions.append([start, t])
-                    start = t
-                    active = False
-            elif y > onset:
-                start = t
-                active = True
-        if active:
-            regions.append([start, t])
+        if onset == offset and not np.any(col == onset):
+            state = col > onset                                   # no hysteresis band: the state is the comparison
+        else:
+            state = np.zeros(n, bool)
+            active = bool(col[0] > onset)
+            state[0] = active
+            for i in range(1, n):
+                if active:
+                    if col[i] < offset:
+                        active = False
+                elif col[i] > onset:
+                    active = True
+                state[i] = active
+        # a region opens at the first active frame's middle and closes at the middle of the first inactive frame after
+        # it (the last frame's middle when still active at the end)
+        edge = np.diff(state.astype(np.int8))
+        starts = list(ts[np.nonzero(edge == 1)[0] + 1])
+        ends = list(ts[np.nonzero(edge == -1)[0] + 1])
+        if state[0]:
+            starts.insert(0, ts[0])
+        if state[-1]:
+            ends.append(ts[-1])
         merged: List[List[float]] = []
-        for r in regions:
-            if merged and min_duration_off > 0.0 and r[0] - merged[-1][1] <= min_duration_off:
-                merged[-1][1] = r[1]
+        for a0, b0 in zip(starts, ends):
+            if merged and min_duration_off > 0.0 and a0 - merged[-1][1] <= min_duration_off:
+                merged[-1][1] = float(b0)
             else:
-                merged.append(r)
-        out.extend((a, b, k) for a, b in merged if b > a)
+                merged.append([float(a0), float(b0)])
+        out.extend((a0, b0, k) for a0, b0 in merged if b0 > a0)
     return out
 
 
@@ -175,7 +182,8 @@ class SpeakerDiarization:
     def __init__(self, segmentation: Callable, embedding: Callable, *, sample_rate: int = 16000, duration: float = 10.0,
                  step_ratio: float = 0.1, clustering_threshold: float = 0.7045654963945799, min_cluster_size: int = 12,
                  min_duration_off: float = 0.0, embedding_exclude_overlap: bool = True, max_speakers_per_chunk: int = 3,
-                 max_speakers_per_frame: int = 2, batch_size: int = 32, embedding_min_samples: int = 400,
+                 max_speakers_per_frame: int = 2, batch_size: int = 32, segmentation_batch_size: Optional[int] = None,
+                 embedding_min_samples: int = 400,
                  device: str = "cuda"):
         # `device` exists for the host-logic tests, which drive the glue with stub networks; the real networks are CUDA-only
         self.device = device
@@ -189,6 +197,8 @@ class SpeakerDiarization:
         self.min_duration_off = min_duration_off
         self.exclude_overlap = embedding_exclude_overlap
         self.batch_size = batch_size
+        # the LSTM recurrence runs 8 windows per 2-CTA cluster and direction: 296 windows fill the 148 SMs of a B200
+        self.seg_batch_size = segmentation_batch_size or max(batch_size, 296)
         self.embedding_min_samples = embedding_min_samples
         self.mapping = powerset_mapping(max_speakers_per_chunk, max_speakers_per_frame)
         self.frames = receptive_field(sample_rate)
@@ -207,8 +217,8 @@ class SpeakerDiarization:
     def get_segmentations(self, chunks: torch.Tensor) -> np.ndarray:
         mapping = torch.from_numpy(self.mapping).to(chunks.device)
         out = []
-        for i in range(0, chunks.shape[0], self.batch_size):
-            logp = self.segmentation(chunks[i:i + self.batch_size].contiguous())
+        for i in range(0, chunks.shape[0], self.seg_batch_size):
+            logp = self.segmentation(chunks[i:i + self.seg_batch_size].contiguous())
             out.append(mapping[logp.argmax(dim=-1)])
         return torch.cat(out).cpu().numpy()                       # (num_chunks, frames, local speakers) in {0, 1}
 
@@ -263,12 +273,11 @@ class SpeakerDiarization:
             activations = np.pad(activations, ((0, 0), (0, max_per_frame - activations.shape[1])))
         n = min(activations.shape[0], count.shape[0])
         activations, count = activations[:n], count[:n]
+        # per frame, the count[t] most active clusters speak (ties: lower index first, like a stable argsort)
         order = np.argsort(-activations, axis=-1, kind="stable")
-        binary = np.zeros_like(activations)
-        for t in range(n):
-            for i in range(int(count[t, 0])):
-                binary[t, order[t, i]] = 1.0
-        return binary
+        rank = np.empty_like(order)
+        np.put_along_axis(rank, order, np.broadcast_to(np.arange(order.shape[1]), order.shape), axis=1)
+        return (rank < count[:, :1].astype(np.int64)).astype(np.float32)
 
     # -- the call ------------------------------------------------------------------------------------------------------
     def apply(self, wave) -> List[Turn]:
@@ -276,14 +285,27 @@ class SpeakerDiarization:
         if not torch.is_tensor(wave):
             wave = torch.from_numpy(np.asarray(wave, np.float32))
         wave = wave.to(device=self.device, dtype=torch.float32).flatten()
+        import time
+        sync = torch.cuda.synchronize if wave.is_cuda else (lambda: None)
+        tm = {}
+        t0 = time.perf_counter()
         chunks = self.windows(wave)
         window = SlidingWindow(0.0, self.duration, self.step)
         binarized = self.get_segmentations(chunks)
+        sync()
+        tm["segmentation"] = time.perf_counter() - t0
         count = self.speaker_count(binarized, window)
         if int(count.max()) == 0:
+            self.last = dict(binarized=binarized, count=count, timing=tm)
             return []
+        t1 = time.perf_counter()
         embeddings = self.get_embeddings(chunks, binarized)
+        sync()
+        tm["embedding"] = time.perf_counter() - t1
+        t1 = time.perf_counter()
         hard, _ = self.cluster(embeddings, binarized)
+        tm["clustering"] = time.perf_counter() - t1
+        t1 = time.perf_counter()
         count = np.minimum(count, binarized.shape[2]).astype(np.int8)
         hard = hard.copy()
         hard[binarized.sum(axis=1) == 0] = -2
@@ -294,7 +316,9 @@ class SpeakerDiarization:
         names = {k: f"SPEAKER_{i:02d}" for i, k in enumerate(labels)}
         turns = [Turn(a, b, names[k]) for a, b, k in regions]
         turns.sort(key=lambda t: (t.start, t.end))
-        self.last = dict(binarized=binarized, count=count, embeddings=embeddings, hard=hard, discrete=discrete)
+        tm["reconstruction"] = time.perf_counter() - t1
+        tm["total"] = time.perf_counter() - t0
+        self.last = dict(binarized=binarized, count=count, embeddings=embeddings, hard=hard, discrete=discrete, timing=tm)
         return turns
 
     __call__ = apply

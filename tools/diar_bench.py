@@ -60,6 +60,7 @@ def main():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out.update({"recording_seconds": args.seconds, "pipeline_seconds": dt, "pipeline_rtfx": args.seconds / dt,
+                "pipeline_stages_seconds": {k: round(v, 4) for k, v in pipe.last["timing"].items()},
                 "windows": int(pipe.last["binarized"].shape[0]), "turns": len(turns),
                 "speakers": len({t.label for t in turns}), "data": "synthetic audio, synthetic weights"})
     print(json.dumps(out))
