@@ -28,7 +28,8 @@ namespace rvb {
 
 constexpr int AT_BM = 128;  // query rows per CTA
 constexpr int AT_DK = 64;
-constexpr int AT_KST = 5;   // K'' stages (loaded two tiles ahead of their QK issue)
+constexpr int AT_KST = 4;   // K'' stages
+constexpr int AT_VST = 3;   // V stages
 constexpr int AT_NS = 3;    // S accumulator buffers in TMEM: QK runs three tiles ahead of the softmax warps
 constexpr uint32_t AT_Q_BYTES = 128 * AT_DK * 2;  // 16 KB Q tile (= one 64-key K-block of P~)
 constexpr bool AT_TRUNC_P = true;                 // P~ truncated (ALU) instead of rounded (XU) to bf16, see the softmax loop
@@ -39,7 +40,7 @@ template <int BN>
 struct AtCfg {
   static constexpr uint32_t KV_BYTES = BN * AT_DK * 2;   // one K'' / V tile
   static constexpr uint32_t P_BYTES = 128 * BN * 2;      // P~: 128 rows x BN keys (BN / 64 K-blocks of 16 KB)
-  static constexpr uint32_t SMEM_FIXED = AT_Q_BYTES + AT_KST * KV_BYTES + 2 * KV_BYTES + 2 * P_BYTES + 1024 + 256;
+  static constexpr uint32_t SMEM_FIXED = AT_Q_BYTES + (AT_KST + AT_VST) * KV_BYTES + 2 * P_BYTES + 1024 + 256;
   static constexpr uint32_t TMEM_COLS = (BN == 128) ? 512 : 256;  // S0 [0,BN), S1 [BN,2BN), O [2BN,2BN+64), S2 [2BN+64,3BN+64)
   static constexpr int CTAS_PER_SM = (BN == 128) ? 1 : 2;
 };
@@ -106,8 +107,18 @@ struct AttnTcParams {
 //     tile maxima / row sums meet through shared memory and a 64-thread named barrier.  Measured slightly SLOWER than
 //     SW = 4 (0.403 vs 0.388 ms per encoder layer): the kernel is not short of warps; what bounds it is the
 //     ex2 + issue budget per tile and the per-tile hand-offs, which the split duplicates.
-template <int BN, int SW, int POLY>
-__global__ void __launch_bounds__(32 * (SW + 1), AtCfg<BN>::CTAS_PER_SM)
+// CW3: the control work is split over THREE warps — TMA loader, QK issuer, PV issuer (+ one idle warp so that the control
+// side is a whole warpgroup for setmaxnreg) — instead of one thread doing all three in turn.  Measured with the timing
+// ablations below: with the entire softmax arithmetic removed the kernel still took 0.43 ms per encoder layer, i.e. the
+// single control thread's chain of ~24 long-latency special instructions per tile (6 mbarrier waits, 8 tcgen05.mma,
+// 4 commits, 2 TMA issues, ...) was the critical path, not MUFU / issue slots / TMEM loads.
+// PT: P~ lives in TENSOR MEMORY instead of shared memory.  ncu showed the tensor sub-pipe occupied 75 % of the time at 15 %
+// of its FLOP rate: the N = 64 products are operand-fetch (shared-memory bandwidth) bound — per 64-key tile the MMAs read
+// Q 16 KB + K'' 8 KB + P~ 16 KB + V 8 KB next to 16 KB of P~ stores and 16 KB of TMA writes.  With PT the softmax thread
+// writes its packed P~ row over its own S row (tcgen05.st, 32 columns) and the PV product takes A from TMEM: 32 KB less
+// shared-memory traffic per tile, no proxy fence, and the S buffer returns to the QK issuer when PV(j) retires.
+template <int BN, int SW, int POLY, bool CW3 = false, bool PT = false>
+__global__ void __launch_bounds__(32 * (SW + (CW3 ? 4 : 1)), AtCfg<BN>::CTAS_PER_SM)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -119,27 +130,34 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   constexpr uint32_t AT_TMEM_COLS = Cfg::TMEM_COLS;
   uint8_t* sQ = smem;
   uint8_t* sK = sQ + AT_Q_BYTES;               // AT_KST stages
-  uint8_t* sV = sK + AT_KST * AT_TILE_BYTES;   // 2 stages
-  uint8_t* sP = sV + 2 * AT_TILE_BYTES;        // 2 buffers x (BN / 64 K-blocks of 64 keys)
+  uint8_t* sV = sK + AT_KST * AT_TILE_BYTES;   // AT_VST stages
+  uint8_t* sP = sV + AT_VST * AT_TILE_BYTES;        // 2 buffers x (BN / 64 K-blocks of 64 keys)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * AT_P_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* k_full = bars + 1;                      // [AT_KST]
   uint64_t* k_empty = k_full + AT_KST;              // [AT_KST]
-  uint64_t* v_full = k_empty + AT_KST;              // [2]
-  uint64_t* v_empty = v_full + 2;                   // [2]
-  uint64_t* s_full = v_empty + 2;                   // [AT_NS]
+  uint64_t* v_full = k_empty + AT_KST;              // [AT_VST]
+  uint64_t* v_empty = v_full + AT_VST;              // [AT_VST]
+  uint64_t* s_full = v_empty + AT_VST;              // [AT_NS]
   uint64_t* s_empty = s_full + AT_NS;               // [AT_NS]
   uint64_t* p_full = s_empty + AT_NS;               // [2]
   uint64_t* p_empty = p_full + 2;                   // [2]
   uint64_t* o_done = p_empty + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
-  static_assert(1 + 2 * AT_KST + 4 + 2 * AT_NS + 4 + 1 + 1 <= 32, "barrier block is 256 bytes");
+  static_assert(1 + 2 * AT_KST + 2 * AT_VST + 2 * AT_NS + 4 + 1 + 1 <= 32, "barrier block is 256 bytes");
   constexpr bool SPLIT = (SW == 8);
+  static_assert(!PT || (BN == 64 && SW == 4 && !CW3), "P~ in tensor memory is built for the default configuration");
   // timing ablations (RVB_ATTN_POLY = 8 | 9 | 10 | 11, WRONG RESULTS by construction; tools/attn_bench.py): which part of
   // the softmax warps' tile loop costs what
   constexpr bool ABL_NOEXP = (POLY == 8 || POLY == 11);   // no MUFU.EX2: P~ = x - m
   constexpr bool ABL_NOSTS = (POLY == 9 || POLY == 11);   // P~ is not written to shared memory
   constexpr bool ABL_NOMAX = (POLY == 10 || POLY == 11);  // no scale / key bias / tile maximum
+  constexpr bool ABL_NOPV = (POLY == 12);                 // the control thread skips the PV products (barriers kept)
+  constexpr bool ABL_NOQK = (POLY == 13);                 // the control thread skips the QK products (barriers kept)
+  constexpr bool ABL_NOFENCE = (POLY == 14);              // no fence.proxy.async after the P~ stores
+  constexpr bool ABL_NOLD = (POLY == 15);                 // no tcgen05.ld of S (softmax on stale registers)
+  constexpr bool ABL_NOTMAWAIT = (POLY == 16);            // the MMAs do not wait for the K'' / V tiles to land
+  constexpr bool ABL_NOMMA = (POLY == 17);                // neither product is issued
   constexpr int CW = BN * 4 / SW;   // S columns per thread and tile
   constexpr int OW = AT_DK * 4 / SW;  // O columns per thread (rescale, epilogue)
   static_assert(SW == 4 || (SW == 8 && BN == 64), "8 softmax warps are built for 64-key tiles");
@@ -158,32 +176,58 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int jt0 = vis_lo(q0) / AT_BN;
   const int ntiles = max(0, (vis_hi(q0 + AT_BM - 1) + AT_BN - 1) / AT_BN - jt0);
 
-  if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
-    for (int i = 0; i < AT_KST; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-    }
-    for (int i = 0; i < AT_NS; ++i) {
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], SW);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-      mbar_init(&p_full[i], SW);
-      mbar_init(&p_empty[i], 1);
-    }
-    mbar_init(o_done, 1);
-    fence_barrier_init();
-    tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
-  }
+  const long long qrow = (long long)g * p.Tq + q0;
+  const long long krow0 = (long long)g * p.Tk;
+  // TMA loads of K'' / V tile n into their rings (control thread only; the wait on the ring slot passes at first use)
+  auto load_k = [&](int n) {
+    const int st = n % AT_KST, use = n / AT_KST;
+    mbar_wait(&k_empty[st], (use & 1) ^ 1);
+    mbar_expect_tx(&k_full[st], AT_TILE_BYTES);
+    tma_load_2d(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], h * AT_DK, (int)(krow0 + (jt0 + n) * AT_BN));
+  };
+  auto load_v = [&](int j) {
+    const int st = j % AT_VST;
+    mbar_wait(&v_empty[st], ((j / AT_VST) & 1) ^ 1);
+    mbar_expect_tx(&v_full[st], AT_TILE_BYTES);
+    tma_load_2d(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], h * AT_DK, (int)(krow0 + (jt0 + j) * AT_BN));
+  };
   if (warp == SW) {
+    if (lane == 0) {
+      mbar_init(q_full, 1);
+      for (int i = 0; i < AT_KST; ++i) {
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], 1);
+      }
+      for (int i = 0; i < AT_NS; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_empty[i], PT ? 1 : SW);   // PT: released by PV(j)'s commit, otherwise by the softmax warps' pull
+      }
+      for (int i = 0; i < AT_VST; ++i) {
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&p_full[i], SW);
+        mbar_init(&p_empty[i], (PT && i == 0) ? SW : 1);   // PT: p_full[0..2] = one "P~ written" barrier per S buffer
+      }
+      mbar_init(o_done, 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+      // The first loads go out BEFORE the CTA-wide barrier: their latency overlaps the key-bias fill and the TMEM
+      // allocation instead of following them (the per-CTA fixed cost was 22 % of the kernel, tools/attn_bench.py --sweep).
+      if (!CW3 && ntiles > 0) {
+        mbar_expect_tx(q_full, AT_Q_BYTES);
+        tma_load_2d(sQ, &tmQ, q_full, h * AT_DK, (int)qrow);
+        for (int n = 0; n < AT_KST && n < ntiles; ++n) load_k(n);
+        for (int n = 0; n < AT_VST - 1 && n < ntiles; ++n) load_v(n);
+      }
+    }
+    __syncwarp();
     tmem_alloc(tmem_ptr, AT_TMEM_COLS);
     tmem_relinquish();
-  } else {
+  } else if (warp < SW) {
     // key bias row of this (group, head), pre-scaled; masked keys -> -inf
     const float* kb = p.key_bias ? p.key_bias + ((long long)g * p.H + h) * p.Tk : nullptr;
     for (int kk = threadIdx.x; kk < ntiles * AT_BN; kk += 32 * SW) {
@@ -198,83 +242,103 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_o = tmem_base + 2 * AT_BN;
   auto s_col = [&](int sb) -> uint32_t { return tmem_base + (sb < 2 ? sb * AT_BN : 2 * AT_BN + 64); };
 
-  if (warp == SW) {
-    if (lane == 0 && ntiles > 0) {
-      // ------------------------------------------------------------ TMA + MMA control thread
+  if (warp >= SW) {
+    if constexpr (CW3 && BN == 64) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (lane == 0 && ntiles > 0 && (!CW3 || warp < SW + 3)) {
+      // ------------------------------------------------------------ TMA + MMA control thread(s)
       // instruction descriptors: D=f32, A=B=bf16.  QK: N=128, both K-major.  PV: N=64, B (V) MN-major (bit 16).
       constexpr uint32_t idesc_qk =
           (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AT_BN >> 3) << 17) | ((128u >> 4) << 24);
       constexpr uint32_t idesc_pv =
           (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      const long long qrow = (long long)g * p.Tq + q0;
-      const long long krow0 = (long long)g * p.Tk;
       const int total = ntiles;
-      auto load_k = [&](int n) {
-        const int st = n % AT_KST, use = n / AT_KST;
-        mbar_wait(&k_empty[st], (use & 1) ^ 1);
-        mbar_expect_tx(&k_full[st], AT_TILE_BYTES);
-        tma_load_2d(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], h * AT_DK, (int)(krow0 + (jt0 + n) * AT_BN));
-      };
-      auto load_v = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&v_full[st], AT_TILE_BYTES);
-        tma_load_2d(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], h * AT_DK, (int)(krow0 + (jt0 + j) * AT_BN));
-      };
       auto issue_qk = [&](int n) {
         const int st = n % AT_KST, sb = n % AT_NS;
-        mbar_wait(&k_full[st], (n / AT_KST) & 1);
+        if (!ABL_NOTMAWAIT) mbar_wait(&k_full[st], (n / AT_KST) & 1);
         mbar_wait(&s_empty[sb], ((n / AT_NS) & 1) ^ 1);
         tc_fence_after();
         const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sQ));
         const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sK + st * AT_TILE_BYTES));
 #pragma unroll
-        for (int k = 0; k < AT_DK / 16; ++k)
+        for (int k = 0; k < ((ABL_NOQK || ABL_NOMMA) ? 0 : AT_DK / 16); ++k)
           umma_f16(s_col(sb), adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[sb]);
         umma_commit(&k_empty[st]);
       };
-      mbar_expect_tx(q_full, AT_Q_BYTES);
-      tma_load_2d(sQ, &tmQ, q_full, h * AT_DK, (int)qrow);
-      for (int n = 0; n < AT_KST && n < total; ++n) load_k(n);
-      load_v(0);
-      if (ntiles > 1) load_v(1);
-      mbar_wait(q_full, 0);
-      for (int n = 0; n < AT_NS && n < total; ++n) issue_qk(n);
-      for (int i = 0; i < total; ++i) {
-        // Keep the QK products AT_NS tiles ahead: S buffer (i % AT_NS) is free as soon as the softmax warps have pulled
-        // S(i) out of TMEM (they signal that BEFORE doing the exponentials), so QK(i+AT_NS) is queued long before it
-        // is needed and the barrier round trips (pull -> issue -> commit -> visible) stay off the softmax warps'
-        // critical path.  K'' tiles are requested two tiles before their product.
-        if (i + AT_NS < total) issue_qk(i + AT_NS);
-        if (i + AT_KST < total) load_k(i + AT_KST);  // stage of K''(i): released by QK(i)'s commit, long done
-        {
-          const int j = i, pb = j & 1;  // O += P~(j) . V(j)
-          mbar_wait(&v_full[pb], (j >> 1) & 1);
-          mbar_wait(&p_full[pb], (j >> 1) & 1);
-          tc_fence_after();
-          const uint64_t pdesc = make_sw128_kmajor_desc(smem_u32(sP + pb * AT_P_BYTES));
-          const uint64_t vdesc = make_sw128_kmajor_desc(smem_u32(sV + pb * AT_TILE_BYTES));  // MN-major view
+      auto issue_pv = [&](int j) {
+        const int pb = PT ? j % AT_NS : (j & 1);  // O += P~(j) . V(j)
+        const int vs = j % AT_VST;
+        if (!ABL_NOTMAWAIT) mbar_wait(&v_full[vs], (j / AT_VST) & 1);
+        mbar_wait(&p_full[pb], PT ? (j / AT_NS) & 1 : (j >> 1) & 1);
+        tc_fence_after();
+        const uint64_t vdesc = make_sw128_kmajor_desc(smem_u32(sV + vs * AT_TILE_BYTES));  // MN-major view
+        if constexpr (PT) {
 #pragma unroll
-          for (int ks = 0; ks < AT_BN / 16; ++ks) {
+          for (int ks = 0; ks < ((ABL_NOPV || ABL_NOMMA) ? 0 : AT_BN / 16); ++ks) {
+            // A: 16 keys = 8 packed columns of the S buffer this tile's P~ overwrote; B: 16 key rows of 128 B
+            const uint64_t bd = vdesc + (uint64_t)(ks * ((16 * 128) >> 4));
+            umma_f16_ts(tmem_o, s_col(pb) + 8 * ks, bd, idesc_pv, (j | ks) != 0);
+          }
+          umma_commit(&s_empty[pb]);
+        } else {
+          const uint64_t pdesc = make_sw128_kmajor_desc(smem_u32(sP + pb * AT_P_BYTES));
+#pragma unroll
+          for (int ks = 0; ks < ((ABL_NOPV || ABL_NOMMA) ? 0 : AT_BN / 16); ++ks) {
             // A: 16 keys = 32 B inside the 64-key K-block (ks / 4); B: 16 key rows of 128 B
             const uint64_t a = pdesc + (uint64_t)((ks >> 2) * (AT_Q_BYTES >> 4) + (ks & 3) * 2);
             const uint64_t bd = vdesc + (uint64_t)(ks * ((16 * 128) >> 4));
             umma_f16(tmem_o, a, bd, idesc_pv, (j | ks) != 0);
           }
           umma_commit(&p_empty[pb]);
-          umma_commit(&v_empty[pb]);
-          if (j + 1 == ntiles) umma_commit(o_done);
-          // V(j+1) goes into the stage PV(j-1) read; that product was issued a whole iteration ago
-          if (j >= 1 && j + 1 < ntiles) load_v(j + 1);
         }
+        umma_commit(&v_empty[vs]);
+        if (j + 1 == ntiles) umma_commit(o_done);
+      };
+      if constexpr (!CW3) {
+        // Q, K''(0 .. AT_KST-1), V(0 .. AT_VST-2) were requested in the prologue
+        mbar_wait(q_full, 0);
+        for (int n = 0; n < AT_NS && n < total; ++n) issue_qk(n);
+        for (int i = 0; i < total; ++i) {
+          // Keep the QK products AT_NS tiles ahead: S buffer (i % AT_NS) is free as soon as the softmax warps have pulled
+          // S(i) out of TMEM (they signal that BEFORE doing the exponentials), so QK(i+AT_NS) is queued long before it
+          // is needed.  K'' tiles are requested two tiles before their product.
+          if constexpr (PT) {
+            // the S buffer of tile i comes back when PV(i) retires: QK(i + AT_NS - 1) waits for PV(i - 1), issued a whole
+            // iteration ago, so the products still run AT_NS - 1 tiles ahead of the softmax warps
+            issue_pv(i);
+            if (i >= 1 && i - 1 + AT_NS < total) issue_qk(i - 1 + AT_NS);
+            if (i + AT_KST < total) load_k(i + AT_KST);
+          } else {
+            if (i + AT_NS < total) issue_qk(i + AT_NS);
+            if (i + AT_KST < total) load_k(i + AT_KST);  // stage of K''(i): released by QK(i)'s commit, long done
+            issue_pv(i);
+          }
+          // V(i + AT_VST - 1) goes into the stage PV(i-1) read; that product was issued a whole iteration ago
+          if (i + AT_VST - 1 < ntiles) load_v(i + AT_VST - 1);
+        }
+      } else if (warp == SW) {
+        // ---- loader: runs ahead as far as the K'' (AT_KST) and V (AT_VST) rings allow
+        mbar_expect_tx(q_full, AT_Q_BYTES);
+        tma_load_2d(sQ, &tmQ, q_full, h * AT_DK, (int)qrow);
+        for (int n = 0; n < total; ++n) {
+          load_k(n);
+          load_v(n);
+        }
+      } else if (warp == SW + 1) {
+        // ---- QK issuer: S(n) as soon as K''(n) has landed and the softmax warps have pulled S(n - AT_NS)
+        mbar_wait(q_full, 0);
+        for (int n = 0; n < total; ++n) issue_qk(n);
+      } else {
+        // ---- PV issuer: O += P~(j) V(j) as soon as the softmax warps have published P~(j)
+        for (int j = 0; j < total; ++j) issue_pv(j);
       }
     }
   } else {
     // ---------------------------------------------------------------- softmax warps: thread = query row (x column half)
+    if constexpr (CW3 && BN == 64) asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
     const int wq = warp & 3, hh = warp >> 2;   // TMEM lane quarter; column half (always 0 when SW == 4)
     const int r = wq * 32 + lane;
-    const bool pipe = (p.pipe != 0) && (CW == 64);
+    const bool pipe = (p.pipe != 0) && (CW == 64) && !PT;
     const uint32_t lane_addr = ((uint32_t)(wq * 32) << 16);
     const int c0 = hh * CW, ob = hh * OW;
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + wq) : "memory"); };
@@ -287,7 +351,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&s_full[sb], (j / AT_NS) & 1);
       tc_fence_after();
 #pragma unroll
-      for (int c = 0; c < CW; c += 32) tmem_ld_32x32(s_col(sb) + lane_addr + c0 + c, dst + c);
+      for (int c = 0; c < (ABL_NOLD ? 0 : CW); c += 32) tmem_ld_32x32(s_col(sb) + lane_addr + c0 + c, dst + c);
     };
     // PIPE (CW == 64 only): S(j+1) is pulled in two halves INSIDE tile j's exponential loop, each half into the registers
     // the loop has just finished with — the tcgen05.ld latency hides behind the other half's exponentials without a
@@ -298,7 +362,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(&s_full[sb], (j / AT_NS) & 1);
         tc_fence_after();
       }
-      tmem_ld_32x32(s_col(sb) + lane_addr + c0 + 32 * half, dst + 32 * half);
+      if (!ABL_NOLD) tmem_ld_32x32(s_col(sb) + lane_addr + c0 + 32 * half, dst + 32 * half);
     };
     auto tile = [&](int j, uint32_t(&sv)[CW]) {
       const int sb = j % AT_NS, pb = j & 1;
@@ -306,7 +370,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);   // the S buffer goes back to the MMA issuer as early as possible
+      if (!PT && lane == 0) mbar_arrive(&s_empty[sb]);   // the S buffer goes back to the MMA issuer as early as possible
       const uint32_t bias_addr = smem_u32(s_bias + j * AT_BN + c0);
       // x = s * scale*log2e + key bias (masked keys: -inf), kept in place of the raw scores; tile maximum
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // 4 independent chains
@@ -371,7 +435,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (__any_sync(0xffffffffu, raise)) {
           // Lazy rescale (rare): O and the row sum move to the new maximum.  The last product issued, PV(j-1), must
           // have retired before O is touched; PV(j) is not issued before every softmax warp arrives on p_full(j).
-          mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
+          if constexpr (PT) mbar_wait(&s_empty[(j - 1) % AT_NS], ((j - 1) / AT_NS) & 1);
+          else mbar_wait(&p_empty[(j - 1) & 1], ((j - 1) >> 1) & 1);
           tc_fence_after();
           const float m_new = raise ? tmax : m_run;
           // 1 for the rows that keep their maximum; 0 for rows that see their first visible key only now (their O
@@ -401,7 +466,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // P~ goes to shared memory chunk by chunk (8 keys = 16 bytes) as it is produced, so only one chunk of packed
       // probabilities is ever live in registers.  The buffer was last read by PV(j-2), which has had a whole tile of
       // exponentials to retire: this wait is practically free.
-      mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
+      if (!PT) mbar_wait(&p_empty[pb], ((j >> 1) & 1) ^ 1);
 #pragma unroll
       for (int e = 0; e < CW; e += 8) {
         uint32_t w[4];
@@ -440,7 +505,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int kc = c0 + e;
         uint8_t* blk = sP + pb * AT_P_BYTES + (kc >> 6) * AT_Q_BYTES + r * 128;
         const int ch = ((kc & 63) >> 3) ^ (r & 7);
-        if (!ABL_NOSTS) *reinterpret_cast<uint4*>(blk + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+        if constexpr (PT) {   // packed P~ replaces the consumed scores in place: word i = keys (2i, 2i+1)
+          sv[(e >> 1) + 0] = w[0];
+          sv[(e >> 1) + 1] = w[1];
+          sv[(e >> 1) + 2] = w[2];
+          sv[(e >> 1) + 3] = w[3];
+        } else if (!ABL_NOSTS) *reinterpret_cast<uint4*>(blk + ch * 16) = make_uint4(w[0], w[1], w[2], w[3]);
         else if (w[0] == 0x12345678u && w[1] == w[2] + w[3]) *reinterpret_cast<uint4*>(blk) = make_uint4(w[0], w[1], w[2], w[3]);
         if constexpr (CW == 64) {
           if (pipe && j + 1 < ntiles) {
@@ -451,9 +521,17 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       const float sm[4] = {sm01.x, sm01.y, sm23.x, sm23.y};
       row_sum += (sm[0] + sm[1]) + (sm[2] + sm[3]);
-      fence_proxy_async();  // generic-proxy writes of P~ -> visible to the tensor-core (async) proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[pb]);
+      if constexpr (PT) {
+        if constexpr (CW == 64) tmem_st_32x32(s_col(sb) + lane_addr, sv);   // P~ row over the first 32 columns of its S row
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[sb]);
+      } else {
+        if (!ABL_NOFENCE) fence_proxy_async();  // generic-proxy writes of P~ -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[pb]);
+      }
     };
     {
       uint32_t sv[CW];
@@ -707,10 +785,10 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
     if (poly_sel < 0) {
       const char* e = getenv("RVB_ATTN_POLY");
       poly_sel = e ? atoi(e) : 0;
-      if (poly_sel < 0 || (poly_sel > 2 && poly_sel < 8) || poly_sel > 11) poly_sel = 0;
+      if (poly_sel < 0 || (poly_sel > 2 && poly_sel < 8) || poly_sel > 17) poly_sel = 0;
     }
     static DynSmemOptIn optin[3];
-    static DynSmemOptIn optin_abl[4];
+    static DynSmemOptIn optin_abl[10];
     if (poly_sel >= 8) {   // timing ablations, wrong results (see the kernel)
 #define RVB_ABL(V)                                                                     \
   do {                                                                                 \
@@ -720,7 +798,13 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
       if (poly_sel == 8) RVB_ABL(8);
       else if (poly_sel == 9) RVB_ABL(9);
       else if (poly_sel == 10) RVB_ABL(10);
-      else RVB_ABL(11);
+      else if (poly_sel == 11) RVB_ABL(11);
+      else if (poly_sel == 12) RVB_ABL(12);
+      else if (poly_sel == 13) RVB_ABL(13);
+      else if (poly_sel == 14) RVB_ABL(14);
+      else if (poly_sel == 15) RVB_ABL(15);
+      else if (poly_sel == 16) RVB_ABL(16);
+      else RVB_ABL(17);
 #undef RVB_ABL
     } else
     if (poly_sel == 1) {
@@ -730,8 +814,27 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
       if (optin[2].ensure(attention_tc_kernel<64, 4, 2>, smem)) return -1;
       attention_tc_kernel<64, 4, 2><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
     } else {
-      if (optin[0].ensure(attention_tc_kernel<64, 4, 0>, smem)) return -1;
-      attention_tc_kernel<64, 4, 0><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+      static int cw_sel = -1;   // RVB_ATTN_CW=3: three control warps (measured slower: 0.481 vs 0.435 ms); default: one thread
+      if (cw_sel < 0) {
+        const char* e = getenv("RVB_ATTN_CW");
+        cw_sel = (e && atoi(e) == 3) ? 3 : 1;
+      }
+      static int pt_sel = -1;   // RVB_ATTN_PT=0: P~ through shared memory (A/B); default: P~ in tensor memory
+      if (pt_sel < 0) {
+        const char* e = getenv("RVB_ATTN_PT");
+        pt_sel = (e && atoi(e) == 0) ? 0 : 1;
+      }
+      static DynSmemOptIn optin_cw3, optin_pt;
+      if (cw_sel != 3 && pt_sel == 1) {
+        if (optin_pt.ensure(attention_tc_kernel<64, 4, 0, false, true>, smem)) return -1;
+        attention_tc_kernel<64, 4, 0, false, true><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+      } else if (cw_sel == 3) {
+        if (optin_cw3.ensure(attention_tc_kernel<64, 4, 0, true>, smem)) return -1;
+        attention_tc_kernel<64, 4, 0, true><<<grid, 256, smem, stream>>>(tmQ, tmK, tmV, p);
+      } else {
+        if (optin[0].ensure(attention_tc_kernel<64, 4, 0>, smem)) return -1;
+        attention_tc_kernel<64, 4, 0><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+      }
     }
   } else {
     const size_t smem = AtCfg<64>::SMEM_FIXED + 3072 + (size_t)((a.Tk + 63) / 64) * 64 * sizeof(float);

@@ -579,6 +579,11 @@ static int encoder_forward(rvb_model* m, const float* d_feats, const int* h_feat
       m->ws_cbias.ensure(((size_t)B * H * Tp + (size_t)M * 2 * ((d / 2 + 127) / 128)) * 4))
     return -1;
   const bool tc_attn = attn_impl() == 1 && dk == 64 && !x3;
+  if (!tc_attn && !x3 && attn_impl() == 1) {   // say so once: a d_k != 64 model runs the (slower) mma.sync attention
+    static std::atomic<bool> warned{false};
+    if (!warned.exchange(true))
+      fprintf(stderr, "reverb_b200: d_k = %d — the tcgen05 attention kernel is built for d_k = 64; using the mma.sync kernel\n", dk);
+  }
   // rel-pos key transform inside the [q; k; v] projection's epilogue (default); RVB_RELPOS=prep keeps the separate kernel
   const char* rp_env = getenv("RVB_RELPOS");   // read per call: tests A/B the two paths in one process
   const bool relpos_fused = tc_attn && !(rp_env && strcmp(rp_env, "prep") == 0) && get_gemm_impl() != 1;

@@ -40,3 +40,13 @@ r["tc_attn_tflops"] = flop / ((r["tc_total_ms"] - r["prep_ms"]) * 1e-3) / 1e12
 r["mma_tflops_equiv"] = flop / (r["mma_ms"] * 1e-3) / 1e12
 r["max_abs_diff"] = float((out.float() - out2.float()).abs().max())
 print(json.dumps(r))
+if "--sweep" in sys.argv:
+    # per-CTA fixed cost vs per-key-tile cost: the same launch with the key lengths capped (ceil(klen / 64) tiles visited)
+    def only_attn():
+        lib.rvb_attention_tc(p(qkv), p(kpp), C.c_void_p(qkv.data_ptr() + 4 * d), p(out), 3 * d, d, 3 * d, d, B, T, T, H, dk, p(cb), p(klens), 0, scale, st)
+    rows = []
+    for L in (64, 128, 256, 384, 512, 640, 748):
+        klens.fill_(L)
+        rows.append({"klen": L, "tiles": (L + 63) // 64, "ms": timeit(only_attn, 20)})
+    klens.fill_(T)
+    print(json.dumps({"sweep": rows}))
