@@ -22,6 +22,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "kernels.h"
 
 namespace rvb {
@@ -481,9 +483,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // of the tile is visible: masked keys carry -inf, which the polynomial path does not produce exact zeros for)
           float2 p23;
           if (ABL_NOEXP) p23 = d23;
-          else if (POLY > 0 && POLY < 8 && poly_ok && ((f >> 2) % (POLY > 0 ? POLY : 1)) == 0) p23 = exp2_poly2(d23);
+          else if ((POLY == 1 || POLY == 2) && poly_ok && ((f >> 2) % (POLY > 0 ? POLY : 1)) == 0) p23 = exp2_poly2(d23);
           else p23 = make_float2(fast_exp2(d23.x), fast_exp2(d23.y));
-          if (AT_TRUNC_P) {
+          if (AT_TRUNC_P && POLY != 3) {   // POLY == 3: A/B variant with F2FP rounding and an unrounded row sum
             // P~ = the exponentials TRUNCATED to bf16 (upper 16 bits: one ALU byte-permute per pair) instead of rounded
             // by F2FP — the conversion shares the XU pipe with MUFU.EX2, the pipe that bounds this kernel (ncu: xu 54 %,
             // everything else < 20 %).  The row sum adds the same truncated values, so O / row_sum is normalised by
@@ -579,6 +581,437 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   if (warp == SW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
+// =====================================================================================================================
+// PERSISTENT variant (default for the plain / causal / bit-mask cases): one CTA per SM slot (2 x #SMs CTAs) loops over
+// (query tile, head, group) items.  tools/attn_bench.py --sweep showed 22 % of the one-item-per-CTA kernel's time was
+// per-CTA fixed cost (launch, barrier init, TMEM allocation, first TMA round trip, key-bias fill, pipeline fill, drain).
+// Here TMEM and the barriers are set up once and ALL rings (K'', V, S / P~) keep running across item boundaries: four
+// cursors — K'' load, V load, QK issue, PV issue — walk the same (item, tile) sequence at different leads, so the next
+// item's Q and first tiles are in flight while the softmax warps finish the current one; the key-bias row of the next
+// item is fetched into registers an item ahead.  P~ lives in tensor memory (see PT above).  Same arithmetic, same
+// results as attention_tc_kernel<64, 4, 0, false, true>.
+struct AtItem {
+  int g, h, q0, klen, jt0, ntiles;
+};
+
+__device__ __forceinline__ AtItem at_item(const AttnTcParams& p, int it, int nq) {
+  AtItem a;
+  const int qt = it % nq;
+  a.h = (it / nq) % p.H;
+  a.g = it / (nq * p.H);
+  a.q0 = qt * AT_BM;
+  a.klen = p.Tk;
+  if (p.k_lens) a.klen = min(a.klen, __ldg(p.k_lens + a.g));
+  const int lo = (p.chunk > 0 && p.left >= 0) ? max(0, (a.q0 / p.chunk - p.left) * p.chunk) : 0;
+  const int last = a.q0 + AT_BM - 1;
+  const int hi = p.chunk > 0 ? min(a.klen, (last / p.chunk + 1) * p.chunk) : a.klen;
+  a.jt0 = lo / 64;
+  a.ntiles = max(0, (hi + 63) / 64 - a.jt0);
+  return a;
+}
+
+// walks the tiles of the CTA's items in order; `n` counts tiles globally (ring slots and barrier phases follow it)
+struct AtCursor {
+  int k;        // index into this CTA's item list
+  int j;        // tile inside the item
+  int n;        // global tile count
+  int ne;       // number of non-empty items before the current one
+  AtItem it;
+  bool valid;
+};
+
+__device__ __forceinline__ void at_cursor_seek(const AttnTcParams& p, AtCursor& c, int n_items, int nq) {
+  // position on the first item at or after c.k that has tiles
+  for (;;) {
+    const long long id = (long long)blockIdx.x + (long long)c.k * gridDim.x;
+    if (id >= n_items) {
+      c.valid = false;
+      return;
+    }
+    c.it = at_item(p, (int)id, nq);
+    if (c.it.ntiles > 0) {
+      c.valid = true;
+      return;
+    }
+    ++c.k;
+  }
+}
+__device__ __forceinline__ void at_cursor_init(const AttnTcParams& p, AtCursor& c, int n_items, int nq) {
+  c.k = 0;
+  c.j = 0;
+  c.n = 0;
+  c.ne = 0;
+  at_cursor_seek(p, c, n_items, nq);
+}
+__device__ __forceinline__ void at_cursor_next(const AttnTcParams& p, AtCursor& c, int n_items, int nq) {
+  ++c.n;
+  if (++c.j == c.it.ntiles) {
+    c.j = 0;
+    ++c.k;
+    ++c.ne;
+    at_cursor_seek(p, c, n_items, nq);
+  }
+}
+
+constexpr int ATP_KST = 5, ATP_VST = 4, ATP_NS = 3;
+constexpr bool ATP_TRUNC = false;   // true: P~ truncated on the ALU (see AT_TRUNC_P)
+constexpr uint32_t ATP_TILE = 64 * AT_DK * 2;   // 8 KB
+constexpr uint32_t ATP_SMEM_FIXED = 2 * AT_Q_BYTES + (ATP_KST + ATP_VST) * ATP_TILE + 1024 + 384;
+
+__global__ void __launch_bounds__(160, 2)
+attention_tcp_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p, int n_items, int nq, int bias_len) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                               // 2 buffers
+  uint8_t* sK = sQ + 2 * AT_Q_BYTES;
+  uint8_t* sV = sK + ATP_KST * ATP_TILE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATP_VST * ATP_TILE);
+  uint64_t* q_full = bars;                          // [2]
+  uint64_t* q_empty = q_full + 2;                   // [2]
+  uint64_t* k_full = q_empty + 2;                   // [KST]
+  uint64_t* k_empty = k_full + ATP_KST;
+  uint64_t* v_full = k_empty + ATP_KST;             // [VST]
+  uint64_t* v_empty = v_full + ATP_VST;
+  uint64_t* s_full = v_empty + ATP_VST;             // [NS]
+  uint64_t* s_empty = s_full + ATP_NS;              // [NS]  (PV(n) retired: S / P~ buffer free)
+  uint64_t* p_full = s_empty + ATP_NS;              // [NS]  (P~(n) written)
+  uint64_t* o_done = p_full + ATP_NS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
+  static_assert(4 + 2 * ATP_KST + 2 * ATP_VST + 3 * ATP_NS + 1 + 1 <= 48, "barrier block is 384 bytes");
+  float* s_bias = reinterpret_cast<float*>(bars + 48);   // [2][bias_len]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1);
+        mbar_init(&q_empty[i], 1);
+      }
+      for (int i = 0; i < ATP_KST; ++i) {
+        mbar_init(&k_full[i], 1);
+        mbar_init(&k_empty[i], 1);
+      }
+      for (int i = 0; i < ATP_VST; ++i) {
+        mbar_init(&v_full[i], 1);
+        mbar_init(&v_empty[i], 1);
+      }
+      for (int i = 0; i < ATP_NS; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&s_empty[i], 1);
+        mbar_init(&p_full[i], 4);
+      }
+      mbar_init(o_done, 1);
+      fence_barrier_init();
+      tma_prefetch_desc(&tmQ);
+      tma_prefetch_desc(&tmK);
+      tma_prefetch_desc(&tmV);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_o = tmem_base + 128;
+  auto s_col = [&](int sb) -> uint32_t { return tmem_base + (sb < 2 ? sb * 64 : 192); };
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- control thread: four cursors over one sequence
+      constexpr uint32_t idesc_qk = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((128u >> 4) << 24);
+      constexpr uint32_t idesc_pv =
+          (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+      AtCursor ck, cv, cq, cp;
+      at_cursor_init(p, ck, n_items, nq);
+      cv = ck;
+      cq = ck;
+      cp = ck;
+      // K''(n) (and, at an item's first tile, its Q) — false when the Q buffer is still being read by the item two
+      // back: the caller retries later.  Never blocks on the Q ring: with one-tile items the K'' cursor would otherwise
+      // wait for a QK product that this same thread has not issued yet.
+      auto try_load_k = [&]() -> bool {
+        if (ck.j == 0) {
+          const int qb = ck.ne & 1;
+          if (!mbar_try_wait(&q_empty[qb], ((ck.ne >> 1) & 1) ^ 1)) return false;
+          mbar_expect_tx(&q_full[qb], AT_Q_BYTES);
+          tma_load_2d(sQ + qb * AT_Q_BYTES, &tmQ, &q_full[qb], ck.it.h * AT_DK,
+                      (int)((long long)ck.it.g * p.Tq + ck.it.q0));
+        }
+        const int st = ck.n % ATP_KST;
+        mbar_wait(&k_empty[st], ((ck.n / ATP_KST) & 1) ^ 1);   // QK(n - KST) was issued (callers keep n - cq.n < KST)
+        mbar_expect_tx(&k_full[st], ATP_TILE);
+        tma_load_2d(sK + st * ATP_TILE, &tmK, &k_full[st], ck.it.h * AT_DK,
+                    (int)((long long)ck.it.g * p.Tk + (ck.it.jt0 + ck.j) * 64));
+        at_cursor_next(p, ck, n_items, nq);
+        return true;
+      };
+      auto load_v = [&]() {
+        const int st = cv.n % ATP_VST;
+        mbar_wait(&v_empty[st], ((cv.n / ATP_VST) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], ATP_TILE);
+        tma_load_2d(sV + st * ATP_TILE, &tmV, &v_full[st], cv.it.h * AT_DK,
+                    (int)((long long)cv.it.g * p.Tk + (cv.it.jt0 + cv.j) * 64));
+        at_cursor_next(p, cv, n_items, nq);
+      };
+      auto issue_qk = [&]() {
+        const int st = cq.n % ATP_KST, sb = cq.n % ATP_NS, qb = cq.ne & 1;
+        if (cq.j == 0) mbar_wait(&q_full[qb], (cq.ne >> 1) & 1);
+        mbar_wait(&k_full[st], (cq.n / ATP_KST) & 1);
+        mbar_wait(&s_empty[sb], ((cq.n / ATP_NS) & 1) ^ 1);
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_kmajor_desc(smem_u32(sQ + qb * AT_Q_BYTES));
+        const uint64_t bdesc = make_sw128_kmajor_desc(smem_u32(sK + st * ATP_TILE));
+#pragma unroll
+        for (int k = 0; k < AT_DK / 16; ++k) umma_f16(s_col(sb), adesc + 2 * k, bdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[sb]);
+        umma_commit(&k_empty[st]);
+        if (cq.j + 1 == cq.it.ntiles) umma_commit(&q_empty[qb]);   // the item's last read of its Q buffer
+        at_cursor_next(p, cq, n_items, nq);
+      };
+      auto issue_pv = [&]() {
+        const int sb = cp.n % ATP_NS, vs = cp.n % ATP_VST;
+        mbar_wait(&v_full[vs], (cp.n / ATP_VST) & 1);
+        mbar_wait(&p_full[sb], (cp.n / ATP_NS) & 1);
+        tc_fence_after();
+        const uint64_t vdesc = make_sw128_kmajor_desc(smem_u32(sV + vs * ATP_TILE));   // MN-major view
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16_ts(tmem_o, s_col(sb) + 8 * ks, vdesc + (uint64_t)(ks * ((16 * 128) >> 4)), idesc_pv, (cp.j | ks) != 0);
+        umma_commit(&s_empty[sb]);
+        umma_commit(&v_empty[vs]);
+        if (cp.j + 1 == cp.it.ntiles) umma_commit(o_done);
+        at_cursor_next(p, cp, n_items, nq);
+      };
+      // Every blocking wait below is on work this thread has ALREADY issued (or on the softmax warps, which only depend on
+      // issued work), so the single control thread can never wait for itself — also with one-tile items:
+      //   K''(n): needs QK(n - KST) issued  -> loaded while n - cq.n < KST - 1 (and the Q buffer is free, non-blocking);
+      //   V(n):   needs PV(n - VST) issued  -> loaded while n - cp.n < VST;
+      //   QK(n):  needs K''(n) requested and PV(n - NS) issued -> issued while n - cp.n < NS - 1 (one iteration of slack);
+      //   PV(n):  needs QK(n) issued and V(n) requested.
+      auto fill_k = [&]() {
+        while (ck.valid && ck.n - cq.n < ATP_KST - 1) {
+          if (!try_load_k()) break;
+        }
+      };
+      while (cp.valid) {
+        fill_k();
+        while (cv.valid && cv.n - cp.n < ATP_VST) load_v();
+        while (cq.valid && ck.n > cq.n && cq.n - cp.n < ATP_NS - 1) {
+          issue_qk();
+          fill_k();
+        }
+        if (cq.n > cp.n) issue_pv();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps: thread = query row
+    const int r = warp * 32 + lane;
+    const uint32_t lane_addr = ((uint32_t)(warp * 32) << 16);
+    constexpr int NB = 8;   // bias entries per thread and item (covers 16 key tiles = Tk <= 1024)
+    float bias_next[NB];
+    auto fetch_bias = [&](const AtItem& it, float(&dst)[NB]) {
+      const float* kb = p.key_bias ? p.key_bias + ((long long)it.g * p.H + it.h) * p.Tk : nullptr;
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int kk = threadIdx.x + i * 128;
+        const int key = it.jt0 * 64 + kk;
+        dst[i] = (kk < it.ntiles * 64 && key < it.klen) ? (kb ? __ldg(kb + key) * p.scale_log2 : 0.f) : -INFINITY;
+      }
+    };
+    AtCursor c;
+    at_cursor_init(p, c, n_items, nq);
+    if (c.valid) fetch_bias(c.it, bias_next);
+    // items without a visible key (ntiles == 0) never enter the rings: their output rows are zero
+    auto zero_items_before = [&](int k_from, int k_to) {
+      for (int k = k_from; k < k_to; ++k) {
+        const long long id = (long long)blockIdx.x + (long long)k * gridDim.x;
+        if (id >= n_items) break;
+        const AtItem z = at_item(p, (int)id, nq);
+        const int row = z.q0 + r;
+        if (row < p.Tq) {
+          bf16* orow = p.out + ((long long)z.g * p.Tq + row) * p.ldo + z.h * AT_DK;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) reinterpret_cast<uint4*>(orow)[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+    };
+    zero_items_before(0, c.valid ? c.k : 0x7fffffff);
+    while (c.valid) {
+      const AtItem it = c.it;
+      const int k_this = c.k;
+      float* bias = s_bias + (c.ne & 1) * bias_len;
+#pragma unroll
+      for (int i = 0; i < NB; ++i) {
+        const int kk = threadIdx.x + i * 128;
+        if (kk < it.ntiles * 64) bias[kk] = bias_next[i];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // the four softmax warps: bias row of this item is complete
+      // next non-empty item's bias row: in flight during this item
+      AtCursor nx = c;
+      nx.j = it.ntiles - 1;
+      at_cursor_next(p, nx, n_items, nq);
+      if (nx.valid) fetch_bias(nx.it, bias_next);
+      float m_run = -INFINITY, row_sum = 0.f;
+      auto vis_lo = [&](int i) { return (p.chunk > 0 && p.left >= 0) ? max(0, (i / p.chunk - p.left) * p.chunk) : 0; };
+      auto vis_hi = [&](int i) { return p.chunk > 0 ? min(it.klen, (i / p.chunk + 1) * p.chunk) : it.klen; };
+      uint32_t sv[64];
+#pragma unroll 1
+      for (int j = 0; j < it.ntiles; ++j) {
+        const int n = c.n + j, sb = n % ATP_NS;
+        mbar_wait(&s_full[sb], (n / ATP_NS) & 1);
+        tc_fence_after();
+        tmem_ld_32x32(s_col(sb) + lane_addr, sv);
+        tmem_ld_32x32(s_col(sb) + lane_addr + 32, sv + 32);
+        tmem_ld_wait();
+        const uint32_t bias_addr = smem_u32(bias + j * 64);
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+#pragma unroll
+        for (int e = 0; e < 64; e += 4) {
+          const float4 b4 = lds128(bias_addr + e * 4);
+          const float2 x01 = ffma2(make_float2(__uint_as_float(sv[e + 0]), __uint_as_float(sv[e + 1])), sc2,
+                                   make_float2(b4.x, b4.y));
+          const float2 x23 = ffma2(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), sc2,
+                                   make_float2(b4.z, b4.w));
+          sv[e + 0] = __float_as_uint(x01.x);
+          sv[e + 1] = __float_as_uint(x01.y);
+          sv[e + 2] = __float_as_uint(x23.x);
+          sv[e + 3] = __float_as_uint(x23.y);
+          mx[(e >> 2) & 3] = fmax3(mx[(e >> 2) & 3], x01.x, x01.y);
+          mx[((e >> 2) + 2) & 3] = fmax3(mx[((e >> 2) + 2) & 3], x23.x, x23.y);
+        }
+        float tmax = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+        if (p.chunk > 0) {   // boundary tiles of the causal / chunk mask (see attention_tc_kernel)
+          const int kbase = (it.jt0 + j) * 64;
+          const int i0 = it.q0 + warp * 32;
+          if (kbase < vis_lo(i0 + 31) || kbase + 64 > vis_hi(i0)) {
+            const int lo = vis_lo(it.q0 + r) - kbase, hi = vis_hi(it.q0 + r) - kbase;
+            tmax = -INFINITY;
+#pragma unroll
+            for (int e = 0; e < 64; ++e) {
+              const float x = (e >= lo && e < hi) ? __uint_as_float(sv[e]) : -INFINITY;
+              sv[e] = __float_as_uint(x);
+              tmax = fmaxf(tmax, x);
+            }
+          }
+        }
+        if (p.key_bits) {
+          const int kbase = (it.jt0 + j) * 64;
+          const uint32_t* mw =
+              p.key_bits + ((long long)it.g * p.Tq + min(it.q0 + r, p.Tq - 1)) * p.bits_ld + (kbase >> 5);
+          tmax = -INFINITY;
+#pragma unroll
+          for (int wi = 0; wi < 2; ++wi) {
+            const uint32_t word = __ldg(mw + wi);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              const float x = ((word >> e) & 1u) ? __uint_as_float(sv[wi * 32 + e]) : -INFINITY;
+              sv[wi * 32 + e] = __float_as_uint(x);
+              tmax = fmaxf(tmax, x);
+            }
+          }
+        }
+        if (j == 0) {
+          m_run = tmax;
+        } else {
+          const bool raise = tmax > m_run + 8.f;
+          if (__any_sync(0xffffffffu, raise)) {
+            // lazy rescale: PV(n - 1) must have retired before O is touched
+            mbar_wait(&s_empty[(n - 1) % ATP_NS], ((n - 1) / ATP_NS) & 1);
+            tc_fence_after();
+            const float m_new = raise ? tmax : m_run;
+            const float f = (m_new == -INFINITY) ? 1.f : fast_exp2(m_run - m_new);
+            m_run = m_new;
+            row_sum *= f;
+#pragma unroll 1
+            for (int cc = 0; cc < 64; cc += 32) {
+              uint32_t ov[32];
+              tmem_ld_32x32(tmem_o + lane_addr + cc, ov);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) ov[e] = __float_as_uint(__uint_as_float(ov[e]) * f);
+              tmem_st_32x32(tmem_o + lane_addr + cc, ov);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+          }
+        }
+        float2 sm01 = make_float2(0.f, 0.f), sm23 = make_float2(0.f, 0.f);
+        const float m_eff = (m_run == -INFINITY) ? 0.f : m_run;
+        const float2 one2 = make_float2(1.f, 1.f), negm2 = make_float2(-m_eff, -m_eff);
+#pragma unroll
+        for (int e = 0; e < 64; e += 4) {
+          const float2 d01 = ffma2(make_float2(__uint_as_float(sv[e + 0]), __uint_as_float(sv[e + 1])), one2, negm2);
+          const float2 d23 = ffma2(make_float2(__uint_as_float(sv[e + 2]), __uint_as_float(sv[e + 3])), one2, negm2);
+          float2 p01 = make_float2(fast_exp2(d01.x), fast_exp2(d01.y));
+          float2 p23 = make_float2(fast_exp2(d23.x), fast_exp2(d23.y));
+          // word i = keys (2i, 2i+1): overwrites consumed scores only
+          if (ATP_TRUNC) {
+            // P~ truncated to bf16 (byte permute), the row sum adds the same truncated values
+            const uint32_t b0 = __float_as_uint(p01.x) & 0xffff0000u, b1 = __float_as_uint(p01.y) & 0xffff0000u;
+            const uint32_t b2 = __float_as_uint(p23.x) & 0xffff0000u, b3 = __float_as_uint(p23.y) & 0xffff0000u;
+            sv[(e >> 1) + 0] = __byte_perm(b0, b1, 0x7632);
+            sv[(e >> 1) + 1] = __byte_perm(b2, b3, 0x7632);
+            p01 = make_float2(__uint_as_float(b0), __uint_as_float(b1));
+            p23 = make_float2(__uint_as_float(b2), __uint_as_float(b3));
+          } else {
+            // P~ rounded to nearest-even bf16 (one F2FP per pair), fp32 row sum of the unrounded values — measured 2.6 %
+            // faster than the truncation path (fewer ALU instructions; the softmax warps are latency / issue bound)
+            sv[(e >> 1) + 0] = pack_bf16x2(p01.x, p01.y);
+            sv[(e >> 1) + 1] = pack_bf16x2(p23.x, p23.y);
+          }
+          sm01 = ffma2(p01, one2, sm01);
+          sm23 = ffma2(p23, one2, sm23);
+        }
+        row_sum += (sm01.x + sm01.y) + (sm23.x + sm23.y);
+        tmem_st_32x32(s_col(sb) + lane_addr, sv);   // P~ row over the first 32 columns of its own S row
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[sb]);
+      }
+      // ---- epilogue of the item: O / row_sum -> bf16 -> global
+      mbar_wait(o_done, c.ne & 1);
+      tc_fence_after();
+      const int row = it.q0 + r;
+      const float inv = row_sum > 0.f ? 1.f / row_sum : 0.f;
+      bf16* orow = p.out + ((long long)it.g * p.Tq + row) * p.ldo + it.h * AT_DK;
+#pragma unroll 1
+      for (int cc = 0; cc < 64; cc += 32) {
+        uint32_t ov[32];
+        tmem_ld_32x32(tmem_o + lane_addr + cc, ov);
+        tmem_ld_wait();
+        if (row < p.Tq) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 u;
+            u.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
+            u.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
+            u.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
+            u.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
+            reinterpret_cast<uint4*>(orow + cc)[q] = u;
+          }
+        }
+      }
+      tc_fence_before();   // the O reads above are ordered before this warp's next p_full arrival (PV(0) of the next item)
+      // advance to the next non-empty item (tile counter moves by this item's tiles)
+      c.j = it.ntiles - 1;
+      c.n += it.ntiles - 1;
+      at_cursor_next(p, c, n_items, nq);
+      zero_items_before(k_this + 1, c.valid ? c.k : 0x7fffffff);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -772,6 +1205,30 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
     const char* e = getenv("RVB_ATTN_SW");
     sw_sel = (e && atoi(e) == 8) ? 8 : 4;  // measured: 4 warps 0.388 ms / encoder layer, 8 warps 0.403 ms
   }
+  static int persist_sel = -1;   // RVB_ATTN_PERSIST=0: one item per CTA (attention_tc_kernel), A/B
+  if (persist_sel < 0) {
+    const char* e = getenv("RVB_ATTN_PERSIST");
+    persist_sel = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  const bool plain_cfg = bn_sel == 64 && sw_sel == 4 && getenv("RVB_ATTN_POLY") == nullptr && getenv("RVB_ATTN_CW") == nullptr &&
+                         getenv("RVB_ATTN_PT") == nullptr;
+  if (persist_sel == 1 && plain_cfg && a.Tk <= 1024) {
+    int dev = 0, sms = 0;
+    RVB_CHECK_CUDA(cudaGetDevice(&dev));
+    RVB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int nq = (a.Tq + AT_BM - 1) / AT_BM;
+    const long long n_items = (long long)nq * a.H * a.groups;
+    RVB_REQUIRE(n_items < (1ll << 31), "attention_tc: too many work items");
+    const int bias_len = ((a.Tk + 63) / 64) * 64;
+    const size_t smem = ATP_SMEM_FIXED + (size_t)2 * bias_len * sizeof(float);
+    static DynSmemOptIn optin_p;
+    if (optin_p.ensure(attention_tcp_kernel, smem)) return -1;
+    const int ctas = (int)std::min<long long>(n_items, 2ll * sms);
+    attention_tcp_kernel<<<ctas, 160, smem, stream>>>(tmQ, tmK, tmV, p, (int)n_items, nq, bias_len);
+    RVB_COUNT_LAUNCH();
+    RVB_CHECK_LAUNCH();
+    return 0;
+  }
   if (bn_sel == 128) {
     const size_t smem = AtCfg<128>::SMEM_FIXED + (size_t)((a.Tk + 127) / 128) * 128 * sizeof(float);
     RVB_REQUIRE(smem <= 227 * 1024, "attention_tc: Tk=%d needs %zu B of shared memory", a.Tk, smem);
@@ -785,11 +1242,15 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
     if (poly_sel < 0) {
       const char* e = getenv("RVB_ATTN_POLY");
       poly_sel = e ? atoi(e) : 0;
-      if (poly_sel < 0 || (poly_sel > 2 && poly_sel < 8) || poly_sel > 17) poly_sel = 0;
+      if (poly_sel < 0 || (poly_sel > 3 && poly_sel < 8) || poly_sel > 17) poly_sel = 0;
     }
     static DynSmemOptIn optin[3];
     static DynSmemOptIn optin_abl[10];
-    if (poly_sel >= 8) {   // timing ablations, wrong results (see the kernel)
+    static DynSmemOptIn optin_rn;
+    if (poly_sel == 3) {   // P~ rounded by F2FP instead of truncated (A/B), P~ in tensor memory
+      if (optin_rn.ensure(attention_tc_kernel<64, 4, 3, false, true>, smem)) return -1;
+      attention_tc_kernel<64, 4, 3, false, true><<<grid, 160, smem, stream>>>(tmQ, tmK, tmV, p);
+    } else if (poly_sel >= 8) {   // timing ablations, wrong results (see the kernel)
 #define RVB_ABL(V)                                                                     \
   do {                                                                                 \
     if (optin_abl[V - 8].ensure(attention_tc_kernel<64, 4, V>, smem)) return -1;       \

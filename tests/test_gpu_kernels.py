@@ -233,6 +233,41 @@ def test_attention_tcgen05_relpos(lib, B, T, H):
     torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
 
 
+def test_attention_tcgen05_persistent_many_items_mixed_lengths(lib):
+    """More (query tile, head, group) items than CTAs, so every CTA of the persistent kernel walks several items, with key
+    lengths that give 0 (empty item -> zero rows), 1, 2 and 5 key tiles in mixed order: the rings (K'', V, S / P~, Q) and
+    barrier phases must stay consistent across item boundaries — also when an item is a single tile long."""
+    torch.manual_seed(77)
+    H, dk = 4, 64
+    d = H * dk
+    G, T = 60, 300                                     # 3 query tiles x 4 heads x 60 groups = 720 items > 2 x 148 CTAs
+    qkv = (torch.randn(G, T, 3 * d, device="cuda") * 0.7).bfloat16()
+    bias = torch.randn(G, H, T, device="cuda") * 0.5
+    lens = [300, 1, 64, 65, 0, 128, 17, 299, 63, 200]
+    klens = torch.tensor([lens[i % len(lens)] for i in range(G)], dtype=torch.int32, device="cuda")
+    out = torch.full((G, T, d), 7.0, device="cuda", dtype=torch.bfloat16)
+    scale = 1.0 / math.sqrt(dk)
+    _check(lib, lib.rvb_attention_tc(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d), _p(out),
+                                     3 * d, 3 * d, 3 * d, d, G, T, T, H, dk, _p(bias), _p(klens), 0, scale, _stream()))
+    torch.cuda.synchronize()
+    q = qkv[..., :d].float().view(G, T, H, dk).transpose(1, 2)
+    k = qkv[..., d:2 * d].float().view(G, T, H, dk).transpose(1, 2)
+    v = qkv[..., 2 * d:].float().view(G, T, H, dk).transpose(1, 2)
+    s = (q @ k.transpose(-1, -2) + bias[:, :, None, :]) * scale
+    mask = torch.arange(T, device="cuda")[None, :] >= klens[:, None]
+    s = s.masked_fill(mask[:, None, None, :], -float("inf"))
+    a = torch.nan_to_num(torch.softmax(s, -1), nan=0.0).masked_fill(mask[:, None, None, :], 0.0)
+    ref = (a @ v).transpose(1, 2).reshape(G, T, d)
+    torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
+    assert float(out[4].float().abs().max()) == 0.0      # klen 0: rows written as zeros
+    # the same launch is deterministic run to run (no dependence on which CTA picked which items)
+    out2 = torch.empty_like(out)
+    _check(lib, lib.rvb_attention_tc(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d), _p(out2),
+                                     3 * d, 3 * d, 3 * d, d, G, T, T, H, dk, _p(bias), _p(klens), 0, scale, _stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)
+
+
 def test_attention_tcgen05_grouped_cross(lib):
     """decoder source-attention form: groups of N*L query rows share one utterance's keys; no bias."""
     torch.manual_seed(11)
