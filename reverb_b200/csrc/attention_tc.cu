@@ -585,7 +585,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 }
 
 // =====================================================================================================================
-// PERSISTENT variant (default for the plain / causal / bit-mask cases): one CTA per SM slot (2 x #SMs CTAs) loops over
+// PERSISTENT variant (RVB_ATTN_PERSIST=1; measured slower, see launch_attention_tc): one CTA per SM slot (2 x #SMs CTAs) loops over
 // (query tile, head, group) items.  tools/attn_bench.py --sweep showed 22 % of the one-item-per-CTA kernel's time was
 // per-CTA fixed cost (launch, barrier init, TMEM allocation, first TMA round trip, key-bias fill, pipeline fill, drain).
 // Here TMEM and the barriers are set up once and ALL rings (K'', V, S / P~) keep running across item boundaries: four
@@ -1205,10 +1205,15 @@ int launch_attention_tc(const AttnTcArgs& a, cudaStream_t stream) {
     const char* e = getenv("RVB_ATTN_SW");
     sw_sel = (e && atoi(e) == 8) ? 8 : 4;  // measured: 4 warps 0.388 ms / encoder layer, 8 warps 0.403 ms
   }
-  static int persist_sel = -1;   // RVB_ATTN_PERSIST=0: one item per CTA (attention_tc_kernel), A/B
-  if (persist_sel < 0) {
-    const char* e = getenv("RVB_ATTN_PERSIST");
-    persist_sel = (e && atoi(e) == 0) ? 0 : 1;
+  // RVB_ATTN_PERSIST=1: the persistent kernel.  Correct (tests/test_gpu_kernels.py::...persistent_many_items...) but
+  // measured SLOWER than one item per CTA with P~ in tensor memory — 0.414 vs 0.330 ms per encoder layer, 0.029 vs
+  // 0.021 ms per key tile, the same 0.094 ms at one tile — so the per-item cost is the dependent chain Q -> S -> P~ -> O
+  // -> epilogue inside the softmax warps, not CTA launch / TMEM allocation / barrier setup, and the cursor bookkeeping
+  // lengthens the control thread's loop.  Default: off.
+  int persist_sel = 0;
+  {
+    const char* e = getenv("RVB_ATTN_PERSIST");   // read per call: the kernel test runs both variants in one process
+    persist_sel = (e && atoi(e) == 1) ? 1 : 0;
   }
   const bool plain_cfg = bn_sel == 64 && sw_sel == 4 && getenv("RVB_ATTN_POLY") == nullptr && getenv("RVB_ATTN_CW") == nullptr &&
                          getenv("RVB_ATTN_PT") == nullptr;

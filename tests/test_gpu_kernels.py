@@ -233,7 +233,8 @@ def test_attention_tcgen05_relpos(lib, B, T, H):
     torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
 
 
-def test_attention_tcgen05_persistent_many_items_mixed_lengths(lib):
+@pytest.mark.parametrize("persist", ["0", "1"])
+def test_attention_tcgen05_persistent_many_items_mixed_lengths(lib, persist):
     """More (query tile, head, group) items than CTAs, so every CTA of the persistent kernel walks several items, with key
     lengths that give 0 (empty item -> zero rows), 1, 2 and 5 key tiles in mixed order: the rings (K'', V, S / P~, Q) and
     barrier phases must stay consistent across item boundaries — also when an item is a single tile long."""
@@ -247,9 +248,20 @@ def test_attention_tcgen05_persistent_many_items_mixed_lengths(lib):
     klens = torch.tensor([lens[i % len(lens)] for i in range(G)], dtype=torch.int32, device="cuda")
     out = torch.full((G, T, d), 7.0, device="cuda", dtype=torch.bfloat16)
     scale = 1.0 / math.sqrt(dk)
-    _check(lib, lib.rvb_attention_tc(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d), _p(out),
-                                     3 * d, 3 * d, 3 * d, d, G, T, T, H, dk, _p(bias), _p(klens), 0, scale, _stream()))
-    torch.cuda.synchronize()
+    import os
+    os.environ["RVB_ATTN_PERSIST"] = persist            # "1": the persistent kernel (off by default: measured slower)
+    try:
+        _check(lib, lib.rvb_attention_tc(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d),
+                                         _p(out), 3 * d, 3 * d, 3 * d, d, G, T, T, H, dk, _p(bias), _p(klens), 0, scale,
+                                         _stream()))
+        torch.cuda.synchronize()
+        out2 = torch.empty_like(out)
+        _check(lib, lib.rvb_attention_tc(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d),
+                                         _p(out2), 3 * d, 3 * d, 3 * d, d, G, T, T, H, dk, _p(bias), _p(klens), 0, scale,
+                                         _stream()))
+        torch.cuda.synchronize()
+    finally:
+        del os.environ["RVB_ATTN_PERSIST"]
     q = qkv[..., :d].float().view(G, T, H, dk).transpose(1, 2)
     k = qkv[..., d:2 * d].float().view(G, T, H, dk).transpose(1, 2)
     v = qkv[..., 2 * d:].float().view(G, T, H, dk).transpose(1, 2)
@@ -261,10 +273,6 @@ def test_attention_tcgen05_persistent_many_items_mixed_lengths(lib):
     torch.testing.assert_close(out.float(), ref, rtol=3e-2, atol=3e-2)
     assert float(out[4].float().abs().max()) == 0.0      # klen 0: rows written as zeros
     # the same launch is deterministic run to run (no dependence on which CTA picked which items)
-    out2 = torch.empty_like(out)
-    _check(lib, lib.rvb_attention_tc(_p(qkv), C.c_void_p(qkv.data_ptr() + 2 * d), C.c_void_p(qkv.data_ptr() + 4 * d), _p(out2),
-                                     3 * d, 3 * d, 3 * d, d, G, T, T, H, dk, _p(bias), _p(klens), 0, scale, _stream()))
-    torch.cuda.synchronize()
     assert torch.equal(out, out2)
 
 
