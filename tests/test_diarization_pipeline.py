@@ -138,3 +138,24 @@ def test_pipeline_recovers_a_three_speaker_timeline_with_stub_networks():
     buf.seek(0)
     back = load_rttm(buf)["rec"]
     assert len(back) == len(turns) and all(abs(a.start - b.start) < 1e-3 for a, b in zip(back, turns))
+
+
+def test_cli_audio_reader_and_model_dir_errors(tmp_path):
+    """`infer.read_audio`: 16 kHz int16 stereo WAV -> mono float32 in [-1, 1] (pyannote's Audio(mono='downmix'));
+    `load_pipeline` without weights fails loudly instead of falling back to anything."""
+    import wave
+    import pytest
+    from reverb_b200.diarization import infer
+    path = tmp_path / "st.wav"
+    left = (np.sin(np.arange(16000) * 0.05) * 16000).astype(np.int16)
+    right = np.zeros(16000, np.int16)
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(2)
+        w.setsampwidth(2)
+        w.setframerate(16000)
+        w.writeframes(np.stack([left, right], axis=1).tobytes())
+    x = infer.read_audio(str(path))
+    assert x.dtype == np.float32 and x.shape == (16000,)
+    assert np.allclose(x, left.astype(np.float32) / 32768.0 / 2, atol=1e-6)
+    with pytest.raises(ValueError):
+        infer.load_pipeline(str(tmp_path / "missing_dir"))
