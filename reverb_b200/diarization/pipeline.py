@@ -85,7 +85,19 @@ def aggregate(scores: np.ndarray, chunks: SlidingWindow, frames: SlidingWindow, 
     return avg
 
 
-def agglomerative_clustering(embeddings: np.ndarray, threshold: float, min_cluster_size: int) -> np.ndarray:
+def condensed_euclidean(emb: np.ndarray, device: Optional[str] = None) -> np.ndarray:
+    """scipy `pdist(emb)` (float64, direct differences) computed with torch on `device`: for the ~8 000 embeddings of a
+    45-minute recording the pairwise distances are 70 % of the clustering time on the host and milliseconds on the GPU.
+    The linkage itself stays scipy's (same dendrogram: `linkage(y)` == `linkage(X)` for Euclidean input)."""
+    x = torch.from_numpy(np.ascontiguousarray(emb, dtype=np.float64)).to(device or "cpu")
+    n = x.shape[0]
+    d = torch.cdist(x, x, p=2.0, compute_mode="donot_use_mm_for_euclid_dist")
+    iu = torch.triu_indices(n, n, offset=1, device=d.device)
+    return d[iu[0], iu[1]].cpu().numpy()
+
+
+def agglomerative_clustering(embeddings: np.ndarray, threshold: float, min_cluster_size: int,
+                             device: Optional[str] = None) -> np.ndarray:
     """`AgglomerativeClustering.cluster` (method "centroid", metric "cosine"): unit-normalise, centroid linkage on
     Euclidean distances, cut at `threshold`, then merge every small cluster (< min_cluster_size members) into the large
     cluster with the nearest centroid (cosine) and renumber from 0."""
@@ -97,7 +109,10 @@ def agglomerative_clustering(embeddings: np.ndarray, threshold: float, min_clust
         return np.zeros((1,), np.int64)
     with np.errstate(divide="ignore", invalid="ignore"):
         emb = embeddings / np.linalg.norm(embeddings, axis=-1, keepdims=True)
-    dendrogram = linkage(emb, method="centroid", metric="euclidean")
+    if device is not None and n > 256:
+        dendrogram = linkage(condensed_euclidean(emb, device), method="centroid")
+    else:
+        dendrogram = linkage(emb, method="centroid", metric="euclidean")
     clusters = fcluster(dendrogram, threshold, criterion="distance") - 1
     unique, counts = np.unique(clusters, return_counts=True)
     large = unique[counts >= min_cluster_size]
@@ -253,7 +268,8 @@ class SpeakerDiarization:
             hard = np.zeros((num_chunks, S), np.int64)
             return hard, None
         train = embeddings[chunk_idx, speaker_idx].astype(np.float64)
-        train_clusters = agglomerative_clustering(train, self.threshold, self.min_cluster_size)
+        train_clusters = agglomerative_clustering(train, self.threshold, self.min_cluster_size,
+                                                  device=self.device if self.device != "cpu" else None)
         hard, soft, centroids = assign_embeddings(embeddings.astype(np.float64), (chunk_idx, speaker_idx), train_clusters)
         return hard, centroids
 

@@ -159,3 +159,17 @@ def test_cli_audio_reader_and_model_dir_errors(tmp_path):
     assert np.allclose(x, left.astype(np.float32) / 32768.0 / 2, atol=1e-6)
     with pytest.raises(ValueError):
         infer.load_pipeline(str(tmp_path / "missing_dir"))
+
+
+def test_gpu_pdist_route_gives_the_same_dendrogram_cut():
+    """`condensed_euclidean` (torch, run on the CPU here) == scipy `pdist`, and clustering through it equals the direct
+    scipy route."""
+    from scipy.spatial.distance import pdist
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(400, 32))
+    x[:, :4] += np.eye(3, 4)[rng.integers(0, 3, 400)] * 5
+    xn = x / np.linalg.norm(x, axis=1, keepdims=True)
+    assert np.allclose(P.condensed_euclidean(xn, "cpu"), pdist(xn), rtol=0, atol=1e-12)
+    a = P.agglomerative_clustering(x.copy(), 0.9, 12)
+    b = P.agglomerative_clustering(x.copy(), 0.9, 12, device="cpu")
+    assert np.array_equal(a, b) and len(set(a)) == 3
