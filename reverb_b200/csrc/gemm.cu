@@ -1130,13 +1130,32 @@ struct GemmProfRec {
 static bool g_prof_on = false;
 static std::vector<GemmProfRec> g_prof;
 static std::mutex g_prof_mutex;
+// Events are pooled per device and reused across profiling windows: creating two per launch inside the timed region cost
+// host time exactly where the step is host-sensitive (two ranks on one node: the device-resident run measured slower than
+// the end-to-end run that follows it without profiling).
+constexpr int kProfMaxDev = 64;
+static std::vector<cudaEvent_t> g_prof_pool[kProfMaxDev];
+static size_t g_prof_pool_used[kProfMaxDev];
+
+static int prof_event(cudaEvent_t* out) {
+  int dev = 0;
+  RVB_CHECK_CUDA(cudaGetDevice(&dev));
+  RVB_REQUIRE(dev >= 0 && dev < kProfMaxDev, "gemm profile: device index %d out of range", dev);
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
+  auto& pool = g_prof_pool[dev];
+  if (g_prof_pool_used[dev] == pool.size()) {
+    cudaEvent_t e;
+    RVB_CHECK_CUDA(cudaEventCreate(&e));
+    pool.push_back(e);
+  }
+  *out = pool[g_prof_pool_used[dev]++];
+  return 0;
+}
 
 void gemm_profile_begin() {
-  for (auto& r : g_prof) {
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
-  }
+  std::lock_guard<std::mutex> lock(g_prof_mutex);
   g_prof.clear();
+  for (int d = 0; d < kProfMaxDev; ++d) g_prof_pool_used[d] = 0;
   g_prof_on = true;
 }
 int gemm_profile_end(double* total_ms, double* total_flops, long long* launches) {
@@ -1148,8 +1167,6 @@ int gemm_profile_end(double* total_ms, double* total_flops, long long* launches)
     RVB_CHECK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
     ms += t;
     fl += r.flops;
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
   }
   if (total_ms) *total_ms = ms;
   if (total_flops) *total_flops = fl;
@@ -1202,8 +1219,7 @@ static int launch_tc(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
   GemmProfRec rec;
   if (g_prof_on) {
-    RVB_CHECK_CUDA(cudaEventCreate(&rec.a));
-    RVB_CHECK_CUDA(cudaEventCreate(&rec.b));
+    if (prof_event(&rec.a) || prof_event(&rec.b)) return -1;
     rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K * (a.x3 ? 3.0 : 1.0);
     RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }
@@ -1266,8 +1282,7 @@ static int launch_tc2(const GemmArgs& a, GemmKParams& p, cudaStream_t stream) {
   if (p.num_tiles < clusters) clusters = p.num_tiles;
   GemmProfRec rec;
   if (g_prof_on) {
-    RVB_CHECK_CUDA(cudaEventCreate(&rec.a));
-    RVB_CHECK_CUDA(cudaEventCreate(&rec.b));
+    if (prof_event(&rec.a) || prof_event(&rec.b)) return -1;
     rec.flops = 2.0 * (double)a.M * (double)a.N * (double)a.K * (a.x3 ? 3.0 : 1.0);
     RVB_CHECK_CUDA(cudaEventRecord(rec.a, stream));
   }

@@ -46,6 +46,118 @@ def prefix_beam_results(per_utt) -> List[DecodeResult]:
     return out
 
 
+def _log_add2(a: float, b: float) -> float:
+    """utils/common.py log_add([a, b]): max + log(sum(exp(x - max))) in double precision, -inf when both are."""
+    if a == -math.inf and b == -math.inf:
+        return -math.inf
+    m = a if a > b else b
+    return m + math.log(math.exp(a - m) + math.exp(b - m))
+
+
+class _Prefix:
+    """PrefixScore of the reference (search.py:60-104)."""
+    __slots__ = ("s", "ns", "v_s", "v_ns", "cur_token_prob", "times_s", "times_ns", "context_state", "context_score",
+                 "has_context")
+
+    def __init__(self, s=-math.inf, ns=-math.inf, v_s=-math.inf, v_ns=-math.inf, context_state=None, context_score=0.0):
+        self.s, self.ns, self.v_s, self.v_ns = s, ns, v_s, v_ns
+        self.cur_token_prob = -math.inf
+        self.times_s: List[int] = []
+        self.times_ns: List[int] = []
+        self.context_state = context_state
+        self.context_score = context_score
+        self.has_context = False
+
+    def score(self) -> float:
+        return _log_add2(self.s, self.ns)
+
+    def viterbi(self) -> float:
+        return self.v_s if self.v_s > self.v_ns else self.v_ns
+
+    def times(self) -> List[int]:
+        return self.times_s if self.v_s > self.v_ns else self.times_ns
+
+    def total(self) -> float:
+        return self.score() + self.context_score
+
+
+def ctc_prefix_beam_search_biased(topk_val: np.ndarray, topk_idx: np.ndarray, lens: Sequence[int], beam_size: int,
+                                  context_graph, blank_id: int = 0) -> List[DecodeResult]:
+    """CTC prefix beam search WITH a context graph (search.py:124-248, the `context_graph is not None` branches), on the
+    host over the per-frame top-`beam_size` log-probabilities the GPU CTC head produced — the biasing state machine is a
+    pointer-chasing automaton per prefix, and the reference itself only reaches this path through
+    `ASRModel.decode(context_graph=...)`, never from the reverb CLI.  topk_val / topk_idx: (B, T', beam) in `torch.topk`
+    order.  Reference behaviours kept: ranking by score + context score; the `u == last` repeat branch never updates
+    `v_ns` (the `vs_ns` typo, :177); after the last frame `finalize` REPLACES each hypothesis' context score by minus the
+    bonus of its unfinished match (:228-233) and the list is not re-sorted."""
+    out: List[DecodeResult] = []
+    for b in range(topk_val.shape[0]):
+        cur = [((), _Prefix(s=0.0, ns=-math.inf, v_s=0.0, v_ns=0.0, context_state=context_graph.root, context_score=0.0))]
+        for t in range(int(lens[b])):
+            nxt: dict = {}
+
+            def slot(key):
+                ps = nxt.get(key)
+                if ps is None:
+                    ps = nxt[key] = _Prefix()
+                return ps
+
+            for j in range(beam_size):
+                u = int(topk_idx[b, t, j])
+                prob = float(topk_val[b, t, j])
+                for prefix, ps in cur:
+                    last = prefix[-1] if prefix else None
+                    if u == blank_id:
+                        n = slot(prefix)
+                        n.s = _log_add2(n.s, ps.score() + prob)
+                        n.v_s = ps.viterbi() + prob
+                        n.times_s = list(ps.times())
+                        if not n.has_context:
+                            n.context_score, n.context_state, n.has_context = ps.context_score, ps.context_state, True
+                    elif u == last:
+                        n1 = slot(prefix)
+                        n1.ns = _log_add2(n1.ns, ps.ns + prob)
+                        if n1.v_ns < ps.v_ns + prob:
+                            # the reference assigns to a misspelt attribute here: v_ns itself stays as it was
+                            if n1.cur_token_prob < prob:
+                                n1.cur_token_prob = prob
+                                n1.times_ns = list(ps.times_ns)
+                                n1.times_ns[-1] = t
+                        if not n1.has_context:
+                            n1.context_score, n1.context_state, n1.has_context = ps.context_score, ps.context_state, True
+                        n2 = slot(prefix + (u,))
+                        n2.ns = _log_add2(n2.ns, ps.s + prob)
+                        if n2.v_ns < ps.v_s + prob:
+                            n2.v_ns = ps.v_s + prob
+                            n2.cur_token_prob = prob
+                            n2.times_ns = list(ps.times_s)
+                            n2.times_ns.append(t)
+                        if not n2.has_context:
+                            sc, st = context_graph.forward_one_step(ps.context_state, u)
+                            n2.context_score, n2.context_state, n2.has_context = ps.context_score + sc, st, True
+                    else:
+                        n = slot(prefix + (u,))
+                        n.ns = _log_add2(n.ns, ps.score() + prob)
+                        if n.v_ns < ps.viterbi() + prob:
+                            n.v_ns = ps.viterbi() + prob
+                            n.cur_token_prob = prob
+                            n.times_ns = list(ps.times())
+                            n.times_ns.append(t)
+                        if not n.has_context:
+                            sc, st = context_graph.forward_one_step(ps.context_state, u)
+                            n.context_score, n.context_state, n.has_context = ps.context_score + sc, st, True
+            # sorted() is stable: equal totals keep dict insertion order, like the reference
+            cur = sorted(nxt.items(), key=lambda kv: kv[1].total(), reverse=True)[:beam_size]
+        for _, ps in cur:
+            ps.context_score, ps.context_state = context_graph.finalize(ps.context_state)
+        nbest = [k for k, _ in cur]
+        scores = [ps.total() for _, ps in cur]
+        times = [ps.times() for _, ps in cur]
+        out.append(DecodeResult(tokens=nbest[0], score=scores[0], times=times[0], nbest=nbest, nbest_scores=scores,
+                                nbest_times=times))
+    return out
+
+
 def rescoring_pick(hyps: Sequence[tuple], ctc_scores: Sequence[float], nbest_times, l2r: np.ndarray,
                    r2l: Optional[np.ndarray], ctc_weight: float, reverse_weight: float) -> DecodeResult:
     """Combine decoder and CTC scores and keep the first strict maximum (search.py:413-447).

@@ -438,3 +438,37 @@ def test_compute_feats_resamples_non_16k_audio_on_the_gpu(asr, model_dirs, tmp_p
 def test_launch_counter_and_no_cpu_path():
     from reverb_b200.engine import launch_count
     assert launch_count() > 0
+
+
+@pytest.mark.parametrize("case", ["causal_ln", "sym_bn"])
+def test_decode_with_context_graph(asr, golden_cases, case):
+    """`ASRModel.decode(context_graph=...)`: the biased prefix search (host, bit-exact vs the live reference on recorded
+    log-probs: tests/test_context_biasing.py) runs on the GPU's top-k and feeds the rescoring decoder; a graph over a
+    span of the unbiased best hypothesis must raise that hypothesis' prefix score by the phrase bonus."""
+    from reverb_b200.context_graph import ContextGraph
+    from reverb_b200.search import ctc_prefix_beam_search_biased
+    meta, arr = golden_cases[case]
+    m = asr[case]
+    cat = torch.tensor([meta["verbatimicity"], 1.0 - meta["verbatimicity"]])
+    ref_feats = torch.from_numpy(arr["feats"]).unsqueeze(0).cuda()
+    fb, fl = next(iter(m.feats_batcher(ref_feats, meta["chunk_size"], meta["batch_size"])))
+    beam = meta["beam_size"]
+    modes = ["ctc_prefix_beam_search", "attention_rescoring"]
+    plain = m.model.decode(modes, fb, fl, beam, ctc_weight=0.5, cat_embs=cat)
+    best = list(plain["ctc_prefix_beam_search"][0].tokens)
+    assert len(best) >= 4
+    phrase = best[1:4]
+    graph = ContextGraph(token_lists=[phrase], context_score=3.0)
+    biased = m.model.decode(modes, fb, fl, beam, ctc_weight=0.5, cat_embs=cat, context_graph=graph)
+    b0, p0 = biased["ctc_prefix_beam_search"][0], plain["ctc_prefix_beam_search"][0]
+    assert list(b0.tokens) == best                                  # the boosted hypothesis stays on top
+    assert abs((b0.score - p0.score) - 3 * 3.0) < 1e-6              # a complete 3-token match: + 3 x context_score
+    # equals the host search run directly on the GPU's top-k
+    enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
+    val, idx, _ = m.model.engine.ctc_topk(enc, beam)
+    want = ctc_prefix_beam_search_biased(val.cpu().numpy(), idx.cpu().numpy(), enc_lens, beam, graph, 0)
+    for r, w in zip(biased["ctc_prefix_beam_search"], want):
+        assert [list(h) for h in r.nbest] == [list(h) for h in w.nbest] and r.nbest_scores == w.nbest_scores
+    # rescoring consumed the biased n-best
+    for r, pr in zip(biased["attention_rescoring"], biased["ctc_prefix_beam_search"]):
+        assert tuple(r.tokens) in [tuple(h) for h in pr.nbest]
