@@ -122,6 +122,50 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class NvmlClockSampler:
+    """Same record through NVML in-process (nvidia_ml_py): two light queries per sample instead of an nvidia-smi
+    subprocess polling nine fields.  RVB_BENCH_CLOCKS=nvml selects it."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+
+    def __init__(self, gpu_index: int, period: float = 0.2):
+        self.gpu, self.period = gpu_index, period
+        self.ok = False
+        self.sm, self.bits = [], 0
+        self.stop_flag = threading.Event()
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(visible.split(",")[self.gpu]) if visible and visible.split(",")[self.gpu].isdigit() else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.bits |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            self.stop_flag.wait(self.period)
+
+    def stop(self):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+        self.stop_flag.set()
+        self.t.join(timeout=1.0)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.smax,
+                "reasons": sorted(n for b, n in self.REASONS if self.bits & b), "samples": len(self.sm), "via": "nvml"}
+
+
 def host_threads() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -422,8 +466,9 @@ def main():
         tick("pack records", lambda: rdist.pack_results(hy, args.chunks, max_tok), acc)
         tick("whole step, not pipelined", lambda: model.decode([args.mode], eng.fbank_batch(pcm_dev), lens, 10, **dkw), acc)
         print("BREAKDOWN " + json.dumps({k: round(v, 2) for k, v in acc}), file=sys.stderr)
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
+    clocks = NvmlClockSampler(local_rank) if os.environ.get("RVB_BENCH_CLOCKS") == "nvml" else ClockSampler(local_rank)
+    sample_clocks = rank == 0 and os.environ.get("RVB_BENCH_NO_CLOCKS") != "1"   # A/B switch: is the sampler itself felt?
+    if sample_clocks:
         clocks.start()
     l0 = launch_count()
     # one untimed step with the per-launch GEMM timing on: fills the library's event pool, so the timed region below does
@@ -436,7 +481,7 @@ def main():
     gms, gfl, gn = C.c_double(), C.c_double(), C.c_longlong()
     lib.rvb_gemm_profile_end(C.byref(gms), C.byref(gfl), C.byref(gn))
     launches = launch_count() - l0
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if sample_clocks else ({"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled"]} if rank == 0 else None)
     audio_s = args.chunks * 30.0 * args.steps * world
     value = audio_s / (ms / 1e3)
     # the gathered records of the last step must hold every rank's chunks, this rank's block at its place
