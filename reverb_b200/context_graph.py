@@ -1,150 +1,136 @@
-"""Context biasing graph for CTC prefix beam search (host side).
+"""Context biasing graph for CTC prefix beam search (host side), compiled to flat arrays.
 
-Restates `asr/wenet/utils/context_graph.py` of the reference (ContextGraph :104-265, tokenize :24-58): an Aho-Corasick
-automaton over the token sequences of the biasing phrases — a trie whose nodes carry the accumulated bonus
-(`node_score` = depth * context_score), a fail arc and an output arc — queried one token at a time by the search
-(`forward_one_step`) and closed with `finalize`.  Scores and tie-breaking follow the reference exactly, including its
-quirks: the fail-arc walk stops at the root without retrying from it (:168-176, :217-225), and a fail transition earns
-`node.node_score - state.node_score` plus the output score of the node reached.
+Behaviour = `asr/wenet/utils/context_graph.py` of the reference (ContextGraph :104-265, tokenize :24-58): an
+Aho-Corasick automaton over the token sequences of the biasing phrases.  Every node carries the bonus accumulated from
+the root (`depth * context_score`), a fail link and the summed bonus of the phrases that END at it or at a node on its
+output chain; the search feeds it one token at a time (`forward_one_step`) and closes a hypothesis with `finalize`.
+The reference's observable quirks are kept: when a token does not extend the current node, the fail walk stops at the
+root WITHOUT retrying the root's own children unless the loop lands there (:217-225, same in the construction :168-176);
+a phrase that ends on an already existing node does not mark it as a phrase end (:150-161).
 
-Used by `reverb_b200.search.ctc_prefix_beam_search_biased` through `ASRModel.decode(context_graph=...)` — the
-`context_graph` argument of the reference's `ASRModel.decode` (asr_model.py:331-350).  The reverb CLI itself never
-builds one (cli/reverb.py:227 passes `context_graph=None`).
+Representation: states are plain integers (0 = root) indexing parallel lists — `children[s]` (token -> state),
+`fail[s]`, `bonus[s]`, `emit[s]` — instead of linked node objects; `ASRModel.decode(context_graph=...)` and
+`reverb_b200.search.ctc_prefix_beam_search_biased` only use `root`, `forward_one_step` and `finalize`, so the
+reference's own `ContextGraph` object can be passed as well.  The reverb CLI never builds a graph (cli/reverb.py:227).
 """
 from __future__ import annotations
 
 import re
-from collections import deque
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
-
-_CJK = re.compile(r"([\u4e00-\u9fff])")
+_CJK = re.compile(r"([一-鿿])")
 
 
 def tokenize(context_list_path: str, symbol_table: Dict[str, int], bpe_model: Optional[str] = None) -> List[List[int]]:
-    """One biasing phrase per line -> token ids: sentencepiece pieces when a BPE model is given, otherwise characters
-    (space -> '▁'); unknown symbols map to <unk> when the table has one, else they are dropped
-    (context_graph.py:24-58)."""
-    sp = None
+    """One biasing phrase per line -> token ids.  With a sentencepiece model: upper-cased text, CJK characters on their
+    own, everything else through `encode_as_pieces` (text/tokenize_utils.py:19-60); without: one symbol per character,
+    space written as the word-boundary mark.  Symbols missing from the table become <unk> if the table has it and are
+    dropped otherwise."""
+    encode = None
     if bpe_model is not None:
         import sentencepiece as spm
         sp = spm.SentencePieceProcessor()
         sp.load(bpe_model)
-    out: List[List[int]] = []
+
+        def encode(text: str) -> List[str]:
+            pieces: List[str] = []
+            for part in _CJK.split(text.upper()):
+                if part.strip():
+                    pieces.extend([part] if _CJK.fullmatch(part) else sp.encode_as_pieces(part))
+            return pieces
+    unk = symbol_table.get("<unk>")
+    phrases: List[List[int]] = []
     with open(context_list_path, "r") as f:
         for line in f:
             text = line.strip()
-            if sp is not None:
-                # text/tokenize_utils.py:19-20, 28-60: upper-case, CJK characters stand alone, the rest goes through the
-                # sentencepiece model
-                pieces = []
-                for part in _CJK.split(text.upper()):
-                    if not part.strip():
-                        continue
-                    if _CJK.fullmatch(part):
-                        pieces.append(part)
-                    else:
-                        pieces.extend(sp.encode_as_pieces(part))
-            else:
-                pieces = ["▁" if ch == " " else ch for ch in text]
-            ids = []
-            for piece in pieces:
-                if piece in symbol_table:
-                    ids.append(symbol_table[piece])
-                elif "<unk>" in symbol_table:
-                    ids.append(symbol_table["<unk>"])
-            out.append(ids)
-    return out
-
-
-class ContextState:
-    """A trie node.  `token` of the root is -1."""
-    __slots__ = ("id", "token", "token_score", "node_score", "output_score", "is_end", "next", "fail", "output")
-
-    def __init__(self, id: int, token: int, token_score: float, node_score: float, output_score: float, is_end: bool):
-        self.id = id
-        self.token = token
-        self.token_score = token_score
-        self.node_score = node_score
-        self.output_score = output_score
-        self.is_end = is_end
-        self.next: Dict[int, "ContextState"] = {}
-        self.fail: Optional["ContextState"] = None
-        self.output: Optional["ContextState"] = None
+            symbols = encode(text) if encode else [("▁" if ch == " " else ch) for ch in text]
+            ids = [symbol_table.get(sym, unk) for sym in symbols]
+            phrases.append([i for i in ids if i is not None])
+    return phrases
 
 
 class ContextGraph:
+    root = 0
+
     def __init__(self, context_list_path: Optional[str] = None, symbol_table: Optional[Dict[str, int]] = None,
                  bpe_model: Optional[str] = None, context_score: float = 6.0,
                  token_lists: Optional[Iterable[Sequence[int]]] = None):
-        """Same positional arguments as the reference (`context_list_path, symbol_table, bpe_model, context_score`);
+        """Positional arguments as in the reference (`context_list_path, symbol_table, bpe_model, context_score`);
         `token_lists` builds the graph from token ids directly."""
         self.context_score = context_score
-        if token_lists is not None:
-            self.context_list = [list(t) for t in token_lists]
-        else:
-            self.context_list = tokenize(context_list_path, symbol_table or {}, bpe_model)
-        self.num_nodes = 0
-        self.root = ContextState(0, -1, 0, 0, 0, False)
-        self.root.fail = self.root
-        self._build(self.context_list)
+        self.context_list = ([list(t) for t in token_lists] if token_lists is not None
+                             else tokenize(context_list_path, symbol_table or {}, bpe_model))
+        self.children: List[Dict[int, int]] = [{}]
+        self.token: List[int] = [-1]
+        self.bonus: List[float] = [0.0]       # accumulated bonus root -> node ("node_score")
+        self.emit: List[float] = [0.0]        # bonus of the phrases recognised on arrival ("output_score")
+        self.ends: List[bool] = [False]
+        self.fail: List[int] = [0]
+        self._insert_phrases()
+        self._link()
 
-    def _build(self, token_lists: List[List[int]]) -> None:
-        for tokens in token_lists:
-            node = self.root
-            for i, tok in enumerate(tokens):
-                nxt = node.next.get(tok)
+    @property
+    def num_nodes(self) -> int:
+        return len(self.token) - 1
+
+    def _insert_phrases(self) -> None:
+        for phrase in self.context_list:
+            s = 0
+            for pos, tok in enumerate(phrase):
+                nxt = self.children[s].get(tok)
                 if nxt is None:
-                    self.num_nodes += 1
-                    end = i == len(tokens) - 1
-                    score = node.node_score + self.context_score
-                    nxt = ContextState(self.num_nodes, tok, self.context_score, score, score if end else 0, end)
-                    node.next[tok] = nxt
-                node = nxt           # NB (reference :150-161): a phrase that ends on an existing inner node does not mark it
-        # fail / output arcs, breadth first
-        queue = deque()
-        for node in self.root.next.values():
-            node.fail = self.root
-            queue.append(node)
-        while queue:
-            cur = queue.popleft()
-            for tok, node in cur.next.items():
-                fail = cur.fail
-                if tok in fail.next:
-                    fail = fail.next[tok]
-                else:
-                    fail = fail.fail
-                    while tok not in fail.next:
-                        fail = fail.fail
-                        if fail.token == -1:
-                            break
-                    if tok in fail.next:
-                        fail = fail.next[tok]
-                node.fail = fail
-                out = node.fail
-                while not out.is_end:
-                    out = out.fail
-                    if out.token == -1:
-                        out = None
+                    nxt = len(self.token)
+                    last = pos == len(phrase) - 1
+                    depth_bonus = self.bonus[s] + self.context_score
+                    self.children[s][tok] = nxt
+                    self.children.append({})
+                    self.token.append(tok)
+                    self.bonus.append(depth_bonus)
+                    self.emit.append(depth_bonus if last else 0)
+                    self.ends.append(last)
+                    self.fail.append(0)
+                s = nxt
+
+    def _fallback(self, start: int, tok: int) -> int:
+        """Walk fail links from `start` until a node with a `tok` child is found or the root is reached; take that child
+        if there is one.  (The root's children are only consulted when the walk ends on the root.)"""
+        s = start
+        while tok not in self.children[s]:
+            s = self.fail[s]
+            if s == 0:
+                break
+        return self.children[s].get(tok, s)
+
+    def _link(self) -> None:
+        order = list(self.children[0].values())          # breadth first; depth-1 nodes fail to the root
+        head = 0
+        while head < len(order):
+            parent = order[head]
+            head += 1
+            for tok, node in self.children[parent].items():
+                f = self.fail[parent]
+                self.fail[node] = self.children[f][tok] if tok in self.children[f] else self._fallback(self.fail[f], tok)
+                # nearest phrase end on the fail chain contributes its (already complete) output bonus
+                out = self.fail[node]
+                while not self.ends[out]:
+                    out = self.fail[out]
+                    if out == 0:
+                        out = -1
                         break
-                node.output = out
-                node.output_score += 0 if out is None else out.output_score
-                queue.append(node)
+                if out >= 0:
+                    self.emit[node] += self.emit[out]
+                order.append(node)
 
-    def forward_one_step(self, state: ContextState, token: int) -> Tuple[float, ContextState]:
-        if token in state.next:
-            node = state.next[token]
-            score = node.token_score
+    # -- queries ------------------------------------------------------------------------------------------------------
+    def forward_one_step(self, state: int, token: int) -> Tuple[float, int]:
+        nxt = self.children[state].get(token)
+        if nxt is not None:
+            gained = self.context_score
         else:
-            node = state.fail
-            while token not in node.next:
-                node = node.fail
-                if node.token == -1:
-                    break
-            if token in node.next:
-                node = node.next[token]
-            score = node.node_score - state.node_score
-        return score + node.output_score, node
+            nxt = self._fallback(self.fail[state], token)
+            gained = self.bonus[nxt] - self.bonus[state]
+        return gained + self.emit[nxt], nxt
 
-    def finalize(self, state: ContextState) -> Tuple[float, ContextState]:
-        return -state.node_score, self.root
+    def finalize(self, state: int) -> Tuple[float, int]:
+        """Take back the bonus of a match that did not complete; the next state is the root."""
+        return -self.bonus[state], 0

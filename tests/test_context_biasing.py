@@ -30,7 +30,7 @@ def test_context_graph_automaton_traces_equal_the_reference(golden, case):
         st = graph.root
         for tok, (score, node_id) in zip(tr["stream"], tr["steps"]):
             sc, st = graph.forward_one_step(st, tok)
-            assert sc == score and st.id == node_id
+            assert sc == score and st == node_id
         assert graph.finalize(st)[0] == tr["finalize"]
 
 
@@ -62,4 +62,4 @@ def test_tokenize_characters_and_unknowns(tmp_path):
     assert tokenize(str(p), table) == [[2, 3, 4, 2], [3]]
     g = ContextGraph(str(p), table, None, 2.0)
     sc, st = g.forward_one_step(g.root, 2)
-    assert sc == 2.0 and st.node_score == 2.0
+    assert sc == 2.0 and g.bonus[st] == 2.0
