@@ -173,3 +173,36 @@ def test_gpu_pdist_route_gives_the_same_dendrogram_cut():
     a = P.agglomerative_clustering(x.copy(), 0.9, 12)
     b = P.agglomerative_clustering(x.copy(), 0.9, 12, device="cpu")
     assert np.array_equal(a, b) and len(set(a)) == 3
+
+
+def test_windows_follow_inference_slide():
+    """10 s windows every 1 s; a trailing partial window is zero-padded (`Inference.slide`)."""
+    pipe = P.SpeakerDiarization(None, None, device="cpu")
+    w = pipe.windows(torch.arange(16000 * 12, dtype=torch.float32))          # 12 s -> windows at 0, 1, 2 s
+    assert w.shape == (3, 160000) and float(w[2, 0]) == 32000.0
+    w = pipe.windows(torch.ones(16000 * 12 + 8000))                         # + 0.5 s -> a padded 4th window
+    assert w.shape == (4, 160000) and float(w[3, -1]) == 0.0 and float(w[3, 0]) == 1.0
+    w = pipe.windows(torch.ones(5 * 16000))                                 # shorter than one window: one padded window
+    assert w.shape == (1, 160000) and float(w[0, 5 * 16000 - 1]) == 1.0 and float(w[0, 5 * 16000]) == 0.0
+
+
+def test_embedding_masks_exclude_overlap_unless_too_short():
+    """`get_embeddings`: frames where two local speakers are active are dropped from a speaker's pooling mask, unless
+    that leaves no more than `min_num_frames` clean frames — then the full mask is used."""
+    seen = {}
+
+    def emb(chunks, weights):
+        seen["w"] = weights.clone()
+        return torch.zeros(weights.shape[0], weights.shape[1], 4)
+
+    pipe = P.SpeakerDiarization(None, emb, device="cpu")
+    b = np.zeros((1, 589, 3), np.float32)
+    b[0, 0:300, 0] = 1          # speaker 0: 300 frames, 100 of them overlapped by speaker 1
+    b[0, 200:300, 1] = 1        # speaker 1: ONLY overlapped frames -> no clean frame -> falls back to its full mask
+    b[0, 400:500, 2] = 1        # speaker 2: clean
+    pipe.get_embeddings(torch.zeros(1, 160000), b)
+    w = seen["w"][0].numpy()
+    assert w.shape == (3, 589)
+    assert w[0].sum() == 200 and w[0, 200:300].sum() == 0
+    assert w[1].sum() == 100 and w[1, 200:300].sum() == 100
+    assert w[2].sum() == 100
