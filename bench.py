@@ -298,8 +298,8 @@ def main():
     real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="rvb", choices=["rvb", "reference"])
     ap.add_argument("--chunks", type=int, default=64, help="30 s chunks per GPU per step")
     ap.add_argument("--shape", default="bench", choices=["bench", "test"])
