@@ -55,3 +55,24 @@ def test_product_never_imports_the_oracle():
             if fn.endswith(".py"):
                 src = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), fn
+
+
+def test_ctypes_struct_mirrors_match_the_c_headers(tmp_path):
+    """sizeof of every config struct as gcc sees it in include/*.h == ctypes.sizeof of its mirror in reverb_b200/_lib.py
+    (the headers are plain C: they must compile with a C compiler, without CUDA)."""
+    import shutil
+    import subprocess
+    from reverb_b200 import _lib
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "rvb_diar.h"\nint main(void) {\n'
+                   '  printf("%zu %zu %zu\\n", sizeof(rvb_model_config), sizeof(rvb_seg_config), sizeof(rvb_emb_config));\n'
+                   '  return 0;\n}\n')
+    exe = tmp_path / "sz"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)],
+                   check=True)
+    sizes = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert sizes == [ctypes.sizeof(_lib.ModelConfig), ctypes.sizeof(_lib.SegConfig), ctypes.sizeof(_lib.EmbConfig)]
